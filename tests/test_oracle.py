@@ -1,0 +1,95 @@
+"""Oracle vs the golden fixtures minted from the real reference class (CPU only).
+
+Tolerances: the two oracle implementations and the reference differ only in fp32
+summation order, so accumulated probabilities must agree to 2e-5 abs and labels must be
+identical wherever the reference's own top-1/top-2 margin is >= 1e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_case_names, load_case
+from oracle import OracleWeights, TransducerPort, forward_chunk, predict_port, predict_windows, chunk_starts
+from oracle.explicit import top2_margin
+
+MARGIN = 1e-5
+PROB_TOL = 2e-5
+
+
+def assert_labels_match(ref_prob, ref_label, got_label, what):
+    diff = ref_label != got_label
+    if diff.any():
+        margins = top2_margin(ref_prob)[diff]
+        assert (margins < MARGIN).all(), f"{what}: {int(diff.sum())} flips, worst margin {margins.max():.3e}"
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_explicit_oracle_matches_reference(name):
+    case, state = load_case(name)
+    if case["images"].shape[0] > 8:            # keep the CPU suite short: subsample big batches
+        sel = slice(0, 8)
+    else:
+        sel = slice(None)
+    out = predict_windows(OracleWeights.from_state_dict(state, np.float32), case["images"][sel])
+    for head in ("base", "rle"):
+        ref_prob = case[f"f32_{head}_prob"][sel]
+        assert np.abs(out[f"{head}_prob"] - ref_prob).max() <= PROB_TOL
+        assert_labels_match(ref_prob, case[f"f32_{head}_label"][sel], out[f"{head}_label"], f"{name}/{head}")
+    assert np.abs(out["hidden"] - case["f32_hidden"][sel]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["F90_B2_T150_uniform", "F10_B3_T1000_pileup"])
+def test_explicit_oracle_fp64_matches_reference_fp64(name):
+    case, state = load_case(name)
+    out = predict_windows(OracleWeights.from_state_dict(state, np.float64), case["images"])
+    for head in ("base", "rle"):
+        assert np.abs(out[f"{head}_prob"] - case[f"f64_{head}_prob"]).max() <= 1e-9
+        assert (out[f"{head}_label"] == case[f"f64_{head}_label"]).all()
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_torch_port_matches_reference(name):
+    case, state = load_case(name)
+    model = TransducerPort(case["images"].shape[2]).eval()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+    torch.set_num_threads(1)
+    out = predict_port(model, torch.from_numpy(case["images"]))
+    for head in ("base", "rle"):
+        # same library calls as the reference on the same torch build: expect bit identity
+        assert np.array_equal(out[f"{head}_prob"], case[f"f32_{head}_prob"])
+        assert np.array_equal(out[f"{head}_label"], case[f"f32_{head}_label"])
+
+
+def test_forward_chunk_matches_reference_first_chunk():
+    case, state = load_case("cfg1_F10_B64_T100")
+    w = OracleWeights.from_state_dict(state)
+    x = case["images"][:8].astype(np.float32)
+    base, rle, hidden = forward_chunk(w, x, np.zeros((8, 2, 128), np.float32))
+    assert np.abs(base - case["f32_chunk0_base"][:8]).max() <= 1e-5
+    assert np.abs(rle - case["f32_chunk0_rle"][:8]).max() <= 1e-5
+    assert np.abs(hidden - case["f32_chunk0_hidden"][:8]).max() <= 1e-5
+
+
+def test_module_prefix_is_stripped():
+    case, state = load_case("F90_B1_T100_pileup")
+    prefixed = {"module." + k: v for k, v in state.items()}
+    a = predict_windows(OracleWeights.from_state_dict(state), case["images"])
+    b = predict_windows(OracleWeights.from_state_dict(prefixed), case["images"])
+    assert np.array_equal(a["base_prob"], b["base_prob"])
+
+
+def test_chunk_starts():
+    assert chunk_starts(1000) == list(range(0, 901, 50)) and len(chunk_starts(1000)) == 19
+    assert chunk_starts(100) == [0]
+    assert chunk_starts(150) == [0, 50]
+    assert chunk_starts(99) == []
+    assert chunk_starts(149) == [0]
+
+
+def test_first_index_tie_break():
+    # all-zero heads => every class ties; torch.max / the oracle must return index 0
+    case, state = load_case("F90_B1_T100_pileup")
+    state = {k: (np.zeros_like(v) if k.startswith("dense") else v) for k, v in state.items()}
+    out = predict_windows(OracleWeights.from_state_dict(state), case["images"])
+    assert (out["base_label"] == 0).all() and (out["rle_label"] == 0).all()
+    assert np.allclose(out["base_prob"], 0.2) and np.allclose(out["rle_prob"], 1 / 11)
