@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- pileup windows/sec of the HELEN predict hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--features 10]
+                    [--engine default|tensor|fp32] [--impl native|reference] [--sweep]
+
+A *step* is one pass of the hot path over one batch of synthetic pileup windows
+(uint8 [B, T=1000, F]) per GPU: all 19 chunks -> 2 x uint8[B, 1000] labels.
+
+Printed JSON line (rank 0):
+  value   windows/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed per step
+  e2e     same metric through the host-buffer entry (WindowPredictor.predict_host ->
+          hb_predict_windows_host): pageable host images in, host labels out, copies in the timed region
+  roofline      algorithmic FLOP/window x windows per launch / kernel time, vs measured bf16 peak
+  cpu_baseline  the oracle's torch-CPU port of the reference predict loop on this box's host cores
+
+--impl reference times that CPU port alone (the reference itself is a Python package that
+cannot travel to the GPU box), same metric/config keys.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_COLUMNS = 1000
+WINDOW, JUMP, HIDDEN = 100, 50, 128
+L2_FLUSH_BYTES = 256 << 20
+
+
+def flop_per_window(features, seq=T_COLUMNS):
+    """Algorithmic FLOPs of one window: per chunk MACs = 76,800 F (enc ih)
+    + 9,830,400 (enc hh) + 19,660,800 (dec ih) + 9,830,400 (dec hh) + 409,600 (heads)."""
+    chunks = 0 if seq < WINDOW else (seq - WINDOW) // JUMP + 1
+    mac = 2 * WINDOW * 3 * HIDDEN * features + 2 * (2 * WINDOW * 3 * HIDDEN * HIDDEN) \
+        + 2 * WINDOW * 3 * HIDDEN * 2 * HIDDEN + WINDOW * 2 * HIDDEN * 16
+    return 2 * mac * chunks
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"burst": float(p["bf16_tflops"]), "sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def kernel_traffic_bytes(engine, batch, features):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        table = json.load(f)
+    return table.get(f"{engine}_B{batch}_F{features}")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def synthetic_images(batch, features, seed, seq=T_COLUMNS):
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (batch, seq, features), dtype=torch.uint8, generator=gen)
+
+
+def cpu_port_windows_per_s(features, sample_windows, min_seconds, threads, seq=T_COLUMNS, reps_cap=8):
+    """Times the oracle's torch-CPU port of the reference predict loop (the only place bench.py
+    executes oracle/ code)."""
+    import torch
+    from oracle import TransducerPort, predict_port, random_state_dict
+    torch.set_num_threads(threads)
+    model = TransducerPort(features).eval()
+    model.load_state_dict(random_state_dict(features, seed=0))
+    images = synthetic_images(sample_windows, features, seed=1, seq=seq)
+    predict_port(model, images[: max(1, sample_windows // 4)])          # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        predict_port(model, images)
+        done += sample_windows
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or done >= reps_cap * sample_windows:
+            break
+    return done / dt, done, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU arm alone.  Rank 0 only; other ranks exit quietly."""
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    from oracle import TransducerPort, predict_port, random_state_dict
+    model = TransducerPort(args.features).eval()
+    model.load_state_dict(random_state_dict(args.features, seed=0))
+    sample = args.reference_sample
+    images = synthetic_images(sample, args.features, seed=1)
+    for _ in range(args.warmup):
+        predict_port(model, images[: max(1, sample // 4)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        predict_port(model, images)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "pileup windows/sec (B=256, T=1000)", "value": value, "unit": "windows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_windows=sample),
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {sample} windows [T=1000, F={args.features}] per step, "
+                                   f"torch {torch.__version__} CPU fp32 nn.GRU port of the reference predict loop"},
+        "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sample_windows=None):
+    cfg = {"workload": f"1xB200 persistent bidir-GRU inference, B={args.batch}, T={T_COLUMNS}, F={args.features}, "
+                       f"hidden=128, fused base+RLE heads (BASELINE configs[1])",
+           "batch_per_gpu": args.batch, "seq_len": T_COLUMNS, "features": args.features,
+           "chunk_width": WINDOW, "chunk_jump": JUMP, "chunks_per_window": 19,
+           "sharding": f"windows x{args.gpus} ranks, no collective on the data path",
+           "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event brackets)"}
+    if sample_windows is not None:
+        cfg["cpu_sample_windows_per_step"] = sample_windows
+    return cfg
+
+
+def run_native(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from helen_b200 import build as hb_build
+    from helen_b200.predictor import WindowPredictor
+    from oracle import random_state_dict   # parameter generator only (shared with the CPU arm)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    if rank == 0:
+        hb_build.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pred = WindowPredictor(random_state_dict(args.features, seed=0), device=local_rank, engine=args.engine)
+    engine = pred.engine
+    host_images = synthetic_images(args.batch, args.features, seed=1000 + rank)
+    images = host_images.to(dev)
+    host_np = host_images.numpy()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def timed_steps(batch_images, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            pred.predict(batch_images)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        barrier()
+        if sampler:
+            sampler.start()
+        launches0 = pred.launch_count
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            pred.predict(batch_images)
+            ends[i].record()
+        barrier()
+        per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        return per_step, pred.launch_count - launches0
+
+    sampler = ClockSampler(local_rank)
+    pred.enable_kernel_timing(True)
+    pred.kernel_time_ms(reset=True)
+    per_step, launches = timed_steps(images, args.steps, args.warmup, sampler)
+    clocks = sampler.finish()
+    kernel_ms_total, kernel_calls = pred.kernel_time_ms(reset=True)
+    pred.enable_kernel_timing(False)
+    total_ms = max_over_ranks(sum(per_step))
+    value = world * args.batch * args.steps / (total_ms * 1e-3)
+
+    # end to end through the host-buffer entry: pageable numpy in, numpy labels out
+    for _ in range(max(1, args.warmup // 2)):
+        pred.predict_host(host_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pred.predict_host(host_np)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * args.batch * args.steps / e2e_s
+
+    sweep = None
+    if args.sweep and world == 1:
+        sweep = []
+        for b in (64, 128, 256, 512, 1024, 2048):
+            imgs = synthetic_images(b, args.features, seed=7).to(dev)
+            ps, _ = timed_steps(imgs, max(3, args.steps // 4), 2)
+            sweep.append({"batch": b, "windows_per_s": b * len(ps) / (sum(ps) * 1e-3), "ms_per_step": sum(ps) / len(ps)})
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    fpw = flop_per_window(args.features)
+    # the dominant kernel covers a whole batch per launch sequence; its device time comes from the
+    # library's own event bracket around that sequence on the launching stream
+    kernel_ms = kernel_ms_total / max(kernel_calls, 1) if kernel_calls else statistics.mean(per_step)
+    achieved_tf = args.batch * fpw / (kernel_ms * 1e-3) / 1e12
+    line = {
+        "metric": "pileup windows/sec (B=256, T=1000)", "value": value, "unit": "windows/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if engine == "fp32" else "f16x3-split operands, f32 accumulate/state",
+        "data": "synthetic", "engine": engine, "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(host_np.nbytes),
+                "d2h_bytes_per_step": int(2 * args.batch * T_COLUMNS)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["burst"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / peaks["burst"], "frac_of_sustained": achieved_tf / peaks["sustained"],
+                     "peak_source": peaks["source"] + " bf16 burst (MEASURED_PEAKS.json)" if peaks["source"] == "measured"
+                     else "fallback", "flop_per_window": fpw, "kernel_ms_per_launch": kernel_ms,
+                     "traffic": kernel_traffic_bytes(engine, args.batch, args.features),
+                     "hbm_algorithmic_gbs": args.batch * (T_COLUMNS * args.features + 2 * T_COLUMNS) / (kernel_ms * 1e-3) / 1e9},
+    }
+    if sweep:
+        line["batch_sweep"] = sweep
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, done, dt = cpu_port_windows_per_s(args.features, args.cpu_sample, args.cpu_seconds, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": threads, "kind": "port",
+                                "sample": f"{done} windows [T=1000, F={args.features}] in batches of {args.cpu_sample}, "
+                                          f"{dt:.1f} s, torch {torch.__version__} CPU fp32 nn.GRU port of predict.py:90-154"}
+    print(json.dumps(line), flush=True)
+    pred.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="windows per GPU per step")
+    ap.add_argument("--features", type=int, default=10)
+    ap.add_argument("--engine", default="default", choices=["default", "tensor", "fp32"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--sweep", action="store_true", help="also report the batch sweep 64..2048 (BASELINE configs[4])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="windows per CPU-baseline batch")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--reference-sample", type=int, default=32, help="windows per step of --impl reference")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if world != args.gpus and world == 1 and args.gpus > 1 and args.impl == "native":
+        # launched without torchrun: re-exec under torch.distributed.run
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""In-tree build of the CUDA library (nvcc cross-compiles sm_100a without a GPU)."""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+SRC = os.path.join(PKG, "csrc", "hb_api.cu")
+LIB_DIR = os.path.join(PKG, "lib")
+LIB = os.path.join(LIB_DIR, "libhelen_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _sources():
+    csrc = os.path.join(PKG, "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    deps.append(os.path.join(ROOT, "include", "helen_b200.h"))
+    return deps
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in _sources())
+
+
+def build(force=False, verbose=False, extra_flags=()):
+    """Compile helen_b200/csrc/hb_api.cu -> helen_b200/lib/libhelen_b200.so."""
+    if not force and not is_stale():
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; cannot build libhelen_b200.so")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    tmp = LIB + ".tmp"
+    extra_flags = list(extra_flags)
+    if not os.path.exists(os.path.join(PKG, "csrc", "tensor_engine.cuh")):
+        extra_flags.append("-DHB_NO_TENSOR_ENGINE")
+    cmd = [nvcc] + NVCC_FLAGS + extra_flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, SRC]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if verbose:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
