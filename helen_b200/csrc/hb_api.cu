@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fp32_kernels.cuh"
+#include "workspace.cuh"
 #ifndef HB_NO_TENSOR_ENGINE
 #include "tensor_engine.cuh"
 #endif
@@ -36,8 +37,10 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                  \
     } while (0)
 
-constexpr size_t kAlign = 256;
-size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+using hb::Workspace;
+using hb::carve;
+using hb::kAlign;
+using hb::align_up;
 
 struct DeviceGuard {
     int prev = -1;
@@ -94,37 +97,6 @@ struct hb_handle {
 };
 
 namespace {
-
-struct Workspace {
-    float* gi;       // [B*W, 768]
-    float* y1;       // [B*W, 256]
-    float* y2;       // [B*W, 256]
-    float* hid_a;    // [B, 2, 128]
-    float* hid_b;    // [B, 2, 128]
-    float* p_base;   // [B, T, 5]
-    float* p_rle;    // [B, T, 11]
-    size_t bytes;
-};
-
-Workspace carve(void* base, int64_t B, int T, int W) {
-    Workspace ws{};
-    size_t off = 0;
-    auto take = [&](size_t n) {
-        size_t o = off;
-        off += align_up(n);
-        return base ? reinterpret_cast<float*>(static_cast<char*>(base) + o) : nullptr;
-    };
-    const size_t rows = (size_t)B * (size_t)std::max(W, 0);
-    ws.gi = take(rows * 2 * hb::G * sizeof(float));
-    ws.y1 = take(rows * 2 * hb::H * sizeof(float));
-    ws.y2 = take(rows * 2 * hb::H * sizeof(float));
-    ws.hid_a = take((size_t)B * 2 * hb::H * sizeof(float));
-    ws.hid_b = take((size_t)B * 2 * hb::H * sizeof(float));
-    ws.p_base = take((size_t)B * T * hb::NBASE * sizeof(float));
-    ws.p_rle = take((size_t)B * T * hb::NRLE * sizeof(float));
-    ws.bytes = off;
-    return ws;
-}
 
 int upload(float** dst, const float* src, size_t n) {
     HB_CUDA(cudaMalloc(dst, n * sizeof(float)));
@@ -309,6 +281,10 @@ int hb_create(const hb_weights* w, int image_features, int hidden, int n_base, i
         hb_destroy(h);
         return HB_ERR_CUDA;
     }
+    h->tensor->f32_enc_wcat = h->enc_wcat;
+    h->tensor->f32_dec_wcat = h->dec_wcat;
+    h->tensor->f32_enc_whh = h->enc_whh;
+    h->tensor->f32_dec_whh = h->dec_whh;
     h->engine = HB_ENGINE_TENSOR;
 #endif
     *out = h;
@@ -349,6 +325,14 @@ int hb_set_engine(hb_handle* h, int engine) {
     }
 #ifdef HB_NO_TENSOR_ENGINE
     if (engine == HB_ENGINE_TENSOR) return fail(HB_ERR_INVALID_ARGUMENT, "tensor engine not built into this library");
+#endif
+#ifndef HB_NO_TENSOR_ENGINE
+    if (engine == HB_ENGINE_DEBUG_TENSOR_PROJECTION || engine == HB_ENGINE_DEBUG_TENSOR_RECURRENCE) {
+        h->tensor->stages = engine == HB_ENGINE_DEBUG_TENSOR_PROJECTION ? 1 : 2;
+        h->engine = HB_ENGINE_TENSOR;
+        return HB_OK;
+    }
+    if (engine == HB_ENGINE_TENSOR) h->tensor->stages = 3;
 #endif
     if (engine != HB_ENGINE_FP32 && engine != HB_ENGINE_TENSOR)
         return fail(HB_ERR_INVALID_ARGUMENT, "unknown engine %d", engine);

@@ -1,0 +1,565 @@
+// Tensor engine: the GRU contractions on tcgen05 tensor cores (sm_100a), fp32-equivalent
+// results through a 3-term split of fp16 operands:
+//     W = (W_hi + W_lo) * 2^-kw ,  x = (x_hi + x_lo) * 2^-10          (hi, lo in fp16)
+//     W.x  ~=  (W_hi.x_hi + W_lo.x_hi + W_hi.x_lo) * 2^-(kw+10)       fp32 accumulate in TMEM
+// uint8 pileup pixels are exact in fp16, so the encoder input projection needs only 2 terms.
+// (tools/precision_probe.py: max |dP| 2.6e-7 vs fp64, same as plain fp32; bf16 3-term: 1.3e-5.)
+//
+// Operand orientation (both kernels): A = weights, 128 gate rows per MMA (M=128), stationary in
+// shared memory; B = activations, N = data rows (windows or window-columns), K-major; D[gate
+// row, data row] in TMEM, so a thread's TMEM lane is "its" gate row / hidden unit.
+//
+//   tc_projection_kernel   gi[m, 0:768] = A[m, 0:K] . Wcat^T + b_ih         (bulk GEMM)
+//   tc_recurrence_kernel   W dependent GRU steps; per step 72 MMAs (3 gate blocks x 8 k-steps x
+//                          3 split terms) + gate math on the TMEM accumulators
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/helen_b200.h"
+#include "fp32_kernels.cuh"
+#include "tc_ptx.cuh"
+#include "workspace.cuh"
+
+namespace hb {
+
+constexpr float ACT_SCALE = 1024.0f;              // activations in (-1, 1) are scaled by 2^10 before the split
+constexpr float ACT_SCALE_INV = 1.0f / 1024.0f;
+constexpr int W_LBO = 128;                        // weight images: dense core matrices
+constexpr int H_LBO = 144;                        // h operand: padded so the gate threads' 2-byte stores spread over banks
+constexpr int H_SBO = 16 * H_LBO;                 // 8-window group stride of the h operand (K = 128 -> 16 core matrices)
+constexpr int WHH_IMG_HALFS = G * H;              // one [384 x 128] fp16 image
+constexpr int WHH_SBO = (H / 8) * W_LBO;          // 2048
+
+// ---------------------------------------------------------------------------------------------
+// Bulk input projection on tensor cores.
+// grid = (row-tile workers, 6 gate blocks); each CTA keeps its [128 x Kp] weight block (hi, lo) in
+// shared memory and walks over NT-row activation tiles.
+// ---------------------------------------------------------------------------------------------
+template <typename TA, int NT>
+__global__ void __launch_bounds__(256, 1)
+tc_projection_kernel(const TA* __restrict__ a, int64_t a_batch_stride, int64_t a_row_stride, int rows_per_window,
+                     int64_t M, int K, int Kp,
+                     const __half* __restrict__ w_img,      // [6 blocks][hi, lo][128 * Kp] core-matrix images
+                     const float* __restrict__ bias,        // [768]
+                     const float* __restrict__ inv_scale,   // [6]  2^-(kw [+10])
+                     float* __restrict__ gi)                // [M, 768]
+{
+    constexpr bool kSplitA = sizeof(TA) == 4;               // fp32 activations need a lo term; uint8 is exact
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int blk = blockIdx.y;
+    const int kg = Kp >> 3;                                  // 16-byte k groups per row
+    const uint32_t w_bytes = 128u * Kp * 2u;                 // one weight image
+    const uint32_t a_bytes = (uint32_t)NT * Kp * 2u;         // one activation image
+    const uint32_t sbo = (uint32_t)kg * 128u;
+    uint8_t* w_hi = smem;
+    uint8_t* w_lo = smem + w_bytes;
+    uint8_t* a_hi = smem + 2 * w_bytes;
+    uint8_t* a_lo = a_hi + a_bytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(a_lo + (kSplitA ? a_bytes : 0));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    {   // weight block: straight copy of the pre-packed image
+        const int4* src = reinterpret_cast<const int4*>(w_img + (size_t)blk * 2 * 128 * Kp);
+        int4* dst = reinterpret_cast<int4*>(w_hi);
+        for (uint32_t i = tid; i < 2 * w_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(tmem_slot, NT < 32 ? 32 : NT);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = tc::idesc_f16_f32(128, NT);
+    const float inv = inv_scale[blk];
+    const float my_bias = bias[blk * 128 + (warp & 3) * 32 + lane];
+    const int ksteps = Kp >> 4;
+    uint32_t phase = 0;
+
+    const int64_t n_tiles = (M + NT - 1) / NT;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * NT;
+        // ---- stage the activation tile as fp16 hi (/lo) core matrices ----
+        for (int e = tid; e < NT * kg; e += blockDim.x) {
+            const int r = e / kg, g8 = e - r * kg;
+            const int64_t m = row0 + r;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            if (m < M) {
+                const int64_t b = m / rows_per_window, t = m - b * rows_per_window;
+                const TA* src = a + b * a_batch_stride + t * a_row_stride + g8 * 8;
+                if constexpr (kSplitA) {
+                    if (g8 * 8 + 8 <= K) {
+                        float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
+                        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) if (g8 * 8 + i < K) v[i] = (float)src[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (g8 * 8 + i < K) v[i] = (float)src[i];
+                }
+            }
+            const uint32_t off = (uint32_t)(r >> 3) * sbo + (uint32_t)g8 * 128u + (uint32_t)(r & 7) * 16u;
+            __half hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if constexpr (kSplitA) tc::split_f16(v[i] * ACT_SCALE, hi[i], lo[i]);
+                else hi[i] = __float2half_rn(v[i]);
+            }
+            *reinterpret_cast<int4*>(a_hi + off) = *reinterpret_cast<int4*>(hi);
+            if constexpr (kSplitA) *reinterpret_cast<int4*>(a_lo + off) = *reinterpret_cast<int4*>(lo);
+        }
+        tc::fence_proxy_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            const uint32_t whi = tc::smem_u32(w_hi), wlo = tc::smem_u32(w_lo), ahi = tc::smem_u32(a_hi), alo = tc::smem_u32(a_lo);
+            uint32_t acc = 0;
+            const int terms = kSplitA ? 3 : 2;
+            for (int term = 0; term < terms; ++term) {
+                const uint32_t wa = term == 1 ? wlo : whi;
+                const uint32_t aa = term == 2 ? alo : ahi;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    tc::mma_f16_ss(tmem, tc::smem_desc(wa + ks * 256, W_LBO, sbo), tc::smem_desc(aa + ks * 256, W_LBO, sbo), idesc, acc);
+                    acc = 1;
+                }
+            }
+            tc::mma_commit(bar);
+        }
+        tc::mbar_wait(bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after();
+        // ---- epilogue: warp w reads lane quarter w%4, column half w/4 ----
+        constexpr int COLS = NT / 2;
+        const int c0 = (warp >> 2) * COLS;
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+        float* out = gi + blk * 128 + (warp & 3) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < COLS; c += 8) {
+            float v[8];
+            tc::tmem_ld8(taddr + c, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t m = row0 + c0 + c + i;
+                if (m < M) out[m * (2 * G)] = fmaf(v[i], inv, my_bias);
+            }
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem, NT < 32 ? 32 : NT);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Recurrence on tensor cores.  One CTA = N windows x one direction x W dependent steps of one
+// layer.  W_hh (hi, lo fp16 images, 192 KB) stays in shared memory for the whole launch; the
+// state h lives in registers (fp32, one hidden unit per thread) and is re-published each step as
+// the fp16 hi/lo B operand.
+// Thread (warp w, lane l): hidden unit j = 32 (w%4) + l  (== its TMEM lane), windows
+// [ (w/4) N/2, (w/4 + 1) N/2 ).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256, 1)
+tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih already added)
+                     const __half* __restrict__ whh_img,    // [2 dirs][hi, lo][384 * 128]
+                     const float* __restrict__ b_hh,        // [2][384]
+                     const float* __restrict__ inv_scale,   // [2]  2^-(kw + 10)
+                     const float* __restrict__ h_in,        // [B, 2, 128] or nullptr
+                     float* __restrict__ h_out,             // [B, 2, 128]
+                     float* __restrict__ y,                 // [B*W, 256]
+                     int64_t B, int W)
+{
+    static_assert(N % 16 == 0 && N >= 16 && N <= 48, "N windows per CTA");
+    constexpr int NW = N / 2;                                // windows per thread
+    constexpr uint32_t W_BYTES = WHH_IMG_HALFS * 2;          // 98304
+    constexpr uint32_t HB_BYTES = (N / 8) * H_SBO;           // one h operand image
+    constexpr uint32_t TMEM_COLS = 3 * N <= 64 ? 64 : (3 * N <= 128 ? 128 : 256);
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* w_hi = smem;
+    uint8_t* w_lo = smem + W_BYTES;
+    uint8_t* h_hi = smem + 2 * W_BYTES;
+    uint8_t* h_lo = h_hi + HB_BYTES;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(h_lo + HB_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dir = blockIdx.y;
+    const int j = (warp & 3) * 32 + lane;
+    const int win0 = (warp >> 2) * NW;
+    const int64_t b0 = (int64_t)blockIdx.x * N;
+
+    {
+        const int4* src = reinterpret_cast<const int4*>(whh_img + (size_t)dir * 2 * WHH_IMG_HALFS);
+        int4* dst = reinterpret_cast<int4*>(w_hi);
+        for (uint32_t i = tid; i < 2 * W_BYTES / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+
+    const float inv = inv_scale[dir];
+    const float bhr = b_hh[dir * G + j], bhz = b_hh[dir * G + H + j], bhn = b_hh[dir * G + 2 * H + j];
+    float h_own[NW];
+    int64_t row_base[NW];
+    bool live[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const int64_t b = b0 + win0 + i;
+        live[i] = b < B;
+        const int64_t bc = live[i] ? b : B - 1;
+        row_base[i] = bc * W;
+        h_own[i] = (h_in != nullptr) ? h_in[(bc * 2 + dir) * H + j] : 0.f;
+    }
+    // publish h_0
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        __half hi, lo;
+        tc::split_f16(h_own[i] * ACT_SCALE, hi, lo);
+        const uint32_t off = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
+        *reinterpret_cast<__half*>(h_hi + off) = hi;
+        *reinterpret_cast<__half*>(h_lo + off) = lo;
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = tc::idesc_f16_f32(128, N);
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)win0;
+    const float* gi_dir = gi + dir * G + j;
+    float* y_dir = y + dir * H + j;
+
+    int t = dir ? W - 1 : 0;
+    const int dt = dir ? -1 : 1;
+    for (int s = 0; s < W; ++s, t += dt) {
+        if (tid == 0) {
+            tc::tc_fence_after();
+            const uint32_t whi = tc::smem_u32(w_hi), wlo = tc::smem_u32(w_lo), hhi = tc::smem_u32(h_hi), hlo = tc::smem_u32(h_lo);
+#pragma unroll 1
+            for (int gb = 0; gb < 3; ++gb) {                 // gate blocks r, z, n
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t wa = (term == 1 ? wlo : whi) + gb * (16 * WHH_SBO);
+                    const uint32_t ha = term == 2 ? hlo : hhi;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        tc::mma_f16_ss(tmem + gb * N, tc::smem_desc(wa + ks * 2 * W_LBO, W_LBO, WHH_SBO),
+                                       tc::smem_desc(ha + ks * 2 * H_LBO, H_LBO, H_SBO), idesc, acc);
+                        acc = 1;
+                    }
+                }
+            }
+            tc::mma_commit(bar);
+        }
+        // this step's input projections: issued now, consumed after the MMA wait
+        float gir[NW], giz[NW], gin[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const float* p = gi_dir + (row_base[i] + t) * (2 * G);
+            gir[i] = p[0]; giz[i] = p[H]; gin[i] = p[2 * H];
+        }
+        tc::mbar_wait(bar, (uint32_t)(s & 1));
+        tc::tc_fence_after();
+        float ar[NW], az[NW], an[NW];
+#pragma unroll
+        for (int c = 0; c < NW; c += 8) {
+            tc::tmem_ld8(taddr + c, ar + c);
+            tc::tmem_ld8(taddr + N + c, az + c);
+            tc::tmem_ld8(taddr + 2 * N + c, an + c);
+        }
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const float r = sigmoidf_precise(gir[i] + fmaf(ar[i], inv, bhr));
+            const float z = sigmoidf_precise(giz[i] + fmaf(az[i], inv, bhz));
+            const float n = tanhf(gin[i] + r * fmaf(an[i], inv, bhn));
+            const float hn = (1.0f - z) * n + z * h_own[i];
+            h_own[i] = hn;
+            __half hi, lo;
+            tc::split_f16(hn * ACT_SCALE, hi, lo);
+            const uint32_t off = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
+            *reinterpret_cast<__half*>(h_hi + off) = hi;
+            *reinterpret_cast<__half*>(h_lo + off) = lo;
+            if (live[i]) y_dir[(row_base[i] + t) * (2 * H)] = hn;
+        }
+        tc::fence_proxy_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i)
+        if (live[i]) h_out[((b0 + win0 + i) * 2 + dir) * H + j] = h_own[i];
+    if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+struct TensorLayer {
+    __half* wih_img = nullptr;     // [6][hi, lo][128 * Kp]
+    float* wih_inv = nullptr;      // [6]
+    float* bih = nullptr;          // [768]
+    __half* whh_img = nullptr;     // [2][hi, lo][384 * 128]
+    float* whh_inv = nullptr;      // [2]
+    float* bhh = nullptr;          // [2][384]
+    int K = 0, Kp = 0;
+};
+
+struct TensorEngine {
+    TensorLayer enc, dec;
+    float* w_head = nullptr;
+    float* b_head = nullptr;
+    int features = 0;
+    int sm_count = 0;
+    int stages = 3;                // bit 0: tensor projection, bit 1: tensor recurrence (debug A/B switch)
+    // fp32 fallbacks for the A/B switch share the fp32 engine's weights (set by hb_api)
+    const float* f32_enc_wcat = nullptr; const float* f32_dec_wcat = nullptr;
+    const float* f32_enc_whh = nullptr;  const float* f32_dec_whh = nullptr;
+};
+
+namespace detail {
+
+inline int pow2_scale_exponent(const float* w, size_t n) {
+    float mx = 0.f;
+    for (size_t i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    if (!(mx > 0.f) || !isfinite(mx)) return 0;
+    int e = (int)floorf(log2f(16384.0f / mx));      // max |w| 2^e < 2^14  (fp16 max 65504)
+    if (e > 24) e = 24;
+    if (e < -8) e = -8;
+    return e;
+}
+
+// [rows x K] fp32 -> hi and lo fp16 core-matrix images (K-major, LBO 128, SBO (Kp/8)*128), per 128-row block
+inline void pack_split_image(const float* w, int rows, int K, int Kp, float scale, __half* hi, __half* lo) {
+    const int sbo = (Kp / 8) * 128;
+    const size_t block_halfs = (size_t)128 * Kp;
+    for (size_t i = 0; i < (size_t)rows * Kp; ++i) hi[i] = lo[i] = __float2half_rn(0.f);
+    for (int r = 0; r < rows; ++r) {
+        const int blk = r / 128, rr = r % 128;
+        for (int k = 0; k < K; ++k) {
+            const float v = w[(size_t)r * K + k] * scale;
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            const size_t off = blk * block_halfs + tc::core_offset(rr, k, 128, sbo) / 2;
+            hi[off] = h;
+            lo[off] = l;
+        }
+    }
+}
+
+template <typename T>
+inline bool to_device(T** dst, const std::vector<T>& src, char* err, size_t errlen) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), src.size() * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        snprintf(err, errlen, "tensor engine: uploading weights failed: %s", cudaGetErrorString(e));
+        return false;
+    }
+    return true;
+}
+
+inline bool pack_layer(const hb_gru_weights& g, int K, bool activations_scaled, TensorLayer* L, char* err, size_t errlen) {
+    const int Kp = (K + 15) / 16 * 16;
+    L->K = K;
+    L->Kp = Kp;
+    const size_t blk_halfs = (size_t)128 * Kp;
+    std::vector<__half> wih(6 * 2 * blk_halfs);
+    std::vector<float> wih_inv(6), bih(2 * G), whh_inv(2), bhh(2 * G);
+    std::vector<__half> whh((size_t)2 * 2 * WHH_IMG_HALFS);
+    std::vector<__half> hi, lo;
+    for (int d = 0; d < 2; ++d) {
+        {   // W_ih: 3 blocks of 128 rows
+            const int e = pow2_scale_exponent(g.weight_ih[d], (size_t)G * K);
+            hi.assign((size_t)G * Kp, __half());
+            lo.assign((size_t)G * Kp, __half());
+            pack_split_image(g.weight_ih[d], G, K, Kp, ldexpf(1.f, e), hi.data(), lo.data());
+            for (int b = 0; b < 3; ++b) {
+                std::memcpy(&wih[(size_t)(d * 3 + b) * 2 * blk_halfs], &hi[b * blk_halfs], blk_halfs * sizeof(__half));
+                std::memcpy(&wih[(size_t)(d * 3 + b) * 2 * blk_halfs + blk_halfs], &lo[b * blk_halfs], blk_halfs * sizeof(__half));
+                wih_inv[d * 3 + b] = ldexpf(1.f, -e) * (activations_scaled ? ACT_SCALE_INV : 1.f);
+            }
+        }
+        {   // W_hh: one [384 x 128] image, blocks r, z, n consecutive
+            const int e = pow2_scale_exponent(g.weight_hh[d], (size_t)G * H);
+            hi.assign((size_t)G * H, __half());
+            lo.assign((size_t)G * H, __half());
+            pack_split_image(g.weight_hh[d], G, H, H, ldexpf(1.f, e), hi.data(), lo.data());
+            std::memcpy(&whh[(size_t)d * 2 * WHH_IMG_HALFS], hi.data(), WHH_IMG_HALFS * sizeof(__half));
+            std::memcpy(&whh[(size_t)d * 2 * WHH_IMG_HALFS + WHH_IMG_HALFS], lo.data(), WHH_IMG_HALFS * sizeof(__half));
+            whh_inv[d] = ldexpf(1.f, -e) * ACT_SCALE_INV;
+        }
+        std::memcpy(&bih[d * G], g.bias_ih[d], G * sizeof(float));
+        std::memcpy(&bhh[d * G], g.bias_hh[d], G * sizeof(float));
+    }
+    return to_device(&L->wih_img, wih, err, errlen) && to_device(&L->wih_inv, wih_inv, err, errlen) &&
+           to_device(&L->bih, bih, err, errlen) && to_device(&L->whh_img, whh, err, errlen) &&
+           to_device(&L->whh_inv, whh_inv, err, errlen) && to_device(&L->bhh, bhh, err, errlen);
+}
+
+inline void free_layer(TensorLayer* L) {
+    cudaFree(L->wih_img); cudaFree(L->wih_inv); cudaFree(L->bih);
+    cudaFree(L->whh_img); cudaFree(L->whh_inv); cudaFree(L->bhh);
+}
+
+constexpr int PROJ_NT = 64;
+
+inline size_t projection_smem(int Kp, bool split_a) {
+    return (size_t)2 * 128 * Kp * 2 + (size_t)(split_a ? 2 : 1) * PROJ_NT * Kp * 2 + 64;
+}
+template <int N>
+constexpr size_t recurrence_smem() { return (size_t)2 * WHH_IMG_HALFS * 2 + (size_t)2 * (N / 8) * H_SBO + 64; }
+
+}  // namespace detail
+
+inline void tensor_engine_destroy(TensorEngine* e) {
+    if (!e) return;
+    detail::free_layer(&e->enc);
+    detail::free_layer(&e->dec);
+    cudaFree(e->w_head);
+    cudaFree(e->b_head);
+    delete e;
+}
+
+inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int sm_count, char* err, size_t errlen) {
+    TensorEngine* e = new TensorEngine();
+    e->features = features;
+    e->sm_count = sm_count;
+    bool ok = detail::pack_layer(w->encoder, features, /*activations_scaled=*/false, &e->enc, err, errlen) &&
+              detail::pack_layer(w->decoder, 2 * H, /*activations_scaled=*/true, &e->dec, err, errlen);
+    if (ok) {
+        std::vector<float> wh((size_t)NCLS * 2 * H), bh(NCLS);
+        std::memcpy(wh.data(), w->base_weight, (size_t)NBASE * 2 * H * sizeof(float));
+        std::memcpy(wh.data() + (size_t)NBASE * 2 * H, w->rle_weight, (size_t)NRLE * 2 * H * sizeof(float));
+        std::memcpy(bh.data(), w->base_bias, NBASE * sizeof(float));
+        std::memcpy(bh.data() + NBASE, w->rle_bias, NRLE * sizeof(float));
+        ok = detail::to_device(&e->w_head, wh, err, errlen) && detail::to_device(&e->b_head, bh, err, errlen);
+    }
+    if (ok) {
+        cudaError_t ce = cudaSuccess;
+        auto set = [&](const void* fn, size_t bytes) {
+            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        };
+        set((const void*)tc_projection_kernel<uint8_t, detail::PROJ_NT>, detail::projection_smem(e->enc.Kp, false));
+        set((const void*)tc_projection_kernel<float, detail::PROJ_NT>, detail::projection_smem(e->dec.Kp, true));
+        set((const void*)tc_recurrence_kernel<16>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<32>, detail::recurrence_smem<32>());
+        set((const void*)tc_recurrence_kernel<48>, detail::recurrence_smem<48>());
+        if (ce != cudaSuccess) {
+            snprintf(err, errlen, "tensor engine: cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ce));
+            ok = false;
+        }
+    }
+    if (!ok) {
+        tensor_engine_destroy(e);
+        return nullptr;
+    }
+    return e;
+}
+
+inline size_t tensor_engine_workspace_bytes(const TensorEngine*, int64_t B, int T, int W) { return carve(nullptr, B, T, W).bytes; }
+
+// windows per recurrence CTA: smallest tile that still gives every SM at most one CTA's worth of work
+inline int pick_windows_per_cta(int64_t B, int sm_count) {
+    const int64_t dir_windows = 2 * B;
+    if (dir_windows <= (int64_t)16 * sm_count) return 16;
+    if (dir_windows <= (int64_t)32 * sm_count) return 32;
+    return 48;
+}
+
+template <typename TA>
+inline void launch_tc_projection(const TensorEngine* e, const TensorLayer& L, const TA* a, int64_t a_batch_stride,
+                                 int64_t a_row_stride, int W, int64_t M, float* gi, cudaStream_t s) {
+    constexpr int NT = detail::PROJ_NT;
+    const int64_t tiles = (M + NT - 1) / NT;
+    const int workers = (int)std::min<int64_t>(tiles, std::max(1, e->sm_count / 6 * 2));
+    dim3 grid((unsigned)workers, 6);
+    tc_projection_kernel<TA, NT><<<grid, 256, detail::projection_smem(L.Kp, sizeof(TA) == 4), s>>>(
+        a, a_batch_stride, a_row_stride, W, M, L.K, L.Kp, L.wih_img, L.bih, L.wih_inv, gi);
+}
+
+inline void launch_tc_recurrence(const TensorEngine* e, const TensorLayer& L, const float* gi, const float* h_in,
+                                 float* h_out, float* y, int64_t B, int W, cudaStream_t s) {
+    const int n = pick_windows_per_cta(B, e->sm_count);
+    dim3 grid((unsigned)((B + n - 1) / n), 2);
+    if (n == 16)
+        tc_recurrence_kernel<16><<<grid, 256, detail::recurrence_smem<16>(), s>>>(gi, L.whh_img, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
+    else if (n == 32)
+        tc_recurrence_kernel<32><<<grid, 256, detail::recurrence_smem<32>(), s>>>(gi, L.whh_img, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
+    else
+        tc_recurrence_kernel<48><<<grid, 256, detail::recurrence_smem<48>(), s>>>(gi, L.whh_img, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
+}
+
+// Returns the number of kernel launches issued, or a negative hb_status (message in err).
+inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t B, int T, int W, int J,
+                                 uint8_t* base_labels, uint8_t* rle_labels, float* base_prob, float* rle_prob,
+                                 void* workspace, cudaStream_t s, char* err, size_t errlen) {
+    Workspace ws = carve(workspace, B, T, W);
+    float* p_base = base_prob ? base_prob : ws.p_base;
+    float* p_rle = rle_prob ? rle_prob : ws.p_rle;
+    const int F = e->features;
+    int launches = 0;
+    cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s);
+    cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s);
+    const float* hid = nullptr;
+    float* hid_bufs[2] = {ws.hid_a, ws.hid_b};
+    int flip = 0;
+    const int64_t rows = B * W;
+    const bool tc_proj = e->stages & 1, tc_rec = e->stages & 2;
+    for (int i = 0; i + W <= T; i += J) {
+        float* enc_h = hid_bufs[flip];
+        float* dec_h = hid_bufs[flip ^ 1];
+        // encoder
+        if (tc_proj) launch_tc_projection<uint8_t>(e, e->enc, images + (int64_t)i * F, (int64_t)T * F, F, W, rows, ws.gi, s);
+        else {
+            dim3 gp((unsigned)((rows + 63) / 64), 2 * G / 64);
+            input_projection_kernel<uint8_t><<<gp, 256, 0, s>>>(images + (int64_t)i * F, (int64_t)T * F, F, W, rows, F, e->f32_enc_wcat, e->enc.bih, ws.gi);
+        }
+        if (tc_rec) launch_tc_recurrence(e, e->enc, ws.gi, hid, enc_h, ws.y1, B, W, s);
+        else {
+            dim3 gr((unsigned)((B + REC_WINDOWS - 1) / REC_WINDOWS), 2);
+            gru_recurrence_kernel<<<gr, REC_THREADS, 0, s>>>(ws.gi, e->f32_enc_whh, e->enc.bhh, hid, enc_h, ws.y1, B, W);
+        }
+        // decoder
+        if (tc_proj) launch_tc_projection<float>(e, e->dec, ws.y1, (int64_t)W * 2 * H, 2 * H, W, rows, ws.gi, s);
+        else {
+            dim3 gp((unsigned)((rows + 63) / 64), 2 * G / 64);
+            input_projection_kernel<float><<<gp, 256, 0, s>>>(ws.y1, (int64_t)W * 2 * H, 2 * H, W, rows, 2 * H, e->f32_dec_wcat, e->dec.bih, ws.gi);
+        }
+        if (tc_rec) launch_tc_recurrence(e, e->dec, ws.gi, enc_h, dec_h, ws.y2, B, W, s);
+        else {
+            dim3 gr((unsigned)((B + REC_WINDOWS - 1) / REC_WINDOWS), 2);
+            gru_recurrence_kernel<<<gr, REC_THREADS, 0, s>>>(ws.gi, e->f32_dec_whh, e->dec.bhh, enc_h, dec_h, ws.y2, B, W);
+        }
+        const int blocks = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)e->sm_count * 8);
+        heads_kernel<<<blocks, 256, 0, s>>>(ws.y2, e->w_head, e->b_head, rows, W, T, i, p_base, p_rle, nullptr, nullptr, 0);
+        launches += 5;
+        hid = dec_h;
+        flip ^= 1;
+    }
+    const int64_t positions = B * T;
+    argmax_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p_base, p_rle, positions, base_labels, rle_labels);
+    launches += 1;
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+        snprintf(err, errlen, "tensor engine launch failed: %s", cudaGetErrorString(ce));
+        return HB_ERR_CUDA;
+    }
+    return launches;
+}
+
+}  // namespace hb

@@ -87,7 +87,7 @@ class WindowPredictor(object):
     @property
     def engine(self):
         code = _native.check(self._lib.hb_get_engine(self._handle))
-        return {v: k for k, v in _native.ENGINES.items()}[code]
+        return {_native.ENGINE_FP32: "fp32", _native.ENGINE_TENSOR: "tensor"}[code]
 
     @property
     def launch_count(self):
