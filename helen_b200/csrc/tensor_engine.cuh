@@ -124,20 +124,24 @@ tc_projection_kernel(const TA* __restrict__ a, int64_t a_batch_stride, int64_t a
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc::tc_fence_after();
-            const uint32_t whi = tc::smem_u32(w_hi), wlo = tc::smem_u32(w_lo), ahi = tc::smem_u32(a_hi), alo = tc::smem_u32(a_lo);
-            uint32_t acc = 0;
-            const int terms = kSplitA ? 3 : 2;
-            for (int term = 0; term < terms; ++term) {
-                const uint32_t wa = term == 1 ? wlo : whi;
-                const uint32_t aa = term == 2 ? alo : ahi;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    tc::mma_f16_ss(tmem, tc::smem_desc(wa + ks * 256, W_LBO, sbo), tc::smem_desc(aa + ks * 256, W_LBO, sbo), idesc, acc);
-                    acc = 1;
+            if (tc::elect_one()) {
+                const uint64_t whi = tc::smem_desc(tc::smem_u32(w_hi), W_LBO, sbo), wlo = tc::smem_desc(tc::smem_u32(w_lo), W_LBO, sbo);
+                const uint64_t ahi = tc::smem_desc(tc::smem_u32(a_hi), W_LBO, sbo), alo = tc::smem_desc(tc::smem_u32(a_lo), W_LBO, sbo);
+                uint32_t acc = 0;
+                const int terms = kSplitA ? 3 : 2;
+                for (int term = 0; term < terms; ++term) {
+                    const uint64_t wa = term == 1 ? wlo : whi;
+                    const uint64_t aa = term == 2 ? alo : ahi;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        tc::mma_f16_ss(tmem, wa + (uint64_t)(ks * 16), aa + (uint64_t)(ks * 16), idesc, acc);
+                        acc = 1;
+                    }
                 }
+                tc::mma_commit(bar);
             }
-            tc::mma_commit(bar);
+            __syncwarp();
         }
         tc::mbar_wait(bar, phase);
         phase ^= 1;
@@ -166,16 +170,26 @@ tc_projection_kernel(const TA* __restrict__ a, int64_t a_batch_stride, int64_t a
 
 // ---------------------------------------------------------------------------------------------
 // Recurrence on tensor cores.  One CTA = N windows x one direction x W dependent steps of one
-// layer.  W_hh (hi, lo fp16 images, 192 KB) stays in shared memory for the whole launch; the
-// state h lives in registers (fp32, one hidden unit per thread) and is re-published each step as
-// the fp16 hi/lo B operand.
-// Thread (warp w, lane l): hidden unit j = 32 (w%4) + l  (== its TMEM lane), windows
-// [ (w/4) N/2, (w/4 + 1) N/2 ).
+// layer.
+//   * W_hh (fp16 hi and lo, 3 gate blocks x 128 rows x 128 k) is loaded ONCE into tensor memory
+//     and used as the TMEM-resident A operand of every MMA (384 of the 512 columns).  With A in
+//     shared memory each M=128,K=16 MMA would re-read 4 KB of weights (32 cycles of smem
+//     bandwidth) regardless of N; from TMEM the MMA runs at the tensor rate for small N.
+//   * the state h lives in registers (fp32, one hidden unit per thread) and is re-published each
+//     step as the fp16 hi/lo B operand in shared memory (K-major core matrices).
+//   * accumulators r | z | n : TMEM columns [0, 3N).
+// Warps 0..7 are gate warps: (warp w, lane l) owns hidden unit j = 32 (w%4) + l (== its TMEM lane)
+// for windows [(w/4) N/2, (w/4+1) N/2).  Warp 8 issues the MMAs.  Handshake per step:
+//   gate warps --h_ready (8 warp arrivals)--> MMA warp --tcgen05.commit acc_ready--> gate warps
 // ---------------------------------------------------------------------------------------------
+constexpr int REC_TC_THREADS = 288;
+constexpr int TMEM_W_COL0 = 128;                  // weight columns start here (accumulators below)
+constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate block][row][k pair]
+
 template <int N>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(REC_TC_THREADS, 1)
 tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih already added)
-                     const __half* __restrict__ whh_img,    // [2 dirs][hi, lo][384 * 128]
+                     const uint32_t* __restrict__ whh_tmem, // [2 dirs][hi, lo][3][128][64] packed fp16 pairs
                      const float* __restrict__ b_hh,        // [2][384]
                      const float* __restrict__ inv_scale,   // [2]  2^-(kw + 10)
                      const float* __restrict__ h_in,        // [B, 2, 128] or nullptr
@@ -183,128 +197,159 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
                      float* __restrict__ y,                 // [B*W, 256]
                      int64_t B, int W)
 {
-    static_assert(N % 16 == 0 && N >= 16 && N <= 48, "N windows per CTA");
-    constexpr int NW = N / 2;                                // windows per thread
-    constexpr uint32_t W_BYTES = WHH_IMG_HALFS * 2;          // 98304
+    static_assert(N == 16 || N == 32, "N windows per CTA (3N accumulator columns must stay below TMEM_W_COL0)");
+    constexpr int NW = N / 2;                                // windows per gate thread
     constexpr uint32_t HB_BYTES = (N / 8) * H_SBO;           // one h operand image
-    constexpr uint32_t TMEM_COLS = 3 * N <= 64 ? 64 : (3 * N <= 128 ? 128 : 256);
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* w_hi = smem;
-    uint8_t* w_lo = smem + W_BYTES;
-    uint8_t* h_hi = smem + 2 * W_BYTES;
-    uint8_t* h_lo = h_hi + HB_BYTES;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(h_lo + HB_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    uint8_t* h_hi = smem;
+    uint8_t* h_lo = smem + HB_BYTES;
+    uint64_t* acc_ready = reinterpret_cast<uint64_t*>(h_lo + HB_BYTES);
+    uint64_t* h_ready = acc_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
-    const int j = (warp & 3) * 32 + lane;
-    const int win0 = (warp >> 2) * NW;
     const int64_t b0 = (int64_t)blockIdx.x * N;
 
-    {
-        const int4* src = reinterpret_cast<const int4*>(whh_img + (size_t)dir * 2 * WHH_IMG_HALFS);
-        int4* dst = reinterpret_cast<int4*>(w_hi);
-        for (uint32_t i = tid; i < 2 * W_BYTES / 16; i += blockDim.x) dst[i] = src[i];
-    }
-    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+    if (tid == 0) { tc::mbar_init(acc_ready, 1); tc::mbar_init(h_ready, 8); tc::mbar_fence_init(); }
     __syncwarp();
-    if (warp == 0) tc::tmem_alloc(tmem_slot, TMEM_COLS);
-
-    const float inv = inv_scale[dir];
-    const float bhr = b_hh[dir * G + j], bhz = b_hh[dir * G + H + j], bhn = b_hh[dir * G + 2 * H + j];
-    float h_own[NW];
-    int64_t row_base[NW];
-    bool live[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        const int64_t b = b0 + win0 + i;
-        live[i] = b < B;
-        const int64_t bc = live[i] ? b : B - 1;
-        row_base[i] = bc * W;
-        h_own[i] = (h_in != nullptr) ? h_in[(bc * 2 + dir) * H + j] : 0.f;
-    }
-    // publish h_0
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        __half hi, lo;
-        tc::split_f16(h_own[i] * ACT_SCALE, hi, lo);
-        const uint32_t off = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
-        *reinterpret_cast<__half*>(h_hi + off) = hi;
-        *reinterpret_cast<__half*>(h_lo + off) = lo;
-    }
-    tc::fence_proxy_async_smem();
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t idesc = tc::idesc_f16_f32(128, N);
-    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)win0;
-    const float* gi_dir = gi + dir * G + j;
-    float* y_dir = y + dir * H + j;
 
-    int t = dir ? W - 1 : 0;
-    const int dt = dir ? -1 : 1;
-    for (int s = 0; s < W; ++s, t += dt) {
-        if (tid == 0) {
-            tc::tc_fence_after();
-            const uint32_t whi = tc::smem_u32(w_hi), wlo = tc::smem_u32(w_lo), hhi = tc::smem_u32(h_hi), hlo = tc::smem_u32(h_lo);
-#pragma unroll 1
-            for (int gb = 0; gb < 3; ++gb) {                 // gate blocks r, z, n
-                uint32_t acc = 0;
-#pragma unroll 1
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t wa = (term == 1 ? wlo : whi) + gb * (16 * WHH_SBO);
-                    const uint32_t ha = term == 2 ? hlo : hhi;
+    if (warp == 8) {
+        // ===================== MMA issuer =====================
+        __syncthreads();                                     // weights in TMEM, h_0 in smem
+        tc::tc_fence_after();
+        const uint32_t idesc = tc::idesc_f16_f32(128, N);
+        const uint64_t hhi_desc = tc::smem_desc(tc::smem_u32(h_hi), H_LBO, H_SBO);
+        const uint64_t hlo_desc = tc::smem_desc(tc::smem_u32(h_lo), H_LBO, H_SBO);
+        for (int s = 0; s < W; ++s) {
+            if (s > 0) {
+                tc::mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
+                tc::tc_fence_after();
+            }
+            if (tc::elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        tc::mma_f16_ss(tmem + gb * N, tc::smem_desc(wa + ks * 2 * W_LBO, W_LBO, WHH_SBO),
-                                       tc::smem_desc(ha + ks * 2 * H_LBO, H_LBO, H_SBO), idesc, acc);
-                        acc = 1;
+                for (int gb = 0; gb < 3; ++gb) {             // gate blocks r, z, n
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {   // (W_hi,h_hi) (W_lo,h_hi) (W_hi,h_lo)
+                        const uint32_t a_col = tmem + TMEM_W_COL0 + ((term == 1 ? 3 : 0) + gb) * 64;
+                        const uint64_t bd = term == 2 ? hlo_desc : hhi_desc;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            tc::mma_f16_ts(tmem + gb * N, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc,
+                                           (term | ks) != 0);
                     }
                 }
+                tc::mma_commit(acc_ready);
             }
-            tc::mma_commit(bar);
+            __syncwarp();
         }
-        // this step's input projections: issued now, consumed after the MMA wait
-        float gir[NW], giz[NW], gin[NW];
+    } else {
+        // ===================== gate warps =====================
+        const int q = warp & 3;
+        const int j = q * 32 + lane;
+        const int win0 = (warp >> 2) * NW;
+        {   // W_hh -> TMEM: warps 0-3 store the hi image, warps 4-7 the lo image; thread = row j
+            const int term = warp >> 2;
+            const uint32_t* src = whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64;
+#pragma unroll 1
+            for (int gb = 0; gb < 3; ++gb) {
+#pragma unroll
+                for (int c = 0; c < 64; c += 16) {
+                    uint32_t r[16];
+                    const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64 + c);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const uint4 x = p[v];
+                        r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                    }
+                    tc::tmem_st16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_W_COL0 + (term * 3 + gb) * 64 + c, r);
+                }
+            }
+            tc::tmem_st_wait();
+        }
+        const float inv = inv_scale[dir];
+        const float bhr = b_hh[dir * G + j], bhz = b_hh[dir * G + H + j], bhn = b_hh[dir * G + 2 * H + j];
+        // gi / y rows of windows past B exist in the (padded) workspace, so only h_in / h_out,
+        // which may be caller tensors of exactly B windows, need guarding.
+        float h_own[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-            const float* p = gi_dir + (row_base[i] + t) * (2 * G);
-            gir[i] = p[0]; giz[i] = p[H]; gin[i] = p[2 * H];
-        }
-        tc::mbar_wait(bar, (uint32_t)(s & 1));
-        tc::tc_fence_after();
-        float ar[NW], az[NW], an[NW];
-#pragma unroll
-        for (int c = 0; c < NW; c += 8) {
-            tc::tmem_ld8(taddr + c, ar + c);
-            tc::tmem_ld8(taddr + N + c, az + c);
-            tc::tmem_ld8(taddr + 2 * N + c, an + c);
-        }
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            const float r = sigmoidf_precise(gir[i] + fmaf(ar[i], inv, bhr));
-            const float z = sigmoidf_precise(giz[i] + fmaf(az[i], inv, bhz));
-            const float n = tanhf(gin[i] + r * fmaf(an[i], inv, bhn));
-            const float hn = (1.0f - z) * n + z * h_own[i];
-            h_own[i] = hn;
+            const int64_t b = b0 + win0 + i;
+            h_own[i] = (h_in != nullptr && b < B) ? h_in[(b * 2 + dir) * H + j] : 0.f;
             __half hi, lo;
-            tc::split_f16(hn * ACT_SCALE, hi, lo);
+            tc::split_f16(h_own[i] * ACT_SCALE, hi, lo);
             const uint32_t off = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
             *reinterpret_cast<__half*>(h_hi + off) = hi;
             *reinterpret_cast<__half*>(h_lo + off) = lo;
-            if (live[i]) y_dir[(row_base[i] + t) * (2 * H)] = hn;
         }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
-        __syncthreads();
-    }
+        __syncthreads();                                     // pairs with the MMA warp's second barrier
+
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
+        const int wstride_gi = W * 2 * G, wstride_y = W * 2 * H;   // floats between consecutive windows
+        const float* gi_thr = gi + (b0 + win0) * (int64_t)wstride_gi + dir * G + j;
+        float* y_thr = y + (b0 + win0) * (int64_t)wstride_y + dir * H + j;
+        int t = dir ? W - 1 : 0;
+        const int dt = dir ? -1 : 1;
+        for (int s = 0; s < W; ++s, t += dt) {
+            // this step's input projections: issued now, consumed after the MMA wait
+            float gir[NW], giz[NW], gin[NW];
+            const float* gp = gi_thr + t * (2 * G);
 #pragma unroll
-    for (int i = 0; i < NW; ++i)
-        if (live[i]) h_out[((b0 + win0 + i) * 2 + dir) * H + j] = h_own[i];
-    if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
+            for (int i = 0; i < NW; ++i) {
+                const float* p = gp + i * wstride_gi;
+                gir[i] = __ldg(p); giz[i] = __ldg(p + H); gin[i] = __ldg(p + 2 * H);
+            }
+            tc::mbar_wait(acc_ready, (uint32_t)(s & 1));
+            tc::tc_fence_after();
+            float* yp = y_thr + t * (2 * H);
+#pragma unroll
+            for (int c = 0; c < NW; c += 8) {
+                float ar[8], az[8], an[8];
+                tc::tmem_ld8(taddr + c, ar);
+                tc::tmem_ld8(taddr + N + c, az);
+                tc::tmem_ld8(taddr + 2 * N + c, an);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = c + u;
+#ifdef HB_PRECISE_GATES
+                    const float r = sigmoidf_precise(gir[i] + fmaf(ar[u], inv, bhr));
+                    const float z = sigmoidf_precise(giz[i] + fmaf(az[u], inv, bhz));
+                    const float n = tanhf(gin[i] + r * fmaf(an[u], inv, bhn));
+#else
+                    const float r = tc::sigmoid_fast(gir[i] + fmaf(ar[u], inv, bhr));
+                    const float z = tc::sigmoid_fast(giz[i] + fmaf(az[u], inv, bhz));
+                    const float n = tc::tanh_fast(gin[i] + r * fmaf(an[u], inv, bhn));
+#endif
+                    const float hn = fmaf(z, h_own[i] - n, n);   // (1 - z) n + z h
+                    h_own[i] = hn;
+                    __half hi, lo;
+                    tc::split_f16(hn * ACT_SCALE, hi, lo);
+                    const uint32_t off = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
+                    *reinterpret_cast<__half*>(h_hi + off) = hi;
+                    *reinterpret_cast<__half*>(h_lo + off) = lo;
+                    yp[i * wstride_y] = hn;
+                }
+            }
+            tc::fence_proxy_async_smem();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(h_ready);
+        }
+#pragma unroll
+        for (int i = 0; i < NW; ++i)
+            if (b0 + win0 + i < B) h_out[((b0 + win0 + i) * 2 + dir) * H + j] = h_own[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -314,7 +359,7 @@ struct TensorLayer {
     __half* wih_img = nullptr;     // [6][hi, lo][128 * Kp]
     float* wih_inv = nullptr;      // [6]
     float* bih = nullptr;          // [768]
-    __half* whh_img = nullptr;     // [2][hi, lo][384 * 128]
+    uint32_t* whh_tmem = nullptr;  // [2][hi, lo][3][128][64] packed fp16 pairs (TMEM A-operand image)
     float* whh_inv = nullptr;      // [2]
     float* bhh = nullptr;          // [2][384]
     int K = 0, Kp = 0;
@@ -380,7 +425,7 @@ inline bool pack_layer(const hb_gru_weights& g, int K, bool activations_scaled, 
     const size_t blk_halfs = (size_t)128 * Kp;
     std::vector<__half> wih(6 * 2 * blk_halfs);
     std::vector<float> wih_inv(6), bih(2 * G), whh_inv(2), bhh(2 * G);
-    std::vector<__half> whh((size_t)2 * 2 * WHH_IMG_HALFS);
+    std::vector<uint32_t> whh((size_t)2 * WHH_TMEM_WORDS);
     std::vector<__half> hi, lo;
     for (int d = 0; d < 2; ++d) {
         {   // W_ih: 3 blocks of 128 rows
@@ -394,26 +439,36 @@ inline bool pack_layer(const hb_gru_weights& g, int K, bool activations_scaled, 
                 wih_inv[d * 3 + b] = ldexpf(1.f, -e) * (activations_scaled ? ACT_SCALE_INV : 1.f);
             }
         }
-        {   // W_hh: one [384 x 128] image, blocks r, z, n consecutive
+        {   // W_hh: TMEM image, lane = row within the gate block, column c holds k = 2c (low half), 2c+1 (high)
             const int e = pow2_scale_exponent(g.weight_hh[d], (size_t)G * H);
-            hi.assign((size_t)G * H, __half());
-            lo.assign((size_t)G * H, __half());
-            pack_split_image(g.weight_hh[d], G, H, H, ldexpf(1.f, e), hi.data(), lo.data());
-            std::memcpy(&whh[(size_t)d * 2 * WHH_IMG_HALFS], hi.data(), WHH_IMG_HALFS * sizeof(__half));
-            std::memcpy(&whh[(size_t)d * 2 * WHH_IMG_HALFS + WHH_IMG_HALFS], lo.data(), WHH_IMG_HALFS * sizeof(__half));
+            const float scale = ldexpf(1.f, e);
+            for (int gb = 0; gb < 3; ++gb)
+                for (int r = 0; r < 128; ++r)
+                    for (int c = 0; c < 64; ++c) {
+                        uint32_t word[2] = {0, 0};
+                        for (int half_idx = 0; half_idx < 2; ++half_idx) {
+                            const float v = g.weight_hh[d][(size_t)(gb * 128 + r) * H + 2 * c + half_idx] * scale;
+                            const __half hi_h = __float2half_rn(v);
+                            const __half lo_h = __float2half_rn(v - __half2float(hi_h));
+                            word[0] |= (uint32_t)__half_as_ushort(hi_h) << (16 * half_idx);
+                            word[1] |= (uint32_t)__half_as_ushort(lo_h) << (16 * half_idx);
+                        }
+                        for (int term = 0; term < 2; ++term)
+                            whh[(size_t)d * WHH_TMEM_WORDS + (((size_t)term * 3 + gb) * 128 + r) * 64 + c] = word[term];
+                    }
             whh_inv[d] = ldexpf(1.f, -e) * ACT_SCALE_INV;
         }
         std::memcpy(&bih[d * G], g.bias_ih[d], G * sizeof(float));
         std::memcpy(&bhh[d * G], g.bias_hh[d], G * sizeof(float));
     }
     return to_device(&L->wih_img, wih, err, errlen) && to_device(&L->wih_inv, wih_inv, err, errlen) &&
-           to_device(&L->bih, bih, err, errlen) && to_device(&L->whh_img, whh, err, errlen) &&
+           to_device(&L->bih, bih, err, errlen) && to_device(&L->whh_tmem, whh, err, errlen) &&
            to_device(&L->whh_inv, whh_inv, err, errlen) && to_device(&L->bhh, bhh, err, errlen);
 }
 
 inline void free_layer(TensorLayer* L) {
     cudaFree(L->wih_img); cudaFree(L->wih_inv); cudaFree(L->bih);
-    cudaFree(L->whh_img); cudaFree(L->whh_inv); cudaFree(L->bhh);
+    cudaFree(L->whh_tmem); cudaFree(L->whh_inv); cudaFree(L->bhh);
 }
 
 constexpr int PROJ_NT = 64;
@@ -421,8 +476,9 @@ constexpr int PROJ_NT = 64;
 inline size_t projection_smem(int Kp, bool split_a) {
     return (size_t)2 * 128 * Kp * 2 + (size_t)(split_a ? 2 : 1) * PROJ_NT * Kp * 2 + 64;
 }
+// the kernel allocates all 512 TMEM columns, so force one CTA per SM through the smem request
 template <int N>
-constexpr size_t recurrence_smem() { return (size_t)2 * WHH_IMG_HALFS * 2 + (size_t)2 * (N / 8) * H_SBO + 64; }
+constexpr size_t recurrence_smem() { return (size_t)120 * 1024; }
 
 }  // namespace detail
 
@@ -458,7 +514,6 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_projection_kernel<float, detail::PROJ_NT>, detail::projection_smem(e->dec.Kp, true));
         set((const void*)tc_recurrence_kernel<16>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<32>, detail::recurrence_smem<32>());
-        set((const void*)tc_recurrence_kernel<48>, detail::recurrence_smem<48>());
         if (ce != cudaSuccess) {
             snprintf(err, errlen, "tensor engine: cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ce));
             ok = false;
@@ -477,8 +532,7 @@ inline size_t tensor_engine_workspace_bytes(const TensorEngine*, int64_t B, int 
 inline int pick_windows_per_cta(int64_t B, int sm_count) {
     const int64_t dir_windows = 2 * B;
     if (dir_windows <= (int64_t)16 * sm_count) return 16;
-    if (dir_windows <= (int64_t)32 * sm_count) return 32;
-    return 48;
+    return 32;
 }
 
 template <typename TA>
@@ -497,11 +551,9 @@ inline void launch_tc_recurrence(const TensorEngine* e, const TensorLayer& L, co
     const int n = pick_windows_per_cta(B, e->sm_count);
     dim3 grid((unsigned)((B + n - 1) / n), 2);
     if (n == 16)
-        tc_recurrence_kernel<16><<<grid, 256, detail::recurrence_smem<16>(), s>>>(gi, L.whh_img, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
-    else if (n == 32)
-        tc_recurrence_kernel<32><<<grid, 256, detail::recurrence_smem<32>(), s>>>(gi, L.whh_img, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
+        tc_recurrence_kernel<16><<<grid, REC_TC_THREADS, detail::recurrence_smem<16>(), s>>>(gi, L.whh_tmem, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
     else
-        tc_recurrence_kernel<48><<<grid, 256, detail::recurrence_smem<48>(), s>>>(gi, L.whh_img, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
+        tc_recurrence_kernel<32><<<grid, REC_TC_THREADS, detail::recurrence_smem<32>(), s>>>(gi, L.whh_tmem, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
 }
 
 // Returns the number of kernel launches issued, or a negative hb_status (message in err).

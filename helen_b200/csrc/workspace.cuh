@@ -30,12 +30,15 @@ inline Workspace carve(void* base, int64_t B, int T, int W) {
         off += align_up(n);
         return base ? reinterpret_cast<float*>(static_cast<char*>(base) + o) : nullptr;
     };
-    const size_t rows = (size_t)B * (size_t)std::max(W, 0);
+    // window counts are padded to a multiple of 32 so that window tiles of the tensor kernels may
+    // read/write the rows of (non-existent) windows past B without bounds checks
+    const size_t Bp = ((size_t)B + 31) / 32 * 32;
+    const size_t rows = Bp * (size_t)std::max(W, 0);
     ws.gi = take(rows * 2 * G * sizeof(float));
     ws.y1 = take(rows * 2 * H * sizeof(float));
     ws.y2 = take(rows * 2 * H * sizeof(float));
-    ws.hid_a = take((size_t)B * 2 * H * sizeof(float));
-    ws.hid_b = take((size_t)B * 2 * H * sizeof(float));
+    ws.hid_a = take(Bp * 2 * H * sizeof(float));
+    ws.hid_b = take(Bp * 2 * H * sizeof(float));
     ws.p_base = take((size_t)B * T * NBASE * sizeof(float));
     ws.p_rle = take((size_t)B * T * NRLE * sizeof(float));
     ws.bytes = off;
