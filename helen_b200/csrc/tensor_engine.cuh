@@ -182,9 +182,16 @@ tc_projection_kernel(const TA* __restrict__ a, int64_t a_batch_stride, int64_t a
 // for windows [(w/4) N/2, (w/4+1) N/2).  Warp 8 issues the MMAs.  Handshake per step:
 //   gate warps --h_ready (8 warp arrivals)--> MMA warp --tcgen05.commit acc_ready--> gate warps
 // ---------------------------------------------------------------------------------------------
-constexpr int REC_TC_THREADS = 288;
+constexpr int REC_GATE_WARPS = 16;
+constexpr int REC_TC_THREADS = (REC_GATE_WARPS + 1) * 32;
 constexpr int TMEM_W_COL0 = 128;                  // weight columns start here (accumulators below)
 constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate block][row][k pair]
+
+__device__ __forceinline__ float ld_nc_f32(const float* p) {   // asm volatile: stays where it is written
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 
 template <int N>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
@@ -194,32 +201,38 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
                      const float* __restrict__ inv_scale,   // [2]  2^-(kw + 10)
                      const float* __restrict__ h_in,        // [B, 2, 128] or nullptr
                      float* __restrict__ h_out,             // [B, 2, 128]
-                     float* __restrict__ y,                 // [B*W, 256]
+                     float* __restrict__ y,                 // [B*W, 256] fp32, or nullptr
+                     __half* __restrict__ y_hi,             // [B*W, 256] fp16 split of y * 2^10, or nullptr
+                     __half* __restrict__ y_lo,
                      int64_t B, int W)
 {
     static_assert(N == 16 || N == 32, "N windows per CTA (3N accumulator columns must stay below TMEM_W_COL0)");
-    constexpr int NW = N / 2;                                // windows per gate thread
+    constexpr int NW = N / 4;                                // windows per gate thread
     constexpr uint32_t HB_BYTES = (N / 8) * H_SBO;           // one h operand image
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* h_hi = smem;
     uint8_t* h_lo = smem + HB_BYTES;
-    uint64_t* acc_ready = reinterpret_cast<uint64_t*>(h_lo + HB_BYTES);
-    uint64_t* h_ready = acc_ready + 1;
+    uint64_t* acc_ready = reinterpret_cast<uint64_t*>(h_lo + HB_BYTES);   // [3]: r, z, n blocks
+    uint64_t* h_ready = acc_ready + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
     const int64_t b0 = (int64_t)blockIdx.x * N;
 
-    if (tid == 0) { tc::mbar_init(acc_ready, 1); tc::mbar_init(h_ready, 8); tc::mbar_fence_init(); }
+    if (tid == 0) {
+        tc::mbar_init(acc_ready + 0, 1); tc::mbar_init(acc_ready + 1, 1); tc::mbar_init(acc_ready + 2, 1);
+        tc::mbar_init(h_ready, REC_GATE_WARPS);
+        tc::mbar_fence_init();
+    }
     __syncwarp();
-    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == REC_GATE_WARPS) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
@@ -243,8 +256,8 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
                             tc::mma_f16_ts(tmem + gb * N, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc,
                                            (term | ks) != 0);
                     }
+                    tc::mma_commit(acc_ready + gb);          // gates start on r while z, n still run
                 }
-                tc::mma_commit(acc_ready);
             }
             __syncwarp();
         }
@@ -253,7 +266,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
         const int q = warp & 3;
         const int j = q * 32 + lane;
         const int win0 = (warp >> 2) * NW;
-        {   // W_hh -> TMEM: warps 0-3 store the hi image, warps 4-7 the lo image; thread = row j
+        if (warp < 8) {   // W_hh -> TMEM: warps 0-3 store the hi image, warps 4-7 the lo image; thread = row j
             const int term = warp >> 2;
             const uint32_t* src = whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64;
 #pragma unroll 1
@@ -277,66 +290,66 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
         // gi / y rows of windows past B exist in the (padded) workspace, so only h_in / h_out,
         // which may be caller tensors of exactly B windows, need guarding.
         float h_own[NW];
+        uint32_t h_off[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
             const int64_t b = b0 + win0 + i;
             h_own[i] = (h_in != nullptr && b < B) ? h_in[(b * 2 + dir) * H + j] : 0.f;
+            h_off[i] = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
             __half hi, lo;
             tc::split_f16(h_own[i] * ACT_SCALE, hi, lo);
-            const uint32_t off = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
-            *reinterpret_cast<__half*>(h_hi + off) = hi;
-            *reinterpret_cast<__half*>(h_lo + off) = lo;
+            *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
+            *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
         }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
         __syncthreads();                                     // pairs with the MMA warp's second barrier
 
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
-        const int wstride_gi = W * 2 * G, wstride_y = W * 2 * H;   // floats between consecutive windows
+        const int wstride_gi = W * 2 * G, wstride_y = W * 2 * H;   // elements between consecutive windows
         const float* gi_thr = gi + (b0 + win0) * (int64_t)wstride_gi + dir * G + j;
-        float* y_thr = y + (b0 + win0) * (int64_t)wstride_y + dir * H + j;
+        const int64_t y_thr = (b0 + win0) * (int64_t)wstride_y + dir * H + j;
         int t = dir ? W - 1 : 0;
         const int dt = dir ? -1 : 1;
         for (int s = 0; s < W; ++s, t += dt) {
-            // this step's input projections: issued now, consumed after the MMA wait
+            // this step's input projections: issued now, consumed after the MMA waits
             float gir[NW], giz[NW], gin[NW];
             const float* gp = gi_thr + t * (2 * G);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
                 const float* p = gp + i * wstride_gi;
-                gir[i] = __ldg(p); giz[i] = __ldg(p + H); gin[i] = __ldg(p + 2 * H);
+                gir[i] = ld_nc_f32(p); giz[i] = ld_nc_f32(p + H); gin[i] = ld_nc_f32(p + 2 * H);
             }
-            tc::mbar_wait(acc_ready, (uint32_t)(s & 1));
+            const uint32_t par = (uint32_t)(s & 1);
+            float r[NW], z[NW], a[NW];
+            tc::mbar_wait(acc_ready + 0, par);
             tc::tc_fence_after();
-            float* yp = y_thr + t * (2 * H);
+            if constexpr (NW == 4) tc::tmem_ld4(taddr, a); else tc::tmem_ld8(taddr, a);
+            tc::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < NW; c += 8) {
-                float ar[8], az[8], an[8];
-                tc::tmem_ld8(taddr + c, ar);
-                tc::tmem_ld8(taddr + N + c, az);
-                tc::tmem_ld8(taddr + 2 * N + c, an);
-                tc::tmem_ld_wait();
+            for (int i = 0; i < NW; ++i) r[i] = tc::sigmoid_fast(gir[i] + fmaf(a[i], inv, bhr));
+            tc::mbar_wait(acc_ready + 1, par);
+            tc::tc_fence_after();
+            if constexpr (NW == 4) tc::tmem_ld4(taddr + N, a); else tc::tmem_ld8(taddr + N, a);
+            tc::tmem_ld_wait();
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = c + u;
-#ifdef HB_PRECISE_GATES
-                    const float r = sigmoidf_precise(gir[i] + fmaf(ar[u], inv, bhr));
-                    const float z = sigmoidf_precise(giz[i] + fmaf(az[u], inv, bhz));
-                    const float n = tanhf(gin[i] + r * fmaf(an[u], inv, bhn));
-#else
-                    const float r = tc::sigmoid_fast(gir[i] + fmaf(ar[u], inv, bhr));
-                    const float z = tc::sigmoid_fast(giz[i] + fmaf(az[u], inv, bhz));
-                    const float n = tc::tanh_fast(gin[i] + r * fmaf(an[u], inv, bhn));
-#endif
-                    const float hn = fmaf(z, h_own[i] - n, n);   // (1 - z) n + z h
-                    h_own[i] = hn;
-                    __half hi, lo;
-                    tc::split_f16(hn * ACT_SCALE, hi, lo);
-                    const uint32_t off = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
-                    *reinterpret_cast<__half*>(h_hi + off) = hi;
-                    *reinterpret_cast<__half*>(h_lo + off) = lo;
-                    yp[i * wstride_y] = hn;
-                }
+            for (int i = 0; i < NW; ++i) z[i] = tc::sigmoid_fast(giz[i] + fmaf(a[i], inv, bhz));
+            tc::mbar_wait(acc_ready + 2, par);
+            tc::tc_fence_after();
+            if constexpr (NW == 4) tc::tmem_ld4(taddr + 2 * N, a); else tc::tmem_ld8(taddr + 2 * N, a);
+            tc::tmem_ld_wait();
+            const int64_t yo = y_thr + t * (2 * H);
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const float n = tc::tanh_fast(gin[i] + r[i] * fmaf(a[i], inv, bhn));
+                const float hn = fmaf(z[i], h_own[i] - n, n);   // (1 - z) n + z h
+                h_own[i] = hn;
+                __half hi, lo;
+                tc::split_f16(hn * ACT_SCALE, hi, lo);
+                *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
+                *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
+                if (y != nullptr) y[yo + i * wstride_y] = hn;
+                if (y_hi != nullptr) { y_hi[yo + i * wstride_y] = hi; y_lo[yo + i * wstride_y] = lo; }
             }
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
@@ -349,7 +362,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem, 512);
+    if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -551,9 +564,9 @@ inline void launch_tc_recurrence(const TensorEngine* e, const TensorLayer& L, co
     const int n = pick_windows_per_cta(B, e->sm_count);
     dim3 grid((unsigned)((B + n - 1) / n), 2);
     if (n == 16)
-        tc_recurrence_kernel<16><<<grid, REC_TC_THREADS, detail::recurrence_smem<16>(), s>>>(gi, L.whh_tmem, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
+        tc_recurrence_kernel<16><<<grid, REC_TC_THREADS, detail::recurrence_smem<16>(), s>>>(gi, L.whh_tmem, L.bhh, L.whh_inv, h_in, h_out, y, nullptr, nullptr, B, W);
     else
-        tc_recurrence_kernel<32><<<grid, REC_TC_THREADS, detail::recurrence_smem<32>(), s>>>(gi, L.whh_tmem, L.bhh, L.whh_inv, h_in, h_out, y, B, W);
+        tc_recurrence_kernel<32><<<grid, REC_TC_THREADS, detail::recurrence_smem<32>(), s>>>(gi, L.whh_tmem, L.bhh, L.whh_inv, h_in, h_out, y, nullptr, nullptr, B, W);
 }
 
 // Returns the number of kernel launches issued, or a negative hb_status (message in err).
