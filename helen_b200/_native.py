@@ -18,8 +18,7 @@ HB_ERR_WORKSPACE = -4
 HB_ERR_OUT_OF_MEMORY = -5
 
 ENGINE_DEFAULT, ENGINE_FP32, ENGINE_TENSOR = 0, 1, 2
-ENGINES = {"default": ENGINE_DEFAULT, "fp32": ENGINE_FP32, "tensor": ENGINE_TENSOR,
-           "tensor_projection_only": 3, "tensor_recurrence_only": 4}
+ENGINES = {"default": ENGINE_DEFAULT, "fp32": ENGINE_FP32, "tensor": ENGINE_TENSOR}
 
 _FP = POINTER(c_float)
 _U8 = POINTER(c_uint8)

@@ -281,10 +281,6 @@ int hb_create(const hb_weights* w, int image_features, int hidden, int n_base, i
         hb_destroy(h);
         return HB_ERR_CUDA;
     }
-    h->tensor->f32_enc_wcat = h->enc_wcat;
-    h->tensor->f32_dec_wcat = h->dec_wcat;
-    h->tensor->f32_enc_whh = h->enc_whh;
-    h->tensor->f32_dec_whh = h->dec_whh;
     h->engine = HB_ENGINE_TENSOR;
 #endif
     *out = h;
@@ -325,14 +321,6 @@ int hb_set_engine(hb_handle* h, int engine) {
     }
 #ifdef HB_NO_TENSOR_ENGINE
     if (engine == HB_ENGINE_TENSOR) return fail(HB_ERR_INVALID_ARGUMENT, "tensor engine not built into this library");
-#endif
-#ifndef HB_NO_TENSOR_ENGINE
-    if (engine == HB_ENGINE_DEBUG_TENSOR_PROJECTION || engine == HB_ENGINE_DEBUG_TENSOR_RECURRENCE) {
-        h->tensor->stages = engine == HB_ENGINE_DEBUG_TENSOR_PROJECTION ? 1 : 2;
-        h->engine = HB_ENGINE_TENSOR;
-        return HB_OK;
-    }
-    if (engine == HB_ENGINE_TENSOR) h->tensor->stages = 3;
 #endif
     if (engine != HB_ENGINE_FP32 && engine != HB_ENGINE_TENSOR)
         return fail(HB_ERR_INVALID_ARGUMENT, "unknown engine %d", engine);

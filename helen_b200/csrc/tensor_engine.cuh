@@ -1,17 +1,21 @@
-// Tensor engine: the GRU contractions on tcgen05 tensor cores (sm_100a), fp32-equivalent
-// results through a 3-term split of fp16 operands:
+// Tensor engine: the GRU / head contractions on tcgen05 tensor cores (sm_100a) with
+// fp32-equivalent results through a 3-term split of fp16 operands:
 //     W = (W_hi + W_lo) * 2^-kw ,  x = (x_hi + x_lo) * 2^-10          (hi, lo in fp16)
 //     W.x  ~=  (W_hi.x_hi + W_lo.x_hi + W_hi.x_lo) * 2^-(kw+10)       fp32 accumulate in TMEM
 // uint8 pileup pixels are exact in fp16, so the encoder input projection needs only 2 terms.
 // (tools/precision_probe.py: max |dP| 2.6e-7 vs fp64, same as plain fp32; bf16 3-term: 1.3e-5.)
 //
-// Operand orientation (both kernels): A = weights, 128 gate rows per MMA (M=128), stationary in
-// shared memory; B = activations, N = data rows (windows or window-columns), K-major; D[gate
-// row, data row] in TMEM, so a thread's TMEM lane is "its" gate row / hidden unit.
+// Data path of one chunk (reference loop body, predict_gpu.py:114-149):
+//   ximg --proj(enc)--> gi --rec(enc)--> yimg1 --proj(dec)--> gi --rec(dec)--> yimg2 --heads--> P +=
 //
-//   tc_projection_kernel   gi[m, 0:768] = A[m, 0:K] . Wcat^T + b_ih         (bulk GEMM)
-//   tc_recurrence_kernel   W dependent GRU steps; per step 72 MMAs (3 gate blocks x 8 k-steps x
-//                          3 split terms) + gate math on the TMEM accumulators
+// Every activation tensor that feeds an MMA is kept in global memory as *operand images*: blocks
+// of [8 windows x K] fp16 already in the K-major core-matrix layout tcgen05 reads from shared
+// memory, so a tile is staged with a handful of 1-D bulk async copies (TMA engine, cp.async.bulk)
+// and no thread ever touches it:
+//   ximg : [window group][column t][K/8 k-groups][8 windows][8 k]          (pixels, exact fp16)
+//   yimg : [window group][column t][hi, lo][direction][16 k-groups x 144 B] (GRU outputs * 2^10)
+// Weights are the stationary operand: for the GRU contractions they live in tensor memory (TMEM)
+// as the A operand (M = 128 gate rows); a thread's TMEM lane is "its" gate row / hidden unit.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -31,198 +35,244 @@ namespace hb {
 
 constexpr float ACT_SCALE = 1024.0f;              // activations in (-1, 1) are scaled by 2^10 before the split
 constexpr float ACT_SCALE_INV = 1.0f / 1024.0f;
-constexpr int W_LBO = 128;                        // weight images: dense core matrices
-constexpr int H_LBO = 144;                        // h operand: padded so the gate threads' 2-byte stores spread over banks
-constexpr int H_SBO = 16 * H_LBO;                 // 8-window group stride of the h operand (K = 128 -> 16 core matrices)
-constexpr int WHH_IMG_HALFS = G * H;              // one [384 x 128] fp16 image
-constexpr int WHH_SBO = (H / 8) * W_LBO;          // 2048
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int WG = 8;                             // windows per window group == rows of one core matrix
+constexpr int H_LBO = 144;                        // k-group stride of h / y images: 128 B core matrix + 16 B pad,
+                                                  // so the gate threads' 2-byte stores spread over all banks
+constexpr int YBLK = 16 * H_LBO;                  // 2304 B: [8 windows x 128 k] fp16 image of one direction
+constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)
+constexpr int GI_ROW_BYTES = G * 4;               // 1536 B: gi of one (window, t, direction)
+
+__host__ __device__ constexpr int64_t yimg_block(int64_t wg, int t, int W, int part) { return ((wg * W + t) * 2 + part) * (int64_t)YROW; }
 
 // ---------------------------------------------------------------------------------------------
-// Bulk input projection on tensor cores.
-// grid = (row-tile workers, 6 gate blocks); each CTA keeps its [128 x Kp] weight block (hi, lo) in
-// shared memory and walks over NT-row activation tiles.
+// uint8 pileup -> fp16 operand image (once per batch; predict_gpu.py:97 does this cast on the host)
 // ---------------------------------------------------------------------------------------------
-template <typename TA, int NT>
-__global__ void __launch_bounds__(256, 1)
-tc_projection_kernel(const TA* __restrict__ a, int64_t a_batch_stride, int64_t a_row_stride, int rows_per_window,
-                     int64_t M, int K, int Kp,
-                     const __half* __restrict__ w_img,      // [6 blocks][hi, lo][128 * Kp] core-matrix images
-                     const float* __restrict__ bias,        // [768]
-                     const float* __restrict__ inv_scale,   // [6]  2^-(kw [+10])
-                     float* __restrict__ gi)                // [M, 768]
+__global__ void __launch_bounds__(256)
+pileup_to_operand_image_kernel(const uint8_t* __restrict__ images, int64_t B, int T, int F, int Kp, __half* __restrict__ ximg, int64_t n_wg)
 {
-    constexpr bool kSplitA = sizeof(TA) == 4;               // fp32 activations need a lo term; uint8 is exact
+    const int kg = Kp >> 3;
+    const int64_t total = n_wg * T * kg * WG;               // one 16-byte chunk (8 k of one window) per thread
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(e % WG);
+        const int g8 = (int)((e / WG) % kg);
+        const int64_t rest = e / (WG * kg);
+        const int t = (int)(rest % T);
+        const int64_t wg = rest / T;
+        const int64_t b = wg * WG + w;
+        __align__(16) __half v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = g8 * 8 + i;
+            v[i] = __float2half_rn((b < B && k < F) ? (float)images[(b * T + t) * F + k] : 0.f);
+        }
+        *reinterpret_cast<int4*>(ximg + e * 8) = *reinterpret_cast<const int4*>(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Input projection  gi'[m, 0:768] = scale_row * (A[m, :] . Wcat^T) + bias_row
+// grid = (workers, 6 gate blocks).  The CTA's [128 x Kp] weight block (hi, lo) is TMEM-resident;
+// a tile is 64 data rows = 8 windows x 8 consecutive columns, staged by bulk copies.
+// Warps 0-3: epilogue (TMEM lane quarter = warp).  Warp 4: MMA issuer.  Warp 5: tile loader.
+// The epilogue folds the bias sums and the -log2(e) factors of the gate nonlinearities into gi'
+// (see tc_recurrence_kernel), so gi' is NOT the plain pre-activation of the fp32 engine.
+// ---------------------------------------------------------------------------------------------
+constexpr int PROJ_THREADS = 192;
+constexpr int PROJ_NT = 64;
+constexpr int PROJ_STAGES = 2;
+constexpr int PROJ_W_COL0 = 128;
+
+template <bool kSplitA>
+__global__ void __launch_bounds__(PROJ_THREADS, 1)
+tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, int64_t in_t_stride, int64_t in_part_stride,
+                     int blk_bytes, int lbo, int Kp, int64_t n_wg, int W,
+                     const uint32_t* __restrict__ w_tmem,    // [6][hi, lo][128][Kp/2] packed fp16 pairs
+                     const float* __restrict__ scale_row,    // [768]
+                     const float* __restrict__ bias_row,     // [768]
+                     float* __restrict__ gi)                 // [(b * W + t), 768]
+{
+    constexpr int PARTS = kSplitA ? 2 : 1;
     extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t part_bytes = 8u * blk_bytes;              // 8 row groups (columns t0..t0+7)
+    const uint32_t stage_bytes = PARTS * part_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + PROJ_STAGES * stage_bytes);
+    uint64_t* a_empty = a_full + PROJ_STAGES;
+    uint64_t* acc_full = a_empty + PROJ_STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int blk = blockIdx.y;
-    const int kg = Kp >> 3;                                  // 16-byte k groups per row
-    const uint32_t w_bytes = 128u * Kp * 2u;                 // one weight image
-    const uint32_t a_bytes = (uint32_t)NT * Kp * 2u;         // one activation image
-    const uint32_t sbo = (uint32_t)kg * 128u;
-    uint8_t* w_hi = smem;
-    uint8_t* w_lo = smem + w_bytes;
-    uint8_t* a_hi = smem + 2 * w_bytes;
-    uint8_t* a_lo = a_hi + a_bytes;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(a_lo + (kSplitA ? a_bytes : 0));
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-
-    {   // weight block: straight copy of the pre-packed image
-        const int4* src = reinterpret_cast<const int4*>(w_img + (size_t)blk * 2 * 128 * Kp);
-        int4* dst = reinterpret_cast<int4*>(w_hi);
-        for (uint32_t i = tid; i < 2 * w_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    const int kwords = Kp >> 1;
+    if (tid == 0) {
+        for (int i = 0; i < PROJ_STAGES; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
+        tc::mbar_fence_init();
     }
-    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
     __syncwarp();
-    if (warp == 0) tc::tmem_alloc(tmem_slot, NT < 32 ? 32 : NT);
-    tc::fence_proxy_async_smem();
+    if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t idesc = tc::idesc_f16_f32(128, NT);
-    const float inv = inv_scale[blk];
-    const float my_bias = bias[blk * 128 + (warp & 3) * 32 + lane];
-    const int ksteps = Kp >> 4;
-    uint32_t phase = 0;
-
-    const int64_t n_tiles = (M + NT - 1) / NT;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * NT;
-        // ---- stage the activation tile as fp16 hi (/lo) core matrices ----
-        for (int e = tid; e < NT * kg; e += blockDim.x) {
-            const int r = e / kg, g8 = e - r * kg;
-            const int64_t m = row0 + r;
-            float v[8];
+    if (warp < 4) {   // weight block -> TMEM, thread = gate row
+        const int row = warp * 32 + lane;
+        for (int term = 0; term < 2; ++term) {
+            const uint32_t* src = w_tmem + (((size_t)blk * 2 + term) * 128 + row) * kwords;
+            for (int c = 0; c < kwords; c += 16) {
+                uint32_t r[16];
+                const uint4* p = reinterpret_cast<const uint4*>(src + c);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-            if (m < M) {
-                const int64_t b = m / rows_per_window, t = m - b * rows_per_window;
-                const TA* src = a + b * a_batch_stride + t * a_row_stride + g8 * 8;
-                if constexpr (kSplitA) {
-                    if (g8 * 8 + 8 <= K) {
-                        float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
-                        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) if (g8 * 8 + i < K) v[i] = (float)src[i];
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) if (g8 * 8 + i < K) v[i] = (float)src[i];
-                }
+                for (int v = 0; v < 4; ++v) { const uint4 x = p[v]; r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + PROJ_W_COL0 + term * kwords + c, r);
             }
-            const uint32_t off = (uint32_t)(r >> 3) * sbo + (uint32_t)g8 * 128u + (uint32_t)(r & 7) * 16u;
-            __half hi[8], lo[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if constexpr (kSplitA) tc::split_f16(v[i] * ACT_SCALE, hi[i], lo[i]);
-                else hi[i] = __float2half_rn(v[i]);
-            }
-            *reinterpret_cast<int4*>(a_hi + off) = *reinterpret_cast<int4*>(hi);
-            if constexpr (kSplitA) *reinterpret_cast<int4*>(a_lo + off) = *reinterpret_cast<int4*>(lo);
         }
-        tc::fence_proxy_async_smem();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (warp == 0) {
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+
+    const int tiles_t = (W + 7) >> 3;
+    const int64_t n_tiles = n_wg * tiles_t;
+    if (warp == 5) {
+        // ===================== loader =====================
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int stage = it % PROJ_STAGES;
+            if (it >= PROJ_STAGES) tc::mbar_wait(a_empty + stage, (uint32_t)((it / PROJ_STAGES - 1) & 1));
+            const int64_t wg = tile / tiles_t;
+            const int t0 = (int)(tile % tiles_t) * 8;
+            const int valid = min(8, W - t0);
+            if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(valid * PARTS * blk_bytes));
+            __syncwarp();
+            if (lane < 8 * PARTS) {
+                const int tl = lane & 7, part = lane >> 3;
+                if (tl < valid)
+                    tc::bulk_g2s(smem + stage * stage_bytes + part * part_bytes + tl * blk_bytes,
+                                 in_base + wg * in_wg_stride + (int64_t)(t0 + tl) * in_t_stride + part * in_part_stride,
+                                 (uint32_t)blk_bytes, a_full + stage);
+            }
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
+        const int ksteps = Kp >> 4;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int stage = it % PROJ_STAGES, acc = it & 1;
+            tc::mbar_wait(a_full + stage, (uint32_t)((it / PROJ_STAGES) & 1));
+            if (it >= 2) tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1));
             tc::tc_fence_after();
             if (tc::elect_one()) {
-                const uint64_t whi = tc::smem_desc(tc::smem_u32(w_hi), W_LBO, sbo), wlo = tc::smem_desc(tc::smem_u32(w_lo), W_LBO, sbo);
-                const uint64_t ahi = tc::smem_desc(tc::smem_u32(a_hi), W_LBO, sbo), alo = tc::smem_desc(tc::smem_u32(a_lo), W_LBO, sbo);
-                uint32_t acc = 0;
-                const int terms = kSplitA ? 3 : 2;
-                for (int term = 0; term < terms; ++term) {
-                    const uint64_t wa = term == 1 ? wlo : whi;
-                    const uint64_t aa = term == 2 ? alo : ahi;
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        tc::mma_f16_ss(tmem, wa + (uint64_t)(ks * 16), aa + (uint64_t)(ks * 16), idesc, acc);
-                        acc = 1;
-                    }
-                }
-                tc::mma_commit(bar);
+                const uint32_t sbase = tc::smem_u32(smem + stage * stage_bytes);
+                const uint64_t d_hi = tc::smem_desc(sbase, lbo, blk_bytes);
+                const uint64_t d_lo = tc::smem_desc(sbase + part_bytes, lbo, blk_bytes);
+                const uint32_t a_hi = tmem + PROJ_W_COL0, a_lo = a_hi + kwords;
+                const uint32_t d = tmem + acc * PROJ_NT;
+                uint32_t accum = 0;
+                for (int ks = 0; ks < ksteps; ++ks) { tc::mma_f16_ts(d, a_hi + ks * 8, d_hi + (uint64_t)(ks * 2 * lbo / 16), idesc, accum); accum = 1; }
+                for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16_ts(d, a_lo + ks * 8, d_hi + (uint64_t)(ks * 2 * lbo / 16), idesc, 1);
+                if (kSplitA)
+                    for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16_ts(d, a_hi + ks * 8, d_lo + (uint64_t)(ks * 2 * lbo / 16), idesc, 1);
+                tc::mma_commit(a_empty + stage);
+                tc::mma_commit(acc_full + acc);
             }
             __syncwarp();
         }
-        tc::mbar_wait(bar, phase);
-        phase ^= 1;
-        tc::tc_fence_after();
-        // ---- epilogue: warp w reads lane quarter w%4, column half w/4 ----
-        constexpr int COLS = NT / 2;
-        const int c0 = (warp >> 2) * COLS;
-        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
-        float* out = gi + blk * 128 + (warp & 3) * 32 + lane;
+    } else {
+        // ===================== epilogue =====================
+        const int row = blk * 128 + warp * 32 + lane;
+        const float sc = scale_row[row], bi = bias_row[row];
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int64_t wg = tile / tiles_t;
+            const int t0 = (int)(tile % tiles_t) * 8;
+            tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1));
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
 #pragma unroll
-        for (int c = 0; c < COLS; c += 8) {
-            float v[8];
-            tc::tmem_ld8(taddr + c, v);
-            tc::tmem_ld_wait();
+            for (int c16 = 0; c16 < PROJ_NT; c16 += 16) {
+                float v[16];
+                tc::tmem_ld16(taddr + c16, v);
+                tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t m = row0 + c0 + c + i;
-                if (m < M) out[m * (2 * G)] = fmaf(v[i], inv, my_bias);
+                for (int i = 0; i < 16; ++i) {
+                    const int c = c16 + i, t = t0 + (c >> 3);
+                    const int64_t b = wg * WG + (c & 7);
+                    if (t < W) gi[(b * W + t) * (2 * G) + row] = fmaf(v[i], sc, bi);
+                }
             }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty + acc);
         }
-        tc::tc_fence_before();
-        __syncthreads();
     }
-    if (warp == 0) tc::tmem_dealloc(tmem, NT < 32 ? 32 : NT);
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Recurrence on tensor cores.  One CTA = N windows x one direction x W dependent steps of one
-// layer.
-//   * W_hh (fp16 hi and lo, 3 gate blocks x 128 rows x 128 k) is loaded ONCE into tensor memory
-//     and used as the TMEM-resident A operand of every MMA (384 of the 512 columns).  With A in
-//     shared memory each M=128,K=16 MMA would re-read 4 KB of weights (32 cycles of smem
-//     bandwidth) regardless of N; from TMEM the MMA runs at the tensor rate for small N.
-//   * the state h lives in registers (fp32, one hidden unit per thread) and is re-published each
-//     step as the fp16 hi/lo B operand in shared memory (K-major core matrices).
-//   * accumulators r | z | n : TMEM columns [0, 3N).
-// Warps 0..7 are gate warps: (warp w, lane l) owns hidden unit j = 32 (w%4) + l (== its TMEM lane)
-// for windows [(w/4) N/2, (w/4+1) N/2).  Warp 8 issues the MMAs.  Handshake per step:
-//   gate warps --h_ready (8 warp arrivals)--> MMA warp --tcgen05.commit acc_ready--> gate warps
+// Recurrence.  One CTA = N windows x one direction x W dependent steps of one layer.
+//   * W_hh (fp16 hi and lo, 3 gate blocks x 128 rows x 128 k) is loaded ONCE into TMEM and is the
+//     A operand of every MMA (384 of the 512 columns); accumulators r | z | n at columns [0, 3N).
+//   * the state h lives in registers (fp32 * 2^10, one hidden unit per thread) and is re-published
+//     each step as the fp16 hi/lo B operand image in shared memory; that same image is the layer's
+//     output for column t and is bulk-stored to yimg by the store warp.
+//   * gi' rows of the step are prefetched GI_STAGES steps ahead into shared memory by bulk copies.
+// gi' (from tc_projection_kernel) already contains, per gate row,
+//     r, z rows:  -log2e * (W_i. x + b_i. + b_h.)        n rows:  -2 log2e * (W_in x + b_in)
+// so that   r = 1 / (1 + 2^(gi'_r + acc_r * inv_r)),  z likewise,
+//           n * 2^10 = 2048 / (1 + 2^(gi'_n + r * (acc_n * inv_n + b_hn'))) - 1024     (tanh)
+//           h' = n + z (h - n).
+// Warps 0..15: gate warps; (warp w, lane l) owns hidden unit j = 32 (w%4) + l (== its TMEM lane)
+// for windows [(w/4) N/4, (w/4+1) N/4).  Warp 16: MMA issuer.  Warp 17: gi loader.  Warp 18: y store.
 // ---------------------------------------------------------------------------------------------
 constexpr int REC_GATE_WARPS = 16;
-constexpr int REC_TC_THREADS = (REC_GATE_WARPS + 1) * 32;
-constexpr int TMEM_W_COL0 = 128;                  // weight columns start here (accumulators below)
+constexpr int REC_TC_THREADS = (REC_GATE_WARPS + 3) * 32;
+constexpr int REC_W_COL0 = 128;                   // weight columns start here (accumulators below)
 constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate block][row][k pair]
-
-__device__ __forceinline__ float ld_nc_f32(const float* p) {   // asm volatile: stays where it is written
-    float v;
-    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
+constexpr int GI_STAGES = 4;
 
 template <int N>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
-tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih already added)
+tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t), 768]
                      const uint32_t* __restrict__ whh_tmem, // [2 dirs][hi, lo][3][128][64] packed fp16 pairs
-                     const float* __restrict__ b_hh,        // [2][384]
-                     const float* __restrict__ inv_scale,   // [2]  2^-(kw + 10)
-                     const float* __restrict__ h_in,        // [B, 2, 128] or nullptr
-                     float* __restrict__ h_out,             // [B, 2, 128]
-                     float* __restrict__ y,                 // [B*W, 256] fp32, or nullptr
-                     __half* __restrict__ y_hi,             // [B*W, 256] fp16 split of y * 2^10, or nullptr
-                     __half* __restrict__ y_lo,
+                     const float* __restrict__ gate_consts, // [2 dirs][4][128]: inv_r', inv_z', inv_n', b_hn'  (per unit)
+                     const float* __restrict__ h_in,        // [B, 2, 128] fp32 or nullptr (zeros)
+                     float* __restrict__ h_out,             // [B, 2, 128] fp32
+                     uint8_t* __restrict__ yimg,            // operand image of the layer output
                      int64_t B, int W)
 {
-    static_assert(N == 16 || N == 32, "N windows per CTA (3N accumulator columns must stay below TMEM_W_COL0)");
+    static_assert(N == 16 || N == 32, "N windows per CTA (3N accumulator columns must stay below REC_W_COL0)");
     constexpr int NW = N / 4;                                // windows per gate thread
-    constexpr uint32_t HB_BYTES = (N / 8) * H_SBO;           // one h operand image
+    constexpr int NG = N / WG;                               // window groups per CTA
+    constexpr uint32_t HB_BYTES = NG * YBLK;                 // one h operand image (hi or lo)
+    constexpr uint32_t GI_STAGE_BYTES = N * GI_ROW_BYTES;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* h_hi = smem;
     uint8_t* h_lo = smem + HB_BYTES;
-    uint64_t* acc_ready = reinterpret_cast<uint64_t*>(h_lo + HB_BYTES);   // [3]: r, z, n blocks
+    uint8_t* gi_s = smem + 2 * HB_BYTES;
+    uint64_t* acc_ready = reinterpret_cast<uint64_t*>(gi_s + GI_STAGES * GI_STAGE_BYTES);   // [3]: r, z, n blocks
     uint64_t* h_ready = acc_ready + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
+    uint64_t* h_free = h_ready + 1;
+    uint64_t* gi_full = h_free + 1;
+    uint64_t* gi_empty = gi_full + GI_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gi_empty + GI_STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
     const int64_t b0 = (int64_t)blockIdx.x * N;
+    const int t_first = dir ? W - 1 : 0, dt = dir ? -1 : 1;
 
     if (tid == 0) {
-        tc::mbar_init(acc_ready + 0, 1); tc::mbar_init(acc_ready + 1, 1); tc::mbar_init(acc_ready + 2, 1);
+        for (int i = 0; i < 3; ++i) tc::mbar_init(acc_ready + i, 1);
         tc::mbar_init(h_ready, REC_GATE_WARPS);
+        tc::mbar_init(h_free, 1);
+        for (int i = 0; i < GI_STAGES; ++i) { tc::mbar_init(gi_full + i, 1); tc::mbar_init(gi_empty + i, REC_GATE_WARPS); }
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -232,13 +282,39 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == REC_GATE_WARPS) {
+    if (warp == REC_GATE_WARPS + 1) {
+        // ===================== gi loader: bulk copies, GI_STAGES steps ahead =====================
+        __syncthreads();
+        const float* src0 = gi + ((b0 + lane) * W) * (int64_t)(2 * G) + dir * G;
+        for (int s = 0, t = t_first; s < W; ++s, t += dt) {
+            const int stage = s % GI_STAGES;
+            if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
+            if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, GI_STAGE_BYTES);
+            __syncwarp();
+            if (lane < N) tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + lane * GI_ROW_BYTES, src0 + (int64_t)t * (2 * G), GI_ROW_BYTES, gi_full + stage);
+        }
+    } else if (warp == REC_GATE_WARPS + 2) {
+        // ===================== y store: the h image of step s is the layer output at column t_s ====
+        __syncthreads();
+        for (int s = 0, t = t_first; s < W; ++s, t += dt) {
+            tc::mbar_wait(h_ready, (uint32_t)(s & 1));
+            if (lane < 2 * NG) {
+                const int g = lane >> 1, part = lane & 1;
+                tc::bulk_s2g(yimg + yimg_block(b0 / WG + g, t, W, part) + dir * YBLK, (part ? h_lo : h_hi) + g * YBLK, YBLK);
+                tc::bulk_commit();
+                tc::bulk_wait_read0();
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(h_free);
+        }
+        if (lane < 2 * NG) tc::bulk_wait0();
+    } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
         const uint32_t idesc = tc::idesc_f16_f32(128, N);
-        const uint64_t hhi_desc = tc::smem_desc(tc::smem_u32(h_hi), H_LBO, H_SBO);
-        const uint64_t hlo_desc = tc::smem_desc(tc::smem_u32(h_lo), H_LBO, H_SBO);
+        const uint64_t hhi_desc = tc::smem_desc(tc::smem_u32(h_hi), H_LBO, YBLK);
+        const uint64_t hlo_desc = tc::smem_desc(tc::smem_u32(h_lo), H_LBO, YBLK);
         for (int s = 0; s < W; ++s) {
             if (s > 0) {
                 tc::mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
@@ -249,12 +325,11 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
                 for (int gb = 0; gb < 3; ++gb) {             // gate blocks r, z, n
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {   // (W_hi,h_hi) (W_lo,h_hi) (W_hi,h_lo)
-                        const uint32_t a_col = tmem + TMEM_W_COL0 + ((term == 1 ? 3 : 0) + gb) * 64;
+                        const uint32_t a_col = tmem + REC_W_COL0 + ((term == 1 ? 3 : 0) + gb) * 64;
                         const uint64_t bd = term == 2 ? hlo_desc : hhi_desc;
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            tc::mma_f16_ts(tmem + gb * N, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc,
-                                           (term | ks) != 0);
+                            tc::mma_f16_ts(tmem + gb * N, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
                     }
                     tc::mma_commit(acc_ready + gb);          // gates start on r while z, n still run
                 }
@@ -276,80 +351,71 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
                     uint32_t r[16];
                     const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64 + c);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const uint4 x = p[v];
-                        r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
-                    }
-                    tc::tmem_st16(tmem + ((uint32_t)(q * 32) << 16) + TMEM_W_COL0 + (term * 3 + gb) * 64 + c, r);
+                    for (int v = 0; v < 4; ++v) { const uint4 x = p[v]; r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                    tc::tmem_st16(tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + c, r);
                 }
             }
             tc::tmem_st_wait();
         }
-        const float inv = inv_scale[dir];
-        const float bhr = b_hh[dir * G + j], bhz = b_hh[dir * G + H + j], bhn = b_hh[dir * G + 2 * H + j];
-        // gi / y rows of windows past B exist in the (padded) workspace, so only h_in / h_out,
-        // which may be caller tensors of exactly B windows, need guarding.
-        float h_own[NW];
+        const float* gc = gate_consts + (size_t)dir * 4 * H + j;
+        const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
+        float h_own[NW];                                     // h * 2^10
         uint32_t h_off[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
             const int64_t b = b0 + win0 + i;
-            h_own[i] = (h_in != nullptr && b < B) ? h_in[(b * 2 + dir) * H + j] : 0.f;
-            h_off[i] = tc::core_offset(win0 + i, j, H_LBO, H_SBO);
+            h_own[i] = (h_in != nullptr && b < B) ? h_in[(b * 2 + dir) * H + j] * ACT_SCALE : 0.f;
+            h_off[i] = tc::core_offset(win0 + i, j, H_LBO, YBLK);
             __half hi, lo;
-            tc::split_f16(h_own[i] * ACT_SCALE, hi, lo);
+            tc::split_f16(h_own[i], hi, lo);
             *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
             *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
         }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
-        __syncthreads();                                     // pairs with the MMA warp's second barrier
+        __syncthreads();                                     // pairs with the other roles' barrier
 
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
-        const int wstride_gi = W * 2 * G, wstride_y = W * 2 * H;   // elements between consecutive windows
-        const float* gi_thr = gi + (b0 + win0) * (int64_t)wstride_gi + dir * G + j;
-        const int64_t y_thr = (b0 + win0) * (int64_t)wstride_y + dir * H + j;
-        int t = dir ? W - 1 : 0;
-        const int dt = dir ? -1 : 1;
-        for (int s = 0; s < W; ++s, t += dt) {
-            // this step's input projections: issued now, consumed after the MMA waits
-            float gir[NW], giz[NW], gin[NW];
-            const float* gp = gi_thr + t * (2 * G);
-#pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                const float* p = gp + i * wstride_gi;
-                gir[i] = ld_nc_f32(p); giz[i] = ld_nc_f32(p + H); gin[i] = ld_nc_f32(p + 2 * H);
-            }
+        for (int s = 0; s < W; ++s) {
+            const int stage = s % GI_STAGES;
             const uint32_t par = (uint32_t)(s & 1);
+            float gir[NW], giz[NW], gin[NW];
+            tc::mbar_wait(gi_full + stage, (uint32_t)((s / GI_STAGES) & 1));
+            {
+                const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + win0 * G + j;
+#pragma unroll
+                for (int i = 0; i < NW; ++i) { gir[i] = gs[i * G]; giz[i] = gs[i * G + H]; gin[i] = gs[i * G + 2 * H]; }
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(gi_empty + stage);
             float r[NW], z[NW], a[NW];
             tc::mbar_wait(acc_ready + 0, par);
             tc::tc_fence_after();
             if constexpr (NW == 4) tc::tmem_ld4(taddr, a); else tc::tmem_ld8(taddr, a);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < NW; ++i) r[i] = tc::sigmoid_fast(gir[i] + fmaf(a[i], inv, bhr));
+            for (int i = 0; i < NW; ++i) r[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_r, gir[i])));
             tc::mbar_wait(acc_ready + 1, par);
             tc::tc_fence_after();
             if constexpr (NW == 4) tc::tmem_ld4(taddr + N, a); else tc::tmem_ld8(taddr + N, a);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < NW; ++i) z[i] = tc::sigmoid_fast(giz[i] + fmaf(a[i], inv, bhz));
+            for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, giz[i])));
+            if (s > 0) tc::mbar_wait(h_free, (uint32_t)((s - 1) & 1));   // previous image has been read by the store
             tc::mbar_wait(acc_ready + 2, par);
             tc::tc_fence_after();
             if constexpr (NW == 4) tc::tmem_ld4(taddr + 2 * N, a); else tc::tmem_ld8(taddr + 2 * N, a);
             tc::tmem_ld_wait();
-            const int64_t yo = y_thr + t * (2 * H);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
-                const float n = tc::tanh_fast(gin[i] + r[i] * fmaf(a[i], inv, bhn));
-                const float hn = fmaf(z[i], h_own[i] - n, n);   // (1 - z) n + z h
+                const float e = tc::ex2_approx(fmaf(r[i], fmaf(a[i], inv_n, bhn), gin[i]));
+                const float n = fmaf(2.0f * ACT_SCALE, tc::rcp_approx(1.0f + e), -ACT_SCALE);   // tanh * 2^10
+                const float hn = fmaf(z[i], h_own[i] - n, n);                                   // (1 - z) n + z h
                 h_own[i] = hn;
                 __half hi, lo;
-                tc::split_f16(hn * ACT_SCALE, hi, lo);
+                tc::split_f16(hn, hi, lo);
                 *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
                 *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
-                if (y != nullptr) y[yo + i * wstride_y] = hn;
-                if (y_hi != nullptr) { y_hi[yo + i * wstride_y] = hi; y_lo[yo + i * wstride_y] = lo; }
             }
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
@@ -358,7 +424,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
         }
 #pragma unroll
         for (int i = 0; i < NW; ++i)
-            if (b0 + win0 + i < B) h_out[((b0 + win0 + i) * 2 + dir) * H + j] = h_own[i];
+            if (b0 + win0 + i < B) h_out[((b0 + win0 + i) * 2 + dir) * H + j] = h_own[i] * ACT_SCALE_INV;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -366,29 +432,178 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // [B*W, 768] (b_ih 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Heads + softmax + accumulate (predict_gpu.py:137-149) on tensor cores.
+// Roles are swapped here: A = activations (M = 128 positions = 8 windows x 16 columns, straight
+// from yimg), B = the 16 head rows (5 base + 11 rle), so every thread ends up with all 16 logits
+// of ONE position in registers and the two softmaxes need no cross-thread traffic.
+// ---------------------------------------------------------------------------------------------
+constexpr int HEADS_THREADS = 192;
+constexpr int HEADS_WIMG = NCLS * 2 * H * 2;     // one [16 x 256] fp16 image (dense core matrices): 8192 B
+
+__global__ void __launch_bounds__(HEADS_THREADS, 1)
+tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W, int T, int col0,
+                const __half* __restrict__ w_img,     // [hi, lo][16 x 256] core-matrix image, LBO 128 / SBO 4096
+                const float* __restrict__ b_head,     // [16]
+                float inv_scale,
+                float* __restrict__ p_base, float* __restrict__ p_rle)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t PART_BYTES = 16 * YROW;                  // 16 columns of one window group
+    uint8_t* a_img = smem;                                      // [hi, lo][16 row groups][YROW]
+    uint8_t* w_s = smem + 2 * PART_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(w_s + 2 * HEADS_WIMG);
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* acc_full = a_empty + 1;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < 2 * HEADS_WIMG / 16; i += blockDim.x)
+        reinterpret_cast<int4*>(w_s)[i] = reinterpret_cast<const int4*>(w_img)[i];
+    if (tid == 0) {
+        tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1); tc::mbar_init(acc_full, 1); tc::mbar_init(acc_empty, 4);
+        tc::mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 4) tc::tmem_alloc(tmem_slot, 32);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int tiles_t = (W + 15) >> 4;
+    const int64_t n_tiles = n_wg * tiles_t;
+
+    if (warp == 5) {
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            if (it > 0) tc::mbar_wait(a_empty, (uint32_t)((it - 1) & 1));
+            const int64_t wg = tile / tiles_t;
+            const int t0 = (int)(tile % tiles_t) * 16;
+            const int valid = min(16, W - t0);
+            if (lane == 0) tc::mbar_arrive_expect_tx(a_full, (uint32_t)(valid * 2 * YROW));
+            __syncwarp();
+            const int tl = lane & 15, part = lane >> 4;
+            if (tl < valid) tc::bulk_g2s(a_img + part * PART_BYTES + tl * YROW, yimg + yimg_block(wg, t0 + tl, W, part), YROW, a_full);
+        }
+    } else if (warp == 4) {
+        const uint32_t idesc = tc::idesc_f16_f32(128, NCLS);
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            tc::mbar_wait(a_full, (uint32_t)(it & 1));
+            if (it > 0) tc::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint64_t a_hi = tc::smem_desc(tc::smem_u32(a_img), H_LBO, YROW), a_lo = tc::smem_desc(tc::smem_u32(a_img + PART_BYTES), H_LBO, YROW);
+                const uint64_t w_hi = tc::smem_desc(tc::smem_u32(w_s), 128, 4096), w_lo = tc::smem_desc(tc::smem_u32(w_s + HEADS_WIMG), 128, 4096);
+                uint32_t accum = 0;
+                for (int ks = 0; ks < 16; ++ks) { tc::mma_f16_ss(tmem, a_hi + (uint64_t)(ks * 2 * H_LBO / 16), w_hi + (uint64_t)(ks * 16), idesc, accum); accum = 1; }
+                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(tmem, a_lo + (uint64_t)(ks * 2 * H_LBO / 16), w_hi + (uint64_t)(ks * 16), idesc, 1);
+                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(tmem, a_hi + (uint64_t)(ks * 2 * H_LBO / 16), w_lo + (uint64_t)(ks * 16), idesc, 1);
+                tc::mma_commit(a_empty);
+                tc::mma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        float bias[NCLS];
+#pragma unroll
+        for (int c = 0; c < NCLS; ++c) bias[c] = b_head[c];
+        const int row = warp * 32 + lane;                       // position within the tile: (column, window)
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int64_t wg = tile / tiles_t;
+            const int t = (int)(tile % tiles_t) * 16 + (row >> 3);
+            const int64_t b = wg * WG + (row & 7);
+            tc::mbar_wait(acc_full, (uint32_t)(it & 1));
+            tc::tc_fence_after();
+            float v[NCLS];
+            tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty);
+            if (t < W && b < B) {
+                float mb = -INFINITY, mr = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < NCLS; ++c) {
+                    v[c] = fmaf(v[c], inv_scale, bias[c]);
+                    if (c < NBASE) mb = fmaxf(mb, v[c]); else mr = fmaxf(mr, v[c]);
+                }
+                float sb = 0.f, sr = 0.f;
+#pragma unroll
+                for (int c = 0; c < NCLS; ++c) {
+                    v[c] = expf(v[c] - (c < NBASE ? mb : mr));
+                    if (c < NBASE) sb += v[c]; else sr += v[c];
+                }
+                float* pb = p_base + (b * T + col0 + t) * NBASE;
+                float* pr = p_rle + (b * T + col0 + t) * NRLE;
+#pragma unroll
+                for (int c = 0; c < NBASE; ++c) pb[c] += v[c] / sb;
+#pragma unroll
+                for (int c = 0; c < NRLE; ++c) pr[c] += v[NBASE + c] / sr;
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, 32);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
 struct TensorLayer {
-    __half* wih_img = nullptr;     // [6][hi, lo][128 * Kp]
-    float* wih_inv = nullptr;      // [6]
-    float* bih = nullptr;          // [768]
-    uint32_t* whh_tmem = nullptr;  // [2][hi, lo][3][128][64] packed fp16 pairs (TMEM A-operand image)
-    float* whh_inv = nullptr;      // [2]
-    float* bhh = nullptr;          // [2][384]
+    uint32_t* wih_tmem = nullptr;  // [6][hi, lo][128][Kp/2]
+    float* scale_row = nullptr;    // [768]  projection epilogue scale (2^-kw [2^-10]) * (-log2e | -2 log2e)
+    float* bias_row = nullptr;     // [768]  folded biases * (-log2e | -2 log2e)
+    uint32_t* whh_tmem = nullptr;  // [2][hi, lo][3][128][64]
+    float* gate_consts = nullptr;  // [2][4][128]
     int K = 0, Kp = 0;
 };
 
 struct TensorEngine {
     TensorLayer enc, dec;
-    float* w_head = nullptr;
+    __half* head_img = nullptr;    // [hi, lo][16 x 256]
     float* b_head = nullptr;
+    float head_inv = 1.f;
     int features = 0;
     int sm_count = 0;
-    int stages = 3;                // bit 0: tensor projection, bit 1: tensor recurrence (debug A/B switch)
-    // fp32 fallbacks for the A/B switch share the fp32 engine's weights (set by hb_api)
-    const float* f32_enc_wcat = nullptr; const float* f32_dec_wcat = nullptr;
-    const float* f32_enc_whh = nullptr;  const float* f32_dec_whh = nullptr;
 };
+
+struct TensorWorkspace {
+    float* gi;
+    uint8_t* yimg1;
+    uint8_t* yimg2;
+    __half* ximg;
+    float* hid_a;
+    float* hid_b;
+    float* p_base;
+    float* p_rle;
+    size_t bytes;
+};
+
+inline TensorWorkspace tensor_carve(void* base, int64_t B, int T, int W, int Kp) {
+    TensorWorkspace ws{};
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        size_t o = off;
+        off += align_up(n);
+        return base ? static_cast<char*>(base) + o : nullptr;
+    };
+    const size_t Bp = ((size_t)B + 31) / 32 * 32;            // window tiles of the kernels may run past B
+    const size_t Wp = (size_t)std::max(W, 0);
+    ws.gi = reinterpret_cast<float*>(take(Bp * Wp * 2 * G * sizeof(float)));
+    ws.yimg1 = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
+    ws.yimg2 = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
+    ws.ximg = reinterpret_cast<__half*>(take(Bp / WG * (size_t)T * Kp * 16));
+    ws.hid_a = reinterpret_cast<float*>(take(Bp * 2 * H * sizeof(float)));
+    ws.hid_b = reinterpret_cast<float*>(take(Bp * 2 * H * sizeof(float)));
+    ws.p_base = reinterpret_cast<float*>(take((size_t)B * T * NBASE * sizeof(float)));
+    ws.p_rle = reinterpret_cast<float*>(take((size_t)B * T * NRLE * sizeof(float)));
+    ws.bytes = off;
+    return ws;
+}
 
 namespace detail {
 
@@ -402,22 +617,11 @@ inline int pow2_scale_exponent(const float* w, size_t n) {
     return e;
 }
 
-// [rows x K] fp32 -> hi and lo fp16 core-matrix images (K-major, LBO 128, SBO (Kp/8)*128), per 128-row block
-inline void pack_split_image(const float* w, int rows, int K, int Kp, float scale, __half* hi, __half* lo) {
-    const int sbo = (Kp / 8) * 128;
-    const size_t block_halfs = (size_t)128 * Kp;
-    for (size_t i = 0; i < (size_t)rows * Kp; ++i) hi[i] = lo[i] = __float2half_rn(0.f);
-    for (int r = 0; r < rows; ++r) {
-        const int blk = r / 128, rr = r % 128;
-        for (int k = 0; k < K; ++k) {
-            const float v = w[(size_t)r * K + k] * scale;
-            const __half h = __float2half_rn(v);
-            const __half l = __float2half_rn(v - __half2float(h));
-            const size_t off = blk * block_halfs + tc::core_offset(rr, k, 128, sbo) / 2;
-            hi[off] = h;
-            lo[off] = l;
-        }
-    }
+inline void split_pair_words(float v0, float v1, uint32_t* hi_word, uint32_t* lo_word) {
+    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+    const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+    *hi_word = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    *lo_word = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
 }
 
 template <typename T>
@@ -431,67 +635,62 @@ inline bool to_device(T** dst, const std::vector<T>& src, char* err, size_t errl
     return true;
 }
 
+// TMEM A-operand image of a [rows x K] matrix block: lane = row, 32-bit column c holds k = 2c (low half), 2c+1
 inline bool pack_layer(const hb_gru_weights& g, int K, bool activations_scaled, TensorLayer* L, char* err, size_t errlen) {
-    const int Kp = (K + 15) / 16 * 16;
+    const int Kp = (K + 31) / 32 * 32;
+    const int kwords = Kp / 2;
     L->K = K;
     L->Kp = Kp;
-    const size_t blk_halfs = (size_t)128 * Kp;
-    std::vector<__half> wih(6 * 2 * blk_halfs);
-    std::vector<float> wih_inv(6), bih(2 * G), whh_inv(2), bhh(2 * G);
-    std::vector<uint32_t> whh((size_t)2 * WHH_TMEM_WORDS);
-    std::vector<__half> hi, lo;
+    std::vector<uint32_t> wih((size_t)6 * 2 * 128 * kwords, 0u), whh((size_t)2 * WHH_TMEM_WORDS, 0u);
+    std::vector<float> scale_row(2 * G), bias_row(2 * G), consts((size_t)2 * 4 * H);
     for (int d = 0; d < 2; ++d) {
-        {   // W_ih: 3 blocks of 128 rows
-            const int e = pow2_scale_exponent(g.weight_ih[d], (size_t)G * K);
-            hi.assign((size_t)G * Kp, __half());
-            lo.assign((size_t)G * Kp, __half());
-            pack_split_image(g.weight_ih[d], G, K, Kp, ldexpf(1.f, e), hi.data(), lo.data());
-            for (int b = 0; b < 3; ++b) {
-                std::memcpy(&wih[(size_t)(d * 3 + b) * 2 * blk_halfs], &hi[b * blk_halfs], blk_halfs * sizeof(__half));
-                std::memcpy(&wih[(size_t)(d * 3 + b) * 2 * blk_halfs + blk_halfs], &lo[b * blk_halfs], blk_halfs * sizeof(__half));
-                wih_inv[d * 3 + b] = ldexpf(1.f, -e) * (activations_scaled ? ACT_SCALE_INV : 1.f);
+        const int e_ih = pow2_scale_exponent(g.weight_ih[d], (size_t)G * K);
+        const float s_ih = ldexpf(1.f, e_ih);
+        for (int r = 0; r < G; ++r) {
+            const int blk = d * 3 + r / 128, rr = r % 128;
+            for (int c = 0; c < kwords; ++c) {
+                const float v0 = 2 * c < K ? g.weight_ih[d][(size_t)r * K + 2 * c] * s_ih : 0.f;
+                const float v1 = 2 * c + 1 < K ? g.weight_ih[d][(size_t)r * K + 2 * c + 1] * s_ih : 0.f;
+                split_pair_words(v0, v1, &wih[(((size_t)blk * 2 + 0) * 128 + rr) * kwords + c],
+                                 &wih[(((size_t)blk * 2 + 1) * 128 + rr) * kwords + c]);
             }
+            // gate-dependent folding: r, z rows carry -log2e and both biases; n rows carry -2 log2e and b_in only
+            const bool is_n = r >= 2 * H;
+            const float f = is_n ? -2.0f * LOG2E : -LOG2E;
+            scale_row[d * G + r] = f * ldexpf(1.f, -e_ih) * (activations_scaled ? ACT_SCALE_INV : 1.f);
+            bias_row[d * G + r] = f * (g.bias_ih[d][r] + (is_n ? 0.f : g.bias_hh[d][r]));
         }
-        {   // W_hh: TMEM image, lane = row within the gate block, column c holds k = 2c (low half), 2c+1 (high)
-            const int e = pow2_scale_exponent(g.weight_hh[d], (size_t)G * H);
-            const float scale = ldexpf(1.f, e);
-            for (int gb = 0; gb < 3; ++gb)
-                for (int r = 0; r < 128; ++r)
-                    for (int c = 0; c < 64; ++c) {
-                        uint32_t word[2] = {0, 0};
-                        for (int half_idx = 0; half_idx < 2; ++half_idx) {
-                            const float v = g.weight_hh[d][(size_t)(gb * 128 + r) * H + 2 * c + half_idx] * scale;
-                            const __half hi_h = __float2half_rn(v);
-                            const __half lo_h = __float2half_rn(v - __half2float(hi_h));
-                            word[0] |= (uint32_t)__half_as_ushort(hi_h) << (16 * half_idx);
-                            word[1] |= (uint32_t)__half_as_ushort(lo_h) << (16 * half_idx);
-                        }
-                        for (int term = 0; term < 2; ++term)
-                            whh[(size_t)d * WHH_TMEM_WORDS + (((size_t)term * 3 + gb) * 128 + r) * 64 + c] = word[term];
-                    }
-            whh_inv[d] = ldexpf(1.f, -e) * ACT_SCALE_INV;
+        const int e_hh = pow2_scale_exponent(g.weight_hh[d], (size_t)G * H);
+        const float s_hh = ldexpf(1.f, e_hh);
+        for (int gb = 0; gb < 3; ++gb)
+            for (int r = 0; r < 128; ++r)
+                for (int c = 0; c < 64; ++c) {
+                    const float* row = g.weight_hh[d] + (size_t)(gb * 128 + r) * H;
+                    split_pair_words(row[2 * c] * s_hh, row[2 * c + 1] * s_hh,
+                                     &whh[(size_t)d * WHH_TMEM_WORDS + (((size_t)0 * 3 + gb) * 128 + r) * 64 + c],
+                                     &whh[(size_t)d * WHH_TMEM_WORDS + (((size_t)1 * 3 + gb) * 128 + r) * 64 + c]);
+                }
+        const float inv = ldexpf(1.f, -e_hh) * ACT_SCALE_INV;     // accumulator -> W_hh . h
+        for (int j = 0; j < H; ++j) {
+            consts[((size_t)d * 4 + 0) * H + j] = -LOG2E * inv;
+            consts[((size_t)d * 4 + 1) * H + j] = -LOG2E * inv;
+            consts[((size_t)d * 4 + 2) * H + j] = -2.0f * LOG2E * inv;
+            consts[((size_t)d * 4 + 3) * H + j] = -2.0f * LOG2E * g.bias_hh[d][2 * H + j];
         }
-        std::memcpy(&bih[d * G], g.bias_ih[d], G * sizeof(float));
-        std::memcpy(&bhh[d * G], g.bias_hh[d], G * sizeof(float));
     }
-    return to_device(&L->wih_img, wih, err, errlen) && to_device(&L->wih_inv, wih_inv, err, errlen) &&
-           to_device(&L->bih, bih, err, errlen) && to_device(&L->whh_tmem, whh, err, errlen) &&
-           to_device(&L->whh_inv, whh_inv, err, errlen) && to_device(&L->bhh, bhh, err, errlen);
+    return to_device(&L->wih_tmem, wih, err, errlen) && to_device(&L->scale_row, scale_row, err, errlen) &&
+           to_device(&L->bias_row, bias_row, err, errlen) && to_device(&L->whh_tmem, whh, err, errlen) &&
+           to_device(&L->gate_consts, consts, err, errlen);
 }
 
 inline void free_layer(TensorLayer* L) {
-    cudaFree(L->wih_img); cudaFree(L->wih_inv); cudaFree(L->bih);
-    cudaFree(L->whh_tmem); cudaFree(L->whh_inv); cudaFree(L->bhh);
+    cudaFree(L->wih_tmem); cudaFree(L->scale_row); cudaFree(L->bias_row); cudaFree(L->whh_tmem); cudaFree(L->gate_consts);
 }
 
-constexpr int PROJ_NT = 64;
-
-inline size_t projection_smem(int Kp, bool split_a) {
-    return (size_t)2 * 128 * Kp * 2 + (size_t)(split_a ? 2 : 1) * PROJ_NT * Kp * 2 + 64;
-}
-// the kernel allocates all 512 TMEM columns, so force one CTA per SM through the smem request
+inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 128; }
 template <int N>
-constexpr size_t recurrence_smem() { return (size_t)120 * 1024; }
+constexpr size_t recurrence_smem() { return (size_t)2 * (N / WG) * YBLK + (size_t)GI_STAGES * N * GI_ROW_BYTES + 256; }
+constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128; }
 
 }  // namespace detail
 
@@ -499,7 +698,7 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     if (!e) return;
     detail::free_layer(&e->enc);
     detail::free_layer(&e->dec);
-    cudaFree(e->w_head);
+    cudaFree(e->head_img);
     cudaFree(e->b_head);
     delete e;
 }
@@ -511,22 +710,36 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
     bool ok = detail::pack_layer(w->encoder, features, /*activations_scaled=*/false, &e->enc, err, errlen) &&
               detail::pack_layer(w->decoder, 2 * H, /*activations_scaled=*/true, &e->dec, err, errlen);
     if (ok) {
+        // head rows 0..4 = dense1_base, 5..15 = dense2_rle; B-operand image [16 x 256], dense core matrices
         std::vector<float> wh((size_t)NCLS * 2 * H), bh(NCLS);
         std::memcpy(wh.data(), w->base_weight, (size_t)NBASE * 2 * H * sizeof(float));
         std::memcpy(wh.data() + (size_t)NBASE * 2 * H, w->rle_weight, (size_t)NRLE * 2 * H * sizeof(float));
         std::memcpy(bh.data(), w->base_bias, NBASE * sizeof(float));
         std::memcpy(bh.data() + NBASE, w->rle_bias, NRLE * sizeof(float));
-        ok = detail::to_device(&e->w_head, wh, err, errlen) && detail::to_device(&e->b_head, bh, err, errlen);
+        const int eh = detail::pow2_scale_exponent(wh.data(), wh.size());
+        const float sh = ldexpf(1.f, eh);
+        std::vector<__half> img((size_t)2 * NCLS * 2 * H);
+        for (int r = 0; r < NCLS; ++r)
+            for (int k = 0; k < 2 * H; ++k) {
+                const float v = wh[(size_t)r * 2 * H + k] * sh;
+                const __half hi = __float2half_rn(v);
+                const size_t off = tc::core_offset(r, k, 128, 4096) / 2;
+                img[off] = hi;
+                img[(size_t)NCLS * 2 * H + off] = __float2half_rn(v - __half2float(hi));
+            }
+        e->head_inv = ldexpf(1.f, -eh) * ACT_SCALE_INV;
+        ok = detail::to_device(&e->head_img, img, err, errlen) && detail::to_device(&e->b_head, bh, err, errlen);
     }
     if (ok) {
         cudaError_t ce = cudaSuccess;
         auto set = [&](const void* fn, size_t bytes) {
             if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         };
-        set((const void*)tc_projection_kernel<uint8_t, detail::PROJ_NT>, detail::projection_smem(e->enc.Kp, false));
-        set((const void*)tc_projection_kernel<float, detail::PROJ_NT>, detail::projection_smem(e->dec.Kp, true));
+        set((const void*)tc_projection_kernel<false>, detail::projection_smem(e->enc.Kp * 16, 1));
+        set((const void*)tc_projection_kernel<true>, detail::projection_smem(YROW, 2));
         set((const void*)tc_recurrence_kernel<16>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<32>, detail::recurrence_smem<32>());
+        set((const void*)tc_heads_kernel, detail::heads_smem());
         if (ce != cudaSuccess) {
             snprintf(err, errlen, "tensor engine: cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ce));
             ok = false;
@@ -539,79 +752,57 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
     return e;
 }
 
-inline size_t tensor_engine_workspace_bytes(const TensorEngine*, int64_t B, int T, int W) { return carve(nullptr, B, T, W).bytes; }
-
-// windows per recurrence CTA: smallest tile that still gives every SM at most one CTA's worth of work
-inline int pick_windows_per_cta(int64_t B, int sm_count) {
-    const int64_t dir_windows = 2 * B;
-    if (dir_windows <= (int64_t)16 * sm_count) return 16;
-    return 32;
+inline size_t tensor_engine_workspace_bytes(const TensorEngine* e, int64_t B, int T, int W) {
+    return tensor_carve(nullptr, B, T, W, e->enc.Kp).bytes;
 }
 
-template <typename TA>
-inline void launch_tc_projection(const TensorEngine* e, const TensorLayer& L, const TA* a, int64_t a_batch_stride,
-                                 int64_t a_row_stride, int W, int64_t M, float* gi, cudaStream_t s) {
-    constexpr int NT = detail::PROJ_NT;
-    const int64_t tiles = (M + NT - 1) / NT;
-    const int workers = (int)std::min<int64_t>(tiles, std::max(1, e->sm_count / 6 * 2));
-    dim3 grid((unsigned)workers, 6);
-    tc_projection_kernel<TA, NT><<<grid, 256, detail::projection_smem(L.Kp, sizeof(TA) == 4), s>>>(
-        a, a_batch_stride, a_row_stride, W, M, L.K, L.Kp, L.wih_img, L.bih, L.wih_inv, gi);
-}
-
-inline void launch_tc_recurrence(const TensorEngine* e, const TensorLayer& L, const float* gi, const float* h_in,
-                                 float* h_out, float* y, int64_t B, int W, cudaStream_t s) {
-    const int n = pick_windows_per_cta(B, e->sm_count);
-    dim3 grid((unsigned)((B + n - 1) / n), 2);
-    if (n == 16)
-        tc_recurrence_kernel<16><<<grid, REC_TC_THREADS, detail::recurrence_smem<16>(), s>>>(gi, L.whh_tmem, L.bhh, L.whh_inv, h_in, h_out, y, nullptr, nullptr, B, W);
-    else
-        tc_recurrence_kernel<32><<<grid, REC_TC_THREADS, detail::recurrence_smem<32>(), s>>>(gi, L.whh_tmem, L.bhh, L.whh_inv, h_in, h_out, y, nullptr, nullptr, B, W);
-}
+// windows per recurrence CTA: the smallest tile (lowest step latency) that still fits the batch on the chip
+inline int pick_windows_per_cta(int64_t B, int sm_count) { return 2 * B <= (int64_t)16 * sm_count ? 16 : 32; }
 
 // Returns the number of kernel launches issued, or a negative hb_status (message in err).
 inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t B, int T, int W, int J,
                                  uint8_t* base_labels, uint8_t* rle_labels, float* base_prob, float* rle_prob,
                                  void* workspace, cudaStream_t s, char* err, size_t errlen) {
-    Workspace ws = carve(workspace, B, T, W);
+    TensorWorkspace ws = tensor_carve(workspace, B, T, W, e->enc.Kp);
     float* p_base = base_prob ? base_prob : ws.p_base;
     float* p_rle = rle_prob ? rle_prob : ws.p_rle;
     const int F = e->features;
+    const int64_t n_wg = (B + WG - 1) / WG;
     int launches = 0;
     cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s);
     cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s);
+    const int xblk = e->enc.Kp * 16;                           // bytes of one (group, column) pixel block
+    if (T >= W) {
+        const int64_t chunks16 = n_wg * T * (e->enc.Kp / 8) * WG;
+        const int blocks = (int)std::min<int64_t>((chunks16 + 255) / 256, (int64_t)e->sm_count * 16);
+        pileup_to_operand_image_kernel<<<blocks, 256, 0, s>>>(images, B, T, F, e->enc.Kp, ws.ximg, n_wg);
+        ++launches;
+    }
     const float* hid = nullptr;
     float* hid_bufs[2] = {ws.hid_a, ws.hid_b};
     int flip = 0;
-    const int64_t rows = B * W;
-    const bool tc_proj = e->stages & 1, tc_rec = e->stages & 2;
+    const int nrec = pick_windows_per_cta(B, e->sm_count);
+    const dim3 grid_rec((unsigned)((B + nrec - 1) / nrec), 2);
+    const int tiles_proj = (int)std::min<int64_t>(n_wg * ((W + 7) / 8), std::max(1, e->sm_count / 6));
+    const int tiles_heads = (int)std::min<int64_t>(n_wg * ((W + 15) / 16), e->sm_count);
+    auto recurrence = [&](const TensorLayer& L, const float* h_in, float* h_out, uint8_t* yimg) {
+        if (nrec == 16)
+            tc_recurrence_kernel<16><<<grid_rec, REC_TC_THREADS, detail::recurrence_smem<16>(), s>>>(ws.gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W);
+        else
+            tc_recurrence_kernel<32><<<grid_rec, REC_TC_THREADS, detail::recurrence_smem<32>(), s>>>(ws.gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W);
+    };
     for (int i = 0; i + W <= T; i += J) {
         float* enc_h = hid_bufs[flip];
         float* dec_h = hid_bufs[flip ^ 1];
-        // encoder
-        if (tc_proj) launch_tc_projection<uint8_t>(e, e->enc, images + (int64_t)i * F, (int64_t)T * F, F, W, rows, ws.gi, s);
-        else {
-            dim3 gp((unsigned)((rows + 63) / 64), 2 * G / 64);
-            input_projection_kernel<uint8_t><<<gp, 256, 0, s>>>(images + (int64_t)i * F, (int64_t)T * F, F, W, rows, F, e->f32_enc_wcat, e->enc.bih, ws.gi);
-        }
-        if (tc_rec) launch_tc_recurrence(e, e->enc, ws.gi, hid, enc_h, ws.y1, B, W, s);
-        else {
-            dim3 gr((unsigned)((B + REC_WINDOWS - 1) / REC_WINDOWS), 2);
-            gru_recurrence_kernel<<<gr, REC_THREADS, 0, s>>>(ws.gi, e->f32_enc_whh, e->enc.bhh, hid, enc_h, ws.y1, B, W);
-        }
-        // decoder
-        if (tc_proj) launch_tc_projection<float>(e, e->dec, ws.y1, (int64_t)W * 2 * H, 2 * H, W, rows, ws.gi, s);
-        else {
-            dim3 gp((unsigned)((rows + 63) / 64), 2 * G / 64);
-            input_projection_kernel<float><<<gp, 256, 0, s>>>(ws.y1, (int64_t)W * 2 * H, 2 * H, W, rows, 2 * H, e->f32_dec_wcat, e->dec.bih, ws.gi);
-        }
-        if (tc_rec) launch_tc_recurrence(e, e->dec, ws.gi, enc_h, dec_h, ws.y2, B, W, s);
-        else {
-            dim3 gr((unsigned)((B + REC_WINDOWS - 1) / REC_WINDOWS), 2);
-            gru_recurrence_kernel<<<gr, REC_THREADS, 0, s>>>(ws.gi, e->f32_dec_whh, e->dec.bhh, enc_h, dec_h, ws.y2, B, W);
-        }
-        const int blocks = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)e->sm_count * 8);
-        heads_kernel<<<blocks, 256, 0, s>>>(ws.y2, e->w_head, e->b_head, rows, W, T, i, p_base, p_rle, nullptr, nullptr, 0);
+        tc_projection_kernel<false><<<dim3(tiles_proj, 6), PROJ_THREADS, detail::projection_smem(xblk, 1), s>>>(
+            reinterpret_cast<const uint8_t*>(ws.ximg) + (int64_t)i * xblk, (int64_t)T * xblk, xblk, 0, xblk, 128, e->enc.Kp, n_wg, W,
+            e->enc.wih_tmem, e->enc.scale_row, e->enc.bias_row, ws.gi);
+        recurrence(e->enc, hid, enc_h, ws.yimg1);
+        tc_projection_kernel<true><<<dim3(tiles_proj, 6), PROJ_THREADS, detail::projection_smem(YROW, 2), s>>>(
+            ws.yimg1, (int64_t)W * 2 * YROW, 2 * YROW, YROW, YROW, H_LBO, e->dec.Kp, n_wg, W,
+            e->dec.wih_tmem, e->dec.scale_row, e->dec.bias_row, ws.gi);
+        recurrence(e->dec, enc_h, dec_h, ws.yimg2);
+        tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), s>>>(ws.yimg2, n_wg, B, W, T, i, e->head_img, e->b_head, e->head_inv, p_base, p_rle);
         launches += 5;
         hid = dec_h;
         flip ^= 1;

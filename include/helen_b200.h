@@ -66,10 +66,7 @@ typedef struct hb_handle hb_handle;
 typedef enum hb_engine {
     HB_ENGINE_DEFAULT = 0,
     HB_ENGINE_FP32 = 1,
-    HB_ENGINE_TENSOR = 2,
-    /* test-only A/B switches: one stage on tensor cores, the other on the fp32 pipes */
-    HB_ENGINE_DEBUG_TENSOR_PROJECTION = 3,
-    HB_ENGINE_DEBUG_TENSOR_RECURRENCE = 4
+    HB_ENGINE_TENSOR = 2
 } hb_engine;
 
 int hb_abi_version(void);

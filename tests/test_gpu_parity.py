@@ -22,7 +22,7 @@ MARGIN = 1e-5
 
 def engines(pred):
     out = []
-    for e in ("tensor_projection_only", "tensor_recurrence_only", "tensor", "fp32"):
+    for e in ("tensor", "fp32"):
         try:
             pred.set_engine(e)
             out.append(e)
