@@ -23,6 +23,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -245,8 +246,9 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
                      const float* __restrict__ h_in,        // [B, 2, 128] fp32 or nullptr (zeros)
                      float* __restrict__ h_out,             // [B, 2, 128] fp32
                      uint8_t* __restrict__ yimg,            // operand image of the layer output
-                     int64_t B, int W)
+                     int64_t B, int W, long long* __restrict__ dbg = nullptr)
 {
+#define HB_DBG(role, s, k) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N windows per CTA (3N accumulator columns must stay below REC_W_COL0)");
     constexpr int NW = N / 4;                                // windows per gate thread
     constexpr int NG = N / WG;                               // window groups per CTA
@@ -310,6 +312,10 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
         if (lane < 2 * NG) tc::bulk_wait0();
     } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
+        // Measured (HB_DEBUG_TIMELINE): an M=128, N=16, K=16 MMA occupies the tensor pipe ~13 cycles, so
+        // the 72 MMAs of a step take ~1000 cycles however they are issued (a second issuer warp and an
+        // issue order rotating over the gate blocks were both slower); per-block commits let the gate
+        // warps overlap the r and z sigmoids with the remaining MMAs.
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
         const uint32_t idesc = tc::idesc_f16_f32(128, N);
@@ -320,6 +326,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
                 tc::mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
                 tc::tc_fence_after();
             }
+            HB_DBG(0, s, 0);
             if (tc::elect_one()) {
 #pragma unroll
                 for (int gb = 0; gb < 3; ++gb) {             // gate blocks r, z, n
@@ -335,6 +342,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
                 }
             }
             __syncwarp();
+            HB_DBG(0, s, 1);
         }
     } else {
         // ===================== gate warps =====================
@@ -380,7 +388,9 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
             const int stage = s % GI_STAGES;
             const uint32_t par = (uint32_t)(s & 1);
             float gir[NW], giz[NW], gin[NW];
+            const int drole = warp == 0 ? 1 : (warp == 15 ? 2 : 3);
             tc::mbar_wait(gi_full + stage, (uint32_t)((s / GI_STAGES) & 1));
+            if (drole < 3) HB_DBG(drole, s, 0);
             {
                 const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + win0 * G + j;
 #pragma unroll
@@ -390,12 +400,14 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
             if (lane == 0) tc::mbar_arrive(gi_empty + stage);
             float r[NW], z[NW], a[NW];
             tc::mbar_wait(acc_ready + 0, par);
+            if (drole < 3) HB_DBG(drole, s, 1);
             tc::tc_fence_after();
             if constexpr (NW == 4) tc::tmem_ld4(taddr, a); else tc::tmem_ld8(taddr, a);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < NW; ++i) r[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_r, gir[i])));
             tc::mbar_wait(acc_ready + 1, par);
+            if (drole < 3) HB_DBG(drole, s, 2);
             tc::tc_fence_after();
             if constexpr (NW == 4) tc::tmem_ld4(taddr + N, a); else tc::tmem_ld8(taddr + N, a);
             tc::tmem_ld_wait();
@@ -403,9 +415,11 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
             for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, giz[i])));
             if (s > 0) tc::mbar_wait(h_free, (uint32_t)((s - 1) & 1));   // previous image has been read by the store
             tc::mbar_wait(acc_ready + 2, par);
+            if (drole < 3) HB_DBG(drole, s, 3);
             tc::tc_fence_after();
             if constexpr (NW == 4) tc::tmem_ld4(taddr + 2 * N, a); else tc::tmem_ld8(taddr + 2 * N, a);
             tc::tmem_ld_wait();
+            if (drole < 3) HB_DBG(drole, s, 4);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
                 const float e = tc::ex2_approx(fmaf(r[i], fmaf(a[i], inv_n, bhn), gin[i]));
@@ -417,10 +431,12 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
                 *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
                 *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
             }
+            if (drole < 3) HB_DBG(drole, s, 5);
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(h_ready);
+            if (drole < 3) HB_DBG(drole, s, 6);
         }
 #pragma unroll
         for (int i = 0; i < NW; ++i)
@@ -785,9 +801,12 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const dim3 grid_rec((unsigned)((B + nrec - 1) / nrec), 2);
     const int tiles_proj = (int)std::min<int64_t>(n_wg * ((W + 7) / 8), std::max(1, e->sm_count / 6));
     const int tiles_heads = (int)std::min<int64_t>(n_wg * ((W + 15) / 16), e->sm_count);
+    static long long* dbg_buf = nullptr;
+    static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
+    if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 4 * 128 * 8 * sizeof(long long));
     auto recurrence = [&](const TensorLayer& L, const float* h_in, float* h_out, uint8_t* yimg) {
         if (nrec == 16)
-            tc_recurrence_kernel<16><<<grid_rec, REC_TC_THREADS, detail::recurrence_smem<16>(), s>>>(ws.gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W);
+            tc_recurrence_kernel<16><<<grid_rec, REC_TC_THREADS, detail::recurrence_smem<16>(), s>>>(ws.gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W, dbg_buf);
         else
             tc_recurrence_kernel<32><<<grid_rec, REC_TC_THREADS, detail::recurrence_smem<32>(), s>>>(ws.gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W);
     };
@@ -810,6 +829,31 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const int64_t positions = B * T;
     argmax_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p_base, p_rle, positions, base_labels, rle_labels);
     launches += 1;
+    if (dbg_on && dbg_buf) {
+        static int printed = 0;
+        cudaStreamSynchronize(s);
+        if (printed++ == 2) {
+            std::vector<long long> hbuf(4 * 128 * 8);
+            cudaMemcpy(hbuf.data(), dbg_buf, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            auto at = [&](int role, int st, int k) { return hbuf[((size_t)role * 128 + st) * 8 + k]; };
+            double acc[16] = {0};
+            int n = 0;
+            for (int st = 20; st < 90; ++st, ++n) {
+                const long long base = at(0, st, 0);              // MMA warp released for step st
+                acc[0] += at(0, st, 1) - base;                    // issue done
+                for (int role = 1; role <= 2; ++role)
+                    for (int k = 0; k < 7; ++k) acc[1 + (role - 1) * 7 + k] += at(role, st, k) - base;
+                acc[15] += at(0, st + 1, 0) - base;               // full step
+            }
+            fprintf(stderr, "[timeline, cycles after MMA warp release] issue_done=%.0f step=%.0f\n", acc[0] / n, acc[15] / n);
+            for (int role = 1; role <= 2; ++role) {
+                fprintf(stderr, "  gate warp %s:", role == 1 ? "0 " : "15");
+                const char* names[7] = {"gi_full", "acc_r", "acc_z", "acc_n", "ldtm_n", "math_done", "arrived"};
+                for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.0f", names[k], acc[1 + (role - 1) * 7 + k] / n);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) {
         snprintf(err, errlen, "tensor engine launch failed: %s", cudaGetErrorString(ce));
