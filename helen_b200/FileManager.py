@@ -1,0 +1,19 @@
+"""Small filesystem helpers with the reference's behaviour (helen/modules/python/FileManager.py)."""
+import os
+
+
+class FileManager:
+    @staticmethod
+    def handle_output_directory(output_dir):
+        """Create the directory if needed and return its absolute path (FileManager.py:10-23)."""
+        if output_dir[-1] != "/":
+            output_dir += "/"
+        if not os.path.exists(output_dir):
+            os.mkdir(output_dir)
+        return os.path.abspath(output_dir)
+
+    @staticmethod
+    def get_file_paths_from_directory(directory_path):
+        """MarginPolish image files are those whose name ends in 'h5' (FileManager.py:52-61)."""
+        return [os.path.join(directory_path, name) for name in os.listdir(directory_path)
+                if os.path.isfile(os.path.join(directory_path, name)) and name[-2:] == 'h5']

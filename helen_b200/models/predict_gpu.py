@@ -1,0 +1,72 @@
+"""GPU inference driver with the reference's entry points
+(helen/modules/python/models/predict_gpu.py:38, :186, :207).
+
+One OS process per GPU (mp.spawn), each with its own file list and its own
+``<prefix>_<rank>.hdf`` output; no process group and no collective: in the reference the gloo
+group only served a DistributedDataParallel wrapper that does nothing under no_grad.  The whole
+per-batch loop body of the reference (predict_gpu.py:97-159) is one call into the CUDA library.
+"""
+import sys
+import time
+
+import torch
+import torch.multiprocessing as mp
+from torch.utils.data import DataLoader
+
+from ..DataStore import DataStore
+from ..options import ImageSizeOptions
+from ..predictor import WindowPredictor
+from ..TextColor import TextColor
+from .dataloader_predict import SequenceDataset
+from .ModelHander import ModelHandler
+
+
+def predict(test_file, output_filename, model_path, batch_size, num_workers, rank, device_id):
+    prediction_data_file = DataStore(output_filename + "_" + str(rank) + ".hdf", mode='w')
+    checkpoint = ModelHandler.load_checkpoint(model_path)
+    state_dict = checkpoint['model_state_dict']
+    if checkpoint['gru_layers'] != 1 or checkpoint['hidden_size'] != 128:
+        raise ValueError("helen_b200 supports gru_layers=1, hidden_size=128 checkpoints only "
+                         f"(got {checkpoint['gru_layers']}, {checkpoint['hidden_size']})")
+    torch.cuda.set_device(device_id)
+    predictor = WindowPredictor(state_dict, device=device_id)
+    if predictor.image_features != ImageSizeOptions.IMAGE_HEIGHT:
+        sys.stderr.write(TextColor.YELLOW + "WARN: MODEL EXPECTS " + str(predictor.image_features)
+                         + " FEATURES PER COLUMN, MARGINPOLISH IMAGES HAVE " + str(ImageSizeOptions.IMAGE_HEIGHT)
+                         + ".\n" + TextColor.END)
+    if rank == 0:
+        print(output_filename + "_" + str(rank) + ".hdf")
+        sys.stderr.write(TextColor.PURPLE + 'Loading data\n' + TextColor.END)
+
+    test_data = SequenceDataset(image_directory=None, file_list=test_file)
+    test_loader = DataLoader(test_data, batch_size=batch_size, shuffle=False, num_workers=num_workers)
+    total_batches = len(test_loader)
+    windows_done, t_begin = 0, time.time()
+    for batch_iterator, (contig, contig_start, contig_end, chunk_id, images, position, filename) in enumerate(test_loader, 1):
+        start_time = time.time()
+        base_labels, rle_labels = predictor.predict_host(images.numpy())
+        windows_done += images.size(0)
+        if rank == 0:
+            eta = (time.time() - start_time) * (total_batches - batch_iterator)
+            stamp = "{} HOURS {} MINS {} SECS.".format(int(eta / 3600), int(eta % 3600 / 60), int(eta) % 60)
+            sys.stderr.write(TextColor.GREEN + "INFO: BATCHES DONE: " + str(batch_iterator) + "/" + str(total_batches)
+                             + ". ESTIMATED TIME LEFT: " + stamp + " ("
+                             + str(int(windows_done / max(time.time() - t_begin, 1e-9))) + " WINDOWS/S)\n" + TextColor.END)
+        for i in range(images.size(0)):
+            prediction_data_file.write_prediction(contig[i], contig_start[i], contig_end[i], chunk_id[i],
+                                                  position[i], base_labels[i], rle_labels[i], filename[i])
+    prediction_data_file.close()
+    predictor.close()
+
+
+def setup(rank, total_callers, args, all_input_files, all_devices):
+    output_filepath, model_path, batch_size, num_workers = args
+    predict(all_input_files[rank], output_filepath, model_path, batch_size, num_workers, rank, all_devices[rank])
+
+
+def predict_gpu(file_chunks, output_filepath, model_path, batch_size, total_callers, devices, num_workers):
+    args = (output_filepath, model_path, batch_size, num_workers)
+    if total_callers == 1:
+        setup(0, 1, args, file_chunks, devices)
+        return
+    mp.spawn(setup, args=(total_callers, args, file_chunks, devices), nprocs=total_callers, join=True)

@@ -1,0 +1,112 @@
+"""Host-side mirror of the reference surface: dataset padding rules, prediction file schema,
+file sharding, CLI flags and argument-error behaviour (CPU only)."""
+import numpy as np
+import pytest
+
+import fake_h5
+from helen_b200 import hdf5
+from helen_b200.options import ImageSizeOptions, TrainOptions
+
+
+@pytest.fixture(autouse=True)
+def _fake_hdf5(monkeypatch):
+    fake_h5.reset()
+    monkeypatch.setattr(hdf5, "open_file", fake_h5.open_file)
+    yield
+    fake_h5.reset()
+
+
+def test_options_match_reference_constants():
+    assert (ImageSizeOptions.IMAGE_HEIGHT, ImageSizeOptions.SEQ_LENGTH, ImageSizeOptions.SEQ_OVERLAP) == (90, 1000, 200)
+    assert (ImageSizeOptions.TOTAL_BASE_LABELS, ImageSizeOptions.TOTAL_RLE_LABELS) == (5, 11)
+    assert (TrainOptions.TRAIN_WINDOW, TrainOptions.WINDOW_JUMP, TrainOptions.GRU_LAYERS, TrainOptions.HIDDEN_SIZE) == (100, 50, 1, 128)
+
+
+def test_sequence_dataset_pads_short_images():
+    from helen_b200.models.dataloader_predict import SequenceDataset
+    rng = np.random.default_rng(0)
+    full = rng.integers(0, 256, (1000, 90), dtype=np.uint8)
+    short = rng.integers(0, 256, (412, 90), dtype=np.uint8)
+    pos_full = np.stack([np.arange(1000), np.zeros(1000, int), np.zeros(1000, int)], 1)
+    fake_h5.add_image("a.h5", "img0", "chr1", 0, 1000, 3, full, pos_full)
+    fake_h5.add_image("a.h5", "img1", "chr1", 1000, 1412, 4, short, pos_full[:412])
+    fake_h5.open_file("empty.h5", "w")                      # a file without images only warns
+    ds = SequenceDataset(None, file_list=["a.h5", "empty.h5"])
+    assert len(ds) == 2
+    contig, start, end, chunk, image, position, path = ds[0]
+    assert (contig, start, end, chunk, path) == ("chr1", 0, 1000, 3, "a.h5")
+    assert image.dtype == np.uint8 and image.shape == (1000, 90) and np.array_equal(image, full)
+    _, _, _, _, image, position, _ = ds[1]
+    assert image.shape == (1000, 90) and np.array_equal(image[:412], short) and not image[412:].any()
+    assert position.shape == (1000, 3) and (position[412:] == -1).all()
+
+
+def test_sequence_dataset_batches_through_dataloader():
+    from torch.utils.data import DataLoader
+    from helen_b200.models.dataloader_predict import SequenceDataset
+    for i in range(5):
+        fake_h5.add_image("b.h5", f"img{i}", "ctg", i * 1000, (i + 1) * 1000, i,
+                          np.full((1000, 90), i, np.uint8), np.zeros((1000, 3), int))
+    loader = DataLoader(SequenceDataset(None, file_list=["b.h5"]), batch_size=4, shuffle=False, num_workers=0)
+    contig, start, end, chunk, images, position, path = next(iter(loader))
+    assert images.shape == (4, 1000, 90) and images.dtype.is_floating_point is False
+    assert list(contig) == ["ctg"] * 4 and start.tolist() == [0, 1000, 2000, 3000]
+
+
+def test_datastore_schema_and_dedup():
+    from helen_b200.DataStore import DataStore
+    store = DataStore("out_0.hdf", "w")
+    pos = np.full((1000, 3), -1)
+    pos[:10, 0] = np.arange(10)
+    bases = np.arange(1000) % 5
+    rles = np.arange(1000) % 11
+    store.write_prediction("chr2", np.int64(100), np.int64(1100), np.int64(7), pos, bases, rles, "f.h5")
+    store.write_prediction("chr2", np.int64(100), np.int64(1100), np.int64(7), pos, bases * 0, rles, "f.h5")   # duplicate: ignored
+    store.write_prediction("chr2", np.int64(100), np.int64(1100), np.int64(8), pos, bases, rles, "f.h5")
+    f = fake_h5.open_file("out_0.hdf")
+    region = f["predictions/chr2/chr2-100-1100"]
+    assert int(region["contig_start"][()]) == 100 and int(region["contig_end"][()]) == 1100
+    chunk = region["7"]
+    assert chunk["bases"][()].dtype == np.uint8 and np.array_equal(chunk["bases"][()], bases)
+    assert chunk["rles"][()].dtype == np.uint8
+    assert chunk["position"][()].dtype == np.uint32 and chunk["position"][()][20, 0] == 4294967295   # -1 wraps, as in the reference
+    assert "8" in region
+
+
+def test_round_robin_file_sharding():
+    from helen_b200.CallConsensusInterface import shard_files
+    files = [f"f{i}.h5" for i in range(7)]
+    assert shard_files(files, 3) == [["f0.h5", "f3.h5", "f6.h5"], ["f1.h5", "f4.h5"], ["f2.h5", "f5.h5"]]
+    assert shard_files(files[:2], 8) == [["f0.h5"], ["f1.h5"]]          # empty callers are dropped
+    assert shard_files([], 4) == []
+
+
+def test_cli_flags_and_defaults():
+    from helen_b200.helen import build_parser
+    p = build_parser()
+    a = p.parse_args(["polish", "-i", "imgs", "-m", "m.pkl"])
+    assert (a.batch_size, a.num_workers, a.threads, a.output_dir, a.output_prefix, a.gpu_mode, a.device_ids, a.callers) == \
+        (512, 8, 1, "./output/", "HELEN_prediction", False, None, 8)
+    a = p.parse_args(["call_consensus", "-i", "imgs", "-m", "m.pkl", "-b", "256", "-w", "4", "-g", "-d_ids", "0,1", "-t", "32"])
+    assert (a.batch_size, a.num_workers, a.gpu_mode, a.device_ids, a.threads) == (256, 4, True, "0,1", 32)
+    assert p.parse_args(["call_consensus", "-i", "x", "-m", "y"]).threads == 16
+
+
+@pytest.mark.parametrize("kwargs", [
+    dict(model_path="/nonexistent/model.pkl"),
+    dict(image_dir="/nonexistent/dir"),
+    dict(batch_size=0),
+    dict(num_workers=-1),
+    dict(threads=0),
+    dict(gpu_mode=False),            # no CPU fallback in this package
+])
+def test_call_consensus_argument_errors_exit_1(tmp_path, kwargs):
+    from helen_b200.CallConsensusInterface import call_consensus
+    model = tmp_path / "m.pkl"
+    model.write_bytes(b"x")
+    args = dict(image_dir=str(tmp_path), model_path=str(model), batch_size=8, num_workers=0, threads=1,
+                output_dir=str(tmp_path / "out"), output_prefix="p", gpu_mode=True, device_ids=None, callers=1)
+    args.update(kwargs)
+    with pytest.raises(SystemExit) as err:
+        call_consensus(**args)
+    assert err.value.code == 1
