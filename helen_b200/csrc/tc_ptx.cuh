@@ -53,6 +53,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- programmatic dependent launch ----------------------------------------------------------
+// launch_dependents: the next kernel in the stream (launched with the programmatic-serialization
+// attribute) may start its prologue now.  grid_dependency_wait: block until the previous kernel has
+// completed and its memory is visible; everything that reads upstream results comes after it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core operand fetch)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -106,6 +106,7 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int blk = blockIdx.y;
     const int kwords = Kp >> 1;
+    tc::pdl_launch_dependents();
     if (tid == 0) {
         for (int i = 0; i < PROJ_STAGES; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
@@ -131,6 +132,7 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
         }
         tc::tmem_st_wait();
     }
+    tc::pdl_grid_dependency_wait();                          // activations / gi buffers belong to upstream kernels
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -246,7 +248,9 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
                      const float* __restrict__ h_in,        // [B, 2, 128] fp32 or nullptr (zeros)
                      float* __restrict__ h_out,             // [B, 2, 128] fp32
                      uint8_t* __restrict__ yimg,            // operand image of the layer output
-                     int64_t B, int W, long long* __restrict__ dbg = nullptr)
+                     int64_t B, int W,
+                     int gi_cols, int gi_col0,              // gi' row of (window b, step column t) = b * gi_cols + gi_col0 + t
+                     long long* __restrict__ dbg = nullptr)
 {
 #define HB_DBG(role, s, k) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N windows per CTA (3N accumulator columns must stay below REC_W_COL0)");
@@ -270,6 +274,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
     const int64_t b0 = (int64_t)blockIdx.x * N;
     const int t_first = dir ? W - 1 : 0, dt = dir ? -1 : 1;
 
+    tc::pdl_launch_dependents();
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) tc::mbar_init(acc_ready + i, 1);
         tc::mbar_init(h_ready, REC_GATE_WARPS);
@@ -286,8 +291,9 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
 
     if (warp == REC_GATE_WARPS + 1) {
         // ===================== gi loader: bulk copies, GI_STAGES steps ahead =====================
+        tc::pdl_grid_dependency_wait();
         __syncthreads();
-        const float* src0 = gi + ((b0 + lane) * W) * (int64_t)(2 * G) + dir * G;
+        const float* src0 = gi + ((b0 + lane) * gi_cols + gi_col0) * (int64_t)(2 * G) + dir * G;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % GI_STAGES;
             if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
@@ -297,6 +303,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
         }
     } else if (warp == REC_GATE_WARPS + 2) {
         // ===================== y store: the h image of step s is the layer output at column t_s ====
+        tc::pdl_grid_dependency_wait();
         __syncthreads();
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             tc::mbar_wait(h_ready, (uint32_t)(s & 1));
@@ -316,6 +323,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
         // the 72 MMAs of a step take ~1000 cycles however they are issued (a second issuer warp and an
         // issue order rotating over the gate blocks were both slower); per-block commits let the gate
         // warps overlap the r and z sigmoids with the remaining MMAs.
+        tc::pdl_grid_dependency_wait();
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
         const uint32_t idesc = tc::idesc_f16_f32(128, N);
@@ -367,6 +375,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
         }
         const float* gc = gate_consts + (size_t)dir * 4 * H + j;
         const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
+        tc::pdl_grid_dependency_wait();                      // h_in, gi', yimg belong to upstream kernels
         float h_own[NW];                                     // h * 2^10
         uint32_t h_off[NW];
 #pragma unroll
@@ -474,6 +483,7 @@ tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    tc::pdl_launch_dependents();
     for (int i = tid; i < 2 * HEADS_WIMG / 16; i += blockDim.x)
         reinterpret_cast<int4*>(w_s)[i] = reinterpret_cast<const int4*>(w_img)[i];
     if (tid == 0) {
@@ -482,6 +492,7 @@ tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W
     }
     __syncwarp();
     if (warp == 4) tc::tmem_alloc(tmem_slot, 32);
+    tc::pdl_grid_dependency_wait();
     tc::fence_proxy_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -579,6 +590,8 @@ struct TensorLayer {
 };
 
 struct TensorEngine {
+    cudaStream_t side = nullptr;   // heads + softmax run here, beside the next chunk's encoder
+    cudaEvent_t ev_dec[2] = {nullptr, nullptr}, ev_heads[2] = {nullptr, nullptr};
     TensorLayer enc, dec;
     __half* head_img = nullptr;    // [hi, lo][16 x 256]
     float* b_head = nullptr;
@@ -588,9 +601,10 @@ struct TensorEngine {
 };
 
 struct TensorWorkspace {
-    float* gi;
+    float* gi_enc;      // [Bp, enc_cols, 768]  encoder projections of every image column, computed once per batch
+    float* gi;          // [Bp, W, 768]         decoder projections of the current chunk
     uint8_t* yimg1;
-    uint8_t* yimg2;
+    uint8_t* yimg2[2];  // double buffered: heads(k) runs beside the encoder of chunk k+1
     __half* ximg;
     float* hid_a;
     float* hid_b;
@@ -599,7 +613,10 @@ struct TensorWorkspace {
     size_t bytes;
 };
 
-inline TensorWorkspace tensor_carve(void* base, int64_t B, int T, int W, int Kp) {
+// image columns covered by the chunk loop range(0, T, J) with W-column chunks (predict_gpu.py:114-117)
+inline int covered_columns(int T, int W, int J) { return T < W ? 0 : (T - W) / J * J + W; }
+
+inline TensorWorkspace tensor_carve(void* base, int64_t B, int T, int W, int Kp, int enc_cols) {
     TensorWorkspace ws{};
     size_t off = 0;
     auto take = [&](size_t n) {
@@ -609,9 +626,11 @@ inline TensorWorkspace tensor_carve(void* base, int64_t B, int T, int W, int Kp)
     };
     const size_t Bp = ((size_t)B + 31) / 32 * 32;            // window tiles of the kernels may run past B
     const size_t Wp = (size_t)std::max(W, 0);
+    ws.gi_enc = reinterpret_cast<float*>(take(Bp * (size_t)enc_cols * 2 * G * sizeof(float)));
     ws.gi = reinterpret_cast<float*>(take(Bp * Wp * 2 * G * sizeof(float)));
     ws.yimg1 = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
-    ws.yimg2 = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
+    ws.yimg2[0] = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
+    ws.yimg2[1] = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
     ws.ximg = reinterpret_cast<__half*>(take(Bp / WG * (size_t)T * Kp * 16));
     ws.hid_a = reinterpret_cast<float*>(take(Bp * 2 * H * sizeof(float)));
     ws.hid_b = reinterpret_cast<float*>(take(Bp * 2 * H * sizeof(float)));
@@ -622,6 +641,27 @@ inline TensorWorkspace tensor_carve(void* base, int64_t B, int T, int W, int Kp)
 }
 
 namespace detail {
+
+template <class T> struct ident { using type = T; };
+
+// Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start
+// while its predecessor in the stream is still running and synchronises with griddepcontrol.wait.
+template <typename... KArgs>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                          typename ident<KArgs>::type... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    void* params[] = {(void*)&args...};
+    return cudaLaunchKernelExC(&cfg, (const void*)kernel, params);
+}
 
 inline int pow2_scale_exponent(const float* w, size_t n) {
     float mx = 0.f;
@@ -716,6 +756,11 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     detail::free_layer(&e->dec);
     cudaFree(e->head_img);
     cudaFree(e->b_head);
+    if (e->side) cudaStreamDestroy(e->side);
+    for (int i = 0; i < 2; ++i) {
+        if (e->ev_dec[i]) cudaEventDestroy(e->ev_dec[i]);
+        if (e->ev_heads[i]) cudaEventDestroy(e->ev_heads[i]);
+    }
     delete e;
 }
 
@@ -756,6 +801,11 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_recurrence_kernel<16>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<32>, detail::recurrence_smem<32>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
+            ce = cudaEventCreateWithFlags(&e->ev_dec[i], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_heads[i], cudaEventDisableTiming);
+        }
         if (ce != cudaSuccess) {
             snprintf(err, errlen, "tensor engine: cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ce));
             ok = false;
@@ -769,7 +819,7 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
 }
 
 inline size_t tensor_engine_workspace_bytes(const TensorEngine* e, int64_t B, int T, int W) {
-    return tensor_carve(nullptr, B, T, W, e->enc.Kp).bytes;
+    return tensor_carve(nullptr, B, T, W, e->enc.Kp, T).bytes;     // J >= 1: at most T covered columns
 }
 
 // windows per recurrence CTA: the smallest tile (lowest step latency) that still fits the batch on the chip
@@ -779,7 +829,8 @@ inline int pick_windows_per_cta(int64_t B, int sm_count) { return 2 * B <= (int6
 inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t B, int T, int W, int J,
                                  uint8_t* base_labels, uint8_t* rle_labels, float* base_prob, float* rle_prob,
                                  void* workspace, cudaStream_t s, char* err, size_t errlen) {
-    TensorWorkspace ws = tensor_carve(workspace, B, T, W, e->enc.Kp);
+    const int enc_cols = covered_columns(T, W, J);
+    TensorWorkspace ws = tensor_carve(workspace, B, T, W, e->enc.Kp, T);
     float* p_base = base_prob ? base_prob : ws.p_base;
     float* p_rle = rle_prob ? rle_prob : ws.p_rle;
     const int F = e->features;
@@ -788,44 +839,58 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s);
     cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s);
     const int xblk = e->enc.Kp * 16;                           // bytes of one (group, column) pixel block
-    if (T >= W) {
+    const int proj_workers = std::max(1, e->sm_count / 6);
+    static const bool pdl = getenv("HB_NO_PDL") == nullptr;
+    if (enc_cols > 0) {
+        // once per batch: pixels -> operand image, then the encoder projection of EVERY covered column
+        // (chunks overlap by W - J columns and gi of a column does not depend on the chunk)
         const int64_t chunks16 = n_wg * T * (e->enc.Kp / 8) * WG;
         const int blocks = (int)std::min<int64_t>((chunks16 + 255) / 256, (int64_t)e->sm_count * 16);
         pileup_to_operand_image_kernel<<<blocks, 256, 0, s>>>(images, B, T, F, e->enc.Kp, ws.ximg, n_wg);
-        ++launches;
+        const int tiles = (int)std::min<int64_t>(n_wg * ((enc_cols + 7) / 8), proj_workers);
+        detail::launch(tc_projection_kernel<false>, dim3(tiles, 6), dim3(PROJ_THREADS), detail::projection_smem(xblk, 1), s, pdl,
+                       reinterpret_cast<const uint8_t*>(ws.ximg), (int64_t)T * xblk, xblk, 0, xblk, 128, e->enc.Kp, n_wg, enc_cols,
+                       e->enc.wih_tmem, e->enc.scale_row, e->enc.bias_row, ws.gi_enc);
+        launches += 2;
     }
     const float* hid = nullptr;
     float* hid_bufs[2] = {ws.hid_a, ws.hid_b};
     int flip = 0;
     const int nrec = pick_windows_per_cta(B, e->sm_count);
     const dim3 grid_rec((unsigned)((B + nrec - 1) / nrec), 2);
-    const int tiles_proj = (int)std::min<int64_t>(n_wg * ((W + 7) / 8), std::max(1, e->sm_count / 6));
+    const int tiles_proj = (int)std::min<int64_t>(n_wg * ((W + 7) / 8), proj_workers);
     const int tiles_heads = (int)std::min<int64_t>(n_wg * ((W + 15) / 16), e->sm_count);
     static long long* dbg_buf = nullptr;
     static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
     if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 4 * 128 * 8 * sizeof(long long));
-    auto recurrence = [&](const TensorLayer& L, const float* h_in, float* h_out, uint8_t* yimg) {
+    auto recurrence = [&](const TensorLayer& L, const float* gi, int gi_cols, int gi_col0, const float* h_in, float* h_out, uint8_t* yimg, bool use_pdl) {
         if (nrec == 16)
-            tc_recurrence_kernel<16><<<grid_rec, REC_TC_THREADS, detail::recurrence_smem<16>(), s>>>(ws.gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W, dbg_buf);
+            detail::launch(tc_recurrence_kernel<16>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl,
+                           gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W, gi_cols, gi_col0, dbg_buf);
         else
-            tc_recurrence_kernel<32><<<grid_rec, REC_TC_THREADS, detail::recurrence_smem<32>(), s>>>(ws.gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W);
+            detail::launch(tc_recurrence_kernel<32>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl,
+                           gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W, gi_cols, gi_col0, (long long*)nullptr);
     };
-    for (int i = 0; i + W <= T; i += J) {
+    int chunk = 0;
+    for (int i = 0; i + W <= T; i += J, ++chunk) {
         float* enc_h = hid_bufs[flip];
         float* dec_h = hid_bufs[flip ^ 1];
-        tc_projection_kernel<false><<<dim3(tiles_proj, 6), PROJ_THREADS, detail::projection_smem(xblk, 1), s>>>(
-            reinterpret_cast<const uint8_t*>(ws.ximg) + (int64_t)i * xblk, (int64_t)T * xblk, xblk, 0, xblk, 128, e->enc.Kp, n_wg, W,
-            e->enc.wih_tmem, e->enc.scale_row, e->enc.bias_row, ws.gi);
-        recurrence(e->enc, hid, enc_h, ws.yimg1);
-        tc_projection_kernel<true><<<dim3(tiles_proj, 6), PROJ_THREADS, detail::projection_smem(YROW, 2), s>>>(
-            ws.yimg1, (int64_t)W * 2 * YROW, 2 * YROW, YROW, YROW, H_LBO, e->dec.Kp, n_wg, W,
-            e->dec.wih_tmem, e->dec.scale_row, e->dec.bias_row, ws.gi);
-        recurrence(e->dec, enc_h, dec_h, ws.yimg2);
-        tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), s>>>(ws.yimg2, n_wg, B, W, T, i, e->head_img, e->b_head, e->head_inv, p_base, p_rle);
-        launches += 5;
+        const int buf = chunk & 1;
+        if (chunk >= 2) cudaStreamWaitEvent(s, e->ev_heads[buf], 0);      // heads(chunk - 2) has read this yimg2 buffer
+        recurrence(e->enc, ws.gi_enc, enc_cols, i, hid, enc_h, ws.yimg1, pdl && chunk == 0);
+        detail::launch(tc_projection_kernel<true>, dim3(tiles_proj, 6), dim3(PROJ_THREADS), detail::projection_smem(YROW, 2), s, pdl,
+                       (const uint8_t*)ws.yimg1, (int64_t)W * 2 * YROW, (int64_t)2 * YROW, (int64_t)YROW, YROW, H_LBO, e->dec.Kp, n_wg, W,
+                       e->dec.wih_tmem, e->dec.scale_row, e->dec.bias_row, ws.gi);
+        recurrence(e->dec, ws.gi, W, 0, enc_h, dec_h, ws.yimg2[buf], pdl);
+        cudaEventRecord(e->ev_dec[buf], s);
+        cudaStreamWaitEvent(e->side, e->ev_dec[buf], 0);
+        tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), e->side>>>(ws.yimg2[buf], n_wg, B, W, T, i, e->head_img, e->b_head, e->head_inv, p_base, p_rle);
+        cudaEventRecord(e->ev_heads[buf], e->side);
+        launches += 4;
         hid = dec_h;
         flip ^= 1;
     }
+    for (int b = 0; b < std::min(chunk, 2); ++b) cudaStreamWaitEvent(s, e->ev_heads[b], 0);   // join the side stream
     const int64_t positions = B * T;
     argmax_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p_base, p_rle, positions, base_labels, rle_labels);
     launches += 1;
