@@ -120,7 +120,7 @@ def synthetic_images(batch, features, seed, seq=T_COLUMNS):
     return torch.randint(0, 256, (batch, seq, features), dtype=torch.uint8, generator=gen)
 
 
-def cpu_port_windows_per_s(features, sample_windows, min_seconds, threads, seq=T_COLUMNS, reps_cap=8):
+def cpu_port_windows_per_s(features, sample_windows, min_seconds, threads, seq=T_COLUMNS, reps_cap=64):
     """Times the oracle's torch-CPU port of the reference predict loop (the only place bench.py
     executes oracle/ code)."""
     import torch
@@ -240,7 +240,7 @@ def run_native(args, rank, world, local_rank):
         per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
         return per_step, pred.launch_count - launches0
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period=0.02)
     pred.enable_kernel_timing(True)
     pred.kernel_time_ms(reset=True)
     per_step, launches = timed_steps(images, args.steps, args.warmup, sampler)
@@ -249,6 +249,18 @@ def run_native(args, rank, world, local_rank):
     pred.enable_kernel_timing(False)
     total_ms = max_over_ranks(sum(per_step))
     value = world * args.batch * args.steps / (total_ms * 1e-3)
+
+    # dominant kernel (GRU recurrence) timed on its own: separate short pass, CUDA events around every launch
+    dom_ms, dom_launches = None, 0
+    if engine == "tensor":
+        pred.enable_kernel_timing(2)
+        pred.dominant_kernel_time_ms(reset=True)
+        for _ in range(3):
+            flush.zero_()
+            pred.predict(images)
+        torch.cuda.synchronize()
+        dom_ms, dom_launches = pred.dominant_kernel_time_ms(reset=True)
+        pred.enable_kernel_timing(False)
 
     # end to end through the host-buffer entry: pageable numpy in, numpy labels out
     for _ in range(max(1, args.warmup // 2)):
@@ -277,6 +289,24 @@ def run_native(args, rank, world, local_rank):
     # library's own event bracket around that sequence on the launching stream
     kernel_ms = kernel_ms_total / max(kernel_calls, 1) if kernel_calls else statistics.mean(per_step)
     achieved_tf = args.batch * fpw / (kernel_ms * 1e-3) / 1e12
+    path_roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["burst"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / peaks["burst"], "frac_of_sustained": achieved_tf / peaks["sustained"],
+                     "flop_per_window": fpw, "ms_per_batch": kernel_ms,
+                     "what": "all kernels of one batch (library event bracket on the launching stream)"}
+    if dom_launches:
+        # one recurrence launch = batch windows x 100 dependent steps x 2 directions of one layer
+        rec_flop = args.batch * WINDOW * 2 * (2 * 3 * HIDDEN * HIDDEN)
+        rec_ms = dom_ms / dom_launches
+        rec_tf = rec_flop / (rec_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "tc_recurrence_kernel", "achieved": rec_tf, "peak": peaks["burst"],
+                    "unit": "TFLOP/s", "frac": rec_tf / peaks["burst"], "frac_of_sustained": rec_tf / peaks["sustained"],
+                    "peak_source": ("measured" if peaks["source"] == "measured" else "fallback") + " bf16 burst",
+                    "flop_per_launch": rec_flop, "kernel_ms_per_launch": rec_ms, "launches_timed": dom_launches,
+                    "us_per_dependent_step": 1e3 * rec_ms / WINDOW,
+                    "traffic": kernel_traffic_bytes(engine, args.batch, args.features),
+                    "note": "latency-bound at this batch: 100 dependent GRU steps per launch (DESIGN.md section 5)"}
+    else:
+        roofline = dict(path_roofline, traffic=kernel_traffic_bytes(engine, args.batch, args.features))
     line = {
         "metric": "pileup windows/sec (B=256, T=1000)", "value": value, "unit": "windows/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -287,12 +317,8 @@ def run_native(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(2 * args.batch * T_COLUMNS)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["burst"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["burst"], "frac_of_sustained": achieved_tf / peaks["sustained"],
-                     "peak_source": peaks["source"] + " bf16 burst (MEASURED_PEAKS.json)" if peaks["source"] == "measured"
-                     else "fallback", "flop_per_window": fpw, "kernel_ms_per_launch": kernel_ms,
-                     "traffic": kernel_traffic_bytes(engine, args.batch, args.features),
-                     "hbm_algorithmic_gbs": args.batch * (T_COLUMNS * args.features + 2 * T_COLUMNS) / (kernel_ms * 1e-3) / 1e9},
+        "roofline": roofline,
+        "roofline_path": path_roofline,
     }
     if sweep:
         line["batch_sweep"] = sweep

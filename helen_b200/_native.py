@@ -52,6 +52,7 @@ SIGNATURES = {
     "hb_launch_count": (c_int64, [c_void_p]),
     "hb_enable_kernel_timing": (c_int, [c_void_p, c_int]),
     "hb_kernel_time_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
+    "hb_dominant_kernel_time_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
 }
 
 _lib = None

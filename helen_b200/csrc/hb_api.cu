@@ -452,6 +452,28 @@ int64_t hb_launch_count(const hb_handle* h) { return h ? h->launches : 0; }
 int hb_enable_kernel_timing(hb_handle* h, int enable) {
     if (!h) return fail(HB_ERR_INVALID_ARGUMENT, "null handle");
     h->timing = enable != 0;
+#ifndef HB_NO_TENSOR_ENGINE
+    h->tensor->time_recurrence = enable == 2;
+#endif
+    return HB_OK;
+}
+
+int hb_dominant_kernel_time_ms(hb_handle* h, double* total_ms, int64_t* launches, int reset) {
+    if (!h || !total_ms || !launches) return fail(HB_ERR_INVALID_ARGUMENT, "null argument");
+    *total_ms = 0.0;
+    *launches = 0;
+#ifndef HB_NO_TENSOR_ENGINE
+    DeviceGuard guard(h->device);
+    hb::TensorEngine* e = h->tensor;
+    for (size_t i = 0; i < e->rec_events_used; ++i) {
+        HB_CUDA(cudaEventSynchronize(e->rec_events[i].second));
+        float ms = 0.f;
+        HB_CUDA(cudaEventElapsedTime(&ms, e->rec_events[i].first, e->rec_events[i].second));
+        *total_ms += ms;
+    }
+    *launches = (int64_t)e->rec_events_used;
+    if (reset) e->rec_events_used = 0;
+#endif
     return HB_OK;
 }
 

@@ -590,6 +590,10 @@ struct TensorLayer {
 };
 
 struct TensorEngine {
+    // optional device timing of every recurrence launch (the dominant kernel), bench.py's roofline pass
+    bool time_recurrence = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> rec_events;
+    size_t rec_events_used = 0;
     cudaStream_t side = nullptr;   // heads + softmax run here, beside the next chunk's encoder
     cudaEvent_t ev_dec[2] = {nullptr, nullptr}, ev_heads[2] = {nullptr, nullptr};
     TensorLayer enc, dec;
@@ -757,6 +761,7 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     cudaFree(e->head_img);
     cudaFree(e->b_head);
     if (e->side) cudaStreamDestroy(e->side);
+    for (auto& ev : e->rec_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (int i = 0; i < 2; ++i) {
         if (e->ev_dec[i]) cudaEventDestroy(e->ev_dec[i]);
         if (e->ev_heads[i]) cudaEventDestroy(e->ev_heads[i]);
@@ -864,12 +869,25 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
     if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 4 * 128 * 8 * sizeof(long long));
     auto recurrence = [&](const TensorLayer& L, const float* gi, int gi_cols, int gi_col0, const float* h_in, float* h_out, uint8_t* yimg, bool use_pdl) {
+        size_t slot = 0;
+        if (e->time_recurrence) {
+            if (e->rec_events_used == e->rec_events.size()) {
+                cudaEvent_t a, b;
+                cudaEventCreate(&a);
+                cudaEventCreate(&b);
+                e->rec_events.emplace_back(a, b);
+            }
+            slot = e->rec_events_used++;
+            cudaEventRecord(e->rec_events[slot].first, s);
+            use_pdl = false;
+        }
         if (nrec == 16)
             detail::launch(tc_recurrence_kernel<16>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl,
                            gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W, gi_cols, gi_col0, dbg_buf);
         else
             detail::launch(tc_recurrence_kernel<32>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl,
                            gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W, gi_cols, gi_col0, (long long*)nullptr);
+        if (e->time_recurrence) cudaEventRecord(e->rec_events[slot].second, s);
     };
     int chunk = 0;
     for (int i = 0; i + W <= T; i += J, ++chunk) {

@@ -94,7 +94,13 @@ class WindowPredictor(object):
         return int(self._lib.hb_launch_count(self._handle))
 
     def enable_kernel_timing(self, enable=True):
-        _native.check(self._lib.hb_enable_kernel_timing(self._handle, int(bool(enable))))
+        """True/1: bracket the whole launch sequence of each predict call; 2: also each recurrence launch."""
+        _native.check(self._lib.hb_enable_kernel_timing(self._handle, int(enable)))
+
+    def dominant_kernel_time_ms(self, reset=True):
+        total, n = ctypes.c_double(), ctypes.c_int64()
+        _native.check(self._lib.hb_dominant_kernel_time_ms(self._handle, ctypes.byref(total), ctypes.byref(n), int(reset)))
+        return total.value, n.value
 
     def kernel_time_ms(self, reset=True):
         total, n = ctypes.c_double(), ctypes.c_int64()

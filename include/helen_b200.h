@@ -134,6 +134,12 @@ int64_t hb_launch_count(const hb_handle *handle);
 int hb_enable_kernel_timing(hb_handle *handle, int enable);
 int hb_kernel_time_ms(hb_handle *handle, double *total_ms, int64_t *launches, int reset);
 
+/* With hb_enable_kernel_timing(handle, 2) every launch of the dominant kernel (the GRU recurrence,
+ * one launch = B windows x W dependent steps x 2 directions of one layer) is bracketed on its own;
+ * returns the accumulated milliseconds and the launch count since the last reset (synchronises).
+ * This mode disables launch overlap between kernels, so it is for measurement passes only. */
+int hb_dominant_kernel_time_ms(hb_handle *handle, double *total_ms, int64_t *launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif
