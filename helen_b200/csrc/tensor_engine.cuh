@@ -22,6 +22,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +44,12 @@ constexpr int H_LBO = 144;                        // k-group stride of h / y ima
 constexpr int YBLK = 16 * H_LBO;                  // 2304 B: [8 windows x 128 k] fp16 image of one direction
 constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)
 constexpr int GI_ROW_BYTES = G * 4;               // 1536 B: gi of one (window, t, direction)
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __host__ __device__ constexpr int64_t yimg_block(int64_t wg, int t, int W, int part) { return ((wg * W + t) * 2 + part) * (int64_t)YROW; }
 
@@ -84,17 +91,37 @@ constexpr int PROJ_NT = 64;
 constexpr int PROJ_STAGES = 2;
 constexpr int PROJ_W_COL0 = 128;
 
+struct ProjArgs {
+    const uint8_t* in_base; int64_t in_wg_stride, in_t_stride, in_part_stride;   // operand image addressing (bytes)
+    int blk_bytes, lbo, Kp; int64_t n_wg; int W;
+    const uint32_t* w_tmem;        // [6][hi, lo][128][Kp/2] packed fp16 pairs
+    const float* scale_row;        // [768]
+    const float* bias_row;         // [768]
+    float* gi;                     // [(b * W + t), 768]
+    // producer/consumer mode (fused with the encoder recurrence): column tiles are taken in the order
+    // the encoder finishes them and the loader waits on the recurrence CTAs' progress counters
+    const unsigned long long* progress; unsigned long long epoch; const int* tile_order; int rec_n;
+};
+
+// tile index -> (window group, column tile); all roles use the same mapping
+__device__ __forceinline__ void proj_tile(const ProjArgs& a, int64_t tile, int64_t& wg, int& t0) {
+    const int pos = (int)(tile / a.n_wg);
+    wg = tile % a.n_wg;
+    t0 = (a.tile_order ? a.tile_order[pos] : pos) * 8;
+}
+
 template <bool kSplitA>
-__global__ void __launch_bounds__(PROJ_THREADS, 1)
-tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, int64_t in_t_stride, int64_t in_part_stride,
-                     int blk_bytes, int lbo, int Kp, int64_t n_wg, int W,
-                     const uint32_t* __restrict__ w_tmem,    // [6][hi, lo][128][Kp/2] packed fp16 pairs
-                     const float* __restrict__ scale_row,    // [768]
-                     const float* __restrict__ bias_row,     // [768]
-                     float* __restrict__ gi)                 // [(b * W + t), 768]
+__device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem, const int blk, const int worker, const int n_workers)
 {
+    const uint8_t* __restrict__ in_base = a.in_base;
+    const int64_t in_wg_stride = a.in_wg_stride, in_t_stride = a.in_t_stride, in_part_stride = a.in_part_stride;
+    const int blk_bytes = a.blk_bytes, lbo = a.lbo, Kp = a.Kp, W = a.W;
+    const int64_t n_wg = a.n_wg;
+    const uint32_t* __restrict__ w_tmem = a.w_tmem;
+    const float* __restrict__ scale_row = a.scale_row;
+    const float* __restrict__ bias_row = a.bias_row;
+    float* __restrict__ gi = a.gi;
     constexpr int PARTS = kSplitA ? 2 : 1;
-    extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t part_bytes = 8u * blk_bytes;              // 8 row groups (columns t0..t0+7)
     const uint32_t stage_bytes = PARTS * part_bytes;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + PROJ_STAGES * stage_bytes);
@@ -104,7 +131,6 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int blk = blockIdx.y;
     const int kwords = Kp >> 1;
     tc::pdl_launch_dependents();
     if (tid == 0) {
@@ -115,7 +141,7 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
     __syncwarp();
     if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
-    __syncthreads();
+    tc::named_barrier_sync(1, PROJ_THREADS);
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     if (warp < 4) {   // weight block -> TMEM, thread = gate row
@@ -134,7 +160,7 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
     }
     tc::pdl_grid_dependency_wait();                          // activations / gi buffers belong to upstream kernels
     tc::tc_fence_before();
-    __syncthreads();
+    tc::named_barrier_sync(1, PROJ_THREADS);
     tc::tc_fence_after();
 
     const int tiles_t = (W + 7) >> 3;
@@ -142,12 +168,22 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
     if (warp == 5) {
         // ===================== loader =====================
         int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
             const int stage = it % PROJ_STAGES;
             if (it >= PROJ_STAGES) tc::mbar_wait(a_empty + stage, (uint32_t)((it / PROJ_STAGES - 1) & 1));
-            const int64_t wg = tile / tiles_t;
-            const int t0 = (int)(tile % tiles_t) * 8;
+            int64_t wg; int t0;
+            proj_tile(a, tile, wg, t0);
             const int valid = min(8, W - t0);
+            if (a.progress != nullptr) {
+                // the forward encoder must have passed column t0+valid-1, the reverse one column t0
+                if (lane < 2) {
+                    const unsigned long long need = a.epoch + (unsigned long long)(lane == 0 ? t0 + valid : W - t0);
+                    const unsigned long long* flag = a.progress + ((wg * WG) / a.rec_n) * 2 + lane;
+                    while (tc::ld_acquire_gpu(flag) < need) __nanosleep(200);
+                }
+                tc::fence_proxy_async_all();
+                __syncwarp();
+            }
             if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(valid * PARTS * blk_bytes));
             __syncwarp();
             if (lane < 8 * PARTS) {
@@ -163,7 +199,7 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
         const int ksteps = Kp >> 4;
         int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
             const int stage = it % PROJ_STAGES, acc = it & 1;
             tc::mbar_wait(a_full + stage, (uint32_t)((it / PROJ_STAGES) & 1));
             if (it >= 2) tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1));
@@ -189,23 +225,23 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
         const int row = blk * 128 + warp * 32 + lane;
         const float sc = scale_row[row], bi = bias_row[row];
         int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
             const int acc = it & 1;
-            const int64_t wg = tile / tiles_t;
-            const int t0 = (int)(tile % tiles_t) * 8;
+            int64_t wg; int t0;
+            proj_tile(a, tile, wg, t0);
             tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1));
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
-#pragma unroll
-            for (int c16 = 0; c16 < PROJ_NT; c16 += 16) {
-                float v[16];
-                tc::tmem_ld16(taddr + c16, v);
+#pragma unroll 2
+            for (int c8 = 0; c8 < PROJ_NT; c8 += 8) {       // 8 accumulator columns = the 8 windows of column t0 + c8/8
+                float v[8];
+                tc::tmem_ld8(taddr + c8, v);
                 tc::tmem_ld_wait();
+                const int t = t0 + (c8 >> 3);
+                if (t < W) {
+                    float* out = gi + ((wg * WG) * W + t) * (int64_t)(2 * G) + row;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = c16 + i, t = t0 + (c >> 3);
-                    const int64_t b = wg * WG + (c & 7);
-                    if (t < W) gi[(b * W + t) * (2 * G) + row] = fmaf(v[i], sc, bi);
+                    for (int i = 0; i < 8; ++i) out[(int64_t)i * W * (2 * G)] = fmaf(v[i], sc, bi);
                 }
             }
             tc::tc_fence_before();
@@ -214,8 +250,16 @@ tc_projection_kernel(const uint8_t* __restrict__ in_base, int64_t in_wg_stride, 
         }
     }
     tc::tc_fence_before();
-    __syncthreads();
+    tc::named_barrier_sync(1, PROJ_THREADS);
     if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
+template <bool kSplitA>
+__global__ void __launch_bounds__(PROJ_THREADS, 1)
+tc_projection_kernel(const ProjArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_proj[];
+    projection_role<kSplitA>(a, smem_proj, (int)blockIdx.y, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -238,47 +282,64 @@ constexpr int REC_GATE_WARPS = 16;
 constexpr int REC_TC_THREADS = (REC_GATE_WARPS + 3) * 32;
 constexpr int REC_W_COL0 = 128;                   // weight columns start here (accumulators below)
 constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate block][row][k pair]
-constexpr int GI_STAGES = 4;
+template <int N> __host__ __device__ constexpr int gi_stages() { return N <= 16 ? 4 : 3; }   // N = 32: 3 x 48 KB (227 KB smem limit)
+constexpr int PUBLISH_LAG = 4;
+
+struct RecArgs {
+    const float* gi;               // gi' rows; row of (window b, step column t) = b * gi_cols + gi_col0 + t
+    const uint32_t* whh_tmem;      // [2 dirs][hi, lo][3][128][64] packed fp16 pairs
+    const float* gate_consts;      // [2 dirs][4][128]: inv_r', inv_z', inv_n', b_hn'  (per unit)
+    const float* h_in;             // [B, 2, 128] fp32 or nullptr (zeros)
+    float* h_out;                  // [B, 2, 128] fp32
+    uint8_t* yimg;                 // operand image of the layer output
+    int64_t B; int W; int gi_cols, gi_col0;
+    unsigned long long* progress;  // [ctas][2 dirs] steps whose output has landed in yimg (+ epoch), or nullptr
+    unsigned long long epoch;
+    long long* dbg;
+};
 
 template <int N>
-__global__ void __launch_bounds__(REC_TC_THREADS, 1)
-tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t), 768]
-                     const uint32_t* __restrict__ whh_tmem, // [2 dirs][hi, lo][3][128][64] packed fp16 pairs
-                     const float* __restrict__ gate_consts, // [2 dirs][4][128]: inv_r', inv_z', inv_n', b_hn'  (per unit)
-                     const float* __restrict__ h_in,        // [B, 2, 128] fp32 or nullptr (zeros)
-                     float* __restrict__ h_out,             // [B, 2, 128] fp32
-                     uint8_t* __restrict__ yimg,            // operand image of the layer output
-                     int64_t B, int W,
-                     int gi_cols, int gi_col0,              // gi' row of (window b, step column t) = b * gi_cols + gi_col0 + t
-                     long long* __restrict__ dbg = nullptr)
+__device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem, const int cta_x, const int dir)
 {
-#define HB_DBG(role, s, k) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
+    const float* __restrict__ gi = ra.gi;
+    const uint32_t* __restrict__ whh_tmem = ra.whh_tmem;
+    const float* __restrict__ gate_consts = ra.gate_consts;
+    const float* __restrict__ h_in = ra.h_in;
+    float* __restrict__ h_out = ra.h_out;
+    uint8_t* __restrict__ yimg = ra.yimg;
+    const int64_t B = ra.B;
+    const int W = ra.W, gi_cols = ra.gi_cols, gi_col0 = ra.gi_col0;
+    long long* __restrict__ dbg = ra.dbg;
+#define HB_DBG(role, s, k) do { if (dbg && cta_x == 0 && dir == 0 && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N windows per CTA (3N accumulator columns must stay below REC_W_COL0)");
     constexpr int NW = N / 4;                                // windows per gate thread
     constexpr int NG = N / WG;                               // window groups per CTA
     constexpr uint32_t HB_BYTES = NG * YBLK;                 // one h operand image (hi or lo)
     constexpr uint32_t GI_STAGE_BYTES = N * GI_ROW_BYTES;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* h_hi = smem;
-    uint8_t* h_lo = smem + HB_BYTES;
-    uint8_t* gi_s = smem + 2 * HB_BYTES;
+    constexpr int GI_STAGES = gi_stages<N>();
+    // h operand images, double buffered: step s reads buffer s&1 (h_s) and writes buffer (s+1)&1 (h_{s+1}),
+    // so the y store of an image has two steps to drain before the buffer is written again
+    uint8_t* h_img = smem;                                   // [2 buffers][hi, lo][HB_BYTES]
+    uint8_t* gi_s = smem + 4 * HB_BYTES;
     uint64_t* acc_ready = reinterpret_cast<uint64_t*>(gi_s + GI_STAGES * GI_STAGE_BYTES);   // [3]: r, z, n blocks
     uint64_t* h_ready = acc_ready + 3;
-    uint64_t* h_free = h_ready + 1;
-    uint64_t* gi_full = h_free + 1;
+    uint64_t* h_free = h_ready + 1;                          // [2], one per buffer: its y store has drained
+    uint64_t* y_ready = h_free + 2;                          // [2], one per buffer: image complete (for the store warp;
+                                                             // per-buffer so a lagging store warp cannot alias phases)
+    uint64_t* gi_full = y_ready + 2;
     uint64_t* gi_empty = gi_full + GI_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gi_empty + GI_STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int dir = blockIdx.y;
-    const int64_t b0 = (int64_t)blockIdx.x * N;
+    const int64_t b0 = (int64_t)cta_x * N;
     const int t_first = dir ? W - 1 : 0, dt = dir ? -1 : 1;
 
     tc::pdl_launch_dependents();
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) tc::mbar_init(acc_ready + i, 1);
         tc::mbar_init(h_ready, REC_GATE_WARPS);
-        tc::mbar_init(h_free, 1);
+        tc::mbar_init(h_free + 0, 1); tc::mbar_init(h_free + 1, 1);
+        tc::mbar_init(y_ready + 0, REC_GATE_WARPS); tc::mbar_init(y_ready + 1, REC_GATE_WARPS);
         for (int i = 0; i < GI_STAGES; ++i) { tc::mbar_init(gi_full + i, 1); tc::mbar_init(gi_empty + i, REC_GATE_WARPS); }
         tc::mbar_fence_init();
     }
@@ -305,18 +366,30 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
         // ===================== y store: the h image of step s is the layer output at column t_s ====
         tc::pdl_grid_dependency_wait();
         __syncthreads();
+        unsigned long long* flag = ra.progress ? ra.progress + (size_t)cta_x * 2 + dir : nullptr;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
-            tc::mbar_wait(h_ready, (uint32_t)(s & 1));
+            const int buf = (s + 1) & 1;                     // the image written during step s
+            tc::mbar_wait(y_ready + buf, (uint32_t)((s >> 1) & 1));
             if (lane < 2 * NG) {
                 const int g = lane >> 1, part = lane & 1;
-                tc::bulk_s2g(yimg + yimg_block(b0 / WG + g, t, W, part) + dir * YBLK, (part ? h_lo : h_hi) + g * YBLK, YBLK);
+                tc::bulk_s2g(yimg + yimg_block(b0 / WG + g, t, W, part) + dir * YBLK, h_img + (buf * 2 + part) * HB_BYTES + g * YBLK, YBLK);
                 tc::bulk_commit();
                 tc::bulk_wait_read0();
             }
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(h_free);
+            if (lane == 0) tc::mbar_arrive(h_free + buf);
+            if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG) & 3) == 0) {
+                // every 4th step: all stores but the newest PUBLISH_LAG have landed in global memory, publish
+                // that many completed columns to the projection CTAs.  (Waiting for the newest store, or
+                // fencing every step, would put a global round trip on the step's critical path via h_free.)
+                if (lane < 2 * NG) { tc::bulk_wait_pending<PUBLISH_LAG>(); tc::fence_proxy_async_all(); }
+                __syncwarp();
+                if (lane == 0) tc::st_release_gpu(flag, ra.epoch + (unsigned long long)(s + 1 - PUBLISH_LAG));
+            }
         }
-        if (lane < 2 * NG) tc::bulk_wait0();
+        if (lane < 2 * NG) { tc::bulk_wait0(); tc::fence_proxy_async_all(); }
+        __syncwarp();
+        if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, ra.epoch + (unsigned long long)W);
     } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
         // Measured (HB_DEBUG_TIMELINE): an M=128, N=16, K=16 MMA occupies the tensor pipe ~13 cycles, so
@@ -327,13 +400,14 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
         const uint32_t idesc = tc::idesc_f16_f32(128, N);
-        const uint64_t hhi_desc = tc::smem_desc(tc::smem_u32(h_hi), H_LBO, YBLK);
-        const uint64_t hlo_desc = tc::smem_desc(tc::smem_u32(h_lo), H_LBO, YBLK);
+        const uint64_t himg_desc = tc::smem_desc(tc::smem_u32(h_img), H_LBO, YBLK);
         for (int s = 0; s < W; ++s) {
             if (s > 0) {
                 tc::mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
                 tc::tc_fence_after();
             }
+            const uint64_t hhi_desc = himg_desc + (uint64_t)(((s & 1) * 2 + 0) * HB_BYTES / 16);
+            const uint64_t hlo_desc = himg_desc + (uint64_t)(((s & 1) * 2 + 1) * HB_BYTES / 16);
             HB_DBG(0, s, 0);
             if (tc::elect_one()) {
 #pragma unroll
@@ -385,8 +459,8 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
             h_off[i] = tc::core_offset(win0 + i, j, H_LBO, YBLK);
             __half hi, lo;
             tc::split_f16(h_own[i], hi, lo);
-            *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
-            *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
+            *reinterpret_cast<__half*>(h_img + h_off[i]) = hi;                      // h_0 -> buffer 0
+            *reinterpret_cast<__half*>(h_img + HB_BYTES + h_off[i]) = lo;
         }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
@@ -422,7 +496,9 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, giz[i])));
-            if (s > 0) tc::mbar_wait(h_free, (uint32_t)((s - 1) & 1));   // previous image has been read by the store
+            uint8_t* h_hi = h_img + (((s + 1) & 1) * 2) * HB_BYTES;            // image of h_{s+1}
+            uint8_t* h_lo = h_hi + HB_BYTES;
+            if (s >= 2) tc::mbar_wait(h_free + ((s + 1) & 1), (uint32_t)(((s - 2) >> 1) & 1));   // its store of step s-2 has drained
             tc::mbar_wait(acc_ready + 2, par);
             if (drole < 3) HB_DBG(drole, s, 3);
             tc::tc_fence_after();
@@ -444,7 +520,7 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(h_ready);
+            if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + ((s + 1) & 1)); }
             if (drole < 3) HB_DBG(drole, s, 6);
         }
 #pragma unroll
@@ -454,6 +530,36 @@ tc_recurrence_kernel(const float* __restrict__ gi,          // gi' [(b * W + t),
     tc::tc_fence_before();
     __syncthreads();
     if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
+}
+
+template <int N>
+__global__ void __launch_bounds__(REC_TC_THREADS, 1)
+tc_recurrence_kernel(const RecArgs ra)
+{
+    extern __shared__ __align__(128) uint8_t smem_rec[];
+    recurrence_role<N>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// Encoder recurrence and decoder input projection in ONE launch: CTAs [0, 2 * rec_ctas) run the
+// recurrence, the others hold the decoder's W_ih blocks in TMEM and project column tiles as soon
+// as both encoder directions have stored them (progress counters in global memory), so that when
+// the encoder's last step retires only the two edge tiles are left.  All CTAs are co-resident
+// (grid <= SM count, one CTA per SM), which makes spinning on the counters safe.
+template <int N>
+__global__ void __launch_bounds__(REC_TC_THREADS, 1)
+tc_encoder_fused_kernel(const RecArgs ra, const ProjArgs pa, const int rec_ctas, const int proj_workers)
+{
+    extern __shared__ __align__(128) uint8_t smem_fused[];
+    const int bid = (int)blockIdx.x;
+    if (bid < 2 * rec_ctas) {
+        recurrence_role<N>(ra, smem_fused, bid >> 1, bid & 1);
+        if (ra.dbg && threadIdx.x == 0) atomicMax((unsigned long long*)ra.dbg + 4 * 128 * 8 - 2, globaltimer_ns());   // last recurrence CTA done
+    } else {
+        if (threadIdx.x >= PROJ_THREADS) return;
+        const int pb = bid - 2 * rec_ctas;
+        projection_role<true>(pa, smem_fused, pb % 6, pb / 6, proj_workers);
+        if (ra.dbg && threadIdx.x == 0) atomicMax((unsigned long long*)ra.dbg + 4 * 128 * 8 - 1, globaltimer_ns());   // last projection CTA done
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -590,6 +696,11 @@ struct TensorLayer {
 };
 
 struct TensorEngine {
+    unsigned long long* progress = nullptr;   // [<= sm_count][2] encoder progress counters of the fused launch
+    int* tile_order = nullptr;                // column-tile order of the fused projection (earliest complete first)
+    int tile_order_w = -1;
+    std::vector<int> tile_order_host;
+    unsigned long long launch_epoch = 0;
     // optional device timing of every recurrence launch (the dominant kernel), bench.py's roofline pass
     bool time_recurrence = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> rec_events;
@@ -749,7 +860,7 @@ inline void free_layer(TensorLayer* L) {
 
 inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 128; }
 template <int N>
-constexpr size_t recurrence_smem() { return (size_t)2 * (N / WG) * YBLK + (size_t)GI_STAGES * N * GI_ROW_BYTES + 256; }
+constexpr size_t recurrence_smem() { return (size_t)4 * (N / WG) * YBLK + (size_t)gi_stages<N>() * N * GI_ROW_BYTES + 512; }
 constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128; }
 
 }  // namespace detail
@@ -760,6 +871,8 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     detail::free_layer(&e->dec);
     cudaFree(e->head_img);
     cudaFree(e->b_head);
+    cudaFree(e->progress);
+    cudaFree(e->tile_order);
     if (e->side) cudaStreamDestroy(e->side);
     for (auto& ev : e->rec_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (int i = 0; i < 2; ++i) {
@@ -806,6 +919,10 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_recurrence_kernel<16>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<32>, detail::recurrence_smem<32>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
+        set((const void*)tc_encoder_fused_kernel<16>, std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)));
+        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->progress), (size_t)sm_count * 2 * sizeof(unsigned long long));
+        if (ce == cudaSuccess) ce = cudaMemset(e->progress, 0, (size_t)sm_count * 2 * sizeof(unsigned long long));
+        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order), 4096 * sizeof(int));
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
         for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
             ce = cudaEventCreateWithFlags(&e->ev_dec[i], cudaEventDisableTiming);
@@ -853,9 +970,11 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         const int blocks = (int)std::min<int64_t>((chunks16 + 255) / 256, (int64_t)e->sm_count * 16);
         pileup_to_operand_image_kernel<<<blocks, 256, 0, s>>>(images, B, T, F, e->enc.Kp, ws.ximg, n_wg);
         const int tiles = (int)std::min<int64_t>(n_wg * ((enc_cols + 7) / 8), proj_workers);
-        detail::launch(tc_projection_kernel<false>, dim3(tiles, 6), dim3(PROJ_THREADS), detail::projection_smem(xblk, 1), s, pdl,
-                       reinterpret_cast<const uint8_t*>(ws.ximg), (int64_t)T * xblk, xblk, 0, xblk, 128, e->enc.Kp, n_wg, enc_cols,
-                       e->enc.wih_tmem, e->enc.scale_row, e->enc.bias_row, ws.gi_enc);
+        ProjArgs pe{};
+        pe.in_base = reinterpret_cast<const uint8_t*>(ws.ximg); pe.in_wg_stride = (int64_t)T * xblk; pe.in_t_stride = xblk; pe.in_part_stride = 0;
+        pe.blk_bytes = xblk; pe.lbo = 128; pe.Kp = e->enc.Kp; pe.n_wg = n_wg; pe.W = enc_cols;
+        pe.w_tmem = e->enc.wih_tmem; pe.scale_row = e->enc.scale_row; pe.bias_row = e->enc.bias_row; pe.gi = ws.gi_enc;
+        detail::launch(tc_projection_kernel<false>, dim3(tiles, 6), dim3(PROJ_THREADS), detail::projection_smem(xblk, 1), s, pdl, pe);
         launches += 2;
     }
     const float* hid = nullptr;
@@ -868,7 +987,36 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     static long long* dbg_buf = nullptr;
     static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
     if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 4 * 128 * 8 * sizeof(long long));
-    auto recurrence = [&](const TensorLayer& L, const float* gi, int gi_cols, int gi_col0, const float* h_in, float* h_out, uint8_t* yimg, bool use_pdl) {
+    // decoder projection arguments (the same for every chunk)
+    ProjArgs pd{};
+    pd.in_base = ws.yimg1; pd.in_wg_stride = (int64_t)W * 2 * YROW; pd.in_t_stride = 2 * YROW; pd.in_part_stride = YROW;
+    pd.blk_bytes = YROW; pd.lbo = H_LBO; pd.Kp = e->dec.Kp; pd.n_wg = n_wg; pd.W = W;
+    pd.w_tmem = e->dec.wih_tmem; pd.scale_row = e->dec.scale_row; pd.bias_row = e->dec.bias_row; pd.gi = ws.gi;
+    // fused encoder + projection launch when the recurrence leaves at least half of the SMs free
+    const int rec_ctas = (int)grid_rec.x;
+    const int fused_workers = (e->sm_count - 2 * rec_ctas) / 6;
+    static const bool fuse_allowed = getenv("HB_NO_FUSED") == nullptr;
+    const bool fused = fuse_allowed && nrec == 16 && fused_workers >= 8 && (W + 7) / 8 <= 4096 && !e->time_recurrence;
+    if (fused && e->tile_order_w != W) {
+        // column tile tt is complete once the forward pass is past column 8tt+7 and the reverse pass past 8tt
+        const int tiles_t = (W + 7) / 8;
+        std::vector<int>& order = e->tile_order_host;             // outlives the async copy
+        order.resize(tiles_t);
+        for (int i = 0; i < tiles_t; ++i) order[i] = i;
+        auto ready = [&](int tt) { return std::max(std::min(8 * tt + 8, W), W - 8 * tt); };
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ready(x) < ready(y); });
+        cudaMemcpyAsync(e->tile_order, order.data(), tiles_t * sizeof(int), cudaMemcpyHostToDevice, s);
+        e->tile_order_w = W;
+    }
+    auto rec_args = [&](const TensorLayer& L, const float* gi, int gi_cols, int gi_col0, const float* h_in, float* h_out, uint8_t* yimg) {
+        RecArgs ra{};
+        ra.gi = gi; ra.whh_tmem = L.whh_tmem; ra.gate_consts = L.gate_consts; ra.h_in = h_in; ra.h_out = h_out; ra.yimg = yimg;
+        ra.B = B; ra.W = W; ra.gi_cols = gi_cols; ra.gi_col0 = gi_col0; ra.progress = nullptr; ra.epoch = 0;
+        static const bool dbg_enc = getenv("HB_DEBUG_TIMELINE") != nullptr && getenv("HB_DEBUG_TIMELINE")[0] == 'e';
+        ra.dbg = (nrec == 16 && (dbg_enc == (&L == &e->enc))) ? dbg_buf : nullptr;
+        return ra;
+    };
+    auto recurrence = [&](const RecArgs& ra, bool use_pdl) {
         size_t slot = 0;
         if (e->time_recurrence) {
             if (e->rec_events_used == e->rec_events.size()) {
@@ -882,11 +1030,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             use_pdl = false;
         }
         if (nrec == 16)
-            detail::launch(tc_recurrence_kernel<16>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl,
-                           gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W, gi_cols, gi_col0, dbg_buf);
+            detail::launch(tc_recurrence_kernel<16>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl, ra);
         else
-            detail::launch(tc_recurrence_kernel<32>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl,
-                           gi, L.whh_tmem, L.gate_consts, h_in, h_out, yimg, B, W, gi_cols, gi_col0, (long long*)nullptr);
+            detail::launch(tc_recurrence_kernel<32>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl, ra);
         if (e->time_recurrence) cudaEventRecord(e->rec_events[slot].second, s);
     };
     int chunk = 0;
@@ -895,16 +1041,25 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         float* dec_h = hid_bufs[flip ^ 1];
         const int buf = chunk & 1;
         if (chunk >= 2) cudaStreamWaitEvent(s, e->ev_heads[buf], 0);      // heads(chunk - 2) has read this yimg2 buffer
-        recurrence(e->enc, ws.gi_enc, enc_cols, i, hid, enc_h, ws.yimg1, pdl && chunk == 0);
-        detail::launch(tc_projection_kernel<true>, dim3(tiles_proj, 6), dim3(PROJ_THREADS), detail::projection_smem(YROW, 2), s, pdl,
-                       (const uint8_t*)ws.yimg1, (int64_t)W * 2 * YROW, (int64_t)2 * YROW, (int64_t)YROW, YROW, H_LBO, e->dec.Kp, n_wg, W,
-                       e->dec.wih_tmem, e->dec.scale_row, e->dec.bias_row, ws.gi);
-        recurrence(e->dec, ws.gi, W, 0, enc_h, dec_h, ws.yimg2[buf], pdl);
+        RecArgs renc = rec_args(e->enc, ws.gi_enc, enc_cols, i, hid, enc_h, ws.yimg1);
+        if (fused) {
+            renc.progress = e->progress;
+            renc.epoch = (++e->launch_epoch) << 20;
+            ProjArgs pf = pd;
+            pf.progress = e->progress; pf.epoch = renc.epoch; pf.tile_order = e->tile_order; pf.rec_n = nrec;
+            detail::launch(tc_encoder_fused_kernel<16>, dim3(2 * rec_ctas + 6 * fused_workers), dim3(REC_TC_THREADS),
+                           std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)), s, pdl && chunk == 0,
+                           renc, pf, rec_ctas, fused_workers);
+        } else {
+            recurrence(renc, pdl && chunk == 0);
+            detail::launch(tc_projection_kernel<true>, dim3(tiles_proj, 6), dim3(PROJ_THREADS), detail::projection_smem(YROW, 2), s, pdl, pd);
+        }
+        recurrence(rec_args(e->dec, ws.gi, W, 0, enc_h, dec_h, ws.yimg2[buf]), pdl);
         cudaEventRecord(e->ev_dec[buf], s);
         cudaStreamWaitEvent(e->side, e->ev_dec[buf], 0);
         tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), e->side>>>(ws.yimg2[buf], n_wg, B, W, T, i, e->head_img, e->b_head, e->head_inv, p_base, p_rle);
         cudaEventRecord(e->ev_heads[buf], e->side);
-        launches += 4;
+        launches += fused ? 3 : 4;
         hid = dec_h;
         flip ^= 1;
     }
@@ -929,6 +1084,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 acc[15] += at(0, st + 1, 0) - base;               // full step
             }
             fprintf(stderr, "[timeline, cycles after MMA warp release] issue_done=%.0f step=%.0f\n", acc[0] / n, acc[15] / n);
+            fprintf(stderr, "  fused launch: last projection CTA finished %.1f us after the last recurrence CTA\n",
+                    (double)(hbuf[4 * 128 * 8 - 1] - hbuf[4 * 128 * 8 - 2]) * 1e-3);
             for (int role = 1; role <= 2; ++role) {
                 fprintf(stderr, "  gate warp %s:", role == 1 ? "0 " : "15");
                 const char* names[7] = {"gi_full", "acc_r", "acc_z", "acc_n", "ldtm_n", "math_done", "arrived"};
