@@ -15,6 +15,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
@@ -64,6 +67,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 }
 __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until_ge(const unsigned long long* flag, unsigned long long need) {
+    while (ld_acquire_gpu(flag) < need) __nanosleep(100);
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 template <int kPending>
@@ -157,6 +166,19 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
                  : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
+    uint32_t r[2];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+    v[0] = __uint_as_float(r[0]);
+    v[1] = __uint_as_float(r[1]);
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
+    static_assert(kCols == 2 || kCols == 4 || kCols == 8, "columns per thread");
+    if constexpr (kCols == 2) tmem_ld2(taddr, v);
+    else if constexpr (kCols == 4) tmem_ld4(taddr, v);
+    else tmem_ld8(taddr, v);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];

@@ -101,6 +101,9 @@ struct ProjArgs {
     // producer/consumer mode (fused with the encoder recurrence): column tiles are taken in the order
     // the encoder finishes them and the loader waits on the recurrence CTAs' progress counters
     const unsigned long long* progress; unsigned long long epoch; const int* tile_order; int rec_n;
+    // persistent mode: the role walks n_chunks chunks; a chunk's columns count from chunk * W in the progress
+    // counters, and every finished tile is announced to the decoder CTAs (4 epilogue warps -> +4 per tile and block)
+    int n_chunks; unsigned long long* tile_flags;
 };
 
 // tile index -> (window group, column tile); all roles use the same mapping
@@ -165,9 +168,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 
     const int tiles_t = (W + 7) >> 3;
     const int64_t n_tiles = n_wg * tiles_t;
+    const int n_chunks = a.n_chunks > 0 ? a.n_chunks : 1;
     if (warp == 5) {
         // ===================== loader =====================
         int it = 0;
+        for (int chunk = 0; chunk < n_chunks; ++chunk)
         for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
             const int stage = it % PROJ_STAGES;
             if (it >= PROJ_STAGES) tc::mbar_wait(a_empty + stage, (uint32_t)((it / PROJ_STAGES - 1) & 1));
@@ -177,7 +182,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             if (a.progress != nullptr) {
                 // the forward encoder must have passed column t0+valid-1, the reverse one column t0
                 if (lane < 2) {
-                    const unsigned long long need = a.epoch + (unsigned long long)(lane == 0 ? t0 + valid : W - t0);
+                    const unsigned long long need = a.epoch + (unsigned long long)chunk * W + (unsigned long long)(lane == 0 ? t0 + valid : W - t0);
                     const unsigned long long* flag = a.progress + ((wg * WG) / a.rec_n) * 2 + lane;
                     while (tc::ld_acquire_gpu(flag) < need) __nanosleep(200);
                 }
@@ -199,6 +204,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
         const int ksteps = Kp >> 4;
         int it = 0;
+        for (int chunk = 0; chunk < n_chunks; ++chunk)
         for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
             const int stage = it % PROJ_STAGES, acc = it & 1;
             tc::mbar_wait(a_full + stage, (uint32_t)((it / PROJ_STAGES) & 1));
@@ -225,6 +231,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const int row = blk * 128 + warp * 32 + lane;
         const float sc = scale_row[row], bi = bias_row[row];
         int it = 0;
+        for (int chunk = 0; chunk < n_chunks; ++chunk)
         for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
             const int acc = it & 1;
             int64_t wg; int t0;
@@ -247,6 +254,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + acc);
+            if (a.tile_flags != nullptr) {                   // gi' rows of this tile are in global memory
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) tc::red_release_gpu_add(a.tile_flags + ((wg * tiles_t + (t0 >> 3)) * 2 + blk / 3), 1ull);
+            }
         }
     }
     tc::tc_fence_before();
@@ -296,26 +308,38 @@ struct RecArgs {
     unsigned long long* progress;  // [ctas][2 dirs] steps whose output has landed in yimg (+ epoch), or nullptr
     unsigned long long epoch;
     long long* dbg;
+    // persistent mode (one launch walks n_chunks chunks of the reference loop; 0/1 = single chunk):
+    int n_chunks; int gi_col_step;               // chunk k reads gi' columns gi_col0 + k * gi_col_step + t
+    const float* h_in_next;                      // h_in of chunks k > 0 (written by the other layer's CTA)
+    uint8_t* yimg_odd;                           // output image of odd chunks (nullptr: same as yimg)
+    const unsigned long long* wait_done; int wait_done_bias;   // chunk k starts when wait_done[cta][dir] >= k + bias
+    unsigned long long* publish_done;            // [cta][dir] = chunks finished (h_out visible)
+    const unsigned long long* tile_flags; int tiles_t;         // decoder: gi' tile (group, tile, dir) ready at >= 12 (k + 1)
+    const unsigned long long* heads_done; int heads_per_chunk; // decoder: yimg buffer reusable when >= heads_per_chunk (k - 1)
+    int n_wg;                                    // existing window groups (flags of groups past it are never raised)
+    int dbg_role;                                // HB_DEBUG_TIMELINE: 0 encoder, 1 decoder
 };
 
-template <int N>
+// NLIVE <= N windows of the N accumulator columns are real: the MMA shape needs N >= 16, but with 8 live windows
+// per CTA a small batch spreads over twice as many SMs and the exposed gate math (MUFU-bound) halves.
+template <int N, int NLIVE>
 __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem, const int cta_x, const int dir)
 {
     const float* __restrict__ gi = ra.gi;
     const uint32_t* __restrict__ whh_tmem = ra.whh_tmem;
     const float* __restrict__ gate_consts = ra.gate_consts;
-    const float* __restrict__ h_in = ra.h_in;
     float* __restrict__ h_out = ra.h_out;
-    uint8_t* __restrict__ yimg = ra.yimg;
     const int64_t B = ra.B;
-    const int W = ra.W, gi_cols = ra.gi_cols, gi_col0 = ra.gi_col0;
+    const int W = ra.W, gi_cols = ra.gi_cols;
+    const int n_chunks = ra.n_chunks > 0 ? ra.n_chunks : 1;
     long long* __restrict__ dbg = ra.dbg;
 #define HB_DBG(role, s, k) do { if (dbg && cta_x == 0 && dir == 0 && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
-    static_assert(N == 16 || N == 32, "N windows per CTA (3N accumulator columns must stay below REC_W_COL0)");
-    constexpr int NW = N / 4;                                // windows per gate thread
-    constexpr int NG = N / WG;                               // window groups per CTA
-    constexpr uint32_t HB_BYTES = NG * YBLK;                 // one h operand image (hi or lo)
-    constexpr uint32_t GI_STAGE_BYTES = N * GI_ROW_BYTES;
+    static_assert(N == 16 || N == 32, "N accumulator columns per gate block (3N must stay below REC_W_COL0)");
+    static_assert(NLIVE == N || (N == 16 && NLIVE == 8), "live windows per CTA");
+    constexpr int NW = NLIVE / 4;                            // windows per gate thread
+    constexpr int NG = NLIVE / WG;                           // live window groups per CTA
+    constexpr uint32_t HB_BYTES = (N / WG) * YBLK;           // one h operand image (hi or lo), all N columns
+    constexpr uint32_t GI_STAGE_BYTES = NLIVE * GI_ROW_BYTES;
     constexpr int GI_STAGES = gi_stages<N>();
     // h operand images, double buffered: step s reads buffer s&1 (h_s) and writes buffer (s+1)&1 (h_{s+1}),
     // so the y store of an image has two steps to drain before the buffer is written again
@@ -331,10 +355,14 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gi_empty + GI_STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t b0 = (int64_t)cta_x * N;
+    const int64_t b0 = (int64_t)cta_x * NLIVE;
     const int t_first = dir ? W - 1 : 0, dt = dir ? -1 : 1;
 
     tc::pdl_launch_dependents();
+    if constexpr (NLIVE < N) {                               // dead accumulator columns: keep their operand rows finite
+        for (uint32_t i = tid; i < 4 * HB_BYTES / 16; i += REC_TC_THREADS) reinterpret_cast<int4*>(h_img)[i] = make_int4(0, 0, 0, 0);
+        tc::fence_proxy_async_smem();
+    }
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) tc::mbar_init(acc_ready + i, 1);
         tc::mbar_init(h_ready, REC_GATE_WARPS);
@@ -350,21 +378,76 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    if (warp < 8) {   // W_hh -> TMEM (once): warps 0-3 store the hi image, warps 4-7 the lo image; thread = row j
+        const int q = warp & 3, j = q * 32 + lane, term = warp >> 2;
+        const uint32_t* src = whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64;
+#pragma unroll 1
+        for (int gb = 0; gb < 3; ++gb) {
+#pragma unroll
+            for (int c = 0; c < 64; c += 16) {
+                uint32_t r[16];
+                const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64 + c);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) { const uint4 x = p[v]; r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                tc::tmem_st16(tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + c, r);
+            }
+        }
+        tc::tmem_st_wait();
+    }
+    tc::pdl_grid_dependency_wait();                          // everything below touches upstream kernels' buffers
+
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const float* __restrict__ h_in = chunk == 0 ? ra.h_in : ra.h_in_next;
+    uint8_t* __restrict__ yimg = ((chunk & 1) && ra.yimg_odd) ? ra.yimg_odd : ra.yimg;
+    const int gi_col0 = ra.gi_col0 + chunk * ra.gi_col_step;
+    const unsigned long long prog_base = ra.epoch + (unsigned long long)chunk * W;
+    if (chunk > 0 || ra.wait_done != nullptr) {
+        // chunk boundary of the persistent kernel: fresh barriers, then wait for the upstream layer
+        if (tid == 0) {
+            if (chunk > 0) {
+                for (int i = 0; i < 3; ++i) { tc::mbar_inval(acc_ready + i); tc::mbar_init(acc_ready + i, 1); }
+                tc::mbar_inval(h_ready); tc::mbar_init(h_ready, REC_GATE_WARPS);
+                for (int i = 0; i < 2; ++i) {
+                    tc::mbar_inval(h_free + i); tc::mbar_init(h_free + i, 1);
+                    tc::mbar_inval(y_ready + i); tc::mbar_init(y_ready + i, REC_GATE_WARPS);
+                }
+                for (int i = 0; i < GI_STAGES; ++i) {
+                    tc::mbar_inval(gi_full + i); tc::mbar_init(gi_full + i, 1);
+                    tc::mbar_inval(gi_empty + i); tc::mbar_init(gi_empty + i, REC_GATE_WARPS);
+                }
+                tc::mbar_fence_init();
+            }
+            if (ra.wait_done != nullptr && chunk + ra.wait_done_bias > 0)
+                tc::spin_until_ge(ra.wait_done + (size_t)cta_x * 2 + dir, (unsigned long long)(chunk + ra.wait_done_bias));
+            if (ra.heads_done != nullptr && chunk >= 2)
+                for (int g = 0; g < NG; ++g)
+                    if (cta_x * NG + g < ra.n_wg)
+                        tc::spin_until_ge(ra.heads_done + (size_t)cta_x * NG + g, (unsigned long long)ra.heads_per_chunk * (chunk - 1));
+        }
+        __syncthreads();
+    }
+    if (dbg && n_chunks > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (ra.dbg_role * 64 + chunk) * 2] = (long long)globaltimer_ns();
+
     if (warp == REC_GATE_WARPS + 1) {
         // ===================== gi loader: bulk copies, GI_STAGES steps ahead =====================
-        tc::pdl_grid_dependency_wait();
         __syncthreads();
         const float* src0 = gi + ((b0 + lane) * gi_cols + gi_col0) * (int64_t)(2 * G) + dir * G;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % GI_STAGES;
+            if (ra.tile_flags != nullptr && (s == 0 || (t & 7) == (dir ? 7 : 0))) {
+                // decoder in the persistent kernel: the projection CTAs announce finished gi' tiles
+                if (lane < NG && cta_x * NG + lane < ra.n_wg)
+                    tc::spin_until_ge(ra.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 12ull * (chunk + 1));
+                tc::fence_proxy_async_all();
+                __syncwarp();
+            }
             if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
             if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, GI_STAGE_BYTES);
             __syncwarp();
-            if (lane < N) tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + lane * GI_ROW_BYTES, src0 + (int64_t)t * (2 * G), GI_ROW_BYTES, gi_full + stage);
+            if (lane < NLIVE) tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + lane * GI_ROW_BYTES, src0 + (int64_t)t * (2 * G), GI_ROW_BYTES, gi_full + stage);
         }
     } else if (warp == REC_GATE_WARPS + 2) {
         // ===================== y store: the h image of step s is the layer output at column t_s ====
-        tc::pdl_grid_dependency_wait();
         __syncthreads();
         unsigned long long* flag = ra.progress ? ra.progress + (size_t)cta_x * 2 + dir : nullptr;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
@@ -384,19 +467,18 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 // fencing every step, would put a global round trip on the step's critical path via h_free.)
                 if (lane < 2 * NG) { tc::bulk_wait_pending<PUBLISH_LAG>(); tc::fence_proxy_async_all(); }
                 __syncwarp();
-                if (lane == 0) tc::st_release_gpu(flag, ra.epoch + (unsigned long long)(s + 1 - PUBLISH_LAG));
+                if (lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)(s + 1 - PUBLISH_LAG));
             }
         }
         if (lane < 2 * NG) { tc::bulk_wait0(); tc::fence_proxy_async_all(); }
         __syncwarp();
-        if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, ra.epoch + (unsigned long long)W);
+        if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)W);
     } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
         // Measured (HB_DEBUG_TIMELINE): an M=128, N=16, K=16 MMA occupies the tensor pipe ~13 cycles, so
         // the 72 MMAs of a step take ~1000 cycles however they are issued (a second issuer warp and an
         // issue order rotating over the gate blocks were both slower); per-block commits let the gate
         // warps overlap the r and z sigmoids with the remaining MMAs.
-        tc::pdl_grid_dependency_wait();
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
         const uint32_t idesc = tc::idesc_f16_f32(128, N);
@@ -431,31 +513,14 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         const int q = warp & 3;
         const int j = q * 32 + lane;
         const int win0 = (warp >> 2) * NW;
-        if (warp < 8) {   // W_hh -> TMEM: warps 0-3 store the hi image, warps 4-7 the lo image; thread = row j
-            const int term = warp >> 2;
-            const uint32_t* src = whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64;
-#pragma unroll 1
-            for (int gb = 0; gb < 3; ++gb) {
-#pragma unroll
-                for (int c = 0; c < 64; c += 16) {
-                    uint32_t r[16];
-                    const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64 + c);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) { const uint4 x = p[v]; r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-                    tc::tmem_st16(tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + c, r);
-                }
-            }
-            tc::tmem_st_wait();
-        }
         const float* gc = gate_consts + (size_t)dir * 4 * H + j;
         const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
-        tc::pdl_grid_dependency_wait();                      // h_in, gi', yimg belong to upstream kernels
         float h_own[NW];                                     // h * 2^10
         uint32_t h_off[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
             const int64_t b = b0 + win0 + i;
-            h_own[i] = (h_in != nullptr && b < B) ? h_in[(b * 2 + dir) * H + j] * ACT_SCALE : 0.f;
+            h_own[i] = (h_in != nullptr && b < B) ? __ldcg(h_in + (b * 2 + dir) * H + j) * ACT_SCALE : 0.f;   // L2: may come from another SM
             h_off[i] = tc::core_offset(win0 + i, j, H_LBO, YBLK);
             __half hi, lo;
             tc::split_f16(h_own[i], hi, lo);
@@ -485,14 +550,14 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::mbar_wait(acc_ready + 0, par);
             if (drole < 3) HB_DBG(drole, s, 1);
             tc::tc_fence_after();
-            if constexpr (NW == 4) tc::tmem_ld4(taddr, a); else tc::tmem_ld8(taddr, a);
+            tc::tmem_ld_n<NW>(taddr, a);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < NW; ++i) r[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_r, gir[i])));
             tc::mbar_wait(acc_ready + 1, par);
             if (drole < 3) HB_DBG(drole, s, 2);
             tc::tc_fence_after();
-            if constexpr (NW == 4) tc::tmem_ld4(taddr + N, a); else tc::tmem_ld8(taddr + N, a);
+            tc::tmem_ld_n<NW>(taddr + N, a);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, giz[i])));
@@ -502,7 +567,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::mbar_wait(acc_ready + 2, par);
             if (drole < 3) HB_DBG(drole, s, 3);
             tc::tc_fence_after();
-            if constexpr (NW == 4) tc::tmem_ld4(taddr + 2 * N, a); else tc::tmem_ld8(taddr + 2 * N, a);
+            tc::tmem_ld_n<NW>(taddr + 2 * N, a);
             tc::tmem_ld_wait();
             if (drole < 3) HB_DBG(drole, s, 4);
 #pragma unroll
@@ -526,18 +591,22 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 #pragma unroll
         for (int i = 0; i < NW; ++i)
             if (b0 + win0 + i < B) h_out[((b0 + win0 + i) * 2 + dir) * H + j] = h_own[i] * ACT_SCALE_INV;
+        if (ra.publish_done != nullptr) __threadfence();
     }
     tc::tc_fence_before();
-    __syncthreads();
+    __syncthreads();                                         // chunk end: every role is done with the barriers
+    if (ra.publish_done != nullptr && tid == 0) tc::st_release_gpu(ra.publish_done + (size_t)cta_x * 2 + dir, (unsigned long long)(chunk + 1));
+    if (dbg && n_chunks > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (ra.dbg_role * 64 + chunk) * 2 + 1] = (long long)globaltimer_ns();
+    }   // chunk loop
     if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int N>
+template <int N, int NLIVE>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
 tc_recurrence_kernel(const RecArgs ra)
 {
     extern __shared__ __align__(128) uint8_t smem_rec[];
-    recurrence_role<N>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
+    recurrence_role<N, NLIVE>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // Encoder recurrence and decoder input projection in ONE launch: CTAs [0, 2 * rec_ctas) run the
@@ -545,14 +614,14 @@ tc_recurrence_kernel(const RecArgs ra)
 // as both encoder directions have stored them (progress counters in global memory), so that when
 // the encoder's last step retires only the two edge tiles are left.  All CTAs are co-resident
 // (grid <= SM count, one CTA per SM), which makes spinning on the counters safe.
-template <int N>
+template <int N, int NLIVE>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
 tc_encoder_fused_kernel(const RecArgs ra, const ProjArgs pa, const int rec_ctas, const int proj_workers)
 {
     extern __shared__ __align__(128) uint8_t smem_fused[];
     const int bid = (int)blockIdx.x;
     if (bid < 2 * rec_ctas) {
-        recurrence_role<N>(ra, smem_fused, bid >> 1, bid & 1);
+        recurrence_role<N, NLIVE>(ra, smem_fused, bid >> 1, bid & 1);
         if (ra.dbg && threadIdx.x == 0) atomicMax((unsigned long long*)ra.dbg + 4 * 128 * 8 - 2, globaltimer_ns());   // last recurrence CTA done
     } else {
         if (threadIdx.x >= PROJ_THREADS) return;
@@ -571,14 +640,43 @@ tc_encoder_fused_kernel(const RecArgs ra, const ProjArgs pa, const int rec_ctas,
 constexpr int HEADS_THREADS = 192;
 constexpr int HEADS_WIMG = NCLS * 2 * H * 2;     // one [16 x 256] fp16 image (dense core matrices): 8192 B
 
-__global__ void __launch_bounds__(HEADS_THREADS, 1)
-tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W, int T, int col0,
-                const __half* __restrict__ w_img,     // [hi, lo][16 x 256] core-matrix image, LBO 128 / SBO 4096
-                const float* __restrict__ b_head,     // [16]
-                float inv_scale,
-                float* __restrict__ p_base, float* __restrict__ p_rle)
+struct HeadsArgs {
+    const uint8_t* yimg; const uint8_t* yimg_odd;      // decoder output image (odd chunks may use a second buffer)
+    int64_t n_wg, B; int W, T, col0, col_step;         // chunk k accumulates into image columns col0 + k * col_step + t
+    const __half* w_img;                               // [hi, lo][16 x 256] core-matrix image, LBO 128 / SBO 4096
+    const float* b_head; float inv_scale;
+    float* p_base; float* p_rle;
+    // persistent mode
+    int n_chunks; const unsigned long long* progress; int rec_n; const int* tile_order;
+    unsigned long long* heads_done;                    // [group] += 4 per finished tile
+};
+
+// job q of a worker -> (chunk, window group, column tile).  Single-chunk launches spread tiles over all workers;
+// the persistent kernel pins window groups to workers so that the accumulation of successive chunks into
+// the same P rows stays ordered.
+__device__ __forceinline__ bool heads_job(const HeadsArgs& a, int worker, int n_workers, int tiles_t, int64_t q,
+                                          int& chunk, int64_t& wg, int& t0) {
+    if (a.n_chunks <= 0) {
+        const int64_t tile = worker + q * n_workers;
+        if (tile >= a.n_wg * tiles_t) return false;
+        chunk = 0; wg = tile / tiles_t; t0 = (int)(tile % tiles_t) * 16;
+        return true;
+    }
+    const int64_t my_wgs = (a.n_wg - worker + n_workers - 1) / n_workers;
+    const int64_t per_chunk = my_wgs * tiles_t;
+    if (per_chunk <= 0 || q >= per_chunk * a.n_chunks) return false;
+    chunk = (int)(q / per_chunk);
+    const int64_t r = q % per_chunk;
+    wg = worker + (r / tiles_t) * n_workers;
+    const int pos = (int)(r % tiles_t);
+    t0 = (a.tile_order ? a.tile_order[pos] : pos) * 16;
+    return true;
+}
+
+__device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, const int worker, const int n_workers)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    const int W = a.W, T = a.T;
+    const int64_t B = a.B;
     constexpr uint32_t PART_BYTES = 16 * YROW;                  // 16 columns of one window group
     uint8_t* a_img = smem;                                      // [hi, lo][16 row groups][YROW]
     uint8_t* w_s = smem + 2 * PART_BYTES;
@@ -590,8 +688,8 @@ tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     tc::pdl_launch_dependents();
-    for (int i = tid; i < 2 * HEADS_WIMG / 16; i += blockDim.x)
-        reinterpret_cast<int4*>(w_s)[i] = reinterpret_cast<const int4*>(w_img)[i];
+    for (int i = tid; i < 2 * HEADS_WIMG / 16; i += HEADS_THREADS)
+        reinterpret_cast<int4*>(w_s)[i] = reinterpret_cast<const int4*>(a.w_img)[i];
     if (tid == 0) {
         tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1); tc::mbar_init(acc_full, 1); tc::mbar_init(acc_empty, 4);
         tc::mbar_fence_init();
@@ -601,28 +699,32 @@ tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W
     tc::pdl_grid_dependency_wait();
     tc::fence_proxy_async_smem();
     tc::tc_fence_before();
-    __syncthreads();
+    tc::named_barrier_sync(2, HEADS_THREADS);
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int tiles_t = (W + 15) >> 4;
-    const int64_t n_tiles = n_wg * tiles_t;
+    int chunk; int64_t wg; int t0;
 
     if (warp == 5) {
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
             if (it > 0) tc::mbar_wait(a_empty, (uint32_t)((it - 1) & 1));
-            const int64_t wg = tile / tiles_t;
-            const int t0 = (int)(tile % tiles_t) * 16;
             const int valid = min(16, W - t0);
+            if (a.progress != nullptr) {                     // both decoder directions must have stored these columns
+                if (lane < 2)
+                    tc::spin_until_ge(a.progress + ((wg * WG) / a.rec_n) * 2 + lane,
+                                      (unsigned long long)chunk * W + (unsigned long long)(lane == 0 ? t0 + valid : W - t0));
+                tc::fence_proxy_async_all();
+                __syncwarp();
+            }
+            const uint8_t* img = ((chunk & 1) && a.yimg_odd) ? a.yimg_odd : a.yimg;
             if (lane == 0) tc::mbar_arrive_expect_tx(a_full, (uint32_t)(valid * 2 * YROW));
             __syncwarp();
             const int tl = lane & 15, part = lane >> 4;
-            if (tl < valid) tc::bulk_g2s(a_img + part * PART_BYTES + tl * YROW, yimg + yimg_block(wg, t0 + tl, W, part), YROW, a_full);
+            if (tl < valid) tc::bulk_g2s(a_img + part * PART_BYTES + tl * YROW, img + yimg_block(wg, t0 + tl, W, part), YROW, a_full);
         }
     } else if (warp == 4) {
         const uint32_t idesc = tc::idesc_f16_f32(128, NCLS);
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
             tc::mbar_wait(a_full, (uint32_t)(it & 1));
             if (it > 0) tc::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
             tc::tc_fence_after();
@@ -641,13 +743,12 @@ tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W
     } else {
         float bias[NCLS];
 #pragma unroll
-        for (int c = 0; c < NCLS; ++c) bias[c] = b_head[c];
+        for (int c = 0; c < NCLS; ++c) bias[c] = a.b_head[c];
         const int row = warp * 32 + lane;                       // position within the tile: (column, window)
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int64_t wg = tile / tiles_t;
-            const int t = (int)(tile % tiles_t) * 16 + (row >> 3);
+        for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
+            const int t = t0 + (row >> 3);
             const int64_t b = wg * WG + (row & 7);
+            const int col = a.col0 + chunk * a.col_step + t;
             tc::mbar_wait(acc_full, (uint32_t)(it & 1));
             tc::tc_fence_after();
             float v[NCLS];
@@ -660,7 +761,7 @@ tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W
                 float mb = -INFINITY, mr = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < NCLS; ++c) {
-                    v[c] = fmaf(v[c], inv_scale, bias[c]);
+                    v[c] = fmaf(v[c], a.inv_scale, bias[c]);
                     if (c < NBASE) mb = fmaxf(mb, v[c]); else mr = fmaxf(mr, v[c]);
                 }
                 float sb = 0.f, sr = 0.f;
@@ -669,18 +770,63 @@ tc_heads_kernel(const uint8_t* __restrict__ yimg, int64_t n_wg, int64_t B, int W
                     v[c] = expf(v[c] - (c < NBASE ? mb : mr));
                     if (c < NBASE) sb += v[c]; else sr += v[c];
                 }
-                float* pb = p_base + (b * T + col0 + t) * NBASE;
-                float* pr = p_rle + (b * T + col0 + t) * NRLE;
+                float* pb = a.p_base + (b * T + col) * NBASE;
+                float* pr = a.p_rle + (b * T + col) * NRLE;
 #pragma unroll
                 for (int c = 0; c < NBASE; ++c) pb[c] += v[c] / sb;
 #pragma unroll
                 for (int c = 0; c < NRLE; ++c) pr[c] += v[NBASE + c] / sr;
             }
+            if (a.heads_done != nullptr) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) tc::red_release_gpu_add(a.heads_done + wg, 1ull);
+            }
         }
     }
     tc::tc_fence_before();
-    __syncthreads();
+    tc::named_barrier_sync(2, HEADS_THREADS);
     if (warp == 4) tc::tmem_dealloc(tmem, 32);
+}
+
+__global__ void __launch_bounds__(HEADS_THREADS, 1)
+tc_heads_kernel(const HeadsArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem_heads[];
+    heads_role(a, smem_heads, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The whole chunk loop of one batch in ONE launch (small batches: every role fits on the chip at once).
+//   CTAs [0, 2R)        encoder recurrence   (window tile, direction), W_hh(enc) resident in TMEM
+//   CTAs [2R, 4R)       decoder recurrence                            W_hh(dec) resident in TMEM
+//   CTAs [4R, 4R + 6P)  decoder input projection, one gate block each, W_ih(dec) block resident in TMEM
+//   the rest            heads + softmax + accumulate
+// Hand-offs go through counters in global memory (release/acquire at gpu scope):
+//   encoder columns done -> projection;  projection tiles done -> decoder;  decoder columns done -> heads;
+//   h of a finished chunk -> the other layer;  heads done -> decoder (yimg2 buffer reuse).
+// Every CTA is resident (grid <= SM count, > 113 KB smem each), so spinning is safe; per chunk the critical
+// path is 100 encoder steps + the two edge tiles of the projection + 100 decoder steps.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(REC_TC_THREADS, 1)
+tc_window_kernel(const RecArgs enc, const RecArgs dec, const ProjArgs proj, const HeadsArgs heads,
+                 const int rec_ctas, const int proj_workers, const int heads_workers)
+{
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    const int bid = (int)blockIdx.x;
+    if (bid < 2 * rec_ctas) {
+        recurrence_role<N, N>(enc, smem_all, bid >> 1, bid & 1);
+    } else if (bid < 4 * rec_ctas) {
+        recurrence_role<N, N>(dec, smem_all, (bid - 2 * rec_ctas) >> 1, bid & 1);
+    } else if (bid < 4 * rec_ctas + 6 * proj_workers) {
+        if (threadIdx.x >= PROJ_THREADS) return;
+        const int pb = bid - 4 * rec_ctas;
+        projection_role<true>(proj, smem_all, pb % 6, pb / 6, proj_workers);
+    } else {
+        if (threadIdx.x >= HEADS_THREADS) return;
+        heads_role(heads, smem_all, bid - 4 * rec_ctas - 6 * proj_workers, heads_workers);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -700,6 +846,10 @@ struct TensorEngine {
     int* tile_order = nullptr;                // column-tile order of the fused projection (earliest complete first)
     int tile_order_w = -1;
     std::vector<int> tile_order_host;
+    int* tile_order16 = nullptr;              // same for the 16-column tiles of the heads role
+    std::vector<int> tile_order16_host;
+    unsigned long long* flags = nullptr;      // counters of the persistent window kernel
+    size_t flags_capacity = 0;
     unsigned long long launch_epoch = 0;
     // optional device timing of every recurrence launch (the dominant kernel), bench.py's roofline pass
     bool time_recurrence = false;
@@ -873,6 +1023,8 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     cudaFree(e->b_head);
     cudaFree(e->progress);
     cudaFree(e->tile_order);
+    cudaFree(e->tile_order16);
+    cudaFree(e->flags);
     if (e->side) cudaStreamDestroy(e->side);
     for (auto& ev : e->rec_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (int i = 0; i < 2; ++i) {
@@ -916,13 +1068,19 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         };
         set((const void*)tc_projection_kernel<false>, detail::projection_smem(e->enc.Kp * 16, 1));
         set((const void*)tc_projection_kernel<true>, detail::projection_smem(YROW, 2));
-        set((const void*)tc_recurrence_kernel<16>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<32>, detail::recurrence_smem<32>());
+        set((const void*)tc_recurrence_kernel<16, 8>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 16>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<32, 32>, detail::recurrence_smem<32>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
-        set((const void*)tc_encoder_fused_kernel<16>, std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)));
+        set((const void*)tc_encoder_fused_kernel<16, 8>, std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)));
+        set((const void*)tc_encoder_fused_kernel<16, 16>, std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->progress), (size_t)sm_count * 2 * sizeof(unsigned long long));
         if (ce == cudaSuccess) ce = cudaMemset(e->progress, 0, (size_t)sm_count * 2 * sizeof(unsigned long long));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order), 4096 * sizeof(int));
+        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order16), 4096 * sizeof(int));
+        e->flags_capacity = (size_t)1 << 16;
+        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->flags), e->flags_capacity * sizeof(unsigned long long));
+        set((const void*)tc_window_kernel<16>, std::max({detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()}));
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
         for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
             ce = cudaEventCreateWithFlags(&e->ev_dec[i], cudaEventDisableTiming);
@@ -944,8 +1102,12 @@ inline size_t tensor_engine_workspace_bytes(const TensorEngine* e, int64_t B, in
     return tensor_carve(nullptr, B, T, W, e->enc.Kp, T).bytes;     // J >= 1: at most T covered columns
 }
 
-// windows per recurrence CTA: the smallest tile (lowest step latency) that still fits the batch on the chip
-inline int pick_windows_per_cta(int64_t B, int sm_count) { return 2 * B <= (int64_t)16 * sm_count ? 16 : 32; }
+// live windows per recurrence CTA: the smallest tile (lowest step latency) that still fits the batch on the chip
+inline int pick_windows_per_cta(int64_t B, int sm_count) {
+    static const bool allow8 = getenv("HB_NO_LIVE8") == nullptr && getenv("HB_PERSISTENT") == nullptr;
+    if (allow8 && 2 * B <= (int64_t)8 * sm_count) return 8;
+    return 2 * B <= (int64_t)16 * sm_count ? 16 : 32;
+}
 
 // Returns the number of kernel launches issued, or a negative hb_status (message in err).
 inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t B, int T, int W, int J,
@@ -960,6 +1122,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     int launches = 0;
     cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s);
     cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s);
+    cudaMemsetAsync(e->flags, 0, std::min(e->flags_capacity, (size_t)16384) * sizeof(unsigned long long), s);   // persistent-kernel counters
     const int xblk = e->enc.Kp * 16;                           // bytes of one (group, column) pixel block
     const int proj_workers = std::max(1, e->sm_count / 6);
     static const bool pdl = getenv("HB_NO_PDL") == nullptr;
@@ -986,7 +1149,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const int tiles_heads = (int)std::min<int64_t>(n_wg * ((W + 15) / 16), e->sm_count);
     static long long* dbg_buf = nullptr;
     static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
-    if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 4 * 128 * 8 * sizeof(long long));
+    if (dbg_on && !dbg_buf) { cudaMalloc(&dbg_buf, 8192 * sizeof(long long)); cudaMemset(dbg_buf, 0, 8192 * sizeof(long long)); }
     // decoder projection arguments (the same for every chunk)
     ProjArgs pd{};
     pd.in_base = ws.yimg1; pd.in_wg_stride = (int64_t)W * 2 * YROW; pd.in_t_stride = 2 * YROW; pd.in_part_stride = YROW;
@@ -995,25 +1158,53 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     // fused encoder + projection launch when the recurrence leaves at least half of the SMs free
     const int rec_ctas = (int)grid_rec.x;
     const int fused_workers = (e->sm_count - 2 * rec_ctas) / 6;
-    static const bool fuse_allowed = getenv("HB_NO_FUSED") == nullptr;
-    const bool fused = fuse_allowed && nrec == 16 && fused_workers >= 8 && (W + 7) / 8 <= 4096 && !e->time_recurrence;
-    if (fused && e->tile_order_w != W) {
-        // column tile tt is complete once the forward pass is past column 8tt+7 and the reverse pass past 8tt
-        const int tiles_t = (W + 7) / 8;
-        std::vector<int>& order = e->tile_order_host;             // outlives the async copy
-        order.resize(tiles_t);
-        for (int i = 0; i < tiles_t; ++i) order[i] = i;
-        auto ready = [&](int tt) { return std::max(std::min(8 * tt + 8, W), W - 8 * tt); };
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ready(x) < ready(y); });
-        cudaMemcpyAsync(e->tile_order, order.data(), tiles_t * sizeof(int), cudaMemcpyHostToDevice, s);
+    // Opt-in (HB_FUSED=1): correct and tested; measured slower than separate launches (4.45 vs 4.17 ms per batch at
+    // B=256): the projection CTAs that share the launch get fewer SMs and compete with the recurrence for L2.
+    static const bool fuse_allowed = getenv("HB_FUSED") != nullptr;
+    const bool fused = fuse_allowed && nrec <= 16 && fused_workers >= 8 && (W + 7) / 8 <= 4096 && !e->time_recurrence;
+    // persistent window kernel: every role of the whole chunk loop resident at once
+    const int n_chunks = T < W ? 0 : (T - W) / J + 1;
+    const int heads_workers = 8;
+    const int persistent_workers = (e->sm_count - 4 * rec_ctas - heads_workers) / 6;
+    const int tiles8 = (W + 7) / 8, tiles16 = (W + 15) / 16;
+    const size_t flags_needed = (size_t)8 * rec_ctas + (size_t)2 * rec_ctas + (size_t)2 * rec_ctas * tiles8 * 2;
+    // Opt-in (HB_PERSISTENT=1): correct and tested, but measured SLOWER than the per-chunk launches at B=256
+    // (5.0-5.3 ms vs 4.8 ms per batch): with half of the SMs pinned to the recurrence roles the projection
+    // role, which is L2-bound (each activation tile is fetched by 6 gate-block CTAs), cannot hide behind the encoder.
+    static const bool persistent_allowed = getenv("HB_PERSISTENT") != nullptr;
+    const bool persistent = persistent_allowed && nrec == 16 && n_chunks > 0 && persistent_workers >= 8 && tiles8 <= 4096 &&
+                            flags_needed <= 16384 && !e->time_recurrence;
+    if ((fused || persistent) && e->tile_order_w != W) {
+        // a column tile is complete once the forward pass is past its last column and the reverse pass past its first
+        auto make_order = [&](int width, std::vector<int>& order, int* dev) {
+            const int n = (W + width - 1) / width;
+            order.resize(n);                                       // member vector: outlives the async copy
+            for (int i = 0; i < n; ++i) order[i] = i;
+            auto ready = [&](int tt) { return std::max(std::min(width * tt + width, W), W - width * tt); };
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ready(x) < ready(y); });
+            cudaMemcpyAsync(dev, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
+        };
+        make_order(8, e->tile_order_host, e->tile_order);
+        make_order(16, e->tile_order16_host, e->tile_order16);
+        if (persistent) {
+            // The decoder consumes tiles edges-first, the encoder finishes them edges-last.  Whatever the
+            // projection CTAs cannot finish while the encoder is still running is therefore taken in the
+            // decoder's order: the last ~30 % of the availability order is re-sorted edges-first.
+            std::vector<int>& o = e->tile_order_host;
+            const int n = (int)o.size(), tail = std::max(2, (n * 3 + 9) / 10);
+            auto edge_dist = [&](int tt) { return std::min(tt, n - 1 - tt); };
+            std::stable_sort(o.end() - std::min(tail, n), o.end(), [&](int x, int y) { return edge_dist(x) < edge_dist(y); });
+            cudaMemcpyAsync(e->tile_order, o.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
+        }
         e->tile_order_w = W;
     }
     auto rec_args = [&](const TensorLayer& L, const float* gi, int gi_cols, int gi_col0, const float* h_in, float* h_out, uint8_t* yimg) {
         RecArgs ra{};
         ra.gi = gi; ra.whh_tmem = L.whh_tmem; ra.gate_consts = L.gate_consts; ra.h_in = h_in; ra.h_out = h_out; ra.yimg = yimg;
         ra.B = B; ra.W = W; ra.gi_cols = gi_cols; ra.gi_col0 = gi_col0; ra.progress = nullptr; ra.epoch = 0;
+        ra.n_wg = (int)n_wg; ra.dbg_role = (&L == &e->enc) ? 0 : 1;
         static const bool dbg_enc = getenv("HB_DEBUG_TIMELINE") != nullptr && getenv("HB_DEBUG_TIMELINE")[0] == 'e';
-        ra.dbg = (nrec == 16 && (dbg_enc == (&L == &e->enc))) ? dbg_buf : nullptr;
+        ra.dbg = (nrec <= 16 && (dbg_enc == (&L == &e->enc))) ? dbg_buf : nullptr;
         return ra;
     };
     auto recurrence = [&](const RecArgs& ra, bool use_pdl) {
@@ -1029,14 +1220,46 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             cudaEventRecord(e->rec_events[slot].first, s);
             use_pdl = false;
         }
-        if (nrec == 16)
-            detail::launch(tc_recurrence_kernel<16>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl, ra);
+        if (nrec == 8)
+            detail::launch(tc_recurrence_kernel<16, 8>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl, ra);
+        else if (nrec == 16)
+            detail::launch(tc_recurrence_kernel<16, 16>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl, ra);
         else
-            detail::launch(tc_recurrence_kernel<32>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl, ra);
+            detail::launch(tc_recurrence_kernel<32, 32>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl, ra);
         if (e->time_recurrence) cudaEventRecord(e->rec_events[slot].second, s);
     };
+    HeadsArgs heads_base{};
+    heads_base.n_wg = n_wg; heads_base.B = B; heads_base.W = W; heads_base.T = T; heads_base.col_step = J;
+    heads_base.w_img = e->head_img; heads_base.b_head = e->b_head; heads_base.inv_scale = e->head_inv;
+    heads_base.p_base = p_base; heads_base.p_rle = p_rle;
+    if (persistent) {
+        unsigned long long* f = e->flags;
+        unsigned long long* enc_prog = f;                 f += 2 * rec_ctas;
+        unsigned long long* dec_prog = f;                 f += 2 * rec_ctas;
+        unsigned long long* enc_done = f;                 f += 2 * rec_ctas;
+        unsigned long long* dec_done = f;                 f += 2 * rec_ctas;
+        unsigned long long* heads_done = f;               f += 2 * rec_ctas;           // one per window group
+        unsigned long long* tile_flags = f;
+        RecArgs renc = rec_args(e->enc, ws.gi_enc, enc_cols, 0, nullptr, ws.hid_a, ws.yimg1);
+        renc.n_chunks = n_chunks; renc.gi_col_step = J; renc.h_in_next = ws.hid_b;
+        renc.progress = enc_prog; renc.wait_done = dec_done; renc.wait_done_bias = 0; renc.publish_done = enc_done;
+        RecArgs rdec = rec_args(e->dec, ws.gi, W, 0, ws.hid_a, ws.hid_b, ws.yimg2[0]);
+        rdec.n_chunks = n_chunks; rdec.gi_col_step = 0; rdec.h_in_next = ws.hid_a; rdec.yimg_odd = ws.yimg2[1];
+        rdec.progress = dec_prog; rdec.wait_done = enc_done; rdec.wait_done_bias = 1; rdec.publish_done = dec_done;
+        rdec.tile_flags = tile_flags; rdec.tiles_t = tiles8; rdec.heads_done = heads_done; rdec.heads_per_chunk = 4 * tiles16;
+        renc.dbg = rdec.dbg = dbg_buf;
+        ProjArgs pp = pd;
+        pp.progress = enc_prog; pp.epoch = 0; pp.tile_order = e->tile_order; pp.rec_n = nrec; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
+        HeadsArgs hp = heads_base;
+        hp.yimg = ws.yimg2[0]; hp.yimg_odd = ws.yimg2[1]; hp.col0 = 0; hp.n_chunks = n_chunks;
+        hp.progress = dec_prog; hp.rec_n = nrec; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
+        detail::launch(tc_window_kernel<16>, dim3(4 * rec_ctas + 6 * persistent_workers + heads_workers), dim3(REC_TC_THREADS),
+                       std::max({detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()}), s, pdl,
+                       renc, rdec, pp, hp, rec_ctas, persistent_workers, heads_workers);
+        launches += 1;
+    }
     int chunk = 0;
-    for (int i = 0; i + W <= T; i += J, ++chunk) {
+    for (int i = 0; !persistent && i + W <= T; i += J, ++chunk) {
         float* enc_h = hid_bufs[flip];
         float* dec_h = hid_bufs[flip ^ 1];
         const int buf = chunk & 1;
@@ -1047,7 +1270,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             renc.epoch = (++e->launch_epoch) << 20;
             ProjArgs pf = pd;
             pf.progress = e->progress; pf.epoch = renc.epoch; pf.tile_order = e->tile_order; pf.rec_n = nrec;
-            detail::launch(tc_encoder_fused_kernel<16>, dim3(2 * rec_ctas + 6 * fused_workers), dim3(REC_TC_THREADS),
+            detail::launch(nrec == 8 ? tc_encoder_fused_kernel<16, 8> : tc_encoder_fused_kernel<16, 16>,
+                           dim3(2 * rec_ctas + 6 * fused_workers), dim3(REC_TC_THREADS),
                            std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)), s, pdl && chunk == 0,
                            renc, pf, rec_ctas, fused_workers);
         } else {
@@ -1057,7 +1281,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         recurrence(rec_args(e->dec, ws.gi, W, 0, enc_h, dec_h, ws.yimg2[buf]), pdl);
         cudaEventRecord(e->ev_dec[buf], s);
         cudaStreamWaitEvent(e->side, e->ev_dec[buf], 0);
-        tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), e->side>>>(ws.yimg2[buf], n_wg, B, W, T, i, e->head_img, e->b_head, e->head_inv, p_base, p_rle);
+        HeadsArgs ha = heads_base;
+        ha.yimg = ws.yimg2[buf]; ha.col0 = i;
+        tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), e->side>>>(ha);
         cudaEventRecord(e->ev_heads[buf], e->side);
         launches += fused ? 3 : 4;
         hid = dec_h;
@@ -1071,8 +1297,16 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         static int printed = 0;
         cudaStreamSynchronize(s);
         if (printed++ == 2) {
-            std::vector<long long> hbuf(4 * 128 * 8);
+            std::vector<long long> hbuf(8192);
             cudaMemcpy(hbuf.data(), dbg_buf, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            if (persistent) {
+                const long long t0 = hbuf[4096];
+                fprintf(stderr, "[persistent kernel, CTA 0 fwd, us since encoder chunk 0 start]\n");
+                for (int k = 0; k < std::min(n_chunks, 6); ++k)
+                    fprintf(stderr, "  chunk %d: enc %.1f -> %.1f   dec %.1f -> %.1f\n", k,
+                            (hbuf[4096 + k * 2] - t0) * 1e-3, (hbuf[4096 + k * 2 + 1] - t0) * 1e-3,
+                            (hbuf[4096 + (64 + k) * 2] - t0) * 1e-3, (hbuf[4096 + (64 + k) * 2 + 1] - t0) * 1e-3);
+            }
             auto at = [&](int role, int st, int k) { return hbuf[((size_t)role * 128 + st) * 8 + k]; };
             double acc[16] = {0};
             int n = 0;
