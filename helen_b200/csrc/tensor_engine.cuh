@@ -104,6 +104,9 @@ struct ProjArgs {
     // persistent mode: the role walks n_chunks chunks; a chunk's columns count from chunk * W in the progress
     // counters, and every finished tile is announced to the decoder CTAs (4 epilogue warps -> +4 per tile and block)
     int n_chunks; unsigned long long* tile_flags;
+    // pair mode: the launch uses clusters of 2 CTAs along the gate-block axis; both CTAs of a pair walk the same
+    // tiles, each fetches half of a tile and multicasts it to both, halving the L2 traffic of the activations
+    int pair;
 };
 
 // tile index -> (window group, column tile); all roles use the same mapping
@@ -137,7 +140,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     const int kwords = Kp >> 1;
     tc::pdl_launch_dependents();
     if (tid == 0) {
-        for (int i = 0; i < PROJ_STAGES; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < PROJ_STAGES; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, a.pair ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
         tc::mbar_fence_init();
     }
@@ -147,16 +150,26 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     tc::named_barrier_sync(1, PROJ_THREADS);
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (warp < 4) {   // weight block -> TMEM, thread = gate row
+    if (warp < 4) {   // weight block -> TMEM, thread = gate row; 32 words in flight per round trip
         const int row = warp * 32 + lane;
         for (int term = 0; term < 2; ++term) {
             const uint32_t* src = w_tmem + (((size_t)blk * 2 + term) * 128 + row) * kwords;
-            for (int c = 0; c < kwords; c += 16) {
+            const uint32_t dst = tmem + ((uint32_t)(warp * 32) << 16) + PROJ_W_COL0 + term * kwords;
+            int c = 0;
+            for (; c + 32 <= kwords; c += 32) {
+                uint32_t r[32];
+                const uint4* p = reinterpret_cast<const uint4*>(src + c);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                tc::tmem_st16(dst + c, r);
+                tc::tmem_st16(dst + c + 16, r + 16);
+            }
+            for (; c < kwords; c += 16) {
                 uint32_t r[16];
                 const uint4* p = reinterpret_cast<const uint4*>(src + c);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) { const uint4 x = p[v]; r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-                tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + PROJ_W_COL0 + term * kwords + c, r);
+                for (int v = 0; v < 4; ++v) { const uint4 x = __ldg(p + v); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                tc::tmem_st16(dst + c, r);
             }
         }
         tc::tmem_st_wait();
@@ -165,6 +178,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     tc::tc_fence_before();
     tc::named_barrier_sync(1, PROJ_THREADS);
     tc::tc_fence_after();
+    const uint32_t pair_rank = a.pair ? tc::cluster_ctarank() : 0u;
+    if (a.pair) tc::cluster_sync_all();                      // the peer's mbarriers exist before anything is multicast at them
 
     const int tiles_t = (W + 7) >> 3;
     const int64_t n_tiles = n_wg * tiles_t;
@@ -193,10 +208,12 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             __syncwarp();
             if (lane < 8 * PARTS) {
                 const int tl = lane & 7, part = lane >> 3;
-                if (tl < valid)
-                    tc::bulk_g2s(smem + stage * stage_bytes + part * part_bytes + tl * blk_bytes,
-                                 in_base + wg * in_wg_stride + (int64_t)(t0 + tl) * in_t_stride + part * in_part_stride,
-                                 (uint32_t)blk_bytes, a_full + stage);
+                uint8_t* dst = smem + stage * stage_bytes + part * part_bytes + tl * blk_bytes;
+                const uint8_t* src = in_base + wg * in_wg_stride + (int64_t)(t0 + tl) * in_t_stride + part * in_part_stride;
+                if (tl < valid) {
+                    if (!a.pair) tc::bulk_g2s(dst, src, (uint32_t)blk_bytes, a_full + stage);
+                    else if ((uint32_t)(tl & 1) == pair_rank) tc::bulk_g2s_multicast(dst, src, (uint32_t)blk_bytes, a_full + stage, (uint16_t)3);
+                }
             }
         }
     } else if (warp == 4) {
@@ -221,7 +238,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16_ts(d, a_lo + ks * 8, d_hi + (uint64_t)(ks * 2 * lbo / 16), idesc, 1);
                 if (kSplitA)
                     for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16_ts(d, a_hi + ks * 8, d_lo + (uint64_t)(ks * 2 * lbo / 16), idesc, 1);
-                tc::mma_commit(a_empty + stage);
+                if (a.pair) tc::mma_commit_multicast(a_empty + stage, (uint16_t)3);   // both loaders wait for both consumers
+                else tc::mma_commit(a_empty + stage);
                 tc::mma_commit(acc_full + acc);
             }
             __syncwarp();
@@ -263,6 +281,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     }
     tc::tc_fence_before();
     tc::named_barrier_sync(1, PROJ_THREADS);
+    if (a.pair) tc::cluster_sync_all();                      // no multicast / remote arrive may target a CTA that has exited
     if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -378,19 +397,20 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {   // W_hh -> TMEM (once): warps 0-3 store the hi image, warps 4-7 the lo image; thread = row j
-        const int q = warp & 3, j = q * 32 + lane, term = warp >> 2;
-        const uint32_t* src = whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64;
+    if (warp < REC_GATE_WARPS) {
+        // W_hh -> TMEM (once).  Warp w covers TMEM lanes 32 (w%4)..+31 (thread = gate row j); the four warps of a
+        // lane quarter split (hi | lo image) x (k-pair columns 0-31 | 32-63); 32 words in flight per round trip.
+        const int q = warp & 3, j = q * 32 + lane, term = (warp >> 2) & 1, half = warp >> 3;
+        const uint32_t* src = whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64 + half * 32;
 #pragma unroll 1
         for (int gb = 0; gb < 3; ++gb) {
+            uint32_t r[32];
+            const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64);
 #pragma unroll
-            for (int c = 0; c < 64; c += 16) {
-                uint32_t r[16];
-                const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64 + c);
-#pragma unroll
-                for (int v = 0; v < 4; ++v) { const uint4 x = p[v]; r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-                tc::tmem_st16(tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + c, r);
-            }
+            for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+            const uint32_t dst = tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
+            tc::tmem_st16(dst, r);
+            tc::tmem_st16(dst + 16, r + 16);
         }
         tc::tmem_st_wait();
     }
@@ -912,20 +932,35 @@ template <class T> struct ident { using type = T; };
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start
 // while its predecessor in the stream is still running and synchronises with griddepcontrol.wait.
 template <typename... KArgs>
-inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
-                          typename ident<KArgs>::type... args) {
+inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, dim3 cluster,
+                                  typename ident<KArgs>::type... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster.x; attr[n].val.clusterDim.y = cluster.y; attr[n].val.clusterDim.z = cluster.z;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = n;
     void* params[] = {(void*)&args...};
     return cudaLaunchKernelExC(&cfg, (const void*)kernel, params);
+}
+
+template <typename... KArgs>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                          typename ident<KArgs>::type... args) {
+    return launch_cluster(kernel, grid, block, smem, s, pdl, dim3(1, 1, 1), args...);
 }
 
 inline int pow2_scale_exponent(const float* w, size_t n) {
@@ -1126,6 +1161,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const int xblk = e->enc.Kp * 16;                           // bytes of one (group, column) pixel block
     const int proj_workers = std::max(1, e->sm_count / 6);
     static const bool pdl = getenv("HB_NO_PDL") == nullptr;
+    static const int pair_mode = getenv("HB_NO_PAIR") == nullptr ? 1 : 0;   // 2-CTA clusters share activation tiles by multicast
     if (enc_cols > 0) {
         // once per batch: pixels -> operand image, then the encoder projection of EVERY covered column
         // (chunks overlap by W - J columns and gi of a column does not depend on the chunk)
@@ -1137,7 +1173,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         pe.in_base = reinterpret_cast<const uint8_t*>(ws.ximg); pe.in_wg_stride = (int64_t)T * xblk; pe.in_t_stride = xblk; pe.in_part_stride = 0;
         pe.blk_bytes = xblk; pe.lbo = 128; pe.Kp = e->enc.Kp; pe.n_wg = n_wg; pe.W = enc_cols;
         pe.w_tmem = e->enc.wih_tmem; pe.scale_row = e->enc.scale_row; pe.bias_row = e->enc.bias_row; pe.gi = ws.gi_enc;
-        detail::launch(tc_projection_kernel<false>, dim3(tiles, 6), dim3(PROJ_THREADS), detail::projection_smem(xblk, 1), s, pdl, pe);
+        pe.pair = pair_mode;
+        detail::launch_cluster(tc_projection_kernel<false>, dim3(tiles, 6), dim3(PROJ_THREADS), detail::projection_smem(xblk, 1), s, pdl,
+                               dim3(1, pair_mode ? 2 : 1, 1), pe);
         launches += 2;
     }
     const float* hid = nullptr;
@@ -1276,7 +1314,10 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                            renc, pf, rec_ctas, fused_workers);
         } else {
             recurrence(renc, pdl && chunk == 0);
-            detail::launch(tc_projection_kernel<true>, dim3(tiles_proj, 6), dim3(PROJ_THREADS), detail::projection_smem(YROW, 2), s, pdl, pd);
+            ProjArgs pq = pd;
+            pq.pair = pair_mode;
+            detail::launch_cluster(tc_projection_kernel<true>, dim3(tiles_proj, 6), dim3(PROJ_THREADS), detail::projection_smem(YROW, 2), s, pdl,
+                                   dim3(1, pair_mode ? 2 : 1, 1), pq);
         }
         recurrence(rec_args(e->dec, ws.gi, W, 0, enc_h, dec_h, ws.yimg2[buf]), pdl);
         cudaEventRecord(e->ev_dec[buf], s);
