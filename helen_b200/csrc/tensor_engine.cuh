@@ -341,7 +341,12 @@ struct RecArgs {
 
 // NLIVE <= N windows of the N accumulator columns are real: the MMA shape needs N >= 16, but with 8 live windows
 // per CTA a small batch spreads over twice as many SMs and the exposed gate math (MUFU-bound) halves.
-template <int N, int NLIVE>
+//
+// STACK: the hi and lo images of h are read as ONE B operand, [h_hi (NLIVE rows) | h_lo (NLIVE rows)], so a step needs
+// only the two A terms W_hi and W_lo (48 MMAs instead of 72; the MMA time of a step is set by the instruction count,
+// not by N, at these sizes).  Accumulator columns [0, NLIVE) hold W.h_hi, [NLIVE, 2 NLIVE) hold W.h_lo; the gate
+// threads add the two.  That is the full 4-term product (W_lo.h_lo included).
+template <int N, int NLIVE, bool STACK = false>
 __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem, const int cta_x, const int dir)
 {
     const float* __restrict__ gi = ra.gi;
@@ -355,6 +360,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 #define HB_DBG(role, s, k) do { if (dbg && cta_x == 0 && dir == 0 && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N accumulator columns per gate block (3N must stay below REC_W_COL0)");
     static_assert(NLIVE == N || (N == 16 && NLIVE == 8), "live windows per CTA");
+    static_assert(!STACK || N == 16, "stacked operand: 3 x 2 NLIVE accumulator columns must stay below REC_W_COL0");
+    constexpr int NACC = STACK ? 2 * NLIVE : N;              // accumulator columns per gate block == N of the MMA
     constexpr int NW = NLIVE / 4;                            // windows per gate thread
     constexpr int NG = NLIVE / WG;                           // live window groups per CTA
     constexpr uint32_t HB_BYTES = (N / WG) * YBLK;           // one h operand image (hi or lo), all N columns
@@ -501,8 +508,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         // warps overlap the r and z sigmoids with the remaining MMAs.
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
-        const uint32_t idesc = tc::idesc_f16_f32(128, N);
-        const uint64_t himg_desc = tc::smem_desc(tc::smem_u32(h_img), H_LBO, YBLK);
+        const uint32_t idesc = tc::idesc_f16_f32(128, NACC);
+        // stacked operand: NLIVE == 8 takes rows 8..15 from the lo image (group stride = HB_BYTES); with NLIVE == 16
+        // the lo image directly follows the two hi groups, so the plain group stride covers all 32 rows
+        const uint64_t himg_desc = tc::smem_desc(tc::smem_u32(h_img), H_LBO, (STACK && NLIVE == 8) ? HB_BYTES : YBLK);
         for (int s = 0; s < W; ++s) {
             if (s > 0) {
                 tc::mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
@@ -514,13 +523,23 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (tc::elect_one()) {
 #pragma unroll
                 for (int gb = 0; gb < 3; ++gb) {             // gate blocks r, z, n
+                    if constexpr (STACK) {
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {   // (W_hi,h_hi) (W_lo,h_hi) (W_hi,h_lo)
-                        const uint32_t a_col = tmem + REC_W_COL0 + ((term == 1 ? 3 : 0) + gb) * 64;
-                        const uint64_t bd = term == 2 ? hlo_desc : hhi_desc;
+                        for (int term = 0; term < 2; ++term) {   // W_hi, W_lo against [h_hi | h_lo]
+                            const uint32_t a_col = tmem + REC_W_COL0 + (term * 3 + gb) * 64;
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            tc::mma_f16_ts(tmem + gb * N, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
+                            for (int ks = 0; ks < 8; ++ks)
+                                tc::mma_f16_ts(tmem + gb * NACC, a_col + ks * 8, hhi_desc + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {   // (W_hi,h_hi) (W_lo,h_hi) (W_hi,h_lo)
+                            const uint32_t a_col = tmem + REC_W_COL0 + ((term == 1 ? 3 : 0) + gb) * 64;
+                            const uint64_t bd = term == 2 ? hlo_desc : hhi_desc;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks)
+                                tc::mma_f16_ts(tmem + gb * NACC, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
+                        }
                     }
                     tc::mma_commit(acc_ready + gb);          // gates start on r while z, n still run
                 }
@@ -552,6 +571,18 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         __syncthreads();                                     // pairs with the other roles' barrier
 
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
+        auto load_acc = [](uint32_t addr, float* a) {
+            tc::tmem_ld_n<NW>(addr, a);
+            if constexpr (STACK) {
+                float a_lo[NW];
+                tc::tmem_ld_n<NW>(addr + NLIVE, a_lo);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < NW; ++i) a[i] += a_lo[i];
+            } else {
+                tc::tmem_ld_wait();
+            }
+        };
         for (int s = 0; s < W; ++s) {
             const int stage = s % GI_STAGES;
             const uint32_t par = (uint32_t)(s & 1);
@@ -570,15 +601,13 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::mbar_wait(acc_ready + 0, par);
             if (drole < 3) HB_DBG(drole, s, 1);
             tc::tc_fence_after();
-            tc::tmem_ld_n<NW>(taddr, a);
-            tc::tmem_ld_wait();
+            load_acc(taddr, a);
 #pragma unroll
             for (int i = 0; i < NW; ++i) r[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_r, gir[i])));
             tc::mbar_wait(acc_ready + 1, par);
             if (drole < 3) HB_DBG(drole, s, 2);
             tc::tc_fence_after();
-            tc::tmem_ld_n<NW>(taddr + N, a);
-            tc::tmem_ld_wait();
+            load_acc(taddr + NACC, a);
 #pragma unroll
             for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, giz[i])));
             uint8_t* h_hi = h_img + (((s + 1) & 1) * 2) * HB_BYTES;            // image of h_{s+1}
@@ -587,8 +616,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::mbar_wait(acc_ready + 2, par);
             if (drole < 3) HB_DBG(drole, s, 3);
             tc::tc_fence_after();
-            tc::tmem_ld_n<NW>(taddr + 2 * N, a);
-            tc::tmem_ld_wait();
+            load_acc(taddr + 2 * NACC, a);
             if (drole < 3) HB_DBG(drole, s, 4);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
@@ -621,12 +649,12 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int N, int NLIVE>
+template <int N, int NLIVE, bool STACK>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
 tc_recurrence_kernel(const RecArgs ra)
 {
     extern __shared__ __align__(128) uint8_t smem_rec[];
-    recurrence_role<N, NLIVE>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
+    recurrence_role<N, NLIVE, STACK>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // Encoder recurrence and decoder input projection in ONE launch: CTAs [0, 2 * rec_ctas) run the
@@ -861,7 +889,34 @@ struct TensorLayer {
     int K = 0, Kp = 0;
 };
 
+// Switches read from the environment when a handle is created (A/B measurements and tests of every kernel variant;
+// the defaults are the product configuration).
+struct TensorTuning {
+    bool pdl = true;            // HB_NO_PDL: no programmatic dependent launch
+    bool pair = true;           // HB_NO_PAIR: projection without 2-CTA multicast clusters
+    bool stack = true;          // HB_NO_STACK: 3-term recurrence MMAs instead of the stacked [h_hi | h_lo] operand
+    bool live8 = true;          // HB_NO_LIVE8: never use the 8-live-window recurrence tile
+    int windows_per_cta = 0;    // HB_WINDOWS_PER_CTA = 8 | 16 | 32: force the recurrence tile
+    bool fused = false;         // HB_FUSED: encoder recurrence + decoder projection in one launch
+    bool persistent = false;    // HB_PERSISTENT: whole chunk loop in one launch
+    static TensorTuning from_env() {
+        TensorTuning t;
+        t.pdl = getenv("HB_NO_PDL") == nullptr;
+        t.pair = getenv("HB_NO_PAIR") == nullptr;
+        t.stack = getenv("HB_NO_STACK") == nullptr;
+        t.persistent = getenv("HB_PERSISTENT") != nullptr;
+        t.live8 = getenv("HB_NO_LIVE8") == nullptr && !t.persistent;
+        t.fused = getenv("HB_FUSED") != nullptr;
+        if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
+            const int n = atoi(v);
+            if (n == 8 || n == 16 || n == 32) t.windows_per_cta = n;
+        }
+        return t;
+    }
+};
+
 struct TensorEngine {
+    TensorTuning tune;
     unsigned long long* progress = nullptr;   // [<= sm_count][2] encoder progress counters of the fused launch
     int* tile_order = nullptr;                // column-tile order of the fused projection (earliest complete first)
     int tile_order_w = -1;
@@ -1071,6 +1126,7 @@ inline void tensor_engine_destroy(TensorEngine* e) {
 
 inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int sm_count, char* err, size_t errlen) {
     TensorEngine* e = new TensorEngine();
+    e->tune = TensorTuning::from_env();
     e->features = features;
     e->sm_count = sm_count;
     bool ok = detail::pack_layer(w->encoder, features, /*activations_scaled=*/false, &e->enc, err, errlen) &&
@@ -1103,9 +1159,11 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         };
         set((const void*)tc_projection_kernel<false>, detail::projection_smem(e->enc.Kp * 16, 1));
         set((const void*)tc_projection_kernel<true>, detail::projection_smem(YROW, 2));
-        set((const void*)tc_recurrence_kernel<16, 8>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<16, 16>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<32, 32>, detail::recurrence_smem<32>());
+        set((const void*)tc_recurrence_kernel<16, 8, false>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 16, false>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 8, true>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 16, true>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<32, 32, false>, detail::recurrence_smem<32>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
         set((const void*)tc_encoder_fused_kernel<16, 8>, std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)));
         set((const void*)tc_encoder_fused_kernel<16, 16>, std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)));
@@ -1138,9 +1196,9 @@ inline size_t tensor_engine_workspace_bytes(const TensorEngine* e, int64_t B, in
 }
 
 // live windows per recurrence CTA: the smallest tile (lowest step latency) that still fits the batch on the chip
-inline int pick_windows_per_cta(int64_t B, int sm_count) {
-    static const bool allow8 = getenv("HB_NO_LIVE8") == nullptr && getenv("HB_PERSISTENT") == nullptr;
-    if (allow8 && 2 * B <= (int64_t)8 * sm_count) return 8;
+inline int pick_windows_per_cta(const TensorTuning& tune, int64_t B, int sm_count) {
+    if (tune.windows_per_cta) return tune.windows_per_cta;
+    if (tune.live8 && 2 * B <= (int64_t)8 * sm_count) return 8;
     return 2 * B <= (int64_t)16 * sm_count ? 16 : 32;
 }
 
@@ -1160,8 +1218,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     cudaMemsetAsync(e->flags, 0, std::min(e->flags_capacity, (size_t)16384) * sizeof(unsigned long long), s);   // persistent-kernel counters
     const int xblk = e->enc.Kp * 16;                           // bytes of one (group, column) pixel block
     const int proj_workers = std::max(1, e->sm_count / 6);
-    static const bool pdl = getenv("HB_NO_PDL") == nullptr;
-    static const int pair_mode = getenv("HB_NO_PAIR") == nullptr ? 1 : 0;   // 2-CTA clusters share activation tiles by multicast
+    const bool pdl = e->tune.pdl;
+    const int pair_mode = e->tune.pair ? 1 : 0;               // 2-CTA clusters share activation tiles by multicast
     if (enc_cols > 0) {
         // once per batch: pixels -> operand image, then the encoder projection of EVERY covered column
         // (chunks overlap by W - J columns and gi of a column does not depend on the chunk)
@@ -1181,7 +1239,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const float* hid = nullptr;
     float* hid_bufs[2] = {ws.hid_a, ws.hid_b};
     int flip = 0;
-    const int nrec = pick_windows_per_cta(B, e->sm_count);
+    const int nrec = pick_windows_per_cta(e->tune, B, e->sm_count);
     const dim3 grid_rec((unsigned)((B + nrec - 1) / nrec), 2);
     const int tiles_proj = (int)std::min<int64_t>(n_wg * ((W + 7) / 8), proj_workers);
     const int tiles_heads = (int)std::min<int64_t>(n_wg * ((W + 15) / 16), e->sm_count);
@@ -1198,7 +1256,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const int fused_workers = (e->sm_count - 2 * rec_ctas) / 6;
     // Opt-in (HB_FUSED=1): correct and tested; measured slower than separate launches (4.45 vs 4.17 ms per batch at
     // B=256): the projection CTAs that share the launch get fewer SMs and compete with the recurrence for L2.
-    static const bool fuse_allowed = getenv("HB_FUSED") != nullptr;
+    const bool fuse_allowed = e->tune.fused;
     const bool fused = fuse_allowed && nrec <= 16 && fused_workers >= 8 && (W + 7) / 8 <= 4096 && !e->time_recurrence;
     // persistent window kernel: every role of the whole chunk loop resident at once
     const int n_chunks = T < W ? 0 : (T - W) / J + 1;
@@ -1209,7 +1267,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     // Opt-in (HB_PERSISTENT=1): correct and tested, but measured SLOWER than the per-chunk launches at B=256
     // (5.0-5.3 ms vs 4.8 ms per batch): with half of the SMs pinned to the recurrence roles the projection
     // role, which is L2-bound (each activation tile is fetched by 6 gate-block CTAs), cannot hide behind the encoder.
-    static const bool persistent_allowed = getenv("HB_PERSISTENT") != nullptr;
+    const bool persistent_allowed = e->tune.persistent;
     const bool persistent = persistent_allowed && nrec == 16 && n_chunks > 0 && persistent_workers >= 8 && tiles8 <= 4096 &&
                             flags_needed <= 16384 && !e->time_recurrence;
     if ((fused || persistent) && e->tile_order_w != W) {
@@ -1258,12 +1316,15 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             cudaEventRecord(e->rec_events[slot].first, s);
             use_pdl = false;
         }
+        const bool stack = e->tune.stack;
         if (nrec == 8)
-            detail::launch(tc_recurrence_kernel<16, 8>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl, ra);
+            detail::launch(stack ? tc_recurrence_kernel<16, 8, true> : tc_recurrence_kernel<16, 8, false>, grid_rec, dim3(REC_TC_THREADS),
+                           detail::recurrence_smem<16>(), s, use_pdl, ra);
         else if (nrec == 16)
-            detail::launch(tc_recurrence_kernel<16, 16>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<16>(), s, use_pdl, ra);
+            detail::launch(stack ? tc_recurrence_kernel<16, 16, true> : tc_recurrence_kernel<16, 16, false>, grid_rec, dim3(REC_TC_THREADS),
+                           detail::recurrence_smem<16>(), s, use_pdl, ra);
         else
-            detail::launch(tc_recurrence_kernel<32, 32>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl, ra);
+            detail::launch(tc_recurrence_kernel<32, 32, false>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl, ra);
         if (e->time_recurrence) cudaEventRecord(e->rec_events[slot].second, s);
     };
     HeadsArgs heads_base{};

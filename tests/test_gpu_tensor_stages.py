@@ -26,3 +26,43 @@ def test_stage_matches_fp32_engine(engine, batch, seq, features):
     err = max(np.abs(got[2] - ref[2]).max(), np.abs(got[3] - ref[3]).max())
     assert np.isfinite(got[2]).all() and np.isfinite(got[3]).all()
     assert err <= 5e-6, f"{engine}: max |dP| vs fp32 engine = {err:.3e}"
+
+
+VARIANTS = {
+    "tile8_stacked": {"HB_WINDOWS_PER_CTA": "8"},
+    "tile8_3term": {"HB_WINDOWS_PER_CTA": "8", "HB_NO_STACK": "1"},
+    "tile16_stacked": {"HB_WINDOWS_PER_CTA": "16"},
+    "tile16_3term": {"HB_WINDOWS_PER_CTA": "16", "HB_NO_STACK": "1"},
+    "tile32": {"HB_WINDOWS_PER_CTA": "32"},
+    "no_pair_no_pdl": {"HB_NO_PAIR": "1", "HB_NO_PDL": "1"},
+    "fused_encoder_projection": {"HB_FUSED": "1"},
+    "persistent_window_kernel": {"HB_PERSISTENT": "1"},
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_kernel_variants_match_fp32_engine(variant, monkeypatch):
+    """Every recurrence tile / launch-structure variant of the tensor engine (the switches are read from the
+    environment when the handle is created) against the fp32 engine, same tolerance as above."""
+    from helen_b200.predictor import WindowPredictor
+    for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_FUSED", "HB_PERSISTENT", "HB_NO_LIVE8"):
+        monkeypatch.delenv(k, raising=False)
+    batch, seq, features = 45, 250, 10
+    sd = random_state_dict(features, seed=5)
+    gen = torch.Generator().manual_seed(77)
+    images = torch.randint(0, 256, (batch, seq, features), dtype=torch.uint8, generator=gen).cuda()
+    ref_pred = WindowPredictor(sd, device=0)
+    ref_pred.set_engine("fp32")
+    ref = [t.cpu().numpy() for t in ref_pred.predict(images, return_probs=True)]
+    ref_pred.close()
+    for k, v in VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+    pred = WindowPredictor(sd, device=0)
+    pred.set_engine("tensor")
+    got = [t.cpu().numpy() for t in pred.predict(images, return_probs=True)]
+    again = [t.cpu().numpy() for t in pred.predict(images, return_probs=True)]
+    pred.close()
+    err = max(np.abs(got[2] - ref[2]).max(), np.abs(got[3] - ref[3]).max())
+    assert np.isfinite(got[2]).all() and np.isfinite(got[3]).all()
+    assert err <= 5e-6, f"{variant}: max |dP| vs fp32 engine = {err:.3e}"
+    assert np.array_equal(got[0], again[0]) and np.array_equal(got[1], again[1]), f"{variant}: not repeatable"
