@@ -261,6 +261,9 @@ def run_native(args, rank, world, local_rank):
         torch.cuda.synchronize()
         dom_ms, dom_launches = pred.dominant_kernel_time_ms(reset=True)
         pred.enable_kernel_timing(False)
+    pred.predict(images)
+    torch.cuda.synchronize()
+    plan = pred.last_launch_plan()
 
     # end to end through the host-buffer entry: pageable numpy in, numpy labels out
     for _ in range(max(1, args.warmup // 2)):
@@ -293,7 +296,22 @@ def run_native(args, rank, world, local_rank):
                      "frac": achieved_tf / peaks["burst"], "frac_of_sustained": achieved_tf / peaks["sustained"],
                      "flop_per_window": fpw, "ms_per_batch": kernel_ms,
                      "what": "all kernels of one batch (library event bracket on the launching stream)"}
-    if dom_launches:
+    if dom_launches and plan["chunkloop"]:
+        # one launch = the whole chunk loop of the batch: per chunk enc hh + dec ih + dec hh + heads (SURVEY 8d terms;
+        # the encoder input projection runs once per batch in its own kernel and is not counted here)
+        chunks = (T_COLUMNS - WINDOW) // JUMP + 1
+        mac_chunk = 2 * (2 * WINDOW * 3 * HIDDEN * HIDDEN) + 2 * WINDOW * 3 * HIDDEN * 2 * HIDDEN + WINDOW * 2 * HIDDEN * 16
+        dom_flop = args.batch * chunks * 2 * mac_chunk
+        dom_ms_launch = dom_ms / dom_launches
+        dom_tf = dom_flop / (dom_ms_launch * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "tc_chunkloop_kernel", "achieved": dom_tf, "peak": peaks["burst"],
+                    "unit": "TFLOP/s", "frac": dom_tf / peaks["burst"], "frac_of_sustained": dom_tf / peaks["sustained"],
+                    "peak_source": ("measured" if peaks["source"] == "measured" else "fallback") + " bf16 burst",
+                    "flop_per_launch": dom_flop, "kernel_ms_per_launch": dom_ms_launch, "launches_timed": dom_launches,
+                    "us_per_dependent_step": 1e3 * dom_ms_launch / (chunks * 2 * WINDOW),
+                    "traffic": kernel_traffic_bytes(engine, args.batch, args.features),
+                    "note": "latency-bound at this batch: 3,800 dependent GRU steps per launch (DESIGN.md section 5)"}
+    elif dom_launches:
         # one recurrence launch = batch windows x 100 dependent steps x 2 directions of one layer
         rec_flop = args.batch * WINDOW * 2 * (2 * 3 * HIDDEN * HIDDEN)
         rec_ms = dom_ms / dom_launches
@@ -316,6 +334,7 @@ def run_native(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(host_np.nbytes),
                 "d2h_bytes_per_step": int(2 * args.batch * T_COLUMNS)},
         "gpu_launches": int(launches),
+        "launch_plan": plan,
         "clocks": clocks,
         "roofline": roofline,
         "roofline_path": path_roofline,

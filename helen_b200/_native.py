@@ -9,7 +9,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhelen_b200.so")
 
-HB_ABI_VERSION = 1
+HB_ABI_VERSION = 2
 HB_OK = 0
 HB_ERR_INVALID_ARGUMENT = -1
 HB_ERR_UNSUPPORTED_DEVICE = -2
@@ -33,6 +33,11 @@ class hb_weights(ctypes.Structure):
                 ("base_weight", _FP), ("base_bias", _FP), ("rle_weight", _FP), ("rle_bias", _FP)]
 
 
+class hb_launch_plan(ctypes.Structure):
+    _fields_ = [("chunkloop", c_int), ("windows_per_cta", c_int), ("stacked_operand", c_int),
+                ("recurrence_ctas", c_int), ("projection_workers", c_int), ("heads_workers", c_int)]
+
+
 # every symbol include/helen_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "hb_abi_version": (c_int, []),
@@ -50,6 +55,7 @@ SIGNATURES = {
     "hb_forward_chunk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
     "hb_launch_count": (c_int64, [c_void_p]),
+    "hb_last_launch_plan": (c_int, [c_void_p, POINTER(hb_launch_plan)]),
     "hb_enable_kernel_timing": (c_int, [c_void_p, c_int]),
     "hb_kernel_time_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
     "hb_dominant_kernel_time_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),

@@ -458,6 +458,15 @@ int hb_enable_kernel_timing(hb_handle* h, int enable) {
     return HB_OK;
 }
 
+int hb_last_launch_plan(const hb_handle* h, hb_launch_plan* out) {
+    if (!h || !out) return fail(HB_ERR_INVALID_ARGUMENT, "null argument");
+    std::memset(out, 0, sizeof(*out));
+#ifndef HB_NO_TENSOR_ENGINE
+    *out = h->tensor->last_plan;
+#endif
+    return HB_OK;
+}
+
 int hb_dominant_kernel_time_ms(hb_handle* h, double* total_ms, int64_t* launches, int reset) {
     if (!h || !total_ms || !launches) return fail(HB_ERR_INVALID_ARGUMENT, "null argument");
     *total_ms = 0.0;

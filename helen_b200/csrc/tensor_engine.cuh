@@ -316,27 +316,35 @@ constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate 
 template <int N> __host__ __device__ constexpr int gi_stages() { return N <= 16 ? 4 : 3; }   // N = 32: 3 x 48 KB (227 KB smem limit)
 constexpr int PUBLISH_LAG = 4;
 
-struct RecArgs {
-    const float* gi;               // gi' rows; row of (window b, step column t) = b * gi_cols + gi_col0 + t
+// One GRU layer as the recurrence role sees it.
+struct RecLayer {
+    const float* gi;               // gi' rows; row of (window b, chunk k, step column t) = b * gi_cols + gi_col0 + k * gi_col_step + t
+    int gi_cols, gi_col0, gi_col_step;
     const uint32_t* whh_tmem;      // [2 dirs][hi, lo][3][128][64] packed fp16 pairs
     const float* gate_consts;      // [2 dirs][4][128]: inv_r', inv_z', inv_n', b_hn'  (per unit)
+    uint8_t* yimg[2];              // operand image of the layer output: [0] even chunks, [1] odd chunks
+    unsigned long long* progress;  // [ctas][2 dirs] columns whose output has landed in yimg (+ epoch + chunk * W), or nullptr
+    // chunk-loop kernel only (counters in global memory, see tc_chunkloop_kernel):
+    const unsigned long long* tile_flags;      // decoder: gi' tile (group, tile, dir) of chunk k is ready at >= 12 (k + 1)
+    const unsigned long long* heads_done; int heads_per_chunk;   // decoder: yimg[k & 1] reusable when >= heads_per_chunk (k - 1)
+    const unsigned long long* consumed_flags;  // encoder: tile flags (both directions) that tell yimg of chunk k - 1 has been read
+};
+
+// n_layers == 1: one layer, one chunk (per-chunk launches).  n_layers == 2: the whole chunk loop of the reference
+// (predict_gpu.py:114-149) in one CTA: encoder and decoder phases alternate, the state h stays in registers from phase
+// to phase (decoder h_0 = encoder h_n, next encoder h_0 = decoder h_n, TransducerModel.py:68-78) and only W_hh is
+// re-uploaded into TMEM at every phase switch.
+struct RecArgs {
+    RecLayer layer[2];
+    int n_layers, n_chunks;
     const float* h_in;             // [B, 2, 128] fp32 or nullptr (zeros)
-    float* h_out;                  // [B, 2, 128] fp32
-    uint8_t* yimg;                 // operand image of the layer output
-    int64_t B; int W; int gi_cols, gi_col0;
-    unsigned long long* progress;  // [ctas][2 dirs] steps whose output has landed in yimg (+ epoch), or nullptr
+    float* h_out;                  // [B, 2, 128] fp32 or nullptr
+    int64_t B; int W;
+    int tiles_t;                   // 8-column tiles per chunk (tile_flags indexing)
+    int n_wg;                      // existing window groups (flags of groups past it are never raised)
     unsigned long long epoch;
     long long* dbg;
-    // persistent mode (one launch walks n_chunks chunks of the reference loop; 0/1 = single chunk):
-    int n_chunks; int gi_col_step;               // chunk k reads gi' columns gi_col0 + k * gi_col_step + t
-    const float* h_in_next;                      // h_in of chunks k > 0 (written by the other layer's CTA)
-    uint8_t* yimg_odd;                           // output image of odd chunks (nullptr: same as yimg)
-    const unsigned long long* wait_done; int wait_done_bias;   // chunk k starts when wait_done[cta][dir] >= k + bias
-    unsigned long long* publish_done;            // [cta][dir] = chunks finished (h_out visible)
-    const unsigned long long* tile_flags; int tiles_t;         // decoder: gi' tile (group, tile, dir) ready at >= 12 (k + 1)
-    const unsigned long long* heads_done; int heads_per_chunk; // decoder: yimg buffer reusable when >= heads_per_chunk (k - 1)
-    int n_wg;                                    // existing window groups (flags of groups past it are never raised)
-    int dbg_role;                                // HB_DEBUG_TIMELINE: 0 encoder, 1 decoder
+    int dbg_layer;                 // HB_DEBUG_TIMELINE: which layer's steps are recorded
 };
 
 // NLIVE <= N windows of the N accumulator columns are real: the MMA shape needs N >= 16, but with 8 live windows
@@ -349,15 +357,12 @@ struct RecArgs {
 template <int N, int NLIVE, bool STACK = false>
 __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem, const int cta_x, const int dir)
 {
-    const float* __restrict__ gi = ra.gi;
-    const uint32_t* __restrict__ whh_tmem = ra.whh_tmem;
-    const float* __restrict__ gate_consts = ra.gate_consts;
-    float* __restrict__ h_out = ra.h_out;
     const int64_t B = ra.B;
-    const int W = ra.W, gi_cols = ra.gi_cols;
-    const int n_chunks = ra.n_chunks > 0 ? ra.n_chunks : 1;
+    const int W = ra.W;
+    const int n_layers = ra.n_layers;
+    const int n_phases = (ra.n_chunks > 0 ? ra.n_chunks : 1) * n_layers;
     long long* __restrict__ dbg = ra.dbg;
-#define HB_DBG(role, s, k) do { if (dbg && cta_x == 0 && dir == 0 && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
+#define HB_DBG(role, s, k) do { if (dbg_on && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N accumulator columns per gate block (3N must stay below REC_W_COL0)");
     static_assert(NLIVE == N || (N == 16 && NLIVE == 8), "live windows per CTA");
     static_assert(!STACK || N == 16, "stacked operand: 3 x 2 NLIVE accumulator columns must stay below REC_W_COL0");
@@ -404,67 +409,63 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < REC_GATE_WARPS) {
-        // W_hh -> TMEM (once).  Warp w covers TMEM lanes 32 (w%4)..+31 (thread = gate row j); the four warps of a
-        // lane quarter split (hi | lo image) x (k-pair columns 0-31 | 32-63); 32 words in flight per round trip.
-        const int q = warp & 3, j = q * 32 + lane, term = (warp >> 2) & 1, half = warp >> 3;
-        const uint32_t* src = whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64 + half * 32;
-#pragma unroll 1
-        for (int gb = 0; gb < 3; ++gb) {
-            uint32_t r[32];
-            const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64);
+    // gate-thread state that lives across phases: (warp w, lane l) owns hidden unit j = 32 (w%4) + l for NW windows
+    const int q = warp & 3;
+    const int j = q * 32 + lane;
+    const int win0 = (warp >> 2) * NW;
+    float h_own[NW];                                         // h * 2^10
 #pragma unroll
-            for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-            const uint32_t dst = tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
-            tc::tmem_st16(dst, r);
-            tc::tmem_st16(dst + 16, r + 16);
-        }
-        tc::tmem_st_wait();
-    }
-    tc::pdl_grid_dependency_wait();                          // everything below touches upstream kernels' buffers
+    for (int i = 0; i < NW; ++i) h_own[i] = 0.f;
 
-    for (int chunk = 0; chunk < n_chunks; ++chunk) {
-    const float* __restrict__ h_in = chunk == 0 ? ra.h_in : ra.h_in_next;
-    uint8_t* __restrict__ yimg = ((chunk & 1) && ra.yimg_odd) ? ra.yimg_odd : ra.yimg;
-    const int gi_col0 = ra.gi_col0 + chunk * ra.gi_col_step;
+    for (int phase = 0; phase < n_phases; ++phase) {
+    const int chunk = phase / n_layers, li = phase - chunk * n_layers;
+    const RecLayer& L = ra.layer[li];
+    const float* __restrict__ gi = L.gi;
+    const int gi_cols = L.gi_cols;
+    const int gi_col0 = L.gi_col0 + chunk * L.gi_col_step;
+    uint8_t* __restrict__ yimg = L.yimg[chunk & 1];
     const unsigned long long prog_base = ra.epoch + (unsigned long long)chunk * W;
-    if (chunk > 0 || ra.wait_done != nullptr) {
-        // chunk boundary of the persistent kernel: fresh barriers, then wait for the upstream layer
+    const bool dbg_on = dbg != nullptr && cta_x == 0 && dir == 0 && li == ra.dbg_layer && (n_layers == 1 || chunk == 2);
+    if (phase > 0) {
+        // phase boundary: fresh barriers, then the cross-CTA conditions of this phase
         if (tid == 0) {
-            if (chunk > 0) {
-                for (int i = 0; i < 3; ++i) { tc::mbar_inval(acc_ready + i); tc::mbar_init(acc_ready + i, 1); }
-                tc::mbar_inval(h_ready); tc::mbar_init(h_ready, REC_GATE_WARPS);
-                for (int i = 0; i < 2; ++i) {
-                    tc::mbar_inval(h_free + i); tc::mbar_init(h_free + i, 1);
-                    tc::mbar_inval(y_ready + i); tc::mbar_init(y_ready + i, REC_GATE_WARPS);
-                }
-                for (int i = 0; i < GI_STAGES; ++i) {
-                    tc::mbar_inval(gi_full + i); tc::mbar_init(gi_full + i, 1);
-                    tc::mbar_inval(gi_empty + i); tc::mbar_init(gi_empty + i, REC_GATE_WARPS);
-                }
-                tc::mbar_fence_init();
+            for (int i = 0; i < 3; ++i) { tc::mbar_inval(acc_ready + i); tc::mbar_init(acc_ready + i, 1); }
+            tc::mbar_inval(h_ready); tc::mbar_init(h_ready, REC_GATE_WARPS);
+            for (int i = 0; i < 2; ++i) {
+                tc::mbar_inval(h_free + i); tc::mbar_init(h_free + i, 1);
+                tc::mbar_inval(y_ready + i); tc::mbar_init(y_ready + i, REC_GATE_WARPS);
             }
-            if (ra.wait_done != nullptr && chunk + ra.wait_done_bias > 0)
-                tc::spin_until_ge(ra.wait_done + (size_t)cta_x * 2 + dir, (unsigned long long)(chunk + ra.wait_done_bias));
-            if (ra.heads_done != nullptr && chunk >= 2)
-                for (int g = 0; g < NG; ++g)
+            for (int i = 0; i < GI_STAGES; ++i) {
+                tc::mbar_inval(gi_full + i); tc::mbar_init(gi_full + i, 1);
+                tc::mbar_inval(gi_empty + i); tc::mbar_init(gi_empty + i, REC_GATE_WARPS);
+            }
+            tc::mbar_fence_init();
+        }
+        if (warp == 0) {
+            if (L.heads_done != nullptr && chunk >= 2)       // the heads role has read the image this phase overwrites
+                for (int g = lane; g < NG; g += 32)
                     if (cta_x * NG + g < ra.n_wg)
-                        tc::spin_until_ge(ra.heads_done + (size_t)cta_x * NG + g, (unsigned long long)ra.heads_per_chunk * (chunk - 1));
+                        tc::spin_until_ge(L.heads_done + (size_t)cta_x * NG + g, (unsigned long long)L.heads_per_chunk * (chunk - 1));
+            if (L.consumed_flags != nullptr && chunk >= 1)   // every projection CTA has read this layer's previous image
+                for (int f = lane; f < NG * ra.tiles_t * 2; f += 32)
+                    if (cta_x * NG + f / (ra.tiles_t * 2) < ra.n_wg)
+                        tc::spin_until_ge(L.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, 12ull * chunk);
         }
         __syncthreads();
     }
-    if (dbg && n_chunks > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (ra.dbg_role * 64 + chunk) * 2] = (long long)globaltimer_ns();
+    if (dbg && n_layers > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (li * 64 + chunk) * 2] = (long long)globaltimer_ns();
 
     if (warp == REC_GATE_WARPS + 1) {
         // ===================== gi loader: bulk copies, GI_STAGES steps ahead =====================
+        if (phase == 0) tc::pdl_grid_dependency_wait();      // gi' comes from an upstream kernel
         __syncthreads();
         const float* src0 = gi + ((b0 + lane) * gi_cols + gi_col0) * (int64_t)(2 * G) + dir * G;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % GI_STAGES;
-            if (ra.tile_flags != nullptr && (s == 0 || (t & 7) == (dir ? 7 : 0))) {
-                // decoder in the persistent kernel: the projection CTAs announce finished gi' tiles
+            if (L.tile_flags != nullptr && (s == 0 || (t & 7) == (dir ? 7 : 0))) {
+                // decoder in the chunk-loop kernel: the projection CTAs announce finished gi' tiles
                 if (lane < NG && cta_x * NG + lane < ra.n_wg)
-                    tc::spin_until_ge(ra.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 12ull * (chunk + 1));
+                    tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 12ull * (chunk + 1));
                 tc::fence_proxy_async_all();
                 __syncwarp();
             }
@@ -475,8 +476,9 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         }
     } else if (warp == REC_GATE_WARPS + 2) {
         // ===================== y store: the h image of step s is the layer output at column t_s ====
+        if (phase == 0) tc::pdl_grid_dependency_wait();      // yimg may still be read by an upstream kernel
         __syncthreads();
-        unsigned long long* flag = ra.progress ? ra.progress + (size_t)cta_x * 2 + dir : nullptr;
+        unsigned long long* flag = L.progress ? L.progress + (size_t)cta_x * 2 + dir : nullptr;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int buf = (s + 1) & 1;                     // the image written during step s
             tc::mbar_wait(y_ready + buf, (uint32_t)((s >> 1) & 1));
@@ -490,7 +492,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (lane == 0) tc::mbar_arrive(h_free + buf);
             if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG) & 3) == 0) {
                 // every 4th step: all stores but the newest PUBLISH_LAG have landed in global memory, publish
-                // that many completed columns to the projection CTAs.  (Waiting for the newest store, or
+                // that many completed columns to the consumer CTAs.  (Waiting for the newest store, or
                 // fencing every step, would put a global round trip on the step's critical path via h_free.)
                 if (lane < 2 * NG) { tc::bulk_wait_pending<PUBLISH_LAG>(); tc::fence_proxy_async_all(); }
                 __syncwarp();
@@ -502,10 +504,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)W);
     } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
-        // Measured (HB_DEBUG_TIMELINE): an M=128, N=16, K=16 MMA occupies the tensor pipe ~13 cycles, so
-        // the 72 MMAs of a step take ~1000 cycles however they are issued (a second issuer warp and an
-        // issue order rotating over the gate blocks were both slower); per-block commits let the gate
-        // warps overlap the r and z sigmoids with the remaining MMAs.
+        // Measured (HB_DEBUG_TIMELINE): an M=128, N=16, K=16 MMA occupies the tensor pipe ~12 cycles, so the MMA time
+        // of a step is set by the instruction count (a second issuer warp and an issue order rotating over the gate
+        // blocks were both slower); per-block commits let the gate warps overlap the r and z sigmoids with the
+        // remaining MMAs.
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
         const uint32_t idesc = tc::idesc_f16_f32(128, NACC);
@@ -549,17 +551,37 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         }
     } else {
         // ===================== gate warps =====================
-        const int q = warp & 3;
-        const int j = q * 32 + lane;
-        const int win0 = (warp >> 2) * NW;
-        const float* gc = gate_consts + (size_t)dir * 4 * H + j;
+        if (phase == 0 || n_layers > 1) {
+            // W_hh of this phase's layer -> TMEM.  Warp w covers TMEM lanes 32 (w%4)..+31 (thread = gate row j); the four
+            // warps of a lane quarter split (hi | lo image) x (k-pair columns 0-31 | 32-63); 32 words in flight per round
+            // trip.  (All MMAs of the previous phase have completed: every gate warp waited for its last accumulator.)
+            const int term = (warp >> 2) & 1, half = warp >> 3;
+            const uint32_t* src = L.whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64 + half * 32;
+#pragma unroll 1
+            for (int gb = 0; gb < 3; ++gb) {
+                uint32_t r[32];
+                const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                const uint32_t dst = tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
+                tc::tmem_st16(dst, r);
+                tc::tmem_st16(dst + 16, r + 16);
+            }
+            tc::tmem_st_wait();
+        }
+        const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
         const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
-        float h_own[NW];                                     // h * 2^10
         uint32_t h_off[NW];
+        if (phase == 0) {
+            tc::pdl_grid_dependency_wait();                  // h_in comes from an upstream kernel
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const int64_t b = b0 + win0 + i;
+                h_own[i] = (ra.h_in != nullptr && b < B) ? __ldcg(ra.h_in + (b * 2 + dir) * H + j) * ACT_SCALE : 0.f;   // L2: may come from another SM
+            }
+        }
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-            const int64_t b = b0 + win0 + i;
-            h_own[i] = (h_in != nullptr && b < B) ? __ldcg(h_in + (b * 2 + dir) * H + j) * ACT_SCALE : 0.f;   // L2: may come from another SM
             h_off[i] = tc::core_offset(win0 + i, j, H_LBO, YBLK);
             __half hi, lo;
             tc::split_f16(h_own[i], hi, lo);
@@ -636,16 +658,17 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + ((s + 1) & 1)); }
             if (drole < 3) HB_DBG(drole, s, 6);
         }
+        if (phase == n_phases - 1 && ra.h_out != nullptr) {
 #pragma unroll
-        for (int i = 0; i < NW; ++i)
-            if (b0 + win0 + i < B) h_out[((b0 + win0 + i) * 2 + dir) * H + j] = h_own[i] * ACT_SCALE_INV;
-        if (ra.publish_done != nullptr) __threadfence();
+            for (int i = 0; i < NW; ++i)
+                if (b0 + win0 + i < B) ra.h_out[((b0 + win0 + i) * 2 + dir) * H + j] = h_own[i] * ACT_SCALE_INV;
+        }
     }
     tc::tc_fence_before();
-    __syncthreads();                                         // chunk end: every role is done with the barriers
-    if (ra.publish_done != nullptr && tid == 0) tc::st_release_gpu(ra.publish_done + (size_t)cta_x * 2 + dir, (unsigned long long)(chunk + 1));
-    if (dbg && n_chunks > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (ra.dbg_role * 64 + chunk) * 2 + 1] = (long long)globaltimer_ns();
-    }   // chunk loop
+    __syncthreads();                                         // phase end: every role is done with the barriers
+    if (dbg && n_layers > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (li * 64 + chunk) * 2 + 1] = (long long)globaltimer_ns();
+    }   // phase loop
+#undef HB_DBG
     if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -655,28 +678,6 @@ tc_recurrence_kernel(const RecArgs ra)
 {
     extern __shared__ __align__(128) uint8_t smem_rec[];
     recurrence_role<N, NLIVE, STACK>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
-}
-
-// Encoder recurrence and decoder input projection in ONE launch: CTAs [0, 2 * rec_ctas) run the
-// recurrence, the others hold the decoder's W_ih blocks in TMEM and project column tiles as soon
-// as both encoder directions have stored them (progress counters in global memory), so that when
-// the encoder's last step retires only the two edge tiles are left.  All CTAs are co-resident
-// (grid <= SM count, one CTA per SM), which makes spinning on the counters safe.
-template <int N, int NLIVE>
-__global__ void __launch_bounds__(REC_TC_THREADS, 1)
-tc_encoder_fused_kernel(const RecArgs ra, const ProjArgs pa, const int rec_ctas, const int proj_workers)
-{
-    extern __shared__ __align__(128) uint8_t smem_fused[];
-    const int bid = (int)blockIdx.x;
-    if (bid < 2 * rec_ctas) {
-        recurrence_role<N, NLIVE>(ra, smem_fused, bid >> 1, bid & 1);
-        if (ra.dbg && threadIdx.x == 0) atomicMax((unsigned long long*)ra.dbg + 4 * 128 * 8 - 2, globaltimer_ns());   // last recurrence CTA done
-    } else {
-        if (threadIdx.x >= PROJ_THREADS) return;
-        const int pb = bid - 2 * rec_ctas;
-        projection_role<true>(pa, smem_fused, pb % 6, pb / 6, proj_workers);
-        if (ra.dbg && threadIdx.x == 0) atomicMax((unsigned long long*)ra.dbg + 4 * 128 * 8 - 1, globaltimer_ns());   // last projection CTA done
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -845,35 +846,38 @@ tc_heads_kernel(const HeadsArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
-// The whole chunk loop of one batch in ONE launch (small batches: every role fits on the chip at once).
-//   CTAs [0, 2R)        encoder recurrence   (window tile, direction), W_hh(enc) resident in TMEM
-//   CTAs [2R, 4R)       decoder recurrence                            W_hh(dec) resident in TMEM
-//   CTAs [4R, 4R + 6P)  decoder input projection, one gate block each, W_ih(dec) block resident in TMEM
-//   the rest            heads + softmax + accumulate
+// The whole chunk loop of one batch in ONE launch (every role fits on the chip at once).
+//   CTAs [0, 2R)           recurrence (window tile, direction): encoder and decoder phases alternate in the same CTA,
+//                          h stays in registers, W_hh of the phase's layer is re-uploaded into TMEM (~1 us per switch)
+//   CTAs [2R, 2R + 6P)     decoder input projection, one gate block each, W_ih(dec) block resident in TMEM;
+//                          column tiles are projected as soon as both encoder directions have stored them
+//   the rest               heads + softmax + accumulate, following the decoder's progress
 // Hand-offs go through counters in global memory (release/acquire at gpu scope):
-//   encoder columns done -> projection;  projection tiles done -> decoder;  decoder columns done -> heads;
-//   h of a finished chunk -> the other layer;  heads done -> decoder (yimg2 buffer reuse).
-// Every CTA is resident (grid <= SM count, > 113 KB smem each), so spinning is safe; per chunk the critical
-// path is 100 encoder steps + the two edge tiles of the projection + 100 decoder steps.
+//   encoder columns done -> projection;  projection tiles done -> decoder (gi') and next encoder phase (yimg1 reuse);
+//   decoder columns done -> heads;  heads done -> decoder (yimg2 buffer reuse).
+// Every CTA is resident (grid <= SM count, one CTA per SM), so spinning is safe; per chunk the critical path is
+// 100 encoder steps + the edge tiles of the projection + 100 decoder steps, with no launch boundary in between.
+// Launched as clusters of 2 CTAs: the projection role pairs gate blocks (2b, 2b+1) and multicasts activation tiles.
 // ---------------------------------------------------------------------------------------------
-template <int N>
+template <int N, int NLIVE, bool STACK>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
-tc_window_kernel(const RecArgs enc, const RecArgs dec, const ProjArgs proj, const HeadsArgs heads,
-                 const int rec_ctas, const int proj_workers, const int heads_workers)
+tc_chunkloop_kernel(const RecArgs rec, const ProjArgs proj, const HeadsArgs heads,
+                    const int rec_ctas, const int proj_workers, const int heads_workers)
 {
     extern __shared__ __align__(128) uint8_t smem_all[];
     const int bid = (int)blockIdx.x;
     if (bid < 2 * rec_ctas) {
-        recurrence_role<N, N>(enc, smem_all, bid >> 1, bid & 1);
-    } else if (bid < 4 * rec_ctas) {
-        recurrence_role<N, N>(dec, smem_all, (bid - 2 * rec_ctas) >> 1, bid & 1);
-    } else if (bid < 4 * rec_ctas + 6 * proj_workers) {
-        if (threadIdx.x >= PROJ_THREADS) return;
-        const int pb = bid - 4 * rec_ctas;
+        recurrence_role<N, NLIVE, STACK>(rec, smem_all, bid >> 1, bid & 1);
+    } else if (bid < 2 * rec_ctas + 6 * proj_workers) {
+        if (threadIdx.x >= PROJ_THREADS) {                   // spare warps only keep the pair's cluster barriers aligned
+            if (proj.pair) { tc::cluster_sync_all(); tc::cluster_sync_all(); }
+            return;
+        }
+        const int pb = bid - 2 * rec_ctas;
         projection_role<true>(proj, smem_all, pb % 6, pb / 6, proj_workers);
     } else {
         if (threadIdx.x >= HEADS_THREADS) return;
-        heads_role(heads, smem_all, bid - 4 * rec_ctas - 6 * proj_workers, heads_workers);
+        heads_role(heads, smem_all, bid - 2 * rec_ctas - 6 * proj_workers, heads_workers);
     }
 }
 
@@ -897,33 +901,33 @@ struct TensorTuning {
     bool stack = true;          // HB_NO_STACK: 3-term recurrence MMAs instead of the stacked [h_hi | h_lo] operand
     bool live8 = true;          // HB_NO_LIVE8: never use the 8-live-window recurrence tile
     int windows_per_cta = 0;    // HB_WINDOWS_PER_CTA = 8 | 16 | 32: force the recurrence tile
-    bool fused = false;         // HB_FUSED: encoder recurrence + decoder projection in one launch
-    bool persistent = false;    // HB_PERSISTENT: whole chunk loop in one launch
+    bool chunkloop = true;      // HB_NO_CHUNKLOOP: per-chunk launches even when the whole chunk loop fits on the chip
+    int heads_workers = 0;      // HB_HEADS_WORKERS: CTAs of the heads role in the chunk-loop kernel (even)
     static TensorTuning from_env() {
         TensorTuning t;
         t.pdl = getenv("HB_NO_PDL") == nullptr;
         t.pair = getenv("HB_NO_PAIR") == nullptr;
         t.stack = getenv("HB_NO_STACK") == nullptr;
-        t.persistent = getenv("HB_PERSISTENT") != nullptr;
-        t.live8 = getenv("HB_NO_LIVE8") == nullptr && !t.persistent;
-        t.fused = getenv("HB_FUSED") != nullptr;
+        t.live8 = getenv("HB_NO_LIVE8") == nullptr;
+        t.chunkloop = getenv("HB_NO_CHUNKLOOP") == nullptr;
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
             const int n = atoi(v);
             if (n == 8 || n == 16 || n == 32) t.windows_per_cta = n;
         }
+        if (const char* v = getenv("HB_HEADS_WORKERS")) t.heads_workers = std::max(2, atoi(v) / 2 * 2);
         return t;
     }
 };
 
 struct TensorEngine {
     TensorTuning tune;
-    unsigned long long* progress = nullptr;   // [<= sm_count][2] encoder progress counters of the fused launch
-    int* tile_order = nullptr;                // column-tile order of the fused projection (earliest complete first)
+    hb_launch_plan last_plan{};
+    int* tile_order = nullptr;                // column-tile order of the chunk-loop projection role (earliest complete first)
     int tile_order_w = -1;
     std::vector<int> tile_order_host;
     int* tile_order16 = nullptr;              // same for the 16-column tiles of the heads role
     std::vector<int> tile_order16_host;
-    unsigned long long* flags = nullptr;      // counters of the persistent window kernel
+    unsigned long long* flags = nullptr;      // counters of the chunk-loop kernel
     size_t flags_capacity = 0;
     unsigned long long launch_epoch = 0;
     // optional device timing of every recurrence launch (the dominant kernel), bench.py's roofline pass
@@ -1111,7 +1115,6 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     detail::free_layer(&e->dec);
     cudaFree(e->head_img);
     cudaFree(e->b_head);
-    cudaFree(e->progress);
     cudaFree(e->tile_order);
     cudaFree(e->tile_order16);
     cudaFree(e->flags);
@@ -1165,15 +1168,17 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_recurrence_kernel<16, 16, true>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<32, 32, false>, detail::recurrence_smem<32>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
-        set((const void*)tc_encoder_fused_kernel<16, 8>, std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)));
-        set((const void*)tc_encoder_fused_kernel<16, 16>, std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)));
-        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->progress), (size_t)sm_count * 2 * sizeof(unsigned long long));
-        if (ce == cudaSuccess) ce = cudaMemset(e->progress, 0, (size_t)sm_count * 2 * sizeof(unsigned long long));
+        const size_t loop16 = std::max({detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
+        const size_t loop32 = std::max({detail::recurrence_smem<32>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
+        set((const void*)tc_chunkloop_kernel<16, 8, true>, loop16);
+        set((const void*)tc_chunkloop_kernel<16, 8, false>, loop16);
+        set((const void*)tc_chunkloop_kernel<16, 16, true>, loop16);
+        set((const void*)tc_chunkloop_kernel<16, 16, false>, loop16);
+        set((const void*)tc_chunkloop_kernel<32, 32, false>, loop32);
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order), 4096 * sizeof(int));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order16), 4096 * sizeof(int));
         e->flags_capacity = (size_t)1 << 16;
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->flags), e->flags_capacity * sizeof(unsigned long long));
-        set((const void*)tc_window_kernel<16>, std::max({detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()}));
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
         for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
             ce = cudaEventCreateWithFlags(&e->ev_dec[i], cudaEventDisableTiming);
@@ -1202,6 +1207,31 @@ inline int pick_windows_per_cta(const TensorTuning& tune, int64_t B, int sm_coun
     return 2 * B <= (int64_t)16 * sm_count ? 16 : 32;
 }
 
+// Role split of the chunk-loop kernel: recurrence CTAs for the smallest tile that leaves room for a useful number of
+// projection workers (6 CTAs each) and heads workers.  Returns false when the batch does not fit on the chip at once.
+struct ChunkloopPlan { int tile, rec_ctas, proj_workers, heads_workers; };
+inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, ChunkloopPlan* plan) {
+    const int sms = sm_count / 2 * 2;                          // clusters of 2
+    for (int tile : {8, 16, 32}) {
+        if (tune.windows_per_cta && tile != tune.windows_per_cta) continue;
+        if (tile == 8 && !tune.live8 && !tune.windows_per_cta) continue;
+        const int64_t rec = (B + tile - 1) / tile;
+        if (2 * rec > sms) continue;
+        const int left = sms - (int)(2 * rec);
+        // heads: one CTA in seven of what the recurrence leaves (a heads tile is latency-bound, ~4 us), at least 2;
+        // projection: at least 6 workers (36 CTAs)
+        int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 14) * 2);
+        int proj = (left - heads) / 6;
+        if (proj < 6) continue;
+        heads = left - 6 * proj;                               // whatever the 6-CTA granularity leaves goes to the heads
+        heads = heads / 2 * 2;
+        if (heads < 2) { --proj; heads += 6; }
+        plan->tile = tile; plan->rec_ctas = (int)rec; plan->proj_workers = proj; plan->heads_workers = heads;
+        return true;
+    }
+    return false;
+}
+
 // Returns the number of kernel launches issued, or a negative hb_status (message in err).
 inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t B, int T, int W, int J,
                                  uint8_t* base_labels, uint8_t* rle_labels, float* base_prob, float* rle_prob,
@@ -1215,7 +1245,6 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     int launches = 0;
     cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s);
     cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s);
-    cudaMemsetAsync(e->flags, 0, std::min(e->flags_capacity, (size_t)16384) * sizeof(unsigned long long), s);   // persistent-kernel counters
     const int xblk = e->enc.Kp * 16;                           // bytes of one (group, column) pixel block
     const int proj_workers = std::max(1, e->sm_count / 6);
     const bool pdl = e->tune.pdl;
@@ -1236,6 +1265,104 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                                dim3(1, pair_mode ? 2 : 1, 1), pe);
         launches += 2;
     }
+    static long long* dbg_buf = nullptr;
+    static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
+    static const bool dbg_enc = dbg_on && getenv("HB_DEBUG_TIMELINE")[0] == 'e';
+    if (dbg_on && !dbg_buf) { cudaMalloc(&dbg_buf, 8192 * sizeof(long long)); cudaMemset(dbg_buf, 0, 8192 * sizeof(long long)); }
+    // decoder projection arguments (the same for every chunk)
+    ProjArgs pd{};
+    pd.in_base = ws.yimg1; pd.in_wg_stride = (int64_t)W * 2 * YROW; pd.in_t_stride = 2 * YROW; pd.in_part_stride = YROW;
+    pd.blk_bytes = YROW; pd.lbo = H_LBO; pd.Kp = e->dec.Kp; pd.n_wg = n_wg; pd.W = W;
+    pd.w_tmem = e->dec.wih_tmem; pd.scale_row = e->dec.scale_row; pd.bias_row = e->dec.bias_row; pd.gi = ws.gi;
+    pd.pair = pair_mode;
+    const int n_chunks = T < W ? 0 : (T - W) / J + 1;
+    const int tiles8 = (W + 7) / 8, tiles16 = (W + 15) / 16;
+    auto layer_args = [&](const TensorLayer& L, const float* gi, int gi_cols, int gi_col0, int gi_col_step, uint8_t* y_even, uint8_t* y_odd) {
+        RecLayer r{};
+        r.gi = gi; r.gi_cols = gi_cols; r.gi_col0 = gi_col0; r.gi_col_step = gi_col_step;
+        r.whh_tmem = L.whh_tmem; r.gate_consts = L.gate_consts; r.yimg[0] = y_even; r.yimg[1] = y_odd;
+        return r;
+    };
+    HeadsArgs heads_base{};
+    heads_base.n_wg = n_wg; heads_base.B = B; heads_base.W = W; heads_base.T = T; heads_base.col_step = J;
+    heads_base.w_img = e->head_img; heads_base.b_head = e->b_head; heads_base.inv_scale = e->head_inv;
+    heads_base.p_base = p_base; heads_base.p_rle = p_rle;
+
+    // hb_enable_kernel_timing(2): CUDA events around every launch of the dominant kernel (no launch overlap then)
+    auto dominant_begin = [&]() -> size_t {
+        if (!e->time_recurrence) return 0;
+        if (e->rec_events_used == e->rec_events.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            e->rec_events.emplace_back(a, b);
+        }
+        const size_t slot = e->rec_events_used++;
+        cudaEventRecord(e->rec_events[slot].first, s);
+        return slot;
+    };
+    auto dominant_end = [&](size_t slot) {
+        if (e->time_recurrence) cudaEventRecord(e->rec_events[slot].second, s);
+    };
+    // ---- chunk-loop kernel: every role of the whole chunk loop resident at once ----
+    ChunkloopPlan plan{};
+    bool chunkloop = e->tune.chunkloop && n_chunks > 0 && B > 0 && tiles8 <= 4096 && plan_chunkloop(e->tune, B, e->sm_count, &plan);
+    size_t n_groups = 0, flags_needed = 0;
+    if (chunkloop) {
+        n_groups = (size_t)plan.rec_ctas * (plan.tile / WG);       // window groups the recurrence CTAs cover (>= n_wg)
+        flags_needed = (size_t)4 * plan.rec_ctas + n_groups + n_groups * tiles8 * 2;
+        chunkloop = flags_needed <= e->flags_capacity;
+    }
+    if (chunkloop) {
+        if (e->tile_order_w != W) {
+            // a column tile is complete once the forward pass is past its last column and the reverse pass past its first
+            auto make_order = [&](int width, std::vector<int>& order, int* dev) {
+                const int n = (W + width - 1) / width;
+                order.resize(n);                                   // member vector: outlives the async copy
+                for (int i = 0; i < n; ++i) order[i] = i;
+                auto ready = [&](int tt) { return std::max(std::min(width * tt + width, W), W - width * tt); };
+                std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ready(x) < ready(y); });
+                cudaMemcpyAsync(dev, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
+            };
+            make_order(8, e->tile_order_host, e->tile_order);
+            make_order(16, e->tile_order16_host, e->tile_order16);
+            e->tile_order_w = W;
+        }
+        cudaMemsetAsync(e->flags, 0, flags_needed * sizeof(unsigned long long), s);
+        unsigned long long* f = e->flags;
+        unsigned long long* enc_prog = f;                 f += 2 * plan.rec_ctas;
+        unsigned long long* dec_prog = f;                 f += 2 * plan.rec_ctas;
+        unsigned long long* heads_done = f;               f += n_groups;               // one per window group
+        unsigned long long* tile_flags = f;                                            // [group][tile][dec direction]
+        RecArgs ra{};
+        ra.layer[0] = layer_args(e->enc, ws.gi_enc, enc_cols, 0, J, ws.yimg1, ws.yimg1);
+        ra.layer[0].progress = enc_prog; ra.layer[0].consumed_flags = tile_flags;
+        ra.layer[1] = layer_args(e->dec, ws.gi, W, 0, 0, ws.yimg2[0], ws.yimg2[1]);
+        ra.layer[1].progress = dec_prog; ra.layer[1].tile_flags = tile_flags;
+        ra.layer[1].heads_done = heads_done; ra.layer[1].heads_per_chunk = 4 * tiles16;
+        ra.n_layers = 2; ra.n_chunks = n_chunks; ra.h_in = nullptr; ra.h_out = nullptr; ra.B = B; ra.W = W;
+        ra.tiles_t = tiles8; ra.n_wg = (int)n_wg; ra.epoch = 0; ra.dbg = dbg_buf; ra.dbg_layer = dbg_enc ? 0 : 1;
+        ProjArgs pp = pd;
+        pp.progress = enc_prog; pp.epoch = 0; pp.tile_order = e->tile_order; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
+        HeadsArgs hp = heads_base;
+        hp.yimg = ws.yimg2[0]; hp.yimg_odd = ws.yimg2[1]; hp.col0 = 0; hp.n_chunks = n_chunks;
+        hp.progress = dec_prog; hp.rec_n = plan.tile; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
+        const dim3 grid(2 * plan.rec_ctas + 6 * plan.proj_workers + plan.heads_workers), cluster(pair_mode ? 2 : 1, 1, 1);
+        const size_t smem = std::max({plan.tile == 32 ? detail::recurrence_smem<32>() : detail::recurrence_smem<16>(),
+                                      detail::projection_smem(YROW, 2), detail::heads_smem()});
+        auto go = [&](auto kernel) {
+            const size_t slot = dominant_begin();
+            detail::launch_cluster(kernel, grid, dim3(REC_TC_THREADS), smem, s, pdl && !e->time_recurrence, cluster,
+                                   ra, pp, hp, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
+            dominant_end(slot);
+        };
+        if (plan.tile == 8) { if (e->tune.stack) go(tc_chunkloop_kernel<16, 8, true>); else go(tc_chunkloop_kernel<16, 8, false>); }
+        else if (plan.tile == 16) { if (e->tune.stack) go(tc_chunkloop_kernel<16, 16, true>); else go(tc_chunkloop_kernel<16, 16, false>); }
+        else go(tc_chunkloop_kernel<32, 32, false>);
+        launches += 1;
+    }
+
+    // ---- per-chunk launches (batches too large for the chip, or HB_NO_CHUNKLOOP) ----
     const float* hid = nullptr;
     float* hid_bufs[2] = {ws.hid_a, ws.hid_b};
     int flip = 0;
@@ -1243,79 +1370,17 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const dim3 grid_rec((unsigned)((B + nrec - 1) / nrec), 2);
     const int tiles_proj = (int)std::min<int64_t>(n_wg * ((W + 7) / 8), proj_workers);
     const int tiles_heads = (int)std::min<int64_t>(n_wg * ((W + 15) / 16), e->sm_count);
-    static long long* dbg_buf = nullptr;
-    static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
-    if (dbg_on && !dbg_buf) { cudaMalloc(&dbg_buf, 8192 * sizeof(long long)); cudaMemset(dbg_buf, 0, 8192 * sizeof(long long)); }
-    // decoder projection arguments (the same for every chunk)
-    ProjArgs pd{};
-    pd.in_base = ws.yimg1; pd.in_wg_stride = (int64_t)W * 2 * YROW; pd.in_t_stride = 2 * YROW; pd.in_part_stride = YROW;
-    pd.blk_bytes = YROW; pd.lbo = H_LBO; pd.Kp = e->dec.Kp; pd.n_wg = n_wg; pd.W = W;
-    pd.w_tmem = e->dec.wih_tmem; pd.scale_row = e->dec.scale_row; pd.bias_row = e->dec.bias_row; pd.gi = ws.gi;
-    // fused encoder + projection launch when the recurrence leaves at least half of the SMs free
-    const int rec_ctas = (int)grid_rec.x;
-    const int fused_workers = (e->sm_count - 2 * rec_ctas) / 6;
-    // Opt-in (HB_FUSED=1): correct and tested; measured slower than separate launches (4.45 vs 4.17 ms per batch at
-    // B=256): the projection CTAs that share the launch get fewer SMs and compete with the recurrence for L2.
-    const bool fuse_allowed = e->tune.fused;
-    const bool fused = fuse_allowed && nrec <= 16 && fused_workers >= 8 && (W + 7) / 8 <= 4096 && !e->time_recurrence;
-    // persistent window kernel: every role of the whole chunk loop resident at once
-    const int n_chunks = T < W ? 0 : (T - W) / J + 1;
-    const int heads_workers = 8;
-    const int persistent_workers = (e->sm_count - 4 * rec_ctas - heads_workers) / 6;
-    const int tiles8 = (W + 7) / 8, tiles16 = (W + 15) / 16;
-    const size_t flags_needed = (size_t)8 * rec_ctas + (size_t)2 * rec_ctas + (size_t)2 * rec_ctas * tiles8 * 2;
-    // Opt-in (HB_PERSISTENT=1): correct and tested, but measured SLOWER than the per-chunk launches at B=256
-    // (5.0-5.3 ms vs 4.8 ms per batch): with half of the SMs pinned to the recurrence roles the projection
-    // role, which is L2-bound (each activation tile is fetched by 6 gate-block CTAs), cannot hide behind the encoder.
-    const bool persistent_allowed = e->tune.persistent;
-    const bool persistent = persistent_allowed && nrec == 16 && n_chunks > 0 && persistent_workers >= 8 && tiles8 <= 4096 &&
-                            flags_needed <= 16384 && !e->time_recurrence;
-    if ((fused || persistent) && e->tile_order_w != W) {
-        // a column tile is complete once the forward pass is past its last column and the reverse pass past its first
-        auto make_order = [&](int width, std::vector<int>& order, int* dev) {
-            const int n = (W + width - 1) / width;
-            order.resize(n);                                       // member vector: outlives the async copy
-            for (int i = 0; i < n; ++i) order[i] = i;
-            auto ready = [&](int tt) { return std::max(std::min(width * tt + width, W), W - width * tt); };
-            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ready(x) < ready(y); });
-            cudaMemcpyAsync(dev, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
-        };
-        make_order(8, e->tile_order_host, e->tile_order);
-        make_order(16, e->tile_order16_host, e->tile_order16);
-        if (persistent) {
-            // The decoder consumes tiles edges-first, the encoder finishes them edges-last.  Whatever the
-            // projection CTAs cannot finish while the encoder is still running is therefore taken in the
-            // decoder's order: the last ~30 % of the availability order is re-sorted edges-first.
-            std::vector<int>& o = e->tile_order_host;
-            const int n = (int)o.size(), tail = std::max(2, (n * 3 + 9) / 10);
-            auto edge_dist = [&](int tt) { return std::min(tt, n - 1 - tt); };
-            std::stable_sort(o.end() - std::min(tail, n), o.end(), [&](int x, int y) { return edge_dist(x) < edge_dist(y); });
-            cudaMemcpyAsync(e->tile_order, o.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
-        }
-        e->tile_order_w = W;
-    }
     auto rec_args = [&](const TensorLayer& L, const float* gi, int gi_cols, int gi_col0, const float* h_in, float* h_out, uint8_t* yimg) {
         RecArgs ra{};
-        ra.gi = gi; ra.whh_tmem = L.whh_tmem; ra.gate_consts = L.gate_consts; ra.h_in = h_in; ra.h_out = h_out; ra.yimg = yimg;
-        ra.B = B; ra.W = W; ra.gi_cols = gi_cols; ra.gi_col0 = gi_col0; ra.progress = nullptr; ra.epoch = 0;
-        ra.n_wg = (int)n_wg; ra.dbg_role = (&L == &e->enc) ? 0 : 1;
-        static const bool dbg_enc = getenv("HB_DEBUG_TIMELINE") != nullptr && getenv("HB_DEBUG_TIMELINE")[0] == 'e';
+        ra.layer[0] = layer_args(L, gi, gi_cols, gi_col0, 0, yimg, yimg);
+        ra.n_layers = 1; ra.n_chunks = 1; ra.h_in = h_in; ra.h_out = h_out; ra.B = B; ra.W = W;
+        ra.tiles_t = tiles8; ra.n_wg = (int)n_wg; ra.epoch = 0; ra.dbg_layer = 0;
         ra.dbg = (nrec <= 16 && (dbg_enc == (&L == &e->enc))) ? dbg_buf : nullptr;
         return ra;
     };
     auto recurrence = [&](const RecArgs& ra, bool use_pdl) {
-        size_t slot = 0;
-        if (e->time_recurrence) {
-            if (e->rec_events_used == e->rec_events.size()) {
-                cudaEvent_t a, b;
-                cudaEventCreate(&a);
-                cudaEventCreate(&b);
-                e->rec_events.emplace_back(a, b);
-            }
-            slot = e->rec_events_used++;
-            cudaEventRecord(e->rec_events[slot].first, s);
-            use_pdl = false;
-        }
+        const size_t slot = dominant_begin();
+        if (e->time_recurrence) use_pdl = false;
         const bool stack = e->tune.stack;
         if (nrec == 8)
             detail::launch(stack ? tc_recurrence_kernel<16, 8, true> : tc_recurrence_kernel<16, 8, false>, grid_rec, dim3(REC_TC_THREADS),
@@ -1325,61 +1390,24 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                            detail::recurrence_smem<16>(), s, use_pdl, ra);
         else
             detail::launch(tc_recurrence_kernel<32, 32, false>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl, ra);
-        if (e->time_recurrence) cudaEventRecord(e->rec_events[slot].second, s);
+        dominant_end(slot);
     };
-    HeadsArgs heads_base{};
-    heads_base.n_wg = n_wg; heads_base.B = B; heads_base.W = W; heads_base.T = T; heads_base.col_step = J;
-    heads_base.w_img = e->head_img; heads_base.b_head = e->b_head; heads_base.inv_scale = e->head_inv;
-    heads_base.p_base = p_base; heads_base.p_rle = p_rle;
-    if (persistent) {
-        unsigned long long* f = e->flags;
-        unsigned long long* enc_prog = f;                 f += 2 * rec_ctas;
-        unsigned long long* dec_prog = f;                 f += 2 * rec_ctas;
-        unsigned long long* enc_done = f;                 f += 2 * rec_ctas;
-        unsigned long long* dec_done = f;                 f += 2 * rec_ctas;
-        unsigned long long* heads_done = f;               f += 2 * rec_ctas;           // one per window group
-        unsigned long long* tile_flags = f;
-        RecArgs renc = rec_args(e->enc, ws.gi_enc, enc_cols, 0, nullptr, ws.hid_a, ws.yimg1);
-        renc.n_chunks = n_chunks; renc.gi_col_step = J; renc.h_in_next = ws.hid_b;
-        renc.progress = enc_prog; renc.wait_done = dec_done; renc.wait_done_bias = 0; renc.publish_done = enc_done;
-        RecArgs rdec = rec_args(e->dec, ws.gi, W, 0, ws.hid_a, ws.hid_b, ws.yimg2[0]);
-        rdec.n_chunks = n_chunks; rdec.gi_col_step = 0; rdec.h_in_next = ws.hid_a; rdec.yimg_odd = ws.yimg2[1];
-        rdec.progress = dec_prog; rdec.wait_done = enc_done; rdec.wait_done_bias = 1; rdec.publish_done = dec_done;
-        rdec.tile_flags = tile_flags; rdec.tiles_t = tiles8; rdec.heads_done = heads_done; rdec.heads_per_chunk = 4 * tiles16;
-        renc.dbg = rdec.dbg = dbg_buf;
-        ProjArgs pp = pd;
-        pp.progress = enc_prog; pp.epoch = 0; pp.tile_order = e->tile_order; pp.rec_n = nrec; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
-        HeadsArgs hp = heads_base;
-        hp.yimg = ws.yimg2[0]; hp.yimg_odd = ws.yimg2[1]; hp.col0 = 0; hp.n_chunks = n_chunks;
-        hp.progress = dec_prog; hp.rec_n = nrec; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
-        detail::launch(tc_window_kernel<16>, dim3(4 * rec_ctas + 6 * persistent_workers + heads_workers), dim3(REC_TC_THREADS),
-                       std::max({detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()}), s, pdl,
-                       renc, rdec, pp, hp, rec_ctas, persistent_workers, heads_workers);
-        launches += 1;
-    }
+    e->last_plan = hb_launch_plan{};
+    e->last_plan.chunkloop = chunkloop ? 1 : 0;
+    e->last_plan.windows_per_cta = chunkloop ? plan.tile : nrec;
+    e->last_plan.stacked_operand = (e->tune.stack && e->last_plan.windows_per_cta <= 16) ? 1 : 0;
+    e->last_plan.recurrence_ctas = chunkloop ? plan.rec_ctas : (int)grid_rec.x;
+    e->last_plan.projection_workers = chunkloop ? plan.proj_workers : tiles_proj;
+    e->last_plan.heads_workers = chunkloop ? plan.heads_workers : tiles_heads;
     int chunk = 0;
-    for (int i = 0; !persistent && i + W <= T; i += J, ++chunk) {
+    for (int i = 0; !chunkloop && i + W <= T; i += J, ++chunk) {
         float* enc_h = hid_bufs[flip];
         float* dec_h = hid_bufs[flip ^ 1];
         const int buf = chunk & 1;
         if (chunk >= 2) cudaStreamWaitEvent(s, e->ev_heads[buf], 0);      // heads(chunk - 2) has read this yimg2 buffer
-        RecArgs renc = rec_args(e->enc, ws.gi_enc, enc_cols, i, hid, enc_h, ws.yimg1);
-        if (fused) {
-            renc.progress = e->progress;
-            renc.epoch = (++e->launch_epoch) << 20;
-            ProjArgs pf = pd;
-            pf.progress = e->progress; pf.epoch = renc.epoch; pf.tile_order = e->tile_order; pf.rec_n = nrec;
-            detail::launch(nrec == 8 ? tc_encoder_fused_kernel<16, 8> : tc_encoder_fused_kernel<16, 16>,
-                           dim3(2 * rec_ctas + 6 * fused_workers), dim3(REC_TC_THREADS),
-                           std::max(detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2)), s, pdl && chunk == 0,
-                           renc, pf, rec_ctas, fused_workers);
-        } else {
-            recurrence(renc, pdl && chunk == 0);
-            ProjArgs pq = pd;
-            pq.pair = pair_mode;
-            detail::launch_cluster(tc_projection_kernel<true>, dim3(tiles_proj, 6), dim3(PROJ_THREADS), detail::projection_smem(YROW, 2), s, pdl,
-                                   dim3(1, pair_mode ? 2 : 1, 1), pq);
-        }
+        recurrence(rec_args(e->enc, ws.gi_enc, enc_cols, i, hid, enc_h, ws.yimg1), pdl && chunk == 0);
+        detail::launch_cluster(tc_projection_kernel<true>, dim3(tiles_proj, 6), dim3(PROJ_THREADS), detail::projection_smem(YROW, 2), s, pdl,
+                               dim3(1, pair_mode ? 2 : 1, 1), pd);
         recurrence(rec_args(e->dec, ws.gi, W, 0, enc_h, dec_h, ws.yimg2[buf]), pdl);
         cudaEventRecord(e->ev_dec[buf], s);
         cudaStreamWaitEvent(e->side, e->ev_dec[buf], 0);
@@ -1387,7 +1415,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         ha.yimg = ws.yimg2[buf]; ha.col0 = i;
         tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), e->side>>>(ha);
         cudaEventRecord(e->ev_heads[buf], e->side);
-        launches += fused ? 3 : 4;
+        launches += 4;
         hid = dec_h;
         flip ^= 1;
     }
@@ -1401,13 +1429,17 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         if (printed++ == 2) {
             std::vector<long long> hbuf(8192);
             cudaMemcpy(hbuf.data(), dbg_buf, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-            if (persistent) {
+            if (chunkloop) {
                 const long long t0 = hbuf[4096];
-                fprintf(stderr, "[persistent kernel, CTA 0 fwd, us since encoder chunk 0 start]\n");
+                fprintf(stderr, "[chunk-loop kernel: tile %d, %d recurrence CTAs x 2, %d projection workers x 6, %d heads workers]\n",
+                        plan.tile, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
+                fprintf(stderr, "[CTA 0 fwd, us since encoder phase 0 start]\n");
                 for (int k = 0; k < std::min(n_chunks, 6); ++k)
                     fprintf(stderr, "  chunk %d: enc %.1f -> %.1f   dec %.1f -> %.1f\n", k,
                             (hbuf[4096 + k * 2] - t0) * 1e-3, (hbuf[4096 + k * 2 + 1] - t0) * 1e-3,
                             (hbuf[4096 + (64 + k) * 2] - t0) * 1e-3, (hbuf[4096 + (64 + k) * 2 + 1] - t0) * 1e-3);
+                if (n_chunks > 0)
+                    fprintf(stderr, "  last chunk: dec end %.1f\n", (hbuf[4096 + (64 + n_chunks - 1) * 2 + 1] - t0) * 1e-3);
             }
             auto at = [&](int role, int st, int k) { return hbuf[((size_t)role * 128 + st) * 8 + k]; };
             double acc[16] = {0};
@@ -1420,8 +1452,6 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 acc[15] += at(0, st + 1, 0) - base;               // full step
             }
             fprintf(stderr, "[timeline, cycles after MMA warp release] issue_done=%.0f step=%.0f\n", acc[0] / n, acc[15] / n);
-            fprintf(stderr, "  fused launch: last projection CTA finished %.1f us after the last recurrence CTA\n",
-                    (double)(hbuf[4 * 128 * 8 - 1] - hbuf[4 * 128 * 8 - 2]) * 1e-3);
             for (int role = 1; role <= 2; ++role) {
                 fprintf(stderr, "  gate warp %s:", role == 1 ? "0 " : "15");
                 const char* names[7] = {"gi_full", "acc_r", "acc_z", "acc_n", "ldtm_n", "math_done", "arrived"};

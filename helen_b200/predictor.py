@@ -94,8 +94,14 @@ class WindowPredictor(object):
         return int(self._lib.hb_launch_count(self._handle))
 
     def enable_kernel_timing(self, enable=True):
-        """True/1: bracket the whole launch sequence of each predict call; 2: also each recurrence launch."""
+        """True/1: bracket the whole launch sequence of each predict call; 2: also each launch of the dominant kernel."""
         _native.check(self._lib.hb_enable_kernel_timing(self._handle, int(enable)))
+
+    def last_launch_plan(self):
+        """How the last predict call was laid out on the chip (hb_last_launch_plan)."""
+        plan = _native.hb_launch_plan()
+        _native.check(self._lib.hb_last_launch_plan(self._handle, ctypes.byref(plan)))
+        return {name: int(getattr(plan, name)) for name, _ in plan._fields_}
 
     def dominant_kernel_time_ms(self, reset=True):
         total, n = ctypes.c_double(), ctypes.c_int64()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 
 typedef enum hb_status {
     HB_OK = 0,
@@ -134,8 +134,24 @@ int64_t hb_launch_count(const hb_handle *handle);
 int hb_enable_kernel_timing(hb_handle *handle, int enable);
 int hb_kernel_time_ms(hb_handle *handle, double *total_ms, int64_t *launches, int reset);
 
-/* With hb_enable_kernel_timing(handle, 2) every launch of the dominant kernel (the GRU recurrence,
- * one launch = B windows x W dependent steps x 2 directions of one layer) is bracketed on its own;
+/* How the last hb_predict_windows call of the tensor engine was laid out on the chip (reporting only).
+ * chunkloop = 1: the whole chunk loop of the batch ran as ONE launch of tc_chunkloop_kernel with
+ * 2 * recurrence_ctas recurrence CTAs, 6 * projection_workers projection CTAs and heads_workers heads
+ * CTAs, all resident at once; chunkloop = 0: four launches per chunk (the batch does not fit on the chip). */
+typedef struct hb_launch_plan {
+    int chunkloop;
+    int windows_per_cta;     /* live windows per recurrence CTA: 8, 16 or 32 */
+    int stacked_operand;     /* 1: [h_hi | h_lo] stacked B operand (48 MMAs per step), 0: 3-term (72) */
+    int recurrence_ctas;     /* per direction */
+    int projection_workers;
+    int heads_workers;
+} hb_launch_plan;
+int hb_last_launch_plan(const hb_handle *handle, hb_launch_plan *out);
+
+/* With hb_enable_kernel_timing(handle, 2) every launch of the dominant kernel is bracketed on its own:
+ * tc_chunkloop_kernel (one launch = the whole chunk loop of the batch) when hb_last_launch_plan reports
+ * chunkloop = 1, else the per-chunk GRU recurrence kernel (one launch = B windows x W dependent steps x
+ * 2 directions of one layer);
  * returns the accumulated milliseconds and the launch count since the last reset (synchronises).
  * This mode disables launch overlap between kernels, so it is for measurement passes only. */
 int hb_dominant_kernel_time_ms(hb_handle *handle, double *total_ms, int64_t *launches, int reset);

@@ -35,8 +35,12 @@ VARIANTS = {
     "tile16_3term": {"HB_WINDOWS_PER_CTA": "16", "HB_NO_STACK": "1"},
     "tile32": {"HB_WINDOWS_PER_CTA": "32"},
     "no_pair_no_pdl": {"HB_NO_PAIR": "1", "HB_NO_PDL": "1"},
-    "fused_encoder_projection": {"HB_FUSED": "1"},
-    "persistent_window_kernel": {"HB_PERSISTENT": "1"},
+    "per_chunk_launches": {"HB_NO_CHUNKLOOP": "1"},
+    "per_chunk_tile8_3term": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "8", "HB_NO_STACK": "1"},
+    "per_chunk_tile16": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "16"},
+    "per_chunk_tile32": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "32"},
+    "chunkloop_no_pair": {"HB_NO_PAIR": "1"},
+    "chunkloop_few_heads_workers": {"HB_HEADS_WORKERS": "2"},
 }
 
 
@@ -45,7 +49,7 @@ def test_kernel_variants_match_fp32_engine(variant, monkeypatch):
     """Every recurrence tile / launch-structure variant of the tensor engine (the switches are read from the
     environment when the handle is created) against the fp32 engine, same tolerance as above."""
     from helen_b200.predictor import WindowPredictor
-    for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_FUSED", "HB_PERSISTENT", "HB_NO_LIVE8"):
+    for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8"):
         monkeypatch.delenv(k, raising=False)
     batch, seq, features = 45, 250, 10
     sd = random_state_dict(features, seed=5)
