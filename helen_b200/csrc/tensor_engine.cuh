@@ -51,6 +51,19 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+// Weight images in global memory are stored in the order the TMEM upload reads them: one warp instruction (32 lanes x
+// 16 bytes, lane = TMEM lane = matrix row within a 32-row quarter) fetches 512 contiguous bytes.  (Row-major rows made
+// every such instruction touch 32 different lines and the upload - once per launch, or per phase of the chunk-loop
+// kernel - took ~10 us.)
+//   W_ih block image: [gate block 6][hi, lo][quarter 4][16-word unit][v 4][lane 32][4 words]
+//   W_hh image      : [dir 2][hi, lo][gate block 3][quarter 4][half 2][v 8][lane 32][4 words]
+__host__ __device__ constexpr size_t wih_word_index(int blk, int term, int row, int c, int kwords) {
+    return ((((((size_t)blk * 2 + term) * 4 + (row >> 5)) * (kwords >> 4) + (c >> 4)) * 4 + ((c >> 2) & 3)) * 32 + (row & 31)) * 4 + (c & 3);
+}
+__host__ __device__ constexpr size_t whh_word_index(int dir, int term, int gb, int row, int c) {
+    return (((((((size_t)dir * 2 + term) * 3 + gb) * 4 + (row >> 5)) * 2 + (c >> 5)) * 8 + ((c >> 2) & 7)) * 32 + (row & 31)) * 4 + (c & 3);
+}
+
 __host__ __device__ constexpr int64_t yimg_block(int64_t wg, int t, int W, int part) { return ((wg * W + t) * 2 + part) * (int64_t)YROW; }
 
 // ---------------------------------------------------------------------------------------------
@@ -94,26 +107,45 @@ constexpr int PROJ_W_COL0 = 128;
 struct ProjArgs {
     const uint8_t* in_base; int64_t in_wg_stride, in_t_stride, in_part_stride;   // operand image addressing (bytes)
     int blk_bytes, lbo, Kp; int64_t n_wg; int W;
-    const uint32_t* w_tmem;        // [6][hi, lo][128][Kp/2] packed fp16 pairs
+    const uint32_t* w_tmem;        // packed fp16 pairs, see wih_word_index
     const float* scale_row;        // [768]
     const float* bias_row;         // [768]
     float* gi;                     // [(b * W + t), 768]
-    // producer/consumer mode (fused with the encoder recurrence): column tiles are taken in the order
-    // the encoder finishes them and the loader waits on the recurrence CTAs' progress counters
-    const unsigned long long* progress; unsigned long long epoch; const int* tile_order; int rec_n;
-    // persistent mode: the role walks n_chunks chunks; a chunk's columns count from chunk * W in the progress
-    // counters, and every finished tile is announced to the decoder CTAs (4 epilogue warps -> +4 per tile and block)
-    int n_chunks; unsigned long long* tile_flags;
     // pair mode: the launch uses clusters of 2 CTAs along the gate-block axis; both CTAs of a pair walk the same
     // tiles, each fetches half of a tile and multicasts it to both, halving the L2 traffic of the activations
     int pair;
+    // ---- chunk-loop kernel (producer/consumer mode): the role walks n_chunks chunks and its K = 256 contraction is
+    // split by SOURCE direction.  A job is one half of a column tile: the K = 128 slice that multiplies the forward
+    // (or the reverse) encoder's outputs, runnable as soon as THAT direction has stored the tile's columns, so the
+    // projection keeps pace with the encoder instead of starting when both directions meet in the middle.  The
+    // first half of a tile writes scale * acc + bias, the second adds scale * acc to it (red.add); both halves of a tile
+    // belong to the same worker (same thread, program order), and which half is first is fixed by the job table,
+    // so the result does not depend on timing.
+    const int* jobs;               // per worker, in the order the encoder makes them runnable (see pack_proj_job)
+    const int* job_offsets;        // [workers + 1]
+    const unsigned long long* progress; unsigned long long epoch; int rec_n;   // encoder progress counters, [cta][dir]
+    int n_chunks;                  // a chunk's columns count from chunk * W in the progress counters
+    unsigned long long* tile_flags;   // [group][tile][decoder direction]: += 1 per epilogue warp and job (24 per chunk)
 };
 
-// tile index -> (window group, column tile); all roles use the same mapping
-__device__ __forceinline__ void proj_tile(const ProjArgs& a, int64_t tile, int64_t& wg, int& t0) {
-    const int pos = (int)(tile / a.n_wg);
-    wg = tile % a.n_wg;
-    t0 = (a.tile_order ? a.tile_order[pos] : pos) * 8;
+__host__ __device__ constexpr int pack_proj_job(int wg, int tile, int src_dir, int second) { return wg | (tile << 16) | (src_dir << 28) | (second << 29); }
+
+struct ProjJob { int64_t wg; int t0, valid, src_dir; bool split, second; };
+
+// idx-th job of a worker; all roles of a CTA walk the same sequence
+__device__ __forceinline__ bool proj_job(const ProjArgs& a, int worker, int n_workers, int64_t idx, ProjJob& j) {
+    if (a.jobs != nullptr) {
+        const int begin = __ldg(a.job_offsets + worker), end = __ldg(a.job_offsets + worker + 1);
+        if (idx >= end - begin) return false;
+        const int e = __ldg(a.jobs + begin + idx);
+        j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.src_dir = (e >> 28) & 1; j.second = (e >> 29) & 1; j.split = true;
+    } else {
+        const int64_t tile = worker + idx * n_workers;
+        if (tile >= a.n_wg * ((a.W + 7) >> 3)) return false;
+        j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.src_dir = 0; j.second = false; j.split = false;
+    }
+    j.valid = min(8, a.W - j.t0);
+    return true;
 }
 
 template <bool kSplitA>
@@ -121,15 +153,16 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 {
     const uint8_t* __restrict__ in_base = a.in_base;
     const int64_t in_wg_stride = a.in_wg_stride, in_t_stride = a.in_t_stride, in_part_stride = a.in_part_stride;
-    const int blk_bytes = a.blk_bytes, lbo = a.lbo, Kp = a.Kp, W = a.W;
-    const int64_t n_wg = a.n_wg;
+    const int lbo = a.lbo, Kp = a.Kp, W = a.W;
+    const bool split = a.jobs != nullptr;
+    const int blk_bytes = split ? YBLK : a.blk_bytes;       // bytes of one (window group, column) block in a stage
     const uint32_t* __restrict__ w_tmem = a.w_tmem;
     const float* __restrict__ scale_row = a.scale_row;
     const float* __restrict__ bias_row = a.bias_row;
     float* __restrict__ gi = a.gi;
     constexpr int PARTS = kSplitA ? 2 : 1;
     const uint32_t part_bytes = 8u * blk_bytes;              // 8 row groups (columns t0..t0+7)
-    const uint32_t stage_bytes = PARTS * part_bytes;
+    const uint32_t stage_bytes = PARTS * 8u * a.blk_bytes;   // allocation (full K)
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + PROJ_STAGES * stage_bytes);
     uint64_t* a_empty = a_full + PROJ_STAGES;
     uint64_t* acc_full = a_empty + PROJ_STAGES;
@@ -153,22 +186,21 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     if (warp < 4) {   // weight block -> TMEM, thread = gate row; 32 words in flight per round trip
         const int row = warp * 32 + lane;
         for (int term = 0; term < 2; ++term) {
-            const uint32_t* src = w_tmem + (((size_t)blk * 2 + term) * 128 + row) * kwords;
             const uint32_t dst = tmem + ((uint32_t)(warp * 32) << 16) + PROJ_W_COL0 + term * kwords;
             int c = 0;
             for (; c + 32 <= kwords; c += 32) {
                 uint32_t r[32];
-                const uint4* p = reinterpret_cast<const uint4*>(src + c);
+                const uint4* p = reinterpret_cast<const uint4*>(w_tmem + wih_word_index(blk, term, row, c, kwords));
 #pragma unroll
-                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
                 tc::tmem_st16(dst + c, r);
                 tc::tmem_st16(dst + c + 16, r + 16);
             }
             for (; c < kwords; c += 16) {
                 uint32_t r[16];
-                const uint4* p = reinterpret_cast<const uint4*>(src + c);
+                const uint4* p = reinterpret_cast<const uint4*>(w_tmem + wih_word_index(blk, term, row, c, kwords));
 #pragma unroll
-                for (int v = 0; v < 4; ++v) { const uint4 x = __ldg(p + v); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                for (int v = 0; v < 4; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
                 tc::tmem_st16(dst + c, r);
             }
         }
@@ -181,36 +213,32 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     const uint32_t pair_rank = a.pair ? tc::cluster_ctarank() : 0u;
     if (a.pair) tc::cluster_sync_all();                      // the peer's mbarriers exist before anything is multicast at them
 
-    const int tiles_t = (W + 7) >> 3;
-    const int64_t n_tiles = n_wg * tiles_t;
     const int n_chunks = a.n_chunks > 0 ? a.n_chunks : 1;
+    ProjJob j;
     if (warp == 5) {
         // ===================== loader =====================
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
-        for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
+        for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
             const int stage = it % PROJ_STAGES;
             if (it >= PROJ_STAGES) tc::mbar_wait(a_empty + stage, (uint32_t)((it / PROJ_STAGES - 1) & 1));
-            int64_t wg; int t0;
-            proj_tile(a, tile, wg, t0);
-            const int valid = min(8, W - t0);
             if (a.progress != nullptr) {
-                // the forward encoder must have passed column t0+valid-1, the reverse one column t0
-                if (lane < 2) {
-                    const unsigned long long need = a.epoch + (unsigned long long)chunk * W + (unsigned long long)(lane == 0 ? t0 + valid : W - t0);
-                    const unsigned long long* flag = a.progress + ((wg * WG) / a.rec_n) * 2 + lane;
-                    while (tc::ld_acquire_gpu(flag) < need) __nanosleep(200);
+                // the source encoder direction must have stored the job's columns: forward past t0+valid-1, reverse past t0
+                if (lane == 0) {
+                    const unsigned long long need = a.epoch + (unsigned long long)chunk * W + (unsigned long long)(j.src_dir == 0 ? j.t0 + j.valid : W - j.t0);
+                    const unsigned long long* flag = a.progress + ((j.wg * WG) / a.rec_n) * 2 + j.src_dir;
+                    while (tc::ld_acquire_gpu(flag) < need) __nanosleep(100);
                 }
                 tc::fence_proxy_async_all();
                 __syncwarp();
             }
-            if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(valid * PARTS * blk_bytes));
+            if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * PARTS * blk_bytes));
             __syncwarp();
             if (lane < 8 * PARTS) {
                 const int tl = lane & 7, part = lane >> 3;
                 uint8_t* dst = smem + stage * stage_bytes + part * part_bytes + tl * blk_bytes;
-                const uint8_t* src = in_base + wg * in_wg_stride + (int64_t)(t0 + tl) * in_t_stride + part * in_part_stride;
-                if (tl < valid) {
+                const uint8_t* src = in_base + j.wg * in_wg_stride + (int64_t)(j.t0 + tl) * in_t_stride + part * in_part_stride + (split ? j.src_dir * YBLK : 0);
+                if (tl < j.valid) {
                     if (!a.pair) tc::bulk_g2s(dst, src, (uint32_t)blk_bytes, a_full + stage);
                     else if ((uint32_t)(tl & 1) == pair_rank) tc::bulk_g2s_multicast(dst, src, (uint32_t)blk_bytes, a_full + stage, (uint16_t)3);
                 }
@@ -219,10 +247,10 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
-        const int ksteps = Kp >> 4;
+        const int ksteps = split ? 8 : (Kp >> 4);
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
-        for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
+        for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
             const int stage = it % PROJ_STAGES, acc = it & 1;
             tc::mbar_wait(a_full + stage, (uint32_t)((it / PROJ_STAGES) & 1));
             if (it >= 2) tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1));
@@ -231,7 +259,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 const uint32_t sbase = tc::smem_u32(smem + stage * stage_bytes);
                 const uint64_t d_hi = tc::smem_desc(sbase, lbo, blk_bytes);
                 const uint64_t d_lo = tc::smem_desc(sbase + part_bytes, lbo, blk_bytes);
-                const uint32_t a_hi = tmem + PROJ_W_COL0, a_lo = a_hi + kwords;
+                const uint32_t a_hi = tmem + PROJ_W_COL0 + (split ? j.src_dir * 64 : 0), a_lo = a_hi + kwords;
                 const uint32_t d = tmem + acc * PROJ_NT;
                 uint32_t accum = 0;
                 for (int ks = 0; ks < ksteps; ++ks) { tc::mma_f16_ts(d, a_hi + ks * 8, d_hi + (uint64_t)(ks * 2 * lbo / 16), idesc, accum); accum = 1; }
@@ -248,12 +276,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         // ===================== epilogue =====================
         const int row = blk * 128 + warp * 32 + lane;
         const float sc = scale_row[row], bi = bias_row[row];
+        const int tiles_t = (W + 7) >> 3;
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
-        for (int64_t tile = worker; tile < n_tiles; tile += n_workers, ++it) {
+        for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
             const int acc = it & 1;
-            int64_t wg; int t0;
-            proj_tile(a, tile, wg, t0);
             tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1));
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
@@ -262,20 +289,27 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 float v[8];
                 tc::tmem_ld8(taddr + c8, v);
                 tc::tmem_ld_wait();
-                const int t = t0 + (c8 >> 3);
+                const int t = j.t0 + (c8 >> 3);
                 if (t < W) {
-                    float* out = gi + ((wg * WG) * W + t) * (int64_t)(2 * G) + row;
+                    float* out = gi + ((j.wg * WG) * W + t) * (int64_t)(2 * G) + row;
+                    if (j.second) {
+                        // add to what this thread stored for the tile's first half (same thread, same address: ordered).
+                        // Fire-and-forget reduction at L2: reading the old value back would stall on a global round trip.
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) out[(int64_t)i * W * (2 * G)] = fmaf(v[i], sc, bi);
+                        for (int i = 0; i < 8; ++i) atomicAdd(out + (int64_t)i * W * (2 * G), v[i] * sc);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) out[(int64_t)i * W * (2 * G)] = fmaf(v[i], sc, bi);
+                    }
                 }
             }
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty + acc);
-            if (a.tile_flags != nullptr) {                   // gi' rows of this tile are in global memory
+            if (a.tile_flags != nullptr) {                   // gi' rows of this job are in global memory
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) tc::red_release_gpu_add(a.tile_flags + ((wg * tiles_t + (t0 >> 3)) * 2 + blk / 3), 1ull);
+                if (lane == 0) tc::red_release_gpu_add(a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3), 1ull);
             }
         }
     }
@@ -314,18 +348,21 @@ constexpr int REC_TC_THREADS = (REC_GATE_WARPS + 3) * 32;
 constexpr int REC_W_COL0 = 128;                   // weight columns start here (accumulators below)
 constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate block][row][k pair]
 template <int N> __host__ __device__ constexpr int gi_stages() { return N <= 16 ? 4 : 3; }   // N = 32: 3 x 48 KB (227 KB smem limit)
+// h operand image buffers: 4 give the y store three steps to drain, which hides the global-memory round trips of the
+// progress publication (chunk-loop kernel); N = 32 has room for 2 only
+template <int N> __host__ __device__ constexpr int h_buffers() { return N <= 16 ? 4 : 2; }
 constexpr int PUBLISH_LAG = 4;
 
 // One GRU layer as the recurrence role sees it.
 struct RecLayer {
     const float* gi;               // gi' rows; row of (window b, chunk k, step column t) = b * gi_cols + gi_col0 + k * gi_col_step + t
     int gi_cols, gi_col0, gi_col_step;
-    const uint32_t* whh_tmem;      // [2 dirs][hi, lo][3][128][64] packed fp16 pairs
+    const uint32_t* whh_tmem;      // packed fp16 pairs, see whh_word_index
     const float* gate_consts;      // [2 dirs][4][128]: inv_r', inv_z', inv_n', b_hn'  (per unit)
     uint8_t* yimg[2];              // operand image of the layer output: [0] even chunks, [1] odd chunks
     unsigned long long* progress;  // [ctas][2 dirs] columns whose output has landed in yimg (+ epoch + chunk * W), or nullptr
     // chunk-loop kernel only (counters in global memory, see tc_chunkloop_kernel):
-    const unsigned long long* tile_flags;      // decoder: gi' tile (group, tile, dir) of chunk k is ready at >= 12 (k + 1)
+    const unsigned long long* tile_flags;      // decoder: gi' tile (group, tile, dir) of chunk k is ready at >= 24 (k + 1)
     const unsigned long long* heads_done; int heads_per_chunk;   // decoder: yimg[k & 1] reusable when >= heads_per_chunk (k - 1)
     const unsigned long long* consumed_flags;  // encoder: tile flags (both directions) that tell yimg of chunk k - 1 has been read
 };
@@ -362,7 +399,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     const int n_layers = ra.n_layers;
     const int n_phases = (ra.n_chunks > 0 ? ra.n_chunks : 1) * n_layers;
     long long* __restrict__ dbg = ra.dbg;
-#define HB_DBG(role, s, k) do { if (dbg_on && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
+#define HB_DBG(role, s, k) do { if (dbg_steps && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N accumulator columns per gate block (3N must stay below REC_W_COL0)");
     static_assert(NLIVE == N || (N == 16 && NLIVE == 8), "live windows per CTA");
     static_assert(!STACK || N == 16, "stacked operand: 3 x 2 NLIVE accumulator columns must stay below REC_W_COL0");
@@ -372,16 +409,17 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     constexpr uint32_t HB_BYTES = (N / WG) * YBLK;           // one h operand image (hi or lo), all N columns
     constexpr uint32_t GI_STAGE_BYTES = NLIVE * GI_ROW_BYTES;
     constexpr int GI_STAGES = gi_stages<N>();
-    // h operand images, double buffered: step s reads buffer s&1 (h_s) and writes buffer (s+1)&1 (h_{s+1}),
-    // so the y store of an image has two steps to drain before the buffer is written again
-    uint8_t* h_img = smem;                                   // [2 buffers][hi, lo][HB_BYTES]
-    uint8_t* gi_s = smem + 4 * HB_BYTES;
+    // h operand images, NBUF buffers: step s reads buffer s % NBUF (h_s) and writes buffer (s+1) % NBUF (h_{s+1}),
+    // so the y store of an image has NBUF steps to drain before the buffer is written again
+    constexpr int NBUF = h_buffers<N>();
+    uint8_t* h_img = smem;                                   // [NBUF buffers][hi, lo][HB_BYTES]
+    uint8_t* gi_s = smem + 2 * NBUF * HB_BYTES;
     uint64_t* acc_ready = reinterpret_cast<uint64_t*>(gi_s + GI_STAGES * GI_STAGE_BYTES);   // [3]: r, z, n blocks
     uint64_t* h_ready = acc_ready + 3;
-    uint64_t* h_free = h_ready + 1;                          // [2], one per buffer: its y store has drained
-    uint64_t* y_ready = h_free + 2;                          // [2], one per buffer: image complete (for the store warp;
+    uint64_t* h_free = h_ready + 1;                          // [NBUF], one per buffer: its y store has drained
+    uint64_t* y_ready = h_free + NBUF;                       // [NBUF], one per buffer: image complete (for the store warp;
                                                              // per-buffer so a lagging store warp cannot alias phases)
-    uint64_t* gi_full = y_ready + 2;
+    uint64_t* gi_full = y_ready + NBUF;
     uint64_t* gi_empty = gi_full + GI_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gi_empty + GI_STAGES);
 
@@ -391,14 +429,13 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 
     tc::pdl_launch_dependents();
     if constexpr (NLIVE < N) {                               // dead accumulator columns: keep their operand rows finite
-        for (uint32_t i = tid; i < 4 * HB_BYTES / 16; i += REC_TC_THREADS) reinterpret_cast<int4*>(h_img)[i] = make_int4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < 2 * NBUF * HB_BYTES / 16; i += REC_TC_THREADS) reinterpret_cast<int4*>(h_img)[i] = make_int4(0, 0, 0, 0);
         tc::fence_proxy_async_smem();
     }
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) tc::mbar_init(acc_ready + i, 1);
         tc::mbar_init(h_ready, REC_GATE_WARPS);
-        tc::mbar_init(h_free + 0, 1); tc::mbar_init(h_free + 1, 1);
-        tc::mbar_init(y_ready + 0, REC_GATE_WARPS); tc::mbar_init(y_ready + 1, REC_GATE_WARPS);
+        for (int i = 0; i < NBUF; ++i) { tc::mbar_init(h_free + i, 1); tc::mbar_init(y_ready + i, REC_GATE_WARPS); }
         for (int i = 0; i < GI_STAGES; ++i) { tc::mbar_init(gi_full + i, 1); tc::mbar_init(gi_empty + i, REC_GATE_WARPS); }
         tc::mbar_fence_init();
     }
@@ -425,13 +462,14 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     const int gi_col0 = L.gi_col0 + chunk * L.gi_col_step;
     uint8_t* __restrict__ yimg = L.yimg[chunk & 1];
     const unsigned long long prog_base = ra.epoch + (unsigned long long)chunk * W;
-    const bool dbg_on = dbg != nullptr && cta_x == 0 && dir == 0 && li == ra.dbg_layer && (n_layers == 1 || chunk == 2);
+    const bool dbg_on = dbg != nullptr && cta_x == 0 && dir == 0 && (n_layers == 1 ? li == ra.dbg_layer : chunk == 2);
+    const bool dbg_steps = dbg_on && li == ra.dbg_layer;
     if (phase > 0) {
         // phase boundary: fresh barriers, then the cross-CTA conditions of this phase
         if (tid == 0) {
             for (int i = 0; i < 3; ++i) { tc::mbar_inval(acc_ready + i); tc::mbar_init(acc_ready + i, 1); }
             tc::mbar_inval(h_ready); tc::mbar_init(h_ready, REC_GATE_WARPS);
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < NBUF; ++i) {
                 tc::mbar_inval(h_free + i); tc::mbar_init(h_free + i, 1);
                 tc::mbar_inval(y_ready + i); tc::mbar_init(y_ready + i, REC_GATE_WARPS);
             }
@@ -449,23 +487,32 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (L.consumed_flags != nullptr && chunk >= 1)   // every projection CTA has read this layer's previous image
                 for (int f = lane; f < NG * ra.tiles_t * 2; f += 32)
                     if (cta_x * NG + f / (ra.tiles_t * 2) < ra.n_wg)
-                        tc::spin_until_ge(L.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, 12ull * chunk);
+                        tc::spin_until_ge(L.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, 24ull * chunk);
         }
         __syncthreads();
     }
     if (dbg && n_layers > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (li * 64 + chunk) * 2] = (long long)globaltimer_ns();
+    // (a clock read right after bar.sync records the ARRIVAL at the barrier - the block is deferred to the next access
+    // of barrier-protected state - so the stamps read a shared word first)
+#define HB_STAMP(k) do { if (dbg_on && n_layers > 1 && lane == 0) { \
+        uint32_t probe; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(probe) : "r"(tc::smem_u32(tmem_slot)) : "memory"); \
+        dbg[6144 + li * 8 + (k)] = clock64() + (probe & 0); } } while (0)
+    if (warp == 0) HB_STAMP(0);                              // phase start (barriers fresh, cross-CTA conditions met)
 
     if (warp == REC_GATE_WARPS + 1) {
         // ===================== gi loader: bulk copies, GI_STAGES steps ahead =====================
+        // (the first GI_STAGES rows are requested before the phase's start barrier: the stages are free and the
+        // prefetch then overlaps the W_hh upload of the gate warps)
         if (phase == 0) tc::pdl_grid_dependency_wait();      // gi' comes from an upstream kernel
-        __syncthreads();
+        bool synced = false;
         const float* src0 = gi + ((b0 + lane) * gi_cols + gi_col0) * (int64_t)(2 * G) + dir * G;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % GI_STAGES;
+            if (s == GI_STAGES) { __syncthreads(); synced = true; }
             if (L.tile_flags != nullptr && (s == 0 || (t & 7) == (dir ? 7 : 0))) {
                 // decoder in the chunk-loop kernel: the projection CTAs announce finished gi' tiles
                 if (lane < NG && cta_x * NG + lane < ra.n_wg)
-                    tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 12ull * (chunk + 1));
+                    tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 24ull * (chunk + 1));
                 tc::fence_proxy_async_all();
                 __syncwarp();
             }
@@ -474,14 +521,15 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             __syncwarp();
             if (lane < NLIVE) tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + lane * GI_ROW_BYTES, src0 + (int64_t)t * (2 * G), GI_ROW_BYTES, gi_full + stage);
         }
+        if (!synced) __syncthreads();
     } else if (warp == REC_GATE_WARPS + 2) {
         // ===================== y store: the h image of step s is the layer output at column t_s ====
         if (phase == 0) tc::pdl_grid_dependency_wait();      // yimg may still be read by an upstream kernel
         __syncthreads();
         unsigned long long* flag = L.progress ? L.progress + (size_t)cta_x * 2 + dir : nullptr;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
-            const int buf = (s + 1) & 1;                     // the image written during step s
-            tc::mbar_wait(y_ready + buf, (uint32_t)((s >> 1) & 1));
+            const int buf = (s + 1) % NBUF;                  // the image written during step s
+            tc::mbar_wait(y_ready + buf, (uint32_t)((s / NBUF) & 1));
             if (lane < 2 * NG) {
                 const int g = lane >> 1, part = lane & 1;
                 tc::bulk_s2g(yimg + yimg_block(b0 / WG + g, t, W, part) + dir * YBLK, h_img + (buf * 2 + part) * HB_BYTES + g * YBLK, YBLK);
@@ -499,9 +547,11 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 if (lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)(s + 1 - PUBLISH_LAG));
             }
         }
+        HB_STAMP(3);                                         // last image handed to the copy engine
         if (lane < 2 * NG) { tc::bulk_wait0(); tc::fence_proxy_async_all(); }
         __syncwarp();
         if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)W);
+        HB_STAMP(4);                                         // all columns published
     } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
         // Measured (HB_DEBUG_TIMELINE): an M=128, N=16, K=16 MMA occupies the tensor pipe ~12 cycles, so the MMA time
@@ -510,6 +560,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         // remaining MMAs.
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
+        HB_STAMP(1);                                         // first step released
         const uint32_t idesc = tc::idesc_f16_f32(128, NACC);
         // stacked operand: NLIVE == 8 takes rows 8..15 from the lo image (group stride = HB_BYTES); with NLIVE == 16
         // the lo image directly follows the two hi groups, so the plain group stride covers all 32 rows
@@ -519,8 +570,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 tc::mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
                 tc::tc_fence_after();
             }
-            const uint64_t hhi_desc = himg_desc + (uint64_t)(((s & 1) * 2 + 0) * HB_BYTES / 16);
-            const uint64_t hlo_desc = himg_desc + (uint64_t)(((s & 1) * 2 + 1) * HB_BYTES / 16);
+            const uint64_t hhi_desc = himg_desc + (uint64_t)(((s % NBUF) * 2 + 0) * HB_BYTES / 16);
+            const uint64_t hlo_desc = himg_desc + (uint64_t)(((s % NBUF) * 2 + 1) * HB_BYTES / 16);
             HB_DBG(0, s, 0);
             if (tc::elect_one()) {
 #pragma unroll
@@ -555,18 +606,25 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             // W_hh of this phase's layer -> TMEM.  Warp w covers TMEM lanes 32 (w%4)..+31 (thread = gate row j); the four
             // warps of a lane quarter split (hi | lo image) x (k-pair columns 0-31 | 32-63); 32 words in flight per round
             // trip.  (All MMAs of the previous phase have completed: every gate warp waited for its last accumulator.)
+            // Two register buffers: the loads of gate block gb+1 are in flight while block gb is stored.
             const int term = (warp >> 2) & 1, half = warp >> 3;
-            const uint32_t* src = L.whh_tmem + (size_t)dir * WHH_TMEM_WORDS + (size_t)term * 3 * 128 * 64 + half * 32;
-#pragma unroll 1
-            for (int gb = 0; gb < 3; ++gb) {
-                uint32_t r[32];
-                const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)gb * 128 + j) * 64);
+            auto fetch = [&](int gb, uint32_t* r) {
+                const uint4* p = reinterpret_cast<const uint4*>(L.whh_tmem + whh_word_index(dir, term, gb, j, half * 32));
 #pragma unroll
-                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+            };
+            auto store = [&](int gb, const uint32_t* r) {
                 const uint32_t dst = tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
                 tc::tmem_st16(dst, r);
                 tc::tmem_st16(dst + 16, r + 16);
-            }
+            };
+            uint32_t ra0[32], ra1[32];
+            fetch(0, ra0);
+            fetch(1, ra1);
+            store(0, ra0);
+            fetch(2, ra0);
+            store(1, ra1);
+            store(2, ra0);
             tc::tmem_st_wait();
         }
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
@@ -632,9 +690,9 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             load_acc(taddr + NACC, a);
 #pragma unroll
             for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, giz[i])));
-            uint8_t* h_hi = h_img + (((s + 1) & 1) * 2) * HB_BYTES;            // image of h_{s+1}
+            uint8_t* h_hi = h_img + (((s + 1) % NBUF) * 2) * HB_BYTES;         // image of h_{s+1}
             uint8_t* h_lo = h_hi + HB_BYTES;
-            if (s >= 2) tc::mbar_wait(h_free + ((s + 1) & 1), (uint32_t)(((s - 2) >> 1) & 1));   // its store of step s-2 has drained
+            if (s >= NBUF) tc::mbar_wait(h_free + ((s + 1) % NBUF), (uint32_t)(((s - NBUF) / NBUF) & 1));   // its store of step s-NBUF has drained
             tc::mbar_wait(acc_ready + 2, par);
             if (drole < 3) HB_DBG(drole, s, 3);
             tc::tc_fence_after();
@@ -655,9 +713,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + ((s + 1) & 1)); }
+            if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + ((s + 1) % NBUF)); }
             if (drole < 3) HB_DBG(drole, s, 6);
         }
+        if (warp == 0) HB_STAMP(2);                          // last step done
         if (phase == n_phases - 1 && ra.h_out != nullptr) {
 #pragma unroll
             for (int i = 0; i < NW; ++i)
@@ -666,6 +725,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     }
     tc::tc_fence_before();
     __syncthreads();                                         // phase end: every role is done with the barriers
+    if (warp == 0) HB_STAMP(5);
+#undef HB_STAMP
     if (dbg && n_layers > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (li * 64 + chunk) * 2 + 1] = (long long)globaltimer_ns();
     }   // phase loop
 #undef HB_DBG
@@ -922,10 +983,13 @@ struct TensorTuning {
 struct TensorEngine {
     TensorTuning tune;
     hb_launch_plan last_plan{};
-    int* tile_order = nullptr;                // column-tile order of the chunk-loop projection role (earliest complete first)
+    int* proj_jobs = nullptr;                 // job table of the chunk-loop projection role (see ProjArgs::jobs)
+    int* proj_job_offsets = nullptr;
+    size_t proj_jobs_capacity = 0;
+    int jobs_w = -1, jobs_workers = -1; int64_t jobs_n_wg = -1;
+    std::vector<int> proj_jobs_host, proj_job_offsets_host;
     int tile_order_w = -1;
-    std::vector<int> tile_order_host;
-    int* tile_order16 = nullptr;              // same for the 16-column tiles of the heads role
+    int* tile_order16 = nullptr;              // column-tile order of the heads role (earliest complete first)
     std::vector<int> tile_order16_host;
     unsigned long long* flags = nullptr;      // counters of the chunk-loop kernel
     size_t flags_capacity = 0;
@@ -1066,8 +1130,7 @@ inline bool pack_layer(const hb_gru_weights& g, int K, bool activations_scaled, 
             for (int c = 0; c < kwords; ++c) {
                 const float v0 = 2 * c < K ? g.weight_ih[d][(size_t)r * K + 2 * c] * s_ih : 0.f;
                 const float v1 = 2 * c + 1 < K ? g.weight_ih[d][(size_t)r * K + 2 * c + 1] * s_ih : 0.f;
-                split_pair_words(v0, v1, &wih[(((size_t)blk * 2 + 0) * 128 + rr) * kwords + c],
-                                 &wih[(((size_t)blk * 2 + 1) * 128 + rr) * kwords + c]);
+                split_pair_words(v0, v1, &wih[wih_word_index(blk, 0, rr, c, kwords)], &wih[wih_word_index(blk, 1, rr, c, kwords)]);
             }
             // gate-dependent folding: r, z rows carry -log2e and both biases; n rows carry -2 log2e and b_in only
             const bool is_n = r >= 2 * H;
@@ -1081,9 +1144,7 @@ inline bool pack_layer(const hb_gru_weights& g, int K, bool activations_scaled, 
             for (int r = 0; r < 128; ++r)
                 for (int c = 0; c < 64; ++c) {
                     const float* row = g.weight_hh[d] + (size_t)(gb * 128 + r) * H;
-                    split_pair_words(row[2 * c] * s_hh, row[2 * c + 1] * s_hh,
-                                     &whh[(size_t)d * WHH_TMEM_WORDS + (((size_t)0 * 3 + gb) * 128 + r) * 64 + c],
-                                     &whh[(size_t)d * WHH_TMEM_WORDS + (((size_t)1 * 3 + gb) * 128 + r) * 64 + c]);
+                    split_pair_words(row[2 * c] * s_hh, row[2 * c + 1] * s_hh, &whh[whh_word_index(d, 0, gb, r, c)], &whh[whh_word_index(d, 1, gb, r, c)]);
                 }
         const float inv = ldexpf(1.f, -e_hh) * ACT_SCALE_INV;     // accumulator -> W_hh . h
         for (int j = 0; j < H; ++j) {
@@ -1104,7 +1165,7 @@ inline void free_layer(TensorLayer* L) {
 
 inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 128; }
 template <int N>
-constexpr size_t recurrence_smem() { return (size_t)4 * (N / WG) * YBLK + (size_t)gi_stages<N>() * N * GI_ROW_BYTES + 512; }
+constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<N>() * N * GI_ROW_BYTES + 512; }
 constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128; }
 
 }  // namespace detail
@@ -1115,7 +1176,8 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     detail::free_layer(&e->dec);
     cudaFree(e->head_img);
     cudaFree(e->b_head);
-    cudaFree(e->tile_order);
+    cudaFree(e->proj_jobs);
+    cudaFree(e->proj_job_offsets);
     cudaFree(e->tile_order16);
     cudaFree(e->flags);
     if (e->side) cudaStreamDestroy(e->side);
@@ -1175,7 +1237,7 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_chunkloop_kernel<16, 16, true>, loop16);
         set((const void*)tc_chunkloop_kernel<16, 16, false>, loop16);
         set((const void*)tc_chunkloop_kernel<32, 32, false>, loop32);
-        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order), 4096 * sizeof(int));
+        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->proj_job_offsets), 256 * sizeof(int));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order16), 4096 * sizeof(int));
         e->flags_capacity = (size_t)1 << 16;
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->flags), e->flags_capacity * sizeof(unsigned long long));
@@ -1315,18 +1377,52 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     }
     if (chunkloop) {
         if (e->tile_order_w != W) {
-            // a column tile is complete once the forward pass is past its last column and the reverse pass past its first
-            auto make_order = [&](int width, std::vector<int>& order, int* dev) {
-                const int n = (W + width - 1) / width;
-                order.resize(n);                                   // member vector: outlives the async copy
-                for (int i = 0; i < n; ++i) order[i] = i;
-                auto ready = [&](int tt) { return std::max(std::min(width * tt + width, W), W - width * tt); };
-                std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ready(x) < ready(y); });
-                cudaMemcpyAsync(dev, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
-            };
-            make_order(8, e->tile_order_host, e->tile_order);
-            make_order(16, e->tile_order16_host, e->tile_order16);
+            // heads: a column tile is complete once the forward pass is past its last column and the reverse pass past its first
+            const int n = tiles16;
+            std::vector<int>& order = e->tile_order16_host;            // member vector: outlives the async copy
+            order.resize(n);
+            for (int i = 0; i < n; ++i) order[i] = i;
+            auto ready = [&](int tt) { return std::max(std::min(16 * tt + 16, W), W - 16 * tt); };
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ready(x) < ready(y); });
+            cudaMemcpyAsync(e->tile_order16, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
             e->tile_order_w = W;
+        }
+        if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg) {
+            // projection job table: tile (group, tile) belongs to worker (group * tiles + tile) % workers; a worker takes
+            // the halves of its tiles in the order the encoder makes them runnable (forward half of tile t after step
+            // 8t+8, reverse half after step W-8t); the earlier half of a tile is the "first" (writes), the other adds
+            struct Job { int ready, second, id, packed; };
+            std::vector<std::vector<Job>> per(plan.proj_workers);
+            for (int64_t wg = 0; wg < n_wg; ++wg)
+                for (int t = 0; t < tiles8; ++t) {
+                    const int id = (int)(wg * tiles8 + t);
+                    const int rf = std::min(8 * t + 8, W), rb = W - 8 * t;
+                    const int first_dir = rf <= rb ? 0 : 1;
+                    for (int d = 0; d < 2; ++d) {
+                        const int second = d == first_dir ? 0 : 1;
+                        per[id % plan.proj_workers].push_back({d == 0 ? rf : rb, second, id, pack_proj_job((int)wg, t, d, second)});
+                    }
+                }
+            e->proj_jobs_host.clear();
+            e->proj_job_offsets_host.assign(1, 0);
+            for (auto& v : per) {
+                std::stable_sort(v.begin(), v.end(), [](const Job& x, const Job& y) {
+                    if (x.ready != y.ready) return x.ready < y.ready;
+                    if (x.second != y.second) return x.second < y.second;
+                    return x.id < y.id;
+                });
+                for (const Job& jb : v) e->proj_jobs_host.push_back(jb.packed);
+                e->proj_job_offsets_host.push_back((int)e->proj_jobs_host.size());
+            }
+            if (e->proj_jobs_host.size() > e->proj_jobs_capacity) {
+                cudaStreamSynchronize(s);
+                cudaFree(e->proj_jobs);
+                e->proj_jobs_capacity = e->proj_jobs_host.size() * 2;
+                cudaMalloc(reinterpret_cast<void**>(&e->proj_jobs), e->proj_jobs_capacity * sizeof(int));
+            }
+            cudaMemcpyAsync(e->proj_jobs, e->proj_jobs_host.data(), e->proj_jobs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(e->proj_job_offsets, e->proj_job_offsets_host.data(), e->proj_job_offsets_host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+            e->jobs_w = W; e->jobs_workers = plan.proj_workers; e->jobs_n_wg = n_wg;
         }
         cudaMemsetAsync(e->flags, 0, flags_needed * sizeof(unsigned long long), s);
         unsigned long long* f = e->flags;
@@ -1343,7 +1439,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         ra.n_layers = 2; ra.n_chunks = n_chunks; ra.h_in = nullptr; ra.h_out = nullptr; ra.B = B; ra.W = W;
         ra.tiles_t = tiles8; ra.n_wg = (int)n_wg; ra.epoch = 0; ra.dbg = dbg_buf; ra.dbg_layer = dbg_enc ? 0 : 1;
         ProjArgs pp = pd;
-        pp.progress = enc_prog; pp.epoch = 0; pp.tile_order = e->tile_order; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
+        pp.progress = enc_prog; pp.epoch = 0; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
+        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets;
         HeadsArgs hp = heads_base;
         hp.yimg = ws.yimg2[0]; hp.yimg_odd = ws.yimg2[1]; hp.col0 = 0; hp.n_chunks = n_chunks;
         hp.progress = dec_prog; hp.rec_n = plan.tile; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
@@ -1438,6 +1535,12 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                     fprintf(stderr, "  chunk %d: enc %.1f -> %.1f   dec %.1f -> %.1f\n", k,
                             (hbuf[4096 + k * 2] - t0) * 1e-3, (hbuf[4096 + k * 2 + 1] - t0) * 1e-3,
                             (hbuf[4096 + (64 + k) * 2] - t0) * 1e-3, (hbuf[4096 + (64 + k) * 2 + 1] - t0) * 1e-3);
+                for (int li = 0; li < 2; ++li) {
+                    const long long* st = &hbuf[6144 + li * 8];
+                    fprintf(stderr, "  chunk 2 %s phase, cycles after phase start: first step released %lld | last step done %lld | last image "
+                            "handed to copy engine %lld | all columns published %lld | phase end %lld\n", li ? "dec" : "enc",
+                            st[1] - st[0], st[2] - st[0], st[3] - st[0], st[4] - st[0], st[5] - st[0]);
+                }
                 if (n_chunks > 0)
                     fprintf(stderr, "  last chunk: dec end %.1f\n", (hbuf[4096 + (64 + n_chunks - 1) * 2 + 1] - t0) * 1e-3);
             }
