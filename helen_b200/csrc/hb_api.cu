@@ -87,6 +87,9 @@ struct hb_handle {
     char* stage_workspace = nullptr;
     size_t cap_images = 0, cap_images_dev = 0, cap_labels = 0, cap_labels_dev = 0, cap_prob = 0, cap_workspace = 0;
     cudaStream_t host_stream = nullptr;
+    // The engines keep per-handle device state (chunk-loop counters, job tables) and the chunk-loop kernel wants the whole
+    // chip: successive predict calls of one handle are serialised on the device even when they come on different streams.
+    cudaEvent_t last_predict = nullptr;
 
     // device timing of the predict kernel sequence
     bool timing = false;
@@ -303,6 +306,7 @@ void hb_destroy(hb_handle* h) {
     if (h->stage_prob_dev) cudaFree(h->stage_prob_dev);
     if (h->stage_workspace) cudaFree(h->stage_workspace);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    if (h->last_predict) cudaEventDestroy(h->last_predict);
     for (auto& ev : h->events) {
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
@@ -357,6 +361,8 @@ int hb_predict_windows(hb_handle* h, const uint8_t* images_dev, int64_t B, int T
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace_dev)));
+    if (!h->last_predict) HB_CUDA(cudaEventCreateWithFlags(&h->last_predict, cudaEventDisableTiming));
+    else HB_CUDA(cudaStreamWaitEvent(s, h->last_predict, 0));
     size_t slot;
     if ((rc = begin_timing(h, s, &slot))) return rc;
 #ifndef HB_NO_TENSOR_ENGINE
@@ -375,6 +381,7 @@ int hb_predict_windows(hb_handle* h, const uint8_t* images_dev, int64_t B, int T
     }
     if ((rc = end_timing(h, s, slot))) return rc;
     h->timed_launches += (slot != (size_t)-1);
+    HB_CUDA(cudaEventRecord(h->last_predict, s));
     return HB_OK;
 }
 

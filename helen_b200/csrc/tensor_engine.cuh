@@ -44,6 +44,12 @@ constexpr int H_LBO = 144;                        // k-group stride of h / y ima
 constexpr int YBLK = 16 * H_LBO;                  // 2304 B: [8 windows x 128 k] fp16 image of one direction
 constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)
 constexpr int GI_ROW_BYTES = G * 4;               // 1536 B: gi of one (window, t, direction)
+// gi' lives in global memory as a "gi image": [window group][column][direction][gate r,z,n][8 windows][128 units] fp32,
+// so that what one recurrence step needs (all gates of a window group's column and direction, 12 KB) and what one
+// projection job produces per column (one gate block of 8 windows, 4 KB) are each ONE contiguous bulk copy.
+constexpr int GI_BLK_FLOATS = WG * H;             // 1024: one (group, column, gate block)
+constexpr int GI_GRP_BYTES = 3 * GI_BLK_FLOATS * 4;   // 12288 B: one (group, column, direction)
+__host__ __device__ constexpr int64_t gi_block(int64_t wg, int64_t cols, int64_t t, int blk) { return ((wg * cols + t) * 6 + blk) * GI_BLK_FLOATS; }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -95,13 +101,18 @@ pileup_to_operand_image_kernel(const uint8_t* __restrict__ images, int64_t B, in
 // Input projection  gi'[m, 0:768] = scale_row * (A[m, :] . Wcat^T) + bias_row
 // grid = (workers, 6 gate blocks).  The CTA's [128 x Kp] weight block (hi, lo) is TMEM-resident;
 // a tile is 64 data rows = 8 windows x 8 consecutive columns, staged by bulk copies.
-// Warps 0-3: epilogue (TMEM lane quarter = warp).  Warp 4: MMA issuer.  Warp 5: tile loader.
+// Warps 0-3: epilogue (TMEM lane quarter = warp).  Warp 4: MMA issuer.  Warp 5: tile loader.  Warp 6: gi' store - the
+// epilogue stages the block in shared memory and the store warp writes it with bulk copies (512 contiguous bytes per
+// (window, column)), so completion is tracked per job by bulk groups: the chunk-loop kernel publishes a job's flag
+// when ITS copies have landed, without a memory fence that would also wait for the newest stores.
 // The epilogue folds the bias sums and the -log2(e) factors of the gate nonlinearities into gi'
 // (see tc_recurrence_kernel), so gi' is NOT the plain pre-activation of the fp32 engine.
 // ---------------------------------------------------------------------------------------------
-constexpr int PROJ_THREADS = 192;
+constexpr int PROJ_THREADS = 224;                // warps 0-3 epilogue, 4 MMA issuer, 5 tile loader, 6 gi' store
 constexpr int PROJ_NT = 64;
+constexpr int PROJ_STG_BYTES = PROJ_NT * 128 * 4;   // fp32 staging of one tile's output block: [64 (column, window)][128 gate rows]
 constexpr int PROJ_STAGES = 2;
+constexpr int PROJ_PUBLISH_BATCH = 8;
 constexpr int PROJ_W_COL0 = 128;
 
 struct ProjArgs {
@@ -110,7 +121,8 @@ struct ProjArgs {
     const uint32_t* w_tmem;        // packed fp16 pairs, see wih_word_index
     const float* scale_row;        // [768]
     const float* bias_row;         // [768]
-    float* gi;                     // [(b * W + t), 768]
+    float* gi;                     // gi image with W columns (see gi_block)
+    float* gi_b;                   // chunk-loop kernel: where the reverse-source K-half goes (see jobs)
     // pair mode: the launch uses clusters of 2 CTAs along the gate-block axis; both CTAs of a pair walk the same
     // tiles, each fetches half of a tile and multicasts it to both, halving the L2 traffic of the activations
     int pair;
@@ -118,19 +130,21 @@ struct ProjArgs {
     // split by SOURCE direction.  A job is one half of a column tile: the K = 128 slice that multiplies the forward
     // (or the reverse) encoder's outputs, runnable as soon as THAT direction has stored the tile's columns, so the
     // projection keeps pace with the encoder instead of starting when both directions meet in the middle.  The
-    // first half of a tile writes scale * acc + bias, the second adds scale * acc to it (red.add); both halves of a tile
-    // belong to the same worker (same thread, program order), and which half is first is fixed by the job table,
-    // so the result does not depend on timing.
+    // forward-source half writes scale * acc + bias to gi, the reverse-source half writes scale * acc to gi_b, and
+    // the decoder's gate threads add the two rows (fixed order: the result does not depend on timing).  (Adding in
+    // place was tried: reading the first half back stalls the epilogue on a global round trip, and red.add is
+    // issued lane by lane - either way the role fell behind the encoder.)
     const int* jobs;               // per worker, in the order the encoder makes them runnable (see pack_proj_job)
     const int* job_offsets;        // [workers + 1]
     const unsigned long long* progress; unsigned long long epoch; int rec_n;   // encoder progress counters, [cta][dir]
     int n_chunks;                  // a chunk's columns count from chunk * W in the progress counters
-    unsigned long long* tile_flags;   // [group][tile][decoder direction]: += 1 per epilogue warp and job (24 per chunk)
+    unsigned long long* tile_flags;   // [group][tile][decoder direction]: += 1 per job and gate block (3 blocks x 2 K-halves = 6 per chunk)
+    long long* dbg;                   // HB_DEBUG_TIMELINE: worker 0 records when it finished each chunk
 };
 
-__host__ __device__ constexpr int pack_proj_job(int wg, int tile, int src_dir, int second) { return wg | (tile << 16) | (src_dir << 28) | (second << 29); }
+__host__ __device__ constexpr int pack_proj_job(int wg, int tile, int src_dir) { return wg | (tile << 16) | (src_dir << 28); }
 
-struct ProjJob { int64_t wg; int t0, valid, src_dir; bool split, second; };
+struct ProjJob { int64_t wg; int t0, valid, src_dir; bool split; };
 
 // idx-th job of a worker; all roles of a CTA walk the same sequence
 __device__ __forceinline__ bool proj_job(const ProjArgs& a, int worker, int n_workers, int64_t idx, ProjJob& j) {
@@ -138,11 +152,11 @@ __device__ __forceinline__ bool proj_job(const ProjArgs& a, int worker, int n_wo
         const int begin = __ldg(a.job_offsets + worker), end = __ldg(a.job_offsets + worker + 1);
         if (idx >= end - begin) return false;
         const int e = __ldg(a.jobs + begin + idx);
-        j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.src_dir = (e >> 28) & 1; j.second = (e >> 29) & 1; j.split = true;
+        j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.src_dir = (e >> 28) & 1; j.split = true;
     } else {
         const int64_t tile = worker + idx * n_workers;
         if (tile >= a.n_wg * ((a.W + 7) >> 3)) return false;
-        j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.src_dir = 0; j.second = false; j.split = false;
+        j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.src_dir = 0; j.split = false;
     }
     j.valid = min(8, a.W - j.t0);
     return true;
@@ -163,11 +177,14 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     constexpr int PARTS = kSplitA ? 2 : 1;
     const uint32_t part_bytes = 8u * blk_bytes;              // 8 row groups (columns t0..t0+7)
     const uint32_t stage_bytes = PARTS * 8u * a.blk_bytes;   // allocation (full K)
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + PROJ_STAGES * stage_bytes);
+    uint8_t* staging = smem + PROJ_STAGES * stage_bytes;     // [2][PROJ_STG_BYTES]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(staging + 2 * PROJ_STG_BYTES);
     uint64_t* a_empty = a_full + PROJ_STAGES;
     uint64_t* acc_full = a_empty + PROJ_STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* stg_full = acc_empty + 2;                      // [2]: the 4 epilogue warps have written the staging buffer
+    uint64_t* stg_empty = stg_full + 2;                      // [2]: its bulk copies have read it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kwords = Kp >> 1;
@@ -175,6 +192,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     if (tid == 0) {
         for (int i = 0; i < PROJ_STAGES; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, a.pair ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(stg_full + i, 4); tc::mbar_init(stg_empty + i, 1); }
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -244,6 +262,49 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 }
             }
         }
+    } else if (warp == 6) {
+        // ===================== gi' store =====================
+        // lane c < 8 copies column t0 + c of the staged block: [8 windows][128 gate rows] = 4 KB, contiguous in the gi image
+        const int tiles_t = (W + 7) >> 3;
+        // Flags are raised in batches: the release below is a gpu-scope fence (~1 us), one per job would make this warp
+        // the bottleneck of the role.  A batch goes out when PROJ_PUBLISH_BATCH jobs are waiting or the role runs dry
+        // (the consumers only wait for a chunk's LAST jobs, and those are followed by an idle period).
+        unsigned long long* pending[PROJ_PUBLISH_BATCH];     // flags of the jobs whose copies may still be in flight
+        int n_pending = 0;
+        auto publish = [&](int keep) {                       // wait until all but the newest `keep` (0 or 2) jobs have landed, raise their flags
+            if (n_pending <= keep) return;
+            if (keep == 0) tc::bulk_wait0(); else tc::bulk_wait_pending<2>();
+            tc::fence_proxy_async_all();
+            __syncwarp();
+            for (int k = 0; k < n_pending - keep; ++k)
+                if (lane == 0 && pending[k] != nullptr) tc::red_release_gpu_add(pending[k], 1ull);
+            for (int k = 0; k < keep; ++k) pending[k] = pending[n_pending - keep + k];
+            n_pending = keep;
+        };
+        int it = 0;
+        for (int chunk = 0; chunk < n_chunks; ++chunk)
+        for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
+            const int sb = it & 1;
+            const uint32_t par = (uint32_t)((it >> 1) & 1);
+            if (!tc::mbar_test_wait(stg_full + sb, par)) {   // nothing to store yet: do not sit on finished jobs
+                publish(0);
+                tc::mbar_wait(stg_full + sb, par);
+            }
+            float* out = j.src_dir ? a.gi_b : gi;
+            if (lane < 8 && j.t0 + lane < W)
+                tc::bulk_s2g(out + gi_block(j.wg, W, j.t0 + lane, blk), staging + sb * PROJ_STG_BYTES + lane * (GI_BLK_FLOATS * 4), GI_BLK_FLOATS * 4);
+            tc::bulk_commit();
+            tc::bulk_wait_read0();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(stg_empty + sb);
+            if (a.tile_flags != nullptr) {
+                pending[n_pending++] = a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
+                if (n_pending == PROJ_PUBLISH_BATCH) publish(2);   // copies issued two jobs ago have normally landed: no stall
+            }
+            if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
+        }
+        publish(0);
+        if (lane < 32) tc::bulk_wait0();                     // the kernel's results are complete when the role returns
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
@@ -274,43 +335,30 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         }
     } else {
         // ===================== epilogue =====================
-        const int row = blk * 128 + warp * 32 + lane;
-        const float sc = scale_row[row], bi = bias_row[row];
-        const int tiles_t = (W + 7) >> 3;
+        const int r = warp * 32 + lane;                      // gate row within the block == TMEM lane
+        const float sc = scale_row[blk * 128 + r], bi = bias_row[blk * 128 + r];
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
         for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
-            const int acc = it & 1;
+            const int acc = it & 1, sb = it & 1;
+            if (it >= 2) tc::mbar_wait(stg_empty + sb, (uint32_t)((it / 2 - 1) & 1));
             tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1));
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
+            float* stg = reinterpret_cast<float*>(staging + sb * PROJ_STG_BYTES) + r;
+            const float add = j.src_dir ? 0.f : bi;          // the bias rides on the forward-source half (or the only one)
 #pragma unroll 2
             for (int c8 = 0; c8 < PROJ_NT; c8 += 8) {       // 8 accumulator columns = the 8 windows of column t0 + c8/8
                 float v[8];
                 tc::tmem_ld8(taddr + c8, v);
                 tc::tmem_ld_wait();
-                const int t = j.t0 + (c8 >> 3);
-                if (t < W) {
-                    float* out = gi + ((j.wg * WG) * W + t) * (int64_t)(2 * G) + row;
-                    if (j.second) {
-                        // add to what this thread stored for the tile's first half (same thread, same address: ordered).
-                        // Fire-and-forget reduction at L2: reading the old value back would stall on a global round trip.
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) atomicAdd(out + (int64_t)i * W * (2 * G), v[i] * sc);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) out[(int64_t)i * W * (2 * G)] = fmaf(v[i], sc, bi);
-                    }
-                }
+                for (int i = 0; i < 8; ++i) stg[(c8 + i) * 128] = fmaf(v[i], sc, add);
             }
             tc::tc_fence_before();
+            tc::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(acc_empty + acc);
-            if (a.tile_flags != nullptr) {                   // gi' rows of this job are in global memory
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) tc::red_release_gpu_add(a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3), 1ull);
-            }
+            if (lane == 0) { tc::mbar_arrive(acc_empty + acc); tc::mbar_arrive(stg_full + sb); }
         }
     }
     tc::tc_fence_before();
@@ -347,7 +395,10 @@ constexpr int REC_GATE_WARPS = 16;
 constexpr int REC_TC_THREADS = (REC_GATE_WARPS + 3) * 32;
 constexpr int REC_W_COL0 = 128;                   // weight columns start here (accumulators below)
 constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate block][row][k pair]
-template <int N> __host__ __device__ constexpr int gi_stages() { return N <= 16 ? 4 : 3; }   // N = 32: 3 x 48 KB (227 KB smem limit)
+// GI2: a stage holds TWO gi' rows per window (the two K-halves of the chunk-loop projection, added by the gate threads)
+template <int N, int NLIVE, bool GI2> __host__ __device__ constexpr int gi_stages() {
+    return GI2 ? (NLIVE <= 8 ? 4 : 3) : (N <= 16 ? 4 : 3);   // N = 32: 3 x 48 KB, 16 live x 2 rows: 3 x 48 KB (227 KB smem limit)
+}
 // h operand image buffers: 4 give the y store three steps to drain, which hides the global-memory round trips of the
 // progress publication (chunk-loop kernel); N = 32 has room for 2 only
 template <int N> __host__ __device__ constexpr int h_buffers() { return N <= 16 ? 4 : 2; }
@@ -356,13 +407,14 @@ constexpr int PUBLISH_LAG = 4;
 // One GRU layer as the recurrence role sees it.
 struct RecLayer {
     const float* gi;               // gi' rows; row of (window b, chunk k, step column t) = b * gi_cols + gi_col0 + k * gi_col_step + t
+    const float* gi_b;             // second addend of gi' (same indexing) or nullptr: the K-halves of the chunk-loop projection
     int gi_cols, gi_col0, gi_col_step;
     const uint32_t* whh_tmem;      // packed fp16 pairs, see whh_word_index
     const float* gate_consts;      // [2 dirs][4][128]: inv_r', inv_z', inv_n', b_hn'  (per unit)
     uint8_t* yimg[2];              // operand image of the layer output: [0] even chunks, [1] odd chunks
     unsigned long long* progress;  // [ctas][2 dirs] columns whose output has landed in yimg (+ epoch + chunk * W), or nullptr
     // chunk-loop kernel only (counters in global memory, see tc_chunkloop_kernel):
-    const unsigned long long* tile_flags;      // decoder: gi' tile (group, tile, dir) of chunk k is ready at >= 24 (k + 1)
+    const unsigned long long* tile_flags;      // decoder: gi' tile (group, tile, dir) of chunk k is ready at >= 6 (k + 1)
     const unsigned long long* heads_done; int heads_per_chunk;   // decoder: yimg[k & 1] reusable when >= heads_per_chunk (k - 1)
     const unsigned long long* consumed_flags;  // encoder: tile flags (both directions) that tell yimg of chunk k - 1 has been read
 };
@@ -391,7 +443,11 @@ struct RecArgs {
 // only the two A terms W_hi and W_lo (48 MMAs instead of 72; the MMA time of a step is set by the instruction count,
 // not by N, at these sizes).  Accumulator columns [0, NLIVE) hold W.h_hi, [NLIVE, 2 NLIVE) hold W.h_lo; the gate
 // threads add the two.  That is the full 4-term product (W_lo.h_lo included).
-template <int N, int NLIVE, bool STACK = false>
+//
+// MODE 0: 3-term.  MODE 1: STACK.  MODE 2: STACK with two accumulators per gate block (NLIVE = 8 only): the W_hi and
+// the W_lo MMAs of a k-step go to different TMEM columns and are issued alternately, so consecutive MMAs do not
+// accumulate into the same tile (a chain of 16 dependent accumulations ran at ~15 cycles per MMA).
+template <int N, int NLIVE, int MODE = 0, bool GI2 = false>
 __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem, const int cta_x, const int dir)
 {
     const int64_t B = ra.B;
@@ -402,13 +458,17 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 #define HB_DBG(role, s, k) do { if (dbg_steps && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N accumulator columns per gate block (3N must stay below REC_W_COL0)");
     static_assert(NLIVE == N || (N == 16 && NLIVE == 8), "live windows per CTA");
+    constexpr bool STACK = MODE >= 1, DUAL = MODE == 2;
     static_assert(!STACK || N == 16, "stacked operand: 3 x 2 NLIVE accumulator columns must stay below REC_W_COL0");
-    constexpr int NACC = STACK ? 2 * NLIVE : N;              // accumulator columns per gate block == N of the MMA
+    static_assert(!DUAL || NLIVE == 8, "two accumulators per gate block: 3 x 2 x 16 columns");
+    constexpr int NACC = STACK ? 2 * NLIVE : N;              // N of the MMA
+    constexpr int NBLK = DUAL ? 2 * NACC : NACC;             // accumulator columns per gate block
     constexpr int NW = NLIVE / 4;                            // windows per gate thread
     constexpr int NG = NLIVE / WG;                           // live window groups per CTA
     constexpr uint32_t HB_BYTES = (N / WG) * YBLK;           // one h operand image (hi or lo), all N columns
-    constexpr uint32_t GI_STAGE_BYTES = NLIVE * GI_ROW_BYTES;
-    constexpr int GI_STAGES = gi_stages<N>();
+    static_assert(!GI2 || NLIVE <= 16, "two gi' rows per window: at most 16 live windows fit");
+    constexpr uint32_t GI_STAGE_BYTES = (GI2 ? 2 : 1) * NLIVE * GI_ROW_BYTES;
+    constexpr int GI_STAGES = gi_stages<N, NLIVE, GI2>();
     // h operand images, NBUF buffers: step s reads buffer s % NBUF (h_s) and writes buffer (s+1) % NBUF (h_{s+1}),
     // so the y store of an image has NBUF steps to drain before the buffer is written again
     constexpr int NBUF = h_buffers<N>();
@@ -458,6 +518,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     const int chunk = phase / n_layers, li = phase - chunk * n_layers;
     const RecLayer& L = ra.layer[li];
     const float* __restrict__ gi = L.gi;
+    const bool two_rows = GI2 && L.gi_b != nullptr;          // gi' = gi[row] + gi_b[row]
     const int gi_cols = L.gi_cols;
     const int gi_col0 = L.gi_col0 + chunk * L.gi_col_step;
     uint8_t* __restrict__ yimg = L.yimg[chunk & 1];
@@ -487,7 +548,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (L.consumed_flags != nullptr && chunk >= 1)   // every projection CTA has read this layer's previous image
                 for (int f = lane; f < NG * ra.tiles_t * 2; f += 32)
                     if (cta_x * NG + f / (ra.tiles_t * 2) < ra.n_wg)
-                        tc::spin_until_ge(L.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, 24ull * chunk);
+                        tc::spin_until_ge(L.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, 6ull * chunk);
         }
         __syncthreads();
     }
@@ -505,21 +566,28 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         // prefetch then overlaps the W_hh upload of the gate warps)
         if (phase == 0) tc::pdl_grid_dependency_wait();      // gi' comes from an upstream kernel
         bool synced = false;
-        const float* src0 = gi + ((b0 + lane) * gi_cols + gi_col0) * (int64_t)(2 * G) + dir * G;
+        // lane g < NG fetches group g's block of the step (all three gates, 12 KB); lanes 16.. the second addend's
+        const int lane2 = lane - 16;
+        const float* src0 = gi + gi_block(b0 / WG + min(lane, NG - 1), gi_cols, gi_col0, dir * 3);
+        const float* src0b = two_rows ? L.gi_b + gi_block(b0 / WG + min(max(lane2, 0), NG - 1), gi_cols, gi_col0, dir * 3) : nullptr;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % GI_STAGES;
             if (s == GI_STAGES) { __syncthreads(); synced = true; }
             if (L.tile_flags != nullptr && (s == 0 || (t & 7) == (dir ? 7 : 0))) {
                 // decoder in the chunk-loop kernel: the projection CTAs announce finished gi' tiles
                 if (lane < NG && cta_x * NG + lane < ra.n_wg)
-                    tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 24ull * (chunk + 1));
+                    tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 6ull * (chunk + 1));
                 tc::fence_proxy_async_all();
                 __syncwarp();
             }
             if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
-            if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, GI_STAGE_BYTES);
+            if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, (two_rows ? 2u : 1u) * NG * GI_GRP_BYTES);
             __syncwarp();
-            if (lane < NLIVE) tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + lane * GI_ROW_BYTES, src0 + (int64_t)t * (2 * G), GI_ROW_BYTES, gi_full + stage);
+            if (lane < NG) tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + lane * GI_GRP_BYTES, src0 + (int64_t)t * (6 * GI_BLK_FLOATS), GI_GRP_BYTES, gi_full + stage);
+            if constexpr (GI2) {
+                if (two_rows && lane2 >= 0 && lane2 < NG)
+                    tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + (NG + lane2) * GI_GRP_BYTES, src0b + (int64_t)t * (6 * GI_BLK_FLOATS), GI_GRP_BYTES, gi_full + stage);
+            }
         }
         if (!synced) __syncthreads();
     } else if (warp == REC_GATE_WARPS + 2) {
@@ -576,13 +644,20 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (tc::elect_one()) {
 #pragma unroll
                 for (int gb = 0; gb < 3; ++gb) {             // gate blocks r, z, n
-                    if constexpr (STACK) {
+                    if constexpr (DUAL) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                            for (int term = 0; term < 2; ++term)     // W_hi -> columns [0, 16), W_lo -> [16, 32) of the block
+                                tc::mma_f16_ts(tmem + gb * NBLK + term * NACC, tmem + REC_W_COL0 + (term * 3 + gb) * 64 + ks * 8,
+                                               hhi_desc + (uint64_t)(ks * 2 * H_LBO / 16), idesc, ks != 0);
+                    } else if constexpr (STACK) {
 #pragma unroll
                         for (int term = 0; term < 2; ++term) {   // W_hi, W_lo against [h_hi | h_lo]
                             const uint32_t a_col = tmem + REC_W_COL0 + (term * 3 + gb) * 64;
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks)
-                                tc::mma_f16_ts(tmem + gb * NACC, a_col + ks * 8, hhi_desc + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
+                                tc::mma_f16_ts(tmem + gb * NBLK, a_col + ks * 8, hhi_desc + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
                         }
                     } else {
 #pragma unroll
@@ -591,7 +666,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                             const uint64_t bd = term == 2 ? hlo_desc : hhi_desc;
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks)
-                                tc::mma_f16_ts(tmem + gb * NACC, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
+                                tc::mma_f16_ts(tmem + gb * NBLK, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
                         }
                     }
                     tc::mma_commit(acc_ready + gb);          // gates start on r while z, n still run
@@ -653,7 +728,15 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
         auto load_acc = [](uint32_t addr, float* a) {
             tc::tmem_ld_n<NW>(addr, a);
-            if constexpr (STACK) {
+            if constexpr (DUAL) {
+                float b1[NW], b2[NW], b3[NW];
+                tc::tmem_ld_n<NW>(addr + NLIVE, b1);
+                tc::tmem_ld_n<NW>(addr + NACC, b2);
+                tc::tmem_ld_n<NW>(addr + NACC + NLIVE, b3);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < NW; ++i) a[i] = (a[i] + b1[i]) + (b2[i] + b3[i]);
+            } else if constexpr (STACK) {
                 float a_lo[NW];
                 tc::tmem_ld_n<NW>(addr + NLIVE, a_lo);
                 tc::tmem_ld_wait();
@@ -671,9 +754,17 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::mbar_wait(gi_full + stage, (uint32_t)((s / GI_STAGES) & 1));
             if (drole < 3) HB_DBG(drole, s, 0);
             {
-                const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + win0 * G + j;
+                // stage: [addend][group][gate][window in group][unit]; this thread's NW windows lie in one group
+                const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + (win0 / WG) * (3 * GI_BLK_FLOATS) + (win0 % WG) * H + j;
 #pragma unroll
-                for (int i = 0; i < NW; ++i) { gir[i] = gs[i * G]; giz[i] = gs[i * G + H]; gin[i] = gs[i * G + 2 * H]; }
+                for (int i = 0; i < NW; ++i) { gir[i] = gs[i * H]; giz[i] = gs[GI_BLK_FLOATS + i * H]; gin[i] = gs[2 * GI_BLK_FLOATS + i * H]; }
+                if constexpr (GI2) {
+                    if (two_rows) {
+                        const float* gb = gs + NG * (3 * GI_BLK_FLOATS);
+#pragma unroll
+                        for (int i = 0; i < NW; ++i) { gir[i] += gb[i * H]; giz[i] += gb[GI_BLK_FLOATS + i * H]; gin[i] += gb[2 * GI_BLK_FLOATS + i * H]; }
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(gi_empty + stage);
@@ -687,7 +778,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::mbar_wait(acc_ready + 1, par);
             if (drole < 3) HB_DBG(drole, s, 2);
             tc::tc_fence_after();
-            load_acc(taddr + NACC, a);
+            load_acc(taddr + NBLK, a);
 #pragma unroll
             for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, giz[i])));
             uint8_t* h_hi = h_img + (((s + 1) % NBUF) * 2) * HB_BYTES;         // image of h_{s+1}
@@ -696,7 +787,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::mbar_wait(acc_ready + 2, par);
             if (drole < 3) HB_DBG(drole, s, 3);
             tc::tc_fence_after();
-            load_acc(taddr + 2 * NACC, a);
+            load_acc(taddr + 2 * NBLK, a);
             if (drole < 3) HB_DBG(drole, s, 4);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
@@ -733,12 +824,12 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
-template <int N, int NLIVE, bool STACK>
+template <int N, int NLIVE, int MODE>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
 tc_recurrence_kernel(const RecArgs ra)
 {
     extern __shared__ __align__(128) uint8_t smem_rec[];
-    recurrence_role<N, NLIVE, STACK>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
+    recurrence_role<N, NLIVE, MODE>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -759,6 +850,7 @@ struct HeadsArgs {
     // persistent mode
     int n_chunks; const unsigned long long* progress; int rec_n; const int* tile_order;
     unsigned long long* heads_done;                    // [group] += 4 per finished tile
+    long long* dbg;                                    // HB_DEBUG_TIMELINE: worker 0 records when it finished each chunk
 };
 
 // job q of a worker -> (chunk, window group, column tile).  Single-chunk launches spread tiles over all workers;
@@ -882,16 +974,22 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                 }
                 float* pb = a.p_base + (b * T + col) * NBASE;
                 float* pr = a.p_rle + (b * T + col) * NRLE;
+                float old[NCLS];                             // all 16 reads in flight at once (one global round trip, not 16)
 #pragma unroll
-                for (int c = 0; c < NBASE; ++c) pb[c] += v[c] / sb;
+                for (int c = 0; c < NBASE; ++c) old[c] = __ldcg(pb + c);
 #pragma unroll
-                for (int c = 0; c < NRLE; ++c) pr[c] += v[NBASE + c] / sr;
+                for (int c = 0; c < NRLE; ++c) old[NBASE + c] = __ldcg(pr + c);
+#pragma unroll
+                for (int c = 0; c < NBASE; ++c) pb[c] = old[c] + v[c] / sb;
+#pragma unroll
+                for (int c = 0; c < NRLE; ++c) pr[c] = old[NBASE + c] + v[NBASE + c] / sr;
             }
             if (a.heads_done != nullptr) {
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) tc::red_release_gpu_add(a.heads_done + wg, 1ull);
             }
+            if (a.dbg != nullptr && worker == 0 && tid == 0) a.dbg[7100 + chunk] = (long long)globaltimer_ns();
         }
     }
     tc::tc_fence_before();
@@ -920,7 +1018,7 @@ tc_heads_kernel(const HeadsArgs a)
 // 100 encoder steps + the edge tiles of the projection + 100 decoder steps, with no launch boundary in between.
 // Launched as clusters of 2 CTAs: the projection role pairs gate blocks (2b, 2b+1) and multicasts activation tiles.
 // ---------------------------------------------------------------------------------------------
-template <int N, int NLIVE, bool STACK>
+template <int N, int NLIVE, int MODE>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
 tc_chunkloop_kernel(const RecArgs rec, const ProjArgs proj, const HeadsArgs heads,
                     const int rec_ctas, const int proj_workers, const int heads_workers)
@@ -928,7 +1026,7 @@ tc_chunkloop_kernel(const RecArgs rec, const ProjArgs proj, const HeadsArgs head
     extern __shared__ __align__(128) uint8_t smem_all[];
     const int bid = (int)blockIdx.x;
     if (bid < 2 * rec_ctas) {
-        recurrence_role<N, NLIVE, STACK>(rec, smem_all, bid >> 1, bid & 1);
+        recurrence_role<N, NLIVE, MODE, true>(rec, smem_all, bid >> 1, bid & 1);
     } else if (bid < 2 * rec_ctas + 6 * proj_workers) {
         if (threadIdx.x >= PROJ_THREADS) {                   // spare warps only keep the pair's cluster barriers aligned
             if (proj.pair) { tc::cluster_sync_all(); tc::cluster_sync_all(); }
@@ -960,6 +1058,7 @@ struct TensorTuning {
     bool pdl = true;            // HB_NO_PDL: no programmatic dependent launch
     bool pair = true;           // HB_NO_PAIR: projection without 2-CTA multicast clusters
     bool stack = true;          // HB_NO_STACK: 3-term recurrence MMAs instead of the stacked [h_hi | h_lo] operand
+    bool dual = true;           // HB_NO_DUAL: one accumulator per gate block in the 8-window stacked tile
     bool live8 = true;          // HB_NO_LIVE8: never use the 8-live-window recurrence tile
     int windows_per_cta = 0;    // HB_WINDOWS_PER_CTA = 8 | 16 | 32: force the recurrence tile
     bool chunkloop = true;      // HB_NO_CHUNKLOOP: per-chunk launches even when the whole chunk loop fits on the chip
@@ -969,6 +1068,7 @@ struct TensorTuning {
         t.pdl = getenv("HB_NO_PDL") == nullptr;
         t.pair = getenv("HB_NO_PAIR") == nullptr;
         t.stack = getenv("HB_NO_STACK") == nullptr;
+        t.dual = getenv("HB_NO_DUAL") == nullptr;
         t.live8 = getenv("HB_NO_LIVE8") == nullptr;
         t.chunkloop = getenv("HB_NO_CHUNKLOOP") == nullptr;
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
@@ -1011,6 +1111,7 @@ struct TensorEngine {
 struct TensorWorkspace {
     float* gi_enc;      // [Bp, enc_cols, 768]  encoder projections of every image column, computed once per batch
     float* gi;          // [Bp, W, 768]         decoder projections of the current chunk
+    float* gi_b;        // [Bp, W, 768]         chunk-loop kernel: the reverse-source K-half (gi holds the forward-source half)
     uint8_t* yimg1;
     uint8_t* yimg2[2];  // double buffered: heads(k) runs beside the encoder of chunk k+1
     __half* ximg;
@@ -1036,6 +1137,7 @@ inline TensorWorkspace tensor_carve(void* base, int64_t B, int T, int W, int Kp,
     const size_t Wp = (size_t)std::max(W, 0);
     ws.gi_enc = reinterpret_cast<float*>(take(Bp * (size_t)enc_cols * 2 * G * sizeof(float)));
     ws.gi = reinterpret_cast<float*>(take(Bp * Wp * 2 * G * sizeof(float)));
+    ws.gi_b = reinterpret_cast<float*>(take(Bp * Wp * 2 * G * sizeof(float)));
     ws.yimg1 = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
     ws.yimg2[0] = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
     ws.yimg2[1] = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
@@ -1163,9 +1265,11 @@ inline void free_layer(TensorLayer* L) {
     cudaFree(L->wih_tmem); cudaFree(L->scale_row); cudaFree(L->bias_row); cudaFree(L->whh_tmem); cudaFree(L->gate_consts);
 }
 
-inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 128; }
+inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 2 * PROJ_STG_BYTES + 256; }
 template <int N>
-constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<N>() * N * GI_ROW_BYTES + 512; }
+constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<N, N, false>() * N * GI_ROW_BYTES + 512; }
+template <int NLIVE>   // chunk-loop kernel (N = 16, two gi' rows per window)
+constexpr size_t recurrence_smem_gi2() { return (size_t)2 * h_buffers<16>() * (16 / WG) * YBLK + (size_t)gi_stages<16, NLIVE, true>() * 2 * NLIVE * GI_ROW_BYTES + 512; }
 constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128; }
 
 }  // namespace detail
@@ -1224,19 +1328,20 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         };
         set((const void*)tc_projection_kernel<false>, detail::projection_smem(e->enc.Kp * 16, 1));
         set((const void*)tc_projection_kernel<true>, detail::projection_smem(YROW, 2));
-        set((const void*)tc_recurrence_kernel<16, 8, false>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<16, 16, false>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<16, 8, true>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<16, 16, true>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<32, 32, false>, detail::recurrence_smem<32>());
+        set((const void*)tc_recurrence_kernel<16, 8, 0>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 16, 0>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 8, 1>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 8, 2>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 16, 1>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<32, 32, 0>, detail::recurrence_smem<32>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
-        const size_t loop16 = std::max({detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
-        const size_t loop32 = std::max({detail::recurrence_smem<32>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
-        set((const void*)tc_chunkloop_kernel<16, 8, true>, loop16);
-        set((const void*)tc_chunkloop_kernel<16, 8, false>, loop16);
-        set((const void*)tc_chunkloop_kernel<16, 16, true>, loop16);
-        set((const void*)tc_chunkloop_kernel<16, 16, false>, loop16);
-        set((const void*)tc_chunkloop_kernel<32, 32, false>, loop32);
+        const size_t loop8 = std::max({detail::recurrence_smem_gi2<8>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
+        const size_t loop16 = std::max({detail::recurrence_smem_gi2<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
+        set((const void*)tc_chunkloop_kernel<16, 8, 1>, loop8);
+        set((const void*)tc_chunkloop_kernel<16, 8, 2>, loop8);
+        set((const void*)tc_chunkloop_kernel<16, 8, 0>, loop8);
+        set((const void*)tc_chunkloop_kernel<16, 16, 1>, loop16);
+        set((const void*)tc_chunkloop_kernel<16, 16, 0>, loop16);
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->proj_job_offsets), 256 * sizeof(int));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order16), 4096 * sizeof(int));
         e->flags_capacity = (size_t)1 << 16;
@@ -1274,7 +1379,7 @@ inline int pick_windows_per_cta(const TensorTuning& tune, int64_t B, int sm_coun
 struct ChunkloopPlan { int tile, rec_ctas, proj_workers, heads_workers; };
 inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, ChunkloopPlan* plan) {
     const int sms = sm_count / 2 * 2;                          // clusters of 2
-    for (int tile : {8, 16, 32}) {
+    for (int tile : {8, 16}) {                                 // (32 live windows leave no room for two gi' rows per window)
         if (tune.windows_per_cta && tile != tune.windows_per_cta) continue;
         if (tile == 8 && !tune.live8 && !tune.windows_per_cta) continue;
         const int64_t rec = (B + tile - 1) / tile;
@@ -1390,27 +1495,19 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg) {
             // projection job table: tile (group, tile) belongs to worker (group * tiles + tile) % workers; a worker takes
             // the halves of its tiles in the order the encoder makes them runnable (forward half of tile t after step
-            // 8t+8, reverse half after step W-8t); the earlier half of a tile is the "first" (writes), the other adds
-            struct Job { int ready, second, id, packed; };
+            // 8t+8, reverse half after step W-8t)
+            struct Job { int ready, id, packed; };
             std::vector<std::vector<Job>> per(plan.proj_workers);
             for (int64_t wg = 0; wg < n_wg; ++wg)
                 for (int t = 0; t < tiles8; ++t) {
                     const int id = (int)(wg * tiles8 + t);
-                    const int rf = std::min(8 * t + 8, W), rb = W - 8 * t;
-                    const int first_dir = rf <= rb ? 0 : 1;
-                    for (int d = 0; d < 2; ++d) {
-                        const int second = d == first_dir ? 0 : 1;
-                        per[id % plan.proj_workers].push_back({d == 0 ? rf : rb, second, id, pack_proj_job((int)wg, t, d, second)});
-                    }
+                    per[id % plan.proj_workers].push_back({std::min(8 * t + 8, W), id, pack_proj_job((int)wg, t, 0)});
+                    per[id % plan.proj_workers].push_back({W - 8 * t, id, pack_proj_job((int)wg, t, 1)});
                 }
             e->proj_jobs_host.clear();
             e->proj_job_offsets_host.assign(1, 0);
             for (auto& v : per) {
-                std::stable_sort(v.begin(), v.end(), [](const Job& x, const Job& y) {
-                    if (x.ready != y.ready) return x.ready < y.ready;
-                    if (x.second != y.second) return x.second < y.second;
-                    return x.id < y.id;
-                });
+                std::stable_sort(v.begin(), v.end(), [](const Job& x, const Job& y) { return x.ready != y.ready ? x.ready < y.ready : x.id < y.id; });
                 for (const Job& jb : v) e->proj_jobs_host.push_back(jb.packed);
                 e->proj_job_offsets_host.push_back((int)e->proj_jobs_host.size());
             }
@@ -1434,18 +1531,21 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         ra.layer[0] = layer_args(e->enc, ws.gi_enc, enc_cols, 0, J, ws.yimg1, ws.yimg1);
         ra.layer[0].progress = enc_prog; ra.layer[0].consumed_flags = tile_flags;
         ra.layer[1] = layer_args(e->dec, ws.gi, W, 0, 0, ws.yimg2[0], ws.yimg2[1]);
+        ra.layer[1].gi_b = ws.gi_b;
         ra.layer[1].progress = dec_prog; ra.layer[1].tile_flags = tile_flags;
         ra.layer[1].heads_done = heads_done; ra.layer[1].heads_per_chunk = 4 * tiles16;
         ra.n_layers = 2; ra.n_chunks = n_chunks; ra.h_in = nullptr; ra.h_out = nullptr; ra.B = B; ra.W = W;
         ra.tiles_t = tiles8; ra.n_wg = (int)n_wg; ra.epoch = 0; ra.dbg = dbg_buf; ra.dbg_layer = dbg_enc ? 0 : 1;
         ProjArgs pp = pd;
         pp.progress = enc_prog; pp.epoch = 0; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
-        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets;
+        pp.dbg = dbg_buf;
+        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets; pp.gi_b = ws.gi_b;
         HeadsArgs hp = heads_base;
         hp.yimg = ws.yimg2[0]; hp.yimg_odd = ws.yimg2[1]; hp.col0 = 0; hp.n_chunks = n_chunks;
         hp.progress = dec_prog; hp.rec_n = plan.tile; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
+        hp.dbg = dbg_buf;
         const dim3 grid(2 * plan.rec_ctas + 6 * plan.proj_workers + plan.heads_workers), cluster(pair_mode ? 2 : 1, 1, 1);
-        const size_t smem = std::max({plan.tile == 32 ? detail::recurrence_smem<32>() : detail::recurrence_smem<16>(),
+        const size_t smem = std::max({plan.tile == 8 ? detail::recurrence_smem_gi2<8>() : detail::recurrence_smem_gi2<16>(),
                                       detail::projection_smem(YROW, 2), detail::heads_smem()});
         auto go = [&](auto kernel) {
             const size_t slot = dominant_begin();
@@ -1453,9 +1553,12 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                                    ra, pp, hp, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
             dominant_end(slot);
         };
-        if (plan.tile == 8) { if (e->tune.stack) go(tc_chunkloop_kernel<16, 8, true>); else go(tc_chunkloop_kernel<16, 8, false>); }
-        else if (plan.tile == 16) { if (e->tune.stack) go(tc_chunkloop_kernel<16, 16, true>); else go(tc_chunkloop_kernel<16, 16, false>); }
-        else go(tc_chunkloop_kernel<32, 32, false>);
+        if (plan.tile == 8) {
+            if (e->tune.stack && e->tune.dual) go(tc_chunkloop_kernel<16, 8, 2>);
+            else if (e->tune.stack) go(tc_chunkloop_kernel<16, 8, 1>);
+            else go(tc_chunkloop_kernel<16, 8, 0>);
+        }
+        else { if (e->tune.stack) go(tc_chunkloop_kernel<16, 16, 1>); else go(tc_chunkloop_kernel<16, 16, 0>); }
         launches += 1;
     }
 
@@ -1480,13 +1583,13 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         if (e->time_recurrence) use_pdl = false;
         const bool stack = e->tune.stack;
         if (nrec == 8)
-            detail::launch(stack ? tc_recurrence_kernel<16, 8, true> : tc_recurrence_kernel<16, 8, false>, grid_rec, dim3(REC_TC_THREADS),
+            detail::launch(stack ? (e->tune.dual ? tc_recurrence_kernel<16, 8, 2> : tc_recurrence_kernel<16, 8, 1>) : tc_recurrence_kernel<16, 8, 0>, grid_rec, dim3(REC_TC_THREADS),
                            detail::recurrence_smem<16>(), s, use_pdl, ra);
         else if (nrec == 16)
-            detail::launch(stack ? tc_recurrence_kernel<16, 16, true> : tc_recurrence_kernel<16, 16, false>, grid_rec, dim3(REC_TC_THREADS),
+            detail::launch(stack ? tc_recurrence_kernel<16, 16, 1> : tc_recurrence_kernel<16, 16, 0>, grid_rec, dim3(REC_TC_THREADS),
                            detail::recurrence_smem<16>(), s, use_pdl, ra);
         else
-            detail::launch(tc_recurrence_kernel<32, 32, false>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl, ra);
+            detail::launch(tc_recurrence_kernel<32, 32, 0>, grid_rec, dim3(REC_TC_THREADS), detail::recurrence_smem<32>(), s, use_pdl, ra);
         dominant_end(slot);
     };
     e->last_plan = hb_launch_plan{};
@@ -1532,9 +1635,10 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                         plan.tile, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
                 fprintf(stderr, "[CTA 0 fwd, us since encoder phase 0 start]\n");
                 for (int k = 0; k < std::min(n_chunks, 6); ++k)
-                    fprintf(stderr, "  chunk %d: enc %.1f -> %.1f   dec %.1f -> %.1f\n", k,
+                    fprintf(stderr, "  chunk %d: enc %.1f -> %.1f   dec %.1f -> %.1f   projection worker 0 done %.1f   heads worker 0 done %.1f\n", k,
                             (hbuf[4096 + k * 2] - t0) * 1e-3, (hbuf[4096 + k * 2 + 1] - t0) * 1e-3,
-                            (hbuf[4096 + (64 + k) * 2] - t0) * 1e-3, (hbuf[4096 + (64 + k) * 2 + 1] - t0) * 1e-3);
+                            (hbuf[4096 + (64 + k) * 2] - t0) * 1e-3, (hbuf[4096 + (64 + k) * 2 + 1] - t0) * 1e-3,
+                            (hbuf[7000 + k] - t0) * 1e-3, (hbuf[7100 + k] - t0) * 1e-3);
                 for (int li = 0; li < 2; ++li) {
                     const long long* st = &hbuf[6144 + li * 8];
                     fprintf(stderr, "  chunk 2 %s phase, cycles after phase start: first step released %lld | last step done %lld | last image "
