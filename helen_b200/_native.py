@@ -7,7 +7,8 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint8, c_void_p
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhelen_b200.so")
+# HB_LIB: another build of the same library (A/B measurements of compile-time variants, tools/build_variants.py)
+LIB_PATH = os.environ.get("HB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhelen_b200.so")
 
 HB_ABI_VERSION = 2
 HB_OK = 0

@@ -31,15 +31,18 @@ def is_stale():
     return any(os.path.getmtime(p) > t for p in _sources())
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    """Compile helen_b200/csrc/hb_api.cu -> helen_b200/lib/libhelen_b200.so."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile helen_b200/csrc/hb_api.cu -> helen_b200/lib/libhelen_b200.so (or `out`, for experiment variants)."""
+    if out is None and os.environ.get("HB_LIB"):
+        return os.environ["HB_LIB"]                    # a prebuilt variant is in use: leave it alone
+    if out is None and not force and not is_stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build libhelen_b200.so")
     os.makedirs(LIB_DIR, exist_ok=True)
-    tmp = LIB + ".tmp"
+    target = out or LIB
+    tmp = target + ".tmp"
     extra_flags = list(extra_flags)
     if not os.path.exists(os.path.join(PKG, "csrc", "tensor_engine.cuh")):
         extra_flags.append("-DHB_NO_TENSOR_ENGINE")
@@ -49,8 +52,8 @@ def build(force=False, verbose=False, extra_flags=()):
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         sys.stderr.write(proc.stdout + proc.stderr)
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, target)
+    return target
 
 
 if __name__ == "__main__":

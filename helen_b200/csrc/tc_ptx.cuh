@@ -89,10 +89,16 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 __device__ __forceinline__ void red_release_gpu_add(unsigned long long* p, unsigned long long v) {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void spin_until_ge(const unsigned long long* flag, unsigned long long need) {
     while (ld_acquire_gpu(flag) < need) __nanosleep(100);
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read_pending() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
 template <int kPending>
 __device__ __forceinline__ void bulk_wait_pending() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory"); }
 

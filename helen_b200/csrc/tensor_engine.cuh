@@ -13,7 +13,8 @@
 // memory, so a tile is staged with a handful of 1-D bulk async copies (TMA engine, cp.async.bulk)
 // and no thread ever touches it:
 //   ximg : [window group][column t][K/8 k-groups][8 windows][8 k]          (pixels, exact fp16)
-//   yimg : [window group][column t][hi, lo][direction][16 k-groups x 144 B] (GRU outputs * 2^10)
+//   yimg : [window group][direction][hi, lo][column t][16 k-groups x 144 B] (GRU outputs * 2^10); consecutive columns of
+//          one (group, direction, part) are contiguous, so a tile of columns is ONE bulk copy per direction and part
 // Weights are the stationary operand: for the GRU contractions they live in tensor memory (TMEM)
 // as the A operand (M = 128 gate rows); a thread's TMEM lane is "its" gate row / hidden unit.
 #pragma once
@@ -23,6 +24,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,7 +44,7 @@ constexpr int WG = 8;                             // windows per window group ==
 constexpr int H_LBO = 144;                        // k-group stride of h / y images: 128 B core matrix + 16 B pad,
                                                   // so the gate threads' 2-byte stores spread over all banks
 constexpr int YBLK = 16 * H_LBO;                  // 2304 B: [8 windows x 128 k] fp16 image of one direction
-constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)
+constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)  [sizes only]
 constexpr int GI_ROW_BYTES = G * 4;               // 1536 B: gi of one (window, t, direction)
 // gi' lives in global memory as a "gi image": [window group][column][direction][gate r,z,n][8 windows][128 units] fp32,
 // so that what one recurrence step needs (all gates of a window group's column and direction, 12 KB) and what one
@@ -70,7 +72,7 @@ __host__ __device__ constexpr size_t whh_word_index(int dir, int term, int gb, i
     return (((((((size_t)dir * 2 + term) * 3 + gb) * 4 + (row >> 5)) * 2 + (c >> 5)) * 8 + ((c >> 2) & 7)) * 32 + (row & 31)) * 4 + (c & 3);
 }
 
-__host__ __device__ constexpr int64_t yimg_block(int64_t wg, int t, int W, int part) { return ((wg * W + t) * 2 + part) * (int64_t)YROW; }
+__host__ __device__ constexpr int64_t yimg_block(int64_t wg, int dir, int part, int t, int W) { return (((wg * 2 + dir) * 2 + part) * W + t) * (int64_t)YBLK; }
 
 // ---------------------------------------------------------------------------------------------
 // uint8 pileup -> fp16 operand image (once per batch; predict_gpu.py:97 does this cast on the host)
@@ -111,13 +113,17 @@ pileup_to_operand_image_kernel(const uint8_t* __restrict__ images, int64_t B, in
 constexpr int PROJ_THREADS = 224;                // warps 0-3 epilogue, 4 MMA issuer, 5 tile loader, 6 gi' store
 constexpr int PROJ_NT = 64;
 constexpr int PROJ_STG_BYTES = PROJ_NT * 128 * 4;   // fp32 staging of one tile's output block: [64 (column, window)][128 gate rows]
-constexpr int PROJ_STAGES = 2;
+constexpr int PROJ_STAGES = 2;                    // full-K tiles; the K-half jobs of the chunk-loop kernel are half as large: 4 stages
 constexpr int PROJ_PUBLISH_BATCH = 8;
 constexpr int PROJ_W_COL0 = 128;
 
 struct ProjArgs {
-    const uint8_t* in_base; int64_t in_wg_stride, in_t_stride, in_part_stride;   // operand image addressing (bytes)
-    int blk_bytes, lbo, Kp; int64_t n_wg; int W;
+    // operand image addressing (bytes): block of (group wg, K-slice d, part p, column t) at
+    // in_base + wg * in_wg_stride + d * in_dir_stride + p * in_part_stride + t * blk_bytes  (columns contiguous)
+    const uint8_t* in_base; int64_t in_wg_stride, in_dir_stride, in_part_stride;
+    int blk_bytes;                 // one (group, column) block of ONE K-slice
+    int n_dirs;                    // K-slices per column: 2 for the GRU output image (forward | reverse units), 1 for pixels
+    int lbo, Kp; int64_t n_wg; int W;
     const uint32_t* w_tmem;        // packed fp16 pairs, see wih_word_index
     const float* scale_row;        // [768]
     const float* bias_row;         // [768]
@@ -166,21 +172,25 @@ template <bool kSplitA>
 __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem, const int blk, const int worker, const int n_workers)
 {
     const uint8_t* __restrict__ in_base = a.in_base;
-    const int64_t in_wg_stride = a.in_wg_stride, in_t_stride = a.in_t_stride, in_part_stride = a.in_part_stride;
+    const int64_t in_wg_stride = a.in_wg_stride, in_dir_stride = a.in_dir_stride, in_part_stride = a.in_part_stride;
     const int lbo = a.lbo, Kp = a.Kp, W = a.W;
     const bool split = a.jobs != nullptr;
-    const int blk_bytes = split ? YBLK : a.blk_bytes;       // bytes of one (window group, column) block in a stage
+    const int blk_bytes = a.blk_bytes;
+    const int n_dirs = split ? 1 : a.n_dirs;                 // K-slices per stage
     const uint32_t* __restrict__ w_tmem = a.w_tmem;
     const float* __restrict__ scale_row = a.scale_row;
     const float* __restrict__ bias_row = a.bias_row;
     float* __restrict__ gi = a.gi;
     constexpr int PARTS = kSplitA ? 2 : 1;
-    const uint32_t part_bytes = 8u * blk_bytes;              // 8 row groups (columns t0..t0+7)
-    const uint32_t stage_bytes = PARTS * 8u * a.blk_bytes;   // allocation (full K)
-    uint8_t* staging = smem + PROJ_STAGES * stage_bytes;     // [2][PROJ_STG_BYTES]
+    // stage: [part hi, lo][K-slice][8 row groups = columns t0..t0+7][blk_bytes]
+    const uint32_t slice_bytes = 8u * blk_bytes;
+    const uint32_t part_bytes = n_dirs * slice_bytes;
+    const uint32_t stage_bytes = PARTS * part_bytes;
+    const int n_stages = split ? 2 * PROJ_STAGES : PROJ_STAGES;   // same allocation: PROJ_STAGES full-K stages
+    uint8_t* staging = smem + PROJ_STAGES * PARTS * a.n_dirs * 8u * a.blk_bytes;     // [2][PROJ_STG_BYTES]
     uint64_t* a_full = reinterpret_cast<uint64_t*>(staging + 2 * PROJ_STG_BYTES);
-    uint64_t* a_empty = a_full + PROJ_STAGES;
-    uint64_t* acc_full = a_empty + PROJ_STAGES;
+    uint64_t* a_empty = a_full + 2 * PROJ_STAGES;
+    uint64_t* acc_full = a_empty + 2 * PROJ_STAGES;
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* stg_full = acc_empty + 2;                      // [2]: the 4 epilogue warps have written the staging buffer
     uint64_t* stg_empty = stg_full + 2;                      // [2]: its bulk copies have read it
@@ -190,7 +200,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     const int kwords = Kp >> 1;
     tc::pdl_launch_dependents();
     if (tid == 0) {
-        for (int i = 0; i < PROJ_STAGES; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, a.pair ? 2 : 1); }
+        for (int i = 0; i < n_stages; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, a.pair ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(stg_full + i, 4); tc::mbar_init(stg_empty + i, 1); }
         tc::mbar_fence_init();
@@ -233,42 +243,66 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 
     const int n_chunks = a.n_chunks > 0 ? a.n_chunks : 1;
     ProjJob j;
+    // HB_DEBUG_TIMELINE: worker 0 / block 0 adds up the cycles each role spends at its wait points (slots 7200 + 8 role + k)
+    const bool acct = a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0;
+    long long t_wait[4] = {0, 0, 0, 0};
+    long long t_role0 = acct ? clock64() : 0;
+#define HB_TIMED(k, stmt) do { const long long t_ = acct ? clock64() : 0; stmt; if (acct) t_wait[k] += clock64() - t_; } while (0)
+#define HB_ROLE_REPORT(role) do { if (acct) { for (int k_ = 0; k_ < 4; ++k_) a.dbg[7200 + 8 * (role) + k_] = t_wait[k_]; \
+                                              a.dbg[7200 + 8 * (role) + 4] = clock64() - t_role0; } } while (0)
     if (warp == 5) {
         // ===================== loader =====================
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
         for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
-            const int stage = it % PROJ_STAGES;
-            if (it >= PROJ_STAGES) tc::mbar_wait(a_empty + stage, (uint32_t)((it / PROJ_STAGES - 1) & 1));
+            const int stage = it % n_stages;
+            if (it >= n_stages) HB_TIMED(0, tc::mbar_wait(a_empty + stage, (uint32_t)((it / n_stages - 1) & 1)));
             if (a.progress != nullptr) {
                 // the source encoder direction must have stored the job's columns: forward past t0+valid-1, reverse past t0
                 if (lane == 0) {
                     const unsigned long long need = a.epoch + (unsigned long long)chunk * W + (unsigned long long)(j.src_dir == 0 ? j.t0 + j.valid : W - j.t0);
                     const unsigned long long* flag = a.progress + ((j.wg * WG) / a.rec_n) * 2 + j.src_dir;
-                    while (tc::ld_acquire_gpu(flag) < need) __nanosleep(100);
+                    HB_TIMED(1, while (tc::ld_acquire_gpu(flag) < need) __nanosleep(100));
                 }
-                tc::fence_proxy_async_all();
+                // No proxy fence here: the producer completed its bulk stores (wait_group), fenced and released the counter;
+                // our bulk loads are issued after the acquire in program order and read L2 directly.  (fence.proxy.async
+                // cost ~1000 cycles per job and made this warp the bottleneck of the role.)
+#ifdef HB_STRICT_PROXY_FENCE
+                HB_TIMED(2, tc::fence_proxy_async_all());
+#endif
                 __syncwarp();
             }
-            if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * PARTS * blk_bytes));
+            const long long t_issue = acct ? clock64() : 0;
+            if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * PARTS * n_dirs * blk_bytes));
             __syncwarp();
-            if (lane < 8 * PARTS) {
-                const int tl = lane & 7, part = lane >> 3;
-                uint8_t* dst = smem + stage * stage_bytes + part * part_bytes + tl * blk_bytes;
-                const uint8_t* src = in_base + j.wg * in_wg_stride + (int64_t)(j.t0 + tl) * in_t_stride + part * in_part_stride + (split ? j.src_dir * YBLK : 0);
-                if (tl < j.valid) {
-                    if (!a.pair) tc::bulk_g2s(dst, src, (uint32_t)blk_bytes, a_full + stage);
-                    else if ((uint32_t)(tl & 1) == pair_rank) tc::bulk_g2s_multicast(dst, src, (uint32_t)blk_bytes, a_full + stage, (uint16_t)3);
+            if (lane < 2 * PARTS * n_dirs) {
+                // the job's columns are contiguous per (part, K-slice); two copies of four columns each (one big copy is
+                // served by a single copy engine queue and was slower)
+                const int half = lane & 1, pd = lane >> 1, part = pd / n_dirs, d = pd % n_dirs;
+                const int cols = min(4, j.valid - 4 * half);
+                uint8_t* dst = smem + stage * stage_bytes + part * part_bytes + d * slice_bytes + half * 4 * blk_bytes;
+                const uint8_t* src = in_base + j.wg * in_wg_stride + (split ? j.src_dir : d) * in_dir_stride + part * in_part_stride + (int64_t)(j.t0 + 4 * half) * blk_bytes;
+                const uint32_t bytes = (uint32_t)(max(cols, 0) * blk_bytes);
+                // pair mode: the two CTAs split the copies and multicast them to both
+                const bool mine = cols > 0 && (!a.pair || (uint32_t)(lane & 1) == pair_rank);
+                if (mine) {
+                    if (a.pair) tc::bulk_g2s_multicast(dst, src, bytes, a_full + stage, (uint16_t)3);
+                    else tc::bulk_g2s(dst, src, bytes, a_full + stage);
                 }
             }
+            __syncwarp();
+            if (acct) t_wait[3] += clock64() - t_issue;
         }
+        HB_ROLE_REPORT(0);
     } else if (warp == 6) {
         // ===================== gi' store =====================
         // lane c < 8 copies column t0 + c of the staged block: [8 windows][128 gate rows] = 4 KB, contiguous in the gi image
         const int tiles_t = (W + 7) >> 3;
         // Flags are raised in batches: the release below is a gpu-scope fence (~1 us), one per job would make this warp
-        // the bottleneck of the role.  A batch goes out when PROJ_PUBLISH_BATCH jobs are waiting or the role runs dry
-        // (the consumers only wait for a chunk's LAST jobs, and those are followed by an idle period).
+        // the bottleneck of the role.  A batch goes out when PROJ_PUBLISH_BATCH jobs are waiting and after the worker's
+        // last job of a chunk (the decoder starts with the tiles that are projected last, and nothing else in the kernel
+        // waits for a flag while the same chunk's encoder is still feeding this worker).  Flushing whenever the warp
+        // ran dry was tried: it runs dry after almost every job, and each flush waits ~1.5 us for the newest copies.
         unsigned long long* pending[PROJ_PUBLISH_BATCH];     // flags of the jobs whose copies may still be in flight
         int n_pending = 0;
         auto publish = [&](int keep) {                       // wait until all but the newest `keep` (0 or 2) jobs have landed, raise their flags
@@ -276,8 +310,10 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             if (keep == 0) tc::bulk_wait0(); else tc::bulk_wait_pending<2>();
             tc::fence_proxy_async_all();
             __syncwarp();
-            for (int k = 0; k < n_pending - keep; ++k)
-                if (lane == 0 && pending[k] != nullptr) tc::red_release_gpu_add(pending[k], 1ull);
+            if (lane == 0) {                                 // ONE release fence for the whole batch, then relaxed increments
+                tc::fence_acq_rel_gpu();
+                for (int k = 0; k < n_pending - keep; ++k) tc::red_relaxed_gpu_add(pending[k], 1ull);
+            }
             for (int k = 0; k < keep; ++k) pending[k] = pending[n_pending - keep + k];
             n_pending = keep;
         };
@@ -286,25 +322,26 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
             const int sb = it & 1;
             const uint32_t par = (uint32_t)((it >> 1) & 1);
-            if (!tc::mbar_test_wait(stg_full + sb, par)) {   // nothing to store yet: do not sit on finished jobs
-                publish(0);
-                tc::mbar_wait(stg_full + sb, par);
-            }
+            HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
             float* out = j.src_dir ? a.gi_b : gi;
             if (lane < 8 && j.t0 + lane < W)
                 tc::bulk_s2g(out + gi_block(j.wg, W, j.t0 + lane, blk), staging + sb * PROJ_STG_BYTES + lane * (GI_BLK_FLOATS * 4), GI_BLK_FLOATS * 4);
             tc::bulk_commit();
-            tc::bulk_wait_read0();
+            // the PREVIOUS job's copies have read their staging buffer (this job's read overlaps the next epilogue)
+            HB_TIMED(1, tc::bulk_wait_read_pending<1>());
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(stg_empty + sb);
+            if (lane == 0 && it > 0) tc::mbar_arrive(stg_empty + (sb ^ 1));
             if (a.tile_flags != nullptr) {
                 pending[n_pending++] = a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
-                if (n_pending == PROJ_PUBLISH_BATCH) publish(2);   // copies issued two jobs ago have normally landed: no stall
+                ProjJob next;
+                if (!proj_job(a, worker, n_workers, idx + 1, next)) HB_TIMED(2, publish(0));         // last job of the chunk
+                else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2));   // copies issued two jobs ago have normally landed: no stall
             }
             if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
         }
         publish(0);
         if (lane < 32) tc::bulk_wait0();                     // the kernel's results are complete when the role returns
+        HB_ROLE_REPORT(3);
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
@@ -312,9 +349,9 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
         for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
-            const int stage = it % PROJ_STAGES, acc = it & 1;
-            tc::mbar_wait(a_full + stage, (uint32_t)((it / PROJ_STAGES) & 1));
-            if (it >= 2) tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1));
+            const int stage = it % n_stages, acc = it & 1;
+            HB_TIMED(0, tc::mbar_wait(a_full + stage, (uint32_t)((it / n_stages) & 1)));
+            if (it >= 2) HB_TIMED(1, tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1)));
             tc::tc_fence_after();
             if (tc::elect_one()) {
                 const uint32_t sbase = tc::smem_u32(smem + stage * stage_bytes);
@@ -322,17 +359,32 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 const uint64_t d_lo = tc::smem_desc(sbase + part_bytes, lbo, blk_bytes);
                 const uint32_t a_hi = tmem + PROJ_W_COL0 + (split ? j.src_dir * 64 : 0), a_lo = a_hi + kwords;
                 const uint32_t d = tmem + acc * PROJ_NT;
-                uint32_t accum = 0;
-                for (int ks = 0; ks < ksteps; ++ks) { tc::mma_f16_ts(d, a_hi + ks * 8, d_hi + (uint64_t)(ks * 2 * lbo / 16), idesc, accum); accum = 1; }
-                for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16_ts(d, a_lo + ks * 8, d_hi + (uint64_t)(ks * 2 * lbo / 16), idesc, 1);
-                if (kSplitA)
-                    for (int ks = 0; ks < ksteps; ++ks) tc::mma_f16_ts(d, a_hi + ks * 8, d_lo + (uint64_t)(ks * 2 * lbo / 16), idesc, 1);
+                // Issue loops with compile-time trip counts for the two hot shapes: the operands of every MMA are then
+                // immediates on the uniform datapath (a runtime k loop went through R2UR moves: ~80 cycles per MMA).
+                // k-step ks of the stage: K-slice ks / 8 (a slice of the GRU output image is 128 units), then 16 units per step
+                auto issue = [&](auto ksteps_c, auto dirs_c) {
+                    constexpr int KS = decltype(ksteps_c)::value, ND = decltype(dirs_c)::value;
+                    const int ks_n = KS > 0 ? KS : ksteps;
+                    auto koff = [&](int ks) { return (uint64_t)((ND == 2 ? (ks >> 3) * slice_bytes + (ks & 7) * 2 * lbo : ks * 2 * lbo) / 16); };
+#pragma unroll
+                    for (int ks = 0; ks < ks_n; ++ks) tc::mma_f16_ts(d, a_hi + ks * 8, d_hi + koff(ks), idesc, ks != 0);
+#pragma unroll
+                    for (int ks = 0; ks < ks_n; ++ks) tc::mma_f16_ts(d, a_lo + ks * 8, d_hi + koff(ks), idesc, 1);
+                    if (kSplitA) {
+#pragma unroll
+                        for (int ks = 0; ks < ks_n; ++ks) tc::mma_f16_ts(d, a_hi + ks * 8, d_lo + koff(ks), idesc, 1);
+                    }
+                };
+                if (split) issue(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
+                else if (n_dirs == 2 && ksteps == 16) issue(std::integral_constant<int, 16>{}, std::integral_constant<int, 2>{});
+                else issue(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});     // pixels: K = padded feature count
                 if (a.pair) tc::mma_commit_multicast(a_empty + stage, (uint16_t)3);   // both loaders wait for both consumers
                 else tc::mma_commit(a_empty + stage);
                 tc::mma_commit(acc_full + acc);
             }
             __syncwarp();
         }
+        HB_ROLE_REPORT(1);
     } else {
         // ===================== epilogue =====================
         const int r = warp * 32 + lane;                      // gate row within the block == TMEM lane
@@ -341,8 +393,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         for (int chunk = 0; chunk < n_chunks; ++chunk)
         for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
             const int acc = it & 1, sb = it & 1;
-            if (it >= 2) tc::mbar_wait(stg_empty + sb, (uint32_t)((it / 2 - 1) & 1));
-            tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1));
+            if (it >= 2) HB_TIMED(0, tc::mbar_wait(stg_empty + sb, (uint32_t)((it / 2 - 1) & 1)));   // arrives once job it-1 is being stored
+            HB_TIMED(1, tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1)));
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
             float* stg = reinterpret_cast<float*>(staging + sb * PROJ_STG_BYTES) + r;
@@ -360,7 +412,10 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(acc_empty + acc); tc::mbar_arrive(stg_full + sb); }
         }
+        if (warp == 0) HB_ROLE_REPORT(2);
     }
+#undef HB_TIMED
+#undef HB_ROLE_REPORT
     tc::tc_fence_before();
     tc::named_barrier_sync(1, PROJ_THREADS);
     if (a.pair) tc::cluster_sync_all();                      // no multicast / remote arrive may target a CTA that has exited
@@ -443,10 +498,10 @@ struct RecArgs {
 // only the two A terms W_hi and W_lo (48 MMAs instead of 72; the MMA time of a step is set by the instruction count,
 // not by N, at these sizes).  Accumulator columns [0, NLIVE) hold W.h_hi, [NLIVE, 2 NLIVE) hold W.h_lo; the gate
 // threads add the two.  That is the full 4-term product (W_lo.h_lo included).
+// (Measured and dropped: two accumulators per gate block, W_hi and W_lo MMAs issued alternately so that consecutive MMAs
+// do not accumulate into the same tile - the MMAs were no faster and the extra TMEM loads cost 90 cycles per step.)
 //
-// MODE 0: 3-term.  MODE 1: STACK.  MODE 2: STACK with two accumulators per gate block (NLIVE = 8 only): the W_hi and
-// the W_lo MMAs of a k-step go to different TMEM columns and are issued alternately, so consecutive MMAs do not
-// accumulate into the same tile (a chain of 16 dependent accumulations ran at ~15 cycles per MMA).
+// MODE 0: 3-term.  MODE 1: STACK.
 template <int N, int NLIVE, int MODE = 0, bool GI2 = false>
 __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem, const int cta_x, const int dir)
 {
@@ -458,11 +513,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 #define HB_DBG(role, s, k) do { if (dbg_steps && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N accumulator columns per gate block (3N must stay below REC_W_COL0)");
     static_assert(NLIVE == N || (N == 16 && NLIVE == 8), "live windows per CTA");
-    constexpr bool STACK = MODE >= 1, DUAL = MODE == 2;
+    constexpr bool STACK = MODE >= 1;
     static_assert(!STACK || N == 16, "stacked operand: 3 x 2 NLIVE accumulator columns must stay below REC_W_COL0");
-    static_assert(!DUAL || NLIVE == 8, "two accumulators per gate block: 3 x 2 x 16 columns");
-    constexpr int NACC = STACK ? 2 * NLIVE : N;              // N of the MMA
-    constexpr int NBLK = DUAL ? 2 * NACC : NACC;             // accumulator columns per gate block
+    constexpr int NACC = STACK ? 2 * NLIVE : N;              // N of the MMA == accumulator columns per gate block
+    constexpr int NBLK = NACC;
     constexpr int NW = NLIVE / 4;                            // windows per gate thread
     constexpr int NG = NLIVE / WG;                           // live window groups per CTA
     constexpr uint32_t HB_BYTES = (N / WG) * YBLK;           // one h operand image (hi or lo), all N columns
@@ -474,6 +528,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     constexpr int NBUF = h_buffers<N>();
     uint8_t* h_img = smem;                                   // [NBUF buffers][hi, lo][HB_BYTES]
     uint8_t* gi_s = smem + 2 * NBUF * HB_BYTES;
+    // (Measured and dropped: one commit barrier per group of four gate warps - the extra commits delayed every
+    // accumulator by ~90 cycles and the last gate warp was as late as before.)
     uint64_t* acc_ready = reinterpret_cast<uint64_t*>(gi_s + GI_STAGES * GI_STAGE_BYTES);   // [3]: r, z, n blocks
     uint64_t* h_ready = acc_ready + 3;
     uint64_t* h_free = h_ready + 1;                          // [NBUF], one per buffer: its y store has drained
@@ -600,7 +656,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::mbar_wait(y_ready + buf, (uint32_t)((s / NBUF) & 1));
             if (lane < 2 * NG) {
                 const int g = lane >> 1, part = lane & 1;
-                tc::bulk_s2g(yimg + yimg_block(b0 / WG + g, t, W, part) + dir * YBLK, h_img + (buf * 2 + part) * HB_BYTES + g * YBLK, YBLK);
+                tc::bulk_s2g(yimg + yimg_block(b0 / WG + g, dir, part, t, W), h_img + (buf * 2 + part) * HB_BYTES + g * YBLK, YBLK);
                 tc::bulk_commit();
                 tc::bulk_wait_read0();
             }
@@ -644,14 +700,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (tc::elect_one()) {
 #pragma unroll
                 for (int gb = 0; gb < 3; ++gb) {             // gate blocks r, z, n
-                    if constexpr (DUAL) {
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                            for (int term = 0; term < 2; ++term)     // W_hi -> columns [0, 16), W_lo -> [16, 32) of the block
-                                tc::mma_f16_ts(tmem + gb * NBLK + term * NACC, tmem + REC_W_COL0 + (term * 3 + gb) * 64 + ks * 8,
-                                               hhi_desc + (uint64_t)(ks * 2 * H_LBO / 16), idesc, ks != 0);
-                    } else if constexpr (STACK) {
+                    if constexpr (STACK) {
 #pragma unroll
                         for (int term = 0; term < 2; ++term) {   // W_hi, W_lo against [h_hi | h_lo]
                             const uint32_t a_col = tmem + REC_W_COL0 + (term * 3 + gb) * 64;
@@ -728,15 +777,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
         auto load_acc = [](uint32_t addr, float* a) {
             tc::tmem_ld_n<NW>(addr, a);
-            if constexpr (DUAL) {
-                float b1[NW], b2[NW], b3[NW];
-                tc::tmem_ld_n<NW>(addr + NLIVE, b1);
-                tc::tmem_ld_n<NW>(addr + NACC, b2);
-                tc::tmem_ld_n<NW>(addr + NACC + NLIVE, b3);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < NW; ++i) a[i] = (a[i] + b1[i]) + (b2[i] + b3[i]);
-            } else if constexpr (STACK) {
+            if constexpr (STACK) {
                 float a_lo[NW];
                 tc::tmem_ld_n<NW>(addr + NLIVE, a_lo);
                 tc::tmem_ld_wait();
@@ -791,6 +832,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (drole < 3) HB_DBG(drole, s, 4);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
+                // (2^x as a degree-7 polynomial on the FMA pipe instead of MUFU.EX2 was measured: +50 cycles per step)
                 const float e = tc::ex2_approx(fmaf(r[i], fmaf(a[i], inv_n, bhn), gin[i]));
                 const float n = fmaf(2.0f * ACT_SCALE, tc::rcp_approx(1.0f + e), -ACT_SCALE);   // tanh * 2^10
                 const float hn = fmaf(z[i], h_own[i] - n, n);                                   // (1 - z) n + z h
@@ -879,8 +921,9 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
 {
     const int W = a.W, T = a.T;
     const int64_t B = a.B;
-    constexpr uint32_t PART_BYTES = 16 * YROW;                  // 16 columns of one window group
-    uint8_t* a_img = smem;                                      // [hi, lo][16 row groups][YROW]
+    constexpr uint32_t SLICE_BYTES = 16 * YBLK;                 // 16 columns of one (window group, direction, part)
+    constexpr uint32_t PART_BYTES = 2 * SLICE_BYTES;
+    uint8_t* a_img = smem;                                      // [hi, lo][direction][16 row groups][YBLK]
     uint8_t* w_s = smem + 2 * PART_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(w_s + 2 * HEADS_WIMG);
     uint64_t* a_empty = a_full + 1;
@@ -921,8 +964,12 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             const uint8_t* img = ((chunk & 1) && a.yimg_odd) ? a.yimg_odd : a.yimg;
             if (lane == 0) tc::mbar_arrive_expect_tx(a_full, (uint32_t)(valid * 2 * YROW));
             __syncwarp();
-            const int tl = lane & 15, part = lane >> 4;
-            if (tl < valid) tc::bulk_g2s(a_img + part * PART_BYTES + tl * YROW, img + yimg_block(wg, t0 + tl, W, part), YROW, a_full);
+            if (lane < 16) {                                 // four copies of four columns per (part, direction); columns are contiguous
+                const int q4 = lane & 3, part = lane >> 3, d = (lane >> 2) & 1;
+                const int cols = min(4, valid - 4 * q4);
+                if (cols > 0)
+                    tc::bulk_g2s(a_img + part * PART_BYTES + d * SLICE_BYTES + q4 * 4 * YBLK, img + yimg_block(wg, d, part, t0 + 4 * q4, W), (uint32_t)(cols * YBLK), a_full);
+            }
         }
     } else if (warp == 4) {
         const uint32_t idesc = tc::idesc_f16_f32(128, NCLS);
@@ -931,12 +978,17 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             if (it > 0) tc::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
             tc::tc_fence_after();
             if (tc::elect_one()) {
-                const uint64_t a_hi = tc::smem_desc(tc::smem_u32(a_img), H_LBO, YROW), a_lo = tc::smem_desc(tc::smem_u32(a_img + PART_BYTES), H_LBO, YROW);
+                const uint64_t a_hi = tc::smem_desc(tc::smem_u32(a_img), H_LBO, YBLK), a_lo = tc::smem_desc(tc::smem_u32(a_img + PART_BYTES), H_LBO, YBLK);
                 const uint64_t w_hi = tc::smem_desc(tc::smem_u32(w_s), 128, 4096), w_lo = tc::smem_desc(tc::smem_u32(w_s + HEADS_WIMG), 128, 4096);
+                // k-step ks: direction ks / 8 (forward units are k < 128), then (ks % 8) * 16 units into its slice
+                auto koff = [](int ks) { return (uint64_t)(((ks >> 3) * SLICE_BYTES + (ks & 7) * 2 * H_LBO) / 16); };
                 uint32_t accum = 0;
-                for (int ks = 0; ks < 16; ++ks) { tc::mma_f16_ss(tmem, a_hi + (uint64_t)(ks * 2 * H_LBO / 16), w_hi + (uint64_t)(ks * 16), idesc, accum); accum = 1; }
-                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(tmem, a_lo + (uint64_t)(ks * 2 * H_LBO / 16), w_hi + (uint64_t)(ks * 16), idesc, 1);
-                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(tmem, a_hi + (uint64_t)(ks * 2 * H_LBO / 16), w_lo + (uint64_t)(ks * 16), idesc, 1);
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) { tc::mma_f16_ss(tmem, a_hi + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, accum); accum = 1; }
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(tmem, a_lo + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, 1);
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(tmem, a_hi + koff(ks), w_lo + (uint64_t)(ks * 16), idesc, 1);
                 tc::mma_commit(a_empty);
                 tc::mma_commit(acc_full);
             }
@@ -1058,7 +1110,6 @@ struct TensorTuning {
     bool pdl = true;            // HB_NO_PDL: no programmatic dependent launch
     bool pair = true;           // HB_NO_PAIR: projection without 2-CTA multicast clusters
     bool stack = true;          // HB_NO_STACK: 3-term recurrence MMAs instead of the stacked [h_hi | h_lo] operand
-    bool dual = true;           // HB_NO_DUAL: one accumulator per gate block in the 8-window stacked tile
     bool live8 = true;          // HB_NO_LIVE8: never use the 8-live-window recurrence tile
     int windows_per_cta = 0;    // HB_WINDOWS_PER_CTA = 8 | 16 | 32: force the recurrence tile
     bool chunkloop = true;      // HB_NO_CHUNKLOOP: per-chunk launches even when the whole chunk loop fits on the chip
@@ -1068,7 +1119,6 @@ struct TensorTuning {
         t.pdl = getenv("HB_NO_PDL") == nullptr;
         t.pair = getenv("HB_NO_PAIR") == nullptr;
         t.stack = getenv("HB_NO_STACK") == nullptr;
-        t.dual = getenv("HB_NO_DUAL") == nullptr;
         t.live8 = getenv("HB_NO_LIVE8") == nullptr;
         t.chunkloop = getenv("HB_NO_CHUNKLOOP") == nullptr;
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
@@ -1331,14 +1381,12 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_recurrence_kernel<16, 8, 0>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<16, 16, 0>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<16, 8, 1>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<16, 8, 2>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<16, 16, 1>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<32, 32, 0>, detail::recurrence_smem<32>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
         const size_t loop8 = std::max({detail::recurrence_smem_gi2<8>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
         const size_t loop16 = std::max({detail::recurrence_smem_gi2<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
         set((const void*)tc_chunkloop_kernel<16, 8, 1>, loop8);
-        set((const void*)tc_chunkloop_kernel<16, 8, 2>, loop8);
         set((const void*)tc_chunkloop_kernel<16, 8, 0>, loop8);
         set((const void*)tc_chunkloop_kernel<16, 16, 1>, loop16);
         set((const void*)tc_chunkloop_kernel<16, 16, 0>, loop16);
@@ -1424,7 +1472,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         pileup_to_operand_image_kernel<<<blocks, 256, 0, s>>>(images, B, T, F, e->enc.Kp, ws.ximg, n_wg);
         const int tiles = (int)std::min<int64_t>(n_wg * ((enc_cols + 7) / 8), proj_workers);
         ProjArgs pe{};
-        pe.in_base = reinterpret_cast<const uint8_t*>(ws.ximg); pe.in_wg_stride = (int64_t)T * xblk; pe.in_t_stride = xblk; pe.in_part_stride = 0;
+        pe.in_base = reinterpret_cast<const uint8_t*>(ws.ximg); pe.in_wg_stride = (int64_t)T * xblk; pe.in_dir_stride = 0; pe.in_part_stride = 0; pe.n_dirs = 1;
         pe.blk_bytes = xblk; pe.lbo = 128; pe.Kp = e->enc.Kp; pe.n_wg = n_wg; pe.W = enc_cols;
         pe.w_tmem = e->enc.wih_tmem; pe.scale_row = e->enc.scale_row; pe.bias_row = e->enc.bias_row; pe.gi = ws.gi_enc;
         pe.pair = pair_mode;
@@ -1438,8 +1486,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     if (dbg_on && !dbg_buf) { cudaMalloc(&dbg_buf, 8192 * sizeof(long long)); cudaMemset(dbg_buf, 0, 8192 * sizeof(long long)); }
     // decoder projection arguments (the same for every chunk)
     ProjArgs pd{};
-    pd.in_base = ws.yimg1; pd.in_wg_stride = (int64_t)W * 2 * YROW; pd.in_t_stride = 2 * YROW; pd.in_part_stride = YROW;
-    pd.blk_bytes = YROW; pd.lbo = H_LBO; pd.Kp = e->dec.Kp; pd.n_wg = n_wg; pd.W = W;
+    pd.in_base = ws.yimg1; pd.in_wg_stride = (int64_t)W * 4 * YBLK; pd.in_dir_stride = (int64_t)W * 2 * YBLK; pd.in_part_stride = (int64_t)W * YBLK;
+    pd.blk_bytes = YBLK; pd.n_dirs = 2; pd.lbo = H_LBO; pd.Kp = e->dec.Kp; pd.n_wg = n_wg; pd.W = W;
     pd.w_tmem = e->dec.wih_tmem; pd.scale_row = e->dec.scale_row; pd.bias_row = e->dec.bias_row; pd.gi = ws.gi;
     pd.pair = pair_mode;
     const int n_chunks = T < W ? 0 : (T - W) / J + 1;
@@ -1553,11 +1601,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                                    ra, pp, hp, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
             dominant_end(slot);
         };
-        if (plan.tile == 8) {
-            if (e->tune.stack && e->tune.dual) go(tc_chunkloop_kernel<16, 8, 2>);
-            else if (e->tune.stack) go(tc_chunkloop_kernel<16, 8, 1>);
-            else go(tc_chunkloop_kernel<16, 8, 0>);
-        }
+        if (plan.tile == 8) { if (e->tune.stack) go(tc_chunkloop_kernel<16, 8, 1>); else go(tc_chunkloop_kernel<16, 8, 0>); }
         else { if (e->tune.stack) go(tc_chunkloop_kernel<16, 16, 1>); else go(tc_chunkloop_kernel<16, 16, 0>); }
         launches += 1;
     }
@@ -1583,7 +1627,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         if (e->time_recurrence) use_pdl = false;
         const bool stack = e->tune.stack;
         if (nrec == 8)
-            detail::launch(stack ? (e->tune.dual ? tc_recurrence_kernel<16, 8, 2> : tc_recurrence_kernel<16, 8, 1>) : tc_recurrence_kernel<16, 8, 0>, grid_rec, dim3(REC_TC_THREADS),
+            detail::launch(stack ? tc_recurrence_kernel<16, 8, 1> : tc_recurrence_kernel<16, 8, 0>, grid_rec, dim3(REC_TC_THREADS),
                            detail::recurrence_smem<16>(), s, use_pdl, ra);
         else if (nrec == 16)
             detail::launch(stack ? tc_recurrence_kernel<16, 16, 1> : tc_recurrence_kernel<16, 16, 0>, grid_rec, dim3(REC_TC_THREADS),
@@ -1639,6 +1683,18 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                             (hbuf[4096 + k * 2] - t0) * 1e-3, (hbuf[4096 + k * 2 + 1] - t0) * 1e-3,
                             (hbuf[4096 + (64 + k) * 2] - t0) * 1e-3, (hbuf[4096 + (64 + k) * 2 + 1] - t0) * 1e-3,
                             (hbuf[7000 + k] - t0) * 1e-3, (hbuf[7100 + k] - t0) * 1e-3);
+                {
+                    const char* role[4] = {"loader  ", "MMA     ", "epilogue", "store   "};
+                    const char* what[4][4] = {{"a_empty", "progress", "proxy fence", "issue copies"}, {"a_full", "acc_empty", "-", "-"},
+                                              {"stg_empty", "acc_full", "-", "-"}, {"stg_full", "smem read", "chunk-end flush", "batch publish"}};
+                    fprintf(stderr, "  projection worker 0 / block 0, cycles waiting over the whole launch (%d chunks):\n", n_chunks);
+                    for (int r = 0; r < 4; ++r) {
+                        const long long* w = &hbuf[7200 + 8 * r];
+                        fprintf(stderr, "    %s total %lld:", role[r], w[4]);
+                        for (int k = 0; k < 4; ++k) fprintf(stderr, "  %s %lld", what[r][k], w[k]);
+                        fprintf(stderr, "\n");
+                    }
+                }
                 for (int li = 0; li < 2; ++li) {
                     const long long* st = &hbuf[6144 + li * 8];
                     fprintf(stderr, "  chunk 2 %s phase, cycles after phase start: first step released %lld | last step done %lld | last image "

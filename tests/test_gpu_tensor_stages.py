@@ -31,8 +31,6 @@ def test_stage_matches_fp32_engine(engine, batch, seq, features):
 VARIANTS = {
     "tile8_stacked": {"HB_WINDOWS_PER_CTA": "8"},
     "tile8_3term": {"HB_WINDOWS_PER_CTA": "8", "HB_NO_STACK": "1"},
-    "tile8_stacked_single_accumulator": {"HB_WINDOWS_PER_CTA": "8", "HB_NO_DUAL": "1"},
-    "per_chunk_tile8_single_accumulator": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "8", "HB_NO_DUAL": "1"},
     "tile16_stacked": {"HB_WINDOWS_PER_CTA": "16"},
     "tile16_3term": {"HB_WINDOWS_PER_CTA": "16", "HB_NO_STACK": "1"},
     "tile32": {"HB_WINDOWS_PER_CTA": "32"},
@@ -51,7 +49,7 @@ def test_kernel_variants_match_fp32_engine(variant, monkeypatch):
     """Every recurrence tile / launch-structure variant of the tensor engine (the switches are read from the
     environment when the handle is created) against the fp32 engine, same tolerance as above."""
     from helen_b200.predictor import WindowPredictor
-    for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8", "HB_NO_DUAL"):
+    for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8"):
         monkeypatch.delenv(k, raising=False)
     batch, seq, features = 45, 250, 10
     sd = random_state_dict(features, seed=5)
