@@ -11,6 +11,9 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// dynamic shared memory base rounded up to the 1024-byte swizzle atom (allocations carry 1024 spare bytes)
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -237,6 +240,21 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
+// K-major, 128-byte swizzle: 8-row x 128-byte atoms (64 fp16 along K); inside an atom the 16-byte chunk c of row r sits at
+// chunk position c ^ r (the hardware applies the XOR to address bits [4,7) with bits [7,10): atoms are 1024 B aligned).
+// A k-step (16 fp16 = 32 B) advances the start address by 32 B inside an atom; sbo_bytes = distance between 8-row groups.
+// bits [16,30) LBO = 1 (unused for swizzled K-major) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// byte offset of element (row 0..7, k 0..127) inside a [8 rows x 128 k] fp16 block stored as two swizzled atoms (k < 64 | k >= 64)
+__host__ __device__ constexpr uint32_t sw128_offset(int row, int k) {
+    return (uint32_t)((k >> 6) * 1024 + row * 128 + ((((k >> 3) & 7) ^ row) << 4) + (k & 7) * 2);
+}
+// descriptor start-address advance (16-byte units) of k-step ks (16 fp16 each) inside such a block
+__host__ __device__ constexpr uint64_t sw128_kstep(int ks) { return (uint64_t)(((ks >> 2) * 1024 + (ks & 3) * 32) >> 4); }
+
 // Instruction descriptor for kind::f16: D=f32 (bit 4), A=B=f16 (0), both K-major, N>>3 at 17, M>>4 at 24.
 __host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -41,9 +41,11 @@ constexpr float ACT_SCALE = 1024.0f;              // activations in (-1, 1) are 
 constexpr float ACT_SCALE_INV = 1.0f / 1024.0f;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int WG = 8;                             // windows per window group == rows of one core matrix
-constexpr int H_LBO = 144;                        // k-group stride of h / y images: 128 B core matrix + 16 B pad,
-                                                  // so the gate threads' 2-byte stores spread over all banks
-constexpr int YBLK = 16 * H_LBO;                  // 2304 B: [8 windows x 128 k] fp16 image of one direction
+// h / y images: [8 windows x 128 k] fp16 blocks in the K-major 128-byte-swizzle layout (tc::sw128_offset): dense, the
+// tensor core reads full 128-byte rows, and the gate threads' 2-byte stores still spread over all banks (the XOR moves
+// the four k-chunks a warp writes to different bank groups).  (The no-swizzle core-matrix layout ran every MMA at about
+// half the rate; padding its k-group stride to 144 B only fixed the store conflicts.)
+constexpr int YBLK = 2048;                        // [8 windows x 128 k] fp16 image of one direction: two swizzle atoms
 constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)  [sizes only]
 constexpr int GI_ROW_BYTES = G * 4;               // 1536 B: gi of one (window, t, direction)
 // gi' lives in global memory as a "gi image": [window group][column][direction][gate r,z,n][8 windows][128 units] fp32,
@@ -123,7 +125,8 @@ struct ProjArgs {
     const uint8_t* in_base; int64_t in_wg_stride, in_dir_stride, in_part_stride;
     int blk_bytes;                 // one (group, column) block of ONE K-slice
     int n_dirs;                    // K-slices per column: 2 for the GRU output image (forward | reverse units), 1 for pixels
-    int lbo, Kp; int64_t n_wg; int W;
+    int lbo;                       // k-group stride of a no-swizzle image (pixels), or 0: blocks are 128-byte-swizzle images (GRU outputs)
+    int Kp; int64_t n_wg; int W;
     const uint32_t* w_tmem;        // packed fp16 pairs, see wih_word_index
     const float* scale_row;        // [768]
     const float* bias_row;         // [768]
@@ -355,8 +358,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             tc::tc_fence_after();
             if (tc::elect_one()) {
                 const uint32_t sbase = tc::smem_u32(smem + stage * stage_bytes);
-                const uint64_t d_hi = tc::smem_desc(sbase, lbo, blk_bytes);
-                const uint64_t d_lo = tc::smem_desc(sbase + part_bytes, lbo, blk_bytes);
+                const uint64_t d_hi = lbo ? tc::smem_desc(sbase, lbo, blk_bytes) : tc::smem_desc_sw128(sbase, blk_bytes);
+                const uint64_t d_lo = lbo ? tc::smem_desc(sbase + part_bytes, lbo, blk_bytes) : tc::smem_desc_sw128(sbase + part_bytes, blk_bytes);
                 const uint32_t a_hi = tmem + PROJ_W_COL0 + (split ? j.src_dir * 64 : 0), a_lo = a_hi + kwords;
                 const uint32_t d = tmem + acc * PROJ_NT;
                 // Issue loops with compile-time trip counts for the two hot shapes: the operands of every MMA are then
@@ -365,7 +368,10 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 auto issue = [&](auto ksteps_c, auto dirs_c) {
                     constexpr int KS = decltype(ksteps_c)::value, ND = decltype(dirs_c)::value;
                     const int ks_n = KS > 0 ? KS : ksteps;
-                    auto koff = [&](int ks) { return (uint64_t)((ND == 2 ? (ks >> 3) * slice_bytes + (ks & 7) * 2 * lbo : ks * 2 * lbo) / 16); };
+                    auto koff = [&](int ks) {
+                        if (KS == 0) return (uint64_t)(ks * 2 * lbo / 16);                         // pixels: no-swizzle image
+                        return (uint64_t)((ND == 2 ? (ks >> 3) * slice_bytes : 0) / 16) + tc::sw128_kstep(ks & 7);
+                    };
 #pragma unroll
                     for (int ks = 0; ks < ks_n; ++ks) tc::mma_f16_ts(d, a_hi + ks * 8, d_hi + koff(ks), idesc, ks != 0);
 #pragma unroll
@@ -426,8 +432,8 @@ template <bool kSplitA>
 __global__ void __launch_bounds__(PROJ_THREADS, 1)
 tc_projection_kernel(const ProjArgs a)
 {
-    extern __shared__ __align__(128) uint8_t smem_proj[];
-    projection_role<kSplitA>(a, smem_proj, (int)blockIdx.y, (int)blockIdx.x, (int)gridDim.x);
+    extern __shared__ __align__(1024) uint8_t smem_proj[];
+    projection_role<kSplitA>(a, tc::align_smem_1024(smem_proj), (int)blockIdx.y, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -688,7 +694,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         const uint32_t idesc = tc::idesc_f16_f32(128, NACC);
         // stacked operand: NLIVE == 8 takes rows 8..15 from the lo image (group stride = HB_BYTES); with NLIVE == 16
         // the lo image directly follows the two hi groups, so the plain group stride covers all 32 rows
-        const uint64_t himg_desc = tc::smem_desc(tc::smem_u32(h_img), H_LBO, (STACK && NLIVE == 8) ? HB_BYTES : YBLK);
+        const uint64_t himg_desc = tc::smem_desc_sw128(tc::smem_u32(h_img), (STACK && NLIVE == 8) ? HB_BYTES : YBLK);
         for (int s = 0; s < W; ++s) {
             if (s > 0) {
                 tc::mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
@@ -706,7 +712,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                             const uint32_t a_col = tmem + REC_W_COL0 + (term * 3 + gb) * 64;
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks)
-                                tc::mma_f16_ts(tmem + gb * NBLK, a_col + ks * 8, hhi_desc + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
+                                tc::mma_f16_ts(tmem + gb * NBLK, a_col + ks * 8, hhi_desc + tc::sw128_kstep(ks), idesc, (term | ks) != 0);
                         }
                     } else {
 #pragma unroll
@@ -715,7 +721,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                             const uint64_t bd = term == 2 ? hlo_desc : hhi_desc;
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks)
-                                tc::mma_f16_ts(tmem + gb * NBLK, a_col + ks * 8, bd + (uint64_t)(ks * 2 * H_LBO / 16), idesc, (term | ks) != 0);
+                                tc::mma_f16_ts(tmem + gb * NBLK, a_col + ks * 8, bd + tc::sw128_kstep(ks), idesc, (term | ks) != 0);
                         }
                     }
                     tc::mma_commit(acc_ready + gb);          // gates start on r while z, n still run
@@ -764,7 +770,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         }
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-            h_off[i] = tc::core_offset(win0 + i, j, H_LBO, YBLK);
+            h_off[i] = (uint32_t)((win0 + i) / WG) * YBLK + tc::sw128_offset((win0 + i) % WG, j);
             __half hi, lo;
             tc::split_f16(h_own[i], hi, lo);
             *reinterpret_cast<__half*>(h_img + h_off[i]) = hi;                      // h_0 -> buffer 0
@@ -870,8 +876,8 @@ template <int N, int NLIVE, int MODE>
 __global__ void __launch_bounds__(REC_TC_THREADS, 1)
 tc_recurrence_kernel(const RecArgs ra)
 {
-    extern __shared__ __align__(128) uint8_t smem_rec[];
-    recurrence_role<N, NLIVE, MODE>(ra, smem_rec, (int)blockIdx.x, (int)blockIdx.y);
+    extern __shared__ __align__(1024) uint8_t smem_rec[];
+    recurrence_role<N, NLIVE, MODE>(ra, tc::align_smem_1024(smem_rec), (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -978,10 +984,10 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             if (it > 0) tc::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
             tc::tc_fence_after();
             if (tc::elect_one()) {
-                const uint64_t a_hi = tc::smem_desc(tc::smem_u32(a_img), H_LBO, YBLK), a_lo = tc::smem_desc(tc::smem_u32(a_img + PART_BYTES), H_LBO, YBLK);
+                const uint64_t a_hi = tc::smem_desc_sw128(tc::smem_u32(a_img), YBLK), a_lo = tc::smem_desc_sw128(tc::smem_u32(a_img + PART_BYTES), YBLK);
                 const uint64_t w_hi = tc::smem_desc(tc::smem_u32(w_s), 128, 4096), w_lo = tc::smem_desc(tc::smem_u32(w_s + HEADS_WIMG), 128, 4096);
                 // k-step ks: direction ks / 8 (forward units are k < 128), then (ks % 8) * 16 units into its slice
-                auto koff = [](int ks) { return (uint64_t)(((ks >> 3) * SLICE_BYTES + (ks & 7) * 2 * H_LBO) / 16); };
+                auto koff = [](int ks) { return (uint64_t)(((ks >> 3) * SLICE_BYTES) / 16) + tc::sw128_kstep(ks & 7); };
                 uint32_t accum = 0;
 #pragma unroll
                 for (int ks = 0; ks < 16; ++ks) { tc::mma_f16_ss(tmem, a_hi + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, accum); accum = 1; }
@@ -1052,8 +1058,8 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
 __global__ void __launch_bounds__(HEADS_THREADS, 1)
 tc_heads_kernel(const HeadsArgs a)
 {
-    extern __shared__ __align__(128) uint8_t smem_heads[];
-    heads_role(a, smem_heads, (int)blockIdx.x, (int)gridDim.x);
+    extern __shared__ __align__(1024) uint8_t smem_heads[];
+    heads_role(a, tc::align_smem_1024(smem_heads), (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1075,7 +1081,8 @@ __global__ void __launch_bounds__(REC_TC_THREADS, 1)
 tc_chunkloop_kernel(const RecArgs rec, const ProjArgs proj, const HeadsArgs heads,
                     const int rec_ctas, const int proj_workers, const int heads_workers)
 {
-    extern __shared__ __align__(128) uint8_t smem_all[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem_all = tc::align_smem_1024(smem_raw);
     const int bid = (int)blockIdx.x;
     if (bid < 2 * rec_ctas) {
         recurrence_role<N, NLIVE, MODE, true>(rec, smem_all, bid >> 1, bid & 1);
@@ -1315,12 +1322,13 @@ inline void free_layer(TensorLayer* L) {
     cudaFree(L->wih_tmem); cudaFree(L->scale_row); cudaFree(L->bias_row); cudaFree(L->whh_tmem); cudaFree(L->gate_consts);
 }
 
-inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 2 * PROJ_STG_BYTES + 256; }
+// (+1024: the kernels align their shared memory to the swizzle atom themselves)
+inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 2 * PROJ_STG_BYTES + 256 + 1024; }
 template <int N>
-constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<N, N, false>() * N * GI_ROW_BYTES + 512; }
+constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<N, N, false>() * N * GI_ROW_BYTES + 512 + 1024; }
 template <int NLIVE>   // chunk-loop kernel (N = 16, two gi' rows per window)
-constexpr size_t recurrence_smem_gi2() { return (size_t)2 * h_buffers<16>() * (16 / WG) * YBLK + (size_t)gi_stages<16, NLIVE, true>() * 2 * NLIVE * GI_ROW_BYTES + 512; }
-constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128; }
+constexpr size_t recurrence_smem_gi2() { return (size_t)2 * h_buffers<16>() * (16 / WG) * YBLK + (size_t)gi_stages<16, NLIVE, true>() * 2 * NLIVE * GI_ROW_BYTES + 512 + 1024; }
+constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128 + 1024; }
 
 }  // namespace detail
 
@@ -1487,7 +1495,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     // decoder projection arguments (the same for every chunk)
     ProjArgs pd{};
     pd.in_base = ws.yimg1; pd.in_wg_stride = (int64_t)W * 4 * YBLK; pd.in_dir_stride = (int64_t)W * 2 * YBLK; pd.in_part_stride = (int64_t)W * YBLK;
-    pd.blk_bytes = YBLK; pd.n_dirs = 2; pd.lbo = H_LBO; pd.Kp = e->dec.Kp; pd.n_wg = n_wg; pd.W = W;
+    pd.blk_bytes = YBLK; pd.n_dirs = 2; pd.lbo = 0; pd.Kp = e->dec.Kp; pd.n_wg = n_wg; pd.W = W;
     pd.w_tmem = e->dec.wih_tmem; pd.scale_row = e->dec.scale_row; pd.bias_row = e->dec.bias_row; pd.gi = ws.gi;
     pd.pair = pair_mode;
     const int n_chunks = T < W ? 0 : (T - W) / J + 1;
