@@ -155,20 +155,24 @@ __host__ __device__ constexpr int pack_proj_job(int wg, int tile, int src_dir) {
 
 struct ProjJob { int64_t wg; int t0, valid, src_dir; bool split; };
 
-// idx-th job of a worker; all roles of a CTA walk the same sequence
-__device__ __forceinline__ bool proj_job(const ProjArgs& a, int worker, int n_workers, int64_t idx, ProjJob& j) {
-    if (a.jobs != nullptr) {
-        const int begin = __ldg(a.job_offsets + worker), end = __ldg(a.job_offsets + worker + 1);
-        if (idx >= end - begin) return false;
-        const int e = __ldg(a.jobs + begin + idx);
-        j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.src_dir = (e >> 28) & 1; j.split = true;
-    } else {
-        const int64_t tile = worker + idx * n_workers;
-        if (tile >= a.n_wg * ((a.W + 7) >> 3)) return false;
-        j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.src_dir = 0; j.split = false;
-    }
+// jobs of one worker per chunk, and the idx-th of them in table / tile order
+__device__ __forceinline__ int proj_count(const ProjArgs& a, int worker, int n_workers) {
+    if (a.jobs != nullptr) return __ldg(a.job_offsets + worker + 1) - __ldg(a.job_offsets + worker);
+    const int64_t n_tiles = a.n_wg * ((a.W + 7) >> 3);
+    return n_tiles > worker ? (int)((n_tiles - worker + n_workers - 1) / n_workers) : 0;
+}
+__device__ __forceinline__ ProjJob proj_decode(const ProjArgs& a, int e) {
+    ProjJob j;
+    j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.src_dir = (e >> 28) & 1; j.split = true;
     j.valid = min(8, a.W - j.t0);
-    return true;
+    return j;
+}
+__device__ __forceinline__ ProjJob proj_tile_job(const ProjArgs& a, int worker, int n_workers, int idx) {
+    const int64_t tile = worker + (int64_t)idx * n_workers;
+    ProjJob j;
+    j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.src_dir = 0; j.split = false;
+    j.valid = min(8, a.W - j.t0);
+    return j;
 }
 
 template <bool kSplitA>
@@ -198,6 +202,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     uint64_t* stg_full = acc_empty + 2;                      // [2]: the 4 epilogue warps have written the staging buffer
     uint64_t* stg_empty = stg_full + 2;                      // [2]: its bulk copies have read it
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + 2);
+    // chunk-loop kernel: the loader decides the job order at run time (see below) and passes it on through this ring
+    volatile int* job_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [16] >= jobs in flight between loader and store warp
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kwords = Kp >> 1;
@@ -245,6 +251,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     if (a.pair) tc::cluster_sync_all();                      // the peer's mbarriers exist before anything is multicast at them
 
     const int n_chunks = a.n_chunks > 0 ? a.n_chunks : 1;
+    const int n_jobs = proj_count(a, worker, n_workers);     // per chunk
+    const int job0 = split ? __ldg(a.job_offsets + worker) : 0;
     ProjJob j;
     // HB_DEBUG_TIMELINE: worker 0 / block 0 adds up the cycles each role spends at its wait points (slots 7200 + 8 role + k)
     const bool acct = a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0;
@@ -255,25 +263,51 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                                               a.dbg[7200 + 8 * (role) + 4] = clock64() - t_role0; } } while (0)
     if (warp == 5) {
         // ===================== loader =====================
+        // Job order in the chunk-loop kernel: the table lists a worker's jobs in the order the encoder makes them runnable;
+        // the decoder, however, starts with the tiles that become runnable LAST (its first columns need the other
+        // direction's final outputs).  So the loader works from both ends of the list: the last job as soon as it is
+        // runnable (then the encoder has finished and everything left is runnable: the backlog is cleared in the order
+        // the decoder consumes it), otherwise the first one.
+        // The counters are read with relaxed loads, one job ahead (the value is in flight while the previous job's copies
+        // are issued): the encoder completed and fenced its bulk stores before it released a counter, and our bulk loads
+        // are issued after the value has arrived and read L2 directly.  (ld.acquire + fence.proxy.async per job cost
+        // ~1500 cycles and made this warp the bottleneck of the role.)
+        auto need_of = [&](const ProjJob& q, int chunk) {
+            return a.epoch + (unsigned long long)chunk * W + (unsigned long long)(q.src_dir == 0 ? q.t0 + q.valid : W - q.t0);
+        };
+        auto flag_of = [&](const ProjJob& q) { return a.progress + ((q.wg * WG) / a.rec_n) * 2 + q.src_dir; };
         int it = 0;
-        for (int chunk = 0; chunk < n_chunks; ++chunk)
-        for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        int front = 0, back = n_jobs - 1, ef = 0, eb = 0;
+        ProjJob jf{}, jb{};
+        unsigned long long vf = 0, vb = 0;
+        auto look = [&]() {                                  // lane 0: both ends of what is left, counters requested
+            ef = __ldg(a.jobs + job0 + front); eb = __ldg(a.jobs + job0 + back);
+            jf = proj_decode(a, ef); jb = proj_decode(a, eb);
+            vf = tc::ld_relaxed_gpu(flag_of(jf)); vb = tc::ld_relaxed_gpu(flag_of(jb));
+        };
+        if (split && lane == 0 && n_jobs > 0) look();
+        for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int stage = it % n_stages;
             if (it >= n_stages) HB_TIMED(0, tc::mbar_wait(a_empty + stage, (uint32_t)((it / n_stages - 1) & 1)));
-            if (a.progress != nullptr) {
-                // the source encoder direction must have stored the job's columns: forward past t0+valid-1, reverse past t0
+            if (split) {
+                int e = 0;
                 if (lane == 0) {
-                    const unsigned long long need = a.epoch + (unsigned long long)chunk * W + (unsigned long long)(j.src_dir == 0 ? j.t0 + j.valid : W - j.t0);
-                    const unsigned long long* flag = a.progress + ((j.wg * WG) / a.rec_n) * 2 + j.src_dir;
-                    HB_TIMED(1, while (tc::ld_acquire_gpu(flag) < need) __nanosleep(100));
+                    const long long t_ = acct ? clock64() : 0;
+                    while (true) {
+                        if (front < back && vb >= need_of(jb, chunk)) { e = eb; --back; break; }
+                        if (vf >= need_of(jf, chunk)) { e = ef; ++front; break; }
+                        __nanosleep(100);
+                        vf = tc::ld_relaxed_gpu(flag_of(jf)); vb = tc::ld_relaxed_gpu(flag_of(jb));
+                    }
+                    if (acct) t_wait[1] += clock64() - t_;
+                    job_ring[it & 15] = e;
+                    if (front <= back) look();               // for the next job; the loads complete while this one is issued
                 }
-                // No proxy fence here: the producer completed its bulk stores (wait_group), fenced and released the counter;
-                // our bulk loads are issued after the acquire in program order and read L2 directly.  (fence.proxy.async
-                // cost ~1000 cycles per job and made this warp the bottleneck of the role.)
-#ifdef HB_STRICT_PROXY_FENCE
-                HB_TIMED(2, tc::fence_proxy_async_all());
-#endif
-                __syncwarp();
+                e = __shfl_sync(0xffffffffu, e, 0);
+                j = proj_decode(a, e);
+            } else {
+                j = proj_tile_job(a, worker, n_workers, idx);
             }
             const long long t_issue = acct ? clock64() : 0;
             if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * PARTS * n_dirs * blk_bytes));
@@ -295,6 +329,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             }
             __syncwarp();
             if (acct) t_wait[3] += clock64() - t_issue;
+        }
         }
         HB_ROLE_REPORT(0);
     } else if (warp == 6) {
@@ -322,10 +357,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         };
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
-        for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
+        for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int sb = it & 1;
             const uint32_t par = (uint32_t)((it >> 1) & 1);
             HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
+            j = split ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
             float* out = j.src_dir ? a.gi_b : gi;
             if (lane < 8 && j.t0 + lane < W)
                 tc::bulk_s2g(out + gi_block(j.wg, W, j.t0 + lane, blk), staging + sb * PROJ_STG_BYTES + lane * (GI_BLK_FLOATS * 4), GI_BLK_FLOATS * 4);
@@ -336,8 +372,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             if (lane == 0 && it > 0) tc::mbar_arrive(stg_empty + (sb ^ 1));
             if (a.tile_flags != nullptr) {
                 pending[n_pending++] = a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
-                ProjJob next;
-                if (!proj_job(a, worker, n_workers, idx + 1, next)) HB_TIMED(2, publish(0));         // last job of the chunk
+                if (idx == n_jobs - 1) HB_TIMED(2, publish(0));                      // last job of the chunk
                 else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2));   // copies issued two jobs ago have normally landed: no stall
             }
             if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
@@ -351,9 +386,10 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const int ksteps = split ? 8 : (Kp >> 4);
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
-        for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
+        for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int stage = it % n_stages, acc = it & 1;
             HB_TIMED(0, tc::mbar_wait(a_full + stage, (uint32_t)((it / n_stages) & 1)));
+            j = split ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
             if (it >= 2) HB_TIMED(1, tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1)));
             tc::tc_fence_after();
             if (tc::elect_one()) {
@@ -397,10 +433,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const float sc = scale_row[blk * 128 + r], bi = bias_row[blk * 128 + r];
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk)
-        for (int64_t idx = 0; proj_job(a, worker, n_workers, idx, j); ++idx, ++it) {
+        for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int acc = it & 1, sb = it & 1;
             if (it >= 2) HB_TIMED(0, tc::mbar_wait(stg_empty + sb, (uint32_t)((it / 2 - 1) & 1)));   // arrives once job it-1 is being stored
             HB_TIMED(1, tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1)));
+            j = split ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
             float* stg = reinterpret_cast<float*>(staging + sb * PROJ_STG_BYTES) + r;
@@ -1594,13 +1631,14 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         ra.tiles_t = tiles8; ra.n_wg = (int)n_wg; ra.epoch = 0; ra.dbg = dbg_buf; ra.dbg_layer = dbg_enc ? 0 : 1;
         ProjArgs pp = pd;
         pp.progress = enc_prog; pp.epoch = 0; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
+        pp.pair = 0;          // every CTA of the role picks its own job order (see the loader): no shared tiles
         pp.dbg = dbg_buf;
         pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets; pp.gi_b = ws.gi_b;
         HeadsArgs hp = heads_base;
         hp.yimg = ws.yimg2[0]; hp.yimg_odd = ws.yimg2[1]; hp.col0 = 0; hp.n_chunks = n_chunks;
         hp.progress = dec_prog; hp.rec_n = plan.tile; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
         hp.dbg = dbg_buf;
-        const dim3 grid(2 * plan.rec_ctas + 6 * plan.proj_workers + plan.heads_workers), cluster(pair_mode ? 2 : 1, 1, 1);
+        const dim3 grid(2 * plan.rec_ctas + 6 * plan.proj_workers + plan.heads_workers), cluster(1, 1, 1);
         const size_t smem = std::max({plan.tile == 8 ? detail::recurrence_smem_gi2<8>() : detail::recurrence_smem_gi2<16>(),
                                       detail::projection_smem(YROW, 2), detail::heads_smem()});
         auto go = [&](auto kernel) {
