@@ -345,8 +345,12 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         int n_pending = 0;
         auto publish = [&](int keep) {                       // wait until all but the newest `keep` (0 or 2) jobs have landed, raise their flags
             if (n_pending <= keep) return;
+            // wait_group (not .read) returns when the copies' writes have been performed; the release below orders them
+            // before the counter.  (An additional fence.proxy.async here cost ~1000 cycles per publication.)
             if (keep == 0) tc::bulk_wait0(); else tc::bulk_wait_pending<2>();
+#ifdef HB_STRICT_PROXY_FENCE
             tc::fence_proxy_async_all();
+#endif
             __syncwarp();
             if (lane == 0) {                                 // ONE release fence for the whole batch, then relaxed increments
                 tc::fence_acq_rel_gpu();
@@ -373,6 +377,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             if (a.tile_flags != nullptr) {
                 pending[n_pending++] = a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
                 if (idx == n_jobs - 1) HB_TIMED(2, publish(0));                      // last job of the chunk
+                // (publishing the backlog jobs one by one so the decoder sees its first tiles sooner was measured: no gain)
                 else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2));   // copies issued two jobs ago have normally landed: no stall
             }
             if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
@@ -495,7 +500,8 @@ constexpr int REC_W_COL0 = 128;                   // weight columns start here (
 constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate block][row][k pair]
 // GI2: a stage holds TWO gi' rows per window (the two K-halves of the chunk-loop projection, added by the gate threads)
 template <int N, int NLIVE, bool GI2> __host__ __device__ constexpr int gi_stages() {
-    return GI2 ? (NLIVE <= 8 ? 4 : 3) : (N <= 16 ? 4 : 3);   // N = 32: 3 x 48 KB, 16 live x 2 rows: 3 x 48 KB (227 KB smem limit)
+    return GI2 ? (NLIVE <= 8 ? 6 : 3) : (N <= 16 ? 4 : 3);   // N = 32: 3 x 48 KB, 16 live x 2 rows: 3 x 48 KB (227 KB smem limit);
+                                                             // 8 live x 2 rows: 6 x 24 KB (the other roles' traffic delays gi' rows)
 }
 // h operand image buffers: 4 give the y store three steps to drain, which hides the global-memory round trips of the
 // progress publication (chunk-loop kernel); N = 32 has room for 2 only
@@ -676,7 +682,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 // decoder in the chunk-loop kernel: the projection CTAs announce finished gi' tiles
                 if (lane < NG && cta_x * NG + lane < ra.n_wg)
                     tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 6ull * (chunk + 1));
-                tc::fence_proxy_async_all();
+                // (no proxy fence: the bulk loads below are issued after the acquire and read L2, where the producer's
+                // completed bulk stores already are)
                 __syncwarp();
             }
             if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
@@ -709,13 +716,13 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 // every 4th step: all stores but the newest PUBLISH_LAG have landed in global memory, publish
                 // that many completed columns to the consumer CTAs.  (Waiting for the newest store, or
                 // fencing every step, would put a global round trip on the step's critical path via h_free.)
-                if (lane < 2 * NG) { tc::bulk_wait_pending<PUBLISH_LAG>(); tc::fence_proxy_async_all(); }
+                if (lane < 2 * NG) tc::bulk_wait_pending<PUBLISH_LAG>();   // writes performed; the release orders them before the counter
                 __syncwarp();
                 if (lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)(s + 1 - PUBLISH_LAG));
             }
         }
         HB_STAMP(3);                                         // last image handed to the copy engine
-        if (lane < 2 * NG) { tc::bulk_wait0(); tc::fence_proxy_async_all(); }
+        if (lane < 2 * NG) tc::bulk_wait0();
         __syncwarp();
         if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)W);
         HB_STAMP(4);                                         // all columns published
@@ -1001,7 +1008,7 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                 if (lane < 2)
                     tc::spin_until_ge(a.progress + ((wg * WG) / a.rec_n) * 2 + lane,
                                       (unsigned long long)chunk * W + (unsigned long long)(lane == 0 ? t0 + valid : W - t0));
-                tc::fence_proxy_async_all();
+
                 __syncwarp();
             }
             const uint8_t* img = ((chunk & 1) && a.yimg_odd) ? a.yimg_odd : a.yimg;
