@@ -353,6 +353,74 @@ def run_native(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """--train: BASELINE configs[3], one chunk step = forward + CE(base) + weighted CE(rle) + backward on [B=128, 100, F]
+    (train.py:189-201 through ChunkTrainer.step -> hb_train_step_chunk); secondary line, not the headline metric."""
+    import torch
+    from helen_b200 import build as hb_build
+    from helen_b200.models.TransducerModel import TransducerGRU
+    from helen_b200.models.train_step import ChunkTrainer
+    from oracle import TransducerPort, random_state_dict
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --train: no CUDA device; there is no CPU fallback")
+    hb_build.build()
+    batch, features = args.train_batch, args.features
+    sd = random_state_dict(features, seed=0)
+    model = TransducerGRU(1, features, 1, HIDDEN, 5, 11)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    trainer = ChunkTrainer(model)
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randint(0, 256, (batch, WINDOW, features), generator=gen).float().cuda()
+    lb = torch.randint(0, 5, (batch, WINDOW), generator=gen).cuda()
+    lr = torch.randint(0, 11, (batch, WINDOW), generator=gen).cuda()
+    hidden = None
+    for _ in range(args.warmup):
+        _, _, _, hidden = trainer.step(x, hidden, lb, lr)
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        loss, _, _, hidden = trainer.step(x, hidden, lb, lr)
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / args.steps
+    fwd_mac = 2 * WINDOW * 3 * HIDDEN * features + 2 * (2 * WINDOW * 3 * HIDDEN * HIDDEN) + 2 * WINDOW * 3 * HIDDEN * 2 * HIDDEN + WINDOW * 2 * HIDDEN * 16
+    flop = 3 * 2 * fwd_mac * batch                               # backward ~ 2x forward
+    props = torch.cuda.get_device_properties(0)
+    fp32_peak = props.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
+    # CPU arm: the oracle port's autograd with the reference's criteria, bounded sample
+    from helen_b200.options import TrainOptions
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    port = TransducerPort(features)
+    port.load_state_dict(sd)
+    crit_b = torch.nn.CrossEntropyLoss()
+    crit_r = torch.nn.CrossEntropyLoss(weight=torch.tensor(TrainOptions.CLASS_WEIGHTS))
+    xc, lbc, lrc = x.cpu(), lb.cpu(), lr.cpu()
+    hc = torch.zeros(batch, 2, HIDDEN)
+    cpu_steps, t0 = 0, time.perf_counter()
+    while cpu_steps < 2 or time.perf_counter() - t0 < 5.0:
+        port.zero_grad()
+        ob, orl, hc = port(xc, hc)
+        (crit_b(ob.reshape(-1, 5), lbc.reshape(-1)) + crit_r(orl.reshape(-1, 11), lrc.reshape(-1))).backward()
+        hc = hc.detach()
+        cpu_steps += 1
+    cpu_rate = cpu_steps / (time.perf_counter() - t0)
+    print(json.dumps({
+        "metric": "train chunk-steps/sec (B=128, W=100; forward + CE + weighted CE + backward)", "value": 1e3 / ms, "unit": "chunk-steps/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "last_loss": loss,
+        "config": {"workload": f"helen_train forward+backward GRU on 1xB200, B={batch}, W={WINDOW}, F={features} (BASELINE configs[3])"},
+        "roofline": {"bound": "fp32 FMA", "achieved": flop / (ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": flop / (ms * 1e-3) / 1e12 / fp32_peak, "peak_source": "computed: SMs x 128 lanes x 2 x 1.965 GHz (not measured)",
+                     "flop_per_step": flop, "traffic": None},
+        "cpu_baseline": {"value": cpu_rate, "unit": "chunk-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{cpu_steps} steps, torch {torch.__version__} CPU autograd of the nn.GRU port with the reference's criteria"},
+    }), flush=True)
+    trainer.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -367,6 +435,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="windows per CPU-baseline batch")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--reference-sample", type=int, default=32, help="windows per step of --impl reference")
+    ap.add_argument("--train", action="store_true", help="secondary line: BASELINE configs[3], one training chunk step at B=128")
+    ap.add_argument("--train-batch", type=int, default=128)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -381,7 +451,10 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    if args.impl == "reference":
+    if args.train:
+        if rank == 0:
+            run_train(args)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_native(args, rank, world, local_rank)

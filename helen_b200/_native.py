@@ -10,7 +10,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 # HB_LIB: another build of the same library (A/B measurements of compile-time variants, tools/build_variants.py)
 LIB_PATH = os.environ.get("HB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhelen_b200.so")
 
-HB_ABI_VERSION = 2
+HB_ABI_VERSION = 3
 HB_OK = 0
 HB_ERR_INVALID_ARGUMENT = -1
 HB_ERR_UNSUPPORTED_DEVICE = -2
@@ -55,6 +55,9 @@ SIGNATURES = {
                                         c_void_p, c_void_p]),
     "hb_forward_chunk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
+    "hb_train_workspace_bytes": (c_int, [c_void_p, c_int64, c_int, POINTER(c_size_t)]),
+    "hb_train_step_chunk": (c_int, [c_void_p, POINTER(hb_weights), POINTER(hb_weights), c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hb_launch_count": (c_int64, [c_void_p]),
     "hb_last_launch_plan": (c_int, [c_void_p, POINTER(hb_launch_plan)]),
     "hb_enable_kernel_timing": (c_int, [c_void_p, c_int]),

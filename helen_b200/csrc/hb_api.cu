@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fp32_kernels.cuh"
+#include "train_kernels.cuh"
 #include "workspace.cuh"
 #ifndef HB_NO_TENSOR_ENGINE
 #include "tensor_engine.cuh"
@@ -422,6 +423,152 @@ int hb_predict_windows_host(hb_handle* h, const uint8_t* images_host, int64_t B,
     HB_CUDA(cudaStreamSynchronize(s));
     std::memcpy(base_labels_host, h->stage_labels_host, lab_bytes);
     std::memcpy(rle_labels_host, h->stage_labels_host + lab_bytes, lab_bytes);
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Training step of one chunk (row a15): see train_kernels.cuh
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct TrainWorkspace {
+    float *gi1, *y1, *sv1, *gi2, *y2, *sv2, *h_enc, *logit_b, *logit_r, *sums, *dlogits, *dy, *dgi, *dgh, *hprev, *dh_dec0;
+    size_t bytes;
+};
+
+TrainWorkspace train_carve(void* base, int64_t B, int W) {
+    TrainWorkspace ws{};
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        size_t o = off;
+        off += hb::align_up(n * sizeof(float));
+        return base ? reinterpret_cast<float*>(static_cast<char*>(base) + o) : nullptr;
+    };
+    const size_t M = (size_t)B * (size_t)W;
+    ws.gi1 = take(M * 2 * hb::G); ws.y1 = take(M * 2 * hb::H); ws.sv1 = take(M * 8 * hb::H);
+    ws.gi2 = take(M * 2 * hb::G); ws.y2 = take(M * 2 * hb::H); ws.sv2 = take(M * 8 * hb::H);
+    ws.h_enc = take((size_t)B * 2 * hb::H);
+    ws.logit_b = take(M * hb::NBASE); ws.logit_r = take(M * hb::NRLE);
+    ws.sums = take(4); ws.dlogits = take(M * hb::NCLS);
+    ws.dy = take(M * 2 * hb::H); ws.dgi = take(M * 2 * hb::G); ws.dgh = take(M * 2 * hb::G); ws.hprev = take(M * 2 * hb::H);
+    ws.dh_dec0 = take((size_t)B * 2 * hb::H);
+    ws.bytes = off;
+    return ws;
+}
+
+// C[M, N] (+)= A . B with element strides; split_k > 1 (or accumulate) adds into C
+void gemm(cudaStream_t s, const float* a, int64_t a_m, int64_t a_k, const float* b, int64_t b_k, int64_t b_n,
+          float* c, int64_t c_m, int64_t c_n, const float* bias, int64_t M, int64_t N, int64_t K, int split_k) {
+    hb::train::GemmArgs g{a, a_m, a_k, b, b_k, b_n, c, c_m, c_n, bias, M, N, K, split_k < 0 ? 1 : 0};   // split_k < 0: accumulate, no split
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)std::max(1, split_k));
+    hb::train::gemm_kernel<<<grid, 256, 0, s>>>(g);
+}
+
+void colsum(cudaStream_t s, const float* a, int64_t M, int N, int64_t lda, float* out) {
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, M / 256)));
+    hb::train::colsum_kernel<<<grid, 256, 0, s>>>(a, M, N, lda, out);
+}
+
+bool gru_ptrs_ok(const hb_gru_weights& g) {
+    for (int d = 0; d < 2; ++d)
+        if (!g.weight_ih[d] || !g.weight_hh[d] || !g.bias_ih[d] || !g.bias_hh[d]) return false;
+    return true;
+}
+
+}  // namespace
+
+int hb_train_workspace_bytes(const hb_handle* h, int64_t B, int W, size_t* out) {
+    if (!h || !out) return fail(HB_ERR_INVALID_ARGUMENT, "null argument");
+    if (B < 0 || W <= 0) return fail(HB_ERR_INVALID_ARGUMENT, "hb_train_workspace_bytes: bad shape B=%lld W=%d", (long long)B, W);
+    *out = train_carve(nullptr, B, W).bytes + hb::kAlign;
+    return HB_OK;
+}
+
+int hb_train_step_chunk(hb_handle* h, const hb_weights* w, const hb_weights* gr, const float* x_dev, const float* h_in_dev,
+                        const int64_t* label_base_dev, const int64_t* label_rle_dev, const float* rle_class_weights_dev,
+                        int64_t B, int W, float* loss_dev, float* h_out_dev, float* base_logits_dev, float* rle_logits_dev,
+                        void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h) return fail(HB_ERR_INVALID_ARGUMENT, "null handle");
+    if (B < 0 || W <= 0) return fail(HB_ERR_INVALID_ARGUMENT, "hb_train_step_chunk: bad shape B=%lld W=%d", (long long)B, W);
+    if (B == 0) return HB_OK;
+    if (!w || !gr || !x_dev || !label_base_dev || !label_rle_dev || !rle_class_weights_dev || !loss_dev || !h_out_dev)
+        return fail(HB_ERR_INVALID_ARGUMENT, "hb_train_step_chunk: null pointer");
+    if (!gru_ptrs_ok(w->encoder) || !gru_ptrs_ok(w->decoder) || !w->base_weight || !w->base_bias || !w->rle_weight || !w->rle_bias ||
+        !gru_ptrs_ok(gr->encoder) || !gru_ptrs_ok(gr->decoder) || !gr->base_weight || !gr->base_bias || !gr->rle_weight || !gr->rle_bias)
+        return fail(HB_ERR_INVALID_ARGUMENT, "hb_train_step_chunk: null weight or gradient pointer");
+    size_t need = 0;
+    int rc;
+    if ((rc = hb_train_workspace_bytes(h, B, W, &need))) return rc;
+    if (!workspace_dev || workspace_bytes < need)
+        return fail(HB_ERR_WORKSPACE, "hb_train_step_chunk: workspace %zu bytes < required %zu", workspace_bytes, need);
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TrainWorkspace ws = train_carve(reinterpret_cast<void*>(hb::align_up(reinterpret_cast<size_t>(workspace_dev))), B, W);
+    const int F = h->features, H = hb::H, G = hb::G;
+    const int64_t M = B * W;
+    const dim3 grid_rec((unsigned)((B + hb::REC_WINDOWS - 1) / hb::REC_WINDOWS), 2);
+    float* logit_b = base_logits_dev ? base_logits_dev : ws.logit_b;
+    float* logit_r = rle_logits_dev ? rle_logits_dev : ws.logit_r;
+    const int split = 16;                                     // k-splits of the weight-gradient GEMMs (K = B * W)
+
+    // ---- forward (TransducerModel.py:60-79), activations kept ----
+    for (int d = 0; d < 2; ++d)
+        gemm(s, x_dev, F, 1, w->encoder.weight_ih[d], 1, F, ws.gi1 + d * G, 2 * G, 1, w->encoder.bias_ih[d], M, G, F, 1);
+    hb::train::gru_forward_save_kernel<<<grid_rec, hb::REC_THREADS, 0, s>>>(ws.gi1, w->encoder.weight_hh[0], w->encoder.weight_hh[1],
+        w->encoder.bias_hh[0], w->encoder.bias_hh[1], h_in_dev, ws.h_enc, ws.y1, ws.sv1, B, W);
+    for (int d = 0; d < 2; ++d)
+        gemm(s, ws.y1, 2 * H, 1, w->decoder.weight_ih[d], 1, 2 * H, ws.gi2 + d * G, 2 * G, 1, w->decoder.bias_ih[d], M, G, 2 * H, 1);
+    hb::train::gru_forward_save_kernel<<<grid_rec, hb::REC_THREADS, 0, s>>>(ws.gi2, w->decoder.weight_hh[0], w->decoder.weight_hh[1],
+        w->decoder.bias_hh[0], w->decoder.bias_hh[1], ws.h_enc, h_out_dev, ws.y2, ws.sv2, B, W);
+    gemm(s, ws.y2, 2 * H, 1, w->base_weight, 1, 2 * H, logit_b, hb::NBASE, 1, w->base_bias, M, hb::NBASE, 2 * H, 1);
+    gemm(s, ws.y2, 2 * H, 1, w->rle_weight, 1, 2 * H, logit_r, hb::NRLE, 1, w->rle_bias, M, hb::NRLE, 2 * H, 1);
+
+    // ---- losses (train.py:121-126, 192-198) and their gradient ----
+    HB_CUDA(cudaMemsetAsync(ws.sums, 0, 4 * sizeof(float), s));
+    const unsigned ce_blocks = (unsigned)((M + 255) / 256);
+    hb::train::ce_kernel<1><<<ce_blocks, 256, 0, s>>>(logit_b, logit_r, label_base_dev, label_rle_dev, rle_class_weights_dev, M, ws.sums, nullptr);
+    hb::train::loss_finish_kernel<<<1, 1, 0, s>>>(ws.sums, loss_dev);
+    hb::train::ce_kernel<2><<<ce_blocks, 256, 0, s>>>(logit_b, logit_r, label_base_dev, label_rle_dev, rle_class_weights_dev, M, ws.sums, ws.dlogits);
+
+    // ---- backward: heads ----
+    auto zero = [&](const float* p, size_t n) { return cudaMemsetAsync(const_cast<float*>(p), 0, n * sizeof(float), s); };
+    HB_CUDA(zero(gr->base_weight, (size_t)hb::NBASE * 2 * H)); HB_CUDA(zero(gr->base_bias, hb::NBASE));
+    HB_CUDA(zero(gr->rle_weight, (size_t)hb::NRLE * 2 * H)); HB_CUDA(zero(gr->rle_bias, hb::NRLE));
+    float* g_bw = const_cast<float*>(gr->base_weight); float* g_bb = const_cast<float*>(gr->base_bias);
+    float* g_rw = const_cast<float*>(gr->rle_weight); float* g_rb = const_cast<float*>(gr->rle_bias);
+    gemm(s, ws.dlogits, 1, hb::NCLS, ws.y2, 2 * H, 1, g_bw, 2 * H, 1, nullptr, hb::NBASE, 2 * H, M, split);
+    gemm(s, ws.dlogits + hb::NBASE, 1, hb::NCLS, ws.y2, 2 * H, 1, g_rw, 2 * H, 1, nullptr, hb::NRLE, 2 * H, M, split);
+    colsum(s, ws.dlogits, M, hb::NBASE, hb::NCLS, g_bb);
+    colsum(s, ws.dlogits + hb::NBASE, M, hb::NRLE, hb::NCLS, g_rb);
+    // dy2 = dl_base . W_base + dl_rle . W_rle   (the second product accumulates)
+    gemm(s, ws.dlogits, hb::NCLS, 1, w->base_weight, 2 * H, 1, ws.dy, 2 * H, 1, nullptr, M, 2 * H, hb::NBASE, 1);
+    gemm(s, ws.dlogits + hb::NBASE, hb::NCLS, 1, w->rle_weight, 2 * H, 1, ws.dy, 2 * H, 1, nullptr, M, 2 * H, hb::NRLE, -1);
+
+    // ---- backward: one GRU layer (recurrence kernel, then the weight-gradient GEMMs) ----
+    auto layer_backward = [&](const hb_gru_weights& lw, const hb_gru_weights& lg, const float* in, int K, const float* dh_n,
+                              const float* sv, const float* y, const float* h0, float* dh0) -> int {
+        hb::train::gru_backward_kernel<<<grid_rec, hb::REC_THREADS, 0, s>>>(ws.dy, dh_n, sv, y, h0, lw.weight_hh[0], lw.weight_hh[1],
+                                                                           ws.dgi, ws.dgh, ws.hprev, dh0, B, W);
+        for (int d = 0; d < 2; ++d) {
+            float* g_wih = const_cast<float*>(lg.weight_ih[d]); float* g_whh = const_cast<float*>(lg.weight_hh[d]);
+            float* g_bih = const_cast<float*>(lg.bias_ih[d]); float* g_bhh = const_cast<float*>(lg.bias_hh[d]);
+            HB_CUDA(zero(g_wih, (size_t)G * K)); HB_CUDA(zero(g_whh, (size_t)G * H)); HB_CUDA(zero(g_bih, G)); HB_CUDA(zero(g_bhh, G));
+            gemm(s, ws.dgi + d * G, 1, 2 * G, in, K, 1, g_wih, K, 1, nullptr, G, K, M, split);                    // dW_ih = dgi^T . x
+            gemm(s, ws.dgh + d * G, 1, 2 * G, ws.hprev + d * H, 2 * H, 1, g_whh, H, 1, nullptr, G, H, M, split);  // dW_hh = dgh^T . h_prev
+            colsum(s, ws.dgi + d * G, M, G, 2 * G, g_bih);
+            colsum(s, ws.dgh + d * G, M, G, 2 * G, g_bhh);
+        }
+        return HB_OK;
+    };
+    // decoder: dy = dy2, no gradient through the returned state (the loss does not see it; train.py:206 detaches it)
+    if ((rc = layer_backward(w->decoder, gr->decoder, ws.y1, 2 * H, nullptr, ws.sv2, ws.y2, ws.h_enc, ws.dh_dec0))) return rc;
+    // gradient wrt the encoder output: dy1 = sum_d dgi2[:, d] . W_ih_dec[d]   (overwrites dy; the second direction accumulates)
+    gemm(s, ws.dgi, 2 * G, 1, w->decoder.weight_ih[0], 2 * H, 1, ws.dy, 2 * H, 1, nullptr, M, 2 * H, G, 1);
+    gemm(s, ws.dgi + G, 2 * G, 1, w->decoder.weight_ih[1], 2 * H, 1, ws.dy, 2 * H, 1, nullptr, M, 2 * H, G, -1);
+    // encoder: its final state fed the decoder's initial state
+    if ((rc = layer_backward(w->encoder, gr->encoder, x_dev, F, ws.dh_dec0, ws.sv1, ws.y1, h_in_dev, nullptr))) return rc;
+    h->launches += 40;
+    HB_CUDA(cudaGetLastError());
     return HB_OK;
 }
 

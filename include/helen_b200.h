@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 2
+#define HB_ABI_VERSION 3
 
 typedef enum hb_status {
     HB_OK = 0,
@@ -123,6 +123,26 @@ int hb_forward_chunk(hb_handle *handle, const float *x_dev, const float *h_in_de
                      int64_t B, int W, float *base_logits_dev, float *rle_logits_dev,
                      float *h_out_dev, void *workspace_dev, size_t workspace_bytes,
                      void *stream);
+
+/* Replaces the per-chunk body of the training loop, helen/modules/python/models/train.py:189-201:
+ *   output_base, output_rle, hidden = transducer_model(image_chunk, hidden)              (TransducerModel.py:60-79)
+ *   loss = CrossEntropyLoss()(output_base, label_base) + CrossEntropyLoss(weight=CLASS_WEIGHTS)(output_rle, label_rle)
+ *   loss.backward()
+ * for one chunk: forward with the activations kept, both losses (mean reduction; the run-length loss is the weighted
+ * mean torch computes, Options.py:29), and back-propagation through heads, decoder and encoder (both directions).
+ * `weights_dev` / `grads_dev` hold DEVICE pointers in the hb_weights layout: the caller's own parameter tensors and the
+ * tensors that receive d loss / d parameter (overwritten, not accumulated) -- no copy of the parameters is kept, so an
+ * optimizer may update them between calls (train.py:202).  The initial state gets no gradient (train.py:206 detaches it).
+ *   x_dev float [B, W, F]; h_in_dev float [B, 2, H] or NULL (zeros); labels int64 [B, W]; rle_class_weights_dev float [n_rle]
+ *   loss_dev float [3] = {loss, loss_base, loss_rle}; h_out_dev float [B, 2, H];
+ *   base_logits_dev float [B, W, 5] / rle_logits_dev float [B, W, 11] or NULL.
+ * fp32 on the FMA pipes (gradients match autograd to ~1e-5 relative); image_features comes from the handle. */
+int hb_train_workspace_bytes(const hb_handle *handle, int64_t B, int W, size_t *out);
+int hb_train_step_chunk(hb_handle *handle, const hb_weights *weights_dev, const hb_weights *grads_dev,
+                        const float *x_dev, const float *h_in_dev, const int64_t *label_base_dev,
+                        const int64_t *label_rle_dev, const float *rle_class_weights_dev, int64_t B, int W,
+                        float *loss_dev, float *h_out_dev, float *base_logits_dev, float *rle_logits_dev,
+                        void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* Number of kernel launches issued by this handle since creation (bench.py reports the
  * per-step delta as "gpu_launches"). */

@@ -93,3 +93,28 @@ def test_first_index_tie_break():
     out = predict_windows(OracleWeights.from_state_dict(state), case["images"])
     assert (out["base_label"] == 0).all() and (out["rle_label"] == 0).all()
     assert np.allclose(out["base_prob"], 0.2) and np.allclose(out["rle_prob"], 1 / 11)
+
+
+def test_port_autograd_reproduces_reference_training_fixture():
+    """The training-step oracle (autograd of the torch port with the reference's two criteria, train.py:121-126)
+    against the fixture minted from the reference model class (tests/golden/make_golden_train.py)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import TransducerPort
+    fx = np.load(os.path.join(GOLDEN_DIR, "train_F10_B6_W100.npz"))
+    state = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN_DIR, f"model_{str(fx['model'])}.npz")).items()}
+    port = TransducerPort(10)
+    port.load_state_dict(state)
+    ob, orl, oh = port(torch.from_numpy(fx["x"]), torch.from_numpy(fx["hidden"]))
+    lb, lr = torch.from_numpy(fx["label_base"]), torch.from_numpy(fx["label_rle"])
+    loss_b = torch.nn.CrossEntropyLoss()(ob.reshape(-1, 5), lb.reshape(-1))
+    loss_r = torch.nn.CrossEntropyLoss(weight=torch.from_numpy(fx["class_weights"]))(orl.reshape(-1, 11), lr.reshape(-1))
+    (loss_b + loss_r).backward()
+    np.testing.assert_allclose([loss_b.item() + loss_r.item(), loss_b.item(), loss_r.item()], fx["loss_f32"], rtol=1e-6)
+    assert np.abs(oh.detach().numpy() - fx["hidden_out_f32"]).max() <= 1e-6
+    for name, p in port.named_parameters():
+        ref = fx[f"grad_f32/{name}"]
+        got = p.grad.double().flatten()
+        assert np.abs(got[torch.from_numpy(fx[f"grad_idx/{name}"])].numpy() - ref[2:]).max() <= 1e-6 * (np.abs(ref[2:]).max() + 1e-12), name
+        # fp32 vs fp64 of the reference itself: the noise floor the CUDA path is compared under
+        assert abs(ref[0] - fx[f"grad_f64/{name}"][0]) <= 1e-4 * fx[f"grad_f64/{name}"][0], name
