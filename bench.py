@@ -10,7 +10,7 @@ A *step* is one pass of the hot path over one batch of synthetic pileup windows
 Printed JSON line (rank 0):
   value   windows/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed per step
   e2e     same metric through the host-buffer entry (WindowPredictor.predict_host ->
-          hb_predict_windows_host): pageable host images in, host labels out, copies in the timed region
+          hb_predict_windows_host): pinned host images in, host labels out, copies in the timed region
   roofline      algorithmic FLOP/window x windows per launch / kernel time, vs measured bf16 peak
   cpu_baseline  the oracle's torch-CPU port of the reference predict loop on this box's host cores
 
@@ -217,7 +217,7 @@ def run_native(args, rank, world, local_rank):
 
     pred = WindowPredictor(random_state_dict(args.features, seed=0), device=local_rank, engine=args.engine)
     engine = pred.engine
-    host_images = synthetic_images(args.batch, args.features, seed=1000 + rank)
+    host_images = synthetic_images(args.batch, args.features, seed=1000 + rank).pin_memory()   # e2e inputs start in pinned host memory
     images = host_images.to(dev)
     host_np = host_images.numpy()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -265,7 +265,7 @@ def run_native(args, rank, world, local_rank):
     torch.cuda.synchronize()
     plan = pred.last_launch_plan()
 
-    # end to end through the host-buffer entry: pageable numpy in, numpy labels out
+    # end to end through the host-buffer entry: pinned host images in (numpy view), numpy labels out
     for _ in range(max(1, args.warmup // 2)):
         pred.predict_host(host_np)
     barrier()

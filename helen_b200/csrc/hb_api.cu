@@ -409,9 +409,22 @@ int hb_predict_windows_host(hb_handle* h, const uint8_t* images_host, int64_t B,
     if ((rc = grow(&h->stage_workspace, &h->cap_workspace, ws_bytes, false))) return rc;
     if (want_prob && (rc = grow(&h->stage_prob_dev, &h->cap_prob, pb_bytes + pr_bytes, false))) return rc;
 
-    // pageable caller memory -> pinned staging -> device (the reference's images.to(device))
-    std::memcpy(h->stage_images_host, images_host, img_bytes);
-    HB_CUDA(cudaMemcpyAsync(h->stage_images_dev, h->stage_images_host, img_bytes, cudaMemcpyHostToDevice, s));
+    // caller memory -> device (the reference's images.to(device)).  Page-locked caller memory (torch pin_memory, the
+    // DataLoader's pinned batches) is copied from directly; pageable memory goes through the pinned staging buffer in
+    // slices, so the host memcpy of one slice overlaps the DMA of the previous one.
+    cudaPointerAttributes attr{};
+    const bool caller_pinned = cudaPointerGetAttributes(&attr, images_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();                                      // (unregistered host memory reports an error on old drivers)
+    if (caller_pinned) {
+        HB_CUDA(cudaMemcpyAsync(h->stage_images_dev, images_host, img_bytes, cudaMemcpyHostToDevice, s));
+    } else {
+        const size_t slice = std::max<size_t>((img_bytes / 8 + 4095) / 4096 * 4096, (size_t)1 << 20);
+        for (size_t off = 0; off < img_bytes; off += slice) {
+            const size_t n = std::min(slice, img_bytes - off);
+            std::memcpy(h->stage_images_host + off, images_host + off, n);
+            HB_CUDA(cudaMemcpyAsync(h->stage_images_dev + off, h->stage_images_host + off, n, cudaMemcpyHostToDevice, s));
+        }
+    }
     float* pb = want_prob ? h->stage_prob_dev : nullptr;
     float* pr = want_prob ? reinterpret_cast<float*>(reinterpret_cast<char*>(h->stage_prob_dev) + pb_bytes) : nullptr;
     rc = hb_predict_windows(h, h->stage_images_dev, B, T, W, J, h->stage_labels_dev, h->stage_labels_dev + lab_bytes,

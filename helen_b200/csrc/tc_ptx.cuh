@@ -101,8 +101,15 @@ __device__ __forceinline__ void red_relaxed_gpu_add(unsigned long long* p, unsig
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Every cross-CTA wait of the chunk-loop kernel is bounded: if the producer never shows up (the launch was not fully
+// co-resident, or a role died) the kernel traps after ~4 s instead of hanging the device.
+constexpr long long SPIN_LIMIT_CYCLES = 8000000000ll;
 __device__ __forceinline__ void spin_until_ge(const unsigned long long* flag, unsigned long long need) {
-    while (ld_acquire_gpu(flag) < need) __nanosleep(100);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(flag) < need) {
+        __nanosleep(100);
+        if (clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
+    }
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 template <int kPending>

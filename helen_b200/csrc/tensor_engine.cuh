@@ -294,10 +294,12 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 int e = 0;
                 if (lane == 0) {
                     const long long t_ = acct ? clock64() : 0;
+                    const long long t_spin = clock64();
                     while (true) {
                         if (front < back && vb >= need_of(jb, chunk)) { e = eb; --back; break; }
                         if (vf >= need_of(jf, chunk)) { e = ef; ++front; break; }
                         __nanosleep(100);
+                        if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap();
                         vf = tc::ld_relaxed_gpu(flag_of(jf)); vb = tc::ld_relaxed_gpu(flag_of(jb));
                     }
                     if (acct) t_wait[1] += clock64() - t_;
