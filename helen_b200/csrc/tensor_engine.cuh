@@ -119,6 +119,20 @@ constexpr int PROJ_STAGES = 2;                    // full-K tiles; the K-half jo
 constexpr int PROJ_PUBLISH_BATCH = 8;
 constexpr int PROJ_W_COL0 = 128;
 
+// Encoder input projection inside the chunk-loop kernel ("pixel jobs"): while the encoder of chunk k runs, the projection
+// role is idle until the first decoder jobs become runnable; it uses that time to project the image columns the encoder of
+// chunk k+1 adds (J new columns), so only the first chunk's columns are projected before the kernel starts.
+constexpr int PX_R = 8;                          // at most ceil(J / 8) + 1 new column tiles per chunk
+constexpr int PX_W_COL0 = 384;                   // TMEM columns of the encoder's W_ih block (after the decoder's 256)
+struct ProjPixelArgs {
+    const uint8_t* ximg; int64_t wg_stride; int blk_bytes, Kp;   // pixel operand image (no-swizzle, lbo 128)
+    const uint32_t* w_tmem; const float* scale_row; const float* bias_row;
+    float* gi; int cols, tiles;                  // gi image of all `cols` image columns (`tiles` column tiles)
+    int col_step;                                // J
+    unsigned long long* flags;                   // [group][tile][direction] += 1 per gate block (3 when complete)
+    const int* wgs_of_worker;                    // [workers] window groups whose pixel jobs the worker owns
+};
+
 struct ProjArgs {
     // operand image addressing (bytes): block of (group wg, K-slice d, part p, column t) at
     // in_base + wg * in_wg_stride + d * in_dir_stride + p * in_part_stride + t * blk_bytes  (columns contiguous)
@@ -149,28 +163,33 @@ struct ProjArgs {
     int n_chunks;                  // a chunk's columns count from chunk * W in the progress counters
     unsigned long long* tile_flags;   // [group][tile][decoder direction]: += 1 per job and gate block (3 blocks x 2 K-halves = 6 per chunk)
     long long* dbg;                   // HB_DEBUG_TIMELINE: worker 0 records when it finished each chunk
+    ProjPixelArgs px;                 // px.ximg == nullptr: no pixel jobs
+    int col_tiles;                    // tile mode: project only the first col_tiles column tiles (0 = all)
 };
 
 __host__ __device__ constexpr int pack_proj_job(int wg, int tile, int src_dir) { return wg | (tile << 16) | (src_dir << 28); }
 
-struct ProjJob { int64_t wg; int t0, valid, src_dir; bool split; };
+struct ProjJob { int64_t wg; int t0, valid, src_dir; bool split, pixel; };
 
 // jobs of one worker per chunk, and the idx-th of them in table / tile order
 __device__ __forceinline__ int proj_count(const ProjArgs& a, int worker, int n_workers) {
     if (a.jobs != nullptr) return __ldg(a.job_offsets + worker + 1) - __ldg(a.job_offsets + worker);
-    const int64_t n_tiles = a.n_wg * ((a.W + 7) >> 3);
+    const int tiles_t = a.col_tiles > 0 ? a.col_tiles : ((a.W + 7) >> 3);
+    const int64_t n_tiles = a.n_wg * tiles_t;
     return n_tiles > worker ? (int)((n_tiles - worker + n_workers - 1) / n_workers) : 0;
 }
+// column tiles of the pixel image projected before chunk k's encoder starts
+__device__ __forceinline__ int px_done(const ProjArgs& a, int k) { return min((a.px.col_step * k + a.W + 7) >> 3, a.px.tiles); }
 __device__ __forceinline__ ProjJob proj_decode(const ProjArgs& a, int e) {
     ProjJob j;
-    j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.src_dir = (e >> 28) & 1; j.split = true;
-    j.valid = min(8, a.W - j.t0);
+    j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.src_dir = (e >> 28) & 1; j.split = true; j.pixel = (e >> 29) & 1;
+    j.valid = min(8, (j.pixel ? a.px.cols : a.W) - j.t0);
     return j;
 }
 __device__ __forceinline__ ProjJob proj_tile_job(const ProjArgs& a, int worker, int n_workers, int idx) {
     const int64_t tile = worker + (int64_t)idx * n_workers;
     ProjJob j;
-    j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.src_dir = 0; j.split = false;
+    j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.src_dir = 0; j.split = false; j.pixel = false;
     j.valid = min(8, a.W - j.t0);
     return j;
 }
@@ -220,27 +239,33 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     tc::named_barrier_sync(1, PROJ_THREADS);
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (warp < 4) {   // weight block -> TMEM, thread = gate row; 32 words in flight per round trip
+    const bool pixels = split && a.px.ximg != nullptr;
+    const int kwords_px = pixels ? a.px.Kp >> 1 : 0;
+    if (warp < 4) {   // weight block(s) -> TMEM, thread = gate row; 32 words in flight per round trip
         const int row = warp * 32 + lane;
-        for (int term = 0; term < 2; ++term) {
-            const uint32_t dst = tmem + ((uint32_t)(warp * 32) << 16) + PROJ_W_COL0 + term * kwords;
-            int c = 0;
-            for (; c + 32 <= kwords; c += 32) {
-                uint32_t r[32];
-                const uint4* p = reinterpret_cast<const uint4*>(w_tmem + wih_word_index(blk, term, row, c, kwords));
+        auto upload = [&](const uint32_t* wsrc, int kw, int col0) {
+            for (int term = 0; term < 2; ++term) {
+                const uint32_t dst = tmem + ((uint32_t)(warp * 32) << 16) + col0 + term * kw;
+                int c = 0;
+                for (; c + 32 <= kw; c += 32) {
+                    uint32_t r[32];
+                    const uint4* p = reinterpret_cast<const uint4*>(wsrc + wih_word_index(blk, term, row, c, kw));
 #pragma unroll
-                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-                tc::tmem_st16(dst + c, r);
-                tc::tmem_st16(dst + c + 16, r + 16);
-            }
-            for (; c < kwords; c += 16) {
-                uint32_t r[16];
-                const uint4* p = reinterpret_cast<const uint4*>(w_tmem + wih_word_index(blk, term, row, c, kwords));
+                    for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                    tc::tmem_st16(dst + c, r);
+                    tc::tmem_st16(dst + c + 16, r + 16);
+                }
+                for (; c < kw; c += 16) {
+                    uint32_t r[16];
+                    const uint4* p = reinterpret_cast<const uint4*>(wsrc + wih_word_index(blk, term, row, c, kw));
 #pragma unroll
-                for (int v = 0; v < 4; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-                tc::tmem_st16(dst + c, r);
+                    for (int v = 0; v < 4; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+                    tc::tmem_st16(dst + c, r);
+                }
             }
-        }
+        };
+        upload(w_tmem, kwords, PROJ_W_COL0);
+        if (pixels) upload(a.px.w_tmem, kwords_px, PX_W_COL0);
         tc::tmem_st_wait();
     }
     tc::pdl_grid_dependency_wait();                          // activations / gi buffers belong to upstream kernels
@@ -251,8 +276,14 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     if (a.pair) tc::cluster_sync_all();                      // the peer's mbarriers exist before anything is multicast at them
 
     const int n_chunks = a.n_chunks > 0 ? a.n_chunks : 1;
-    const int n_jobs = proj_count(a, worker, n_workers);     // per chunk
+    const int n_table = proj_count(a, worker, n_workers);    // entries of this worker's list
     const int job0 = split ? __ldg(a.job_offsets + worker) : 0;
+    // list = [pixel entries: PX_R relative tiles x my window groups, tile-major][decoder entries in runnable order];
+    // chunk k uses the first px_tiles(k) x my_groups pixel entries and all decoder entries
+    const int px_wgs = pixels ? __ldg(a.px.wgs_of_worker + worker) : 0;
+    const int n_dec = n_table - px_wgs * PX_R;
+    auto px_count = [&](int chunk) { return (pixels && chunk + 1 < n_chunks) ? px_wgs * (px_done(a, chunk + 1) - px_done(a, chunk)) : 0; };
+    auto table_at = [&](int i, int n_px) { return __ldg(a.jobs + job0 + (i < n_px ? i : px_wgs * PX_R + (i - n_px))); };
     ProjJob j;
     // HB_DEBUG_TIMELINE: worker 0 / block 0 adds up the cycles each role spends at its wait points (slots 7200 + 8 role + k)
     const bool acct = a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0;
@@ -278,13 +309,21 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         auto flag_of = [&](const ProjJob& q) { return a.progress + ((q.wg * WG) / a.rec_n) * 2 + q.src_dir; };
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const int n_px = split ? px_count(chunk) : 0;
+        const int n_jobs = split ? n_px + n_dec : n_table;
+        const int px_tile0 = pixels ? px_done(a, chunk) : 0;
         int front = 0, back = n_jobs - 1, ef = 0, eb = 0;
         ProjJob jf{}, jb{};
         unsigned long long vf = 0, vb = 0;
+        auto entry = [&](int i) {                            // pixel entries hold a relative tile: make it absolute
+            int e = table_at(i, n_px);
+            if ((e >> 29) & 1) e += px_tile0 << 16;
+            return e;
+        };
         auto look = [&]() {                                  // lane 0: both ends of what is left, counters requested
-            ef = __ldg(a.jobs + job0 + front); eb = __ldg(a.jobs + job0 + back);
+            ef = entry(front); eb = entry(back);
             jf = proj_decode(a, ef); jb = proj_decode(a, eb);
-            vf = tc::ld_relaxed_gpu(flag_of(jf)); vb = tc::ld_relaxed_gpu(flag_of(jb));
+            vf = jf.pixel ? ~0ull : tc::ld_relaxed_gpu(flag_of(jf)); vb = jb.pixel ? 0ull : tc::ld_relaxed_gpu(flag_of(jb));
         };
         if (split && lane == 0 && n_jobs > 0) look();
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
@@ -296,11 +335,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                     const long long t_ = acct ? clock64() : 0;
                     const long long t_spin = clock64();
                     while (true) {
-                        if (front < back && vb >= need_of(jb, chunk)) { e = eb; --back; break; }
-                        if (vf >= need_of(jf, chunk)) { e = ef; ++front; break; }
+                        if (front < back && !jb.pixel && vb >= need_of(jb, chunk)) { e = eb; --back; break; }
+                        if (jf.pixel || vf >= need_of(jf, chunk)) { e = ef; ++front; break; }    // pixel jobs wait for nothing
                         __nanosleep(100);
                         if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap();
-                        vf = tc::ld_relaxed_gpu(flag_of(jf)); vb = tc::ld_relaxed_gpu(flag_of(jb));
+                        vf = tc::ld_relaxed_gpu(flag_of(jf)); vb = jb.pixel ? 0ull : tc::ld_relaxed_gpu(flag_of(jb));
                     }
                     if (acct) t_wait[1] += clock64() - t_;
                     job_ring[it & 15] = e;
@@ -312,16 +351,20 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 j = proj_tile_job(a, worker, n_workers, idx);
             }
             const long long t_issue = acct ? clock64() : 0;
-            if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * PARTS * n_dirs * blk_bytes));
+            // geometry of the job's stage: decoder jobs [part hi, lo][K-slice][8 columns][2 KB], pixel jobs [8 columns][xblk]
+            const int jparts = j.pixel ? 1 : PARTS, jdirs = j.pixel ? 1 : n_dirs, jblk = j.pixel ? a.px.blk_bytes : blk_bytes;
+            if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * jparts * jdirs * jblk));
             __syncwarp();
-            if (lane < 2 * PARTS * n_dirs) {
+            if (lane < 2 * jparts * jdirs) {
                 // the job's columns are contiguous per (part, K-slice); two copies of four columns each (one big copy is
                 // served by a single copy engine queue and was slower)
-                const int half = lane & 1, pd = lane >> 1, part = pd / n_dirs, d = pd % n_dirs;
+                const int half = lane & 1, pd = lane >> 1, part = pd / jdirs, d = pd % jdirs;
                 const int cols = min(4, j.valid - 4 * half);
-                uint8_t* dst = smem + stage * stage_bytes + part * part_bytes + d * slice_bytes + half * 4 * blk_bytes;
-                const uint8_t* src = in_base + j.wg * in_wg_stride + (split ? j.src_dir : d) * in_dir_stride + part * in_part_stride + (int64_t)(j.t0 + 4 * half) * blk_bytes;
-                const uint32_t bytes = (uint32_t)(max(cols, 0) * blk_bytes);
+                uint8_t* dst = smem + stage * stage_bytes + (j.pixel ? 0 : part * part_bytes + d * slice_bytes) + half * 4 * jblk;
+                const uint8_t* src = j.pixel
+                    ? a.px.ximg + j.wg * a.px.wg_stride + (int64_t)(j.t0 + 4 * half) * jblk
+                    : in_base + j.wg * in_wg_stride + (split ? j.src_dir : d) * in_dir_stride + part * in_part_stride + (int64_t)(j.t0 + 4 * half) * jblk;
+                const uint32_t bytes = (uint32_t)(max(cols, 0) * jblk);
                 // pair mode: the two CTAs split the copies and multicast them to both
                 const bool mine = cols > 0 && (!a.pair || (uint32_t)(lane & 1) == pair_rank);
                 if (mine) {
@@ -362,27 +405,31 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             n_pending = keep;
         };
         int it = 0;
-        for (int chunk = 0; chunk < n_chunks; ++chunk)
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const int n_jobs = split ? px_count(chunk) + n_dec : n_table;
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int sb = it & 1;
             const uint32_t par = (uint32_t)((it >> 1) & 1);
             HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
             j = split ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
-            float* out = j.src_dir ? a.gi_b : gi;
-            if (lane < 8 && j.t0 + lane < W)
-                tc::bulk_s2g(out + gi_block(j.wg, W, j.t0 + lane, blk), staging + sb * PROJ_STG_BYTES + lane * (GI_BLK_FLOATS * 4), GI_BLK_FLOATS * 4);
+            float* out = j.pixel ? a.px.gi : (j.src_dir ? a.gi_b : gi);
+            const int out_cols = j.pixel ? a.px.cols : W;
+            if (lane < 8 && j.t0 + lane < out_cols)
+                tc::bulk_s2g(out + gi_block(j.wg, out_cols, j.t0 + lane, blk), staging + sb * PROJ_STG_BYTES + lane * (GI_BLK_FLOATS * 4), GI_BLK_FLOATS * 4);
             tc::bulk_commit();
             // the PREVIOUS job's copies have read their staging buffer (this job's read overlaps the next epilogue)
             HB_TIMED(1, tc::bulk_wait_read_pending<1>());
             __syncwarp();
             if (lane == 0 && it > 0) tc::mbar_arrive(stg_empty + (sb ^ 1));
             if (a.tile_flags != nullptr) {
-                pending[n_pending++] = a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
+                pending[n_pending++] = j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
+                                               : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
                 if (idx == n_jobs - 1) HB_TIMED(2, publish(0));                      // last job of the chunk
                 // (publishing the backlog jobs one by one so the decoder sees its first tiles sooner was measured: no gain)
                 else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2));   // copies issued two jobs ago have normally landed: no stall
             }
             if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
+        }
         }
         publish(0);
         if (lane < 32) tc::bulk_wait0();                     // the kernel's results are complete when the role returns
@@ -392,7 +439,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
         const int ksteps = split ? 8 : (Kp >> 4);
         int it = 0;
-        for (int chunk = 0; chunk < n_chunks; ++chunk)
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const int n_jobs = split ? px_count(chunk) + n_dec : n_table;
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int stage = it % n_stages, acc = it & 1;
             HB_TIMED(0, tc::mbar_wait(a_full + stage, (uint32_t)((it / n_stages) & 1)));
@@ -424,7 +472,13 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                         for (int ks = 0; ks < ks_n; ++ks) tc::mma_f16_ts(d, a_hi + ks * 8, d_lo + koff(ks), idesc, 1);
                     }
                 };
-                if (split) issue(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
+                if (j.pixel) {                                // pixels: no-swizzle image, 2 terms (uint8 is exact in fp16)
+                    const uint64_t dx = tc::smem_desc(sbase, 128, a.px.blk_bytes);
+                    const uint32_t ax = tmem + PX_W_COL0;
+                    const int ksx = a.px.Kp >> 4;
+                    for (int ks = 0; ks < ksx; ++ks) tc::mma_f16_ts(d, ax + ks * 8, dx + (uint64_t)(ks * 2 * 128 / 16), idesc, ks != 0);
+                    for (int ks = 0; ks < ksx; ++ks) tc::mma_f16_ts(d, ax + kwords_px + ks * 8, dx + (uint64_t)(ks * 2 * 128 / 16), idesc, 1);
+                } else if (split) issue(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
                 else if (n_dirs == 2 && ksteps == 16) issue(std::integral_constant<int, 16>{}, std::integral_constant<int, 2>{});
                 else issue(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});     // pixels: K = padded feature count
                 if (a.pair) tc::mma_commit_multicast(a_empty + stage, (uint16_t)3);   // both loaders wait for both consumers
@@ -433,13 +487,16 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             }
             __syncwarp();
         }
+        }
         HB_ROLE_REPORT(1);
     } else {
         // ===================== epilogue =====================
         const int r = warp * 32 + lane;                      // gate row within the block == TMEM lane
-        const float sc = scale_row[blk * 128 + r], bi = bias_row[blk * 128 + r];
+        const float sc_dec = scale_row[blk * 128 + r], bi_dec = bias_row[blk * 128 + r];
+        const float sc_px = pixels ? a.px.scale_row[blk * 128 + r] : 0.f, bi_px = pixels ? a.px.bias_row[blk * 128 + r] : 0.f;
         int it = 0;
-        for (int chunk = 0; chunk < n_chunks; ++chunk)
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        const int n_jobs = split ? px_count(chunk) + n_dec : n_table;
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int acc = it & 1, sb = it & 1;
             if (it >= 2) HB_TIMED(0, tc::mbar_wait(stg_empty + sb, (uint32_t)((it / 2 - 1) & 1)));   // arrives once job it-1 is being stored
@@ -448,7 +505,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
             float* stg = reinterpret_cast<float*>(staging + sb * PROJ_STG_BYTES) + r;
-            const float add = j.src_dir ? 0.f : bi;          // the bias rides on the forward-source half (or the only one)
+            const float sc = j.pixel ? sc_px : sc_dec;
+            const float add = j.pixel ? bi_px : (j.src_dir ? 0.f : bi_dec);   // the bias rides on the forward-source half (or the only one)
 #pragma unroll 2
             for (int c8 = 0; c8 < PROJ_NT; c8 += 8) {       // 8 accumulator columns = the 8 windows of column t0 + c8/8
                 float v[8];
@@ -461,6 +519,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(acc_empty + acc); tc::mbar_arrive(stg_full + sb); }
+        }
         }
         if (warp == 0) HB_ROLE_REPORT(2);
     }
@@ -520,7 +579,11 @@ struct RecLayer {
     uint8_t* yimg[2];              // operand image of the layer output: [0] even chunks, [1] odd chunks
     unsigned long long* progress;  // [ctas][2 dirs] columns whose output has landed in yimg (+ epoch + chunk * W), or nullptr
     // chunk-loop kernel only (counters in global memory, see tc_chunkloop_kernel):
-    const unsigned long long* tile_flags;      // decoder: gi' tile (group, tile, dir) of chunk k is ready at >= 6 (k + 1)
+    // gi' tiles are announced by the projection role: tile (group, column tile, dir) is ready for chunk k when its counter
+    // is >= flag_need_base + flag_need_per_chunk (k + 1).  Decoder: tiles of the chunk's own columns, 6 per chunk (3 gate
+    // blocks x 2 K-halves).  Encoder (pixel jobs): tiles of ABSOLUTE image columns, 3 once; tiles below flag_skip_tiles were
+    // projected before the kernel started.
+    const unsigned long long* tile_flags; int flag_tiles, flag_abs, flag_skip_tiles; unsigned long long flag_need_base, flag_need_per_chunk;
     const unsigned long long* heads_done; int heads_per_chunk;   // decoder: yimg[k & 1] reusable when >= heads_per_chunk (k - 1)
     const unsigned long long* consumed_flags;  // encoder: tile flags (both directions) that tell yimg of chunk k - 1 has been read
 };
@@ -680,10 +743,12 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % GI_STAGES;
             if (s == GI_STAGES) { __syncthreads(); synced = true; }
-            if (L.tile_flags != nullptr && (s == 0 || (t & 7) == (dir ? 7 : 0))) {
-                // decoder in the chunk-loop kernel: the projection CTAs announce finished gi' tiles
+            const int col = L.flag_abs ? gi_col0 + t : t;
+            if (L.tile_flags != nullptr && (s == 0 || (col & 7) == (dir ? 7 : 0)) && (col >> 3) >= L.flag_skip_tiles) {
+                // chunk-loop kernel: the projection CTAs announce finished gi' tiles
                 if (lane < NG && cta_x * NG + lane < ra.n_wg)
-                    tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * ra.tiles_t + (t >> 3)) * 2 + dir, 6ull * (chunk + 1));
+                    tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * L.flag_tiles + (col >> 3)) * 2 + dir,
+                                      L.flag_need_base + L.flag_need_per_chunk * (unsigned long long)(chunk + 1));
                 // (no proxy fence: the bulk loads below are issued after the acquire and read L2, where the producer's
                 // completed bulk stores already are)
                 __syncwarp();
@@ -1167,6 +1232,7 @@ struct TensorTuning {
     int windows_per_cta = 0;    // HB_WINDOWS_PER_CTA = 8 | 16 | 32: force the recurrence tile
     bool chunkloop = true;      // HB_NO_CHUNKLOOP: per-chunk launches even when the whole chunk loop fits on the chip
     int heads_workers = 0;      // HB_HEADS_WORKERS: CTAs of the heads role in the chunk-loop kernel (even)
+    bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
     static TensorTuning from_env() {
         TensorTuning t;
         t.pdl = getenv("HB_NO_PDL") == nullptr;
@@ -1174,6 +1240,7 @@ struct TensorTuning {
         t.stack = getenv("HB_NO_STACK") == nullptr;
         t.live8 = getenv("HB_NO_LIVE8") == nullptr;
         t.chunkloop = getenv("HB_NO_CHUNKLOOP") == nullptr;
+        t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
             const int n = atoi(v);
             if (n == 8 || n == 16 || n == 32) t.windows_per_cta = n;
@@ -1189,8 +1256,9 @@ struct TensorEngine {
     int* proj_jobs = nullptr;                 // job table of the chunk-loop projection role (see ProjArgs::jobs)
     int* proj_job_offsets = nullptr;
     size_t proj_jobs_capacity = 0;
-    int jobs_w = -1, jobs_workers = -1; int64_t jobs_n_wg = -1;
-    std::vector<int> proj_jobs_host, proj_job_offsets_host;
+    int jobs_w = -1, jobs_workers = -1, jobs_pixels = -1; int64_t jobs_n_wg = -1;
+    int* proj_px_wgs = nullptr;               // [workers] window groups whose pixel jobs a worker owns
+    std::vector<int> proj_jobs_host, proj_job_offsets_host, proj_px_wgs_host;
     int tile_order_w = -1;
     int* tile_order16 = nullptr;              // column-tile order of the heads role (earliest complete first)
     std::vector<int> tile_order16_host;
@@ -1386,6 +1454,7 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     cudaFree(e->b_head);
     cudaFree(e->proj_jobs);
     cudaFree(e->proj_job_offsets);
+    cudaFree(e->proj_px_wgs);
     cudaFree(e->tile_order16);
     cudaFree(e->flags);
     if (e->side) cudaStreamDestroy(e->side);
@@ -1445,6 +1514,7 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_chunkloop_kernel<16, 16, 1>, loop16);
         set((const void*)tc_chunkloop_kernel<16, 16, 0>, loop16);
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->proj_job_offsets), 256 * sizeof(int));
+        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->proj_px_wgs), 256 * sizeof(int));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order16), 4096 * sizeof(int));
         e->flags_capacity = (size_t)1 << 16;
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->flags), e->flags_capacity * sizeof(unsigned long long));
@@ -1518,14 +1588,33 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const int proj_workers = std::max(1, e->sm_count / 6);
     const bool pdl = e->tune.pdl;
     const int pair_mode = e->tune.pair ? 1 : 0;               // 2-CTA clusters share activation tiles by multicast
+    const int n_chunks = T < W ? 0 : (T - W) / J + 1;
+    const int tiles8 = (W + 7) / 8, tiles16 = (W + 15) / 16;
+    // ---- how the batch is laid out on the chip ----
+    ChunkloopPlan plan{};
+    bool chunkloop = e->tune.chunkloop && n_chunks > 0 && B > 0 && tiles8 <= 4096 && plan_chunkloop(e->tune, B, e->sm_count, &plan);
+    // pixel jobs: the projection role also projects the image columns the next chunk's encoder adds
+    const int px_tiles = (enc_cols + 7) / 8, px_pre_tiles = std::min(px_tiles, tiles8);
+    bool pixels_in_loop = chunkloop && e->tune.pixel_jobs && n_chunks > 1 && e->enc.Kp <= 128 && px_tiles < 4096 && (J + 7) / 8 + 1 <= PX_R;
+    size_t n_groups = 0, flags_needed = 0;
+    if (chunkloop) {
+        n_groups = (size_t)plan.rec_ctas * (plan.tile / WG);       // window groups the recurrence CTAs cover (>= n_wg)
+        flags_needed = (size_t)4 * plan.rec_ctas + n_groups + n_groups * tiles8 * 2;
+        if (pixels_in_loop && flags_needed + n_groups * px_tiles * 2 > e->flags_capacity) pixels_in_loop = false;
+        if (pixels_in_loop) flags_needed += n_groups * px_tiles * 2;
+        chunkloop = flags_needed <= e->flags_capacity;
+        pixels_in_loop = pixels_in_loop && chunkloop;
+    }
     if (enc_cols > 0) {
-        // once per batch: pixels -> operand image, then the encoder projection of EVERY covered column
-        // (chunks overlap by W - J columns and gi of a column does not depend on the chunk)
+        // once per batch: pixels -> operand image, then the encoder projection of every covered column (chunks overlap
+        // by W - J columns and gi of a column does not depend on the chunk) -- or, with pixel jobs in the chunk loop, of
+        // the first chunk's columns only
         const int64_t chunks16 = n_wg * T * (e->enc.Kp / 8) * WG;
         const int blocks = (int)std::min<int64_t>((chunks16 + 255) / 256, (int64_t)e->sm_count * 16);
         pileup_to_operand_image_kernel<<<blocks, 256, 0, s>>>(images, B, T, F, e->enc.Kp, ws.ximg, n_wg);
-        const int tiles = (int)std::min<int64_t>(n_wg * ((enc_cols + 7) / 8), proj_workers);
+        const int tiles = (int)std::min<int64_t>(n_wg * (pixels_in_loop ? px_pre_tiles : px_tiles), proj_workers);
         ProjArgs pe{};
+        pe.col_tiles = pixels_in_loop ? px_pre_tiles : 0;
         pe.in_base = reinterpret_cast<const uint8_t*>(ws.ximg); pe.in_wg_stride = (int64_t)T * xblk; pe.in_dir_stride = 0; pe.in_part_stride = 0; pe.n_dirs = 1;
         pe.blk_bytes = xblk; pe.lbo = 128; pe.Kp = e->enc.Kp; pe.n_wg = n_wg; pe.W = enc_cols;
         pe.w_tmem = e->enc.wih_tmem; pe.scale_row = e->enc.scale_row; pe.bias_row = e->enc.bias_row; pe.gi = ws.gi_enc;
@@ -1544,8 +1633,6 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     pd.blk_bytes = YBLK; pd.n_dirs = 2; pd.lbo = 0; pd.Kp = e->dec.Kp; pd.n_wg = n_wg; pd.W = W;
     pd.w_tmem = e->dec.wih_tmem; pd.scale_row = e->dec.scale_row; pd.bias_row = e->dec.bias_row; pd.gi = ws.gi;
     pd.pair = pair_mode;
-    const int n_chunks = T < W ? 0 : (T - W) / J + 1;
-    const int tiles8 = (W + 7) / 8, tiles16 = (W + 15) / 16;
     auto layer_args = [&](const TensorLayer& L, const float* gi, int gi_cols, int gi_col0, int gi_col_step, uint8_t* y_even, uint8_t* y_odd) {
         RecLayer r{};
         r.gi = gi; r.gi_cols = gi_cols; r.gi_col0 = gi_col0; r.gi_col_step = gi_col_step;
@@ -1574,14 +1661,6 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         if (e->time_recurrence) cudaEventRecord(e->rec_events[slot].second, s);
     };
     // ---- chunk-loop kernel: every role of the whole chunk loop resident at once ----
-    ChunkloopPlan plan{};
-    bool chunkloop = e->tune.chunkloop && n_chunks > 0 && B > 0 && tiles8 <= 4096 && plan_chunkloop(e->tune, B, e->sm_count, &plan);
-    size_t n_groups = 0, flags_needed = 0;
-    if (chunkloop) {
-        n_groups = (size_t)plan.rec_ctas * (plan.tile / WG);       // window groups the recurrence CTAs cover (>= n_wg)
-        flags_needed = (size_t)4 * plan.rec_ctas + n_groups + n_groups * tiles8 * 2;
-        chunkloop = flags_needed <= e->flags_capacity;
-    }
     if (chunkloop) {
         if (e->tile_order_w != W) {
             // heads: a column tile is complete once the forward pass is past its last column and the reverse pass past its first
@@ -1594,7 +1673,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             cudaMemcpyAsync(e->tile_order16, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
             e->tile_order_w = W;
         }
-        if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg) {
+        if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg || e->jobs_pixels != (int)pixels_in_loop) {
             // projection job table: tile (group, tile) belongs to worker (group * tiles + tile) % workers; a worker takes
             // the halves of its tiles in the order the encoder makes them runnable (forward half of tile t after step
             // 8t+8, reverse half after step W-8t)
@@ -1608,7 +1687,19 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 }
             e->proj_jobs_host.clear();
             e->proj_job_offsets_host.assign(1, 0);
-            for (auto& v : per) {
+            e->proj_px_wgs_host.assign(plan.proj_workers, 0);
+            for (int wk = 0; wk < plan.proj_workers; ++wk) {
+                auto& v = per[wk];
+                if (pixels_in_loop) {
+                    // pixel entries first (they wait for nothing and fill the role's idle start of the encoder phase):
+                    // relative tile r of every window group the worker owns, tile-major so that a chunk that adds
+                    // fewer than PX_R tiles uses a prefix of them
+                    std::vector<int> mine;
+                    for (int64_t wg = wk; wg < n_wg; wg += plan.proj_workers) mine.push_back((int)wg);
+                    e->proj_px_wgs_host[wk] = (int)mine.size();
+                    for (int r = 0; r < PX_R; ++r)
+                        for (int wg : mine) e->proj_jobs_host.push_back(pack_proj_job(wg, r, 0) | (1 << 29));
+                }
                 std::stable_sort(v.begin(), v.end(), [](const Job& x, const Job& y) { return x.ready != y.ready ? x.ready < y.ready : x.id < y.id; });
                 for (const Job& jb : v) e->proj_jobs_host.push_back(jb.packed);
                 e->proj_job_offsets_host.push_back((int)e->proj_jobs_host.size());
@@ -1621,20 +1712,28 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             }
             cudaMemcpyAsync(e->proj_jobs, e->proj_jobs_host.data(), e->proj_jobs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
             cudaMemcpyAsync(e->proj_job_offsets, e->proj_job_offsets_host.data(), e->proj_job_offsets_host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
-            e->jobs_w = W; e->jobs_workers = plan.proj_workers; e->jobs_n_wg = n_wg;
+            cudaMemcpyAsync(e->proj_px_wgs, e->proj_px_wgs_host.data(), e->proj_px_wgs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+            e->jobs_w = W; e->jobs_workers = plan.proj_workers; e->jobs_n_wg = n_wg; e->jobs_pixels = (int)pixels_in_loop;
         }
         cudaMemsetAsync(e->flags, 0, flags_needed * sizeof(unsigned long long), s);
         unsigned long long* f = e->flags;
         unsigned long long* enc_prog = f;                 f += 2 * plan.rec_ctas;
         unsigned long long* dec_prog = f;                 f += 2 * plan.rec_ctas;
         unsigned long long* heads_done = f;               f += n_groups;               // one per window group
-        unsigned long long* tile_flags = f;                                            // [group][tile][dec direction]
+        unsigned long long* tile_flags = f;               f += n_groups * tiles8 * 2;  // [group][tile][dec direction]
+        unsigned long long* px_flags = f;                                              // [group][image column tile][enc direction]
         RecArgs ra{};
         ra.layer[0] = layer_args(e->enc, ws.gi_enc, enc_cols, 0, J, ws.yimg1, ws.yimg1);
         ra.layer[0].progress = enc_prog; ra.layer[0].consumed_flags = tile_flags;
         ra.layer[1] = layer_args(e->dec, ws.gi, W, 0, 0, ws.yimg2[0], ws.yimg2[1]);
         ra.layer[1].gi_b = ws.gi_b;
         ra.layer[1].progress = dec_prog; ra.layer[1].tile_flags = tile_flags;
+        ra.layer[1].flag_tiles = tiles8; ra.layer[1].flag_abs = 0; ra.layer[1].flag_skip_tiles = 0;
+        ra.layer[1].flag_need_base = 0; ra.layer[1].flag_need_per_chunk = 6;
+        if (pixels_in_loop) {
+            ra.layer[0].tile_flags = px_flags; ra.layer[0].flag_tiles = px_tiles; ra.layer[0].flag_abs = 1;
+            ra.layer[0].flag_skip_tiles = px_pre_tiles; ra.layer[0].flag_need_base = 3; ra.layer[0].flag_need_per_chunk = 0;
+        }
         ra.layer[1].heads_done = heads_done; ra.layer[1].heads_per_chunk = 4 * tiles16;
         ra.n_layers = 2; ra.n_chunks = n_chunks; ra.h_in = nullptr; ra.h_out = nullptr; ra.B = B; ra.W = W;
         ra.tiles_t = tiles8; ra.n_wg = (int)n_wg; ra.epoch = 0; ra.dbg = dbg_buf; ra.dbg_layer = dbg_enc ? 0 : 1;
@@ -1643,6 +1742,12 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         pp.pair = 0;          // every CTA of the role picks its own job order (see the loader): no shared tiles
         pp.dbg = dbg_buf;
         pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets; pp.gi_b = ws.gi_b;
+        if (pixels_in_loop) {
+            pp.px.ximg = reinterpret_cast<const uint8_t*>(ws.ximg); pp.px.wg_stride = (int64_t)T * xblk; pp.px.blk_bytes = xblk; pp.px.Kp = e->enc.Kp;
+            pp.px.w_tmem = e->enc.wih_tmem; pp.px.scale_row = e->enc.scale_row; pp.px.bias_row = e->enc.bias_row;
+            pp.px.gi = ws.gi_enc; pp.px.cols = enc_cols; pp.px.tiles = px_tiles; pp.px.col_step = J;
+            pp.px.flags = px_flags; pp.px.wgs_of_worker = e->proj_px_wgs;
+        }
         HeadsArgs hp = heads_base;
         hp.yimg = ws.yimg2[0]; hp.yimg_odd = ws.yimg2[1]; hp.col0 = 0; hp.n_chunks = n_chunks;
         hp.progress = dec_prog; hp.rec_n = plan.tile; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
