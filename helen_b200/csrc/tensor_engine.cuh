@@ -1066,15 +1066,22 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
     const uint32_t tmem = *tmem_slot;
     const int tiles_t = (W + 15) >> 4;
     int chunk; int64_t wg; int t0;
+    // HB_DEBUG_TIMELINE: worker 0 adds up the cycles each role spends at its wait points (slots 7300 + 8 role + k)
+    const bool acct = a.dbg != nullptr && worker == 0 && lane == 0;
+    long long t_wait[4] = {0, 0, 0, 0};
+    const long long t_role0 = acct ? clock64() : 0;
+#define HB_TIMED(k, stmt) do { const long long t_ = acct ? clock64() : 0; stmt; if (acct) t_wait[k] += clock64() - t_; } while (0)
+#define HB_ROLE_REPORT(role) do { if (acct) { for (int k_ = 0; k_ < 4; ++k_) a.dbg[7300 + 8 * (role) + k_] = t_wait[k_]; \
+                                              a.dbg[7300 + 8 * (role) + 4] = clock64() - t_role0; } } while (0)
 
     if (warp == 5) {
         for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
-            if (it > 0) tc::mbar_wait(a_empty, (uint32_t)((it - 1) & 1));
+            if (it > 0) HB_TIMED(0, tc::mbar_wait(a_empty, (uint32_t)((it - 1) & 1)));
             const int valid = min(16, W - t0);
             if (a.progress != nullptr) {                     // both decoder directions must have stored these columns
                 if (lane < 2)
-                    tc::spin_until_ge(a.progress + ((wg * WG) / a.rec_n) * 2 + lane,
-                                      (unsigned long long)chunk * W + (unsigned long long)(lane == 0 ? t0 + valid : W - t0));
+                    HB_TIMED(1, tc::spin_until_ge(a.progress + ((wg * WG) / a.rec_n) * 2 + lane,
+                                                  (unsigned long long)chunk * W + (unsigned long long)(lane == 0 ? t0 + valid : W - t0)));
 
                 __syncwarp();
             }
@@ -1088,11 +1095,12 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                     tc::bulk_g2s(a_img + part * PART_BYTES + d * SLICE_BYTES + q4 * 4 * YBLK, img + yimg_block(wg, d, part, t0 + 4 * q4, W), (uint32_t)(cols * YBLK), a_full);
             }
         }
+        HB_ROLE_REPORT(0);
     } else if (warp == 4) {
         const uint32_t idesc = tc::idesc_f16_f32(128, NCLS);
         for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
-            tc::mbar_wait(a_full, (uint32_t)(it & 1));
-            if (it > 0) tc::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1));
+            HB_TIMED(0, tc::mbar_wait(a_full, (uint32_t)(it & 1)));
+            if (it > 0) HB_TIMED(1, tc::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1)));
             tc::tc_fence_after();
             if (tc::elect_one()) {
                 const uint64_t a_hi = tc::smem_desc_sw128(tc::smem_u32(a_img), YBLK), a_lo = tc::smem_desc_sw128(tc::smem_u32(a_img + PART_BYTES), YBLK);
@@ -1111,6 +1119,7 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             }
             __syncwarp();
         }
+        HB_ROLE_REPORT(1);
     } else {
         float bias[NCLS];
 #pragma unroll
@@ -1120,7 +1129,7 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             const int t = t0 + (row >> 3);
             const int64_t b = wg * WG + (row & 7);
             const int col = a.col0 + chunk * a.col_step + t;
-            tc::mbar_wait(acc_full, (uint32_t)(it & 1));
+            HB_TIMED(0, tc::mbar_wait(acc_full, (uint32_t)(it & 1)));
             tc::tc_fence_after();
             float v[NCLS];
             tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
@@ -1128,6 +1137,7 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty);
+            const long long t_math = acct ? clock64() : 0;
             if (t < W && b < B) {
                 float mb = -INFINITY, mr = -INFINITY;
 #pragma unroll
@@ -1153,14 +1163,18 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
 #pragma unroll
                 for (int c = 0; c < NRLE; ++c) pr[c] = old[NBASE + c] + v[NBASE + c] / sr;
             }
+            if (acct) t_wait[2] += clock64() - t_math;
             if (a.heads_done != nullptr) {
-                __threadfence();
+                HB_TIMED(1, __threadfence());
                 __syncwarp();
                 if (lane == 0) tc::red_release_gpu_add(a.heads_done + wg, 1ull);
             }
             if (a.dbg != nullptr && worker == 0 && tid == 0) a.dbg[7100 + chunk] = (long long)globaltimer_ns();
         }
+        if (warp == 0) HB_ROLE_REPORT(2);
     }
+#undef HB_TIMED
+#undef HB_ROLE_REPORT
     tc::tc_fence_before();
     tc::named_barrier_sync(2, HEADS_THREADS);
     if (warp == 4) tc::tmem_dealloc(tmem, 32);
@@ -1852,6 +1866,17 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                         const long long* w = &hbuf[7200 + 8 * r];
                         fprintf(stderr, "    %s total %lld:", role[r], w[4]);
                         for (int k = 0; k < 4; ++k) fprintf(stderr, "  %s %lld", what[r][k], w[k]);
+                        fprintf(stderr, "\n");
+                    }
+                }
+                {
+                    const char* role[3] = {"loader  ", "MMA     ", "epilogue"};
+                    const char* what[3][3] = {{"a_empty", "progress", "-"}, {"a_full", "acc_empty", "-"}, {"acc_full", "fence", "softmax + P update"}};
+                    fprintf(stderr, "  heads worker 0, cycles over the whole launch:\n");
+                    for (int r = 0; r < 3; ++r) {
+                        const long long* w = &hbuf[7300 + 8 * r];
+                        fprintf(stderr, "    %s total %lld:", role[r], w[4]);
+                        for (int k = 0; k < 3; ++k) fprintf(stderr, "  %s %lld", what[r][k], w[k]);
                         fprintf(stderr, "\n");
                     }
                 }
