@@ -39,12 +39,32 @@ def predict(test_file, output_filename, model_path, batch_size, num_workers, ran
         sys.stderr.write(TextColor.PURPLE + 'Loading data\n' + TextColor.END)
 
     test_data = SequenceDataset(image_directory=None, file_list=test_file)
-    test_loader = DataLoader(test_data, batch_size=batch_size, shuffle=False, num_workers=num_workers)
+    # pinned batches: the host->device copy is then a plain DMA (no staging memcpy) and can run asynchronously
+    test_loader = DataLoader(test_data, batch_size=batch_size, shuffle=False, num_workers=num_workers, pin_memory=True)
     total_batches = len(test_loader)
     windows_done, t_begin = 0, time.time()
+    device = torch.device("cuda", device_id)
+
+    def write_out(item):
+        # predict_gpu.py:176-179: one record per image; runs while the GPU works on the next batch
+        meta, base_dev, rle_dev, done = item
+        done.synchronize()
+        base_labels, rle_labels = base_dev.cpu().numpy(), rle_dev.cpu().numpy()
+        contig, contig_start, contig_end, chunk_id, position, filename = meta
+        for i in range(base_labels.shape[0]):
+            prediction_data_file.write_prediction(contig[i], contig_start[i], contig_end[i], chunk_id[i],
+                                                  position[i], base_labels[i], rle_labels[i], filename[i])
+
+    in_flight = None
     for batch_iterator, (contig, contig_start, contig_end, chunk_id, images, position, filename) in enumerate(test_loader, 1):
         start_time = time.time()
-        base_labels, rle_labels = predictor.predict_host(images.numpy())
+        # the whole loop body of the reference (predict_gpu.py:97-159) is this one asynchronous call
+        base_dev, rle_dev = predictor.predict(images.to(device, non_blocking=True))
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(device))
+        if in_flight is not None:
+            write_out(in_flight)
+        in_flight = ((contig, contig_start, contig_end, chunk_id, position, filename), base_dev, rle_dev, done)
         windows_done += images.size(0)
         if rank == 0:
             eta = (time.time() - start_time) * (total_batches - batch_iterator)
@@ -52,9 +72,8 @@ def predict(test_file, output_filename, model_path, batch_size, num_workers, ran
             sys.stderr.write(TextColor.GREEN + "INFO: BATCHES DONE: " + str(batch_iterator) + "/" + str(total_batches)
                              + ". ESTIMATED TIME LEFT: " + stamp + " ("
                              + str(int(windows_done / max(time.time() - t_begin, 1e-9))) + " WINDOWS/S)\n" + TextColor.END)
-        for i in range(images.size(0)):
-            prediction_data_file.write_prediction(contig[i], contig_start[i], contig_end[i], chunk_id[i],
-                                                  position[i], base_labels[i], rle_labels[i], filename[i])
+    if in_flight is not None:
+        write_out(in_flight)
     prediction_data_file.close()
     predictor.close()
 
