@@ -992,6 +992,256 @@ tc_recurrence_kernel(const RecArgs ra)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Recurrence for large batches: TWO window tiles per CTA that share W_hh in TMEM and take turns on the tensor pipe
+// (throughput mode; one layer, one chunk per launch).  With one tile per CTA the tensor pipe idles during the gate
+// math of a step (~45 % of it) and a second CTA cannot share the SM because each needs 384 of the 512 TMEM columns
+// for W_hh.  Here tile A's MMAs of step s+1 are issued while tile B's gate warps still work on step s: the pipe stays
+// busy and a step pair costs its 2 x 48 (stacked, 8-window tiles) or 2 x 72 (3-term, 16-window tiles) MMAs.
+// Warps 0-7: gate warps of tile 0, 8-15: of tile 1 (warp w of a tile: TMEM lane quarter w % 4, window half w / 4),
+// 16: MMA issuer, 17: gi' loader, 18: y store.  NLIVE windows per tile; MODE 1 = stacked [h_hi | h_lo] (NLIVE = 8),
+// MODE 0 = 3-term (NLIVE = 16).
+// ---------------------------------------------------------------------------------------------
+template <int NLIVE> constexpr size_t recurrence2_smem() { return (size_t)2 * (2 * 2 * 2 * YBLK + 3 * NLIVE * GI_ROW_BYTES) + 512 + 1024; }
+
+template <int NLIVE, int MODE>
+__global__ void __launch_bounds__(REC_TC_THREADS, 1)
+tc_recurrence2_kernel(const RecArgs ra)
+{
+    static_assert((NLIVE == 8 && MODE == 1) || (NLIVE == 16 && MODE == 0), "8-window stacked tiles or 16-window 3-term tiles");
+    constexpr bool STACK = MODE == 1;
+    constexpr int NACC = 16;                                 // N of every MMA == accumulator columns per (tile, gate block)
+    constexpr int GW = REC_GATE_WARPS / 2;                   // gate warps per tile
+    constexpr int NW = NLIVE / 2;                            // windows per gate thread
+    constexpr int NG = NLIVE / WG;                           // window groups per tile
+    constexpr uint32_t HB_BYTES = 2 * YBLK;                  // one h operand image (hi or lo): two 8-row groups
+    constexpr int NBUF = 2, ST = 3;
+    constexpr uint32_t GI_STAGE_BYTES = NLIVE * GI_ROW_BYTES;
+    constexpr uint32_t TILE_BYTES = 2 * NBUF * HB_BYTES + ST * GI_STAGE_BYTES;
+    constexpr int NBAR = 3 + 1 + NBUF + NBUF + ST + ST;      // barriers per tile
+    extern __shared__ __align__(1024) uint8_t smem_rec2[];
+    uint8_t* smem = tc::align_smem_1024(smem_rec2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TILE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NBAR);
+    auto h_img_of = [&](int tile) { return smem + tile * TILE_BYTES; };
+    auto gi_of = [&](int tile) { return smem + tile * TILE_BYTES + 2 * NBUF * HB_BYTES; };
+    auto acc_ready = [&](int tile) { return bars + tile * NBAR; };              // [3]
+    auto h_ready = [&](int tile) { return bars + tile * NBAR + 3; };
+    auto h_free = [&](int tile) { return bars + tile * NBAR + 4; };             // [NBUF]
+    auto y_ready = [&](int tile) { return bars + tile * NBAR + 4 + NBUF; };     // [NBUF]
+    auto gi_full = [&](int tile) { return bars + tile * NBAR + 4 + 2 * NBUF; }; // [ST]
+    auto gi_empty = [&](int tile) { return bars + tile * NBAR + 4 + 2 * NBUF + ST; };
+
+    const RecLayer& L = ra.layer[0];
+    const int64_t B = ra.B;
+    const int W = ra.W;
+    const int cta_x = (int)blockIdx.x, dir = (int)blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t b0 = (int64_t)cta_x * 2 * NLIVE;           // tile t covers windows [b0 + t NLIVE, b0 + (t + 1) NLIVE)
+    const int t_first = dir ? W - 1 : 0, dt = dir ? -1 : 1;
+
+    tc::pdl_launch_dependents();
+    if (tid == 0) {
+        for (int tile = 0; tile < 2; ++tile) {
+            for (int i = 0; i < 3; ++i) tc::mbar_init(acc_ready(tile) + i, 1);
+            tc::mbar_init(h_ready(tile), GW);
+            for (int i = 0; i < NBUF; ++i) { tc::mbar_init(h_free(tile) + i, 1); tc::mbar_init(y_ready(tile) + i, GW); }
+            for (int i = 0; i < ST; ++i) { tc::mbar_init(gi_full(tile) + i, 1); tc::mbar_init(gi_empty(tile) + i, GW); }
+        }
+        tc::mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == REC_GATE_WARPS) tc::tmem_alloc(tmem_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == REC_GATE_WARPS + 1) {
+        // ===================== gi' loader: both tiles, ST steps ahead =====================
+        tc::pdl_grid_dependency_wait();
+        bool synced = false;
+        const int tile_l = lane >> 3, g_l = lane & 7;       // lanes [8 tile, 8 tile + NG) fetch the groups of a tile
+        const float* src0 = L.gi + gi_block(b0 / WG + min(tile_l, 1) * NG + min(g_l, NG - 1), L.gi_cols, L.gi_col0, dir * 3);
+        for (int s = 0, t = t_first; s < W; ++s, t += dt) {
+            const int stage = s % ST;
+            if (s == ST) { __syncthreads(); synced = true; }
+            for (int tile = 0; tile < 2; ++tile) {
+                if (s >= ST) tc::mbar_wait(gi_empty(tile) + stage, (uint32_t)((s / ST - 1) & 1));
+                if (lane == 0) tc::mbar_arrive_expect_tx(gi_full(tile) + stage, NG * GI_GRP_BYTES);
+            }
+            __syncwarp();
+            if (tile_l < 2 && g_l < NG)
+                tc::bulk_g2s(gi_of(tile_l) + stage * GI_STAGE_BYTES + g_l * GI_GRP_BYTES, src0 + (int64_t)t * (6 * GI_BLK_FLOATS), GI_GRP_BYTES, gi_full(tile_l) + stage);
+        }
+        if (!synced) __syncthreads();
+    } else if (warp == REC_GATE_WARPS + 2) {
+        // ===================== y store =====================
+        tc::pdl_grid_dependency_wait();
+        __syncthreads();
+        uint8_t* yimg = L.yimg[0];
+        for (int s = 0, t = t_first; s < W; ++s, t += dt) {
+            const int buf = (s + 1) % NBUF;
+            for (int tile = 0; tile < 2; ++tile) {
+                tc::mbar_wait(y_ready(tile) + buf, (uint32_t)((s / NBUF) & 1));
+                if (lane < 2 * NG) {
+                    const int g = lane >> 1, part = lane & 1;
+                    tc::bulk_s2g(yimg + yimg_block(b0 / WG + tile * NG + g, dir, part, t, W), h_img_of(tile) + (buf * 2 + part) * HB_BYTES + g * YBLK, YBLK);
+                    tc::bulk_commit();
+                    tc::bulk_wait_read0();
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(h_free(tile) + buf);
+            }
+        }
+        if (lane < 2 * NG) tc::bulk_wait0();
+    } else if (warp == REC_GATE_WARPS) {
+        // ===================== MMA issuer: tile 0, tile 1, tile 0, ... =====================
+        __syncthreads();                                     // weights in TMEM, h_0 of both tiles in smem
+        tc::tc_fence_after();
+        const uint32_t idesc = tc::idesc_f16_f32(128, NACC);
+        for (int s = 0; s < W; ++s) {
+            for (int tile = 0; tile < 2; ++tile) {
+                if (s > 0) {
+                    tc::mbar_wait(h_ready(tile), (uint32_t)((s - 1) & 1));
+                    tc::tc_fence_after();
+                }
+                const uint64_t base = tc::smem_desc_sw128(tc::smem_u32(h_img_of(tile)), (STACK && NLIVE == 8) ? HB_BYTES : YBLK);
+                const uint64_t hhi_desc = base + (uint64_t)(((s % NBUF) * 2 + 0) * HB_BYTES / 16);
+                const uint64_t hlo_desc = base + (uint64_t)(((s % NBUF) * 2 + 1) * HB_BYTES / 16);
+                const uint32_t acc0 = tmem + tile * 3 * NACC;
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int gb = 0; gb < 3; ++gb) {
+                        if constexpr (STACK) {
+#pragma unroll
+                            for (int term = 0; term < 2; ++term)
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks)
+                                    tc::mma_f16_ts(acc0 + gb * NACC, tmem + REC_W_COL0 + (term * 3 + gb) * 64 + ks * 8, hhi_desc + tc::sw128_kstep(ks), idesc, (term | ks) != 0);
+                        } else {
+#pragma unroll
+                            for (int term = 0; term < 3; ++term) {   // (W_hi,h_hi) (W_lo,h_hi) (W_hi,h_lo)
+                                const uint64_t bd = term == 2 ? hlo_desc : hhi_desc;
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks)
+                                    tc::mma_f16_ts(acc0 + gb * NACC, tmem + REC_W_COL0 + ((term == 1 ? 3 : 0) + gb) * 64 + ks * 8, bd + tc::sw128_kstep(ks), idesc, (term | ks) != 0);
+                            }
+                        }
+                        tc::mma_commit(acc_ready(tile) + gb);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== gate warps =====================
+        const int tile = warp / GW, wi = warp % GW;
+        const int q = wi & 3, j = q * 32 + lane, win0 = (wi >> 2) * NW;
+        {   // W_hh -> TMEM, split over all 16 gate warps as in recurrence_role
+            const int wq = warp & 3, wj = wq * 32 + lane, term = (warp >> 2) & 1, half = warp >> 3;
+            auto fetch = [&](int gb, uint32_t* r) {
+                const uint4* p = reinterpret_cast<const uint4*>(L.whh_tmem + whh_word_index(dir, term, gb, wj, half * 32));
+#pragma unroll
+                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+            };
+            auto store = [&](int gb, const uint32_t* r) {
+                const uint32_t dst = tmem + ((uint32_t)(wq * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
+                tc::tmem_st16(dst, r);
+                tc::tmem_st16(dst + 16, r + 16);
+            };
+            uint32_t ra0[32], ra1[32];
+            fetch(0, ra0); fetch(1, ra1); store(0, ra0); fetch(2, ra0); store(1, ra1); store(2, ra0);
+            tc::tmem_st_wait();
+        }
+        uint8_t* h_img = h_img_of(tile);
+        const uint8_t* gi_s = gi_of(tile);
+        const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
+        const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
+        const int64_t bt = b0 + tile * NLIVE + win0;          // first window of this thread
+        float h_own[NW];
+        uint32_t h_off[NW];
+        tc::pdl_grid_dependency_wait();
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            h_own[i] = (ra.h_in != nullptr && bt + i < B) ? __ldcg(ra.h_in + ((bt + i) * 2 + dir) * H + j) * ACT_SCALE : 0.f;
+            h_off[i] = (uint32_t)((win0 + i) / WG) * YBLK + tc::sw128_offset((win0 + i) % WG, j);
+            __half hi, lo;
+            tc::split_f16(h_own[i], hi, lo);
+            *reinterpret_cast<__half*>(h_img + h_off[i]) = hi;
+            *reinterpret_cast<__half*>(h_img + HB_BYTES + h_off[i]) = lo;
+        }
+        tc::fence_proxy_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * 3 * NACC + win0);
+        auto load_acc = [](uint32_t addr, float* a) {
+            tc::tmem_ld_n<NW>(addr, a);
+            if constexpr (STACK) {
+                float a_lo[NW];
+                tc::tmem_ld_n<NW>(addr + NLIVE, a_lo);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < NW; ++i) a[i] += a_lo[i];
+            } else {
+                tc::tmem_ld_wait();
+            }
+        };
+        for (int s = 0; s < W; ++s) {
+            const int stage = s % ST;
+            const uint32_t par = (uint32_t)(s & 1);
+            const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + (win0 / WG) * (3 * GI_BLK_FLOATS) + (win0 % WG) * H + j;
+            float r[NW], z[NW], a[NW];
+            tc::mbar_wait(gi_full(tile) + stage, (uint32_t)((s / ST) & 1));
+            tc::mbar_wait(acc_ready(tile) + 0, par);
+            tc::tc_fence_after();
+            load_acc(taddr, a);
+#pragma unroll
+            for (int i = 0; i < NW; ++i) r[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_r, gs[i * H])));
+            tc::mbar_wait(acc_ready(tile) + 1, par);
+            tc::tc_fence_after();
+            load_acc(taddr + NACC, a);
+#pragma unroll
+            for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, gs[GI_BLK_FLOATS + i * H])));
+            float gin[NW];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) gin[i] = gs[2 * GI_BLK_FLOATS + i * H];
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(gi_empty(tile) + stage);
+            uint8_t* h_hi = h_img + (((s + 1) % NBUF) * 2) * HB_BYTES;
+            uint8_t* h_lo = h_hi + HB_BYTES;
+            if (s >= NBUF) tc::mbar_wait(h_free(tile) + ((s + 1) % NBUF), (uint32_t)(((s - NBUF) / NBUF) & 1));
+            tc::mbar_wait(acc_ready(tile) + 2, par);
+            tc::tc_fence_after();
+            load_acc(taddr + 2 * NACC, a);
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const float e = tc::ex2_approx(fmaf(r[i], fmaf(a[i], inv_n, bhn), gin[i]));
+                const float n = fmaf(2.0f * ACT_SCALE, tc::rcp_approx(1.0f + e), -ACT_SCALE);
+                const float hn = fmaf(z[i], h_own[i] - n, n);
+                h_own[i] = hn;
+                __half hi, lo;
+                tc::split_f16(hn, hi, lo);
+                *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
+                *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
+            }
+            tc::fence_proxy_async_smem();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(h_ready(tile)); tc::mbar_arrive(y_ready(tile) + ((s + 1) % NBUF)); }
+        }
+        if (ra.h_out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i)
+                if (bt + i < B) ra.h_out[((bt + i) * 2 + dir) * H + j] = h_own[i] * ACT_SCALE_INV;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Heads + softmax + accumulate (predict_gpu.py:137-149) on tensor cores.
 // Roles are swapped here: A = activations (M = 128 positions = 8 windows x 16 columns, straight
 // from yimg), B = the 16 head rows (5 base + 11 rle), so every thread ends up with all 16 logits
@@ -1247,6 +1497,7 @@ struct TensorTuning {
     bool chunkloop = true;      // HB_NO_CHUNKLOOP: per-chunk launches even when the whole chunk loop fits on the chip
     int heads_workers = 0;      // HB_HEADS_WORKERS: CTAs of the heads role in the chunk-loop kernel (even)
     bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
+    bool pingpong = true;       // HB_NO_PINGPONG: one window tile per recurrence CTA in the per-chunk kernels of large batches
     static TensorTuning from_env() {
         TensorTuning t;
         t.pdl = getenv("HB_NO_PDL") == nullptr;
@@ -1255,6 +1506,7 @@ struct TensorTuning {
         t.live8 = getenv("HB_NO_LIVE8") == nullptr;
         t.chunkloop = getenv("HB_NO_CHUNKLOOP") == nullptr;
         t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
+        t.pingpong = getenv("HB_NO_PINGPONG") == nullptr;
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
             const int n = atoi(v);
             if (n == 8 || n == 16 || n == 32) t.windows_per_cta = n;
@@ -1520,6 +1772,8 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_recurrence_kernel<16, 8, 1>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<16, 16, 1>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<32, 32, 0>, detail::recurrence_smem<32>());
+        set((const void*)tc_recurrence2_kernel<8, 1>, recurrence2_smem<8>());
+        set((const void*)tc_recurrence2_kernel<16, 0>, recurrence2_smem<16>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
         const size_t loop8 = std::max({detail::recurrence_smem_gi2<8>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
         const size_t loop16 = std::max({detail::recurrence_smem_gi2<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
@@ -1800,7 +2054,11 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         const size_t slot = dominant_begin();
         if (e->time_recurrence) use_pdl = false;
         const bool stack = e->tune.stack;
-        if (nrec == 8)
+        if (e->tune.pingpong && nrec == 16 && stack)          // two 8-window stacked tiles per CTA
+            detail::launch(tc_recurrence2_kernel<8, 1>, grid_rec, dim3(REC_TC_THREADS), recurrence2_smem<8>(), s, use_pdl, ra);
+        else if (e->tune.pingpong && nrec == 32)              // two 16-window 3-term tiles per CTA
+            detail::launch(tc_recurrence2_kernel<16, 0>, grid_rec, dim3(REC_TC_THREADS), recurrence2_smem<16>(), s, use_pdl, ra);
+        else if (nrec == 8)
             detail::launch(stack ? tc_recurrence_kernel<16, 8, 1> : tc_recurrence_kernel<16, 8, 0>, grid_rec, dim3(REC_TC_THREADS),
                            detail::recurrence_smem<16>(), s, use_pdl, ra);
         else if (nrec == 16)

@@ -166,6 +166,12 @@ def test_full_size_batch_properties():
         perm = torch.randperm(256, generator=gen)
         pb2, pr2 = pred.predict(dev[perm.cuda()].contiguous())
         assert torch.equal(pb2, base[perm.cuda()]) and torch.equal(pr2, rle[perm.cuda()])
+        # (d) run-to-run: the roles of the chunk-loop kernel hand work over through counters in global memory and pick
+        # their job order at run time; results must not depend on that timing
+        for _ in range(12):
+            b_again, r_again, pb_again, pr_again = pred.predict(dev, return_probs=True)
+            assert torch.equal(b_again, base) and torch.equal(r_again, rle)
+            assert torch.equal(pb_again, pb) and torch.equal(pr_again, pr)
         sample = [0, 100, 255]
         ref = predict_windows(OracleWeights.from_state_dict(sd), images[sample].numpy())
         got = (base[sample], rle[sample], pb[sample], pr[sample])

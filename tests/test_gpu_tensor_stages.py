@@ -39,6 +39,8 @@ VARIANTS = {
     "per_chunk_tile8_3term": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "8", "HB_NO_STACK": "1"},
     "per_chunk_tile16": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "16"},
     "per_chunk_tile32": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "32"},
+    "per_chunk_tile16_single_tile": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "16", "HB_NO_PINGPONG": "1"},
+    "per_chunk_tile32_single_tile": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "32", "HB_NO_PINGPONG": "1"},
     "chunkloop_no_pair": {"HB_NO_PAIR": "1"},
     "chunkloop_no_pixel_jobs": {"HB_NO_PIXEL_JOBS": "1"},
     "chunkloop_tile16_pixel_jobs": {"HB_WINDOWS_PER_CTA": "16"},
@@ -51,7 +53,7 @@ def test_kernel_variants_match_fp32_engine(variant, monkeypatch):
     """Every recurrence tile / launch-structure variant of the tensor engine (the switches are read from the
     environment when the handle is created) against the fp32 engine, same tolerance as above."""
     from helen_b200.predictor import WindowPredictor
-    for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8", "HB_NO_PIXEL_JOBS"):
+    for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8", "HB_NO_PIXEL_JOBS", "HB_NO_PINGPONG"):
         monkeypatch.delenv(k, raising=False)
     batch, seq, features = 45, 250, 10
     sd = random_state_dict(features, seed=5)
