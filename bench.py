@@ -114,6 +114,25 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def random_parameters(features, seed):
+    """Random-init TransducerGRU parameters (uniform +-1/sqrt(H), torch's GRU / Linear default range) under the reference's
+    state_dict keys.  Own generator: the native arm imports nothing from oracle/."""
+    import torch
+    from collections import OrderedDict
+    gen = torch.Generator().manual_seed(seed)
+    bound = 1.0 / (HIDDEN ** 0.5)
+    shapes = OrderedDict()
+    for layer, k in (("gru_encoder", features), ("gru_decoder", 2 * HIDDEN)):
+        for rev in ("", "_reverse"):
+            shapes[f"{layer}.weight_ih_l0{rev}"] = (3 * HIDDEN, k)
+            shapes[f"{layer}.weight_hh_l0{rev}"] = (3 * HIDDEN, HIDDEN)
+            shapes[f"{layer}.bias_ih_l0{rev}"] = (3 * HIDDEN,)
+            shapes[f"{layer}.bias_hh_l0{rev}"] = (3 * HIDDEN,)
+    shapes["dense1_base.weight"], shapes["dense1_base.bias"] = (5, 2 * HIDDEN), (5,)
+    shapes["dense2_rle.weight"], shapes["dense2_rle.bias"] = (11, 2 * HIDDEN), (11,)
+    return OrderedDict((k, (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * bound) for k, shape in shapes.items())
+
+
 def synthetic_images(batch, features, seed, seq=T_COLUMNS):
     import torch
     gen = torch.Generator().manual_seed(seed)
@@ -124,10 +143,10 @@ def cpu_port_windows_per_s(features, sample_windows, min_seconds, threads, seq=T
     """Times the oracle's torch-CPU port of the reference predict loop (the only place bench.py
     executes oracle/ code)."""
     import torch
-    from oracle import TransducerPort, predict_port, random_state_dict
+    from oracle import TransducerPort, predict_port
     torch.set_num_threads(threads)
     model = TransducerPort(features).eval()
-    model.load_state_dict(random_state_dict(features, seed=0))
+    model.load_state_dict(random_parameters(features, seed=0))
     images = synthetic_images(sample_windows, features, seed=1, seq=seq)
     predict_port(model, images[: max(1, sample_windows // 4)])          # warm-up
     done, t0 = 0, time.perf_counter()
@@ -147,9 +166,9 @@ def run_reference(args, rank, world):
     import torch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    from oracle import TransducerPort, predict_port, random_state_dict
+    from oracle import TransducerPort, predict_port
     model = TransducerPort(args.features).eval()
-    model.load_state_dict(random_state_dict(args.features, seed=0))
+    model.load_state_dict(random_parameters(args.features, seed=0))
     sample = args.reference_sample
     images = synthetic_images(sample, args.features, seed=1)
     for _ in range(args.warmup):
@@ -190,7 +209,6 @@ def run_native(args, rank, world, local_rank):
     import torch.distributed as dist
     from helen_b200 import build as hb_build
     from helen_b200.predictor import WindowPredictor
-    from oracle import random_state_dict   # parameter generator only (shared with the CPU arm)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
@@ -215,7 +233,7 @@ def run_native(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    pred = WindowPredictor(random_state_dict(args.features, seed=0), device=local_rank, engine=args.engine)
+    pred = WindowPredictor(random_parameters(args.features, seed=0), device=local_rank, engine=args.engine)
     engine = pred.engine
     host_images = synthetic_images(args.batch, args.features, seed=1000 + rank).pin_memory()   # e2e inputs start in pinned host memory
     images = host_images.to(dev)
@@ -360,12 +378,11 @@ def run_train(args):
     from helen_b200 import build as hb_build
     from helen_b200.models.TransducerModel import TransducerGRU
     from helen_b200.models.train_step import ChunkTrainer
-    from oracle import TransducerPort, random_state_dict
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --train: no CUDA device; there is no CPU fallback")
     hb_build.build()
     batch, features = args.train_batch, args.features
-    sd = random_state_dict(features, seed=0)
+    sd = random_parameters(features, seed=0)
     model = TransducerGRU(1, features, 1, HIDDEN, 5, 11)
     model.load_state_dict(sd)
     model = model.cuda()
@@ -389,7 +406,8 @@ def run_train(args):
     flop = 3 * 2 * fwd_mac * batch                               # backward ~ 2x forward
     props = torch.cuda.get_device_properties(0)
     fp32_peak = props.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
-    # CPU arm: the oracle port's autograd with the reference's criteria, bounded sample
+    # CPU arm (cpu_baseline leg: the one place this mode executes oracle/): the port's autograd with the reference's criteria
+    from oracle import TransducerPort
     from helen_b200.options import TrainOptions
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
