@@ -1814,29 +1814,29 @@ inline int pick_windows_per_cta(const TensorTuning& tune, int64_t B, int sm_coun
     return 2 * B <= (int64_t)16 * sm_count ? 16 : 32;
 }
 
-// Role split of the chunk-loop kernel: recurrence CTAs for the smallest tile that leaves room for a useful number of
-// projection workers (6 CTAs each) and heads workers.  Returns false when the batch does not fit on the chip at once.
+// Role split of the chunk-loop kernel: recurrence CTAs for 8-window tiles, the rest shared between projection workers
+// (6 CTAs each) and heads workers.  Returns false when the batch is too large for it: the projection role has to keep
+// pace with the encoder, and measured against the per-chunk launches the kernel only wins while at least 10 projection
+// workers fit (B <= ~320; at B=384 it ran at 64 k windows/s against 90 k, and one 16-window tile per CTA never won:
+// 86 k against 90 k at B=384, 97 k against 107 k at B=512).  HB_WINDOWS_PER_CTA forces a tile (tests).
 struct ChunkloopPlan { int tile, rec_ctas, proj_workers, heads_workers; };
 inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, ChunkloopPlan* plan) {
-    const int sms = sm_count / 2 * 2;                          // clusters of 2
-    for (int tile : {8, 16}) {                                 // (32 live windows leave no room for two gi' rows per window)
-        if (tune.windows_per_cta && tile != tune.windows_per_cta) continue;
-        if (tile == 8 && !tune.live8 && !tune.windows_per_cta) continue;
-        const int64_t rec = (B + tile - 1) / tile;
-        if (2 * rec > sms) continue;
-        const int left = sms - (int)(2 * rec);
-        // heads: one CTA in seven of what the recurrence leaves (a heads tile is latency-bound, ~4 us), at least 2;
-        // projection: at least 6 workers (36 CTAs)
-        int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 14) * 2);
-        int proj = (left - heads) / 6;
-        if (proj < 6) continue;
-        heads = left - 6 * proj;                               // whatever the 6-CTA granularity leaves goes to the heads
-        heads = heads / 2 * 2;
-        if (heads < 2) { --proj; heads += 6; }
-        plan->tile = tile; plan->rec_ctas = (int)rec; plan->proj_workers = proj; plan->heads_workers = heads;
-        return true;
-    }
-    return false;
+    const int sms = sm_count / 2 * 2;
+    const int tile = tune.windows_per_cta ? tune.windows_per_cta : 8;
+    if (tile != 8 && tile != 16) return false;                 // (32 live windows leave no room for two gi' rows per window)
+    if (tile == 8 && !tune.live8 && !tune.windows_per_cta) return false;
+    const int64_t rec = (B + tile - 1) / tile;
+    if (2 * rec > sms) return false;
+    const int left = sms - (int)(2 * rec);
+    // heads: one CTA in seven of what the recurrence leaves (a heads tile is latency-bound, ~4 us), at least 2
+    int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 14) * 2);
+    int proj = (left - heads) / 6;
+    if (proj < (tune.windows_per_cta ? 6 : 10)) return false;
+    heads = left - 6 * proj;                                   // whatever the 6-CTA granularity leaves goes to the heads
+    heads = heads / 2 * 2;
+    if (heads < 2) { --proj; heads += 6; }
+    plan->tile = tile; plan->rec_ctas = (int)rec; plan->proj_workers = proj; plan->heads_workers = heads;
+    return true;
 }
 
 // Returns the number of kernel launches issued, or a negative hb_status (message in err).
