@@ -11,5 +11,5 @@ timeout 400 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/b
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_B256.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_B2048.csv python bench.py --batch 2048 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:tc_chunkloop_kernel -s 2 -c 1 -f -o gpurun_out/prof_chunkloop python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_loop.log 2>&1
-HB_NO_CHUNKLOOP=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_recurrence_kernel -s 10 -c 1 -f -o gpurun_out/prof_recurrence python bench.py --batch 2048 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_rec.log 2>&1
+HB_NO_CHUNKLOOP=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_recurrence -s 10 -c 1 -f -o gpurun_out/prof_recurrence python bench.py --batch 2048 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_rec.log 2>&1
 ls -la gpurun_out
