@@ -1241,6 +1241,25 @@ tc_recurrence2_kernel(const RecArgs ra)
     if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
+// first-index argmax over the [B, T, 16] records: classes 0..4 base, 5..15 run length (predict_gpu.py:155-156)
+__global__ void argmax16_kernel(const float* __restrict__ p16, int64_t positions, uint8_t* __restrict__ base_label, uint8_t* __restrict__ rle_label)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= positions) return;
+    const float4* pp = reinterpret_cast<const float4*>(p16 + i * NCLS);
+    float v[NCLS];
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) { const float4 o = pp[c4]; v[4 * c4] = o.x; v[4 * c4 + 1] = o.y; v[4 * c4 + 2] = o.z; v[4 * c4 + 3] = o.w; }
+    int ib = 0, ir = 0;
+    float vb = v[0], vr = v[NBASE];
+#pragma unroll
+    for (int c = 1; c < NBASE; ++c) if (v[c] > vb) { vb = v[c]; ib = c; }
+#pragma unroll
+    for (int c = 1; c < NRLE; ++c) if (v[NBASE + c] > vr) { vr = v[NBASE + c]; ir = c; }
+    base_label[i] = (uint8_t)ib;
+    rle_label[i] = (uint8_t)ir;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Heads + softmax + accumulate (predict_gpu.py:137-149) on tensor cores.
 // Roles are swapped here: A = activations (M = 128 positions = 8 windows x 16 columns, straight
@@ -1255,7 +1274,9 @@ struct HeadsArgs {
     int64_t n_wg, B; int W, T, col0, col_step;         // chunk k accumulates into image columns col0 + k * col_step + t
     const __half* w_img;                               // [hi, lo][16 x 256] core-matrix image, LBO 128 / SBO 4096
     const float* b_head; float inv_scale;
-    float* p_base; float* p_rle;
+    float* p_base; float* p_rle;                       // accumulated softmax sums in the reference's layouts [B, T, 5] / [B, T, 11] ...
+    float* p16;                                        // ... or (when the caller does not ask for them) one [B, T, 16] array: 64 B per position
+    int chunk0;                                        // index of the launch's first chunk in the reference loop (first-touch rule of p16)
     // persistent mode
     int n_chunks; const unsigned long long* progress; int rec_n; const int* tile_order;
     unsigned long long* heads_done;                    // [group] += 4 per finished tile
@@ -1266,11 +1287,12 @@ struct HeadsArgs {
 // the persistent kernel pins window groups to workers so that the accumulation of successive chunks into
 // the same P rows stays ordered.
 __device__ __forceinline__ bool heads_job(const HeadsArgs& a, int worker, int n_workers, int tiles_t, int64_t q,
-                                          int& chunk, int64_t& wg, int& t0) {
+                                          int& chunk, int64_t& wg, int& t0, bool* last_of_wg = nullptr) {
     if (a.n_chunks <= 0) {
         const int64_t tile = worker + q * n_workers;
         if (tile >= a.n_wg * tiles_t) return false;
         chunk = 0; wg = tile / tiles_t; t0 = (int)(tile % tiles_t) * 16;
+        if (last_of_wg) *last_of_wg = false;
         return true;
     }
     const int64_t my_wgs = (a.n_wg - worker + n_workers - 1) / n_workers;
@@ -1281,6 +1303,7 @@ __device__ __forceinline__ bool heads_job(const HeadsArgs& a, int worker, int n_
     wg = worker + (r / tiles_t) * n_workers;
     const int pos = (int)(r % tiles_t);
     t0 = (a.tile_order ? a.tile_order[pos] : pos) * 16;
+    if (last_of_wg) *last_of_wg = pos == tiles_t - 1;         // a worker takes the tiles of a window group back to back
     return true;
 }
 
@@ -1375,7 +1398,8 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
 #pragma unroll
         for (int c = 0; c < NCLS; ++c) bias[c] = a.b_head[c];
         const int row = warp * 32 + lane;                       // position within the tile: (column, window)
-        for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
+        bool last_of_wg = false;
+        for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0, &last_of_wg); ++it) {
             const int t = t0 + (row >> 3);
             const int64_t b = wg * WG + (row & 7);
             const int col = a.col0 + chunk * a.col_step + t;
@@ -1401,6 +1425,25 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                     v[c] = expf(v[c] - (c < NBASE ? mb : mr));
                     if (c < NBASE) sb += v[c]; else sr += v[c];
                 }
+                if (a.p16 != nullptr) {
+                    // one 64-byte record per position: 4 x 16-byte accesses instead of 16 scattered 4-byte ones, and no read
+                    // at all when this chunk is the first one that covers the column (predict_gpu.py:137-149 adds into zeros)
+#pragma unroll
+                    for (int c = 0; c < NBASE; ++c) v[c] /= sb;
+#pragma unroll
+                    for (int c = NBASE; c < NCLS; ++c) v[c] /= sr;
+                    float4* pp = reinterpret_cast<float4*>(a.p16 + (b * T + col) * NCLS);
+                    const int first_chunk = col < W ? 0 : (col - W) / a.col_step + 1;
+                    if (a.chunk0 + chunk != first_chunk) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const float4 o = __ldcg(pp + c4);
+                            v[4 * c4] += o.x; v[4 * c4 + 1] += o.y; v[4 * c4 + 2] += o.z; v[4 * c4 + 3] += o.w;
+                        }
+                    }
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) pp[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                } else {
                 float* pb = a.p_base + (b * T + col) * NBASE;
                 float* pr = a.p_rle + (b * T + col) * NRLE;
                 float old[NCLS];                             // all 16 reads in flight at once (one global round trip, not 16)
@@ -1412,12 +1455,13 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                 for (int c = 0; c < NBASE; ++c) pb[c] = old[c] + v[c] / sb;
 #pragma unroll
                 for (int c = 0; c < NRLE; ++c) pr[c] = old[NBASE + c] + v[NBASE + c] / sr;
+                }
             }
             if (acct) t_wait[2] += clock64() - t_math;
-            if (a.heads_done != nullptr) {
+            if (a.heads_done != nullptr && last_of_wg) {     // one fence per (chunk, window group), not per tile
                 HB_TIMED(1, __threadfence());
                 __syncwarp();
-                if (lane == 0) tc::red_release_gpu_add(a.heads_done + wg, 1ull);
+                if (lane == 0) tc::red_release_gpu_add(a.heads_done + wg, (unsigned long long)tiles_t);
             }
             if (a.dbg != nullptr && worker == 0 && tid == 0) a.dbg[7100 + chunk] = (long long)globaltimer_ns();
         }
@@ -1556,6 +1600,7 @@ struct TensorWorkspace {
     float* hid_b;
     float* p_base;
     float* p_rle;
+    float* p16;         // [B, T, 16]           accumulated softmax sums of both heads, one 64-byte record per position
     size_t bytes;
 };
 
@@ -1583,6 +1628,7 @@ inline TensorWorkspace tensor_carve(void* base, int64_t B, int T, int W, int Kp,
     ws.hid_b = reinterpret_cast<float*>(take(Bp * 2 * H * sizeof(float)));
     ws.p_base = reinterpret_cast<float*>(take((size_t)B * T * NBASE * sizeof(float)));
     ws.p_rle = reinterpret_cast<float*>(take((size_t)B * T * NRLE * sizeof(float)));
+    ws.p16 = reinterpret_cast<float*>(take((size_t)B * T * NCLS * sizeof(float)));
     ws.bytes = off;
     return ws;
 }
@@ -1828,7 +1874,8 @@ inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, Ch
     const int64_t rec = (B + tile - 1) / tile;
     if (2 * rec > sms) return false;
     const int left = sms - (int)(2 * rec);
-    // heads: one CTA in seven of what the recurrence leaves (a heads tile is latency-bound, ~4 us), at least 2
+    // heads: one CTA in seven of what the recurrence leaves, at least 2 (a heads tile is a serial load -> MMA -> epilogue
+    // chain of ~4 us; with 6 workers at B=256 the decoder waited for the heads: 68 k windows/s against 74.6 k with 12)
     int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 14) * 2);
     int proj = (left - heads) / 6;
     if (proj < (tune.windows_per_cta ? 6 : 10)) return false;
@@ -1850,8 +1897,14 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const int F = e->features;
     const int64_t n_wg = (B + WG - 1) / WG;
     int launches = 0;
-    cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s);
-    cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s);
+    // the reference's two arrays only when the caller wants the probabilities back; else one 64-byte record per position
+    float* p16 = (base_prob || rle_prob) ? nullptr : ws.p16;
+    if (p16) {
+        cudaMemsetAsync(p16, 0, (size_t)B * T * NCLS * sizeof(float), s);
+    } else {
+        cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s);
+        cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s);
+    }
     const int xblk = e->enc.Kp * 16;                           // bytes of one (group, column) pixel block
     const int proj_workers = std::max(1, e->sm_count / 6);
     const bool pdl = e->tune.pdl;
@@ -1910,7 +1963,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     HeadsArgs heads_base{};
     heads_base.n_wg = n_wg; heads_base.B = B; heads_base.W = W; heads_base.T = T; heads_base.col_step = J;
     heads_base.w_img = e->head_img; heads_base.b_head = e->b_head; heads_base.inv_scale = e->head_inv;
-    heads_base.p_base = p_base; heads_base.p_rle = p_rle;
+    heads_base.p_base = p_base; heads_base.p_rle = p_rle; heads_base.p16 = p16;
 
     // hb_enable_kernel_timing(2): CUDA events around every launch of the dominant kernel (no launch overlap then)
     auto dominant_begin = [&]() -> size_t {
@@ -2088,7 +2141,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         cudaEventRecord(e->ev_dec[buf], s);
         cudaStreamWaitEvent(e->side, e->ev_dec[buf], 0);
         HeadsArgs ha = heads_base;
-        ha.yimg = ws.yimg2[buf]; ha.col0 = i;
+        ha.yimg = ws.yimg2[buf]; ha.col0 = i; ha.chunk0 = chunk;
         tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), e->side>>>(ha);
         cudaEventRecord(e->ev_heads[buf], e->side);
         launches += 4;
@@ -2097,7 +2150,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     }
     for (int b = 0; b < std::min(chunk, 2); ++b) cudaStreamWaitEvent(s, e->ev_heads[b], 0);   // join the side stream
     const int64_t positions = B * T;
-    argmax_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p_base, p_rle, positions, base_labels, rle_labels);
+    if (p16) argmax16_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p16, positions, base_labels, rle_labels);
+    else argmax_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p_base, p_rle, positions, base_labels, rle_labels);
     launches += 1;
     if (dbg_on && dbg_buf) {
         static int printed = 0;
