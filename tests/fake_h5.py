@@ -68,5 +68,11 @@ def add_image(path, name, contig, start, end, chunk_idx, image, position):
     grp['position'] = _Dataset(position)
 
 
+def add_labels(path, name, label_base, label_run_length):
+    grp = FakeFile(path, 'a').root['images'][name]
+    grp['label_base'] = _Dataset(np.asarray(label_base).reshape(-1, 1))          # MarginPolish stores [T, 1]
+    grp['label_run_length'] = _Dataset(np.asarray(label_run_length).reshape(-1, 1))
+
+
 def reset():
     _STORE.clear()

@@ -83,3 +83,40 @@ def test_train_step_matches_port_autograd(batch, width, features, with_hidden):
     loss3, *_ = trainer.step(x.cuda(), hidden.cuda() if with_hidden else None, lb.cuda(), lr.cuda())
     assert loss3 < loss
     trainer.close()
+
+
+def test_training_loop_mirror(tmp_path, monkeypatch):
+    """helen_b200.models.train.train (train.py:19-259 mirror) on a tiny in-memory data set: the training loss falls from
+    epoch to epoch, every epoch leaves a reference-format checkpoint that load_simple_model reads back, and retraining
+    continues from it."""
+    import fake_h5
+    from helen_b200 import hdf5
+    from helen_b200.models.ModelHander import ModelHandler
+    from helen_b200.models.train import train
+    fake_h5.reset()
+    monkeypatch.setattr(hdf5, "open_file", fake_h5.open_file)
+    data_dir = tmp_path / "images"
+    data_dir.mkdir()
+    (data_dir / "train.h5").write_bytes(b"")                  # the directory listing is real, the contents are the fake store
+    path = str(data_dir / "train.h5")
+    rng = np.random.default_rng(3)
+    for i in range(6):
+        img = rng.integers(0, 256, (200, 10), dtype=np.uint8)
+        fake_h5.add_image(path, f"img{i}", "chr1", 0, 200, i, img, np.zeros((200, 3), int))
+        # learnable labels: a function of the pixels
+        fake_h5.add_labels(path, f"img{i}", (img[:, 0] // 52).clip(0, 4), (img[:, 1] // 24).clip(0, 10))
+    model_dir, stats_dir = str(tmp_path) + "/models_", str(tmp_path) + "/stats_"
+    torch.manual_seed(0)
+    model, optimizer, stats = train(str(data_dir), str(data_dir), batch_size=3, epoch_limit=3, gpu_mode=True, num_workers=0,
+                                    retrain_model=False, retrain_model_path=None, gru_layers=1, hidden_size=128, lr=1e-3, decay=0.0,
+                                    model_dir=model_dir, stats_dir=stats_dir, not_hyperband=True)
+    losses = [l for _, l in stats['loss_epoch']]
+    assert len(losses) == 3 and losses[-1] < losses[0], losses
+    loaded, hidden, layers, epochs = ModelHandler.load_simple_model(model_dir + "HELEN_epoch_3_checkpoint.pkl", 1, 10, 1000, 5, 11)
+    assert (hidden, layers, epochs) == (128, 1, 2)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), loaded.state_dict()[k])
+    _, _, stats2 = train(str(data_dir), str(data_dir), 3, 1, True, 0, True, model_dir + "HELEN_epoch_3_checkpoint.pkl", 1, 128, 1e-3, 0.0,
+                         model_dir, stats_dir, True)
+    assert stats2['loss_epoch'][-1][1] < losses[-1] * 1.05
+    fake_h5.reset()
