@@ -335,7 +335,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                     const long long t_ = acct ? clock64() : 0;
                     const long long t_spin = clock64();
                     while (true) {
-                        if (front < back && !jb.pixel && vb >= need_of(jb, chunk)) { e = eb; --back; break; }
+                        if (front < back && !jb.pixel && vb >= need_of(jb, chunk)) { e = eb | (1 << 30); --back; break; }   // bit 30: the decoder waits for it
                         if (jf.pixel || vf >= need_of(jf, chunk)) { e = ef; ++front; break; }    // pixel jobs wait for nothing
                         __nanosleep(100);
                         if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap();
@@ -392,7 +392,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             if (n_pending <= keep) return;
             // wait_group (not .read) returns when the copies' writes have been performed; the release below orders them
             // before the counter.  (An additional fence.proxy.async here cost ~1000 cycles per publication.)
-            if (keep == 0) tc::bulk_wait0(); else tc::bulk_wait_pending<2>();
+            if (keep == 0) tc::bulk_wait0(); else if (keep == 1) tc::bulk_wait_pending<1>(); else tc::bulk_wait_pending<2>();
 #ifdef HB_STRICT_PROXY_FENCE
             tc::fence_proxy_async_all();
 #endif
@@ -411,7 +411,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             const int sb = it & 1;
             const uint32_t par = (uint32_t)((it >> 1) & 1);
             HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
-            j = split ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
+            const int e_ring = split ? job_ring[it & 15] : 0;
+            j = split ? proj_decode(a, e_ring) : proj_tile_job(a, worker, n_workers, idx);
             float* out = j.pixel ? a.px.gi : (j.src_dir ? a.gi_b : gi);
             const int out_cols = j.pixel ? a.px.cols : W;
             if (lane < 8 && j.t0 + lane < out_cols)
@@ -425,7 +426,9 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 pending[n_pending++] = j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
                                                : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
                 if (idx == n_jobs - 1) HB_TIMED(2, publish(0));                      // last job of the chunk
-                // (publishing the backlog jobs one by one so the decoder sees its first tiles sooner was measured: no gain)
+                // jobs taken from the back of the list are the ones the decoder is waiting for: batches of three (one
+                // publication per job was measured: the fence makes this warp the bottleneck)
+                else if ((e_ring >> 30) & 1) { if (n_pending >= 4) HB_TIMED(3, publish(1)); }
                 else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2));   // copies issued two jobs ago have normally landed: no stall
             }
             if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
