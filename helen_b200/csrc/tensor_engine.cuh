@@ -43,8 +43,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr int WG = 8;                             // windows per window group == rows of one core matrix
 // h / y images: [8 windows x 128 k] fp16 blocks in the K-major 128-byte-swizzle layout (tc::sw128_offset): dense, the
 // tensor core reads full 128-byte rows, and the gate threads' 2-byte stores still spread over all banks (the XOR moves
-// the four k-chunks a warp writes to different bank groups).  (The no-swizzle core-matrix layout ran every MMA at about
-// half the rate; padding its k-group stride to 144 B only fixed the store conflicts.)
+// the four k-chunks a warp writes to different bank groups).  (The MMA rate is the same as with the no-swizzle core-matrix
+// layout, tools/mma_rate.cu; that layout needed its k-group stride padded to 144 B to avoid the store conflicts.)
 constexpr int YBLK = 2048;                        // [8 windows x 128 k] fp16 image of one direction: two swizzle atoms
 constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)  [sizes only]
 constexpr int GI_ROW_BYTES = G * 4;               // 1536 B: gi of one (window, t, direction)
@@ -798,10 +798,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         HB_STAMP(4);                                         // all columns published
     } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
-        // Measured (HB_DEBUG_TIMELINE): an M=128, N=16, K=16 MMA occupies the tensor pipe ~12 cycles, so the MMA time
-        // of a step is set by the instruction count (a second issuer warp and an issue order rotating over the gate
-        // blocks were both slower); per-block commits let the gate warps overlap the r and z sigmoids with the
-        // remaining MMAs.
+        // An M=128, N=16, K=16 MMA occupies the tensor pipe ~9.6 cycles (tools/mma_rate.cu), so the 48 MMAs of a step are
+        // ~460 cycles plus ~250 of pipeline fill and commit -> wake-up latency (HB_DEBUG_TIMELINE).  A second issuer warp
+        // and an issue order rotating over the gate blocks were both slower; per-block commits let the gate warps
+        // overlap the r and z sigmoids with the remaining MMAs.
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
         HB_STAMP(1);                                         // first step released
