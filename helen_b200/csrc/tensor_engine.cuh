@@ -799,9 +799,11 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer =====================
         // An M=128, N=16, K=16 MMA occupies the tensor pipe ~9.6 cycles (tools/mma_rate.cu), so the 48 MMAs of a step are
-        // ~460 cycles plus ~250 of pipeline fill and commit -> wake-up latency (HB_DEBUG_TIMELINE).  A second issuer warp
-        // and an issue order rotating over the gate blocks were both slower; per-block commits let the gate warps
-        // overlap the r and z sigmoids with the remaining MMAs.
+        // ~460 cycles plus ~250 of pipeline fill and commit -> wake-up latency (HB_DEBUG_TIMELINE).  A second issuer warp,
+        // an issue order rotating over the gate blocks, and starting the r block quarter by quarter as the gate warps
+        // publish h (one h_ready barrier per TMEM lane quarter: +85 cycles per step, the extra waits cost more than the
+        // overlap gives) were all slower; per-block commits let the gate warps overlap the r and z sigmoids with the
+        // remaining MMAs.
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
         HB_STAMP(1);                                         // first step released
