@@ -371,6 +371,91 @@ def run_native(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_polish(args, rank, world, local_rank):
+    """--polish N: BASELINE configs[2], window-sharded polish of N synthetic windows (the 3 Gb contig set is ~3 M): every rank
+    generates its contiguous shard on the device in batches of --batch windows (seed 1000 + rank), predicts it, and the uint8
+    labels are gathered in window-index order on rank 0 and copied to host memory (the "stitch" of this mode).  Secondary line."""
+    import torch
+    import torch.distributed as dist
+    from helen_b200 import build as hb_build
+    from helen_b200.predictor import WindowPredictor
+    from helen_b200.sharding import shard_bounds
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --polish: no CUDA device; there is no CPU fallback")
+    if rank == 0:
+        hb_build.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pred = WindowPredictor(random_parameters(args.features, seed=0), device=local_rank, engine=args.engine)
+    start, end = shard_bounds(args.polish, world, rank)
+    n_local = end - start
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    base_all = torch.empty((n_local, T_COLUMNS), dtype=torch.uint8, device=dev)
+    rle_all = torch.empty((n_local, T_COLUMNS), dtype=torch.uint8, device=dev)
+    warm = torch.randint(0, 256, (min(args.batch, max(n_local, 1)), T_COLUMNS, args.features), dtype=torch.uint8, device=dev, generator=gen)
+    for _ in range(3):
+        pred.predict(warm)
+    host = torch.empty((2, args.polish, T_COLUMNS), dtype=torch.uint8).pin_memory() if rank == 0 else None   # stitched result
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for off in range(0, n_local, args.batch):
+        n = min(args.batch, n_local - off)
+        images = torch.randint(0, 256, (n, T_COLUMNS, args.features), dtype=torch.uint8, device=dev, generator=gen)
+        b, r = pred.predict(images)
+        base_all[off:off + n] = b
+        rle_all[off:off + n] = r
+    torch.cuda.synchronize()
+    t_compute = time.perf_counter() - t0
+    # ordered gather on rank 0 (contiguous shards: concatenation in rank order is window-index order), then to host
+    if world > 1:
+        sizes = [shard_bounds(args.polish, world, q)[1] - shard_bounds(args.polish, world, q)[0] for q in range(world)]
+        if rank == 0:
+            host[0, :n_local].copy_(base_all, non_blocking=True)
+            host[1, :n_local].copy_(rle_all, non_blocking=True)
+            off = n_local
+            recv = torch.empty((2, max(sizes), T_COLUMNS), dtype=torch.uint8, device=dev)
+            for q in range(1, world):
+                dist.recv(recv, src=q)
+                host[:, off:off + sizes[q]].copy_(recv[:, :sizes[q]], non_blocking=True)
+                torch.cuda.synchronize()
+                off += sizes[q]
+        else:
+            send = torch.zeros((2, max(sizes), T_COLUMNS), dtype=torch.uint8, device=dev)
+            send[0, :n_local] = base_all
+            send[1, :n_local] = rle_all
+            dist.send(send, dst=0)
+        torch.cuda.synchronize()
+        dist.barrier()
+    else:
+        host[0].copy_(base_all, non_blocking=True)
+        host[1].copy_(rle_all, non_blocking=True)
+        torch.cuda.synchronize()
+    t_total = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_compute, t_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_compute, t_total = t.tolist()
+    if rank == 0:
+        checksum = int(host[0, ::997].to(torch.int64).sum() + host[1, ::997].to(torch.int64).sum())
+        print(json.dumps({
+            "metric": "window-sharded polish, end-to-end windows/sec (generate on device, predict, ordered gather of labels to host)",
+            "value": args.polish / t_total, "unit": "windows/s", "n_gpus": world, "windows": args.polish, "batch_per_launch": args.batch,
+            "seconds": t_total, "predict_seconds": t_compute, "predict_windows_per_s": args.polish / t_compute,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16x3-split operands, f32 accumulate/state",
+            "data": "synthetic", "label_checksum": checksum,
+            "config": {"workload": f"{world}xB200 window-sharded polish over {args.polish} synthetic windows [T=1000, F={args.features}] "
+                                   f"in batches of {args.batch}, host-side ordered gather (BASELINE configs[2])"},
+        }), flush=True)
+    pred.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_train(args):
     """--train: BASELINE configs[3], one chunk step = forward + CE(base) + weighted CE(rle) + backward on [B=128, 100, F]
     (train.py:189-201 through ChunkTrainer.step -> hb_train_step_chunk); secondary line, not the headline metric."""
@@ -453,6 +538,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="windows per CPU-baseline batch")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--reference-sample", type=int, default=32, help="windows per step of --impl reference")
+    ap.add_argument("--polish", type=int, default=0, metavar="N",
+                    help="secondary line: BASELINE configs[2], window-sharded polish of N synthetic windows (use --batch 2048)")
     ap.add_argument("--train", action="store_true", help="secondary line: BASELINE configs[3], one training chunk step at B=128")
     ap.add_argument("--train-batch", type=int, default=128)
     args = ap.parse_args()
@@ -462,14 +549,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    if world != args.gpus and world == 1 and args.gpus > 1 and args.impl == "native":
+    if world != args.gpus and world == 1 and args.gpus > 1 and args.impl == "native" and not args.train:
         # launched without torchrun: re-exec under torch.distributed.run
         import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
                os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    if args.train:
+    if args.polish:
+        run_polish(args, rank, world, local_rank)
+    elif args.train:
         if rank == 0:
             run_train(args)
     elif args.impl == "reference":
