@@ -53,3 +53,20 @@ class DataStore(object):
             self.file_handler[chunk + '/position'] = np.asarray(position).astype(np.uint32)
             self.file_handler[chunk + '/bases'] = np.asarray(predicted_bases).astype(np.uint8)
             self.file_handler[chunk + '/rles'] = np.asarray(predicted_rles).astype(np.uint8)
+
+    def write_predictions(self, contig, contig_start, contig_end, chunk_id, position, predicted_bases, predicted_rles,
+                          filename=None):
+        """One batch of records (the per-batch loop of predict_gpu.py:176-179 in one call): same file content as
+        calling write_prediction per record, with the dtype conversions done once per batch."""
+        position = np.asarray(position).astype(np.uint32)
+        predicted_bases = np.asarray(predicted_bases).astype(np.uint8)
+        predicted_rles = np.asarray(predicted_rles).astype(np.uint8)
+        contig_start = np.asarray(contig_start).reshape(-1).tolist()
+        contig_end = np.asarray(contig_end).reshape(-1).tolist()
+        chunk_id = np.asarray(chunk_id).reshape(-1).tolist()
+        if not (len(contig) == len(contig_start) == len(contig_end) == len(chunk_id) == len(position)
+                == len(predicted_bases) == len(predicted_rles)):
+            raise ValueError("write_predictions: all arguments must have one entry per record")
+        for i in range(len(contig)):
+            self.write_prediction(contig[i], contig_start[i], contig_end[i], chunk_id[i], position[i],
+                                  predicted_bases[i], predicted_rles[i])

@@ -17,3 +17,8 @@ class FileManager:
         """MarginPolish image files are those whose name ends in 'h5' (FileManager.py:52-61)."""
         return [os.path.join(directory_path, name) for name in os.listdir(directory_path)
                 if os.path.isfile(os.path.join(directory_path, name)) and name[-2:] == 'h5']
+
+    @staticmethod
+    def chunks(file_names, threads):
+        """Consecutive groups of `threads` items (FileManager.py:62-70; the argument is a group size)."""
+        return [file_names[i:i + threads] for i in range(0, len(file_names), threads)]

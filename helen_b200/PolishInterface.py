@@ -1,16 +1,15 @@
 """polish_genome with the reference's signature (helen/modules/python/PolishInterface.py:49-105):
 call_consensus into a timestamped prediction directory, then stitch.
 
-Stitch (SSW-anchored overlap resolution -> FASTA) is downstream of this hot path and is not
-re-implemented here.  If the reference package is importable its
-perform_stitch is used unchanged on the prediction files this package wrote (same HDF5 schema);
-otherwise the prediction directory is reported for `helen stitch`.
+Stitch (label decoding, anchored overlap resolution -> FASTA) is
+helen_b200's own: StitchInterface.perform_stitch over the host library behind include/helen_stitch.h.
 """
 import sys
 import time
 
 from .CallConsensusInterface import call_consensus
 from .FileManager import FileManager
+from .StitchInterface import perform_stitch
 from .TextColor import TextColor
 
 
@@ -32,19 +31,11 @@ def polish_genome(image_dir, model_path, batch_size, num_workers, threads, outpu
     call_consensus(image_dir, model_path, batch_size, num_workers, threads, prediction_output_directory,
                    output_prefix, gpu_mode, device_ids, callers)
     t1 = time.time()
-    try:
-        from helen.modules.python.StitchInterface import perform_stitch
-    except ImportError:
-        perform_stitch = None
-    if perform_stitch is not None:
-        sys.stderr.write(TextColor.GREEN + "INFO: STITCH STARTING\n" + TextColor.END)
-        perform_stitch(prediction_output_directory, output_dir, output_prefix, threads)
-    else:
-        sys.stderr.write(TextColor.YELLOW + "INFO: STITCH IS NOT PART OF helen_b200; RUN `helen stitch -i "
-                         + str(prediction_output_directory) + " -o " + str(output_dir) + " -t " + str(threads)
-                         + "` FROM THE REFERENCE PACKAGE.\n" + TextColor.END)
+    sys.stderr.write(TextColor.GREEN + "INFO: STITCH STARTING\n" + TextColor.END)
+    perform_stitch(prediction_output_directory, output_dir, output_prefix, threads)
     t2 = time.time()
     sys.stderr.write(TextColor.GREEN + "INFO: FINISHED PROCESSING.\n" + TextColor.END)
     sys.stderr.write(TextColor.GREEN + "INFO: TOTAL TIME ELAPSED: " + get_elapsed_time_string(t0, t2) + "\n" + TextColor.END)
     sys.stderr.write(TextColor.GREEN + "INFO: PREDICTION TIME: " + get_elapsed_time_string(t0, t1) + "\n" + TextColor.END)
+    sys.stderr.write(TextColor.GREEN + "INFO: STITCH TIME: " + get_elapsed_time_string(t1, t2) + "\n" + TextColor.END)
     return prediction_output_directory

@@ -1,4 +1,5 @@
-"""In-tree build of the CUDA library (nvcc cross-compiles sm_100a without a GPU)."""
+"""In-tree build of the CUDA library (nvcc cross-compiles sm_100a without a GPU) and of the host-side
+stitch library (plain g++)."""
 import os
 import shutil
 import subprocess
@@ -56,5 +57,28 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     return target
 
 
+STITCH_SRC = os.path.join(PKG, "csrc_host", "stitch_host.cpp")
+STITCH_LIB = os.path.join(LIB_DIR, "libhelen_stitch.so")
+
+
+def build_stitch(force=False):
+    """Compile helen_b200/csrc_host/stitch_host.cpp -> helen_b200/lib/libhelen_stitch.so (include/helen_stitch.h)."""
+    deps = [STITCH_SRC, os.path.join(ROOT, "include", "helen_stitch.h")]
+    if not force and os.path.exists(STITCH_LIB) and all(os.path.getmtime(p) <= os.path.getmtime(STITCH_LIB) for p in deps):
+        return STITCH_LIB
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not found; cannot build libhelen_stitch.so")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    tmp = STITCH_LIB + ".tmp"
+    cmd = [gxx, "-O3", "-g", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", tmp, STITCH_SRC]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, STITCH_LIB)
+    return STITCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_stitch(force="--force" in sys.argv))

@@ -38,12 +38,24 @@ def add_call_consensus_arguments(parser):
     return _common(parser, 16, "Total available threads to use.")
 
 
+def add_stitch_arguments(parser):
+    """Arguments of sub-command "stitch" (helen/helen.py:188-222)."""
+    parser.add_argument("-i", "--input_dir", type=str, required=True,
+                        help="[REQUIRED] Path to a directory containing prediction files call consensus.")
+    parser.add_argument("-o", "--output_dir", type=str, required=True, help="[REQUIRED] Path to the output directory.")
+    parser.add_argument("-t", "--threads", type=int, required=True, help="[REQUIRED] Number of threads.")
+    parser.add_argument("-p", "--output_prefix", type=str, required=False, default="HELEN_consensus",
+                        help="Prefix for the output file. Default is: HELEN_consensus")
+    return parser
+
+
 def build_parser():
     parser = argparse.ArgumentParser(description="HELEN consensus calling on B200 (helen_b200).",
                                      formatter_class=argparse.RawTextHelpFormatter)
     subparsers = parser.add_subparsers(dest='sub_command')
     add_polish_arguments(subparsers.add_parser('polish', help="Run call_consensus then stitch."))
     add_call_consensus_arguments(subparsers.add_parser('call_consensus', help="Generate the prediction HDF5 files."))
+    add_stitch_arguments(subparsers.add_parser('stitch', help="Stitch prediction files into a polished FASTA."))
     subparsers.add_parser('torch_stat', help="See PyTorch configuration.")
     subparsers.add_parser('version', help="Show program version.")
     return parser
@@ -62,6 +74,10 @@ def main(argv=None):
         sys.stderr.write(TextColor.GREEN + "INFO: CALL CONSENSUS MODULE SELECTED\n" + TextColor.END)
         call_consensus(flags.image_dir, flags.model_path, flags.batch_size, flags.num_workers, flags.threads,
                        flags.output_dir, flags.output_prefix, flags.gpu_mode, flags.device_ids, flags.callers)
+    elif flags.sub_command == 'stitch':
+        from .StitchInterface import perform_stitch
+        sys.stderr.write(TextColor.GREEN + "INFO: STITCH MODULE SELECTED\n" + TextColor.END)
+        perform_stitch(flags.input_dir, flags.output_dir, flags.output_prefix, flags.threads)
     elif flags.sub_command == 'torch_stat':
         import torch
         sys.stderr.write(TextColor.YELLOW + "TORCH VERSION: " + TextColor.END + str(torch.__version__) + "\n")

@@ -51,9 +51,8 @@ def predict(test_file, output_filename, model_path, batch_size, num_workers, ran
         done.synchronize()
         base_labels, rle_labels = base_dev.cpu().numpy(), rle_dev.cpu().numpy()
         contig, contig_start, contig_end, chunk_id, position, filename = meta
-        for i in range(base_labels.shape[0]):
-            prediction_data_file.write_prediction(contig[i], contig_start[i], contig_end[i], chunk_id[i],
-                                                  position[i], base_labels[i], rle_labels[i], filename[i])
+        prediction_data_file.write_predictions(contig, contig_start, contig_end, chunk_id, position,
+                                               base_labels, rle_labels, filename)
 
     in_flight = None
     for batch_iterator, (contig, contig_start, contig_end, chunk_id, images, position, filename) in enumerate(test_loader, 1):

@@ -1,4 +1,16 @@
-"""Constants of the predict path (mirrors helen/modules/python/Options.py:13-29)."""
+"""Constants of the predict and stitch paths (mirrors helen/modules/python/Options.py:1-29)."""
+
+
+class StitchOptions(object):
+    BASE_ERROR_RATE = 0.0      # Options.py:2
+    label_decoder = {1: 'A', 2: 'C', 3: 'G', 4: 'T', 0: ''}   # Options.py:3
+    MATCH_PENALTY = 4          # Options.py:4  (a score, despite the name)
+    MISMATCH_PENALTY = 6       # Options.py:5
+    GAP_PENALTY = 8            # Options.py:6
+    GAP_EXTEND_PENALTY = 2     # Options.py:7
+    MIN_SEQUENCE_REQUIRED_FOR_MULTITHREADING = 2   # Options.py:8
+    OVERLAP_THRESHOLD = 8      # Options.py:9  shortest aligned run accepted as an anchor
+    KMER_SIZE = 15             # Options.py:10 (unused by the reference)
 
 
 class ImageSizeOptions(object):

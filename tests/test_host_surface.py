@@ -73,6 +73,37 @@ def test_datastore_schema_and_dedup():
     assert "8" in region
 
 
+def test_datastore_batched_write_equals_per_record():
+    """write_predictions with the collated batch a DataLoader yields (lists of str, torch tensors) leaves the same
+    file as write_prediction per record (predict_gpu.py:176-179)."""
+    import torch
+    from helen_b200.DataStore import DataStore
+    rng = np.random.default_rng(0)
+    n = 5
+    contig = ["chr1", "chr1", "chr2", "chr2", "chr2"]
+    start = torch.tensor([0, 0, 500, 500, 500])
+    end = torch.tensor([900, 900, 1400, 1400, 1400])
+    chunk = torch.tensor([0, 1, 0, 1, 1])                      # the last record repeats a key: ignored in both paths
+    pos = torch.from_numpy(rng.integers(-1, 2000, (n, 1000, 3)))
+    bases, rles = rng.integers(0, 5, (n, 1000)).astype(np.uint8), rng.integers(0, 11, (n, 1000)).astype(np.uint8)
+    one = DataStore("per_record.hdf", "w")
+    for i in range(n):
+        one.write_prediction(contig[i], start[i], end[i], chunk[i], pos[i], bases[i], rles[i], "f.h5")
+    many = DataStore("batched.hdf", "w")
+    many.write_predictions(contig, start, end, chunk, pos, bases, rles, ["f.h5"] * n)
+
+    def dump(node, prefix=""):
+        if isinstance(node, dict):
+            return {k2: v2 for k, v in node.items() for k2, v2 in dump(v, prefix + "/" + k).items()}
+        return {prefix: node.value}
+    a, b = dump(fake_h5.open_file("per_record.hdf").root), dump(fake_h5.open_file("batched.hdf").root)
+    assert sorted(a) == sorted(b) and len(a) == 2 * 2 + 4 * 3
+    for key in a:
+        assert a[key].dtype == b[key].dtype and np.array_equal(a[key], b[key]), key
+    with pytest.raises(ValueError):
+        many.write_predictions(contig[:2], start, end, chunk, pos, bases, rles)
+
+
 def test_round_robin_file_sharding():
     from helen_b200.CallConsensusInterface import shard_files
     files = [f"f{i}.h5" for i in range(7)]
