@@ -3,7 +3,12 @@
 
 __getitem__ -> (contig, contig_start, contig_end, chunk_id, image u8[1000, F], position int[1000, 3], path)
 Images shorter than SEQ_LENGTH are right-padded with zero columns, positions with (-1, -1, -1).
+
+Items are listed file by file, so consecutive reads hit the same file: the handle of the file read last stays
+open (one per dataset copy, i.e. per DataLoader worker) instead of one open/close per image as the reference
+does (dataloader_predict.py:61).
 """
+import os
 import sys
 
 import numpy as np
@@ -36,20 +41,45 @@ class SequenceDataset(Dataset):
                     sys.stderr.write(TextColor.YELLOW + "WARN: NO IMAGES FOUND IN FILE: "
                                      + hdf5_file_path + "\n" + TextColor.END)
         self.all_images = file_image_pair
+        self._open_path, self._open_file, self._open_pid = None, None, None
+
+    def _file(self, path):
+        if self._open_pid != os.getpid():           # a handle inherited through fork is not ours to use or close
+            self._open_path, self._open_file, self._open_pid = None, None, os.getpid()
+        if self._open_path != path:
+            self.close()
+            self._open_file, self._open_path = hdf5.open_file(path, 'r'), path
+        return self._open_file
+
+    def close(self):
+        if self._open_file is not None and self._open_pid == os.getpid():
+            self._open_file.close()
+        self._open_path, self._open_file = None, None
+
+    def __getstate__(self):
+        state = dict(self.__dict__)                 # handles do not travel to DataLoader workers
+        state["_open_path"], state["_open_file"] = None, None
+        return state
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __getitem__(self, index):
         hdf5_filepath, image_name = self.all_images[index]
-        with hdf5.open_file(hdf5_filepath, 'r') as hdf5_file:
-            group = hdf5_file['images'][image_name]
-            contig = _scalar(group['contig'][()])
-            if isinstance(contig, bytes):
-                contig = contig.decode()
-            contig = str(contig).replace("'", '')
-            contig_start = int(_scalar(group['contig_start'][()]))
-            contig_end = int(_scalar(group['contig_end'][()]))
-            chunk_id = int(_scalar(group['feature_chunk_idx'][()]))
-            image = np.asarray(group['image'][()]).astype(np.uint8)
-            position = np.asarray(group['position'][()]).astype(np.int64)
+        hdf5_file = self._file(hdf5_filepath)
+        group = hdf5_file['images'][image_name]
+        contig = _scalar(group['contig'][()])
+        if isinstance(contig, bytes):
+            contig = contig.decode()
+        contig = str(contig).replace("'", '')
+        contig_start = int(_scalar(group['contig_start'][()]))
+        contig_end = int(_scalar(group['contig_end'][()]))
+        chunk_id = int(_scalar(group['feature_chunk_idx'][()]))
+        image = np.asarray(group['image'][()]).astype(np.uint8)
+        position = np.asarray(group['position'][()]).astype(np.int64)
 
         seq = ImageSizeOptions.SEQ_LENGTH
         if image.shape[0] < seq:

@@ -53,6 +53,33 @@ def test_sequence_dataset_batches_through_dataloader():
     assert list(contig) == ["ctg"] * 4 and start.tolist() == [0, 1000, 2000, 3000]
 
 
+def test_sequence_dataset_keeps_one_file_open(monkeypatch):
+    """Consecutive items of one file reuse its handle; moving to the next file closes it; workers start without one."""
+    import pickle
+    import helen_b200.hdf5 as hb_hdf5
+    from helen_b200.models.dataloader_predict import SequenceDataset
+    for name in ("c.h5", "d.h5"):
+        for i in range(3):
+            fake_h5.add_image(name, f"img{i}", "ctg", i * 1000, (i + 1) * 1000, i, np.zeros((1000, 10), np.uint8), np.zeros((1000, 3), int))
+    ds = SequenceDataset(None, file_list=["c.h5", "d.h5"])
+    opened, closed = [], []
+    real_open = hb_hdf5.open_file
+
+    def counting_open(path, mode='r'):
+        handle = real_open(path, mode)
+        opened.append(path)
+        monkeypatch.setattr(handle, "close", lambda: closed.append(path), raising=False)
+        return handle
+    monkeypatch.setattr(hb_hdf5, "open_file", counting_open)
+    for i in range(len(ds)):
+        ds[i]
+    assert opened == ["c.h5", "d.h5"] and closed == ["c.h5"]
+    clone = pickle.loads(pickle.dumps(ds))
+    assert clone._open_file is None and len(clone) == 6
+    ds.close()
+    assert closed == ["c.h5", "d.h5"]
+
+
 def test_datastore_schema_and_dedup():
     from helen_b200.DataStore import DataStore
     store = DataStore("out_0.hdf", "w")
