@@ -1,5 +1,6 @@
 """Small filesystem helpers with the reference's behaviour (helen/modules/python/FileManager.py)."""
 import os
+import time
 
 
 class FileManager:
@@ -11,6 +12,22 @@ class FileManager:
         if not os.path.exists(output_dir):
             os.mkdir(output_dir)
         return os.path.abspath(output_dir)
+
+    @staticmethod
+    def handle_train_output_directory(output_dir):
+        """<output_dir>/trained_models_<stamp>/ and its stats_<stamp>/ sub-directory (FileManager.py:26-49)."""
+        timestr = time.strftime("%m%d%Y_%H%M%S")
+        if output_dir[-1] != "/":
+            output_dir += "/"
+        if not os.path.exists(output_dir):
+            os.mkdir(output_dir)
+        model_save_dir = output_dir + "trained_models_" + timestr + "/"
+        if not os.path.exists(model_save_dir):
+            os.mkdir(model_save_dir)
+        stats_directory = model_save_dir + "stats_" + timestr + "/"
+        if not os.path.exists(stats_directory):
+            os.mkdir(stats_directory)
+        return model_save_dir, stats_directory
 
     @staticmethod
     def get_file_paths_from_directory(directory_path):

@@ -1,5 +1,7 @@
 """Host-side mirror of the reference surface: dataset padding rules, prediction file schema,
 file sharding, CLI flags and argument-error behaviour (CPU only)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -168,3 +170,32 @@ def test_call_consensus_argument_errors_exit_1(tmp_path, kwargs):
     with pytest.raises(SystemExit) as err:
         call_consensus(**args)
     assert err.value.code == 1
+
+
+def test_helen_train_cli_and_output_directories(tmp_path, capsys):
+    """helen_train's flags (helen_train.py:10-137) and the trained_models_<stamp>/stats_<stamp>/ layout
+    (FileManager.py:26-49); running a training needs a GPU and is covered by tests/test_gpu_train.py."""
+    from helen_b200 import helen_train
+    from helen_b200.FileManager import FileManager
+    p = helen_train.build_parser()
+    a = p.parse_args(["train", "--train_image_dir", "tr", "--test_image_dir", "te", "--gpu_mode", "-d_ids", "2,3"])
+    assert (a.batch_size, a.epoch_size, a.output_dir, a.retrain_model, a.retrain_model_path, a.num_workers) == \
+        (100, 10, "./model", False, False, 16)
+    assert a.gpu_mode is True and a.device_ids == "2,3"
+    t = p.parse_args(["test", "--test_image_dir", "te", "--model_path", "m.pkl"])
+    assert (t.batch_size, t.gpu_mode, t.print_details, t.output_dir, t.num_workers) == (100, False, False, "./debug_output", 40)
+    assert helen_train.main(["version"]) == 0 and "VERSION" in capsys.readouterr().out
+    assert helen_train.main([]) == 1
+    model_dir, stats_dir = FileManager.handle_train_output_directory(str(tmp_path / "out"))
+    assert os.path.isdir(model_dir) and os.path.isdir(stats_dir)
+    assert os.path.basename(model_dir.rstrip("/")).startswith("trained_models_") and stats_dir.startswith(model_dir)
+    with pytest.raises(SystemExit):                       # no CPU path: loud, like call_consensus without --gpu_mode
+        from helen_b200.TrainInterface import train_interface
+        train_interface("tr", "te", False, None, 1, 2, 0, str(tmp_path / "out2"), False, False)
+
+
+def test_confusion_matrix_text(tmp_path):
+    from helen_b200.TrainInterface import write_confusion_matrix
+    path = str(tmp_path / "cm.txt")
+    write_confusion_matrix([[5, 1], [0, 7]], ["-", "A"], path)
+    assert open(path).read().splitlines() == ["true\\pred\t-\tA", "-\t5\t1", "A\t0\t7"]
