@@ -1,12 +1,14 @@
+"""ANSI escape sequences behind the INFO / WARN / ERROR lines the command line prints; the attribute names are
+the ones the reference's messages use (helen/modules/python/TextColor.py), so user scripts that strip or match
+them keep working."""
+
+
+def _sgr(code):
+    return '\033[%dm' % code
+
+
 class TextColor:
-    """ANSI colours used by the INFO/ERROR lines the CLI prints (users script against them)."""
-    PURPLE = '\033[95m'
-    CYAN = '\033[96m'
-    DARKCYAN = '\033[36m'
-    BLUE = '\033[94m'
-    GREEN = '\033[92m'
-    YELLOW = '\033[93m'
-    RED = '\033[91m'
-    BOLD = '\033[1m'
-    UNDERLINE = '\033[4m'
-    END = '\033[0m'
+    END = _sgr(0)
+    BOLD, UNDERLINE = _sgr(1), _sgr(4)
+    DARKCYAN = _sgr(36)
+    RED, GREEN, YELLOW, BLUE, PURPLE, CYAN = (_sgr(code) for code in range(91, 97))

@@ -8,32 +8,43 @@ from .TextColor import TextColor
 from . import __version__
 
 
-def add_train_arguments(parser):
-    """helen_train.py:10-84"""
-    parser.add_argument("--train_image_dir", type=str, required=True, help="Training data directory containing HDF files.")
-    parser.add_argument("--test_image_dir", type=str, required=True, help="Training data directory containing HDF files.")
-    parser.add_argument("--batch_size", type=int, required=False, default=100, help="Batch size for training, default is 100.")
-    parser.add_argument("--epoch_size", type=int, required=False, default=10, help="Epoch size for training iteration.")
-    parser.add_argument("--output_dir", type=str, required=False, default='./model', help="Path to the output directory.")
-    parser.add_argument("--retrain_model", type=bool, default=False, help="If true then retrain a pre-trained mode.")
-    parser.add_argument("--retrain_model_path", type=str, default=False, help="Path to the model that will be retrained.")
-    parser.add_argument("--gpu_mode", default=False, action='store_true', help="If set then PyTorch will use GPUs. CUDA required.")
-    parser.add_argument("-d_ids", "--device_ids", type=str, required=False, default=None,
-                        help="List of gpu device ids to use. helen_b200 trains on the first one.")
-    parser.add_argument("--num_workers", type=int, required=False, default=16, help="Number of data loader workers.")
+# flag tables: (names, keyword arguments); defaults and types are the reference's (helen_train.py:10-137)
+_GPU_FLAG = (("--gpu_mode",), dict(default=False, action='store_true', help="Run on the GPU (required: helen_b200 has no CPU path)."))
+TRAIN_FLAGS = [
+    (("--train_image_dir",), dict(type=str, required=True, help="Directory of labelled MarginPolish images to train on.")),
+    (("--test_image_dir",), dict(type=str, required=True, help="Directory of labelled images evaluated after every epoch.")),
+    (("--batch_size",), dict(type=int, default=100, help="Images per batch, default 100.")),
+    (("--epoch_size",), dict(type=int, default=10, help="Number of epochs, default 10.")),
+    (("--output_dir",), dict(type=str, default='./model', help="Where trained_models_<stamp>/ is created.")),
+    (("--retrain_model",), dict(type=bool, default=False, help="Continue from --retrain_model_path.")),
+    (("--retrain_model_path",), dict(type=str, default=False, help="Checkpoint to continue from.")),
+    _GPU_FLAG,
+    (("-d_ids", "--device_ids"), dict(type=str, default=None, help="Comma-separated device ids; training uses the first one.")),
+    (("--num_workers",), dict(type=int, default=16, help="Data loader workers, default 16.")),
+]
+TEST_FLAGS = [
+    (("--test_image_dir",), dict(type=str, required=True, help="Directory of labelled MarginPolish images.")),
+    (("--batch_size",), dict(type=int, default=100, help="Images per batch, default 100.")),
+    (("--model_path",), dict(type=str, default='./model', help="Checkpoint to evaluate.")),
+    _GPU_FLAG,
+    (("--print_details",), dict(default=False, action='store_true', help="Accepted for compatibility; only warns.")),
+    (("--output_dir",), dict(type=str, default='./debug_output', help="Where the confusion matrices are written.")),
+    (("--num_workers",), dict(type=int, default=40, help="Data loader workers, default 40.")),
+]
+
+
+def _add_flags(parser, table):
+    for names, options in table:
+        parser.add_argument(*names, **options)
     return parser
+
+
+def add_train_arguments(parser):
+    return _add_flags(parser, TRAIN_FLAGS)
 
 
 def add_test_arguments(parser):
-    """helen_train.py:87-137"""
-    parser.add_argument("--test_image_dir", type=str, required=True, help="Training data directory containing HDF files.")
-    parser.add_argument("--batch_size", type=int, required=False, default=100, help="Batch size for training, default is 100.")
-    parser.add_argument("--model_path", type=str, required=False, default='./model', help="Path of the model to load and test.")
-    parser.add_argument("--gpu_mode", default=False, action='store_true', help="If set then PyTorch will use GPUs. CUDA required.")
-    parser.add_argument("--print_details", default=False, action='store_true', help="Not mirrored: prints a warning.")
-    parser.add_argument("--output_dir", type=str, required=False, default='./debug_output', help="Output directory.")
-    parser.add_argument("--num_workers", type=int, required=False, default=40, help="Number of data loader workers.")
-    return parser
+    return _add_flags(parser, TEST_FLAGS)
 
 
 def build_parser():
