@@ -171,7 +171,7 @@ class Stitch:
 
     def create_consensus_sequence(self, contig, sequence_chunk_keys, threads):
         """All regions of a contig -> its consensus sequence (Stitch.py:256-301): groups of consecutive regions
-        are stitched in worker processes, the group results are stitched once more."""
+        are stitched by worker threads, the group results are stitched once more."""
         sequence_chunk_key_list = [(contig, hdf5_file, chunk_key, int(st), int(end))
                                    for hdf5_file, chunk_key, st, end in sequence_chunk_keys]
         sequence_chunk_key_list = sorted(sequence_chunk_key_list, key=lambda element: (element[3], element[4]))
@@ -184,8 +184,10 @@ class Stitch:
             for file_chunk in file_chunks:
                 sequence_chunks.append(self.small_chunk_stitch(contig, file_chunk))
         else:
-            with concurrent.futures.ProcessPoolExecutor(max_workers=threads) as executor:
-                futures = [executor.submit(self.small_chunk_stitch, contig, file_chunk) for file_chunk in file_chunks]
+            # threads, not the reference's processes: the library calls run without the interpreter lock and
+            # nothing has to be pickled
+            with concurrent.futures.ThreadPoolExecutor(max_workers=threads) as executor:
+                futures = [executor.submit(Stitch().small_chunk_stitch, contig, file_chunk) for file_chunk in file_chunks]
                 for fut in concurrent.futures.as_completed(futures):
                     if fut.exception() is None:
                         sequence_chunks.append(fut.result())

@@ -31,11 +31,12 @@
 
 #include <algorithm>
 #if defined(__SSE2__)
-#include <emmintrin.h>
+#include <immintrin.h>
 #endif
 #include <array>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -219,9 +220,106 @@ SweepEnd sweep_columns_sse2(const int8_t* ref, int ref_len, bool backwards, cons
 }
 #endif
 
+#if defined(__SSE2__) && defined(__GNUC__)
+#define HS_HAVE_AVX2_SWEEP 1
+// 16 read positions per instruction where the CPU has AVX2 (checked once at run time; the library itself is built
+// for baseline x86-64 because it is compiled on one machine and shipped to another).  Same arithmetic as above; the
+// byte shifts of AVX2 work inside each 128-bit half, so the prefix maximum is finished by folding the last element
+// of the low half into the high half.
+#define HS_LAST_OF_EACH_HALF(v) _mm256_shuffle_epi32(_mm256_shufflehi_epi16((v), 0xFF), 0xFF)
+__attribute__((target("avx2")))
+SweepEnd sweep_columns_avx2(const int8_t* ref, int ref_len, bool backwards, const int8_t* read, int read_len,
+                            const Scoring& sc, int stop_at) {
+    const int vectors = (read_len + 15) / 16, rows = vectors * 16;
+    std::array<std::vector<int16_t>, 5> profile;
+    for (int c = 0; c < 5; ++c) {
+        profile[c].assign(rows, 0);
+        for (int p = 0; p < read_len; ++p) profile[c][p] = static_cast<int16_t>(sc.pair(static_cast<int8_t>(c), read[p]));
+    }
+    std::vector<int16_t> h_a(rows + 16, 0), h_b(rows + 16, 0), e_store(rows, 0);
+    alignas(32) int16_t lanes[16], tail[16];
+    for (int k = 0; k < 16; ++k) {
+        lanes[k] = static_cast<int16_t>(k * sc.gap_extend);
+        tail[k] = (rows - 16 + k) < read_len ? int16_t(-1) : int16_t(0);
+    }
+    const __m256i go = _mm256_set1_epi16(static_cast<int16_t>(sc.gap_open)), ge = _mm256_set1_epi16(static_cast<int16_t>(sc.gap_extend));
+    const __m256i step = _mm256_set1_epi16(static_cast<int16_t>(16 * sc.gap_extend));
+    const __m256i lane_ge = _mm256_load_si256(reinterpret_cast<const __m256i*>(lanes));
+    const __m256i tail_mask = _mm256_load_si256(reinterpret_cast<const __m256i*>(tail));
+    const __m256i zero = _mm256_setzero_si256();
+    int16_t* prev = h_a.data();
+    int16_t* cur = h_b.data();
+    int16_t* e = e_store.data();
+    SweepEnd out;
+    for (int n = 0; n < ref_len; ++n) {
+        const int i = backwards ? ref_len - 1 - n : n;
+        const int16_t* prof = profile[ref[i]].data();
+        __m256i k_ge = lane_ge;
+        __m256i offset = _mm256_add_epi16(lane_ge, _mm256_sub_epi16(go, ge));
+        __m256i carry = zero, column = zero;
+        for (int v = 0; v < vectors; ++v) {
+            const int p = v * 16;
+            const __m256i h_left = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(prev + p + 1));
+            const __m256i h_diag = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(prev + p));
+            __m256i e_now = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(e + p));
+            e_now = _mm256_max_epi16(_mm256_subs_epi16(e_now, ge), _mm256_subs_epi16(h_left, go));
+            _mm256_storeu_si256(reinterpret_cast<__m256i*>(e + p), e_now);
+            __m256i t = _mm256_adds_epi16(h_diag, _mm256_loadu_si256(reinterpret_cast<const __m256i*>(prof + p)));
+            t = _mm256_max_epi16(_mm256_max_epi16(t, e_now), zero);
+            __m256i g = _mm256_adds_epi16(t, k_ge);
+            g = _mm256_max_epi16(g, _mm256_slli_si256(g, 2));
+            g = _mm256_max_epi16(g, _mm256_slli_si256(g, 4));
+            g = _mm256_max_epi16(g, _mm256_slli_si256(g, 8));                     // prefix maximum inside each half
+            const __m256i ends = HS_LAST_OF_EACH_HALF(g);
+            g = _mm256_max_epi16(g, _mm256_permute2x128_si256(ends, ends, 0x08));  // low half's last element into the high half
+            const __m256i low_up = _mm256_permute2x128_si256(g, g, 0x08);          // [0 | low half]
+            const __m256i before = _mm256_max_epi16(_mm256_alignr_epi8(g, low_up, 14), carry);   // one row up, with the rows above
+            const __m256i f = _mm256_subs_epi16(before, offset);
+            __m256i h = _mm256_max_epi16(t, f);
+            if (v == vectors - 1) h = _mm256_and_si256(h, tail_mask);
+            _mm256_storeu_si256(reinterpret_cast<__m256i*>(cur + p + 1), h);
+            column = _mm256_max_epi16(column, h);
+            const __m256i all = HS_LAST_OF_EACH_HALF(_mm256_max_epi16(g, carry));
+            carry = _mm256_permute2x128_si256(all, all, 0x11);                     // last row to every lane
+            k_ge = _mm256_add_epi16(k_ge, step);
+            offset = _mm256_add_epi16(offset, step);
+        }
+        __m128i m = _mm_max_epi16(_mm256_castsi256_si128(column), _mm256_extracti128_si256(column, 1));
+        m = _mm_max_epi16(m, _mm_srli_si128(m, 8));
+        m = _mm_max_epi16(m, _mm_srli_si128(m, 4));
+        m = _mm_max_epi16(m, _mm_srli_si128(m, 2));
+        const int column_best = static_cast<int16_t>(_mm_extract_epi16(m, 0));
+        if (column_best > out.best) {
+            out.best = column_best;
+            out.ref = i;
+            const __m256i wanted = _mm256_set1_epi16(static_cast<int16_t>(column_best));
+            for (int v = 0; v < vectors; ++v) {
+                const unsigned hit = static_cast<unsigned>(_mm256_movemask_epi8(
+                    _mm256_cmpeq_epi16(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(cur + v * 16 + 1)), wanted)));
+                if (hit) {
+                    out.read = v * 16 + __builtin_ctz(hit) / 2;
+                    break;
+                }
+            }
+        }
+        if (column_best == stop_at) break;
+        std::swap(prev, cur);
+    }
+    return out;
+}
+
+bool cpu_has_avx2() {
+    static const bool yes = __builtin_cpu_supports("avx2") && !std::getenv("HS_NO_AVX2");
+    return yes;
+}
+#endif
+
 SweepEnd sweep(const int8_t* ref, int ref_len, bool backwards, const int8_t* read, int read_len, const Scoring& sc, int stop_at) {
     const int64_t bound = static_cast<int64_t>(std::min(ref_len, read_len)) * sc.match + sc.match + sc.gap_open + sc.mismatch
                           + static_cast<int64_t>(read_len + 8) * sc.gap_extend;
+#if defined(HS_HAVE_AVX2_SWEEP)
+    if (bound < 32000 && read_len > 24 && cpu_has_avx2()) return sweep_columns_avx2(ref, ref_len, backwards, read, read_len, sc, stop_at);
+#endif
 #if defined(__SSE2__)
     if (bound < 32000) return sweep_columns_sse2(ref, ref_len, backwards, read, read_len, sc, stop_at);
 #else

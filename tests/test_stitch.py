@@ -149,6 +149,42 @@ def test_differential_against_compiled_reference(lib):
     assert checked > 10000
 
 
+def test_every_sweep_variant_agrees_with_the_reference(lib):
+    """The column sweep has three code paths: AVX2 (16 rows per instruction, when the CPU has it), SSE2 (8 rows;
+    forced by HS_NO_AVX2=1, read once per process, hence the subprocess) and plain 32-bit cells for inputs whose
+    scores could leave 16 bits.  Each against the compiled reference."""
+    import subprocess
+    import sys
+    from oracle import ssw_ref
+    if ssw_ref.load() is None:
+        pytest.skip("oracle/_ref/libssw_ref.so not built and /root/reference not present")
+    script = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "import ctypes, stitch_inputs\n"
+        "from helen_b200 import _stitch_native as native\n"
+        "from oracle import ssw_ref\n"
+        "lib = native.load(); sc = native.hs_scoring(4, 6, 8, 2); n = 0\n"
+        "for ref, query in stitch_inputs.aligner_pairs(seed=77, count=1500):\n"
+        "    out = native.hs_alignment(); cigar = ctypes.create_string_buffer(16 * (len(ref) + len(query)) + 64)\n"
+        "    native.check(lib.hs_ssw_align(ref.encode(), len(ref), query.encode(), len(query), ctypes.byref(sc), ctypes.byref(out), cigar, len(cigar)))\n"
+        "    want = ssw_ref.align(ref, query)\n"
+        "    if want['score'] == 0:\n"
+        "        assert out.score == 0; continue\n"
+        "    got = dict(score=out.score, ref_begin=out.ref_begin, ref_end=out.ref_end, query_begin=out.query_begin, query_end=out.query_end, mismatches=out.mismatches, cigar=cigar.value.decode())\n"
+        "    assert got == want, (ref, query); n += 1\n"
+        "print('checked', n)\n") % (ROOT, os.path.join(ROOT, "tests"))
+    for env_extra in ({"HS_NO_AVX2": "1"}, {}):
+        proc = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env={**os.environ, **env_extra})
+        assert proc.returncode == 0 and "checked" in proc.stdout, proc.stdout + proc.stderr
+    # 32-bit cells: 7,400 matching bases (score 29,000+, still inside the reference's 16-bit kernel)
+    rng = random.Random(3)
+    ref = stitch_inputs.random_sequence(rng, 7600)
+    query = stitch_inputs.with_errors(rng, ref[100:7500], 0.002)
+    assert my_align(lib, ref, query) == ssw_ref.align(ref, query)
+    with pytest.raises(RuntimeError):                   # 36,000 > 32,767: beyond the reference's kernel, refused
+        my_align(lib, "ACGT" * 2250, "ACGT" * 2250)
+
+
 def test_alignment_properties_at_length(lib):
     """Size-independent properties on inputs longer than any fixture (2,000-base overlaps): the cigar consumes
     exactly the aligned spans, its score re-derived from the cigar equals the reported score, an exact copy aligns
