@@ -185,6 +185,25 @@ def test_every_sweep_variant_agrees_with_the_reference(lib):
         my_align(lib, "ACGT" * 2250, "ACGT" * 2250)
 
 
+def test_property_based_against_compiled_reference(lib):
+    """hypothesis-generated pairs (short, repetitive, N-rich: where ties between equally scoring alignments are
+    most frequent) and scorings with gap_open > gap_extend."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import ssw_ref
+    if ssw_ref.load() is None:
+        pytest.skip("oracle/_ref/libssw_ref.so not built and /root/reference not present")
+    sequence = st.text(alphabet="ACGTN", min_size=1, max_size=90)
+    tandem = st.builds(lambda unit, n, tail: unit * n + tail, st.text(alphabet="ACGT", min_size=1, max_size=4),
+                       st.integers(1, 30), st.text(alphabet="ACGT", max_size=6))
+    scoring = st.tuples(st.integers(1, 6), st.integers(0, 9), st.integers(2, 12), st.integers(0, 4)).filter(lambda s: s[2] > s[3])
+
+    @settings(max_examples=600, deadline=None, derandomize=True)
+    @given(st.one_of(sequence, tandem), st.one_of(sequence, tandem), scoring)
+    def check(ref, query, sc):
+        assert my_align(lib, ref, query, sc) == ssw_ref.align(ref, query, *sc), (ref, query, sc)
+    check()
+
+
 def test_alignment_properties_at_length(lib):
     """Size-independent properties on inputs longer than any fixture (2,000-base overlaps): the cigar consumes
     exactly the aligned spans, its score re-derived from the cigar equals the reported score, an exact copy aligns
