@@ -510,6 +510,21 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             float* stg = reinterpret_cast<float*>(staging + sb * PROJ_STG_BYTES) + r;
             const float sc = j.pixel ? sc_px : sc_dec;
             const float add = j.pixel ? bi_px : (j.src_dir ? 0.f : bi_dec);   // the bias rides on the forward-source half (or the only one)
+#ifdef HB_PROJ_WIDE_EPILOGUE
+            // Variant for A/B runs, not measured yet (tools/build_variants.py wide=-DHB_PROJ_WIDE_EPILOGUE): 32 accumulator
+            // columns per TMEM round trip, two waits per job instead of eight.  The timeline shows this role busy for ~65 of
+            // the encoder's 68 us per chunk with ~0.4 us of MMA time per 0.9 us job, i.e. bound by this loop's serialised
+            // load -> wait -> store round trips; what is left over when the encoder ends is what the decoder waits for.
+#pragma unroll 1
+            for (int c32 = 0; c32 < PROJ_NT; c32 += 32) {
+                float v[32];
+                tc::tmem_ld16(taddr + c32, v);
+                tc::tmem_ld16(taddr + c32 + 16, v + 16);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) stg[(c32 + i) * 128] = fmaf(v[i], sc, add);
+            }
+#else
 #pragma unroll 2
             for (int c8 = 0; c8 < PROJ_NT; c8 += 8) {       // 8 accumulator columns = the 8 windows of column t0 + c8/8
                 float v[8];
@@ -518,6 +533,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 #pragma unroll
                 for (int i = 0; i < 8; ++i) stg[(c8 + i) * 128] = fmaf(v[i], sc, add);
             }
+#endif
             tc::tc_fence_before();
             tc::fence_proxy_async_smem();
             __syncwarp();
