@@ -112,7 +112,11 @@ pileup_to_operand_image_kernel(const uint8_t* __restrict__ images, int64_t B, in
 // The epilogue folds the bias sums and the -log2(e) factors of the gate nonlinearities into gi'
 // (see tc_recurrence_kernel), so gi' is NOT the plain pre-activation of the fp32 engine.
 // ---------------------------------------------------------------------------------------------
+#ifdef HB_PROJ_TWO_STORE_WARPS
+constexpr int PROJ_THREADS = 256;                // variant: warps 6 and 7 both store, one staging buffer each
+#else
 constexpr int PROJ_THREADS = 224;                // warps 0-3 epilogue, 4 MMA issuer, 5 tile loader, 6 gi' store
+#endif
 constexpr int PROJ_NT = 64;
 constexpr int PROJ_STG_BYTES = PROJ_NT * 128 * 4;   // fp32 staging of one tile's output block: [64 (column, window)][128 gate rows]
 constexpr int PROJ_STAGES = 2;                    // full-K tiles; the K-half jobs of the chunk-loop kernel are half as large: 4 stages
@@ -377,7 +381,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         }
         }
         HB_ROLE_REPORT(0);
+#ifdef HB_PROJ_TWO_STORE_WARPS
+    } else if (warp >= 6) {
+#else
     } else if (warp == 6) {
+#endif
         // ===================== gi' store =====================
         // lane c < 8 copies column t0 + c of the staged block: [8 windows][128 gate rows] = 4 KB, contiguous in the gi image
         const int tiles_t = (W + 7) >> 3;
@@ -410,6 +418,35 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int sb = it & 1;
             const uint32_t par = (uint32_t)((it >> 1) & 1);
+#ifdef HB_PROJ_TWO_STORE_WARPS
+            // Variant for A/B runs, not measured yet (tools/build_variants.py store2=-DHB_PROJ_TWO_STORE_WARPS).  The timeline's
+            // wait accounting leaves this warp ~1150 cycles per job outside its waits (eight bulk stores issued one lane after
+            // the other) plus ~490 for the flag batches: the slowest stage of the role.  Here warp 6 takes the even jobs
+            // (staging buffer 0) and warp 7 the odd ones (buffer 1); each keeps its own list of flags to raise.
+            if (sb != warp - 6) continue;
+            HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
+            {
+                const int e_ring2 = split ? job_ring[it & 15] : 0;
+                j = split ? proj_decode(a, e_ring2) : proj_tile_job(a, worker, n_workers, idx);
+                float* out2 = j.pixel ? a.px.gi : (j.src_dir ? a.gi_b : gi);
+                const int out_cols2 = j.pixel ? a.px.cols : W;
+                if (lane < 8 && j.t0 + lane < out_cols2)
+                    tc::bulk_s2g(out2 + gi_block(j.wg, out_cols2, j.t0 + lane, blk), staging + sb * PROJ_STG_BYTES + lane * (GI_BLK_FLOATS * 4), GI_BLK_FLOATS * 4);
+                tc::bulk_commit();
+                HB_TIMED(1, tc::bulk_wait_read_pending<0>());        // this job's copies have read MY staging buffer
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(stg_empty + sb);
+                if (a.tile_flags != nullptr) {
+                    pending[n_pending++] = j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
+                                                   : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
+                    if (idx + 2 >= n_jobs) HB_TIMED(2, publish(0));                  // this warp's last job of the chunk
+                    else if ((e_ring2 >> 30) & 1) { if (n_pending >= 2) HB_TIMED(3, publish(1)); }
+                    else if (n_pending >= PROJ_PUBLISH_BATCH / 2) HB_TIMED(3, publish(1));
+                }
+                if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0 && idx == n_jobs - 1) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
+            }
+            continue;
+#endif
             HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
             const int e_ring = split ? job_ring[it & 15] : 0;
             j = split ? proj_decode(a, e_ring) : proj_tile_job(a, worker, n_workers, idx);
@@ -436,7 +473,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         }
         publish(0);
         if (lane < 32) tc::bulk_wait0();                     // the kernel's results are complete when the role returns
-        HB_ROLE_REPORT(3);
+        if (warp == 6) HB_ROLE_REPORT(3);
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of compile-time variants on the GPU box.  Build them first, here, where nvcc is:
-#     python tools/build_variants.py wide=-DHB_PROJ_WIDE_EPILOGUE
-# then:  gpurun --timeout 900 -- 'bash tools/gpu_ab_variant.sh wide'
+#     python tools/build_variants.py wide=-DHB_PROJ_WIDE_EPILOGUE store2=-DHB_PROJ_TWO_STORE_WARPS both=-DHB_PROJ_TWO_STORE_WARPS,-DHB_PROJ_WIDE_EPILOGUE
+# then:  gpurun --timeout 900 -- 'bash tools/gpu_ab_variant.sh wide store2 both'
 # For each variant: the parity tests through that library, then the B=256 bench line (and the product build last,
 # so both numbers come from the same box).
 mkdir -p gpurun_out
