@@ -21,6 +21,10 @@ from .dataloader_predict import SequenceDataset
 from .ModelHander import ModelHandler
 
 
+def _cuda_device(device_id):
+    return torch.device("cuda", device_id)
+
+
 def predict(test_file, output_filename, model_path, batch_size, num_workers, rank, device_id):
     prediction_data_file = DataStore(output_filename + "_" + str(rank) + ".hdf", mode='w')
     checkpoint = ModelHandler.load_checkpoint(model_path)
@@ -43,7 +47,7 @@ def predict(test_file, output_filename, model_path, batch_size, num_workers, ran
     test_loader = DataLoader(test_data, batch_size=batch_size, shuffle=False, num_workers=num_workers, pin_memory=True)
     total_batches = len(test_loader)
     windows_done, t_begin = 0, time.time()
-    device = torch.device("cuda", device_id)
+    device = _cuda_device(device_id)
 
     def write_out(item):
         # predict_gpu.py:176-179: one record per image; runs while the GPU works on the next batch

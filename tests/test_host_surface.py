@@ -199,3 +199,56 @@ def test_confusion_matrix_text(tmp_path):
     path = str(tmp_path / "cm.txt")
     write_confusion_matrix([[5, 1], [0, 7]], ["-", "A"], path)
     assert open(path).read().splitlines() == ["true\\pred\t-\tA", "-\t5\t1", "A\t0\t7"]
+
+
+def test_predict_driver_loop_with_stub_predictor(tmp_path, monkeypatch):
+    """The driver's batch loop (predict_gpu.py:94-179 in the reference: load, predict, write one record per image)
+    without a GPU: the CUDA predictor is replaced by a stub that labels every column with (image index % 5, 1).
+    Checks the order of records, the short-image padding, the overlapped writer and the prediction-file schema;
+    the real predictor runs through the same loop in tests/test_gpu_driver.py."""
+    import torch
+    import helen_b200.models.predict_gpu as drv
+
+    class StubPredictor:
+        image_features = 90
+
+        def __init__(self, state_dict, device=0):
+            self.calls = 0
+
+        def predict(self, images):
+            self.calls += 1
+            assert images.dtype == torch.uint8 and images.shape[1:] == (1000, 90)
+            tag = images[:, 0, 0].to(torch.uint8) % 5                      # first pixel carries the image index
+            return tag[:, None].expand(-1, 1000).contiguous(), torch.ones(images.shape[0], 1000, dtype=torch.uint8)
+
+        def close(self):
+            pass
+
+    class StubEvent:
+        def record(self, stream=None):
+            pass
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(drv, "WindowPredictor", StubPredictor)
+    monkeypatch.setattr(drv.torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(drv.torch.cuda, "Event", StubEvent)
+    monkeypatch.setattr(drv.torch.cuda, "current_stream", lambda d=None: None)
+    monkeypatch.setattr(drv, "_cuda_device", lambda device_id: torch.device("cpu"))
+    model_path = str(tmp_path / "m.pkl")
+    torch.save({"model_state_dict": {}, "model_optimizer": {}, "hidden_size": 128, "gru_layers": 1, "epochs": 1}, model_path)
+    for i in range(5):
+        length = 1000 if i != 2 else 300
+        image = np.full((length, 90), i, np.uint8)
+        pos = np.stack([np.arange(length) + 1000 * i, np.zeros(length, int), np.zeros(length, int)], 1)
+        fake_h5.add_image("drv.h5", f"img{i}", "chrD", 1000 * i, 1000 * i + length, i, image, pos)
+    prefix = str(tmp_path / "pred")
+    drv.predict_gpu([["drv.h5"]], prefix, model_path, batch_size=2, total_callers=1, devices=[0], num_workers=0)
+    out = fake_h5.open_file(prefix + "_0.hdf")
+    for i in range(5):
+        length = 1000 if i != 2 else 300
+        chunk = out[f"predictions/chrD/chrD-{1000 * i}-{1000 * i + length}/{i}"]
+        assert (chunk["bases"][()] == i % 5).all() and (chunk["rles"][()] == 1).all()
+        position = chunk["position"][()]
+        assert position.dtype == np.uint32 and position[0, 0] == 1000 * i and (position[length:] == 4294967295).all()
