@@ -282,3 +282,28 @@ def test_perform_stitch_writes_fasta(lib, in_memory_h5, tmp_path, monkeypatch):
     contig_b, regions_b = _write_records("/t/b.hdf", rec_b)
     want_a = Stitch().create_consensus_sequence("chrA", [(p, n, s, e) for _, p, n, s, e in regions_b], 1)
     assert lines[1] == want_a and len(lines[3]) > 1000
+
+
+def test_polish_genome_ends_in_a_fasta(lib, in_memory_h5, tmp_path, monkeypatch):
+    """polish_genome = call_consensus into predictions_<stamp>/, then stitch into <prefix>.fa
+    (PolishInterface.py:49-105).  The GPU step is replaced by a writer of synthetic predictions here."""
+    import helen_b200.PolishInterface as polish
+    import helen_b200.StitchInterface as iface
+    from helen_b200.Stitch import Stitch
+    records = stitch_inputs.prediction_records(seed=41, regions=4, contig="chrP")
+    written = {}
+
+    def fake_call_consensus(image_dir, model_path, batch_size, num_workers, threads, output_dir, output_prefix, gpu_mode,
+                            device_ids, callers):
+        path = os.path.join(output_dir, output_prefix + "_0.hdf")
+        written["contig"], written["regions"] = _write_records(path, records)
+        written["path"] = path
+
+    monkeypatch.setattr(polish, "call_consensus", fake_call_consensus)
+    monkeypatch.setattr(iface, "get_file_paths_from_directory", lambda directory: [written["path"]])
+    out_dir = str(tmp_path / "polish_out")
+    prediction_dir = polish.polish_genome("imgs", "m.pkl", 8, 0, 2, out_dir, "HELEN_prediction", True, None, 1)
+    assert os.path.basename(prediction_dir).startswith("predictions_") and os.path.dirname(prediction_dir) == out_dir
+    lines = open(os.path.join(out_dir, "HELEN_prediction.fa")).read().splitlines()
+    keys = [(p, n, s, e) for _, p, n, s, e in written["regions"]]
+    assert lines == [">chrP", Stitch().create_consensus_sequence("chrP", keys, 1)] and len(lines[1]) > 2000
