@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY.  The reference's own Smith-Waterman (helen/modules/src/local_reassembly/ssw.c,
 ssw_cpp.cpp), compiled from /root/reference by build_ref.py into oracle/_ref/libssw_ref.so, behind a ctypes
 call.  It is the checker for helen_b200's stitch library (tests/test_stitch.py) and the CPU baseline of
-tools/bench_stitch.py; nothing under helen_b200/ may import it."""
+tests/bench_stitch.py; nothing under helen_b200/ may import it."""
 import ctypes
 
 from . import build_ref

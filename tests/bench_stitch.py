@@ -2,7 +2,7 @@
 alignment_stitch runs, next to the reference's own Smith-Waterman compiled into oracle/_ref (and, where
 /root/reference is present, the reference's Python Stitch class over its pybind module).  Single core.
 
-    python tools/bench_stitch.py [--json profiles/r01_stitch_bench.json]
+    python tests/bench_stitch.py [--json profiles/r01_stitch_bench.json]
 """
 import argparse
 import ctypes
@@ -14,7 +14,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))        # lives under tests/ because it executes oracle/ (the reference, as baseline)
 
 import stitch_inputs  # noqa: E402
 from helen_b200 import _stitch_native as native  # noqa: E402

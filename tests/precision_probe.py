@@ -5,7 +5,7 @@ move, when the GRU contractions run on split-precision tensor-core operands.
 Emulates on CPU (numpy fp64 accumulate of rounded operands) the candidate operand formats
 for the tcgen05 path; evidence for DESIGN.md's choice.  Not part of the product.
 
-    python tools/precision_probe.py [F] [B]
+    python tests/precision_probe.py [F] [B]
 """
 import sys
 import os
