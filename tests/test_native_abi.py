@@ -88,3 +88,18 @@ def test_pkl_round_trip_with_and_without_module_prefix(tmp_path):
     assert epochs == 3
     for k, v in model.state_dict().items():
         assert torch.equal(v, loaded.state_dict()[k])
+
+
+def test_only_the_checkers_touch_the_oracle():
+    """oracle/ is test infrastructure: the package, tools/ and every other script must not import it.  Allowed:
+    tests/, __graft_entry__.py (smoke() and build() of the checker) and bench.py (cpu_baseline / --impl reference)."""
+    allowed_files = {os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")}
+    pattern = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = []
+    for base, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in (".git", "gpurun_out", "__pycache__", "tests", "oracle", "baseline", ".pytest_cache")]
+        for name in files:
+            path = os.path.join(base, name)
+            if name.endswith(".py") and path not in allowed_files and pattern.search(open(path).read()):
+                offenders.append(os.path.relpath(path, ROOT))
+    assert offenders == []
