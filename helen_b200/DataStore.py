@@ -4,7 +4,19 @@ predictions/<contig>/<contig>-<start>-<end>/contig_start, contig_end            
 predictions/<contig>/<contig>-<start>-<end>/<chunk_id>/position  uint32 [1000, 3]
                                                       /bases     uint8  [1000]
                                                       /rles      uint8  [1000]
+
+Packed mode (opt-in: ``DataStore(..., packed=True)`` or HELEN_B200_PACKED_PREDICTIONS=1): the schema above costs three
+HDF5 datasets per image, which a writer cannot create at the rate the GPU predicts them.  A packed file holds ONE group
+per written batch instead,
+
+predictions_packed/<n>/contig S[B], contig_start i64[B], contig_end i64[B], chunk_id i64[B],
+                       position uint32 [B, 1000, 3], bases uint8 [B, 1000], rles uint8 [B, 1000]
+
+and is read back through ``PackedPredictions``, a view with the nested shape of the reference schema, so the stitch
+code is the same for both.  Packed files are for helen_b200's own ``stitch``; the reference's cannot read them.
 """
+import os
+
 import numpy as np
 
 from . import hdf5
@@ -17,12 +29,16 @@ def _item(value):
 class DataStore(object):
     _prediction_path_ = 'predictions'
 
-    def __init__(self, filename, mode='r'):
+    _packed_path_ = 'predictions_packed'
+
+    def __init__(self, filename, mode='r', packed=None):
         self.filename = filename
         self.mode = mode
+        self.packed = (os.environ.get("HELEN_B200_PACKED_PREDICTIONS", "0") not in ("", "0")) if packed is None else bool(packed)
         self.file_handler = hdf5.open_file(self.filename, self.mode)
         self._written_regions = set()
         self._written_chunks = set()
+        self._packed_batches = 0
 
     def __enter__(self):
         return self
@@ -37,6 +53,10 @@ class DataStore(object):
 
     def write_prediction(self, contig, contig_start, contig_end, chunk_id, position,
                          predicted_bases, predicted_rles, filename=None):
+        if self.packed:                                     # a batch of one
+            return self.write_predictions([contig], [_item(contig_start)], [_item(contig_end)], [_item(chunk_id)],
+                                          np.asarray(position)[None], np.asarray(predicted_bases)[None],
+                                          np.asarray(predicted_rles)[None])
         contig_start, contig_end, chunk_id = _item(contig_start), _item(contig_end), _item(chunk_id)
         chunk_name_prefix = str(contig) + "-" + str(contig_start) + "-" + str(contig_end)
         chunk_name_suffix = str(chunk_id)
@@ -67,6 +87,87 @@ class DataStore(object):
         if not (len(contig) == len(contig_start) == len(contig_end) == len(chunk_id) == len(position)
                 == len(predicted_bases) == len(predicted_rles)):
             raise ValueError("write_predictions: all arguments must have one entry per record")
+        if self.packed:
+            group = '{}/{}'.format(self._packed_path_, self._packed_batches)
+            self._packed_batches += 1
+            self.file_handler[group + '/contig'] = np.array([str(c).encode() for c in contig], dtype='S')
+            self.file_handler[group + '/contig_start'] = np.asarray(contig_start, dtype=np.int64)
+            self.file_handler[group + '/contig_end'] = np.asarray(contig_end, dtype=np.int64)
+            self.file_handler[group + '/chunk_id'] = np.asarray(chunk_id, dtype=np.int64)
+            self.file_handler[group + '/position'] = position
+            self.file_handler[group + '/bases'] = predicted_bases
+            self.file_handler[group + '/rles'] = predicted_rles
+            return
         for i in range(len(contig)):
             self.write_prediction(contig[i], contig_start[i], contig_end[i], chunk_id[i], position[i],
                                   predicted_bases[i], predicted_rles[i])
+
+
+class _Value(object):
+    """A dataset of the view: value[()] like an h5py dataset."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __getitem__(self, key):
+        return self.value if key == () else self.value[key]
+
+
+class PackedPredictions(object):
+    """Read view of a packed prediction file: view['predictions'][contig][region][chunk]['bases'][()] and the
+    region's 'contig_start' / 'contig_end', as in the reference schema.  The first record of a (region, chunk) pair
+    wins, like DataStore.write_prediction's duplicate rule."""
+
+    def __init__(self, h5file):
+        contigs = {}
+        packed = h5file[DataStore._packed_path_]
+        for batch in sorted(packed.keys(), key=int):
+            group = packed[batch]
+            names = [c.decode() if isinstance(c, bytes) else str(c) for c in np.asarray(group['contig'][()]).reshape(-1)]
+            starts = np.asarray(group['contig_start'][()]).reshape(-1).tolist()
+            ends = np.asarray(group['contig_end'][()]).reshape(-1).tolist()
+            chunk_ids = np.asarray(group['chunk_id'][()]).reshape(-1).tolist()
+            position, bases, rles = group['position'][()], group['bases'][()], group['rles'][()]
+            for i, name in enumerate(names):
+                region = contigs.setdefault(name, {}).setdefault(
+                    "{}-{}-{}".format(name, starts[i], ends[i]),
+                    {'contig_start': _Value(starts[i]), 'contig_end': _Value(ends[i])})
+                region.setdefault(str(chunk_ids[i]), {'position': _Value(position[i]), 'bases': _Value(bases[i]),
+                                                      'rles': _Value(rles[i])})
+        self._root = {DataStore._prediction_path_: contigs}
+
+    def __contains__(self, key):
+        return key in self._root
+
+    def __getitem__(self, key):
+        return self._root[key]
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *args):
+        return False
+
+    def close(self):
+        pass
+
+
+_packed_views = {}
+
+
+def open_predictions(path):
+    """A prediction file for reading, either schema.  Views of packed files are built once per process and path (the
+    stitch opens a file once per region)."""
+    if path in _packed_views:
+        return _packed_views[path]
+    handle = hdf5.open_file(path, 'r')
+    if DataStore._prediction_path_ in handle or DataStore._packed_path_ not in handle:
+        return handle
+    view = PackedPredictions(handle)
+    handle.close()
+    _packed_views[path] = view
+    return view
+
+
+def forget_packed_views():
+    _packed_views.clear()

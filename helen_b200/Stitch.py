@@ -11,7 +11,7 @@ import sys
 import numpy as np
 
 from . import _stitch_native as native
-from . import hdf5
+from .DataStore import open_predictions
 from .FileManager import FileManager
 from .options import StitchOptions
 from .TextColor import TextColor
@@ -155,7 +155,7 @@ class Stitch:
         name_sequence_tuples = list()
         for contig_name, file_name, chunk_name, contig_start, contig_end in small_chunk_keys:
             positions, bases, rles = [], [], []
-            with hdf5.open_file(file_name, 'r') as hdf5_file:            # one open per region instead of one per image
+            with open_predictions(file_name) as hdf5_file:            # one open per region instead of one per image
                 if 'predictions' in hdf5_file:
                     region = hdf5_file['predictions'][contig][chunk_name]
                     for chunk in sorted(set(region.keys()) - {'contig_start', 'contig_end'}):

@@ -5,7 +5,7 @@ import sys
 from os import listdir
 from os.path import isfile, join
 
-from . import hdf5
+from .DataStore import open_predictions
 from .FileManager import FileManager
 from .Stitch import Stitch
 from .TextColor import TextColor
@@ -23,7 +23,7 @@ def perform_stitch(input_directory, output_path, output_prefix, threads):
     # one pass over the files: contig -> [(file, region key, start, end)] (the reference reopens every file per contig)
     regions_of = dict()
     for prediction_file in sorted(all_prediction_files):
-        with hdf5.open_file(prediction_file, 'r') as hdf5_file:
+        with open_predictions(prediction_file) as hdf5_file:
             if 'predictions' not in hdf5_file:
                 raise ValueError(TextColor.RED + "ERROR: INVALID HDF5 FILE, FILE DOES NOT CONTAIN predictions KEY.\n"
                                  + TextColor.END)

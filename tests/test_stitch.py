@@ -36,9 +36,12 @@ def golden():
 def in_memory_h5(monkeypatch):
     import helen_b200.hdf5 as hb_hdf5
     fake_h5.reset()
+    from helen_b200.DataStore import forget_packed_views
+    forget_packed_views()
     monkeypatch.setattr(hb_hdf5, "open_file", fake_h5.open_file)
     yield
     fake_h5.reset()
+    forget_packed_views()
 
 
 def my_align(lib, ref, query, scoring=(4, 6, 8, 2)):
@@ -307,3 +310,40 @@ def test_polish_genome_ends_in_a_fasta(lib, in_memory_h5, tmp_path, monkeypatch)
     lines = open(os.path.join(out_dir, "HELEN_prediction.fa")).read().splitlines()
     keys = [(p, n, s, e) for _, p, n, s, e in written["regions"]]
     assert lines == [">chrP", Stitch().create_consensus_sequence("chrP", keys, 1)] and len(lines[1]) > 2000
+
+
+def test_packed_prediction_files_stitch_identically(lib, in_memory_h5, tmp_path, monkeypatch):
+    """The packed schema (one HDF5 group per written batch instead of three datasets per image) read back through
+    PackedPredictions gives the same FASTA as the reference schema, duplicates included."""
+    import helen_b200.StitchInterface as iface
+    from helen_b200.DataStore import DataStore, PackedPredictions, open_predictions
+    records = stitch_inputs.prediction_records(seed=51, regions=5, contig="chrQ") + \
+        stitch_inputs.prediction_records(seed=52, regions=3, contig="chrR")
+    records.append(records[3])                                      # a repeated (region, chunk): the first one wins
+    plain, packed = str(tmp_path / "plain_0.hdf"), str(tmp_path / "packed_0.hdf")
+    _write_records(plain, records)
+    store = DataStore(packed, mode='w', packed=True)
+    for lo in range(0, len(records), 4):
+        batch = records[lo:lo + 4]
+        store.write_predictions([r[0] for r in batch], [r[1] for r in batch], [r[2] for r in batch], [r[3] for r in batch],
+                                np.stack([r[4] for r in batch]), np.stack([r[5] for r in batch]), np.stack([r[6] for r in batch]))
+    store.write_prediction(*records[0][:7])                        # single records go into a batch of one
+    store.close()
+    raw = fake_h5.open_file(packed)
+    assert 'predictions' not in raw and len(raw['predictions_packed'].keys()) == (len(records) + 3) // 4 + 1
+    view = open_predictions(packed)
+    assert isinstance(view, PackedPredictions) and open_predictions(packed) is view
+    assert sorted(view['predictions'].keys()) == ["chrQ", "chrR"]
+    fasta = {}
+    for name, path in (("plain", plain), ("packed", packed)):
+        monkeypatch.setattr(iface, "get_file_paths_from_directory", lambda directory, path=path: [path])
+        fasta[name] = open(iface.perform_stitch(str(tmp_path), str(tmp_path / ("out_" + name)), "p", 2)).read()
+    assert fasta["packed"] == fasta["plain"] and fasta["plain"].count(">") == 2
+
+
+def test_packed_mode_follows_the_environment(in_memory_h5, monkeypatch):
+    from helen_b200.DataStore import DataStore
+    monkeypatch.delenv("HELEN_B200_PACKED_PREDICTIONS", raising=False)
+    assert DataStore("/t/a.hdf", "w").packed is False
+    monkeypatch.setenv("HELEN_B200_PACKED_PREDICTIONS", "1")
+    assert DataStore("/t/b.hdf", "w").packed is True and DataStore("/t/c.hdf", "w", packed=False).packed is False
