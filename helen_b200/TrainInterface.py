@@ -1,10 +1,10 @@
 """train_interface / test_interface with the reference's signatures
 (helen/modules/python/TrainInterface.py:127-147, TestInterface.py:90-138).
 
-Training runs on ONE GPU: the per-chunk step is the CUDA library's hb_train_step_chunk (models/train_step.py);
-the reference's multi-GPU mode (train_distributed.py, DistributedDataParallel) is not mirrored, so several
-device ids select the first one and say so.  test_interface writes the two confusion matrices as text instead
-of matplotlib images (matplotlib is not a dependency here)."""
+The per-chunk step is the CUDA library's hb_train_step_chunk (models/train_step.py).  One device id trains in this
+process (models/train.py); several run one process per GPU with the gradients averaged after every step
+(models/train_distributed.py, the reference's DistributedDataParallel mode).  test_interface writes the two confusion
+matrices as text instead of matplotlib images (matplotlib is not a dependency here)."""
 import os
 import sys
 
@@ -36,29 +36,35 @@ class TrainModule:
         self.learning_rate = 0.0001          # TrainInterface.py:37-38
         self.weight_decay = 0
 
-    def selected_device(self):
-        """First of --device_ids (all visible devices when absent), checked like TrainInterface.py:66-92."""
+    def selected_devices(self):
+        """--device_ids (all visible devices when absent), checked like TrainInterface.py:66-92."""
         if not torch.cuda.is_available():
             sys.stderr.write(TextColor.RED + "ERROR: TORCH IS NOT BUILT WITH CUDA.\n" + TextColor.END)
             exit(1)
         if self.device_ids is None:
             device_ids = list(range(torch.cuda.device_count()))
+            sys.stderr.write(TextColor.GREEN + "INFO: TOTAL GPU AVAILABLE: " + str(len(device_ids)) + "\n" + TextColor.END)
         else:
             device_ids = [int(i) for i in self.device_ids.split(',')]
         if len(device_ids) == 0:
             sys.stderr.write(TextColor.RED + "ERROR: NO GPU AVAILABLE BUT GPU MODE IS SET\n" + TextColor.END)
             exit()
-        if len(device_ids) > 1:
-            sys.stderr.write(TextColor.YELLOW + "WARN: helen_b200 TRAINS ON ONE GPU; USING DEVICE " + str(device_ids[0])
-                             + " OF " + str(device_ids) + ".\n" + TextColor.END)
-        return device_ids[0]
+        return device_ids
 
     def train_model_gpu(self):
-        from .models.train import train
-        torch.cuda.set_device(self.selected_device())
-        train(self.train_file, self.test_file, self.batch_size, self.epochs, self.gpu_mode, self.num_workers,
-              self.retrain_model, self.retrain_model_path, self.gru_layers, self.hidden_size, self.learning_rate,
-              self.weight_decay, self.model_dir, self.stats_dir, not_hyperband=True)
+        device_ids = self.selected_devices()
+        if len(device_ids) == 1:
+            from .models.train import train
+            torch.cuda.set_device(device_ids[0])
+            train(self.train_file, self.test_file, self.batch_size, self.epochs, self.gpu_mode, self.num_workers,
+                  self.retrain_model, self.retrain_model_path, self.gru_layers, self.hidden_size, self.learning_rate,
+                  self.weight_decay, self.model_dir, self.stats_dir, not_hyperband=True)
+        else:
+            from .models.train_distributed import train_distributed
+            train_distributed(self.train_file, self.test_file, self.batch_size, self.epochs, self.gpu_mode,
+                              self.num_workers, self.retrain_model, self.retrain_model_path, self.gru_layers,
+                              self.hidden_size, self.learning_rate, self.weight_decay, self.model_dir, self.stats_dir,
+                              device_ids, len(device_ids), train_mode=True)
 
     def train_model(self):
         sys.stderr.write(TextColor.RED + "ERROR: helen_b200 HAS NO CPU PATH, USE --gpu_mode.\n" + TextColor.END)

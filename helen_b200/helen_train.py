@@ -19,7 +19,7 @@ TRAIN_FLAGS = [
     (("--retrain_model",), dict(type=bool, default=False, help="Continue from --retrain_model_path.")),
     (("--retrain_model_path",), dict(type=str, default=False, help="Checkpoint to continue from.")),
     _GPU_FLAG,
-    (("-d_ids", "--device_ids"), dict(type=str, default=None, help="Comma-separated device ids; training uses the first one.")),
+    (("-d_ids", "--device_ids"), dict(type=str, default=None, help="Comma-separated device ids; one training process per device.")),
     (("--num_workers",), dict(type=int, default=16, help="Data loader workers, default 16.")),
 ]
 TEST_FLAGS = [
