@@ -159,6 +159,28 @@ def cpu_port_windows_per_s(features, sample_windows, min_seconds, threads, seq=T
     return done / dt, done, dt
 
 
+def parity_sample(features, images_u8, base_labels, rle_labels, indices, margin=1e-5):
+    """Checker leg (outside every timed region): the labels the GPU produced for `indices` of the timed batch against the
+    oracle's torch-CPU port of predict.py:90-154 on the same images.  Flips are split by the oracle's own top-1/top-2
+    margin (labels must agree wherever the margin is >= 1e-5; closer calls are counted, not gated)."""
+    import numpy as np
+    import torch
+    from oracle import TransducerPort, predict_port
+    from oracle.explicit import top2_margin
+    model = TransducerPort(features).eval()
+    model.load_state_dict(random_parameters(features, seed=0))
+    ref = predict_port(model, images_u8[indices])
+    out = {"windows": len(indices), "positions": int(2 * len(indices) * images_u8.shape[1]), "flips_above_margin": 0,
+           "flips_sub_margin": 0, "margin": margin, "oracle": f"torch {torch.__version__} CPU fp32 port (oracle/torch_port.py)"}
+    for got, ref_lab, ref_prob in ((base_labels, ref["base_label"], ref["base_prob"]), (rle_labels, ref["rle_label"], ref["rle_prob"])):
+        diff = np.asarray(got)[indices] != ref_lab
+        if diff.any():
+            m = top2_margin(ref_prob)[diff]
+            out["flips_sub_margin"] += int((m < margin).sum())
+            out["flips_above_margin"] += int((m >= margin).sum())
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU arm alone.  Rank 0 only; other ranks exit quietly."""
     if rank != 0:
@@ -169,10 +191,10 @@ def run_reference(args, rank, world):
     from oracle import TransducerPort, predict_port
     model = TransducerPort(args.features).eval()
     model.load_state_dict(random_parameters(args.features, seed=0))
-    sample = args.reference_sample
-    images = synthetic_images(sample, args.features, seed=1)
+    sample = args.reference_sample or args.batch              # same windows per step as the native arm
+    images = synthetic_images(sample, args.features, seed=1000)
     for _ in range(args.warmup):
-        predict_port(model, images[: max(1, sample // 4)])
+        predict_port(model, images[: max(1, sample // 8)])      # untimed: an eighth of a step each
     t0 = time.perf_counter()
     for _ in range(args.steps):
         predict_port(model, images)
@@ -182,14 +204,28 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "pileup windows/sec (B=256, T=1000)", "value": value, "unit": "windows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, sample_windows=sample),
+        "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "windows/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample} windows [T=1000, F={args.features}] per step, "
+                         "sample": f"{args.steps} steps x {sample} windows [T=1000, F={args.features}] per step "
+                                   f"(warm-up steps: {max(1, sample // 8)} windows), "
                                    f"torch {torch.__version__} CPU fp32 nn.GRU port of the reference predict loop"},
+        "probes": import_probes(),
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def import_probes():
+    """Which of the reference's optional host-side dependencies exist on this box."""
+    out = {}
+    for name in ("h5py", "onnxruntime", "onnx"):
+        try:
+            mod = __import__(name)
+            out[name] = getattr(mod, "__version__", "present")
+        except Exception:
+            out[name] = None
+    return out
 
 
 def workload_config(args, sample_windows=None):
@@ -294,6 +330,31 @@ def run_native(args, rank, world, local_rank):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * args.batch * args.steps / e2e_s
 
+    # sustained: back-to-back steps for >= --sustained-seconds (the K timed steps above last tens of milliseconds),
+    # L2 flushed before every step as above; one CUDA-event bracket around the whole run, clocks sampled during it
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds / max(sum(per_step) / len(per_step) * 1e-3, 1e-6)))
+        sus_sampler = ClockSampler(local_rank, period=0.05)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sus_sampler.start()
+        ev0.record()
+        for _ in range(n_sus):
+            flush.zero_()
+            pred.predict(images)
+        ev1.record()
+        barrier()
+        sus_ms = max_over_ranks(ev0.elapsed_time(ev1))
+        sustained = {"value": world * args.batch * n_sus / (sus_ms * 1e-3), "unit": "windows/s", "steps": n_sus,
+                     "seconds": sus_ms * 1e-3, "includes": "the 256 MiB L2 flush before every step",
+                     "clocks": sus_sampler.finish()}
+
+    # labels of the timed batch for the parity block (checked against the oracle below, outside every timed region)
+    chk_base, chk_rle = pred.predict(images)
+    torch.cuda.synchronize()
+    chk_base, chk_rle = chk_base.cpu().numpy(), chk_rle.cpu().numpy()
+
     sweep = None
     if args.sweep and world == 1:
         sweep = []
@@ -329,6 +390,12 @@ def run_native(args, rank, world, local_rank):
                     "us_per_dependent_step": 1e3 * dom_ms_launch / (chunks * 2 * WINDOW),
                     "traffic": kernel_traffic_bytes(engine, args.batch, args.features),
                     "note": "latency-bound at this batch: 3,800 dependent GRU steps per launch (DESIGN.md section 5)"}
+        # executed (not algorithmic) MMA work: the fp16 split runs the recurrence as 4 partial products when the
+        # [h_hi | h_lo] operand is stacked (3 otherwise), the decoder projection and the heads as 3
+        rec_terms = 4 if plan["stacked_operand"] else 3
+        mac_exec = rec_terms * 2 * (2 * WINDOW * 3 * HIDDEN * HIDDEN) + 3 * (2 * WINDOW * 3 * HIDDEN * 2 * HIDDEN) + 3 * (WINDOW * 2 * HIDDEN * 16)
+        roofline["executed_over_algorithmic"] = mac_exec / mac_chunk
+        roofline["frac_executed"] = roofline["frac"] * mac_exec / mac_chunk
     elif dom_launches:
         # one recurrence launch = batch windows x 100 dependent steps x 2 directions of one layer
         rec_flop = args.batch * WINDOW * 2 * (2 * 3 * HIDDEN * HIDDEN)
@@ -357,8 +424,14 @@ def run_native(args, rank, world, local_rank):
         "roofline": roofline,
         "roofline_path": path_roofline,
     }
+    if sustained:
+        line["sustained"] = sustained
     if sweep:
         line["batch_sweep"] = sweep
+    line["probes"] = import_probes()
+    if not args.no_parity:
+        idx = sorted(set(int(i) for i in __import__("numpy").linspace(0, args.batch - 1, min(args.parity_windows, args.batch)).astype(int)))
+        line["parity"] = parity_sample(args.features, host_images, chk_base, chk_rle, idx)
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, done, dt = cpu_port_windows_per_s(args.features, args.cpu_sample, args.cpu_seconds, threads)
@@ -373,8 +446,12 @@ def run_native(args, rank, world, local_rank):
 
 def run_polish(args, rank, world, local_rank):
     """--polish N: BASELINE configs[2], window-sharded polish of N synthetic windows (the 3 Gb contig set is ~3 M): every rank
-    generates its contiguous shard on the device in batches of --batch windows (seed 1000 + rank), predicts it, and the uint8
-    labels are gathered in window-index order on rank 0 and copied to host memory (the "stitch" of this mode).  Secondary line."""
+    generates its contiguous shard on the device in batches of --batch windows (seed 1000 + rank) and predicts it.  The
+    "stitch" of this mode is a HOST-side ordered gather with no collective: the stitched result lives in one shared host
+    array (POSIX shared memory, page-locked in every rank), and each rank copies the uint8 labels of every batch straight
+    from its GPU into its own window range of that array, asynchronously on a copy stream while the next batch runs
+    (two device label buffers in rotation).  Secondary line; the parity block checks a few windows per rank against the oracle."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     from helen_b200 import build as hb_build
@@ -392,65 +469,86 @@ def run_polish(args, rank, world, local_rank):
     pred = WindowPredictor(random_parameters(args.features, seed=0), device=local_rank, engine=args.engine)
     start, end = shard_bounds(args.polish, world, rank)
     n_local = end - start
+    # the stitched result: [2 heads, N windows, T] uint8 in shared host memory, created by rank 0
+    shm_path = f"/dev/shm/helen_b200_polish_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
+    total_bytes = 2 * args.polish * T_COLUMNS
+    if rank == 0:
+        with open(shm_path, "wb") as f:
+            f.truncate(total_bytes)
+    if world > 1:
+        dist.barrier()
+    host = torch.from_file(shm_path, shared=True, size=total_bytes, dtype=torch.uint8).view(2, args.polish, T_COLUMNS)
+    cudart = torch.cuda.cudart()
+    registered = int(cudart.cudaHostRegister(host.data_ptr(), total_bytes, 0)) == 0     # page-locked: async DMA straight into it
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    base_all = torch.empty((n_local, T_COLUMNS), dtype=torch.uint8, device=dev)
-    rle_all = torch.empty((n_local, T_COLUMNS), dtype=torch.uint8, device=dev)
     warm = torch.randint(0, 256, (min(args.batch, max(n_local, 1)), T_COLUMNS, args.features), dtype=torch.uint8, device=dev, generator=gen)
     for _ in range(3):
         pred.predict(warm)
-    host = torch.empty((2, args.polish, T_COLUMNS), dtype=torch.uint8).pin_memory() if rank == 0 else None   # stitched result
+    copy_stream = torch.cuda.Stream(device=dev)
+    done = [torch.cuda.Event(), torch.cuda.Event()]            # label buffer b may be overwritten once its copies have run
+    keep = min(args.parity_windows, max(n_local, 1))             # images of the first few windows, for the oracle check
+    kept_images = None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for off in range(0, n_local, args.batch):
+    main = torch.cuda.current_stream(dev)
+    bufs = [None, None]
+    for it, off in enumerate(range(0, n_local, args.batch)):
         n = min(args.batch, n_local - off)
         images = torch.randint(0, 256, (n, T_COLUMNS, args.features), dtype=torch.uint8, device=dev, generator=gen)
+        if it == 0:
+            kept_images = images[:keep].clone()
+        if it >= 2:
+            main.wait_event(done[it & 1])
         b, r = pred.predict(images)
-        base_all[off:off + n] = b
-        rle_all[off:off + n] = r
-    torch.cuda.synchronize()
+        bufs[it & 1] = (b, r)                                    # keep the buffers alive until their copies have run
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            host[0, start + off:start + off + n].copy_(b, non_blocking=True)
+            host[1, start + off:start + off + n].copy_(r, non_blocking=True)
+            done[it & 1].record(copy_stream)
+    main.synchronize()
     t_compute = time.perf_counter() - t0
-    # ordered gather on rank 0 (contiguous shards: concatenation in rank order is window-index order), then to host
+    copy_stream.synchronize()
     if world > 1:
-        sizes = [shard_bounds(args.polish, world, q)[1] - shard_bounds(args.polish, world, q)[0] for q in range(world)]
-        if rank == 0:
-            host[0, :n_local].copy_(base_all, non_blocking=True)
-            host[1, :n_local].copy_(rle_all, non_blocking=True)
-            off = n_local
-            recv = torch.empty((2, max(sizes), T_COLUMNS), dtype=torch.uint8, device=dev)
-            for q in range(1, world):
-                dist.recv(recv, src=q)
-                host[:, off:off + sizes[q]].copy_(recv[:, :sizes[q]], non_blocking=True)
-                torch.cuda.synchronize()
-                off += sizes[q]
-        else:
-            send = torch.zeros((2, max(sizes), T_COLUMNS), dtype=torch.uint8, device=dev)
-            send[0, :n_local] = base_all
-            send[1, :n_local] = rle_all
-            dist.send(send, dst=0)
-        torch.cuda.synchronize()
-        dist.barrier()
-    else:
-        host[0].copy_(base_all, non_blocking=True)
-        host[1].copy_(rle_all, non_blocking=True)
-        torch.cuda.synchronize()
+        dist.barrier()                                           # every rank's range of the shared array is complete
     t_total = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([t_compute, t_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_compute, t_total = t.tolist()
+    # checker leg (untimed): this rank's first windows against the oracle, read back from the stitched array
+    flips = torch.zeros(3, dtype=torch.int64, device=dev)
+    if not args.no_parity and n_local > 0:
+        chk = parity_sample(args.features, kept_images.cpu(), host[0, start:start + keep].numpy(), host[1, start:start + keep].numpy(),
+                            list(range(keep)))
+        flips = torch.tensor([chk["windows"], chk["flips_above_margin"], chk["flips_sub_margin"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(flips)
     if rank == 0:
         checksum = int(host[0, ::997].to(torch.int64).sum() + host[1, ::997].to(torch.int64).sum())
         print(json.dumps({
-            "metric": "window-sharded polish, end-to-end windows/sec (generate on device, predict, ordered gather of labels to host)",
+            "metric": "window-sharded polish, end-to-end windows/sec (generate on device, predict, labels streamed into one host array)",
             "value": args.polish / t_total, "unit": "windows/s", "n_gpus": world, "windows": args.polish, "batch_per_launch": args.batch,
             "seconds": t_total, "predict_seconds": t_compute, "predict_windows_per_s": args.polish / t_compute,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16x3-split operands, f32 accumulate/state",
-            "data": "synthetic", "label_checksum": checksum,
+            "data": "synthetic", "label_checksum": checksum, "host_array_page_locked": registered,
+            "parity": {"windows": int(flips[0]), "flips_above_margin": int(flips[1]), "flips_sub_margin": int(flips[2]),
+                       "what": f"first {keep} windows of every rank's shard against the oracle port, read from the stitched host array"},
             "config": {"workload": f"{world}xB200 window-sharded polish over {args.polish} synthetic windows [T=1000, F={args.features}] "
-                                   f"in batches of {args.batch}, host-side ordered gather (BASELINE configs[2])"},
+                                   f"in batches of {args.batch}, host-side ordered gather through shared host memory, no collective "
+                                   f"(BASELINE configs[2])"},
         }), flush=True)
+    if registered:
+        cudart.cudaHostUnregister(host.data_ptr())
+    del host
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        os.unlink(shm_path)
     pred.close()
     if world > 1:
         dist.destroy_process_group()
@@ -535,9 +633,12 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--sweep", action="store_true", help="also report the batch sweep 64..2048 (BASELINE configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of a sample of the timed batch")
+    ap.add_argument("--parity-windows", type=int, default=16, help="windows of the timed batch checked against the oracle")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the extra back-to-back run (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="windows per CPU-baseline batch")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--reference-sample", type=int, default=32, help="windows per step of --impl reference")
+    ap.add_argument("--reference-sample", type=int, default=0, help="windows per step of --impl reference (0 = --batch, the native arm's step)")
     ap.add_argument("--polish", type=int, default=0, metavar="N",
                     help="secondary line: BASELINE configs[2], window-sharded polish of N synthetic windows (use --batch 2048)")
     ap.add_argument("--train", action="store_true", help="secondary line: BASELINE configs[3], one training chunk step at B=128")

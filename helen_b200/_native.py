@@ -10,7 +10,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 # HB_LIB: another build of the same library (A/B measurements of compile-time variants, tools/build_variants.py)
 LIB_PATH = os.environ.get("HB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhelen_b200.so")
 
-HB_ABI_VERSION = 3
+HB_ABI_VERSION = 4
 HB_OK = 0
 HB_ERR_INVALID_ARGUMENT = -1
 HB_ERR_UNSUPPORTED_DEVICE = -2
@@ -36,7 +36,8 @@ class hb_weights(ctypes.Structure):
 
 class hb_launch_plan(ctypes.Structure):
     _fields_ = [("chunkloop", c_int), ("windows_per_cta", c_int), ("stacked_operand", c_int),
-                ("recurrence_ctas", c_int), ("projection_workers", c_int), ("heads_workers", c_int)]
+                ("recurrence_ctas", c_int), ("projection_workers", c_int), ("heads_workers", c_int),
+                ("cooperative", c_int), ("launches", c_int)]
 
 
 # every symbol include/helen_b200.h declares: name -> (restype, argtypes)

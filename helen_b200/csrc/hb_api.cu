@@ -91,6 +91,7 @@ struct hb_handle {
     // The engines keep per-handle device state (chunk-loop counters, job tables) and the chunk-loop kernel wants the whole
     // chip: successive predict calls of one handle are serialised on the device even when they come on different streams.
     cudaEvent_t last_predict = nullptr;
+    bool predicted = false;
 
     // device timing of the predict kernel sequence
     bool timing = false;
@@ -141,15 +142,11 @@ int run_layer(hb_handle* h, const TA* a, int64_t a_batch_stride, int64_t a_row_s
     return HB_OK;
 }
 
+// Measurement mode: the events were created by hb_enable_kernel_timing; calls beyond them go untimed (nothing is created
+// inside a predict call).
 int begin_timing(hb_handle* h, cudaStream_t s, size_t* slot) {
     *slot = (size_t)-1;
-    if (!h->timing) return HB_OK;
-    if (h->events_used == h->events.size()) {
-        cudaEvent_t a, b;
-        HB_CUDA(cudaEventCreate(&a));
-        HB_CUDA(cudaEventCreate(&b));
-        h->events.emplace_back(a, b);
-    }
+    if (!h->timing || h->events_used == h->events.size()) return HB_OK;
     *slot = h->events_used++;
     HB_CUDA(cudaEventRecord(h->events[*slot].first, s));
     return HB_OK;
@@ -279,6 +276,13 @@ int hb_create(const hb_weights* w, int image_features, int hidden, int n_base, i
         hb_destroy(h);
         return rc;
     }
+    {
+        cudaError_t ee = cudaEventCreateWithFlags(&h->last_predict, cudaEventDisableTiming);
+        if (ee != cudaSuccess) {
+            hb_destroy(h);
+            return fail(HB_ERR_CUDA, "hb_create: cudaEventCreate failed: %s", cudaGetErrorString(ee));
+        }
+    }
 #ifndef HB_NO_TENSOR_ENGINE
     h->tensor = hb::tensor_engine_create(w, image_features, h->sm_count, g_error, sizeof(g_error));
     if (!h->tensor) {
@@ -362,8 +366,8 @@ int hb_predict_windows(hb_handle* h, const uint8_t* images_dev, int64_t B, int T
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace_dev)));
-    if (!h->last_predict) HB_CUDA(cudaEventCreateWithFlags(&h->last_predict, cudaEventDisableTiming));
-    else HB_CUDA(cudaStreamWaitEvent(s, h->last_predict, 0));
+    if (h->predicted) HB_CUDA(cudaStreamWaitEvent(s, h->last_predict, 0));
+    h->predicted = true;
     size_t slot;
     if ((rc = begin_timing(h, s, &slot))) return rc;
 #ifndef HB_NO_TENSOR_ENGINE
@@ -618,8 +622,22 @@ int64_t hb_launch_count(const hb_handle* h) { return h ? h->launches : 0; }
 
 int hb_enable_kernel_timing(hb_handle* h, int enable) {
     if (!h) return fail(HB_ERR_INVALID_ARGUMENT, "null handle");
+    DeviceGuard guard(h->device);
+    // every event the measurement mode uses is created here, never inside a predict call
+    auto ensure = [](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, size_t n) -> cudaError_t {
+        while (v.size() < n) {
+            cudaEvent_t a, b;
+            cudaError_t e = cudaEventCreate(&a);
+            if (e == cudaSuccess) e = cudaEventCreate(&b);
+            if (e != cudaSuccess) return e;
+            v.emplace_back(a, b);
+        }
+        return cudaSuccess;
+    };
+    if (enable) HB_CUDA(ensure(h->events, 4096));
     h->timing = enable != 0;
 #ifndef HB_NO_TENSOR_ENGINE
+    if (enable == 2) HB_CUDA(ensure(h->tensor->rec_events, 1024));
     h->tensor->time_recurrence = enable == 2;
 #endif
     return HB_OK;

@@ -1299,25 +1299,6 @@ tc_recurrence2_kernel(const RecArgs ra)
     if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
-// first-index argmax over the [B, T, 16] records: classes 0..4 base, 5..15 run length (predict_gpu.py:155-156)
-__global__ void argmax16_kernel(const float* __restrict__ p16, int64_t positions, uint8_t* __restrict__ base_label, uint8_t* __restrict__ rle_label)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= positions) return;
-    const float4* pp = reinterpret_cast<const float4*>(p16 + i * NCLS);
-    float v[NCLS];
-#pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) { const float4 o = pp[c4]; v[4 * c4] = o.x; v[4 * c4 + 1] = o.y; v[4 * c4 + 2] = o.z; v[4 * c4 + 3] = o.w; }
-    int ib = 0, ir = 0;
-    float vb = v[0], vr = v[NBASE];
-#pragma unroll
-    for (int c = 1; c < NBASE; ++c) if (v[c] > vb) { vb = v[c]; ib = c; }
-#pragma unroll
-    for (int c = 1; c < NRLE; ++c) if (v[NBASE + c] > vr) { vr = v[NBASE + c]; ir = c; }
-    base_label[i] = (uint8_t)ib;
-    rle_label[i] = (uint8_t)ir;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Heads + softmax + accumulate (predict_gpu.py:137-149) on tensor cores.
 // Roles are swapped here: A = activations (M = 128 positions = 8 windows x 16 columns, straight
@@ -1335,6 +1316,9 @@ struct HeadsArgs {
     float* p_base; float* p_rle;                       // accumulated softmax sums in the reference's layouts [B, T, 5] / [B, T, 11] ...
     float* p16;                                        // ... or (when the caller does not ask for them) one [B, T, 16] array: 64 B per position
     int chunk0;                                        // index of the launch's first chunk in the reference loop (first-touch rule of p16)
+    // p16 mode: the chunk that covers a column LAST turns the finished sums into the two labels itself (first-index argmax,
+    // predict_gpu.py:155-156) and never writes them to p16; total_chunks = chunks of the whole reference loop
+    int total_chunks; uint8_t* base_label; uint8_t* rle_label;
     // persistent mode
     int n_chunks; const unsigned long long* progress; int rec_n; const int* tile_order;
     unsigned long long* heads_done;                    // [group] += 4 per finished tile
@@ -1492,6 +1476,7 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                     for (int c = NBASE; c < NCLS; ++c) v[c] /= sr;
                     float4* pp = reinterpret_cast<float4*>(a.p16 + (b * T + col) * NCLS);
                     const int first_chunk = col < W ? 0 : (col - W) / a.col_step + 1;
+                    const int last_chunk = min(a.total_chunks - 1, col / a.col_step);
                     if (a.chunk0 + chunk != first_chunk) {
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
@@ -1499,8 +1484,20 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                             v[4 * c4] += o.x; v[4 * c4 + 1] += o.y; v[4 * c4 + 2] += o.z; v[4 * c4 + 3] += o.w;
                         }
                     }
+                    if (a.chunk0 + chunk == last_chunk) {
+                        // the sums of this column are final: first-index argmax (strict >, classes in order), labels only
+                        int ib = 0, ir = 0;
+                        float vb = v[0], vr = v[NBASE];
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) pp[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                        for (int c = 1; c < NBASE; ++c) if (v[c] > vb) { vb = v[c]; ib = c; }
+#pragma unroll
+                        for (int c = 1; c < NRLE; ++c) if (v[NBASE + c] > vr) { vr = v[NBASE + c]; ir = c; }
+                        a.base_label[b * T + col] = (uint8_t)ib;
+                        a.rle_label[b * T + col] = (uint8_t)ir;
+                    } else {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) pp[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                    }
                 } else {
                 float* pb = a.p_base + (b * T + col) * NBASE;
                 float* pr = a.p_rle + (b * T + col) * NRLE;
@@ -1600,6 +1597,7 @@ struct TensorTuning {
     int heads_workers = 0;      // HB_HEADS_WORKERS: CTAs of the heads role in the chunk-loop kernel (even)
     bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
     bool pingpong = true;       // HB_NO_PINGPONG: one window tile per recurrence CTA in the per-chunk kernels of large batches
+    bool cooperative = true;    // HB_NO_COOPERATIVE: chunk-loop kernel launched without the cooperative attribute
     static TensorTuning from_env() {
         TensorTuning t;
         t.pdl = getenv("HB_NO_PDL") == nullptr;
@@ -1609,6 +1607,7 @@ struct TensorTuning {
         t.chunkloop = getenv("HB_NO_CHUNKLOOP") == nullptr;
         t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
         t.pingpong = getenv("HB_NO_PINGPONG") == nullptr;
+        t.cooperative = getenv("HB_NO_COOPERATIVE") == nullptr;
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
             const int n = atoi(v);
             if (n == 8 || n == 16 || n == 32) t.windows_per_cta = n;
@@ -1623,7 +1622,9 @@ struct TensorEngine {
     hb_launch_plan last_plan{};
     int* proj_jobs = nullptr;                 // job table of the chunk-loop projection role (see ProjArgs::jobs)
     int* proj_job_offsets = nullptr;
-    size_t proj_jobs_capacity = 0;
+    size_t proj_jobs_capacity = 0;            // fixed at creation: a batch whose table does not fit takes per-chunk launches
+    int loop_max_ctas8 = 0, loop_max_ctas16 = 0;   // CTAs of the chunk-loop kernel (8- / 16-window tiles) that can be resident at once
+    bool coop_with_pdl = true;                // cleared if the driver refuses cooperative + programmatic serialization together
     int jobs_w = -1, jobs_workers = -1, jobs_pixels = -1; int64_t jobs_n_wg = -1;
     int* proj_px_wgs = nullptr;               // [workers] window groups whose pixel jobs a worker owns
     std::vector<int> proj_jobs_host, proj_job_offsets_host, proj_px_wgs_host;
@@ -1697,19 +1698,26 @@ template <class T> struct ident { using type = T; };
 
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start
 // while its predecessor in the stream is still running and synchronises with griddepcontrol.wait.
+// cooperative: the launch is scheduled only when the WHOLE grid can be resident at once (and fails with
+// cudaErrorCooperativeLaunchTooLarge when it never can) - what a kernel whose CTAs wait for each other needs.
 template <typename... KArgs>
-inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, dim3 cluster,
-                                  typename ident<KArgs>::type... args) {
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, dim3 cluster,
+                             bool cooperative, typename ident<KArgs>::type... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     int n = 0;
     if (pdl) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cooperative) {
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
         ++n;
     }
     if (cluster.x * cluster.y * cluster.z > 1) {
@@ -1724,9 +1732,15 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 }
 
 template <typename... KArgs>
+inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, dim3 cluster,
+                                  typename ident<KArgs>::type... args) {
+    return launch_ex(kernel, grid, block, smem, s, pdl, cluster, false, args...);
+}
+
+template <typename... KArgs>
 inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
                           typename ident<KArgs>::type... args) {
-    return launch_cluster(kernel, grid, block, smem, s, pdl, dim3(1, 1, 1), args...);
+    return launch_ex(kernel, grid, block, smem, s, pdl, dim3(1, 1, 1), false, args...);
 }
 
 inline int pow2_scale_exponent(const float* w, size_t n) {
@@ -1885,6 +1899,19 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_chunkloop_kernel<16, 8, 0>, loop8);
         set((const void*)tc_chunkloop_kernel<16, 16, 1>, loop16);
         set((const void*)tc_chunkloop_kernel<16, 16, 0>, loop16);
+        // the chunk-loop kernel's CTAs wait for each other: how many of them fit on the chip at once (one per SM here, but
+        // MPS limits, other resident kernels' reservations or a smaller part change that; the plan respects the answer)
+        auto resident = [&](const void* fn, size_t bytes, int* out) {
+            int per_sm = 0;
+            if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, REC_TC_THREADS, bytes);
+            *out = per_sm * sm_count;
+        };
+        resident((const void*)tc_chunkloop_kernel<16, 8, 1>, loop8, &e->loop_max_ctas8);
+        resident((const void*)tc_chunkloop_kernel<16, 16, 1>, loop16, &e->loop_max_ctas16);
+        // job table of the chunk-loop projection role, sized once for the largest batch the kernel takes (one 8-window
+        // group per two SMs) and chunks of up to 1024 columns; anything larger runs as per-chunk launches
+        e->proj_jobs_capacity = (size_t)(sm_count / 2 + 1) * (2 * 128 + PX_R);
+        if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->proj_jobs), e->proj_jobs_capacity * sizeof(int));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->proj_job_offsets), 256 * sizeof(int));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->proj_px_wgs), 256 * sizeof(int));
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order16), 4096 * sizeof(int));
@@ -1924,13 +1951,14 @@ inline int pick_windows_per_cta(const TensorTuning& tune, int64_t B, int sm_coun
 // workers fit (B <= ~320; at B=384 it ran at 64 k windows/s against 90 k, and one 16-window tile per CTA never won:
 // 86 k against 90 k at B=384, 97 k against 107 k at B=512).  HB_WINDOWS_PER_CTA forces a tile (tests).
 struct ChunkloopPlan { int tile, rec_ctas, proj_workers, heads_workers; };
-inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, ChunkloopPlan* plan) {
+inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, int max_resident8, int max_resident16, ChunkloopPlan* plan) {
     const int sms = sm_count / 2 * 2;
     const int tile = tune.windows_per_cta ? tune.windows_per_cta : 8;
     if (tile != 8 && tile != 16) return false;                 // (32 live windows leave no room for two gi' rows per window)
     if (tile == 8 && !tune.live8 && !tune.windows_per_cta) return false;
     const int64_t rec = (B + tile - 1) / tile;
     if (2 * rec > sms) return false;
+    if (sms > (tile == 8 ? max_resident8 : max_resident16)) return false;   // the grid (one CTA per SM) must be co-resident as a whole
     const int left = sms - (int)(2 * rec);
     // heads: one CTA in seven of what the recurrence leaves, at least 2 (a heads tile is a serial load -> MMA -> epilogue
     // chain of ~4 us; with 6 workers at B=256 the decoder waited for the heads: 68 k windows/s against 74.6 k with 12)
@@ -1955,13 +1983,25 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const int F = e->features;
     const int64_t n_wg = (B + WG - 1) / WG;
     int launches = 0;
-    // the reference's two arrays only when the caller wants the probabilities back; else one 64-byte record per position
+#define TE_CUDA(expr)                                                                                          \
+    do {                                                                                                       \
+        cudaError_t te_ = (expr);                                                                              \
+        if (te_ != cudaSuccess) {                                                                              \
+            snprintf(err, errlen, "tensor engine: %s failed: %s (line %d)", #expr, cudaGetErrorString(te_), __LINE__); \
+            return HB_ERR_CUDA;                                                                                \
+        }                                                                                                      \
+    } while (0)
+    // the reference's two arrays only when the caller wants the probabilities back; else one 64-byte record per position,
+    // written by the first chunk that covers a column and turned into labels by the last one (no fill, no argmax launch)
     float* p16 = (base_prob || rle_prob) ? nullptr : ws.p16;
     if (p16) {
-        cudaMemsetAsync(p16, 0, (size_t)B * T * NCLS * sizeof(float), s);
+        if (enc_cols < T) {                                    // columns no chunk covers keep all-zero sums: label 0
+            TE_CUDA(cudaMemsetAsync(base_labels, 0, (size_t)B * T, s));
+            TE_CUDA(cudaMemsetAsync(rle_labels, 0, (size_t)B * T, s));
+        }
     } else {
-        cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s);
-        cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s);
+        TE_CUDA(cudaMemsetAsync(p_base, 0, (size_t)B * T * NBASE * sizeof(float), s));
+        TE_CUDA(cudaMemsetAsync(p_rle, 0, (size_t)B * T * NRLE * sizeof(float), s));
     }
     const int xblk = e->enc.Kp * 16;                           // bytes of one (group, column) pixel block
     const int proj_workers = std::max(1, e->sm_count / 6);
@@ -1971,7 +2011,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     const int tiles8 = (W + 7) / 8, tiles16 = (W + 15) / 16;
     // ---- how the batch is laid out on the chip ----
     ChunkloopPlan plan{};
-    bool chunkloop = e->tune.chunkloop && n_chunks > 0 && B > 0 && tiles8 <= 4096 && plan_chunkloop(e->tune, B, e->sm_count, &plan);
+    bool chunkloop = e->tune.chunkloop && n_chunks > 0 && B > 0 && tiles8 <= 128 &&
+                     plan_chunkloop(e->tune, B, e->sm_count, e->loop_max_ctas8, e->loop_max_ctas16, &plan);
     // pixel jobs: the projection role also projects the image columns the next chunk's encoder adds
     const int px_tiles = (enc_cols + 7) / 8, px_pre_tiles = std::min(px_tiles, tiles8);
     bool pixels_in_loop = chunkloop && e->tune.pixel_jobs && n_chunks > 1 && e->enc.Kp <= 128 && px_tiles < 4096 && (J + 7) / 8 + 1 <= PX_R;
@@ -1981,7 +2022,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         flags_needed = (size_t)4 * plan.rec_ctas + n_groups + n_groups * tiles8 * 2;
         if (pixels_in_loop && flags_needed + n_groups * px_tiles * 2 > e->flags_capacity) pixels_in_loop = false;
         if (pixels_in_loop) flags_needed += n_groups * px_tiles * 2;
-        chunkloop = flags_needed <= e->flags_capacity;
+        chunkloop = flags_needed <= e->flags_capacity &&
+                    (size_t)n_wg * (2 * tiles8 + (pixels_in_loop ? PX_R : 0)) <= e->proj_jobs_capacity;   // job table sized at creation
         pixels_in_loop = pixels_in_loop && chunkloop;
     }
     if (enc_cols > 0) {
@@ -1991,6 +2033,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         const int64_t chunks16 = n_wg * T * (e->enc.Kp / 8) * WG;
         const int blocks = (int)std::min<int64_t>((chunks16 + 255) / 256, (int64_t)e->sm_count * 16);
         pileup_to_operand_image_kernel<<<blocks, 256, 0, s>>>(images, B, T, F, e->enc.Kp, ws.ximg, n_wg);
+        TE_CUDA(cudaGetLastError());
         const int tiles = (int)std::min<int64_t>(n_wg * (pixels_in_loop ? px_pre_tiles : px_tiles), proj_workers);
         ProjArgs pe{};
         pe.col_tiles = pixels_in_loop ? px_pre_tiles : 0;
@@ -1998,8 +2041,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         pe.blk_bytes = xblk; pe.lbo = 128; pe.Kp = e->enc.Kp; pe.n_wg = n_wg; pe.W = enc_cols;
         pe.w_tmem = e->enc.wih_tmem; pe.scale_row = e->enc.scale_row; pe.bias_row = e->enc.bias_row; pe.gi = ws.gi_enc;
         pe.pair = pair_mode;
-        detail::launch_cluster(tc_projection_kernel<false>, dim3(tiles, 6), dim3(PROJ_THREADS), detail::projection_smem(xblk, 1), s, pdl,
-                               dim3(1, pair_mode ? 2 : 1, 1), pe);
+        TE_CUDA(detail::launch_cluster(tc_projection_kernel<false>, dim3(tiles, 6), dim3(PROJ_THREADS), detail::projection_smem(xblk, 1), s, pdl,
+                                       dim3(1, pair_mode ? 2 : 1, 1), pe));
         launches += 2;
     }
     static long long* dbg_buf = nullptr;
@@ -2022,22 +2065,18 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     heads_base.n_wg = n_wg; heads_base.B = B; heads_base.W = W; heads_base.T = T; heads_base.col_step = J;
     heads_base.w_img = e->head_img; heads_base.b_head = e->b_head; heads_base.inv_scale = e->head_inv;
     heads_base.p_base = p_base; heads_base.p_rle = p_rle; heads_base.p16 = p16;
+    heads_base.total_chunks = n_chunks; heads_base.base_label = base_labels; heads_base.rle_label = rle_labels;
 
     // hb_enable_kernel_timing(2): CUDA events around every launch of the dominant kernel (no launch overlap then)
     auto dominant_begin = [&]() -> size_t {
-        if (!e->time_recurrence) return 0;
-        if (e->rec_events_used == e->rec_events.size()) {
-            cudaEvent_t a, b;
-            cudaEventCreate(&a);
-            cudaEventCreate(&b);
-            e->rec_events.emplace_back(a, b);
-        }
+        // measurement mode only (hb_enable_kernel_timing(2) created the events); launches beyond them go untimed
+        if (!e->time_recurrence || e->rec_events_used == e->rec_events.size()) return (size_t)-1;
         const size_t slot = e->rec_events_used++;
         cudaEventRecord(e->rec_events[slot].first, s);
         return slot;
     };
     auto dominant_end = [&](size_t slot) {
-        if (e->time_recurrence) cudaEventRecord(e->rec_events[slot].second, s);
+        if (slot != (size_t)-1) cudaEventRecord(e->rec_events[slot].second, s);
     };
     // ---- chunk-loop kernel: every role of the whole chunk loop resident at once ----
     if (chunkloop) {
@@ -2049,7 +2088,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             for (int i = 0; i < n; ++i) order[i] = i;
             auto ready = [&](int tt) { return std::max(std::min(16 * tt + 16, W), W - 16 * tt); };
             std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ready(x) < ready(y); });
-            cudaMemcpyAsync(e->tile_order16, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s);
+            TE_CUDA(cudaMemcpyAsync(e->tile_order16, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
             e->tile_order_w = W;
         }
         if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg || e->jobs_pixels != (int)pixels_in_loop) {
@@ -2084,17 +2123,16 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 e->proj_job_offsets_host.push_back((int)e->proj_jobs_host.size());
             }
             if (e->proj_jobs_host.size() > e->proj_jobs_capacity) {
-                cudaStreamSynchronize(s);
-                cudaFree(e->proj_jobs);
-                e->proj_jobs_capacity = e->proj_jobs_host.size() * 2;
-                cudaMalloc(reinterpret_cast<void**>(&e->proj_jobs), e->proj_jobs_capacity * sizeof(int));
+                snprintf(err, errlen, "tensor engine: projection job table of %zu entries exceeds its capacity %zu", e->proj_jobs_host.size(), e->proj_jobs_capacity);
+                return HB_ERR_CUDA;
             }
-            cudaMemcpyAsync(e->proj_jobs, e->proj_jobs_host.data(), e->proj_jobs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
-            cudaMemcpyAsync(e->proj_job_offsets, e->proj_job_offsets_host.data(), e->proj_job_offsets_host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
-            cudaMemcpyAsync(e->proj_px_wgs, e->proj_px_wgs_host.data(), e->proj_px_wgs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+            // (only when the batch shape changed since the last call; the tables are a few KB)
+            TE_CUDA(cudaMemcpyAsync(e->proj_jobs, e->proj_jobs_host.data(), e->proj_jobs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            TE_CUDA(cudaMemcpyAsync(e->proj_job_offsets, e->proj_job_offsets_host.data(), e->proj_job_offsets_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            TE_CUDA(cudaMemcpyAsync(e->proj_px_wgs, e->proj_px_wgs_host.data(), e->proj_px_wgs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
             e->jobs_w = W; e->jobs_workers = plan.proj_workers; e->jobs_n_wg = n_wg; e->jobs_pixels = (int)pixels_in_loop;
         }
-        cudaMemsetAsync(e->flags, 0, flags_needed * sizeof(unsigned long long), s);
+        TE_CUDA(cudaMemsetAsync(e->flags, 0, flags_needed * sizeof(unsigned long long), s));
         unsigned long long* f = e->flags;
         unsigned long long* enc_prog = f;                 f += 2 * plan.rec_ctas;
         unsigned long long* dec_prog = f;                 f += 2 * plan.rec_ctas;
@@ -2134,14 +2172,27 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         const dim3 grid(2 * plan.rec_ctas + 6 * plan.proj_workers + plan.heads_workers), cluster(1, 1, 1);
         const size_t smem = std::max({plan.tile == 8 ? detail::recurrence_smem_gi2<8>() : detail::recurrence_smem_gi2<16>(),
                                       detail::projection_smem(YROW, 2), detail::heads_smem()});
+        // Cooperative launch: the CTAs of this kernel spin on each other's counters, so the grid must be resident as a
+        // whole - with the attribute the launch waits until it can be (another handle's kernel, or any other work on the
+        // device, cannot leave it half scheduled) instead of relying on an idle chip.
+        cudaError_t le = cudaSuccess;
         auto go = [&](auto kernel) {
             const size_t slot = dominant_begin();
-            detail::launch_cluster(kernel, grid, dim3(REC_TC_THREADS), smem, s, pdl && !e->time_recurrence, cluster,
+            const bool coop = e->tune.cooperative;
+            bool use_pdl = pdl && !e->time_recurrence && (!coop || e->coop_with_pdl);
+            le = detail::launch_ex(kernel, grid, dim3(REC_TC_THREADS), smem, s, use_pdl, cluster, coop,
                                    ra, pp, hp, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
+            if (le != cudaSuccess && coop && use_pdl) {       // some drivers refuse the two attributes together
+                cudaGetLastError();
+                e->coop_with_pdl = false;
+                le = detail::launch_ex(kernel, grid, dim3(REC_TC_THREADS), smem, s, false, cluster, coop,
+                                       ra, pp, hp, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
+            }
             dominant_end(slot);
         };
         if (plan.tile == 8) { if (e->tune.stack) go(tc_chunkloop_kernel<16, 8, 1>); else go(tc_chunkloop_kernel<16, 8, 0>); }
         else { if (e->tune.stack) go(tc_chunkloop_kernel<16, 16, 1>); else go(tc_chunkloop_kernel<16, 16, 0>); }
+        TE_CUDA(le);
         launches += 1;
     }
 
@@ -2186,31 +2237,35 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     e->last_plan.recurrence_ctas = chunkloop ? plan.rec_ctas : (int)grid_rec.x;
     e->last_plan.projection_workers = chunkloop ? plan.proj_workers : tiles_proj;
     e->last_plan.heads_workers = chunkloop ? plan.heads_workers : tiles_heads;
+    e->last_plan.cooperative = (chunkloop && e->tune.cooperative) ? 1 : 0;
     int chunk = 0;
     for (int i = 0; !chunkloop && i + W <= T; i += J, ++chunk) {
         float* enc_h = hid_bufs[flip];
         float* dec_h = hid_bufs[flip ^ 1];
         const int buf = chunk & 1;
-        if (chunk >= 2) cudaStreamWaitEvent(s, e->ev_heads[buf], 0);      // heads(chunk - 2) has read this yimg2 buffer
+        if (chunk >= 2) TE_CUDA(cudaStreamWaitEvent(s, e->ev_heads[buf], 0));      // heads(chunk - 2) has read this yimg2 buffer
         recurrence(rec_args(e->enc, ws.gi_enc, enc_cols, i, hid, enc_h, ws.yimg1), pdl && chunk == 0);
         detail::launch_cluster(tc_projection_kernel<true>, dim3(tiles_proj, 6), dim3(PROJ_THREADS), detail::projection_smem(YROW, 2), s, pdl,
                                dim3(1, pair_mode ? 2 : 1, 1), pd);
         recurrence(rec_args(e->dec, ws.gi, W, 0, enc_h, dec_h, ws.yimg2[buf]), pdl);
-        cudaEventRecord(e->ev_dec[buf], s);
-        cudaStreamWaitEvent(e->side, e->ev_dec[buf], 0);
+        TE_CUDA(cudaEventRecord(e->ev_dec[buf], s));
+        TE_CUDA(cudaStreamWaitEvent(e->side, e->ev_dec[buf], 0));
         HeadsArgs ha = heads_base;
         ha.yimg = ws.yimg2[buf]; ha.col0 = i; ha.chunk0 = chunk;
         tc_heads_kernel<<<tiles_heads, HEADS_THREADS, detail::heads_smem(), e->side>>>(ha);
-        cudaEventRecord(e->ev_heads[buf], e->side);
+        TE_CUDA(cudaGetLastError());
+        TE_CUDA(cudaEventRecord(e->ev_heads[buf], e->side));
         launches += 4;
         hid = dec_h;
         flip ^= 1;
     }
-    for (int b = 0; b < std::min(chunk, 2); ++b) cudaStreamWaitEvent(s, e->ev_heads[b], 0);   // join the side stream
+    for (int b = 0; b < std::min(chunk, 2); ++b) TE_CUDA(cudaStreamWaitEvent(s, e->ev_heads[b], 0));   // join the side stream
     const int64_t positions = B * T;
-    if (p16) argmax16_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p16, positions, base_labels, rle_labels);
-    else argmax_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p_base, p_rle, positions, base_labels, rle_labels);
-    launches += 1;
+    if (!p16) {                                                // probabilities requested: labels from the returned arrays
+        argmax_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p_base, p_rle, positions, base_labels, rle_labels);
+        launches += 1;
+    } else if (n_chunks == 0) {                                // T < W: no chunk at all, labels 0 (memset above covered it)
+    }
     if (dbg_on && dbg_buf) {
         static int printed = 0;
         cudaStreamSynchronize(s);
@@ -2283,7 +2338,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         snprintf(err, errlen, "tensor engine launch failed: %s", cudaGetErrorString(ce));
         return HB_ERR_CUDA;
     }
+    e->last_plan.launches = launches;
     return launches;
+#undef TE_CUDA
 }
 
 }  // namespace hb

@@ -137,12 +137,15 @@ class WindowPredictor(object):
             raise ValueError(f"images on {images.device}, predictor on {self.device}")
         images = images.contiguous()
         batch, seq_len = images.shape[0], images.shape[1]
-        base = torch.zeros((batch, seq_len), dtype=torch.uint8, device=self.device)
-        rle = torch.zeros((batch, seq_len), dtype=torch.uint8, device=self.device)
+        # the library writes every element of its outputs (columns no chunk covers get label 0 / probability 0):
+        # no fill kernels here
+        alloc = torch.empty if (batch and seq_len) else torch.zeros
+        base = alloc((batch, seq_len), dtype=torch.uint8, device=self.device)
+        rle = alloc((batch, seq_len), dtype=torch.uint8, device=self.device)
         pb = pr = None
         if return_probs:
-            pb = torch.zeros((batch, seq_len, ImageSizeOptions.TOTAL_BASE_LABELS), dtype=torch.float32, device=self.device)
-            pr = torch.zeros((batch, seq_len, ImageSizeOptions.TOTAL_RLE_LABELS), dtype=torch.float32, device=self.device)
+            pb = alloc((batch, seq_len, ImageSizeOptions.TOTAL_BASE_LABELS), dtype=torch.float32, device=self.device)
+            pr = alloc((batch, seq_len, ImageSizeOptions.TOTAL_RLE_LABELS), dtype=torch.float32, device=self.device)
         if batch and seq_len:
             ws = self._get_workspace(batch, seq_len, window)
             stream = torch.cuda.current_stream(self.device).cuda_stream

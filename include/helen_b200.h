@@ -13,8 +13,11 @@
  *  - a handle is bound to one CUDA device and is not thread-safe (one handle per
  *    process/GPU, like the reference's one-process-per-GPU predict(), predict_gpu.py:38).
  *  - "_dev" pointers are device memory owned by the caller; the handle owns only its
- *    packed copy of the weights.  Device entry points allocate nothing, never
- *    synchronise the host, and are ordered on the cudaStream_t passed as `stream`.
+ *    packed copy of the weights and a few KB of scheduling tables sized in hb_create.
+ *    Device entry points allocate nothing, create no events, never synchronise the
+ *    host, and are ordered on the cudaStream_t passed as `stream` (successive calls of
+ *    one handle are also ordered among themselves, whatever their streams).  The
+ *    measurement modes (hb_enable_kernel_timing) create their events when enabled.
  *  - there is no CPU fallback: every call fails loudly without a CUDA sm_100 device.
  */
 #ifndef HELEN_B200_H
@@ -27,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 3
+#define HB_ABI_VERSION 4
 
 typedef enum hb_status {
     HB_OK = 0,
@@ -165,6 +168,8 @@ typedef struct hb_launch_plan {
     int recurrence_ctas;     /* per direction */
     int projection_workers;
     int heads_workers;
+    int cooperative;         /* 1: the chunk-loop kernel was a cooperative launch (co-residency guaranteed by the driver) */
+    int launches;            /* kernel launches the call issued */
 } hb_launch_plan;
 int hb_last_launch_plan(const hb_handle *handle, hb_launch_plan *out);
 
