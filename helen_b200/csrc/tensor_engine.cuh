@@ -48,12 +48,16 @@ constexpr int WG = 8;                             // windows per window group ==
 constexpr int YBLK = 2048;                        // [8 windows x 128 k] fp16 image of one direction: two swizzle atoms
 constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)  [sizes only]
 constexpr int GI_ROW_BYTES = G * 4;               // 1536 B: gi of one (window, t, direction)
-// gi' lives in global memory as a "gi image": [window group][column][direction][gate r,z,n][8 windows][128 units] fp32,
-// so that what one recurrence step needs (all gates of a window group's column and direction, 12 KB) and what one
-// projection job produces per column (one gate block of 8 windows, 4 KB) are each ONE contiguous bulk copy.
-constexpr int GI_BLK_FLOATS = WG * H;             // 1024: one (group, column, gate block)
-constexpr int GI_GRP_BYTES = 3 * GI_BLK_FLOATS * 4;   // 12288 B: one (group, column, direction)
-__host__ __device__ constexpr int64_t gi_block(int64_t wg, int64_t cols, int64_t t, int blk) { return ((wg * cols + t) * 6 + blk) * GI_BLK_FLOATS; }
+// gi' lives in global memory as a "gi image": [window group][direction x gate r,z,n = 6 blocks][column][8 windows][128 units]
+// fp32.  What one projection job produces (one gate block of 8 windows x 8 consecutive columns, 32 KB) is ONE contiguous
+// bulk copy; what one recurrence step needs (the three gate blocks of a window group's column and direction) is three
+// 4 KB copies.  (The first layout kept a step's 12 KB contiguous instead, which made every projection job eight separate
+// bulk stores: their issue cost, ~1150 cycles per job, made the store warp the slowest stage of the projection role and
+// left the decoder waiting 12-18 us per chunk for its first tiles.)
+constexpr int GI_BLK_FLOATS = WG * H;             // 1024: one (group, gate block, column)
+constexpr int GI_BLK_BYTES = GI_BLK_FLOATS * 4;   // 4096
+constexpr int GI_GRP_BYTES = 3 * GI_BLK_BYTES;    // 12288 B: the three gate blocks of one (group, column, direction) in a shared-memory stage
+__host__ __device__ constexpr int64_t gi_block(int64_t wg, int64_t cols, int64_t t, int blk) { return ((wg * 6 + blk) * cols + t) * GI_BLK_FLOATS; }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -112,15 +116,13 @@ pileup_to_operand_image_kernel(const uint8_t* __restrict__ images, int64_t B, in
 // The epilogue folds the bias sums and the -log2(e) factors of the gate nonlinearities into gi'
 // (see tc_recurrence_kernel), so gi' is NOT the plain pre-activation of the fp32 engine.
 // ---------------------------------------------------------------------------------------------
-#ifdef HB_PROJ_TWO_STORE_WARPS
-constexpr int PROJ_THREADS = 256;                // variant: warps 6 and 7 both store, one staging buffer each
-#else
 constexpr int PROJ_THREADS = 224;                // warps 0-3 epilogue, 4 MMA issuer, 5 tile loader, 6 gi' store
-#endif
 constexpr int PROJ_NT = 64;
 constexpr int PROJ_STG_BYTES = PROJ_NT * 128 * 4;   // fp32 staging of one tile's output block: [64 (column, window)][128 gate rows]
 constexpr int PROJ_STAGES = 2;                    // full-K tiles; the K-half jobs of the chunk-loop kernel are half as large: 4 stages
 constexpr int PROJ_PUBLISH_BATCH = 8;
+constexpr int PROJ_URGENT_BATCH = 3;              // flags of the jobs the decoder is waiting for go out in batches of three
+constexpr int PROJ_TILE_SLOTS = 2048;             // chunk-loop kernel: tiles one worker may own (first-half bookkeeping of the store warp)
 constexpr int PROJ_W_COL0 = 128;
 
 // Encoder input projection inside the chunk-loop kernel ("pixel jobs"): while the encoder of chunk k runs, the projection
@@ -149,18 +151,19 @@ struct ProjArgs {
     const float* scale_row;        // [768]
     const float* bias_row;         // [768]
     float* gi;                     // gi image with W columns (see gi_block)
-    float* gi_b;                   // chunk-loop kernel: where the reverse-source K-half goes (see jobs)
     // pair mode: the launch uses clusters of 2 CTAs along the gate-block axis; both CTAs of a pair walk the same
     // tiles, each fetches half of a tile and multicasts it to both, halving the L2 traffic of the activations
     int pair;
     // ---- chunk-loop kernel (producer/consumer mode): the role walks n_chunks chunks and its K = 256 contraction is
     // split by SOURCE direction.  A job is one half of a column tile: the K = 128 slice that multiplies the forward
     // (or the reverse) encoder's outputs, runnable as soon as THAT direction has stored the tile's columns, so the
-    // projection keeps pace with the encoder instead of starting when both directions meet in the middle.  The
-    // forward-source half writes scale * acc + bias to gi, the reverse-source half writes scale * acc to gi_b, and
-    // the decoder's gate threads add the two rows (fixed order: the result does not depend on timing).  (Adding in
-    // place was tried: reading the first half back stalls the epilogue on a global round trip, and red.add is
-    // issued lane by lane - either way the role fell behind the encoder.)
+    // projection keeps pace with the encoder instead of starting when both directions meet in the middle.  Both
+    // halves land in the SAME gi block: whichever half of a tile a CTA processes first stores scale * acc (+ bias on the
+    // forward-source half), the other one is added to it at the destination by a reducing bulk copy
+    // (cp.reduce.async.bulk .add.f32: the L2 does the read-modify-write, nothing comes back to the SM).  a + b == b + a
+    // in fp32, so the sum does not depend on which half ran first.  (Two separate gi arrays added by the decoder's gate
+    // threads were the first version: twice the gi traffic and shared memory, 12 more instructions per gate thread and
+    // step.  Reading the first half back in the epilogue, or red.add per element, stalled the role.)
     const int* jobs;               // per worker, in the order the encoder makes them runnable (see pack_proj_job)
     const int* job_offsets;        // [workers + 1]
     const unsigned long long* progress; unsigned long long epoch; int rec_n;   // encoder progress counters, [cta][dir]
@@ -227,6 +230,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + 2);
     // chunk-loop kernel: the loader decides the job order at run time (see below) and passes it on through this ring
     volatile int* job_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [16] >= jobs in flight between loader and store warp
+    volatile int* first_it = job_ring + 16;                  // [PROJ_TILE_SLOTS], store warp only: job that stored a tile's first K-half, or -1
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kwords = Kp >> 1;
@@ -290,12 +294,17 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     auto table_at = [&](int i, int n_px) { return __ldg(a.jobs + job0 + (i < n_px ? i : px_wgs * PX_R + (i - n_px))); };
     ProjJob j;
     // HB_DEBUG_TIMELINE: worker 0 / block 0 adds up the cycles each role spends at its wait points (slots 7200 + 8 role + k)
+#ifdef HB_TIMELINE
     const bool acct = a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0;
     long long t_wait[4] = {0, 0, 0, 0};
     long long t_role0 = acct ? clock64() : 0;
-#define HB_TIMED(k, stmt) do { const long long t_ = acct ? clock64() : 0; stmt; if (acct) t_wait[k] += clock64() - t_; } while (0)
+#define HB_TIMED(k, ...) do { const long long t_ = acct ? clock64() : 0; __VA_ARGS__; if (acct) t_wait[k] += clock64() - t_; } while (0)
 #define HB_ROLE_REPORT(role) do { if (acct) { for (int k_ = 0; k_ < 4; ++k_) a.dbg[7200 + 8 * (role) + k_] = t_wait[k_]; \
                                               a.dbg[7200 + 8 * (role) + 4] = clock64() - t_role0; } } while (0)
+#else
+#define HB_TIMED(k, ...) do { __VA_ARGS__; } while (0)
+#define HB_ROLE_REPORT(role) do { } while (0)
+#endif
     if (warp == 5) {
         // ===================== loader =====================
         // Job order in the chunk-loop kernel: the table lists a worker's jobs in the order the encoder makes them runnable;
@@ -336,7 +345,9 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             if (split) {
                 int e = 0;
                 if (lane == 0) {
+#ifdef HB_TIMELINE
                     const long long t_ = acct ? clock64() : 0;
+#endif
                     const long long t_spin = clock64();
                     while (true) {
                         if (front < back && !jb.pixel && vb >= need_of(jb, chunk)) { e = eb | (1 << 30); --back; break; }   // bit 30: the decoder waits for it
@@ -345,7 +356,9 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                         if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap();
                         vf = tc::ld_relaxed_gpu(flag_of(jf)); vb = jb.pixel ? 0ull : tc::ld_relaxed_gpu(flag_of(jb));
                     }
+#ifdef HB_TIMELINE
                     if (acct) t_wait[1] += clock64() - t_;
+#endif
                     job_ring[it & 15] = e;
                     if (front <= back) look();               // for the next job; the loads complete while this one is issued
                 }
@@ -354,7 +367,9 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             } else {
                 j = proj_tile_job(a, worker, n_workers, idx);
             }
+#ifdef HB_TIMELINE
             const long long t_issue = acct ? clock64() : 0;
+#endif
             // geometry of the job's stage: decoder jobs [part hi, lo][K-slice][8 columns][2 KB], pixel jobs [8 columns][xblk]
             const int jparts = j.pixel ? 1 : PARTS, jdirs = j.pixel ? 1 : n_dirs, jblk = j.pixel ? a.px.blk_bytes : blk_bytes;
             if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * jparts * jdirs * jblk));
@@ -377,17 +392,19 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 }
             }
             __syncwarp();
+#ifdef HB_TIMELINE
             if (acct) t_wait[3] += clock64() - t_issue;
+#endif
         }
         }
         HB_ROLE_REPORT(0);
-#ifdef HB_PROJ_TWO_STORE_WARPS
-    } else if (warp >= 6) {
-#else
     } else if (warp == 6) {
-#endif
         // ===================== gi' store =====================
-        // lane c < 8 copies column t0 + c of the staged block: [8 windows][128 gate rows] = 4 KB, contiguous in the gi image
+        // The staged block [valid columns][8 windows][128 gate rows] is contiguous in the gi image: ONE bulk copy per job,
+        // issued by lane 0.  In the chunk-loop kernel the two K-halves of a tile go to the same block: the half this CTA
+        // stores first is a plain copy, the other one a reducing copy (fp32 add at the destination).  Bulk copies of one
+        // thread are not ordered among themselves, so the reducing copy is only issued once the first half's copy is
+        // known to be complete (first_it / n_complete below; the two halves are normally many jobs apart).
         const int tiles_t = (W + 7) >> 3;
         // Flags are raised in batches: the release below is a gpu-scope fence (~1 us), one per job would make this warp
         // the bottleneck of the role.  A batch goes out when PROJ_PUBLISH_BATCH jobs are waiting and after the worker's
@@ -396,11 +413,13 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         // ran dry was tried: it runs dry after almost every job, and each flush waits ~1.5 us for the newest copies.
         unsigned long long* pending[PROJ_PUBLISH_BATCH];     // flags of the jobs whose copies may still be in flight
         int n_pending = 0;
-        auto publish = [&](int keep) {                       // wait until all but the newest `keep` (0 or 2) jobs have landed, raise their flags
+        int n_complete = 0;                                  // jobs [0, n_complete) of this CTA: their copies have been performed
+        auto publish = [&](int keep, int it_now) {           // wait until all but the newest `keep` (0, 1 or 2) jobs have landed, raise their flags
             if (n_pending <= keep) return;
             // wait_group (not .read) returns when the copies' writes have been performed; the release below orders them
             // before the counter.  (An additional fence.proxy.async here cost ~1000 cycles per publication.)
             if (keep == 0) tc::bulk_wait0(); else if (keep == 1) tc::bulk_wait_pending<1>(); else tc::bulk_wait_pending<2>();
+            n_complete = it_now + 1 - keep;
 #ifdef HB_STRICT_PROXY_FENCE
             tc::fence_proxy_async_all();
 #endif
@@ -415,65 +434,58 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
         const int n_jobs = split ? px_count(chunk) + n_dec : n_table;
+        // which of this worker's tiles already hold one half in this chunk, and the job that stored it
+        if (split) for (int i = lane; i < PROJ_TILE_SLOTS; i += 32) first_it[i] = -1;
+        __syncwarp();
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int sb = it & 1;
             const uint32_t par = (uint32_t)((it >> 1) & 1);
-#ifdef HB_PROJ_TWO_STORE_WARPS
-            // Variant for A/B runs, not measured yet (tools/build_variants.py store2=-DHB_PROJ_TWO_STORE_WARPS).  The timeline's
-            // wait accounting leaves this warp ~1150 cycles per job outside its waits (eight bulk stores issued one lane after
-            // the other) plus ~490 for the flag batches: the slowest stage of the role.  Here warp 6 takes the even jobs
-            // (staging buffer 0) and warp 7 the odd ones (buffer 1); each keeps its own list of flags to raise.
-            if (sb != warp - 6) continue;
-            HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
-            {
-                const int e_ring2 = split ? job_ring[it & 15] : 0;
-                j = split ? proj_decode(a, e_ring2) : proj_tile_job(a, worker, n_workers, idx);
-                float* out2 = j.pixel ? a.px.gi : (j.src_dir ? a.gi_b : gi);
-                const int out_cols2 = j.pixel ? a.px.cols : W;
-                if (lane < 8 && j.t0 + lane < out_cols2)
-                    tc::bulk_s2g(out2 + gi_block(j.wg, out_cols2, j.t0 + lane, blk), staging + sb * PROJ_STG_BYTES + lane * (GI_BLK_FLOATS * 4), GI_BLK_FLOATS * 4);
-                tc::bulk_commit();
-                HB_TIMED(1, tc::bulk_wait_read_pending<0>());        // this job's copies have read MY staging buffer
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(stg_empty + sb);
-                if (a.tile_flags != nullptr) {
-                    pending[n_pending++] = j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
-                                                   : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
-                    if (idx + 2 >= n_jobs) HB_TIMED(2, publish(0));                  // this warp's last job of the chunk
-                    else if ((e_ring2 >> 30) & 1) { if (n_pending >= 2) HB_TIMED(3, publish(1)); }
-                    else if (n_pending >= PROJ_PUBLISH_BATCH / 2) HB_TIMED(3, publish(1));
-                }
-                if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0 && idx == n_jobs - 1) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
-            }
-            continue;
-#endif
             HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
             const int e_ring = split ? job_ring[it & 15] : 0;
             j = split ? proj_decode(a, e_ring) : proj_tile_job(a, worker, n_workers, idx);
-            float* out = j.pixel ? a.px.gi : (j.src_dir ? a.gi_b : gi);
+            float* out = j.pixel ? a.px.gi : gi;
             const int out_cols = j.pixel ? a.px.cols : W;
-            if (lane < 8 && j.t0 + lane < out_cols)
-                tc::bulk_s2g(out + gi_block(j.wg, out_cols, j.t0 + lane, blk), staging + sb * PROJ_STG_BYTES + lane * (GI_BLK_FLOATS * 4), GI_BLK_FLOATS * 4);
+            bool second = false;
+            if (split && !j.pixel) {
+                const int slot = (int)((j.wg * tiles_t + (j.t0 >> 3)) / n_workers);       // this worker's tiles, densely numbered
+                const int prev = first_it[slot];
+                second = prev >= 0;
+                __syncwarp();
+                if (!second) { if (lane == 0) first_it[slot] = it; __syncwarp(); }
+                else if (prev >= n_complete) {
+                    // the first half's copy may still be in flight (both halves reached this CTA back to back)
+                    HB_TIMED(2, tc::bulk_wait0());
+                    n_complete = it;
+                }
+            }
+            if (lane == 0) {
+                float* dst = out + gi_block(j.wg, out_cols, j.t0, blk);
+                const uint32_t bytes = (uint32_t)j.valid * GI_BLK_BYTES;
+                if (second) tc::bulk_reduce_add_f32_s2g(dst, staging + sb * PROJ_STG_BYTES, bytes);
+                else tc::bulk_s2g(dst, staging + sb * PROJ_STG_BYTES, bytes);
+            }
             tc::bulk_commit();
-            // the PREVIOUS job's copies have read their staging buffer (this job's read overlaps the next epilogue)
+            // the PREVIOUS job's copy has read its staging buffer (this job's read overlaps the next epilogue)
             HB_TIMED(1, tc::bulk_wait_read_pending<1>());
             __syncwarp();
             if (lane == 0 && it > 0) tc::mbar_arrive(stg_empty + (sb ^ 1));
             if (a.tile_flags != nullptr) {
                 pending[n_pending++] = j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
                                                : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
-                if (idx == n_jobs - 1) HB_TIMED(2, publish(0));                      // last job of the chunk
-                // jobs taken from the back of the list are the ones the decoder is waiting for: batches of three (one
+                if (idx == n_jobs - 1) HB_TIMED(2, publish(0, it));                  // last job of the chunk
+                // jobs taken from the back of the list are the ones the decoder is waiting for: small batches (one
                 // publication per job was measured: the fence makes this warp the bottleneck)
-                else if ((e_ring >> 30) & 1) { if (n_pending >= 4) HB_TIMED(3, publish(1)); }
-                else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2));   // copies issued two jobs ago have normally landed: no stall
+                else if ((e_ring >> 30) & 1) { if (n_pending >= PROJ_URGENT_BATCH + 1) HB_TIMED(3, publish(1, it)); }
+                else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2, it));   // copies issued two jobs ago have normally landed: no stall
             }
+#ifdef HB_TIMELINE
             if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
+#endif
         }
         }
-        publish(0);
-        if (lane < 32) tc::bulk_wait0();                     // the kernel's results are complete when the role returns
-        if (warp == 6) HB_ROLE_REPORT(3);
+        publish(0, it - 1);
+        tc::bulk_wait0();                                    // the kernel's results are complete when the role returns
+        HB_ROLE_REPORT(3);
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
@@ -547,30 +559,19 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             float* stg = reinterpret_cast<float*>(staging + sb * PROJ_STG_BYTES) + r;
             const float sc = j.pixel ? sc_px : sc_dec;
             const float add = j.pixel ? bi_px : (j.src_dir ? 0.f : bi_dec);   // the bias rides on the forward-source half (or the only one)
-#ifdef HB_PROJ_WIDE_EPILOGUE
-            // Variant for A/B runs, not measured yet (tools/build_variants.py wide=-DHB_PROJ_WIDE_EPILOGUE): 32 accumulator
-            // columns per TMEM round trip, two waits per job instead of eight.  The timeline shows this role busy for ~65 of
-            // the encoder's 68 us per chunk with ~0.4 us of MMA time per 0.9 us job, i.e. bound by this loop's serialised
-            // load -> wait -> store round trips; what is left over when the encoder ends is what the decoder waits for.
-#pragma unroll 1
-            for (int c32 = 0; c32 < PROJ_NT; c32 += 32) {
-                float v[32];
-                tc::tmem_ld16(taddr + c32, v);
-                tc::tmem_ld16(taddr + c32 + 16, v + 16);
-                tc::tmem_ld_wait();
+            // 16 accumulator columns (two image columns x 8 windows) per TMEM round trip, the next load in flight while
+            // the current values are scaled and staged
+            {
+                float v[2][16];
+                tc::tmem_ld16(taddr, v[0]);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) stg[(c32 + i) * 128] = fmaf(v[i], sc, add);
-            }
-#else
-#pragma unroll 2
-            for (int c8 = 0; c8 < PROJ_NT; c8 += 8) {       // 8 accumulator columns = the 8 windows of column t0 + c8/8
-                float v[8];
-                tc::tmem_ld8(taddr + c8, v);
-                tc::tmem_ld_wait();
+                for (int c16 = 0; c16 < PROJ_NT / 16; ++c16) {
+                    tc::tmem_ld_wait();
+                    if (c16 + 1 < PROJ_NT / 16) tc::tmem_ld16(taddr + (c16 + 1) * 16, v[(c16 + 1) & 1]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) stg[(c8 + i) * 128] = fmaf(v[i], sc, add);
+                    for (int i = 0; i < 16; ++i) stg[(c16 * 16 + i) * 128] = fmaf(v[c16 & 1][i], sc, add);
+                }
             }
-#endif
             tc::tc_fence_before();
             tc::fence_proxy_async_smem();
             __syncwarp();
@@ -605,21 +606,26 @@ tc_projection_kernel(const ProjArgs a)
 //   * gi' rows of the step are prefetched GI_STAGES steps ahead into shared memory by bulk copies.
 // gi' (from tc_projection_kernel) already contains, per gate row,
 //     r, z rows:  -log2e * (W_i. x + b_i. + b_h.)        n rows:  -2 log2e * (W_in x + b_in)
-// so that   r = 1 / (1 + 2^(gi'_r + acc_r * inv_r)),  z likewise,
-//           n * 2^10 = 2048 / (1 + 2^(gi'_n + r * (acc_n * inv_n + b_hn'))) - 1024     (tanh)
-//           h' = n + z (h - n).
-// Warps 0..15: gate warps; (warp w, lane l) owns hidden unit j = 32 (w%4) + l (== its TMEM lane)
-// for windows [(w/4) N/4, (w/4+1) N/4).  Warp 16: MMA issuer.  Warp 17: gi loader.  Warp 18: y store.
+// With  er = 2^(gi'_r + acc_r inv_r),  ez = 2^(gi'_z + acc_z inv_z),  e = 2^(gi'_n + r (acc_n inv_n + b_hn')):
+//     r = 1 / (1 + er),   z = 1 / (1 + ez),   n = tanh(..) = (1 - e) / (1 + e),   h' = (1 - z) n + z h,
+// and the last two reciprocals are taken as ONE:
+//     h' 2^10 = [2^10 ez (1 - e) + (h 2^10) (1 + e)] / [(1 + e) (1 + ez)]
+// (5 MUFU operations per element and step instead of 6; the exponents are clamped at 2^50 so the products stay finite:
+// 1 / (1 + 2^50) is zero to fp32 precision anyway).
+// GW gate warps; (warp w, lane l) owns hidden unit j = 32 (w%4) + l (== its TMEM lane) for NW = 4 NLIVE / GW windows
+// starting at (w/4) NW.  Warp GW: MMA issuer.  Warp GW+1: gi loader.  Warp GW+2: y store.
+// The gate warps are issue-bound (every scheduler runs GW/4 of them plus at most one helper warp, and a step is ~100
+// instructions per gate warp): the loop below keeps everything that does not change from step to step in registers
+// and the timeline instrumentation is compiled in only with -DHB_TIMELINE.
 // ---------------------------------------------------------------------------------------------
 constexpr int REC_GATE_WARPS = 16;
 constexpr int REC_TC_THREADS = (REC_GATE_WARPS + 3) * 32;
 constexpr int REC_W_COL0 = 128;                   // weight columns start here (accumulators below)
 constexpr int WHH_TMEM_WORDS = 2 * 3 * 128 * 64;  // per direction: [term][gate block][row][k pair]
-// GI2: a stage holds TWO gi' rows per window (the two K-halves of the chunk-loop projection, added by the gate threads)
-template <int N, int NLIVE, bool GI2> __host__ __device__ constexpr int gi_stages() {
-    return GI2 ? (NLIVE <= 8 ? 6 : 3) : (N <= 16 ? 4 : 3);   // N = 32: 3 x 48 KB, 16 live x 2 rows: 3 x 48 KB (227 KB smem limit);
-                                                             // 8 live x 2 rows: 6 x 24 KB (the other roles' traffic delays gi' rows)
-}
+constexpr float EXP2_CLAMP = 50.0f;
+// gi' stages (one step each, NLIVE x 1536 B): 8 live: 6 x 12 KB (the other roles' traffic delays gi' rows in the
+// chunk-loop kernel), 16 live: 4 x 24 KB, 32 live: 3 x 48 KB (227 KB smem limit)
+template <int NLIVE> __host__ __device__ constexpr int gi_stages() { return NLIVE <= 8 ? 6 : (NLIVE <= 16 ? 4 : 3); }
 // h operand image buffers: 4 give the y store three steps to drain, which hides the global-memory round trips of the
 // progress publication (chunk-loop kernel); N = 32 has room for 2 only
 template <int N> __host__ __device__ constexpr int h_buffers() { return N <= 16 ? 4 : 2; }
@@ -627,8 +633,7 @@ constexpr int PUBLISH_LAG = 4;
 
 // One GRU layer as the recurrence role sees it.
 struct RecLayer {
-    const float* gi;               // gi' rows; row of (window b, chunk k, step column t) = b * gi_cols + gi_col0 + k * gi_col_step + t
-    const float* gi_b;             // second addend of gi' (same indexing) or nullptr: the K-halves of the chunk-loop projection
+    const float* gi;               // gi image (see gi_block); the step at column t of chunk k reads column gi_col0 + k * gi_col_step + t
     int gi_cols, gi_col0, gi_col_step;
     const uint32_t* whh_tmem;      // packed fp16 pairs, see whh_word_index
     const float* gate_consts;      // [2 dirs][4][128]: inv_r', inv_z', inv_n', b_hn'  (per unit)
@@ -658,11 +663,62 @@ struct RecArgs {
     int n_wg;                      // existing window groups (flags of groups past it are never raised)
     unsigned long long epoch;
     long long* dbg;
-    int dbg_layer;                 // HB_DEBUG_TIMELINE: which layer's steps are recorded
+    int dbg_layer;                 // -DHB_TIMELINE: which layer's steps are recorded
 };
 
+// W_hh of one direction -> TMEM, spread over `n_warps` gate warps (a multiple of 4).  A warp covers TMEM lanes
+// 32 (w%4)..+31 (thread = gate row); the warps of a lane quarter split the four (hi | lo image) x (k-pair columns 0-31 |
+// 32-63) pieces; 32 words in flight per round trip, two register buffers so that the loads of gate block gb+1 are in
+// flight while block gb is stored.
+// (not inlined: its 64 staging registers would otherwise push the gate loop's state into local memory)
+__device__ __noinline__ void upload_whh(const uint32_t* __restrict__ whh_tmem, const int dir, const uint32_t tmem, const int warp,
+                                           const int lane, const int n_warps)
+{
+    const int q = warp & 3, row = q * 32 + lane;
+    for (int piece = warp >> 2; piece < 4; piece += n_warps >> 2) {
+        const int term = piece & 1, half = piece >> 1;
+        auto fetch = [&](int gb, uint32_t* r) {
+            const uint4* p = reinterpret_cast<const uint4*>(whh_tmem + whh_word_index(dir, term, gb, row, half * 32));
+#pragma unroll
+            for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+        };
+        auto store = [&](int gb, const uint32_t* r) {
+            const uint32_t dst = tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
+            tc::tmem_st16(dst, r);
+            tc::tmem_st16(dst + 16, r + 16);
+        };
+        uint32_t ra0[32], ra1[32];
+        fetch(0, ra0);
+        fetch(1, ra1);
+        store(0, ra0);
+        fetch(2, ra0);
+        store(1, ra1);
+        store(2, ra0);
+    }
+    tc::tmem_st_wait();
+}
+
+// One GRU step of one element, split in the three phases in which the accumulators arrive.  All values in the 2^10
+// scale of the state.
+struct GateR { float c1, c2; };                   // r inv_n,  r b_hn' + gi'_n
+__device__ __forceinline__ GateR gate_r(float acc, float inv_r, float gir, float inv_n, float bhn, float gin) {
+    const float r = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(acc, inv_r, gir)));
+    return GateR{r * inv_n, fmaf(r, bhn, gin)};
+}
+struct GateZ { float q, k; };                     // 1 + ez,  2^10 ez
+__device__ __forceinline__ GateZ gate_z(float acc, float inv_z, float giz) {
+    const float ez = tc::ex2_approx(fminf(fmaf(acc, inv_z, giz), EXP2_CLAMP));
+    return GateZ{1.0f + ez, ez * ACT_SCALE};
+}
+__device__ __forceinline__ float gate_n(float acc, const GateR& gr, const GateZ& gz, float h) {
+    const float e = tc::ex2_approx(fminf(fmaf(acc, gr.c1, gr.c2), EXP2_CLAMP));
+    const float p = 1.0f + e;
+    const float num = fmaf(h, p, fmaf(-e, gz.k, gz.k));           // h (1 + e) + 2^10 ez (1 - e)
+    return num * tc::rcp_approx(p * gz.q);
+}
+
 // NLIVE <= N windows of the N accumulator columns are real: the MMA shape needs N >= 16, but with 8 live windows
-// per CTA a small batch spreads over twice as many SMs and the exposed gate math (MUFU-bound) halves.
+// per CTA a small batch spreads over twice as many SMs and the exposed gate math halves.
 //
 // STACK: the hi and lo images of h are read as ONE B operand, [h_hi (NLIVE rows) | h_lo (NLIVE rows)], so a step needs
 // only the two A terms W_hi and W_lo (48 MMAs instead of 72; the MMA time of a step is set by the instruction count,
@@ -672,27 +728,27 @@ struct RecArgs {
 // do not accumulate into the same tile - the MMAs were no faster and the extra TMEM loads cost 90 cycles per step.)
 //
 // MODE 0: 3-term.  MODE 1: STACK.
-template <int N, int NLIVE, int MODE = 0, bool GI2 = false>
+template <int N, int NLIVE, int MODE = 0, int GW = REC_GATE_WARPS>
 __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem, const int cta_x, const int dir)
 {
     const int64_t B = ra.B;
     const int W = ra.W;
     const int n_layers = ra.n_layers;
     const int n_phases = (ra.n_chunks > 0 ? ra.n_chunks : 1) * n_layers;
-    long long* __restrict__ dbg = ra.dbg;
-#define HB_DBG(role, s, k) do { if (dbg_steps && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
     static_assert(N == 16 || N == 32, "N accumulator columns per gate block (3N must stay below REC_W_COL0)");
     static_assert(NLIVE == N || (N == 16 && NLIVE == 8), "live windows per CTA");
+    static_assert(GW == 8 || GW == 16, "gate warps");
     constexpr bool STACK = MODE >= 1;
     static_assert(!STACK || N == 16, "stacked operand: 3 x 2 NLIVE accumulator columns must stay below REC_W_COL0");
+    constexpr int NTHREADS = (GW + 3) * 32;
     constexpr int NACC = STACK ? 2 * NLIVE : N;              // N of the MMA == accumulator columns per gate block
     constexpr int NBLK = NACC;
-    constexpr int NW = NLIVE / 4;                            // windows per gate thread
+    constexpr int NW = NLIVE * 4 / GW;                       // windows per gate thread
+    static_assert(NW == 2 || NW == 4 || NW == 8, "a gate thread's windows lie in one window group");
     constexpr int NG = NLIVE / WG;                           // live window groups per CTA
     constexpr uint32_t HB_BYTES = (N / WG) * YBLK;           // one h operand image (hi or lo), all N columns
-    static_assert(!GI2 || NLIVE <= 16, "two gi' rows per window: at most 16 live windows fit");
-    constexpr uint32_t GI_STAGE_BYTES = (GI2 ? 2 : 1) * NLIVE * GI_ROW_BYTES;
-    constexpr int GI_STAGES = gi_stages<N, NLIVE, GI2>();
+    constexpr uint32_t GI_STAGE_BYTES = NLIVE * GI_ROW_BYTES;
+    constexpr int GI_STAGES = gi_stages<NLIVE>();
     // h operand images, NBUF buffers: step s reads buffer s % NBUF (h_s) and writes buffer (s+1) % NBUF (h_{s+1}),
     // so the y store of an image has NBUF steps to drain before the buffer is written again
     constexpr int NBUF = h_buffers<N>();
@@ -709,24 +765,31 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     uint64_t* gi_empty = gi_full + GI_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gi_empty + GI_STAGES);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // (tells the compiler the warp index is uniform)
     const int64_t b0 = (int64_t)cta_x * NLIVE;
     const int t_first = dir ? W - 1 : 0, dt = dir ? -1 : 1;
+#ifdef HB_TIMELINE
+    long long* __restrict__ dbg = ra.dbg;
+#define HB_DBG(role, s, k) do { if (dbg_steps && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
+#else
+#define HB_DBG(role, s, k) do { } while (0)
+#endif
 
     tc::pdl_launch_dependents();
     if constexpr (NLIVE < N) {                               // dead accumulator columns: keep their operand rows finite
-        for (uint32_t i = tid; i < 2 * NBUF * HB_BYTES / 16; i += REC_TC_THREADS) reinterpret_cast<int4*>(h_img)[i] = make_int4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < 2 * NBUF * HB_BYTES / 16; i += NTHREADS) reinterpret_cast<int4*>(h_img)[i] = make_int4(0, 0, 0, 0);
         tc::fence_proxy_async_smem();
     }
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) tc::mbar_init(acc_ready + i, 1);
-        tc::mbar_init(h_ready, REC_GATE_WARPS);
-        for (int i = 0; i < NBUF; ++i) { tc::mbar_init(h_free + i, 1); tc::mbar_init(y_ready + i, REC_GATE_WARPS); }
-        for (int i = 0; i < GI_STAGES; ++i) { tc::mbar_init(gi_full + i, 1); tc::mbar_init(gi_empty + i, REC_GATE_WARPS); }
+        tc::mbar_init(h_ready, GW);
+        for (int i = 0; i < NBUF; ++i) { tc::mbar_init(h_free + i, 1); tc::mbar_init(y_ready + i, GW); }
+        for (int i = 0; i < GI_STAGES; ++i) { tc::mbar_init(gi_full + i, 1); tc::mbar_init(gi_empty + i, GW); }
         tc::mbar_fence_init();
     }
     __syncwarp();
-    if (warp == REC_GATE_WARPS) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == GW) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -744,25 +807,26 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     const int chunk = phase / n_layers, li = phase - chunk * n_layers;
     const RecLayer& L = ra.layer[li];
     const float* __restrict__ gi = L.gi;
-    const bool two_rows = GI2 && L.gi_b != nullptr;          // gi' = gi[row] + gi_b[row]
     const int gi_cols = L.gi_cols;
     const int gi_col0 = L.gi_col0 + chunk * L.gi_col_step;
     uint8_t* __restrict__ yimg = L.yimg[chunk & 1];
     const unsigned long long prog_base = ra.epoch + (unsigned long long)chunk * W;
+#ifdef HB_TIMELINE
     const bool dbg_on = dbg != nullptr && cta_x == 0 && dir == 0 && (n_layers == 1 ? li == ra.dbg_layer : chunk == 2);
     const bool dbg_steps = dbg_on && li == ra.dbg_layer;
+#endif
     if (phase > 0) {
         // phase boundary: fresh barriers, then the cross-CTA conditions of this phase
         if (tid == 0) {
             for (int i = 0; i < 3; ++i) { tc::mbar_inval(acc_ready + i); tc::mbar_init(acc_ready + i, 1); }
-            tc::mbar_inval(h_ready); tc::mbar_init(h_ready, REC_GATE_WARPS);
+            tc::mbar_inval(h_ready); tc::mbar_init(h_ready, GW);
             for (int i = 0; i < NBUF; ++i) {
                 tc::mbar_inval(h_free + i); tc::mbar_init(h_free + i, 1);
-                tc::mbar_inval(y_ready + i); tc::mbar_init(y_ready + i, REC_GATE_WARPS);
+                tc::mbar_inval(y_ready + i); tc::mbar_init(y_ready + i, GW);
             }
             for (int i = 0; i < GI_STAGES; ++i) {
                 tc::mbar_inval(gi_full + i); tc::mbar_init(gi_full + i, 1);
-                tc::mbar_inval(gi_empty + i); tc::mbar_init(gi_empty + i, REC_GATE_WARPS);
+                tc::mbar_inval(gi_empty + i); tc::mbar_init(gi_empty + i, GW);
             }
             tc::mbar_fence_init();
         }
@@ -778,24 +842,28 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         }
         __syncthreads();
     }
+#ifdef HB_TIMELINE
     if (dbg && n_layers > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (li * 64 + chunk) * 2] = (long long)globaltimer_ns();
     // (a clock read right after bar.sync records the ARRIVAL at the barrier - the block is deferred to the next access
     // of barrier-protected state - so the stamps read a shared word first)
 #define HB_STAMP(k) do { if (dbg_on && n_layers > 1 && lane == 0) { \
         uint32_t probe; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(probe) : "r"(tc::smem_u32(tmem_slot)) : "memory"); \
         dbg[6144 + li * 8 + (k)] = clock64() + (probe & 0); } } while (0)
+#else
+#define HB_STAMP(k) do { } while (0)
+#endif
     if (warp == 0) HB_STAMP(0);                              // phase start (barriers fresh, cross-CTA conditions met)
 
-    if (warp == REC_GATE_WARPS + 1) {
+    if (warp == GW + 1) {
         // ===================== gi loader: bulk copies, GI_STAGES steps ahead =====================
         // (the first GI_STAGES rows are requested before the phase's start barrier: the stages are free and the
         // prefetch then overlaps the W_hh upload of the gate warps)
         if (phase == 0) tc::pdl_grid_dependency_wait();      // gi' comes from an upstream kernel
         bool synced = false;
-        // lane g < NG fetches group g's block of the step (all three gates, 12 KB); lanes 16.. the second addend's
-        const int lane2 = lane - 16;
-        const float* src0 = gi + gi_block(b0 / WG + min(lane, NG - 1), gi_cols, gi_col0, dir * 3);
-        const float* src0b = two_rows ? L.gi_b + gi_block(b0 / WG + min(max(lane2, 0), NG - 1), gi_cols, gi_col0, dir * 3) : nullptr;
+        // lane 3 g + gate fetches that gate block (4 KB) of group g's column
+        const int lg = min(lane / 3, NG - 1), lgate = lane % 3;
+        const float* src0 = gi + gi_block(b0 / WG + lg, gi_cols, gi_col0, dir * 3 + lgate);
+        uint8_t* dst0 = gi_s + lg * GI_GRP_BYTES + lgate * GI_BLK_BYTES;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % GI_STAGES;
             if (s == GI_STAGES) { __syncthreads(); synced = true; }
@@ -810,16 +878,12 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 __syncwarp();
             }
             if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
-            if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, (two_rows ? 2u : 1u) * NG * GI_GRP_BYTES);
+            if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, NG * GI_GRP_BYTES);
             __syncwarp();
-            if (lane < NG) tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + lane * GI_GRP_BYTES, src0 + (int64_t)t * (6 * GI_BLK_FLOATS), GI_GRP_BYTES, gi_full + stage);
-            if constexpr (GI2) {
-                if (two_rows && lane2 >= 0 && lane2 < NG)
-                    tc::bulk_g2s(gi_s + stage * GI_STAGE_BYTES + (NG + lane2) * GI_GRP_BYTES, src0b + (int64_t)t * (6 * GI_BLK_FLOATS), GI_GRP_BYTES, gi_full + stage);
-            }
+            if (lane < 3 * NG) tc::bulk_g2s(dst0 + stage * GI_STAGE_BYTES, src0 + (int64_t)t * GI_BLK_FLOATS, GI_BLK_BYTES, gi_full + stage);
         }
         if (!synced) __syncthreads();
-    } else if (warp == REC_GATE_WARPS + 2) {
+    } else if (warp == GW + 2) {
         // ===================== y store: the h image of step s is the layer output at column t_s ====
         if (phase == 0) tc::pdl_grid_dependency_wait();      // yimg may still be read by an upstream kernel
         __syncthreads();
@@ -849,13 +913,13 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         __syncwarp();
         if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)W);
         HB_STAMP(4);                                         // all columns published
-    } else if (warp == REC_GATE_WARPS) {
+    } else if (warp == GW) {
         // ===================== MMA issuer =====================
         // An M=128, N=16, K=16 MMA occupies the tensor pipe ~9.6 cycles (tools/mma_rate.cu), so the 48 MMAs of a step are
-        // ~460 cycles plus ~250 of pipeline fill and commit -> wake-up latency (HB_DEBUG_TIMELINE).  A second issuer warp,
+        // ~460 cycles plus ~250 of pipeline fill and commit -> wake-up latency (-DHB_TIMELINE).  A second issuer warp,
         // an issue order rotating over the gate blocks, and starting the r block quarter by quarter as the gate warps
         // publish h (one h_ready barrier per TMEM lane quarter: +85 cycles per step, the extra waits cost more than the
-        // overlap gives) were all slower; per-block commits let the gate warps overlap the r and z sigmoids with the
+        // overlap gives) were all slower; per-block commits let the gate warps overlap the r and z phases with the
         // remaining MMAs.
         __syncthreads();                                     // weights in TMEM, h_0 in smem
         tc::tc_fence_after();
@@ -901,31 +965,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         }
     } else {
         // ===================== gate warps =====================
-        if (phase == 0 || n_layers > 1) {
-            // W_hh of this phase's layer -> TMEM.  Warp w covers TMEM lanes 32 (w%4)..+31 (thread = gate row j); the four
-            // warps of a lane quarter split (hi | lo image) x (k-pair columns 0-31 | 32-63); 32 words in flight per round
-            // trip.  (All MMAs of the previous phase have completed: every gate warp waited for its last accumulator.)
-            // Two register buffers: the loads of gate block gb+1 are in flight while block gb is stored.
-            const int term = (warp >> 2) & 1, half = warp >> 3;
-            auto fetch = [&](int gb, uint32_t* r) {
-                const uint4* p = reinterpret_cast<const uint4*>(L.whh_tmem + whh_word_index(dir, term, gb, j, half * 32));
-#pragma unroll
-                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-            };
-            auto store = [&](int gb, const uint32_t* r) {
-                const uint32_t dst = tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
-                tc::tmem_st16(dst, r);
-                tc::tmem_st16(dst + 16, r + 16);
-            };
-            uint32_t ra0[32], ra1[32];
-            fetch(0, ra0);
-            fetch(1, ra1);
-            store(0, ra0);
-            fetch(2, ra0);
-            store(1, ra1);
-            store(2, ra0);
-            tc::tmem_st_wait();
-        }
+        if (phase == 0 || n_layers > 1)
+            // W_hh of this phase's layer -> TMEM.  (All MMAs of the previous phase have completed: every gate warp waited
+            // for its last accumulator.)
+            upload_whh(L.whh_tmem, dir, tmem, warp, lane, GW);
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
         const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
         uint32_t h_off[NW];
@@ -949,7 +992,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         tc::tc_fence_before();
         __syncthreads();                                     // pairs with the other roles' barrier
 
+        // everything below that does not change from step to step stays in registers
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
+        // stage: [group][gate][window in group][unit]; this thread's NW windows lie in one group
+        const float* gs0 = reinterpret_cast<const float*>(gi_s) + (win0 / WG) * (3 * GI_BLK_FLOATS) + (win0 % WG) * H + j;
         auto load_acc = [](uint32_t addr, float* a) {
             tc::tmem_ld_n<NW>(addr, a);
             if constexpr (STACK) {
@@ -962,67 +1008,66 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 tc::tmem_ld_wait();
             }
         };
+        int stage = 0;
+        uint32_t gi_par = 0;
         for (int s = 0; s < W; ++s) {
-            const int stage = s % GI_STAGES;
             const uint32_t par = (uint32_t)(s & 1);
+            const int nb = (s + 1) % NBUF;
+#ifdef HB_TIMELINE
+            const int drole = warp == 0 ? 1 : (warp == GW - 1 ? 2 : 3);
+#endif
+            tc::mbar_wait(gi_full + stage, gi_par);
+            // the buffer h_{s+1} goes to: its y store of NBUF steps ago has drained long since - waited for HERE, where
+            // the warp would idle anyway, not between the z and n phases
+            if (s >= NBUF) tc::mbar_wait(h_free + nb, (uint32_t)(((s - NBUF) / NBUF) & 1));
+            HB_DBG(drole, s, 0);
             float gir[NW], giz[NW], gin[NW];
-            const int drole = warp == 0 ? 1 : (warp == 15 ? 2 : 3);
-            tc::mbar_wait(gi_full + stage, (uint32_t)((s / GI_STAGES) & 1));
-            if (drole < 3) HB_DBG(drole, s, 0);
             {
-                // stage: [addend][group][gate][window in group][unit]; this thread's NW windows lie in one group
-                const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + (win0 / WG) * (3 * GI_BLK_FLOATS) + (win0 % WG) * H + j;
+                const float* gs = gs0 + stage * (GI_STAGE_BYTES / 4);
 #pragma unroll
                 for (int i = 0; i < NW; ++i) { gir[i] = gs[i * H]; giz[i] = gs[GI_BLK_FLOATS + i * H]; gin[i] = gs[2 * GI_BLK_FLOATS + i * H]; }
-                if constexpr (GI2) {
-                    if (two_rows) {
-                        const float* gb = gs + NG * (3 * GI_BLK_FLOATS);
-#pragma unroll
-                        for (int i = 0; i < NW; ++i) { gir[i] += gb[i * H]; giz[i] += gb[GI_BLK_FLOATS + i * H]; gin[i] += gb[2 * GI_BLK_FLOATS + i * H]; }
-                    }
-                }
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(gi_empty + stage);
-            float r[NW], z[NW], a[NW];
+            if (++stage == GI_STAGES) { stage = 0; gi_par ^= 1u; }
+            float a[NW];
+            GateR gr[NW];
+            GateZ gz[NW];
             tc::mbar_wait(acc_ready + 0, par);
-            if (drole < 3) HB_DBG(drole, s, 1);
+            HB_DBG(drole, s, 1);
             tc::tc_fence_after();
             load_acc(taddr, a);
 #pragma unroll
-            for (int i = 0; i < NW; ++i) r[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_r, gir[i])));
+            for (int i = 0; i < NW; ++i) gr[i] = gate_r(a[i], inv_r, gir[i], inv_n, bhn, gin[i]);
             tc::mbar_wait(acc_ready + 1, par);
-            if (drole < 3) HB_DBG(drole, s, 2);
+            HB_DBG(drole, s, 2);
             tc::tc_fence_after();
             load_acc(taddr + NBLK, a);
 #pragma unroll
-            for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, giz[i])));
-            uint8_t* h_hi = h_img + (((s + 1) % NBUF) * 2) * HB_BYTES;         // image of h_{s+1}
+            for (int i = 0; i < NW; ++i) gz[i] = gate_z(a[i], inv_z, giz[i]);
+            uint8_t* h_hi = h_img + (nb * 2) * HB_BYTES;     // image of h_{s+1}
             uint8_t* h_lo = h_hi + HB_BYTES;
-            if (s >= NBUF) tc::mbar_wait(h_free + ((s + 1) % NBUF), (uint32_t)(((s - NBUF) / NBUF) & 1));   // its store of step s-NBUF has drained
             tc::mbar_wait(acc_ready + 2, par);
-            if (drole < 3) HB_DBG(drole, s, 3);
+            HB_DBG(drole, s, 3);
             tc::tc_fence_after();
             load_acc(taddr + 2 * NBLK, a);
-            if (drole < 3) HB_DBG(drole, s, 4);
+            HB_DBG(drole, s, 4);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
                 // (2^x as a degree-7 polynomial on the FMA pipe instead of MUFU.EX2 was measured: +50 cycles per step)
-                const float e = tc::ex2_approx(fmaf(r[i], fmaf(a[i], inv_n, bhn), gin[i]));
-                const float n = fmaf(2.0f * ACT_SCALE, tc::rcp_approx(1.0f + e), -ACT_SCALE);   // tanh * 2^10
-                const float hn = fmaf(z[i], h_own[i] - n, n);                                   // (1 - z) n + z h
+                const float hn = gate_n(a[i], gr[i], gz[i], h_own[i]);
                 h_own[i] = hn;
                 __half hi, lo;
                 tc::split_f16(hn, hi, lo);
                 *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
                 *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
             }
-            if (drole < 3) HB_DBG(drole, s, 5);
+            HB_DBG(drole, s, 5);
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + ((s + 1) % NBUF)); }
-            if (drole < 3) HB_DBG(drole, s, 6);
+            if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + nb); }
+            HB_DBG(drole, s, 6);
         }
         if (warp == 0) HB_STAMP(2);                          // last step done
         if (phase == n_phases - 1 && ra.h_out != nullptr) {
@@ -1035,10 +1080,12 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     __syncthreads();                                         // phase end: every role is done with the barriers
     if (warp == 0) HB_STAMP(5);
 #undef HB_STAMP
+#ifdef HB_TIMELINE
     if (dbg && n_layers > 1 && cta_x == 0 && dir == 0 && tid == 0) dbg[4096 + (li * 64 + chunk) * 2 + 1] = (long long)globaltimer_ns();
+#endif
     }   // phase loop
 #undef HB_DBG
-    if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
+    if (warp == GW) tc::tmem_dealloc(tmem, 512);
 }
 
 template <int N, int NLIVE, int MODE>
@@ -1118,8 +1165,10 @@ tc_recurrence2_kernel(const RecArgs ra)
         // ===================== gi' loader: both tiles, ST steps ahead =====================
         tc::pdl_grid_dependency_wait();
         bool synced = false;
-        const int tile_l = lane >> 3, g_l = lane & 7;       // lanes [8 tile, 8 tile + NG) fetch the groups of a tile
-        const float* src0 = L.gi + gi_block(b0 / WG + min(tile_l, 1) * NG + min(g_l, NG - 1), L.gi_cols, L.gi_col0, dir * 3);
+        // lanes [8 tile + 3 g, + 3): the three gate blocks (4 KB each) of group g of a tile
+        const int tile_l = lane >> 3, g_l = min((lane & 7) / 3, NG - 1), gate_l = (lane & 7) % 3;
+        const bool loads = tile_l < 2 && (lane & 7) < 3 * NG;
+        const float* src0 = L.gi + gi_block(b0 / WG + min(tile_l, 1) * NG + g_l, L.gi_cols, L.gi_col0, dir * 3 + gate_l);
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % ST;
             if (s == ST) { __syncthreads(); synced = true; }
@@ -1128,8 +1177,9 @@ tc_recurrence2_kernel(const RecArgs ra)
                 if (lane == 0) tc::mbar_arrive_expect_tx(gi_full(tile) + stage, NG * GI_GRP_BYTES);
             }
             __syncwarp();
-            if (tile_l < 2 && g_l < NG)
-                tc::bulk_g2s(gi_of(tile_l) + stage * GI_STAGE_BYTES + g_l * GI_GRP_BYTES, src0 + (int64_t)t * (6 * GI_BLK_FLOATS), GI_GRP_BYTES, gi_full(tile_l) + stage);
+            if (loads)
+                tc::bulk_g2s(gi_of(tile_l) + stage * GI_STAGE_BYTES + g_l * GI_GRP_BYTES + gate_l * GI_BLK_BYTES, src0 + (int64_t)t * GI_BLK_FLOATS,
+                             GI_BLK_BYTES, gi_full(tile_l) + stage);
         }
         if (!synced) __syncthreads();
     } else if (warp == REC_GATE_WARPS + 2) {
@@ -1195,22 +1245,7 @@ tc_recurrence2_kernel(const RecArgs ra)
         // ===================== gate warps =====================
         const int tile = warp / GW, wi = warp % GW;
         const int q = wi & 3, j = q * 32 + lane, win0 = (wi >> 2) * NW;
-        {   // W_hh -> TMEM, split over all 16 gate warps as in recurrence_role
-            const int wq = warp & 3, wj = wq * 32 + lane, term = (warp >> 2) & 1, half = warp >> 3;
-            auto fetch = [&](int gb, uint32_t* r) {
-                const uint4* p = reinterpret_cast<const uint4*>(L.whh_tmem + whh_word_index(dir, term, gb, wj, half * 32));
-#pragma unroll
-                for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-            };
-            auto store = [&](int gb, const uint32_t* r) {
-                const uint32_t dst = tmem + ((uint32_t)(wq * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
-                tc::tmem_st16(dst, r);
-                tc::tmem_st16(dst + 16, r + 16);
-            };
-            uint32_t ra0[32], ra1[32];
-            fetch(0, ra0); fetch(1, ra1); store(0, ra0); fetch(2, ra0); store(1, ra1); store(2, ra0);
-            tc::tmem_st_wait();
-        }
+        upload_whh(L.whh_tmem, dir, tmem, warp, lane, REC_GATE_WARPS);   // W_hh -> TMEM, split over all gate warps
         uint8_t* h_img = h_img_of(tile);
         const uint8_t* gi_s = gi_of(tile);
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
@@ -1381,13 +1416,18 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
     const uint32_t tmem = *tmem_slot;
     const int tiles_t = (W + 15) >> 4;
     int chunk; int64_t wg; int t0;
-    // HB_DEBUG_TIMELINE: worker 0 adds up the cycles each role spends at its wait points (slots 7300 + 8 role + k)
+    // -DHB_TIMELINE: worker 0 adds up the cycles each role spends at its wait points (slots 7300 + 8 role + k)
+#ifdef HB_TIMELINE
     const bool acct = a.dbg != nullptr && worker == 0 && lane == 0;
     long long t_wait[4] = {0, 0, 0, 0};
     const long long t_role0 = acct ? clock64() : 0;
-#define HB_TIMED(k, stmt) do { const long long t_ = acct ? clock64() : 0; stmt; if (acct) t_wait[k] += clock64() - t_; } while (0)
+#define HB_TIMED(k, ...) do { const long long t_ = acct ? clock64() : 0; __VA_ARGS__; if (acct) t_wait[k] += clock64() - t_; } while (0)
 #define HB_ROLE_REPORT(role) do { if (acct) { for (int k_ = 0; k_ < 4; ++k_) a.dbg[7300 + 8 * (role) + k_] = t_wait[k_]; \
                                               a.dbg[7300 + 8 * (role) + 4] = clock64() - t_role0; } } while (0)
+#else
+#define HB_TIMED(k, ...) do { __VA_ARGS__; } while (0)
+#define HB_ROLE_REPORT(role) do { } while (0)
+#endif
 
     if (warp == 5) {
         for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
@@ -1453,7 +1493,9 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(acc_empty);
+#ifdef HB_TIMELINE
             const long long t_math = acct ? clock64() : 0;
+#endif
             if (t < W && b < B) {
                 float mb = -INFINITY, mr = -INFINITY;
 #pragma unroll
@@ -1512,13 +1554,17 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                 for (int c = 0; c < NRLE; ++c) pr[c] = old[NBASE + c] + v[NBASE + c] / sr;
                 }
             }
+#ifdef HB_TIMELINE
             if (acct) t_wait[2] += clock64() - t_math;
+#endif
             if (a.heads_done != nullptr && last_of_wg) {     // one fence per (chunk, window group), not per tile
                 HB_TIMED(1, __threadfence());
                 __syncwarp();
                 if (lane == 0) tc::red_release_gpu_add(a.heads_done + wg, (unsigned long long)tiles_t);
             }
+#ifdef HB_TIMELINE
             if (a.dbg != nullptr && worker == 0 && tid == 0) a.dbg[7100 + chunk] = (long long)globaltimer_ns();
+#endif
         }
         if (warp == 0) HB_ROLE_REPORT(2);
     }
@@ -1550,16 +1596,17 @@ tc_heads_kernel(const HeadsArgs a)
 // 100 encoder steps + the edge tiles of the projection + 100 decoder steps, with no launch boundary in between.
 // Launched as clusters of 2 CTAs: the projection role pairs gate blocks (2b, 2b+1) and multicasts activation tiles.
 // ---------------------------------------------------------------------------------------------
-template <int N, int NLIVE, int MODE>
-__global__ void __launch_bounds__(REC_TC_THREADS, 1)
+template <int N, int NLIVE, int MODE, int GW>
+__global__ void __launch_bounds__((GW + 3) * 32, 1)
 tc_chunkloop_kernel(const RecArgs rec, const ProjArgs proj, const HeadsArgs heads,
                     const int rec_ctas, const int proj_workers, const int heads_workers)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem_all = tc::align_smem_1024(smem_raw);
     const int bid = (int)blockIdx.x;
+    static_assert((GW + 3) * 32 >= PROJ_THREADS && (GW + 3) * 32 >= HEADS_THREADS, "the block must hold every role");
     if (bid < 2 * rec_ctas) {
-        recurrence_role<N, NLIVE, MODE, true>(rec, smem_all, bid >> 1, bid & 1);
+        recurrence_role<N, NLIVE, MODE, GW>(rec, smem_all, bid >> 1, bid & 1);
     } else if (bid < 2 * rec_ctas + 6 * proj_workers) {
         if (threadIdx.x >= PROJ_THREADS) {                   // spare warps only keep the pair's cluster barriers aligned
             if (proj.pair) { tc::cluster_sync_all(); tc::cluster_sync_all(); }
@@ -1598,6 +1645,7 @@ struct TensorTuning {
     bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
     bool pingpong = true;       // HB_NO_PINGPONG: one window tile per recurrence CTA in the per-chunk kernels of large batches
     bool cooperative = true;    // HB_NO_COOPERATIVE: chunk-loop kernel launched without the cooperative attribute
+    int gate_warps = 16;        // HB_GATE_WARPS = 8 | 16: gate warps of the chunk-loop kernel's recurrence role (4 or 2 windows per thread at 8-window tiles)
     static TensorTuning from_env() {
         TensorTuning t;
         t.pdl = getenv("HB_NO_PDL") == nullptr;
@@ -1608,6 +1656,7 @@ struct TensorTuning {
         t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
         t.pingpong = getenv("HB_NO_PINGPONG") == nullptr;
         t.cooperative = getenv("HB_NO_COOPERATIVE") == nullptr;
+        if (const char* v = getenv("HB_GATE_WARPS")) { if (atoi(v) == 8) t.gate_warps = 8; }
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
             const int n = atoi(v);
             if (n == 8 || n == 16 || n == 32) t.windows_per_cta = n;
@@ -1651,7 +1700,6 @@ struct TensorEngine {
 struct TensorWorkspace {
     float* gi_enc;      // [Bp, enc_cols, 768]  encoder projections of every image column, computed once per batch
     float* gi;          // [Bp, W, 768]         decoder projections of the current chunk
-    float* gi_b;        // [Bp, W, 768]         chunk-loop kernel: the reverse-source K-half (gi holds the forward-source half)
     uint8_t* yimg1;
     uint8_t* yimg2[2];  // double buffered: heads(k) runs beside the encoder of chunk k+1
     __half* ximg;
@@ -1678,7 +1726,6 @@ inline TensorWorkspace tensor_carve(void* base, int64_t B, int T, int W, int Kp,
     const size_t Wp = (size_t)std::max(W, 0);
     ws.gi_enc = reinterpret_cast<float*>(take(Bp * (size_t)enc_cols * 2 * G * sizeof(float)));
     ws.gi = reinterpret_cast<float*>(take(Bp * Wp * 2 * G * sizeof(float)));
-    ws.gi_b = reinterpret_cast<float*>(take(Bp * Wp * 2 * G * sizeof(float)));
     ws.yimg1 = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
     ws.yimg2[0] = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
     ws.yimg2[1] = reinterpret_cast<uint8_t*>(take(Bp / WG * Wp * 2 * YROW));
@@ -1821,11 +1868,9 @@ inline void free_layer(TensorLayer* L) {
 }
 
 // (+1024: the kernels align their shared memory to the swizzle atom themselves)
-inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 2 * PROJ_STG_BYTES + 256 + 1024; }
-template <int N>
-constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<N, N, false>() * N * GI_ROW_BYTES + 512 + 1024; }
-template <int NLIVE>   // chunk-loop kernel (N = 16, two gi' rows per window)
-constexpr size_t recurrence_smem_gi2() { return (size_t)2 * h_buffers<16>() * (16 / WG) * YBLK + (size_t)gi_stages<16, NLIVE, true>() * 2 * NLIVE * GI_ROW_BYTES + 512 + 1024; }
+inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 2 * PROJ_STG_BYTES + 256 + PROJ_TILE_SLOTS * 4 + 1024; }
+template <int N, int NLIVE = N>
+constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<NLIVE>() * NLIVE * GI_ROW_BYTES + 512 + 1024; }
 constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128 + 1024; }
 
 }  // namespace detail
@@ -1885,20 +1930,22 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         };
         set((const void*)tc_projection_kernel<false>, detail::projection_smem(e->enc.Kp * 16, 1));
         set((const void*)tc_projection_kernel<true>, detail::projection_smem(YROW, 2));
-        set((const void*)tc_recurrence_kernel<16, 8, 0>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 8, 0>, detail::recurrence_smem<16, 8>());
         set((const void*)tc_recurrence_kernel<16, 16, 0>, detail::recurrence_smem<16>());
-        set((const void*)tc_recurrence_kernel<16, 8, 1>, detail::recurrence_smem<16>());
+        set((const void*)tc_recurrence_kernel<16, 8, 1>, detail::recurrence_smem<16, 8>());
         set((const void*)tc_recurrence_kernel<16, 16, 1>, detail::recurrence_smem<16>());
         set((const void*)tc_recurrence_kernel<32, 32, 0>, detail::recurrence_smem<32>());
         set((const void*)tc_recurrence2_kernel<8, 1>, recurrence2_smem<8>());
         set((const void*)tc_recurrence2_kernel<16, 0>, recurrence2_smem<16>());
         set((const void*)tc_heads_kernel, detail::heads_smem());
-        const size_t loop8 = std::max({detail::recurrence_smem_gi2<8>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
-        const size_t loop16 = std::max({detail::recurrence_smem_gi2<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
-        set((const void*)tc_chunkloop_kernel<16, 8, 1>, loop8);
-        set((const void*)tc_chunkloop_kernel<16, 8, 0>, loop8);
-        set((const void*)tc_chunkloop_kernel<16, 16, 1>, loop16);
-        set((const void*)tc_chunkloop_kernel<16, 16, 0>, loop16);
+        const size_t loop8 = std::max({detail::recurrence_smem<16, 8>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
+        const size_t loop16 = std::max({detail::recurrence_smem<16>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
+        set((const void*)tc_chunkloop_kernel<16, 8, 1, 16>, loop8);
+        set((const void*)tc_chunkloop_kernel<16, 8, 1, 8>, loop8);
+        set((const void*)tc_chunkloop_kernel<16, 8, 0, 16>, loop8);
+        set((const void*)tc_chunkloop_kernel<16, 16, 1, 16>, loop16);
+        set((const void*)tc_chunkloop_kernel<16, 16, 1, 8>, loop16);
+        set((const void*)tc_chunkloop_kernel<16, 16, 0, 16>, loop16);
         // the chunk-loop kernel's CTAs wait for each other: how many of them fit on the chip at once (one per SM here, but
         // MPS limits, other resident kernels' reservations or a smaller part change that; the plan respects the answer)
         auto resident = [&](const void* fn, size_t bytes, int* out) {
@@ -1906,8 +1953,8 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
             if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, REC_TC_THREADS, bytes);
             *out = per_sm * sm_count;
         };
-        resident((const void*)tc_chunkloop_kernel<16, 8, 1>, loop8, &e->loop_max_ctas8);
-        resident((const void*)tc_chunkloop_kernel<16, 16, 1>, loop16, &e->loop_max_ctas16);
+        resident((const void*)tc_chunkloop_kernel<16, 8, 1, 16>, loop8, &e->loop_max_ctas8);
+        resident((const void*)tc_chunkloop_kernel<16, 16, 1, 16>, loop16, &e->loop_max_ctas16);
         // job table of the chunk-loop projection role, sized once for the largest batch the kernel takes (one 8-window
         // group per two SMs) and chunks of up to 1024 columns; anything larger runs as per-chunk launches
         e->proj_jobs_capacity = (size_t)(sm_count / 2 + 1) * (2 * 128 + PX_R);
@@ -2045,10 +2092,16 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                                        dim3(1, pair_mode ? 2 : 1, 1), pe));
         launches += 2;
     }
+    // Timeline instrumentation exists only in the -DHB_TIMELINE build of the library (tools/build_variants.py
+    // timeline=-DHB_TIMELINE, selected with HB_LIB=...); HB_DEBUG_TIMELINE=1 | e then records decoder | encoder steps.
     static long long* dbg_buf = nullptr;
+#ifdef HB_TIMELINE
     static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
     static const bool dbg_enc = dbg_on && getenv("HB_DEBUG_TIMELINE")[0] == 'e';
     if (dbg_on && !dbg_buf) { cudaMalloc(&dbg_buf, 8192 * sizeof(long long)); cudaMemset(dbg_buf, 0, 8192 * sizeof(long long)); }
+#else
+    constexpr bool dbg_on = false, dbg_enc = false;
+#endif
     // decoder projection arguments (the same for every chunk)
     ProjArgs pd{};
     pd.in_base = ws.yimg1; pd.in_wg_stride = (int64_t)W * 4 * YBLK; pd.in_dir_stride = (int64_t)W * 2 * YBLK; pd.in_part_stride = (int64_t)W * YBLK;
@@ -2143,7 +2196,6 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         ra.layer[0] = layer_args(e->enc, ws.gi_enc, enc_cols, 0, J, ws.yimg1, ws.yimg1);
         ra.layer[0].progress = enc_prog; ra.layer[0].consumed_flags = tile_flags;
         ra.layer[1] = layer_args(e->dec, ws.gi, W, 0, 0, ws.yimg2[0], ws.yimg2[1]);
-        ra.layer[1].gi_b = ws.gi_b;
         ra.layer[1].progress = dec_prog; ra.layer[1].tile_flags = tile_flags;
         ra.layer[1].flag_tiles = tiles8; ra.layer[1].flag_abs = 0; ra.layer[1].flag_skip_tiles = 0;
         ra.layer[1].flag_need_base = 0; ra.layer[1].flag_need_per_chunk = 6;
@@ -2158,7 +2210,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         pp.progress = enc_prog; pp.epoch = 0; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
         pp.pair = 0;          // every CTA of the role picks its own job order (see the loader): no shared tiles
         pp.dbg = dbg_buf;
-        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets; pp.gi_b = ws.gi_b;
+        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets;
         if (pixels_in_loop) {
             pp.px.ximg = reinterpret_cast<const uint8_t*>(ws.ximg); pp.px.wg_stride = (int64_t)T * xblk; pp.px.blk_bytes = xblk; pp.px.Kp = e->enc.Kp;
             pp.px.w_tmem = e->enc.wih_tmem; pp.px.scale_row = e->enc.scale_row; pp.px.bias_row = e->enc.bias_row;
@@ -2170,8 +2222,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         hp.progress = dec_prog; hp.rec_n = plan.tile; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
         hp.dbg = dbg_buf;
         const dim3 grid(2 * plan.rec_ctas + 6 * plan.proj_workers + plan.heads_workers), cluster(1, 1, 1);
-        const size_t smem = std::max({plan.tile == 8 ? detail::recurrence_smem_gi2<8>() : detail::recurrence_smem_gi2<16>(),
+        const size_t smem = std::max({plan.tile == 8 ? detail::recurrence_smem<16, 8>() : detail::recurrence_smem<16>(),
                                       detail::projection_smem(YROW, 2), detail::heads_smem()});
+        const int gw = e->tune.stack ? e->tune.gate_warps : 16;
         // Cooperative launch: the CTAs of this kernel spin on each other's counters, so the grid must be resident as a
         // whole - with the attribute the launch waits until it can be (another handle's kernel, or any other work on the
         // device, cannot leave it half scheduled) instead of relying on an idle chip.
@@ -2180,18 +2233,25 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             const size_t slot = dominant_begin();
             const bool coop = e->tune.cooperative;
             bool use_pdl = pdl && !e->time_recurrence && (!coop || e->coop_with_pdl);
-            le = detail::launch_ex(kernel, grid, dim3(REC_TC_THREADS), smem, s, use_pdl, cluster, coop,
+            le = detail::launch_ex(kernel, grid, dim3((gw + 3) * 32), smem, s, use_pdl, cluster, coop,
                                    ra, pp, hp, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
             if (le != cudaSuccess && coop && use_pdl) {       // some drivers refuse the two attributes together
                 cudaGetLastError();
                 e->coop_with_pdl = false;
-                le = detail::launch_ex(kernel, grid, dim3(REC_TC_THREADS), smem, s, false, cluster, coop,
+                le = detail::launch_ex(kernel, grid, dim3((gw + 3) * 32), smem, s, false, cluster, coop,
                                        ra, pp, hp, plan.rec_ctas, plan.proj_workers, plan.heads_workers);
             }
             dominant_end(slot);
         };
-        if (plan.tile == 8) { if (e->tune.stack) go(tc_chunkloop_kernel<16, 8, 1>); else go(tc_chunkloop_kernel<16, 8, 0>); }
-        else { if (e->tune.stack) go(tc_chunkloop_kernel<16, 16, 1>); else go(tc_chunkloop_kernel<16, 16, 0>); }
+        if (plan.tile == 8) {
+            if (!e->tune.stack) go(tc_chunkloop_kernel<16, 8, 0, 16>);
+            else if (gw == 8) go(tc_chunkloop_kernel<16, 8, 1, 8>);
+            else go(tc_chunkloop_kernel<16, 8, 1, 16>);
+        } else {
+            if (!e->tune.stack) go(tc_chunkloop_kernel<16, 16, 0, 16>);
+            else if (gw == 8) go(tc_chunkloop_kernel<16, 16, 1, 8>);
+            else go(tc_chunkloop_kernel<16, 16, 1, 16>);
+        }
         TE_CUDA(le);
         launches += 1;
     }
@@ -2222,7 +2282,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             detail::launch(tc_recurrence2_kernel<16, 0>, grid_rec, dim3(REC_TC_THREADS), recurrence2_smem<16>(), s, use_pdl, ra);
         else if (nrec == 8)
             detail::launch(stack ? tc_recurrence_kernel<16, 8, 1> : tc_recurrence_kernel<16, 8, 0>, grid_rec, dim3(REC_TC_THREADS),
-                           detail::recurrence_smem<16>(), s, use_pdl, ra);
+                           detail::recurrence_smem<16, 8>(), s, use_pdl, ra);
         else if (nrec == 16)
             detail::launch(stack ? tc_recurrence_kernel<16, 16, 1> : tc_recurrence_kernel<16, 16, 0>, grid_rec, dim3(REC_TC_THREADS),
                            detail::recurrence_smem<16>(), s, use_pdl, ra);
