@@ -123,6 +123,7 @@ constexpr int PROJ_STAGES = 2;                    // full-K tiles; the K-half jo
 constexpr int PROJ_PUBLISH_BATCH = 8;
 constexpr int PROJ_URGENT_BATCH = 3;              // flags of the jobs the decoder is waiting for go out in batches of three
 constexpr int PROJ_TILE_SLOTS = 2048;             // chunk-loop kernel: tiles one worker may own (first-half bookkeeping of the store warp)
+constexpr int PROJ_TABLE_MAX = 1024;              // chunk-loop kernel: jobs of one worker per chunk (the loader keeps the list in shared memory)
 constexpr int PROJ_W_COL0 = 128;
 
 // Encoder input projection inside the chunk-loop kernel ("pixel jobs"): while the encoder of chunk k runs, the projection
@@ -231,6 +232,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     // chunk-loop kernel: the loader decides the job order at run time (see below) and passes it on through this ring
     volatile int* job_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [16] >= jobs in flight between loader and store warp
     volatile int* first_it = job_ring + 16;                  // [PROJ_TILE_SLOTS], store warp only: job that stored a tile's first K-half, or -1
+    volatile int* job_tab = first_it + PROJ_TILE_SLOTS;      // [PROJ_TABLE_MAX], loader only: this chunk's job list
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kwords = Kp >> 1;
@@ -325,16 +327,22 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const int n_px = split ? px_count(chunk) : 0;
         const int n_jobs = split ? n_px + n_dec : n_table;
         const int px_tile0 = pixels ? px_done(a, chunk) : 0;
+        // this chunk's job list -> shared memory (coalesced), pixel entries made absolute: the per-job decisions below then
+        // depend on one global load (the progress counter, requested a job ahead), not on a chain of them
+        if (split) {
+            __syncwarp();
+            for (int i = lane; i < n_jobs; i += 32) {
+                int e = table_at(i, n_px);
+                if ((e >> 29) & 1) e += px_tile0 << 16;
+                job_tab[i] = e;
+            }
+            __syncwarp();
+        }
         int front = 0, back = n_jobs - 1, ef = 0, eb = 0;
         ProjJob jf{}, jb{};
         unsigned long long vf = 0, vb = 0;
-        auto entry = [&](int i) {                            // pixel entries hold a relative tile: make it absolute
-            int e = table_at(i, n_px);
-            if ((e >> 29) & 1) e += px_tile0 << 16;
-            return e;
-        };
         auto look = [&]() {                                  // lane 0: both ends of what is left, counters requested
-            ef = entry(front); eb = entry(back);
+            ef = job_tab[front]; eb = job_tab[back];
             jf = proj_decode(a, ef); jb = proj_decode(a, eb);
             vf = jf.pixel ? ~0ull : tc::ld_relaxed_gpu(flag_of(jf)); vb = jb.pixel ? 0ull : tc::ld_relaxed_gpu(flag_of(jb));
         };
@@ -370,19 +378,22 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 #ifdef HB_TIMELINE
             const long long t_issue = acct ? clock64() : 0;
 #endif
-            // geometry of the job's stage: decoder jobs [part hi, lo][K-slice][8 columns][2 KB], pixel jobs [8 columns][xblk]
+            // geometry of the job's stage: decoder jobs [part hi, lo][K-slice][8 columns][2 KB], pixel jobs [8 columns][xblk].
+            // The job's columns are contiguous per (part, K-slice): ONE copy each (issuing a bulk copy costs the lane
+            // ~180 cycles and the lanes take turns; with two copies per (part, K-slice) this warp needed ~2000 cycles per
+            // job and starved the MMA warp, which needs ~780).  A single-slice job is cut in two so that a CTA pair
+            // always has a copy each to multicast.
             const int jparts = j.pixel ? 1 : PARTS, jdirs = j.pixel ? 1 : n_dirs, jblk = j.pixel ? a.px.blk_bytes : blk_bytes;
+            const int pieces = jparts * jdirs == 1 ? 2 : 1;
             if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * jparts * jdirs * jblk));
             __syncwarp();
-            if (lane < 2 * jparts * jdirs) {
-                // the job's columns are contiguous per (part, K-slice); two copies of four columns each (one big copy is
-                // served by a single copy engine queue and was slower)
-                const int half = lane & 1, pd = lane >> 1, part = pd / jdirs, d = pd % jdirs;
-                const int cols = min(4, j.valid - 4 * half);
-                uint8_t* dst = smem + stage * stage_bytes + (j.pixel ? 0 : part * part_bytes + d * slice_bytes) + half * 4 * jblk;
+            if (lane < pieces * jparts * jdirs) {
+                const int piece = lane % pieces, pd = lane / pieces, part = pd / jdirs, d = pd % jdirs;
+                const int c0 = piece * 4, cols = pieces == 1 ? j.valid : min(4, j.valid - c0);
+                uint8_t* dst = smem + stage * stage_bytes + (j.pixel ? 0 : part * part_bytes + d * slice_bytes) + c0 * jblk;
                 const uint8_t* src = j.pixel
-                    ? a.px.ximg + j.wg * a.px.wg_stride + (int64_t)(j.t0 + 4 * half) * jblk
-                    : in_base + j.wg * in_wg_stride + (split ? j.src_dir : d) * in_dir_stride + part * in_part_stride + (int64_t)(j.t0 + 4 * half) * jblk;
+                    ? a.px.ximg + j.wg * a.px.wg_stride + (int64_t)(j.t0 + c0) * jblk
+                    : in_base + j.wg * in_wg_stride + (split ? j.src_dir : d) * in_dir_stride + part * in_part_stride + (int64_t)(j.t0 + c0) * jblk;
                 const uint32_t bytes = (uint32_t)(max(cols, 0) * jblk);
                 // pair mode: the two CTAs split the copies and multicast them to both
                 const bool mine = cols > 0 && (!a.pair || (uint32_t)(lane & 1) == pair_rank);
@@ -465,10 +476,12 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 else tc::bulk_s2g(dst, staging + sb * PROJ_STG_BYTES, bytes);
             }
             tc::bulk_commit();
-            // the PREVIOUS job's copy has read its staging buffer (this job's read overlaps the next epilogue)
-            HB_TIMED(1, tc::bulk_wait_read_pending<1>());
+            // the staging buffer goes back to the epilogue warps as soon as THIS copy has read it (~32 KB of shared-memory
+            // reads); meanwhile they fill the other buffer.  (Releasing a buffer one job later, when the next job had been
+            // staged, serialised epilogue and store: the epilogue warps waited for stg_empty a third of the time.)
+            HB_TIMED(1, tc::bulk_wait_read_pending<0>());
             __syncwarp();
-            if (lane == 0 && it > 0) tc::mbar_arrive(stg_empty + (sb ^ 1));
+            if (lane == 0) tc::mbar_arrive(stg_empty + sb);
             if (a.tile_flags != nullptr) {
                 pending[n_pending++] = j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
                                                : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
@@ -1068,6 +1081,9 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + nb); }
             HB_DBG(drole, s, 6);
+#ifdef HB_TIMELINE
+            if (dbg_steps && lane == 0 && s < 128) dbg[8192 + warp * 128 + s] = clock64();     // every gate warp's arrival
+#endif
         }
         if (warp == 0) HB_STAMP(2);                          // last step done
         if (phase == n_phases - 1 && ra.h_out != nullptr) {
@@ -1645,7 +1661,9 @@ struct TensorTuning {
     bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
     bool pingpong = true;       // HB_NO_PINGPONG: one window tile per recurrence CTA in the per-chunk kernels of large batches
     bool cooperative = true;    // HB_NO_COOPERATIVE: chunk-loop kernel launched without the cooperative attribute
-    int gate_warps = 16;        // HB_GATE_WARPS = 8 | 16: gate warps of the chunk-loop kernel's recurrence role (4 or 2 windows per thread at 8-window tiles)
+    int gate_warps = 8;         // HB_GATE_WARPS = 8 | 16: gate warps of the chunk-loop kernel's recurrence role (4 or 2 windows per thread at 8-window
+                                // tiles).  Measured at B=256: 85.8 k windows/s with 8, 81.7 k with 16 (fewer warps share the per-step waits, TMEM loads,
+                                // fences; with 16 the shared-memory fence before the arrive costs 150-190 cycles instead of ~90)
     static TensorTuning from_env() {
         TensorTuning t;
         t.pdl = getenv("HB_NO_PDL") == nullptr;
@@ -1656,7 +1674,7 @@ struct TensorTuning {
         t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
         t.pingpong = getenv("HB_NO_PINGPONG") == nullptr;
         t.cooperative = getenv("HB_NO_COOPERATIVE") == nullptr;
-        if (const char* v = getenv("HB_GATE_WARPS")) { if (atoi(v) == 8) t.gate_warps = 8; }
+        if (const char* v = getenv("HB_GATE_WARPS")) { if (atoi(v) == 8 || atoi(v) == 16) t.gate_warps = atoi(v); }
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
             const int n = atoi(v);
             if (n == 8 || n == 16 || n == 32) t.windows_per_cta = n;
@@ -1868,7 +1886,7 @@ inline void free_layer(TensorLayer* L) {
 }
 
 // (+1024: the kernels align their shared memory to the swizzle atom themselves)
-inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 2 * PROJ_STG_BYTES + 256 + PROJ_TILE_SLOTS * 4 + 1024; }
+inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 2 * PROJ_STG_BYTES + 256 + (PROJ_TILE_SLOTS + PROJ_TABLE_MAX) * 4 + 1024; }
 template <int N, int NLIVE = N>
 constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<NLIVE>() * NLIVE * GI_ROW_BYTES + 512 + 1024; }
 constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128 + 1024; }
@@ -2069,8 +2087,10 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         flags_needed = (size_t)4 * plan.rec_ctas + n_groups + n_groups * tiles8 * 2;
         if (pixels_in_loop && flags_needed + n_groups * px_tiles * 2 > e->flags_capacity) pixels_in_loop = false;
         if (pixels_in_loop) flags_needed += n_groups * px_tiles * 2;
-        chunkloop = flags_needed <= e->flags_capacity &&
-                    (size_t)n_wg * (2 * tiles8 + (pixels_in_loop ? PX_R : 0)) <= e->proj_jobs_capacity;   // job table sized at creation
+        const int64_t worker_tiles = (n_wg * tiles8 + plan.proj_workers - 1) / plan.proj_workers;    // tiles one projection worker owns
+        const int64_t worker_jobs = 2 * worker_tiles + (n_wg + plan.proj_workers - 1) / plan.proj_workers * PX_R;
+        chunkloop = flags_needed <= e->flags_capacity && worker_tiles <= PROJ_TILE_SLOTS && worker_jobs <= PROJ_TABLE_MAX &&
+                    (size_t)n_wg * (2 * tiles8 + (pixels_in_loop ? PX_R : 0)) <= e->proj_jobs_capacity;   // tables sized at creation / in shared memory
         pixels_in_loop = pixels_in_loop && chunkloop;
     }
     if (enc_cols > 0) {
@@ -2098,7 +2118,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
 #ifdef HB_TIMELINE
     static const bool dbg_on = getenv("HB_DEBUG_TIMELINE") != nullptr;
     static const bool dbg_enc = dbg_on && getenv("HB_DEBUG_TIMELINE")[0] == 'e';
-    if (dbg_on && !dbg_buf) { cudaMalloc(&dbg_buf, 8192 * sizeof(long long)); cudaMemset(dbg_buf, 0, 8192 * sizeof(long long)); }
+    if (dbg_on && !dbg_buf) { cudaMalloc(&dbg_buf, 10240 * sizeof(long long)); cudaMemset(dbg_buf, 0, 10240 * sizeof(long long)); }
 #else
     constexpr bool dbg_on = false, dbg_enc = false;
 #endif
@@ -2330,7 +2350,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         static int printed = 0;
         cudaStreamSynchronize(s);
         if (printed++ == 2) {
-            std::vector<long long> hbuf(8192);
+            std::vector<long long> hbuf(10240);
             cudaMemcpy(hbuf.data(), dbg_buf, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
             if (chunkloop) {
                 const long long t0 = hbuf[4096];
@@ -2385,6 +2405,13 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 acc[15] += at(0, st + 1, 0) - base;               // full step
             }
             fprintf(stderr, "[timeline, cycles after MMA warp release] issue_done=%.0f step=%.0f\n", acc[0] / n, acc[15] / n);
+            fprintf(stderr, "  arrival of every gate warp:");
+            for (int w = 0; w < 16; ++w) {
+                double a_w = 0;
+                for (int st = 20; st < 90; ++st) a_w += hbuf[8192 + w * 128 + st] - at(0, st, 0);
+                if (hbuf[8192 + w * 128 + 20] != 0) fprintf(stderr, " %d:%.0f", w, a_w / 70);
+            }
+            fprintf(stderr, "\n");
             for (int role = 1; role <= 2; ++role) {
                 fprintf(stderr, "  gate warp %s:", role == 1 ? "0 " : "15");
                 const char* names[7] = {"gi_full", "acc_r", "acc_z", "acc_n", "ldtm_n", "math_done", "arrived"};

@@ -45,8 +45,8 @@ VARIANTS = {
     "chunkloop_no_pixel_jobs": {"HB_NO_PIXEL_JOBS": "1"},
     "chunkloop_tile16_pixel_jobs": {"HB_WINDOWS_PER_CTA": "16"},
     "chunkloop_few_heads_workers": {"HB_HEADS_WORKERS": "2"},
-    "chunkloop_8_gate_warps": {"HB_GATE_WARPS": "8"},
-    "chunkloop_8_gate_warps_tile16": {"HB_GATE_WARPS": "8", "HB_WINDOWS_PER_CTA": "16"},
+    "chunkloop_16_gate_warps": {"HB_GATE_WARPS": "16"},
+    "chunkloop_16_gate_warps_tile16": {"HB_GATE_WARPS": "16", "HB_WINDOWS_PER_CTA": "16"},
     "chunkloop_not_cooperative": {"HB_NO_COOPERATIVE": "1"},
 }
 
