@@ -121,7 +121,6 @@ constexpr int PROJ_NT = 64;
 constexpr int PROJ_STG_BYTES = PROJ_NT * 128 * 4;   // fp32 staging of one tile's output block: [64 (column, window)][128 gate rows]
 constexpr int PROJ_STAGES = 2;                    // full-K tiles; the K-half jobs of the chunk-loop kernel are half as large: 4 stages
 constexpr int PROJ_PUBLISH_BATCH = 8;
-constexpr int PROJ_URGENT_BATCH = 3;              // flags of the jobs the decoder is waiting for go out in batches of three
 constexpr int PROJ_TILE_SLOTS = 2048;             // chunk-loop kernel: tiles one worker may own (first-half bookkeeping of the store warp)
 constexpr int PROJ_TABLE_MAX = 1024;              // chunk-loop kernel: jobs of one worker per chunk (the loader keeps the list in shared memory)
 constexpr int PROJ_W_COL0 = 128;
@@ -165,6 +164,9 @@ struct ProjArgs {
     // in fp32, so the sum does not depend on which half ran first.  (Two separate gi arrays added by the decoder's gate
     // threads were the first version: twice the gi traffic and shared memory, 12 more instructions per gate thread and
     // step.  Reading the first half back in the epilogue, or red.add per element, stalled the role.)
+    int urgent_batch;              // chunk-loop kernel: flags of the jobs the decoder is waiting for go out in batches of this many
+    int ksplit;                    // chunk-loop kernel: 1 = K-half jobs as described above, 0 = one job per column tile with the whole
+                                   // K = 256 contraction, runnable when BOTH encoder directions have stored the tile's columns
     const int* jobs;               // per worker, in the order the encoder makes them runnable (see pack_proj_job)
     const int* job_offsets;        // [workers + 1]
     const unsigned long long* progress; unsigned long long epoch; int rec_n;   // encoder progress counters, [cta][dir]
@@ -208,7 +210,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     const uint8_t* __restrict__ in_base = a.in_base;
     const int64_t in_wg_stride = a.in_wg_stride, in_dir_stride = a.in_dir_stride, in_part_stride = a.in_part_stride;
     const int lbo = a.lbo, Kp = a.Kp, W = a.W;
-    const bool split = a.jobs != nullptr;
+    const bool loop = a.jobs != nullptr;                     // chunk-loop kernel: job list, run-time order, flags
+    const bool split = loop && a.ksplit != 0;                // K-half jobs
     const int blk_bytes = a.blk_bytes;
     const int n_dirs = split ? 1 : a.n_dirs;                 // K-slices per stage
     const uint32_t* __restrict__ w_tmem = a.w_tmem;
@@ -249,7 +252,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     tc::named_barrier_sync(1, PROJ_THREADS);
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const bool pixels = split && a.px.ximg != nullptr;
+    const bool pixels = loop && a.px.ximg != nullptr;
     const int kwords_px = pixels ? a.px.Kp >> 1 : 0;
     if (warp < 4) {   // weight block(s) -> TMEM, thread = gate row; 32 words in flight per round trip
         const int row = warp * 32 + lane;
@@ -287,7 +290,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 
     const int n_chunks = a.n_chunks > 0 ? a.n_chunks : 1;
     const int n_table = proj_count(a, worker, n_workers);    // entries of this worker's list
-    const int job0 = split ? __ldg(a.job_offsets + worker) : 0;
+    const int job0 = loop ? __ldg(a.job_offsets + worker) : 0;
     // list = [pixel entries: PX_R relative tiles x my window groups, tile-major][decoder entries in runnable order];
     // chunk k uses the first px_tiles(k) x my_groups pixel entries and all decoder entries
     const int px_wgs = pixels ? __ldg(a.px.wgs_of_worker + worker) : 0;
@@ -318,18 +321,21 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         // are issued): the encoder completed and fenced its bulk stores before it released a counter, and our bulk loads
         // are issued after the value has arrived and read L2 directly.  (ld.acquire + fence.proxy.async per job cost
         // ~1500 cycles and made this warp the bottleneck of the role.)
-        auto need_of = [&](const ProjJob& q, int chunk) {
-            return a.epoch + (unsigned long long)chunk * W + (unsigned long long)(q.src_dir == 0 ? q.t0 + q.valid : W - q.t0);
+        // a job is runnable when the encoder direction(s) it reads have published the tile's columns
+        auto runnable = [&](const ProjJob& q, unsigned long long c_f, unsigned long long c_r, int chunk) {
+            const unsigned long long base = a.epoch + (unsigned long long)chunk * W;
+            const bool f_ok = c_f >= base + (unsigned long long)(q.t0 + q.valid), r_ok = c_r >= base + (unsigned long long)(W - q.t0);
+            return q.pixel || (split ? (q.src_dir == 0 ? f_ok : r_ok) : (f_ok && r_ok));
         };
-        auto flag_of = [&](const ProjJob& q) { return a.progress + ((q.wg * WG) / a.rec_n) * 2 + q.src_dir; };
+        auto flag_of = [&](const ProjJob& q) { return a.progress + ((q.wg * WG) / a.rec_n) * 2; };   // [forward, reverse] counters of the tile's CTA
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int n_px = split ? px_count(chunk) : 0;
-        const int n_jobs = split ? n_px + n_dec : n_table;
+        const int n_px = loop ? px_count(chunk) : 0;
+        const int n_jobs = loop ? n_px + n_dec : n_table;
         const int px_tile0 = pixels ? px_done(a, chunk) : 0;
         // this chunk's job list -> shared memory (coalesced), pixel entries made absolute: the per-job decisions below then
         // depend on one global load (the progress counter, requested a job ahead), not on a chain of them
-        if (split) {
+        if (loop) {
             __syncwarp();
             for (int i = lane; i < n_jobs; i += 32) {
                 int e = table_at(i, n_px);
@@ -340,17 +346,21 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         }
         int front = 0, back = n_jobs - 1, ef = 0, eb = 0;
         ProjJob jf{}, jb{};
-        unsigned long long vf = 0, vb = 0;
+        unsigned long long vf[2] = {0, 0}, vb[2] = {0, 0};
+        auto poll = [&]() {                                  // lane 0: the counters of both candidates, four loads in flight
+            if (!jf.pixel) { vf[0] = tc::ld_relaxed_gpu(flag_of(jf)); vf[1] = tc::ld_relaxed_gpu(flag_of(jf) + 1); }
+            if (!jb.pixel) { vb[0] = tc::ld_relaxed_gpu(flag_of(jb)); vb[1] = tc::ld_relaxed_gpu(flag_of(jb) + 1); }
+        };
         auto look = [&]() {                                  // lane 0: both ends of what is left, counters requested
             ef = job_tab[front]; eb = job_tab[back];
             jf = proj_decode(a, ef); jb = proj_decode(a, eb);
-            vf = jf.pixel ? ~0ull : tc::ld_relaxed_gpu(flag_of(jf)); vb = jb.pixel ? 0ull : tc::ld_relaxed_gpu(flag_of(jb));
+            poll();
         };
-        if (split && lane == 0 && n_jobs > 0) look();
+        if (loop && lane == 0 && n_jobs > 0) look();
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int stage = it % n_stages;
             if (it >= n_stages) HB_TIMED(0, tc::mbar_wait(a_empty + stage, (uint32_t)((it / n_stages - 1) & 1)));
-            if (split) {
+            if (loop) {
                 int e = 0;
                 if (lane == 0) {
 #ifdef HB_TIMELINE
@@ -358,11 +368,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 #endif
                     const long long t_spin = clock64();
                     while (true) {
-                        if (front < back && !jb.pixel && vb >= need_of(jb, chunk)) { e = eb | (1 << 30); --back; break; }   // bit 30: the decoder waits for it
-                        if (jf.pixel || vf >= need_of(jf, chunk)) { e = ef; ++front; break; }    // pixel jobs wait for nothing
+                        if (front < back && !jb.pixel && runnable(jb, vb[0], vb[1], chunk)) { e = eb | (1 << 30); --back; break; }   // bit 30: the decoder waits for it
+                        if (runnable(jf, vf[0], vf[1], chunk)) { e = ef; ++front; break; }       // pixel jobs wait for nothing
                         __nanosleep(100);
                         if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap();
-                        vf = tc::ld_relaxed_gpu(flag_of(jf)); vb = jb.pixel ? 0ull : tc::ld_relaxed_gpu(flag_of(jb));
+                        poll();
                     }
 #ifdef HB_TIMELINE
                     if (acct) t_wait[1] += clock64() - t_;
@@ -444,7 +454,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         };
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int n_jobs = split ? px_count(chunk) + n_dec : n_table;
+        const int n_jobs = loop ? px_count(chunk) + n_dec : n_table;
         // which of this worker's tiles already hold one half in this chunk, and the job that stored it
         if (split) for (int i = lane; i < PROJ_TILE_SLOTS; i += 32) first_it[i] = -1;
         __syncwarp();
@@ -452,8 +462,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             const int sb = it & 1;
             const uint32_t par = (uint32_t)((it >> 1) & 1);
             HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
-            const int e_ring = split ? job_ring[it & 15] : 0;
-            j = split ? proj_decode(a, e_ring) : proj_tile_job(a, worker, n_workers, idx);
+            const int e_ring = loop ? job_ring[it & 15] : 0;
+            j = loop ? proj_decode(a, e_ring) : proj_tile_job(a, worker, n_workers, idx);
             float* out = j.pixel ? a.px.gi : gi;
             const int out_cols = j.pixel ? a.px.cols : W;
             bool second = false;
@@ -488,7 +498,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 if (idx == n_jobs - 1) HB_TIMED(2, publish(0, it));                  // last job of the chunk
                 // jobs taken from the back of the list are the ones the decoder is waiting for: small batches (one
                 // publication per job was measured: the fence makes this warp the bottleneck)
-                else if ((e_ring >> 30) & 1) { if (n_pending >= PROJ_URGENT_BATCH + 1) HB_TIMED(3, publish(1, it)); }
+                else if ((e_ring >> 30) & 1) { if (n_pending >= a.urgent_batch + 1) HB_TIMED(3, publish(1, it)); }
                 else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2, it));   // copies issued two jobs ago have normally landed: no stall
             }
 #ifdef HB_TIMELINE
@@ -505,11 +515,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const int ksteps = split ? 8 : (Kp >> 4);
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int n_jobs = split ? px_count(chunk) + n_dec : n_table;
+        const int n_jobs = loop ? px_count(chunk) + n_dec : n_table;
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int stage = it % n_stages, acc = it & 1;
             HB_TIMED(0, tc::mbar_wait(a_full + stage, (uint32_t)((it / n_stages) & 1)));
-            j = split ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
+            j = loop ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
             if (it >= 2) HB_TIMED(1, tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1)));
             tc::tc_fence_after();
             if (tc::elect_one()) {
@@ -561,17 +571,17 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const float sc_px = pixels ? a.px.scale_row[blk * 128 + r] : 0.f, bi_px = pixels ? a.px.bias_row[blk * 128 + r] : 0.f;
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int n_jobs = split ? px_count(chunk) + n_dec : n_table;
+        const int n_jobs = loop ? px_count(chunk) + n_dec : n_table;
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int acc = it & 1, sb = it & 1;
             if (it >= 2) HB_TIMED(0, tc::mbar_wait(stg_empty + sb, (uint32_t)((it / 2 - 1) & 1)));   // arrives once job it-1 is being stored
             HB_TIMED(1, tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1)));
-            j = split ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
+            j = loop ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
             float* stg = reinterpret_cast<float*>(staging + sb * PROJ_STG_BYTES) + r;
             const float sc = j.pixel ? sc_px : sc_dec;
-            const float add = j.pixel ? bi_px : (j.src_dir ? 0.f : bi_dec);   // the bias rides on the forward-source half (or the only one)
+            const float add = j.pixel ? bi_px : ((split && j.src_dir) ? 0.f : bi_dec);   // the bias rides on the forward-source half (or the only one)
             // 16 accumulator columns (two image columns x 8 windows) per TMEM round trip, the next load in flight while
             // the current values are scaled and staged
             {
@@ -660,6 +670,7 @@ struct RecLayer {
     const unsigned long long* tile_flags; int flag_tiles, flag_abs, flag_skip_tiles; unsigned long long flag_need_base, flag_need_per_chunk;
     const unsigned long long* heads_done; int heads_per_chunk;   // decoder: yimg[k & 1] reusable when >= heads_per_chunk (k - 1)
     const unsigned long long* consumed_flags;  // encoder: tile flags (both directions) that tell yimg of chunk k - 1 has been read
+    int consumed_per_chunk;                    // ... when they have reached consumed_per_chunk * k
 };
 
 // n_layers == 1: one layer, one chunk (per-chunk launches).  n_layers == 2: the whole chunk loop of the reference
@@ -851,7 +862,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (L.consumed_flags != nullptr && chunk >= 1)   // every projection CTA has read this layer's previous image
                 for (int f = lane; f < NG * ra.tiles_t * 2; f += 32)
                     if (cta_x * NG + f / (ra.tiles_t * 2) < ra.n_wg)
-                        tc::spin_until_ge(L.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, 6ull * chunk);
+                        tc::spin_until_ge(L.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, (unsigned long long)L.consumed_per_chunk * chunk);
         }
         __syncthreads();
     }
@@ -1661,6 +1672,9 @@ struct TensorTuning {
     bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
     bool pingpong = true;       // HB_NO_PINGPONG: one window tile per recurrence CTA in the per-chunk kernels of large batches
     bool cooperative = true;    // HB_NO_COOPERATIVE: chunk-loop kernel launched without the cooperative attribute
+    bool ksplit = false;        // HB_PROJ_KSPLIT: chunk-loop projection as K-half jobs (runnable per encoder direction, second half added by a reducing
+                                // bulk copy) instead of one whole-K job per column tile
+    int urgent_batch = 0;       // HB_PROJ_URGENT_BATCH: see ProjArgs::urgent_batch (0: 3 with K-half jobs, 2 with whole-tile jobs)
     int gate_warps = 8;         // HB_GATE_WARPS = 8 | 16: gate warps of the chunk-loop kernel's recurrence role (4 or 2 windows per thread at 8-window
                                 // tiles).  Measured at B=256: 85.8 k windows/s with 8, 81.7 k with 16 (fewer warps share the per-step waits, TMEM loads,
                                 // fences; with 16 the shared-memory fence before the arrive costs 150-190 cycles instead of ~90)
@@ -1674,6 +1688,8 @@ struct TensorTuning {
         t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
         t.pingpong = getenv("HB_NO_PINGPONG") == nullptr;
         t.cooperative = getenv("HB_NO_COOPERATIVE") == nullptr;
+        t.ksplit = getenv("HB_PROJ_KSPLIT") != nullptr;
+        if (const char* v = getenv("HB_PROJ_URGENT_BATCH")) t.urgent_batch = std::min(std::max(atoi(v), 1), PROJ_PUBLISH_BATCH - 2);
         if (const char* v = getenv("HB_GATE_WARPS")) { if (atoi(v) == 8 || atoi(v) == 16) t.gate_warps = atoi(v); }
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
             const int n = atoi(v);
@@ -1692,7 +1708,7 @@ struct TensorEngine {
     size_t proj_jobs_capacity = 0;            // fixed at creation: a batch whose table does not fit takes per-chunk launches
     int loop_max_ctas8 = 0, loop_max_ctas16 = 0;   // CTAs of the chunk-loop kernel (8- / 16-window tiles) that can be resident at once
     bool coop_with_pdl = true;                // cleared if the driver refuses cooperative + programmatic serialization together
-    int jobs_w = -1, jobs_workers = -1, jobs_pixels = -1; int64_t jobs_n_wg = -1;
+    int jobs_w = -1, jobs_workers = -1, jobs_pixels = -1, jobs_ksplit = -1; int64_t jobs_n_wg = -1;
     int* proj_px_wgs = nullptr;               // [workers] window groups whose pixel jobs a worker owns
     std::vector<int> proj_jobs_host, proj_job_offsets_host, proj_px_wgs_host;
     int tile_order_w = -1;
@@ -2164,7 +2180,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             TE_CUDA(cudaMemcpyAsync(e->tile_order16, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
             e->tile_order_w = W;
         }
-        if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg || e->jobs_pixels != (int)pixels_in_loop) {
+        const bool ksplit = e->tune.ksplit;
+        if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg || e->jobs_pixels != (int)pixels_in_loop ||
+            e->jobs_ksplit != (int)ksplit) {
             // projection job table: tile (group, tile) belongs to worker (group * tiles + tile) % workers; a worker takes
             // the halves of its tiles in the order the encoder makes them runnable (forward half of tile t after step
             // 8t+8, reverse half after step W-8t)
@@ -2173,8 +2191,12 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             for (int64_t wg = 0; wg < n_wg; ++wg)
                 for (int t = 0; t < tiles8; ++t) {
                     const int id = (int)(wg * tiles8 + t);
-                    per[id % plan.proj_workers].push_back({std::min(8 * t + 8, W), id, pack_proj_job((int)wg, t, 0)});
-                    per[id % plan.proj_workers].push_back({W - 8 * t, id, pack_proj_job((int)wg, t, 1)});
+                    if (ksplit) {
+                        per[id % plan.proj_workers].push_back({std::min(8 * t + 8, W), id, pack_proj_job((int)wg, t, 0)});
+                        per[id % plan.proj_workers].push_back({W - 8 * t, id, pack_proj_job((int)wg, t, 1)});
+                    } else {                                   // whole tile: runnable when the later of the two directions has stored it
+                        per[id % plan.proj_workers].push_back({std::max(std::min(8 * t + 8, W), W - 8 * t), id, pack_proj_job((int)wg, t, 0)});
+                    }
                 }
             e->proj_jobs_host.clear();
             e->proj_job_offsets_host.assign(1, 0);
@@ -2203,7 +2225,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             TE_CUDA(cudaMemcpyAsync(e->proj_jobs, e->proj_jobs_host.data(), e->proj_jobs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
             TE_CUDA(cudaMemcpyAsync(e->proj_job_offsets, e->proj_job_offsets_host.data(), e->proj_job_offsets_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
             TE_CUDA(cudaMemcpyAsync(e->proj_px_wgs, e->proj_px_wgs_host.data(), e->proj_px_wgs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-            e->jobs_w = W; e->jobs_workers = plan.proj_workers; e->jobs_n_wg = n_wg; e->jobs_pixels = (int)pixels_in_loop;
+            e->jobs_w = W; e->jobs_workers = plan.proj_workers; e->jobs_n_wg = n_wg; e->jobs_pixels = (int)pixels_in_loop; e->jobs_ksplit = (int)ksplit;
         }
         TE_CUDA(cudaMemsetAsync(e->flags, 0, flags_needed * sizeof(unsigned long long), s));
         unsigned long long* f = e->flags;
@@ -2214,11 +2236,11 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         unsigned long long* px_flags = f;                                              // [group][image column tile][enc direction]
         RecArgs ra{};
         ra.layer[0] = layer_args(e->enc, ws.gi_enc, enc_cols, 0, J, ws.yimg1, ws.yimg1);
-        ra.layer[0].progress = enc_prog; ra.layer[0].consumed_flags = tile_flags;
+        ra.layer[0].progress = enc_prog; ra.layer[0].consumed_flags = tile_flags; ra.layer[0].consumed_per_chunk = ksplit ? 6 : 3;
         ra.layer[1] = layer_args(e->dec, ws.gi, W, 0, 0, ws.yimg2[0], ws.yimg2[1]);
         ra.layer[1].progress = dec_prog; ra.layer[1].tile_flags = tile_flags;
         ra.layer[1].flag_tiles = tiles8; ra.layer[1].flag_abs = 0; ra.layer[1].flag_skip_tiles = 0;
-        ra.layer[1].flag_need_base = 0; ra.layer[1].flag_need_per_chunk = 6;
+        ra.layer[1].flag_need_base = 0; ra.layer[1].flag_need_per_chunk = ksplit ? 6 : 3;   // gate blocks (x K-halves) per tile and chunk
         if (pixels_in_loop) {
             ra.layer[0].tile_flags = px_flags; ra.layer[0].flag_tiles = px_tiles; ra.layer[0].flag_abs = 1;
             ra.layer[0].flag_skip_tiles = px_pre_tiles; ra.layer[0].flag_need_base = 3; ra.layer[0].flag_need_per_chunk = 0;
@@ -2230,7 +2252,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         pp.progress = enc_prog; pp.epoch = 0; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
         pp.pair = 0;          // every CTA of the role picks its own job order (see the loader): no shared tiles
         pp.dbg = dbg_buf;
-        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets;
+        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets; pp.ksplit = ksplit ? 1 : 0;
+        pp.urgent_batch = e->tune.urgent_batch ? e->tune.urgent_batch : (ksplit ? 3 : 2);
         if (pixels_in_loop) {
             pp.px.ximg = reinterpret_cast<const uint8_t*>(ws.ximg); pp.px.wg_stride = (int64_t)T * xblk; pp.px.blk_bytes = xblk; pp.px.Kp = e->enc.Kp;
             pp.px.w_tmem = e->enc.wih_tmem; pp.px.scale_row = e->enc.scale_row; pp.px.bias_row = e->enc.bias_row;
