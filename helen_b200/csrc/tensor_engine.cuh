@@ -48,16 +48,38 @@ constexpr int WG = 8;                             // windows per window group ==
 constexpr int YBLK = 2048;                        // [8 windows x 128 k] fp16 image of one direction: two swizzle atoms
 constexpr int YROW = 2 * YBLK;                    // 4608 B: both directions (K = 256) of one (group, t, part)  [sizes only]
 constexpr int GI_ROW_BYTES = G * 4;               // 1536 B: gi of one (window, t, direction)
-// gi' lives in global memory as a "gi image": [window group][direction x gate r,z,n = 6 blocks][column][8 windows][128 units]
-// fp32.  What one projection job produces (one gate block of 8 windows x 8 consecutive columns, 32 KB) is ONE contiguous
-// bulk copy; what one recurrence step needs (the three gate blocks of a window group's column and direction) is three
-// 4 KB copies.  (The first layout kept a step's 12 KB contiguous instead, which made every projection job eight separate
-// bulk stores: their issue cost, ~1150 cycles per job, made the store warp the slowest stage of the projection role and
-// left the decoder waiting 12-18 us per chunk for its first tiles.)
+// gi' lives in global memory as a "gi image": [window group][direction x gate r,z,n = 6 blocks][column][128 units][8 windows]
+// fp32.  What one projection job produces (one gate block of 8 windows x 8 consecutive columns, 32 KB) is contiguous, and
+// a projection thread (one gate row) writes the 8 windows of a column as two 16-byte stores; what one recurrence step
+// needs (the three gate blocks of a window group's column and direction) is three 4 KB bulk copies, and a gate thread
+// (one hidden unit, 2 / 4 / 8 windows) reads its values with one or two vector loads.  The two 16-byte halves of a
+// unit's 8 windows are swapped for units with bit 2 set (gi_window_index), which makes those 16-byte shared-memory reads
+// conflict-free (lane stride 32 bytes).
+// (The first layouts were window-major: [..][8 windows][128 units].  A step's 12 KB contiguous made every projection job
+// eight separate bulk stores; one block per gate made it one 32 KB bulk store, but bulk stores out of shared memory run
+// at ~20 B per cycle next to the MMAs' operand reads and the store warp paced the projection role either way.)
 constexpr int GI_BLK_FLOATS = WG * H;             // 1024: one (group, gate block, column)
 constexpr int GI_BLK_BYTES = GI_BLK_FLOATS * 4;   // 4096
 constexpr int GI_GRP_BYTES = 3 * GI_BLK_BYTES;    // 12288 B: the three gate blocks of one (group, column, direction) in a shared-memory stage
 __host__ __device__ constexpr int64_t gi_block(int64_t wg, int64_t cols, int64_t t, int blk) { return ((wg * 6 + blk) * cols + t) * GI_BLK_FLOATS; }
+// float index of (unit u, window w of the group) inside a block
+__host__ __device__ constexpr int gi_window_index(int u, int w) { return u * WG + ((((w >> 2) ^ (u >> 2)) & 1) << 2) + (w & 3); }
+// a gate thread's NW consecutive windows (starting at w0, a multiple of NW) of unit u: one or two vector loads
+template <int NW>
+__device__ __forceinline__ void gi_load(const float* blk, int u, int w0, float* out) {
+    static_assert(NW == 2 || NW == 4 || NW == 8, "windows per gate thread");
+    if constexpr (NW == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(blk + gi_window_index(u, w0));
+        out[0] = v.x; out[1] = v.y;
+    } else if constexpr (NW == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(blk + gi_window_index(u, w0));
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else {
+        const float4 lo = *reinterpret_cast<const float4*>(blk + gi_window_index(u, 0));
+        const float4 hi = *reinterpret_cast<const float4*>(blk + gi_window_index(u, 4));
+        out[0] = lo.x; out[1] = lo.y; out[2] = lo.z; out[3] = lo.w; out[4] = hi.x; out[5] = hi.y; out[6] = hi.z; out[7] = hi.w;
+    }
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -109,20 +131,24 @@ pileup_to_operand_image_kernel(const uint8_t* __restrict__ images, int64_t B, in
 // Input projection  gi'[m, 0:768] = scale_row * (A[m, :] . Wcat^T) + bias_row
 // grid = (workers, 6 gate blocks).  The CTA's [128 x Kp] weight block (hi, lo) is TMEM-resident;
 // a tile is 64 data rows = 8 windows x 8 consecutive columns, staged by bulk copies.
-// Warps 0-3: epilogue (TMEM lane quarter = warp).  Warp 4: MMA issuer.  Warp 5: tile loader.  Warp 6: gi' store - the
-// epilogue stages the block in shared memory and the store warp writes it with bulk copies (512 contiguous bytes per
-// (window, column)), so completion is tracked per job by bulk groups: the chunk-loop kernel publishes a job's flag
-// when ITS copies have landed, without a memory fence that would also wait for the newest stores.
+// Warps 0-3: epilogue (TMEM lane quarter = warp).  Warp 4: MMA issuer.  Warp 5: tile loader.  Warp 6 (chunk-loop kernel
+// only): job scheduler.
+// The epilogue writes gi' straight from registers: a thread owns one gate row (its TMEM lane) and the 8 windows of a column
+// are contiguous in the gi image, so a column is two 16-byte stores per thread and 1 KB contiguous per warp.  (Staging the
+// block in shared memory for a bulk store was the first version: one 32 KB bulk store took ~1700 cycles to issue and drain
+// - the tile's MMAs, ~1550 cycles, already keep the shared-memory port busy with their operand reads - and the store warp
+// paced the whole role.)  In the chunk-loop kernel every epilogue warp makes its stores visible (gpu-scope fence) and
+// raises the tile's counter itself: PROJ_FLAGS_PER_TILE = 3 gate blocks x 4 warps per tile.
 // The epilogue folds the bias sums and the -log2(e) factors of the gate nonlinearities into gi'
 // (see tc_recurrence_kernel), so gi' is NOT the plain pre-activation of the fp32 engine.
 // ---------------------------------------------------------------------------------------------
-constexpr int PROJ_THREADS = 224;                // warps 0-3 epilogue, 4 MMA issuer, 5 tile loader, 6 gi' store
+constexpr int PROJ_THREADS = 224;                // warps 0-3 epilogue, 4 MMA issuer, 5 tile loader, 6 job scheduler
 constexpr int PROJ_NT = 64;
-constexpr int PROJ_STG_BYTES = PROJ_NT * 128 * 4;   // fp32 staging of one tile's output block: [64 (column, window)][128 gate rows]
-constexpr int PROJ_STAGES = 2;                    // full-K tiles; the K-half jobs of the chunk-loop kernel are half as large: 4 stages
-constexpr int PROJ_PUBLISH_BATCH = 8;
-constexpr int PROJ_TILE_SLOTS = 2048;             // chunk-loop kernel: tiles one worker may own (first-half bookkeeping of the store warp)
-constexpr int PROJ_TABLE_MAX = 1024;              // chunk-loop kernel: jobs of one worker per chunk (the loader keeps the list in shared memory)
+constexpr int PROJ_STAGES = 3;                    // input stages (64 KB each for the decoder's K = 256, hi and lo parts)
+constexpr int PROJ_TABLE_MAX = 1024;              // chunk-loop kernel: jobs of one worker per chunk (the scheduler keeps the list in shared memory)
+constexpr int PROJ_RING = 16;                     // job ids in flight between scheduler / loader / MMA issuer / epilogue
+constexpr int PROJ_SCHED_LEAD = 4;                // jobs the scheduler may decide ahead of the loader
+constexpr int PROJ_FLAGS_PER_TILE = 12;           // counter increments that complete a (group, tile, direction): 3 gate blocks x 4 epilogue warps
 constexpr int PROJ_W_COL0 = 128;
 
 // Encoder input projection inside the chunk-loop kernel ("pixel jobs"): while the encoder of chunk k runs, the projection
@@ -135,7 +161,7 @@ struct ProjPixelArgs {
     const uint32_t* w_tmem; const float* scale_row; const float* bias_row;
     float* gi; int cols, tiles;                  // gi image of all `cols` image columns (`tiles` column tiles)
     int col_step;                                // J
-    unsigned long long* flags;                   // [group][tile][direction] += 1 per gate block (3 when complete)
+    unsigned long long* flags;                   // [group][tile][direction], PROJ_FLAGS_PER_TILE when complete
     const int* wgs_of_worker;                    // [workers] window groups whose pixel jobs the worker owns
 };
 
@@ -154,32 +180,23 @@ struct ProjArgs {
     // pair mode: the launch uses clusters of 2 CTAs along the gate-block axis; both CTAs of a pair walk the same
     // tiles, each fetches half of a tile and multicasts it to both, halving the L2 traffic of the activations
     int pair;
-    // ---- chunk-loop kernel (producer/consumer mode): the role walks n_chunks chunks and its K = 256 contraction is
-    // split by SOURCE direction.  A job is one half of a column tile: the K = 128 slice that multiplies the forward
-    // (or the reverse) encoder's outputs, runnable as soon as THAT direction has stored the tile's columns, so the
-    // projection keeps pace with the encoder instead of starting when both directions meet in the middle.  Both
-    // halves land in the SAME gi block: whichever half of a tile a CTA processes first stores scale * acc (+ bias on the
-    // forward-source half), the other one is added to it at the destination by a reducing bulk copy
-    // (cp.reduce.async.bulk .add.f32: the L2 does the read-modify-write, nothing comes back to the SM).  a + b == b + a
-    // in fp32, so the sum does not depend on which half ran first.  (Two separate gi arrays added by the decoder's gate
-    // threads were the first version: twice the gi traffic and shared memory, 12 more instructions per gate thread and
-    // step.  Reading the first half back in the epilogue, or red.add per element, stalled the role.)
-    int urgent_batch;              // chunk-loop kernel: flags of the jobs the decoder is waiting for go out in batches of this many
-    int ksplit;                    // chunk-loop kernel: 1 = K-half jobs as described above, 0 = one job per column tile with the whole
-                                   // K = 256 contraction, runnable when BOTH encoder directions have stored the tile's columns
+    // ---- chunk-loop kernel (producer/consumer mode): the role walks n_chunks chunks.  A job is one column tile of one
+    // window group (the whole K = 256 contraction), runnable once BOTH encoder directions have published the tile's
+    // columns.  (K-half jobs, runnable per direction with the second half added to the first at the destination, kept
+    // the role busier during the encoder phase but doubled its output traffic, which is what bounds it.)
     const int* jobs;               // per worker, in the order the encoder makes them runnable (see pack_proj_job)
     const int* job_offsets;        // [workers + 1]
     const unsigned long long* progress; unsigned long long epoch; int rec_n;   // encoder progress counters, [cta][dir]
     int n_chunks;                  // a chunk's columns count from chunk * W in the progress counters
-    unsigned long long* tile_flags;   // [group][tile][decoder direction]: += 1 per job and gate block (3 blocks x 2 K-halves = 6 per chunk)
-    long long* dbg;                   // HB_DEBUG_TIMELINE: worker 0 records when it finished each chunk
+    unsigned long long* tile_flags;   // [group][tile][decoder direction], PROJ_FLAGS_PER_TILE per chunk
+    long long* dbg;                   // -DHB_TIMELINE: worker 0 records when it finished each chunk
     ProjPixelArgs px;                 // px.ximg == nullptr: no pixel jobs
     int col_tiles;                    // tile mode: project only the first col_tiles column tiles (0 = all)
 };
 
-__host__ __device__ constexpr int pack_proj_job(int wg, int tile, int src_dir) { return wg | (tile << 16) | (src_dir << 28); }
+__host__ __device__ constexpr int pack_proj_job(int wg, int tile) { return wg | (tile << 16); }
 
-struct ProjJob { int64_t wg; int t0, valid, src_dir; bool split, pixel; };
+struct ProjJob { int64_t wg; int t0, valid; bool pixel; };
 
 // jobs of one worker per chunk, and the idx-th of them in table / tile order
 __device__ __forceinline__ int proj_count(const ProjArgs& a, int worker, int n_workers) {
@@ -192,17 +209,18 @@ __device__ __forceinline__ int proj_count(const ProjArgs& a, int worker, int n_w
 __device__ __forceinline__ int px_done(const ProjArgs& a, int k) { return min((a.px.col_step * k + a.W + 7) >> 3, a.px.tiles); }
 __device__ __forceinline__ ProjJob proj_decode(const ProjArgs& a, int e) {
     ProjJob j;
-    j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.src_dir = (e >> 28) & 1; j.split = true; j.pixel = (e >> 29) & 1;
+    j.wg = e & 0xffff; j.t0 = ((e >> 16) & 0xfff) * 8; j.pixel = (e >> 29) & 1;
     j.valid = min(8, (j.pixel ? a.px.cols : a.W) - j.t0);
     return j;
 }
 __device__ __forceinline__ ProjJob proj_tile_job(const ProjArgs& a, int worker, int n_workers, int idx) {
     const int64_t tile = worker + (int64_t)idx * n_workers;
     ProjJob j;
-    j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.src_dir = 0; j.split = false; j.pixel = false;
+    j.wg = tile % a.n_wg; j.t0 = (int)(tile / a.n_wg) * 8; j.pixel = false;
     j.valid = min(8, a.W - j.t0);
     return j;
 }
+__device__ __forceinline__ int ld_volatile_shared(const volatile int* p) { return *p; }
 
 template <bool kSplitA>
 __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem, const int blk, const int worker, const int n_workers)
@@ -211,9 +229,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     const int64_t in_wg_stride = a.in_wg_stride, in_dir_stride = a.in_dir_stride, in_part_stride = a.in_part_stride;
     const int lbo = a.lbo, Kp = a.Kp, W = a.W;
     const bool loop = a.jobs != nullptr;                     // chunk-loop kernel: job list, run-time order, flags
-    const bool split = loop && a.ksplit != 0;                // K-half jobs
     const int blk_bytes = a.blk_bytes;
-    const int n_dirs = split ? 1 : a.n_dirs;                 // K-slices per stage
+    const int n_dirs = a.n_dirs;                             // K-slices per stage
     const uint32_t* __restrict__ w_tmem = a.w_tmem;
     const float* __restrict__ scale_row = a.scale_row;
     const float* __restrict__ bias_row = a.bias_row;
@@ -223,19 +240,17 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     const uint32_t slice_bytes = 8u * blk_bytes;
     const uint32_t part_bytes = n_dirs * slice_bytes;
     const uint32_t stage_bytes = PARTS * part_bytes;
-    const int n_stages = split ? 2 * PROJ_STAGES : PROJ_STAGES;   // same allocation: PROJ_STAGES full-K stages
-    uint8_t* staging = smem + PROJ_STAGES * PARTS * a.n_dirs * 8u * a.blk_bytes;     // [2][PROJ_STG_BYTES]
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(staging + 2 * PROJ_STG_BYTES);
-    uint64_t* a_empty = a_full + 2 * PROJ_STAGES;
-    uint64_t* acc_full = a_empty + 2 * PROJ_STAGES;
+    constexpr int n_stages = PROJ_STAGES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + PROJ_STAGES * stage_bytes);
+    uint64_t* a_empty = a_full + PROJ_STAGES;
+    uint64_t* acc_full = a_empty + PROJ_STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint64_t* stg_full = acc_empty + 2;                      // [2]: the 4 epilogue warps have written the staging buffer
-    uint64_t* stg_empty = stg_full + 2;                      // [2]: its bulk copies have read it
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + 2);
-    // chunk-loop kernel: the loader decides the job order at run time (see below) and passes it on through this ring
-    volatile int* job_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [16] >= jobs in flight between loader and store warp
-    volatile int* first_it = job_ring + 16;                  // [PROJ_TILE_SLOTS], store warp only: job that stored a tile's first K-half, or -1
-    volatile int* job_tab = first_it + PROJ_TILE_SLOTS;      // [PROJ_TABLE_MAX], loader only: this chunk's job list
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    // chunk-loop kernel: the scheduler decides the job order at run time (see below) and passes it on through this ring
+    volatile int* job_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [PROJ_RING]
+    volatile int* sched_count = job_ring + PROJ_RING;        // jobs the scheduler has published
+    volatile int* loader_count = sched_count + 1;            // jobs the loader has taken
+    volatile int* job_tab = loader_count + 1;                // [PROJ_TABLE_MAX], scheduler only: this chunk's job list
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kwords = Kp >> 1;
@@ -243,7 +258,8 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     if (tid == 0) {
         for (int i = 0; i < n_stages; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, a.pair ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(stg_full + i, 4); tc::mbar_init(stg_empty + i, 1); }
+        *sched_count = 0;
+        *loader_count = 0;
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -297,8 +313,9 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     const int n_dec = n_table - px_wgs * PX_R;
     auto px_count = [&](int chunk) { return (pixels && chunk + 1 < n_chunks) ? px_wgs * (px_done(a, chunk + 1) - px_done(a, chunk)) : 0; };
     auto table_at = [&](int i, int n_px) { return __ldg(a.jobs + job0 + (i < n_px ? i : px_wgs * PX_R + (i - n_px))); };
+    auto jobs_of = [&](int chunk) { return loop ? px_count(chunk) + n_dec : n_table; };
     ProjJob j;
-    // HB_DEBUG_TIMELINE: worker 0 / block 0 adds up the cycles each role spends at its wait points (slots 7200 + 8 role + k)
+    // -DHB_TIMELINE: worker 0 / block 0 adds up the cycles each role spends at its wait points (slots 7200 + 8 role + k)
 #ifdef HB_TIMELINE
     const bool acct = a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0;
     long long t_wait[4] = {0, 0, 0, 0};
@@ -310,75 +327,90 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 #define HB_TIMED(k, ...) do { __VA_ARGS__; } while (0)
 #define HB_ROLE_REPORT(role) do { } while (0)
 #endif
-    if (warp == 5) {
+    if (warp == 6) {
+        // ===================== job scheduler (chunk-loop kernel) =====================
+        // The table lists a worker's jobs in the order the encoder makes them runnable; the decoder, however, starts with
+        // the tiles that become runnable LAST (its first columns need the other direction's final outputs).  So the
+        // scheduler works from both ends of the list: the last job as soon as it is runnable (then the encoder has
+        // finished and everything left is runnable: the backlog is cleared in the order the decoder consumes it),
+        // otherwise the first one.  It runs up to PROJ_SCHED_LEAD jobs ahead of the loader, so the global round trips of
+        // its counter reads never stall a copy.  (With the decisions in the loader warp itself that warp needed ~1800
+        // cycles per job and starved the MMA issuer, which needs ~1550.)
+        // The counters are read with relaxed loads: the encoder completed and fenced its bulk stores before it released a
+        // counter, and the loader's bulk loads are issued after the value has arrived and read L2 directly.
+        if (loop) {
+            auto runnable = [&](const ProjJob& q, unsigned long long c_f, unsigned long long c_r, int chunk) {
+                const unsigned long long base = a.epoch + (unsigned long long)chunk * W;
+                return q.pixel || (c_f >= base + (unsigned long long)(q.t0 + q.valid) && c_r >= base + (unsigned long long)(W - q.t0));
+            };
+            auto flag_of = [&](const ProjJob& q) { return a.progress + ((q.wg * WG) / a.rec_n) * 2; };   // [forward, reverse] counters of the tile's CTA
+            int it = 0;
+            for (int chunk = 0; chunk < n_chunks; ++chunk) {
+                const int n_px = px_count(chunk);
+                const int n_jobs = n_px + n_dec;
+                const int px_tile0 = pixels ? px_done(a, chunk) : 0;
+                __syncwarp();
+                for (int i = lane; i < n_jobs; i += 32) {    // this chunk's list -> shared memory, pixel entries made absolute
+                    int e = table_at(i, n_px);
+                    if ((e >> 29) & 1) e += px_tile0 << 16;
+                    job_tab[i] = e;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    int front = 0, back = n_jobs - 1, ef = 0, eb = 0;
+                    ProjJob jf{}, jb{};
+                    unsigned long long vf[2] = {0, 0}, vb[2] = {0, 0};
+                    auto poll = [&]() {                      // the counters of both candidates, four loads in flight
+                        if (!jf.pixel) { vf[0] = tc::ld_relaxed_gpu(flag_of(jf)); vf[1] = tc::ld_relaxed_gpu(flag_of(jf) + 1); }
+                        if (!jb.pixel) { vb[0] = tc::ld_relaxed_gpu(flag_of(jb)); vb[1] = tc::ld_relaxed_gpu(flag_of(jb) + 1); }
+                    };
+                    auto look = [&]() {                      // both ends of what is left
+                        ef = job_tab[front]; eb = job_tab[back];
+                        jf = proj_decode(a, ef); jb = proj_decode(a, eb);
+                        poll();
+                    };
+                    if (n_jobs > 0) look();
+                    for (int idx = 0; idx < n_jobs; ++idx, ++it) {
+                        const long long t_spin = clock64();
+                        HB_TIMED(0, while (it - ld_volatile_shared(loader_count) >= PROJ_SCHED_LEAD) { if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap(); });
+                        int e = 0;
+#ifdef HB_TIMELINE
+                        const long long t_ = acct ? clock64() : 0;
+#endif
+                        while (true) {
+                            if (front < back && !jb.pixel && runnable(jb, vb[0], vb[1], chunk)) { e = eb | (1 << 30); --back; break; }   // bit 30: the decoder waits for it
+                            if (runnable(jf, vf[0], vf[1], chunk)) { e = ef; ++front; break; }       // pixel jobs wait for nothing
+                            __nanosleep(100);
+                            if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap();
+                            poll();
+                        }
+#ifdef HB_TIMELINE
+                        if (acct) t_wait[1] += clock64() - t_;
+#endif
+                        job_ring[it & (PROJ_RING - 1)] = e;
+                        __threadfence_block();
+                        *sched_count = it + 1;
+                        if (front <= back) look();           // for the next job
+                    }
+                }
+            }
+            HB_ROLE_REPORT(3);
+        }
+    } else if (warp == 5) {
         // ===================== loader =====================
-        // Job order in the chunk-loop kernel: the table lists a worker's jobs in the order the encoder makes them runnable;
-        // the decoder, however, starts with the tiles that become runnable LAST (its first columns need the other
-        // direction's final outputs).  So the loader works from both ends of the list: the last job as soon as it is
-        // runnable (then the encoder has finished and everything left is runnable: the backlog is cleared in the order
-        // the decoder consumes it), otherwise the first one.
-        // The counters are read with relaxed loads, one job ahead (the value is in flight while the previous job's copies
-        // are issued): the encoder completed and fenced its bulk stores before it released a counter, and our bulk loads
-        // are issued after the value has arrived and read L2 directly.  (ld.acquire + fence.proxy.async per job cost
-        // ~1500 cycles and made this warp the bottleneck of the role.)
-        // a job is runnable when the encoder direction(s) it reads have published the tile's columns
-        auto runnable = [&](const ProjJob& q, unsigned long long c_f, unsigned long long c_r, int chunk) {
-            const unsigned long long base = a.epoch + (unsigned long long)chunk * W;
-            const bool f_ok = c_f >= base + (unsigned long long)(q.t0 + q.valid), r_ok = c_r >= base + (unsigned long long)(W - q.t0);
-            return q.pixel || (split ? (q.src_dir == 0 ? f_ok : r_ok) : (f_ok && r_ok));
-        };
-        auto flag_of = [&](const ProjJob& q) { return a.progress + ((q.wg * WG) / a.rec_n) * 2; };   // [forward, reverse] counters of the tile's CTA
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int n_px = loop ? px_count(chunk) : 0;
-        const int n_jobs = loop ? n_px + n_dec : n_table;
-        const int px_tile0 = pixels ? px_done(a, chunk) : 0;
-        // this chunk's job list -> shared memory (coalesced), pixel entries made absolute: the per-job decisions below then
-        // depend on one global load (the progress counter, requested a job ahead), not on a chain of them
-        if (loop) {
-            __syncwarp();
-            for (int i = lane; i < n_jobs; i += 32) {
-                int e = table_at(i, n_px);
-                if ((e >> 29) & 1) e += px_tile0 << 16;
-                job_tab[i] = e;
-            }
-            __syncwarp();
-        }
-        int front = 0, back = n_jobs - 1, ef = 0, eb = 0;
-        ProjJob jf{}, jb{};
-        unsigned long long vf[2] = {0, 0}, vb[2] = {0, 0};
-        auto poll = [&]() {                                  // lane 0: the counters of both candidates, four loads in flight
-            if (!jf.pixel) { vf[0] = tc::ld_relaxed_gpu(flag_of(jf)); vf[1] = tc::ld_relaxed_gpu(flag_of(jf) + 1); }
-            if (!jb.pixel) { vb[0] = tc::ld_relaxed_gpu(flag_of(jb)); vb[1] = tc::ld_relaxed_gpu(flag_of(jb) + 1); }
-        };
-        auto look = [&]() {                                  // lane 0: both ends of what is left, counters requested
-            ef = job_tab[front]; eb = job_tab[back];
-            jf = proj_decode(a, ef); jb = proj_decode(a, eb);
-            poll();
-        };
-        if (loop && lane == 0 && n_jobs > 0) look();
+        const int n_jobs = jobs_of(chunk);
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int stage = it % n_stages;
             if (it >= n_stages) HB_TIMED(0, tc::mbar_wait(a_empty + stage, (uint32_t)((it / n_stages - 1) & 1)));
             if (loop) {
                 int e = 0;
                 if (lane == 0) {
-#ifdef HB_TIMELINE
-                    const long long t_ = acct ? clock64() : 0;
-#endif
                     const long long t_spin = clock64();
-                    while (true) {
-                        if (front < back && !jb.pixel && runnable(jb, vb[0], vb[1], chunk)) { e = eb | (1 << 30); --back; break; }   // bit 30: the decoder waits for it
-                        if (runnable(jf, vf[0], vf[1], chunk)) { e = ef; ++front; break; }       // pixel jobs wait for nothing
-                        __nanosleep(100);
-                        if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap();
-                        poll();
-                    }
-#ifdef HB_TIMELINE
-                    if (acct) t_wait[1] += clock64() - t_;
-#endif
-                    job_ring[it & 15] = e;
-                    if (front <= back) look();               // for the next job; the loads complete while this one is issued
+                    HB_TIMED(1, while (ld_volatile_shared(sched_count) <= it) { if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap(); });
+                    __threadfence_block();
+                    e = job_ring[it & (PROJ_RING - 1)];
                 }
                 e = __shfl_sync(0xffffffffu, e, 0);
                 j = proj_decode(a, e);
@@ -389,10 +421,9 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
             const long long t_issue = acct ? clock64() : 0;
 #endif
             // geometry of the job's stage: decoder jobs [part hi, lo][K-slice][8 columns][2 KB], pixel jobs [8 columns][xblk].
-            // The job's columns are contiguous per (part, K-slice): ONE copy each (issuing a bulk copy costs the lane
-            // ~180 cycles and the lanes take turns; with two copies per (part, K-slice) this warp needed ~2000 cycles per
-            // job and starved the MMA warp, which needs ~780).  A single-slice job is cut in two so that a CTA pair
-            // always has a copy each to multicast.
+            // The job's columns are contiguous per (part, K-slice): ONE copy each (issuing a bulk copy blocks the lane for
+            // about its size / 48 B per cycle, and the lanes take turns).  A single-slice job is cut in two so that a CTA
+            // pair always has a copy each to multicast.
             const int jparts = j.pixel ? 1 : PARTS, jdirs = j.pixel ? 1 : n_dirs, jblk = j.pixel ? a.px.blk_bytes : blk_bytes;
             const int pieces = jparts * jdirs == 1 ? 2 : 1;
             if (lane == 0) tc::mbar_arrive_expect_tx(a_full + stage, (uint32_t)(j.valid * jparts * jdirs * jblk));
@@ -403,7 +434,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 uint8_t* dst = smem + stage * stage_bytes + (j.pixel ? 0 : part * part_bytes + d * slice_bytes) + c0 * jblk;
                 const uint8_t* src = j.pixel
                     ? a.px.ximg + j.wg * a.px.wg_stride + (int64_t)(j.t0 + c0) * jblk
-                    : in_base + j.wg * in_wg_stride + (split ? j.src_dir : d) * in_dir_stride + part * in_part_stride + (int64_t)(j.t0 + c0) * jblk;
+                    : in_base + j.wg * in_wg_stride + d * in_dir_stride + part * in_part_stride + (int64_t)(j.t0 + c0) * jblk;
                 const uint32_t bytes = (uint32_t)(max(cols, 0) * jblk);
                 // pair mode: the two CTAs split the copies and multicast them to both
                 const bool mine = cols > 0 && (!a.pair || (uint32_t)(lane & 1) == pair_rank);
@@ -413,122 +444,33 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 }
             }
             __syncwarp();
+            if (loop && lane == 0) *loader_count = it + 1;
 #ifdef HB_TIMELINE
             if (acct) t_wait[3] += clock64() - t_issue;
 #endif
         }
         }
         HB_ROLE_REPORT(0);
-    } else if (warp == 6) {
-        // ===================== gi' store =====================
-        // The staged block [valid columns][8 windows][128 gate rows] is contiguous in the gi image: ONE bulk copy per job,
-        // issued by lane 0.  In the chunk-loop kernel the two K-halves of a tile go to the same block: the half this CTA
-        // stores first is a plain copy, the other one a reducing copy (fp32 add at the destination).  Bulk copies of one
-        // thread are not ordered among themselves, so the reducing copy is only issued once the first half's copy is
-        // known to be complete (first_it / n_complete below; the two halves are normally many jobs apart).
-        const int tiles_t = (W + 7) >> 3;
-        // Flags are raised in batches: the release below is a gpu-scope fence (~1 us), one per job would make this warp
-        // the bottleneck of the role.  A batch goes out when PROJ_PUBLISH_BATCH jobs are waiting and after the worker's
-        // last job of a chunk (the decoder starts with the tiles that are projected last, and nothing else in the kernel
-        // waits for a flag while the same chunk's encoder is still feeding this worker).  Flushing whenever the warp
-        // ran dry was tried: it runs dry after almost every job, and each flush waits ~1.5 us for the newest copies.
-        unsigned long long* pending[PROJ_PUBLISH_BATCH];     // flags of the jobs whose copies may still be in flight
-        int n_pending = 0;
-        int n_complete = 0;                                  // jobs [0, n_complete) of this CTA: their copies have been performed
-        auto publish = [&](int keep, int it_now) {           // wait until all but the newest `keep` (0, 1 or 2) jobs have landed, raise their flags
-            if (n_pending <= keep) return;
-            // wait_group (not .read) returns when the copies' writes have been performed; the release below orders them
-            // before the counter.  (An additional fence.proxy.async here cost ~1000 cycles per publication.)
-            if (keep == 0) tc::bulk_wait0(); else if (keep == 1) tc::bulk_wait_pending<1>(); else tc::bulk_wait_pending<2>();
-            n_complete = it_now + 1 - keep;
-#ifdef HB_STRICT_PROXY_FENCE
-            tc::fence_proxy_async_all();
-#endif
-            __syncwarp();
-            if (lane == 0) {                                 // ONE release fence for the whole batch, then relaxed increments
-                tc::fence_acq_rel_gpu();
-                for (int k = 0; k < n_pending - keep; ++k) tc::red_relaxed_gpu_add(pending[k], 1ull);
-            }
-            for (int k = 0; k < keep; ++k) pending[k] = pending[n_pending - keep + k];
-            n_pending = keep;
-        };
-        int it = 0;
-        for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int n_jobs = loop ? px_count(chunk) + n_dec : n_table;
-        // which of this worker's tiles already hold one half in this chunk, and the job that stored it
-        if (split) for (int i = lane; i < PROJ_TILE_SLOTS; i += 32) first_it[i] = -1;
-        __syncwarp();
-        for (int idx = 0; idx < n_jobs; ++idx, ++it) {
-            const int sb = it & 1;
-            const uint32_t par = (uint32_t)((it >> 1) & 1);
-            HB_TIMED(0, tc::mbar_wait(stg_full + sb, par));
-            const int e_ring = loop ? job_ring[it & 15] : 0;
-            j = loop ? proj_decode(a, e_ring) : proj_tile_job(a, worker, n_workers, idx);
-            float* out = j.pixel ? a.px.gi : gi;
-            const int out_cols = j.pixel ? a.px.cols : W;
-            bool second = false;
-            if (split && !j.pixel) {
-                const int slot = (int)((j.wg * tiles_t + (j.t0 >> 3)) / n_workers);       // this worker's tiles, densely numbered
-                const int prev = first_it[slot];
-                second = prev >= 0;
-                __syncwarp();
-                if (!second) { if (lane == 0) first_it[slot] = it; __syncwarp(); }
-                else if (prev >= n_complete) {
-                    // the first half's copy may still be in flight (both halves reached this CTA back to back)
-                    HB_TIMED(2, tc::bulk_wait0());
-                    n_complete = it;
-                }
-            }
-            if (lane == 0) {
-                float* dst = out + gi_block(j.wg, out_cols, j.t0, blk);
-                const uint32_t bytes = (uint32_t)j.valid * GI_BLK_BYTES;
-                if (second) tc::bulk_reduce_add_f32_s2g(dst, staging + sb * PROJ_STG_BYTES, bytes);
-                else tc::bulk_s2g(dst, staging + sb * PROJ_STG_BYTES, bytes);
-            }
-            tc::bulk_commit();
-            // the staging buffer goes back to the epilogue warps as soon as THIS copy has read it (~32 KB of shared-memory
-            // reads); meanwhile they fill the other buffer.  (Releasing a buffer one job later, when the next job had been
-            // staged, serialised epilogue and store: the epilogue warps waited for stg_empty a third of the time.)
-            HB_TIMED(1, tc::bulk_wait_read_pending<0>());
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(stg_empty + sb);
-            if (a.tile_flags != nullptr) {
-                pending[n_pending++] = j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
-                                               : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
-                if (idx == n_jobs - 1) HB_TIMED(2, publish(0, it));                  // last job of the chunk
-                // jobs taken from the back of the list are the ones the decoder is waiting for: small batches (one
-                // publication per job was measured: the fence makes this warp the bottleneck)
-                else if ((e_ring >> 30) & 1) { if (n_pending >= a.urgent_batch + 1) HB_TIMED(3, publish(1, it)); }
-                else if (n_pending == PROJ_PUBLISH_BATCH) HB_TIMED(3, publish(2, it));   // copies issued two jobs ago have normally landed: no stall
-            }
-#ifdef HB_TIMELINE
-            if (a.dbg != nullptr && worker == 0 && blk == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
-#endif
-        }
-        }
-        publish(0, it - 1);
-        tc::bulk_wait0();                                    // the kernel's results are complete when the role returns
-        HB_ROLE_REPORT(3);
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = tc::idesc_f16_f32(128, PROJ_NT);
-        const int ksteps = split ? 8 : (Kp >> 4);
+        const int ksteps = Kp >> 4;
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int n_jobs = loop ? px_count(chunk) + n_dec : n_table;
+        const int n_jobs = jobs_of(chunk);
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int stage = it % n_stages, acc = it & 1;
             HB_TIMED(0, tc::mbar_wait(a_full + stage, (uint32_t)((it / n_stages) & 1)));
-            j = loop ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
+            j = loop ? proj_decode(a, job_ring[it & (PROJ_RING - 1)]) : proj_tile_job(a, worker, n_workers, idx);
             if (it >= 2) HB_TIMED(1, tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1)));
             tc::tc_fence_after();
             if (tc::elect_one()) {
                 const uint32_t sbase = tc::smem_u32(smem + stage * stage_bytes);
                 const uint64_t d_hi = lbo ? tc::smem_desc(sbase, lbo, blk_bytes) : tc::smem_desc_sw128(sbase, blk_bytes);
                 const uint64_t d_lo = lbo ? tc::smem_desc(sbase + part_bytes, lbo, blk_bytes) : tc::smem_desc_sw128(sbase + part_bytes, blk_bytes);
-                const uint32_t a_hi = tmem + PROJ_W_COL0 + (split ? j.src_dir * 64 : 0), a_lo = a_hi + kwords;
+                const uint32_t a_hi = tmem + PROJ_W_COL0, a_lo = a_hi + kwords;
                 const uint32_t d = tmem + acc * PROJ_NT;
-                // Issue loops with compile-time trip counts for the two hot shapes: the operands of every MMA are then
+                // Issue loops with compile-time trip counts for the hot shape: the operands of every MMA are then
                 // immediates on the uniform datapath (a runtime k loop went through R2UR moves: ~80 cycles per MMA).
                 // k-step ks of the stage: K-slice ks / 8 (a slice of the GRU output image is 128 units), then 16 units per step
                 auto issue = [&](auto ksteps_c, auto dirs_c) {
@@ -553,8 +495,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                     const int ksx = a.px.Kp >> 4;
                     for (int ks = 0; ks < ksx; ++ks) tc::mma_f16_ts(d, ax + ks * 8, dx + (uint64_t)(ks * 2 * 128 / 16), idesc, ks != 0);
                     for (int ks = 0; ks < ksx; ++ks) tc::mma_f16_ts(d, ax + kwords_px + ks * 8, dx + (uint64_t)(ks * 2 * 128 / 16), idesc, 1);
-                } else if (split) issue(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
-                else if (n_dirs == 2 && ksteps == 16) issue(std::integral_constant<int, 16>{}, std::integral_constant<int, 2>{});
+                } else if (n_dirs == 2 && ksteps == 16) issue(std::integral_constant<int, 16>{}, std::integral_constant<int, 2>{});
                 else issue(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});     // pixels: K = padded feature count
                 if (a.pair) tc::mma_commit_multicast(a_empty + stage, (uint16_t)3);   // both loaders wait for both consumers
                 else tc::mma_commit(a_empty + stage);
@@ -564,26 +505,30 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         }
         }
         HB_ROLE_REPORT(1);
-    } else {
+    } else if (warp < 4) {
         // ===================== epilogue =====================
         const int r = warp * 32 + lane;                      // gate row within the block == TMEM lane
         const float sc_dec = scale_row[blk * 128 + r], bi_dec = bias_row[blk * 128 + r];
         const float sc_px = pixels ? a.px.scale_row[blk * 128 + r] : 0.f, bi_px = pixels ? a.px.bias_row[blk * 128 + r] : 0.f;
+        const int tiles_t = (W + 7) >> 3;
+        // this row's 8 windows of a column: 32 bytes at r * 32, the two 16-byte halves swapped for rows with bit 2 set
+        // (gi_window_index: the recurrence's 16-byte shared-memory reads are then conflict-free)
+        const int swz = (r >> 2) & 1;
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-        const int n_jobs = loop ? px_count(chunk) + n_dec : n_table;
+        const int n_jobs = jobs_of(chunk);
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
-            const int acc = it & 1, sb = it & 1;
-            if (it >= 2) HB_TIMED(0, tc::mbar_wait(stg_empty + sb, (uint32_t)((it / 2 - 1) & 1)));   // arrives once job it-1 is being stored
-            HB_TIMED(1, tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1)));
-            j = loop ? proj_decode(a, job_ring[it & 15]) : proj_tile_job(a, worker, n_workers, idx);
+            const int acc = it & 1;
+            HB_TIMED(0, tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1)));
+            j = loop ? proj_decode(a, job_ring[it & (PROJ_RING - 1)]) : proj_tile_job(a, worker, n_workers, idx);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
-            float* stg = reinterpret_cast<float*>(staging + sb * PROJ_STG_BYTES) + r;
             const float sc = j.pixel ? sc_px : sc_dec;
-            const float add = j.pixel ? bi_px : ((split && j.src_dir) ? 0.f : bi_dec);   // the bias rides on the forward-source half (or the only one)
+            const float add = j.pixel ? bi_px : bi_dec;
+            const int out_cols = j.pixel ? a.px.cols : W;
+            float* dst = (j.pixel ? a.px.gi : gi) + gi_block(j.wg, out_cols, j.t0, blk) + r * WG;
             // 16 accumulator columns (two image columns x 8 windows) per TMEM round trip, the next load in flight while
-            // the current values are scaled and staged
+            // the current values are scaled and stored
             {
                 float v[2][16];
                 tc::tmem_ld16(taddr, v[0]);
@@ -591,14 +536,35 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 for (int c16 = 0; c16 < PROJ_NT / 16; ++c16) {
                     tc::tmem_ld_wait();
                     if (c16 + 1 < PROJ_NT / 16) tc::tmem_ld16(taddr + (c16 + 1) * 16, v[(c16 + 1) & 1]);
+                    else {                                   // every accumulator column is in registers: hand the buffer back
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(acc_empty + acc);
+                    }
+                    const float* x = v[c16 & 1];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) stg[(c16 * 16 + i) * 128] = fmaf(v[c16 & 1][i], sc, add);
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = 2 * c16 + h;
+                        if (col < j.valid) {
+                            float4* p = reinterpret_cast<float4*>(dst + (size_t)col * GI_BLK_FLOATS);
+                            p[swz] = make_float4(fmaf(x[8 * h], sc, add), fmaf(x[8 * h + 1], sc, add), fmaf(x[8 * h + 2], sc, add), fmaf(x[8 * h + 3], sc, add));
+                            p[swz ^ 1] = make_float4(fmaf(x[8 * h + 4], sc, add), fmaf(x[8 * h + 5], sc, add), fmaf(x[8 * h + 6], sc, add), fmaf(x[8 * h + 7], sc, add));
+                        }
+                    }
                 }
             }
-            tc::tc_fence_before();
-            tc::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) { tc::mbar_arrive(acc_empty + acc); tc::mbar_arrive(stg_full + sb); }
+            if (a.tile_flags != nullptr) {
+                // this warp's part of the tile is visible before its counter moves: every lane fences its own stores, the
+                // warp joins, one lane counts
+                HB_TIMED(1, __threadfence());
+                __syncwarp();
+                if (lane == 0)
+                    tc::red_relaxed_gpu_add(j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
+                                                    : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3), 1ull);
+            }
+#ifdef HB_TIMELINE
+            if (a.dbg != nullptr && worker == 0 && blk == 0 && tid == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
+#endif
         }
         }
         if (warp == 0) HB_ROLE_REPORT(2);
@@ -1018,8 +984,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 
         // everything below that does not change from step to step stays in registers
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
-        // stage: [group][gate][window in group][unit]; this thread's NW windows lie in one group
-        const float* gs0 = reinterpret_cast<const float*>(gi_s) + (win0 / WG) * (3 * GI_BLK_FLOATS) + (win0 % WG) * H + j;
+        // stage: [group][gate][unit][window in group]; this thread's NW windows lie in one group
+        const float* gs0 = reinterpret_cast<const float*>(gi_s) + (win0 / WG) * (3 * GI_BLK_FLOATS);
         auto load_acc = [](uint32_t addr, float* a) {
             tc::tmem_ld_n<NW>(addr, a);
             if constexpr (STACK) {
@@ -1048,8 +1014,9 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             float gir[NW], giz[NW], gin[NW];
             {
                 const float* gs = gs0 + stage * (GI_STAGE_BYTES / 4);
-#pragma unroll
-                for (int i = 0; i < NW; ++i) { gir[i] = gs[i * H]; giz[i] = gs[GI_BLK_FLOATS + i * H]; gin[i] = gs[2 * GI_BLK_FLOATS + i * H]; }
+                gi_load<NW>(gs, j, win0 % WG, gir);
+                gi_load<NW>(gs + GI_BLK_FLOATS, j, win0 % WG, giz);
+                gi_load<NW>(gs + 2 * GI_BLK_FLOATS, j, win0 % WG, gin);
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(gi_empty + stage);
@@ -1310,35 +1277,37 @@ tc_recurrence2_kernel(const RecArgs ra)
         for (int s = 0; s < W; ++s) {
             const int stage = s % ST;
             const uint32_t par = (uint32_t)(s & 1);
-            const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + (win0 / WG) * (3 * GI_BLK_FLOATS) + (win0 % WG) * H + j;
-            float r[NW], z[NW], a[NW];
+            const int nb = (s + 1) % NBUF;
+            // stage: [group][gate][unit][window in group]; this thread's NW windows lie in one group
+            const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + (win0 / WG) * (3 * GI_BLK_FLOATS);
+            float a[NW], gir[NW], giz[NW], gin[NW];
+            GateR gr[NW];
+            GateZ gz[NW];
             tc::mbar_wait(gi_full(tile) + stage, (uint32_t)((s / ST) & 1));
+            if (s >= NBUF) tc::mbar_wait(h_free(tile) + nb, (uint32_t)(((s - NBUF) / NBUF) & 1));
+            gi_load<NW>(gs, j, win0 % WG, gir);
+            gi_load<NW>(gs + GI_BLK_FLOATS, j, win0 % WG, giz);
+            gi_load<NW>(gs + 2 * GI_BLK_FLOATS, j, win0 % WG, gin);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(gi_empty(tile) + stage);
             tc::mbar_wait(acc_ready(tile) + 0, par);
             tc::tc_fence_after();
             load_acc(taddr, a);
 #pragma unroll
-            for (int i = 0; i < NW; ++i) r[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_r, gs[i * H])));
+            for (int i = 0; i < NW; ++i) gr[i] = gate_r(a[i], inv_r, gir[i], inv_n, bhn, gin[i]);
             tc::mbar_wait(acc_ready(tile) + 1, par);
             tc::tc_fence_after();
             load_acc(taddr + NACC, a);
 #pragma unroll
-            for (int i = 0; i < NW; ++i) z[i] = tc::rcp_approx(1.0f + tc::ex2_approx(fmaf(a[i], inv_z, gs[GI_BLK_FLOATS + i * H])));
-            float gin[NW];
-#pragma unroll
-            for (int i = 0; i < NW; ++i) gin[i] = gs[2 * GI_BLK_FLOATS + i * H];
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(gi_empty(tile) + stage);
-            uint8_t* h_hi = h_img + (((s + 1) % NBUF) * 2) * HB_BYTES;
+            for (int i = 0; i < NW; ++i) gz[i] = gate_z(a[i], inv_z, giz[i]);
+            uint8_t* h_hi = h_img + (nb * 2) * HB_BYTES;
             uint8_t* h_lo = h_hi + HB_BYTES;
-            if (s >= NBUF) tc::mbar_wait(h_free(tile) + ((s + 1) % NBUF), (uint32_t)(((s - NBUF) / NBUF) & 1));
             tc::mbar_wait(acc_ready(tile) + 2, par);
             tc::tc_fence_after();
             load_acc(taddr + 2 * NACC, a);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
-                const float e = tc::ex2_approx(fmaf(r[i], fmaf(a[i], inv_n, bhn), gin[i]));
-                const float n = fmaf(2.0f * ACT_SCALE, tc::rcp_approx(1.0f + e), -ACT_SCALE);
-                const float hn = fmaf(z[i], h_own[i] - n, n);
+                const float hn = gate_n(a[i], gr[i], gz[i], h_own[i]);
                 h_own[i] = hn;
                 __half hi, lo;
                 tc::split_f16(hn, hi, lo);
@@ -1348,7 +1317,7 @@ tc_recurrence2_kernel(const RecArgs ra)
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) { tc::mbar_arrive(h_ready(tile)); tc::mbar_arrive(y_ready(tile) + ((s + 1) % NBUF)); }
+            if (lane == 0) { tc::mbar_arrive(h_ready(tile)); tc::mbar_arrive(y_ready(tile) + nb); }
         }
         if (ra.h_out != nullptr) {
 #pragma unroll
@@ -1672,9 +1641,6 @@ struct TensorTuning {
     bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
     bool pingpong = true;       // HB_NO_PINGPONG: one window tile per recurrence CTA in the per-chunk kernels of large batches
     bool cooperative = true;    // HB_NO_COOPERATIVE: chunk-loop kernel launched without the cooperative attribute
-    bool ksplit = false;        // HB_PROJ_KSPLIT: chunk-loop projection as K-half jobs (runnable per encoder direction, second half added by a reducing
-                                // bulk copy) instead of one whole-K job per column tile
-    int urgent_batch = 0;       // HB_PROJ_URGENT_BATCH: see ProjArgs::urgent_batch (0: 3 with K-half jobs, 2 with whole-tile jobs)
     int gate_warps = 8;         // HB_GATE_WARPS = 8 | 16: gate warps of the chunk-loop kernel's recurrence role (4 or 2 windows per thread at 8-window
                                 // tiles).  Measured at B=256: 85.8 k windows/s with 8, 81.7 k with 16 (fewer warps share the per-step waits, TMEM loads,
                                 // fences; with 16 the shared-memory fence before the arrive costs 150-190 cycles instead of ~90)
@@ -1688,8 +1654,6 @@ struct TensorTuning {
         t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
         t.pingpong = getenv("HB_NO_PINGPONG") == nullptr;
         t.cooperative = getenv("HB_NO_COOPERATIVE") == nullptr;
-        t.ksplit = getenv("HB_PROJ_KSPLIT") != nullptr;
-        if (const char* v = getenv("HB_PROJ_URGENT_BATCH")) t.urgent_batch = std::min(std::max(atoi(v), 1), PROJ_PUBLISH_BATCH - 2);
         if (const char* v = getenv("HB_GATE_WARPS")) { if (atoi(v) == 8 || atoi(v) == 16) t.gate_warps = atoi(v); }
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
             const int n = atoi(v);
@@ -1708,7 +1672,7 @@ struct TensorEngine {
     size_t proj_jobs_capacity = 0;            // fixed at creation: a batch whose table does not fit takes per-chunk launches
     int loop_max_ctas8 = 0, loop_max_ctas16 = 0;   // CTAs of the chunk-loop kernel (8- / 16-window tiles) that can be resident at once
     bool coop_with_pdl = true;                // cleared if the driver refuses cooperative + programmatic serialization together
-    int jobs_w = -1, jobs_workers = -1, jobs_pixels = -1, jobs_ksplit = -1; int64_t jobs_n_wg = -1;
+    int jobs_w = -1, jobs_workers = -1, jobs_pixels = -1; int64_t jobs_n_wg = -1;
     int* proj_px_wgs = nullptr;               // [workers] window groups whose pixel jobs a worker owns
     std::vector<int> proj_jobs_host, proj_job_offsets_host, proj_px_wgs_host;
     int tile_order_w = -1;
@@ -1902,7 +1866,7 @@ inline void free_layer(TensorLayer* L) {
 }
 
 // (+1024: the kernels align their shared memory to the swizzle atom themselves)
-inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 2 * PROJ_STG_BYTES + 256 + (PROJ_TILE_SLOTS + PROJ_TABLE_MAX) * 4 + 1024; }
+inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 256 + PROJ_TABLE_MAX * 4 + 1024; }
 template <int N, int NLIVE = N>
 constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<NLIVE>() * NLIVE * GI_ROW_BYTES + 512 + 1024; }
 constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128 + 1024; }
@@ -2104,9 +2068,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         if (pixels_in_loop && flags_needed + n_groups * px_tiles * 2 > e->flags_capacity) pixels_in_loop = false;
         if (pixels_in_loop) flags_needed += n_groups * px_tiles * 2;
         const int64_t worker_tiles = (n_wg * tiles8 + plan.proj_workers - 1) / plan.proj_workers;    // tiles one projection worker owns
-        const int64_t worker_jobs = 2 * worker_tiles + (n_wg + plan.proj_workers - 1) / plan.proj_workers * PX_R;
-        chunkloop = flags_needed <= e->flags_capacity && worker_tiles <= PROJ_TILE_SLOTS && worker_jobs <= PROJ_TABLE_MAX &&
-                    (size_t)n_wg * (2 * tiles8 + (pixels_in_loop ? PX_R : 0)) <= e->proj_jobs_capacity;   // tables sized at creation / in shared memory
+        const int64_t worker_jobs = worker_tiles + (n_wg + plan.proj_workers - 1) / plan.proj_workers * PX_R;
+        chunkloop = flags_needed <= e->flags_capacity && worker_jobs <= PROJ_TABLE_MAX &&
+                    (size_t)n_wg * (tiles8 + (pixels_in_loop ? PX_R : 0)) <= e->proj_jobs_capacity;   // tables sized at creation / in shared memory
         pixels_in_loop = pixels_in_loop && chunkloop;
     }
     if (enc_cols > 0) {
@@ -2180,23 +2144,16 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             TE_CUDA(cudaMemcpyAsync(e->tile_order16, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
             e->tile_order_w = W;
         }
-        const bool ksplit = e->tune.ksplit;
-        if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg || e->jobs_pixels != (int)pixels_in_loop ||
-            e->jobs_ksplit != (int)ksplit) {
-            // projection job table: tile (group, tile) belongs to worker (group * tiles + tile) % workers; a worker takes
-            // the halves of its tiles in the order the encoder makes them runnable (forward half of tile t after step
-            // 8t+8, reverse half after step W-8t)
+        if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg || e->jobs_pixels != (int)pixels_in_loop) {
+            // projection job table: tile (group, tile) belongs to worker (group * tiles + tile) % workers; a worker takes its
+            // tiles in the order the encoder makes them runnable (the forward pass has stored tile t after step 8t+8, the
+            // reverse pass after step W-8t: the later of the two)
             struct Job { int ready, id, packed; };
             std::vector<std::vector<Job>> per(plan.proj_workers);
             for (int64_t wg = 0; wg < n_wg; ++wg)
                 for (int t = 0; t < tiles8; ++t) {
                     const int id = (int)(wg * tiles8 + t);
-                    if (ksplit) {
-                        per[id % plan.proj_workers].push_back({std::min(8 * t + 8, W), id, pack_proj_job((int)wg, t, 0)});
-                        per[id % plan.proj_workers].push_back({W - 8 * t, id, pack_proj_job((int)wg, t, 1)});
-                    } else {                                   // whole tile: runnable when the later of the two directions has stored it
-                        per[id % plan.proj_workers].push_back({std::max(std::min(8 * t + 8, W), W - 8 * t), id, pack_proj_job((int)wg, t, 0)});
-                    }
+                    per[id % plan.proj_workers].push_back({std::max(std::min(8 * t + 8, W), W - 8 * t), id, pack_proj_job((int)wg, t)});
                 }
             e->proj_jobs_host.clear();
             e->proj_job_offsets_host.assign(1, 0);
@@ -2211,7 +2168,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                     for (int64_t wg = wk; wg < n_wg; wg += plan.proj_workers) mine.push_back((int)wg);
                     e->proj_px_wgs_host[wk] = (int)mine.size();
                     for (int r = 0; r < PX_R; ++r)
-                        for (int wg : mine) e->proj_jobs_host.push_back(pack_proj_job(wg, r, 0) | (1 << 29));
+                        for (int wg : mine) e->proj_jobs_host.push_back(pack_proj_job(wg, r) | (1 << 29));
                 }
                 std::stable_sort(v.begin(), v.end(), [](const Job& x, const Job& y) { return x.ready != y.ready ? x.ready < y.ready : x.id < y.id; });
                 for (const Job& jb : v) e->proj_jobs_host.push_back(jb.packed);
@@ -2225,7 +2182,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             TE_CUDA(cudaMemcpyAsync(e->proj_jobs, e->proj_jobs_host.data(), e->proj_jobs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
             TE_CUDA(cudaMemcpyAsync(e->proj_job_offsets, e->proj_job_offsets_host.data(), e->proj_job_offsets_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
             TE_CUDA(cudaMemcpyAsync(e->proj_px_wgs, e->proj_px_wgs_host.data(), e->proj_px_wgs_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-            e->jobs_w = W; e->jobs_workers = plan.proj_workers; e->jobs_n_wg = n_wg; e->jobs_pixels = (int)pixels_in_loop; e->jobs_ksplit = (int)ksplit;
+            e->jobs_w = W; e->jobs_workers = plan.proj_workers; e->jobs_n_wg = n_wg; e->jobs_pixels = (int)pixels_in_loop;
         }
         TE_CUDA(cudaMemsetAsync(e->flags, 0, flags_needed * sizeof(unsigned long long), s));
         unsigned long long* f = e->flags;
@@ -2236,14 +2193,14 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         unsigned long long* px_flags = f;                                              // [group][image column tile][enc direction]
         RecArgs ra{};
         ra.layer[0] = layer_args(e->enc, ws.gi_enc, enc_cols, 0, J, ws.yimg1, ws.yimg1);
-        ra.layer[0].progress = enc_prog; ra.layer[0].consumed_flags = tile_flags; ra.layer[0].consumed_per_chunk = ksplit ? 6 : 3;
+        ra.layer[0].progress = enc_prog; ra.layer[0].consumed_flags = tile_flags; ra.layer[0].consumed_per_chunk = PROJ_FLAGS_PER_TILE;
         ra.layer[1] = layer_args(e->dec, ws.gi, W, 0, 0, ws.yimg2[0], ws.yimg2[1]);
         ra.layer[1].progress = dec_prog; ra.layer[1].tile_flags = tile_flags;
         ra.layer[1].flag_tiles = tiles8; ra.layer[1].flag_abs = 0; ra.layer[1].flag_skip_tiles = 0;
-        ra.layer[1].flag_need_base = 0; ra.layer[1].flag_need_per_chunk = ksplit ? 6 : 3;   // gate blocks (x K-halves) per tile and chunk
+        ra.layer[1].flag_need_base = 0; ra.layer[1].flag_need_per_chunk = PROJ_FLAGS_PER_TILE;
         if (pixels_in_loop) {
             ra.layer[0].tile_flags = px_flags; ra.layer[0].flag_tiles = px_tiles; ra.layer[0].flag_abs = 1;
-            ra.layer[0].flag_skip_tiles = px_pre_tiles; ra.layer[0].flag_need_base = 3; ra.layer[0].flag_need_per_chunk = 0;
+            ra.layer[0].flag_skip_tiles = px_pre_tiles; ra.layer[0].flag_need_base = PROJ_FLAGS_PER_TILE; ra.layer[0].flag_need_per_chunk = 0;
         }
         ra.layer[1].heads_done = heads_done; ra.layer[1].heads_per_chunk = 4 * tiles16;
         ra.n_layers = 2; ra.n_chunks = n_chunks; ra.h_in = nullptr; ra.h_out = nullptr; ra.B = B; ra.W = W;
@@ -2252,8 +2209,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         pp.progress = enc_prog; pp.epoch = 0; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
         pp.pair = 0;          // every CTA of the role picks its own job order (see the loader): no shared tiles
         pp.dbg = dbg_buf;
-        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets; pp.ksplit = ksplit ? 1 : 0;
-        pp.urgent_batch = e->tune.urgent_batch ? e->tune.urgent_batch : (ksplit ? 3 : 2);
+        pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets; 
         if (pixels_in_loop) {
             pp.px.ximg = reinterpret_cast<const uint8_t*>(ws.ximg); pp.px.wg_stride = (int64_t)T * xblk; pp.px.blk_bytes = xblk; pp.px.Kp = e->enc.Kp;
             pp.px.w_tmem = e->enc.wih_tmem; pp.px.scale_row = e->enc.scale_row; pp.px.bias_row = e->enc.bias_row;
@@ -2386,9 +2342,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                             (hbuf[4096 + (64 + k) * 2] - t0) * 1e-3, (hbuf[4096 + (64 + k) * 2 + 1] - t0) * 1e-3,
                             (hbuf[7000 + k] - t0) * 1e-3, (hbuf[7100 + k] - t0) * 1e-3);
                 {
-                    const char* role[4] = {"loader  ", "MMA     ", "epilogue", "store   "};
-                    const char* what[4][4] = {{"a_empty", "progress", "proxy fence", "issue copies"}, {"a_full", "acc_empty", "-", "-"},
-                                              {"stg_empty", "acc_full", "-", "-"}, {"stg_full", "smem read", "chunk-end flush", "batch publish"}};
+                    const char* role[4] = {"loader   ", "MMA      ", "epilogue ", "scheduler"};
+                    const char* what[4][4] = {{"a_empty", "job ring", "-", "issue copies"}, {"a_full", "acc_empty", "-", "-"},
+                                              {"acc_full", "gpu fence", "-", "-"}, {"loader lead", "progress", "-", "-"}};
                     fprintf(stderr, "  projection worker 0 / block 0, cycles waiting over the whole launch (%d chunks):\n", n_chunks);
                     for (int r = 0; r < 4; ++r) {
                         const long long* w = &hbuf[7200 + 8 * r];

@@ -48,9 +48,7 @@ VARIANTS = {
     "chunkloop_16_gate_warps": {"HB_GATE_WARPS": "16"},
     "chunkloop_16_gate_warps_tile16": {"HB_GATE_WARPS": "16", "HB_WINDOWS_PER_CTA": "16"},
     "chunkloop_not_cooperative": {"HB_NO_COOPERATIVE": "1"},
-    "chunkloop_k_half_jobs": {"HB_PROJ_KSPLIT": "1"},
-    "chunkloop_k_half_jobs_16_gate_warps": {"HB_PROJ_KSPLIT": "1", "HB_GATE_WARPS": "16"},
-    "chunkloop_urgent_batch_1": {"HB_PROJ_URGENT_BATCH": "1"},
+    "chunkloop_many_heads_workers": {"HB_HEADS_WORKERS": "24"},
 }
 
 
@@ -60,7 +58,7 @@ def test_kernel_variants_match_fp32_engine(variant, monkeypatch):
     environment when the handle is created) against the fp32 engine, same tolerance as above."""
     from helen_b200.predictor import WindowPredictor
     for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8", "HB_NO_PIXEL_JOBS", "HB_NO_PINGPONG",
-              "HB_GATE_WARPS", "HB_NO_COOPERATIVE", "HB_PROJ_KSPLIT", "HB_PROJ_URGENT_BATCH"):
+              "HB_GATE_WARPS", "HB_NO_COOPERATIVE"):
         monkeypatch.delenv(k, raising=False)
     batch, seq, features = 45, 250, 10
     sd = random_state_dict(features, seed=5)
