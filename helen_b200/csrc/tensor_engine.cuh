@@ -131,8 +131,9 @@ pileup_to_operand_image_kernel(const uint8_t* __restrict__ images, int64_t B, in
 // Input projection  gi'[m, 0:768] = scale_row * (A[m, :] . Wcat^T) + bias_row
 // grid = (workers, 6 gate blocks).  The CTA's [128 x Kp] weight block (hi, lo) is TMEM-resident;
 // a tile is 64 data rows = 8 windows x 8 consecutive columns, staged by bulk copies.
-// Warps 0-3: epilogue (TMEM lane quarter = warp).  Warp 4: MMA issuer.  Warp 5: tile loader.  Warp 6 (chunk-loop kernel
-// only): job scheduler.
+// Warps 0-3 and 7-10: two epilogue groups (TMEM lane quarter = warp % 4), one per accumulator buffer, so that one group's
+// gpu-scope fence (~1700 cycles under load) overlaps the other group's tile.  Warp 4: MMA issuer.  Warp 5: tile loader.
+// Warp 6 (chunk-loop kernel only): job scheduler.
 // The epilogue writes gi' straight from registers: a thread owns one gate row (its TMEM lane) and the 8 windows of a column
 // are contiguous in the gi image, so a column is two 16-byte stores per thread and 1 KB contiguous per warp.  (Staging the
 // block in shared memory for a bulk store was the first version: one 32 KB bulk store took ~1700 cycles to issue and drain
@@ -142,7 +143,7 @@ pileup_to_operand_image_kernel(const uint8_t* __restrict__ images, int64_t B, in
 // The epilogue folds the bias sums and the -log2(e) factors of the gate nonlinearities into gi'
 // (see tc_recurrence_kernel), so gi' is NOT the plain pre-activation of the fp32 engine.
 // ---------------------------------------------------------------------------------------------
-constexpr int PROJ_THREADS = 224;                // warps 0-3 epilogue, 4 MMA issuer, 5 tile loader, 6 job scheduler
+constexpr int PROJ_THREADS = 352;                // warps 0-3 and 7-10 epilogue (two groups), 4 MMA issuer, 5 tile loader, 6 job scheduler
 constexpr int PROJ_NT = 64;
 constexpr int PROJ_STAGES = 3;                    // input stages (64 KB each for the decoder's K = 256, hi and lo parts)
 constexpr int PROJ_TABLE_MAX = 1024;              // chunk-loop kernel: jobs of one worker per chunk (the scheduler keeps the list in shared memory)
@@ -505,9 +506,10 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         }
         }
         HB_ROLE_REPORT(1);
-    } else if (warp < 4) {
-        // ===================== epilogue =====================
-        const int r = warp * 32 + lane;                      // gate row within the block == TMEM lane
+    } else {
+        // ===================== epilogue: group 0 (warps 0-3) takes the even jobs / accumulator 0, group 1 (warps 7-10) the odd ones
+        const int grp = warp < 4 ? 0 : 1;
+        const int r = (warp & 3) * 32 + lane;                // gate row within the block == TMEM lane
         const float sc_dec = scale_row[blk * 128 + r], bi_dec = bias_row[blk * 128 + r];
         const float sc_px = pixels ? a.px.scale_row[blk * 128 + r] : 0.f, bi_px = pixels ? a.px.bias_row[blk * 128 + r] : 0.f;
         const int tiles_t = (W + 7) >> 3;
@@ -519,10 +521,11 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         const int n_jobs = jobs_of(chunk);
         for (int idx = 0; idx < n_jobs; ++idx, ++it) {
             const int acc = it & 1;
+            if (acc != grp) continue;
             HB_TIMED(0, tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1)));
             j = loop ? proj_decode(a, job_ring[it & (PROJ_RING - 1)]) : proj_tile_job(a, worker, n_workers, idx);
             tc::tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * PROJ_NT;
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + acc * PROJ_NT;
             const float sc = j.pixel ? sc_px : sc_dec;
             const float add = j.pixel ? bi_px : bi_dec;
             const int out_cols = j.pixel ? a.px.cols : W;
@@ -563,7 +566,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                                                     : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3), 1ull);
             }
 #ifdef HB_TIMELINE
-            if (a.dbg != nullptr && worker == 0 && blk == 0 && tid == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
+            if (a.dbg != nullptr && worker == 0 && blk == 0 && (warp & 3) == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
 #endif
         }
         }
@@ -848,7 +851,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         // ===================== gi loader: bulk copies, GI_STAGES steps ahead =====================
         // (the first GI_STAGES rows are requested before the phase's start barrier: the stages are free and the
         // prefetch then overlaps the W_hh upload of the gate warps)
-        if (phase == 0) tc::pdl_grid_dependency_wait();      // gi' comes from an upstream kernel
+        if (phase == 0) { tc::pdl_grid_dependency_wait(); tc::fence_proxy_async_all(); }   // gi' comes from an upstream kernel (generic-proxy stores)
         bool synced = false;
         // lane 3 g + gate fetches that gate block (4 KB) of group g's column
         const int lg = min(lane / 3, NG - 1), lgate = lane % 3;
@@ -863,9 +866,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 if (lane < NG && cta_x * NG + lane < ra.n_wg)
                     tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NG + lane) * L.flag_tiles + (col >> 3)) * 2 + dir,
                                       L.flag_need_base + L.flag_need_per_chunk * (unsigned long long)(chunk + 1));
-                // (no proxy fence: the bulk loads below are issued after the acquire and read L2, where the producer's
-                // completed bulk stores already are)
+                // the projection role wrote the tile with ordinary (generic-proxy) stores and fenced them before it raised
+                // the counter; the bulk loads below belong to the async proxy: order them after what the acquire made visible
                 __syncwarp();
+                tc::fence_proxy_async_all();
             }
             if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
             if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, NG * GI_GRP_BYTES);
@@ -1158,6 +1162,7 @@ tc_recurrence2_kernel(const RecArgs ra)
     if (warp == REC_GATE_WARPS + 1) {
         // ===================== gi' loader: both tiles, ST steps ahead =====================
         tc::pdl_grid_dependency_wait();
+        tc::fence_proxy_async_all();                         // gi' was written with generic-proxy stores, the bulk loads are async-proxy reads
         bool synced = false;
         // lanes [8 tile + 3 g, + 3): the three gate blocks (4 KB each) of group g of a tile
         const int tile_l = lane >> 3, g_l = min((lane & 7) / 3, NG - 1), gate_l = (lane & 7) % 3;

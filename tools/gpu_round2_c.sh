@@ -2,8 +2,9 @@
 # round 2: projection loader (job list in shared memory, one copy per part), staging released per job; 8 gate warps by default
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_report.jsonl
-timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
+for i in 1 2 3; do timeout 600 python -m pytest tests/test_gpu_tensor_stages.py tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -3; done
 run() {  # name, env...
     name=$1; shift
     env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --sustained-seconds 1 > "gpurun_out/bench_${name}.json" 2> "gpurun_out/bench_${name}.err"
