@@ -64,10 +64,19 @@ constexpr int GI_GRP_BYTES = 3 * GI_BLK_BYTES;    // 12288 B: the three gate blo
 __host__ __device__ constexpr int64_t gi_block(int64_t wg, int64_t cols, int64_t t, int blk) { return ((wg * 6 + blk) * cols + t) * GI_BLK_FLOATS; }
 // float index of (unit u, window w of the group) inside a block
 __host__ __device__ constexpr int gi_window_index(int u, int w) { return u * WG + ((((w >> 2) ^ (u >> 2)) & 1) << 2) + (w & 3); }
+// The shared-memory loads of a stage must have RETURNED before the stage is handed back to the bulk-copy engine: an
+// mbarrier arrive does not wait for the warp's outstanding loads (with 8 windows per thread - six 16-byte loads in flight -
+// the refill was seen to overtake the last ones once in ~50 launches).  Naming the registers here makes the arrive depend on them.
+template <int NW>
+__device__ __forceinline__ void gi_loads_done(const float* r, const float* z, const float* n) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) asm volatile("" ::"f"(r[i]), "f"(z[i]), "f"(n[i]) : "memory");
+}
 // a gate thread's NW consecutive windows (starting at w0, a multiple of NW) of unit u: one or two vector loads
 template <int NW>
 __device__ __forceinline__ void gi_load(const float* blk, int u, int w0, float* out) {
     static_assert(NW == 2 || NW == 4 || NW == 8, "windows per gate thread");
+
     if constexpr (NW == 2) {
         const float2 v = *reinterpret_cast<const float2*>(blk + gi_window_index(u, w0));
         out[0] = v.x; out[1] = v.y;
@@ -150,6 +159,7 @@ constexpr int PROJ_TABLE_MAX = 1024;              // chunk-loop kernel: jobs of 
 constexpr int PROJ_RING = 16;                     // job ids in flight between scheduler / loader / MMA issuer / epilogue
 constexpr int PROJ_SCHED_LEAD = 4;                // jobs the scheduler may decide ahead of the loader
 constexpr int PROJ_FLAGS_PER_TILE = 12;           // counter increments that complete a (group, tile, direction): 3 gate blocks x 4 epilogue warps
+constexpr int PROJ_FLAG_BATCH = 4;                // jobs of an epilogue group whose counters may wait for one common fence
 constexpr int PROJ_W_COL0 = 128;
 
 // Encoder input projection inside the chunk-loop kernel ("pixel jobs"): while the encoder of chunk k runs, the projection
@@ -415,6 +425,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 }
                 e = __shfl_sync(0xffffffffu, e, 0);
                 j = proj_decode(a, e);
+
             } else {
                 j = proj_tile_job(a, worker, n_workers, idx);
             }
@@ -516,6 +527,12 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
         // this row's 8 windows of a column: 32 bytes at r * 32, the two 16-byte halves swapped for rows with bit 2 set
         // (gi_window_index: the recurrence's 16-byte shared-memory reads are then conflict-free)
         const int swz = (r >> 2) & 1;
+        // Counters are raised in batches: the gpu-scope fence that makes a tile's stores visible waits for the newest
+        // stores to be acknowledged (~2000 cycles under load), so one fence covers up to PROJ_FLAG_BATCH tiles - except
+        // for the tiles the decoder is waiting for (taken from the back of the job list) and the group's last tile of a
+        // chunk, which go out at once together with everything pending.
+        unsigned long long* pending[PROJ_FLAG_BATCH];
+        int n_pending = 0;
         int it = 0;
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
         const int n_jobs = jobs_of(chunk);
@@ -557,13 +574,18 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 }
             }
             if (a.tile_flags != nullptr) {
-                // this warp's part of the tile is visible before its counter moves: every lane fences its own stores, the
-                // warp joins, one lane counts
-                HB_TIMED(1, __threadfence());
-                __syncwarp();
-                if (lane == 0)
-                    tc::red_relaxed_gpu_add(j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
-                                                    : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3), 1ull);
+                pending[n_pending++] = j.pixel ? a.px.flags + ((j.wg * a.px.tiles + (j.t0 >> 3)) * 2 + blk / 3)
+                                               : a.tile_flags + ((j.wg * tiles_t + (j.t0 >> 3)) * 2 + blk / 3);
+                const bool urgent = loop && ((job_ring[it & (PROJ_RING - 1)] >> 30) & 1);
+                if (urgent || n_pending == PROJ_FLAG_BATCH || idx + 2 >= n_jobs) {
+                    // this warp's part of the tiles is visible before their counters move: every lane fences its own
+                    // stores, the warp joins, one lane counts
+                    HB_TIMED(1, __threadfence());
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int k = 0; k < n_pending; ++k) tc::red_relaxed_gpu_add(pending[k], 1ull);
+                    n_pending = 0;
+                }
             }
 #ifdef HB_TIMELINE
             if (a.dbg != nullptr && worker == 0 && blk == 0 && (warp & 3) == 0 && lane == 0) a.dbg[7000 + chunk] = (long long)globaltimer_ns();
@@ -661,10 +683,13 @@ struct RecArgs {
 
 // W_hh of one direction -> TMEM, spread over `n_warps` gate warps (a multiple of 4).  A warp covers TMEM lanes
 // 32 (w%4)..+31 (thread = gate row); the warps of a lane quarter split the four (hi | lo image) x (k-pair columns 0-31 |
-// 32-63) pieces; 32 words in flight per round trip, two register buffers so that the loads of gate block gb+1 are in
-// flight while block gb is stored.
-// (not inlined: its 64 staging registers would otherwise push the gate loop's state into local memory)
-__device__ __noinline__ void upload_whh(const uint32_t* __restrict__ whh_tmem, const int dir, const uint32_t tmem, const int warp,
+// 32-63) pieces; 32 words in flight per round trip.  kTwoBuffers: the loads of gate block gb+1 are in flight while block gb
+// is stored (64 staging registers; with 16 gate warps the register budget is 96 per thread and the second buffer would
+// push the gate loop's state into local memory).
+// Must be inlined: as a separate function (tried, to keep its registers out of the caller's allocation) the chunk-loop
+// kernel produced a wrong step about once in 50 launches with 8 windows per gate thread; inlined, 0 in 400.
+template <bool kTwoBuffers>
+__device__ __forceinline__ void upload_whh(const uint32_t* __restrict__ whh_tmem, const int dir, const uint32_t tmem, const int warp,
                                            const int lane, const int n_warps)
 {
     const int q = warp & 3, row = q * 32 + lane;
@@ -680,13 +705,22 @@ __device__ __noinline__ void upload_whh(const uint32_t* __restrict__ whh_tmem, c
             tc::tmem_st16(dst, r);
             tc::tmem_st16(dst + 16, r + 16);
         };
-        uint32_t ra0[32], ra1[32];
-        fetch(0, ra0);
-        fetch(1, ra1);
-        store(0, ra0);
-        fetch(2, ra0);
-        store(1, ra1);
-        store(2, ra0);
+        if constexpr (kTwoBuffers) {
+            uint32_t ra0[32], ra1[32];
+            fetch(0, ra0);
+            fetch(1, ra1);
+            store(0, ra0);
+            fetch(2, ra0);
+            store(1, ra1);
+            store(2, ra0);
+        } else {
+#pragma unroll 1
+            for (int gb = 0; gb < 3; ++gb) {
+                uint32_t ra0[32];
+                fetch(gb, ra0);
+                store(gb, ra0);
+            }
+        }
     }
     tc::tmem_st_wait();
 }
@@ -704,6 +738,7 @@ __device__ __forceinline__ GateZ gate_z(float acc, float inv_z, float giz) {
     return GateZ{1.0f + ez, ez * ACT_SCALE};
 }
 __device__ __forceinline__ float gate_n(float acc, const GateR& gr, const GateZ& gz, float h) {
+
     const float e = tc::ex2_approx(fminf(fmaf(acc, gr.c1, gr.c2), EXP2_CLAMP));
     const float p = 1.0f + e;
     const float num = fmaf(h, p, fmaf(-e, gz.k, gz.k));           // h (1 + e) + 2^10 ez (1 - e)
@@ -962,7 +997,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         if (phase == 0 || n_layers > 1)
             // W_hh of this phase's layer -> TMEM.  (All MMAs of the previous phase have completed: every gate warp waited
             // for its last accumulator.)
-            upload_whh(L.whh_tmem, dir, tmem, warp, lane, GW);
+            upload_whh<GW == 8>(L.whh_tmem, dir, tmem, warp, lane, GW);
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
         const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
         uint32_t h_off[NW];
@@ -1022,6 +1057,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 gi_load<NW>(gs + GI_BLK_FLOATS, j, win0 % WG, giz);
                 gi_load<NW>(gs + 2 * GI_BLK_FLOATS, j, win0 % WG, gin);
             }
+            gi_loads_done<NW>(gir, giz, gin);
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(gi_empty + stage);
             if (++stage == GI_STAGES) { stage = 0; gi_par ^= 1u; }
@@ -1244,7 +1280,7 @@ tc_recurrence2_kernel(const RecArgs ra)
         // ===================== gate warps =====================
         const int tile = warp / GW, wi = warp % GW;
         const int q = wi & 3, j = q * 32 + lane, win0 = (wi >> 2) * NW;
-        upload_whh(L.whh_tmem, dir, tmem, warp, lane, REC_GATE_WARPS);   // W_hh -> TMEM, split over all gate warps
+        upload_whh<true>(L.whh_tmem, dir, tmem, warp, lane, REC_GATE_WARPS);   // W_hh -> TMEM, split over all gate warps
         uint8_t* h_img = h_img_of(tile);
         const uint8_t* gi_s = gi_of(tile);
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
@@ -1293,6 +1329,7 @@ tc_recurrence2_kernel(const RecArgs ra)
             gi_load<NW>(gs, j, win0 % WG, gir);
             gi_load<NW>(gs + GI_BLK_FLOATS, j, win0 % WG, giz);
             gi_load<NW>(gs + 2 * GI_BLK_FLOATS, j, win0 % WG, gin);
+            gi_loads_done<NW>(gir, giz, gin);
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(gi_empty(tile) + stage);
             tc::mbar_wait(acc_ready(tile) + 0, par);
