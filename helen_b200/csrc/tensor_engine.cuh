@@ -294,6 +294,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                     for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
                     tc::tmem_st16(dst + c, r);
                     tc::tmem_st16(dst + c + 16, r + 16);
+                    tc::tmem_st_wait();                      // before r is loaded again (see upload_whh)
                 }
                 for (; c < kw; c += 16) {
                     uint32_t r[16];
@@ -301,6 +302,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 #pragma unroll
                     for (int v = 0; v < 4; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
                     tc::tmem_st16(dst + c, r);
+                    tc::tmem_st_wait();
                 }
             }
         };
@@ -683,12 +685,14 @@ struct RecArgs {
 
 // W_hh of one direction -> TMEM, spread over `n_warps` gate warps (a multiple of 4).  A warp covers TMEM lanes
 // 32 (w%4)..+31 (thread = gate row); the warps of a lane quarter split the four (hi | lo image) x (k-pair columns 0-31 |
-// 32-63) pieces; 32 words in flight per round trip.  kTwoBuffers: the loads of gate block gb+1 are in flight while block gb
-// is stored (64 staging registers; with 16 gate warps the register budget is 96 per thread and the second buffer would
-// push the gate loop's state into local memory).
-// Must be inlined: as a separate function (tried, to keep its registers out of the caller's allocation) the chunk-loop
-// kernel produced a wrong step about once in 50 launches with 8 windows per gate thread; inlined, 0 in 400.
-template <bool kTwoBuffers>
+// 32-63) pieces; 32 words in flight per round trip, two register buffers so that the loads of gate block gb+1 are in
+// flight while block gb is stored.  A buffer is loaded again only after tcgen05.wait::st (the TMEM store reads its
+// source registers asynchronously).
+// Two variants of this routine gave wrong recurrences and are not used: as a separate (not inlined) function, meant to
+// keep its 64 staging registers out of the caller's allocation, the chunk-loop kernel miscomputed a step about once in 50
+// launches with 8 windows per gate thread (inlined: 0 in 400 launches of every tile / gate-warp combination); with ONE
+// staging buffer in a rolled loop over the gate blocks the 32-window per-chunk kernel was wrong in every launch.  Neither
+// was root-caused; tests/test_gpu_stress.py repeats every kernel variant a few hundred times to catch this class of fault.
 __device__ __forceinline__ void upload_whh(const uint32_t* __restrict__ whh_tmem, const int dir, const uint32_t tmem, const int warp,
                                            const int lane, const int n_warps)
 {
@@ -705,24 +709,16 @@ __device__ __forceinline__ void upload_whh(const uint32_t* __restrict__ whh_tmem
             tc::tmem_st16(dst, r);
             tc::tmem_st16(dst + 16, r + 16);
         };
-        if constexpr (kTwoBuffers) {
-            uint32_t ra0[32], ra1[32];
-            fetch(0, ra0);
-            fetch(1, ra1);
-            store(0, ra0);
-            fetch(2, ra0);
-            store(1, ra1);
-            store(2, ra0);
-        } else {
-#pragma unroll 1
-            for (int gb = 0; gb < 3; ++gb) {
-                uint32_t ra0[32];
-                fetch(gb, ra0);
-                store(gb, ra0);
-            }
-        }
+        uint32_t ra0[32], ra1[32];
+        fetch(0, ra0);
+        fetch(1, ra1);
+        store(0, ra0);
+        tc::tmem_st_wait();
+        fetch(2, ra0);
+        store(1, ra1);
+        store(2, ra0);
+        tc::tmem_st_wait();
     }
-    tc::tmem_st_wait();
 }
 
 // One GRU step of one element, split in the three phases in which the accumulators arrive.  All values in the 2^10
@@ -997,7 +993,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         if (phase == 0 || n_layers > 1)
             // W_hh of this phase's layer -> TMEM.  (All MMAs of the previous phase have completed: every gate warp waited
             // for its last accumulator.)
-            upload_whh<GW == 8>(L.whh_tmem, dir, tmem, warp, lane, GW);
+            upload_whh(L.whh_tmem, dir, tmem, warp, lane, GW);
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
         const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
         uint32_t h_off[NW];
@@ -1280,7 +1276,7 @@ tc_recurrence2_kernel(const RecArgs ra)
         // ===================== gate warps =====================
         const int tile = warp / GW, wi = warp % GW;
         const int q = wi & 3, j = q * 32 + lane, win0 = (wi >> 2) * NW;
-        upload_whh<true>(L.whh_tmem, dir, tmem, warp, lane, REC_GATE_WARPS);   // W_hh -> TMEM, split over all gate warps
+        upload_whh(L.whh_tmem, dir, tmem, warp, lane, REC_GATE_WARPS);   // W_hh -> TMEM, split over all gate warps
         uint8_t* h_img = h_img_of(tile);
         const uint8_t* gi_s = gi_of(tile);
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;

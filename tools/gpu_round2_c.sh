@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/parity_report.jsonl
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
-python tools/scratch/dbg_race3.py 2>&1 | tail -6
+
 run() {  # name, env...
     name=$1; shift
     env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --sustained-seconds 1 > "gpurun_out/bench_${name}.json" 2> "gpurun_out/bench_${name}.err"
