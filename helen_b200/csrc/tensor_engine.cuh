@@ -156,6 +156,7 @@ constexpr int PROJ_THREADS = 352;                // warps 0-3 and 7-10 epilogue 
 constexpr int PROJ_NT = 64;
 constexpr int PROJ_STAGES = 3;                    // input stages (64 KB each for the decoder's K = 256, hi and lo parts)
 constexpr int PROJ_TABLE_MAX = 1024;              // chunk-loop kernel: jobs of one worker per chunk (the scheduler keeps the list in shared memory)
+constexpr int PROJ_GROUPS_MAX = 80;               // chunk-loop kernel: window groups of a batch (the scheduler caches their encoder counters)
 constexpr int PROJ_RING = 16;                     // job ids in flight between scheduler / loader / MMA issuer / epilogue
 constexpr int PROJ_SCHED_LEAD = 4;                // jobs the scheduler may decide ahead of the loader
 constexpr int PROJ_FLAGS_PER_TILE = 12;           // counter increments that complete a (group, tile, direction): 3 gate blocks x 4 epilogue warps
@@ -260,8 +261,10 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
     // chunk-loop kernel: the scheduler decides the job order at run time (see below) and passes it on through this ring
     volatile int* job_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [PROJ_RING]
     volatile int* sched_count = job_ring + PROJ_RING;        // jobs the scheduler has published
-    volatile int* loader_count = sched_count + 1;            // jobs the loader has taken
+    volatile int* loader_count = sched_count + 2;            // jobs the loader has taken (+2: keeps what follows 8-byte aligned)
     volatile int* job_tab = loader_count + 1;                // [PROJ_TABLE_MAX], scheduler only: this chunk's job list
+    volatile unsigned char* job_done = reinterpret_cast<volatile unsigned char*>(job_tab + PROJ_TABLE_MAX);   // [PROJ_TABLE_MAX], scheduler only
+    volatile unsigned long long* enc_count = reinterpret_cast<volatile unsigned long long*>(job_done + PROJ_TABLE_MAX);   // [2 PROJ_GROUPS_MAX], scheduler only
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kwords = Kp >> 1;
@@ -342,68 +345,91 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
 #endif
     if (warp == 6) {
         // ===================== job scheduler (chunk-loop kernel) =====================
-        // The table lists a worker's jobs in the order the encoder makes them runnable; the decoder, however, starts with
-        // the tiles that become runnable LAST (its first columns need the other direction's final outputs).  So the
-        // scheduler works from both ends of the list: the last job as soon as it is runnable (then the encoder has
-        // finished and everything left is runnable: the backlog is cleared in the order the decoder consumes it),
-        // otherwise the first one.  It runs up to PROJ_SCHED_LEAD jobs ahead of the loader, so the global round trips of
-        // its counter reads never stall a copy.  (With the decisions in the loader warp itself that warp needed ~1800
-        // cycles per job and starved the MMA issuer, which needs ~1550.)
+        // Which job next is decided at run time.  A decoder tile is runnable once both encoder directions have published
+        // its columns (the middle tiles first, the edge tiles when the encoder ends); the decoder of THIS CTA's direction,
+        // however, consumes its tiles from one edge to the other (forward: tile 0 first, reverse: the last tile first), and
+        // what it needs first becomes runnable last.  So: among the runnable tiles always take the one this CTA's decoder
+        // direction consumes earliest.  The worker's decoder entries are sorted by (tile, group); a forward-direction CTA
+        // scans them upwards, a reverse-direction CTA downwards, 32 entries per ballot, against the encoder counters of
+        // all window groups (re-read before every decision, all loads in flight at once).  Pixel jobs (the next chunk's
+        // encoder projection) wait for nothing and go first: the role is idle at the start of a chunk anyway.
+        // The scheduler runs up to PROJ_SCHED_LEAD jobs ahead of the loader, so the global round trips of its counter reads
+        // never stall a copy.  (With the decisions in the loader warp itself that warp needed ~1800 cycles per job and
+        // starved the MMA issuer, which needs ~1550.  A list walked from both ends - first runnable from the front, last
+        // entry as soon as runnable - was the first policy: it served the two decoder directions' first tiles alternately.)
         // The counters are read with relaxed loads: the encoder completed and fenced its bulk stores before it released a
         // counter, and the loader's bulk loads are issued after the value has arrived and read L2 directly.
         if (loop) {
-            auto runnable = [&](const ProjJob& q, unsigned long long c_f, unsigned long long c_r, int chunk) {
-                const unsigned long long base = a.epoch + (unsigned long long)chunk * W;
-                return q.pixel || (c_f >= base + (unsigned long long)(q.t0 + q.valid) && c_r >= base + (unsigned long long)(W - q.t0));
-            };
-            auto flag_of = [&](const ProjJob& q) { return a.progress + ((q.wg * WG) / a.rec_n) * 2; };   // [forward, reverse] counters of the tile's CTA
+            const int ddir = blk / 3;                        // decoder direction this CTA's gate block belongs to
+            const int n_groups = (int)a.n_wg;
             int it = 0;
             for (int chunk = 0; chunk < n_chunks; ++chunk) {
                 const int n_px = px_count(chunk);
                 const int n_jobs = n_px + n_dec;
                 const int px_tile0 = pixels ? px_done(a, chunk) : 0;
+                const unsigned long long base = a.epoch + (unsigned long long)chunk * W;
                 __syncwarp();
                 for (int i = lane; i < n_jobs; i += 32) {    // this chunk's list -> shared memory, pixel entries made absolute
                     int e = table_at(i, n_px);
                     if ((e >> 29) & 1) e += px_tile0 << 16;
                     job_tab[i] = e;
+                    job_done[i] = 0;
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    int front = 0, back = n_jobs - 1, ef = 0, eb = 0;
-                    ProjJob jf{}, jb{};
-                    unsigned long long vf[2] = {0, 0}, vb[2] = {0, 0};
-                    auto poll = [&]() {                      // the counters of both candidates, four loads in flight
-                        if (!jf.pixel) { vf[0] = tc::ld_relaxed_gpu(flag_of(jf)); vf[1] = tc::ld_relaxed_gpu(flag_of(jf) + 1); }
-                        if (!jb.pixel) { vb[0] = tc::ld_relaxed_gpu(flag_of(jb)); vb[1] = tc::ld_relaxed_gpu(flag_of(jb) + 1); }
-                    };
-                    auto look = [&]() {                      // both ends of what is left
-                        ef = job_tab[front]; eb = job_tab[back];
-                        jf = proj_decode(a, ef); jb = proj_decode(a, eb);
-                        poll();
-                    };
-                    if (n_jobs > 0) look();
-                    for (int idx = 0; idx < n_jobs; ++idx, ++it) {
+                int lo = 0, hi = n_dec - 1, px_next = 0;     // undone decoder entries lie in [lo, hi]
+                for (int idx = 0; idx < n_jobs; ++idx, ++it) {
+                    if (lane == 0) {
                         const long long t_spin = clock64();
                         HB_TIMED(0, while (it - ld_volatile_shared(loader_count) >= PROJ_SCHED_LEAD) { if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap(); });
-                        int e = 0;
+                    }
+                    __syncwarp();
+                    int e = 0;
+                    if (px_next < n_px) {
+                        e = job_tab[px_next++];
+                    } else {
 #ifdef HB_TIMELINE
                         const long long t_ = acct ? clock64() : 0;
 #endif
+                        const long long t_spin = clock64();
+                        int found = -1;
                         while (true) {
-                            if (front < back && !jb.pixel && runnable(jb, vb[0], vb[1], chunk)) { e = eb | (1 << 30); --back; break; }   // bit 30: the decoder waits for it
-                            if (runnable(jf, vf[0], vf[1], chunk)) { e = ef; ++front; break; }       // pixel jobs wait for nothing
-                            __nanosleep(100);
+                            for (int i = lane; i < 2 * n_groups; i += 32)
+                                enc_count[i] = tc::ld_relaxed_gpu(a.progress + (((i >> 1) * WG) / a.rec_n) * 2 + (i & 1));
+                            __syncwarp();
+                            for (int k0 = 0; k0 <= hi - lo && found < 0; k0 += 32) {
+                                const int k = k0 + lane;
+                                const int pos = ddir == 0 ? lo + k : hi - k;
+                                bool ok = false;
+                                if (k <= hi - lo && !job_done[pos]) {
+                                    const ProjJob q = proj_decode(a, job_tab[n_px + pos]);
+                                    ok = enc_count[q.wg * 2] >= base + (unsigned long long)(q.t0 + q.valid) &&
+                                         enc_count[q.wg * 2 + 1] >= base + (unsigned long long)(W - q.t0);
+                                }
+                                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                                if (m) { const int kk = k0 + __ffs(m) - 1; found = ddir == 0 ? lo + kk : hi - kk; }
+                            }
+                            if (found >= 0) break;
+                            __nanosleep(200);
                             if (clock64() - t_spin > tc::SPIN_LIMIT_CYCLES) __trap();
-                            poll();
                         }
 #ifdef HB_TIMELINE
                         if (acct) t_wait[1] += clock64() - t_;
 #endif
+                        e = job_tab[n_px + found];
+                        {   // bit 30: this group's encoder has finished, its decoder may be waiting for the tile: counters go out at once
+                            const ProjJob q = proj_decode(a, e);
+                            if (enc_count[q.wg * 2] >= base + (unsigned long long)W && enc_count[q.wg * 2 + 1] >= base + (unsigned long long)W) e |= 1 << 30;
+                        }
+                        __syncwarp();
+                        if (lane == 0) job_done[found] = 1;
+                        __syncwarp();
+                        while (lo <= hi && job_done[lo]) ++lo;
+                        while (hi >= lo && job_done[hi]) --hi;
+                    }
+                    if (lane == 0) {
                         job_ring[it & (PROJ_RING - 1)] = e;
                         __threadfence_block();
                         *sched_count = it + 1;
-                        if (front <= back) look();           // for the next job
                     }
                 }
             }
@@ -990,10 +1016,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         }
     } else {
         // ===================== gate warps =====================
-        if (phase == 0 || n_layers > 1)
-            // W_hh of this phase's layer -> TMEM.  (All MMAs of the previous phase have completed: every gate warp waited
-            // for its last accumulator.)
-            upload_whh(L.whh_tmem, dir, tmem, warp, lane, GW);
+        if (phase == 0) upload_whh(L.whh_tmem, dir, tmem, warp, lane, GW);   // W_hh of the first phase's layer -> TMEM (later phases: see below)
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
         const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
         uint32_t h_off[NW];
@@ -1100,6 +1123,10 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 #endif
         }
         if (warp == 0) HB_STAMP(2);                          // last step done
+        // W_hh of the NEXT phase's layer -> TMEM right away, while the y store drains and publishes the last columns: all
+        // MMAs of this phase have completed (every gate warp has waited for its last accumulator) and nothing else reads
+        // the weight columns.  (Uploading at the start of the next phase instead kept every role waiting ~1.5 us longer.)
+        if (n_layers > 1 && phase + 1 < n_phases) upload_whh(ra.layer[(li + 1) % n_layers].whh_tmem, dir, tmem, warp, lane, GW);
         if (phase == n_phases - 1 && ra.h_out != nullptr) {
 #pragma unroll
             for (int i = 0; i < NW; ++i)
@@ -1904,7 +1931,9 @@ inline void free_layer(TensorLayer* L) {
 }
 
 // (+1024: the kernels align their shared memory to the swizzle atom themselves)
-inline size_t projection_smem(int blk_bytes, int parts) { return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 256 + PROJ_TABLE_MAX * 4 + 1024; }
+inline size_t projection_smem(int blk_bytes, int parts) {
+    return (size_t)PROJ_STAGES * parts * 8 * blk_bytes + 256 + PROJ_TABLE_MAX * 5 + PROJ_GROUPS_MAX * 16 + 1024;
+}
 template <int N, int NLIVE = N>
 constexpr size_t recurrence_smem() { return (size_t)2 * h_buffers<N>() * (N / WG) * YBLK + (size_t)gi_stages<NLIVE>() * NLIVE * GI_ROW_BYTES + 512 + 1024; }
 constexpr size_t heads_smem() { return (size_t)2 * 16 * YROW + 2 * HEADS_WIMG + 128 + 1024; }
@@ -2045,7 +2074,7 @@ inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, in
     const int left = sms - (int)(2 * rec);
     // heads: one CTA in seven of what the recurrence leaves, at least 2 (a heads tile is a serial load -> MMA -> epilogue
     // chain of ~4 us; with 6 workers at B=256 the decoder waited for the heads: 68 k windows/s against 74.6 k with 12)
-    int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 14) * 2);
+    int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 24) * 2);
     int proj = (left - heads) / 6;
     if (proj < (tune.windows_per_cta ? 6 : 10)) return false;
     heads = left - 6 * proj;                                   // whatever the 6-CTA granularity leaves goes to the heads
@@ -2107,7 +2136,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         if (pixels_in_loop) flags_needed += n_groups * px_tiles * 2;
         const int64_t worker_tiles = (n_wg * tiles8 + plan.proj_workers - 1) / plan.proj_workers;    // tiles one projection worker owns
         const int64_t worker_jobs = worker_tiles + (n_wg + plan.proj_workers - 1) / plan.proj_workers * PX_R;
-        chunkloop = flags_needed <= e->flags_capacity && worker_jobs <= PROJ_TABLE_MAX &&
+        chunkloop = flags_needed <= e->flags_capacity && worker_jobs <= PROJ_TABLE_MAX && n_wg <= PROJ_GROUPS_MAX &&
                     (size_t)n_wg * (tiles8 + (pixels_in_loop ? PX_R : 0)) <= e->proj_jobs_capacity;   // tables sized at creation / in shared memory
         pixels_in_loop = pixels_in_loop && chunkloop;
     }
@@ -2183,16 +2212,14 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             e->tile_order_w = W;
         }
         if (e->jobs_w != W || e->jobs_workers != plan.proj_workers || e->jobs_n_wg != n_wg || e->jobs_pixels != (int)pixels_in_loop) {
-            // projection job table: tile (group, tile) belongs to worker (group * tiles + tile) % workers; a worker takes its
-            // tiles in the order the encoder makes them runnable (the forward pass has stored tile t after step 8t+8, the
-            // reverse pass after step W-8t: the later of the two)
-            struct Job { int ready, id, packed; };
+            // projection job table: tile (group, tile) belongs to worker (group + tile) % workers, which spreads every tile
+            // index (in particular the edge tiles both decoder directions start with) evenly over the workers; a worker's
+            // entries are sorted by (tile, group), the order in which its forward-direction CTAs scan them (see the scheduler)
+            struct Job { int tile, wg, packed; };
             std::vector<std::vector<Job>> per(plan.proj_workers);
             for (int64_t wg = 0; wg < n_wg; ++wg)
-                for (int t = 0; t < tiles8; ++t) {
-                    const int id = (int)(wg * tiles8 + t);
-                    per[id % plan.proj_workers].push_back({std::max(std::min(8 * t + 8, W), W - 8 * t), id, pack_proj_job((int)wg, t)});
-                }
+                for (int t = 0; t < tiles8; ++t)
+                    per[(wg + t) % plan.proj_workers].push_back({t, (int)wg, pack_proj_job((int)wg, t)});
             e->proj_jobs_host.clear();
             e->proj_job_offsets_host.assign(1, 0);
             e->proj_px_wgs_host.assign(plan.proj_workers, 0);
@@ -2208,7 +2235,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                     for (int r = 0; r < PX_R; ++r)
                         for (int wg : mine) e->proj_jobs_host.push_back(pack_proj_job(wg, r) | (1 << 29));
                 }
-                std::stable_sort(v.begin(), v.end(), [](const Job& x, const Job& y) { return x.ready != y.ready ? x.ready < y.ready : x.id < y.id; });
+                std::stable_sort(v.begin(), v.end(), [](const Job& x, const Job& y) { return x.tile != y.tile ? x.tile < y.tile : x.wg < y.wg; });
                 for (const Job& jb : v) e->proj_jobs_host.push_back(jb.packed);
                 e->proj_job_offsets_host.push_back((int)e->proj_jobs_host.size());
             }

@@ -20,14 +20,14 @@ except Exception as e:
 PY
 }
 run stg A=1
-run stg_h6 HB_HEADS_WORKERS=6
-run stg_h8 HB_HEADS_WORKERS=8
+run stg_h4 HB_HEADS_WORKERS=4
+run stg_h12 HB_HEADS_WORKERS=12
 run stg_gw16 HB_GATE_WARPS=16
 
 TL="$PWD/helen_b200/lib/libhelen_b200_timeline.so"
 HB_LIB=$TL HB_DEBUG_TIMELINE=1 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity --sustained-seconds 0 > /dev/null 2> gpurun_out/timeline_gw8_dec.err
 HB_LIB=$TL HB_DEBUG_TIMELINE=e timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity --sustained-seconds 0 > /dev/null 2> gpurun_out/timeline_gw8_enc.err
-HB_LIB=$TL HB_HEADS_WORKERS=6 HB_DEBUG_TIMELINE=1 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity --sustained-seconds 0 > /dev/null 2> gpurun_out/timeline_h6_dec.err
+HB_LIB=$TL HB_HEADS_WORKERS=12 HB_DEBUG_TIMELINE=1 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity --sustained-seconds 0 > /dev/null 2> gpurun_out/timeline_h12_dec.err
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --sustained-seconds 0 --sweep > gpurun_out/bench_sweep.json 2>/dev/null
 python - <<'PY'
 import json
