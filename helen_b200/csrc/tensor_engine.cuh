@@ -819,8 +819,12 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // (tells the compiler the warp index is uniform)
     const int64_t b0 = (int64_t)cta_x * NLIVE;
     const int t_first = dir ? W - 1 : 0, dt = dir ? -1 : 1;
+    // -DHB_TIMELINE: phase-level stamps and the roles' wait accounting (a handful of instructions outside the step loops);
+    // -DHB_TIMELINE_STEPS adds per-step stamps in the MMA issuer and the gate warps, which lengthen a step by ~25 %
 #ifdef HB_TIMELINE
     long long* __restrict__ dbg = ra.dbg;
+#endif
+#ifdef HB_TIMELINE_STEPS
 #define HB_DBG(role, s, k) do { if (dbg_steps && lane == 0) dbg[(((role) * 128 + (s)) * 8) + (k)] = clock64(); } while (0)
 #else
 #define HB_DBG(role, s, k) do { } while (0)
@@ -863,6 +867,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     const unsigned long long prog_base = ra.epoch + (unsigned long long)chunk * W;
 #ifdef HB_TIMELINE
     const bool dbg_on = dbg != nullptr && cta_x == 0 && dir == 0 && (n_layers == 1 ? li == ra.dbg_layer : chunk == 2);
+#endif
+#ifdef HB_TIMELINE_STEPS
     const bool dbg_steps = dbg_on && li == ra.dbg_layer;
 #endif
     if (phase > 0) {
@@ -1061,7 +1067,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         for (int s = 0; s < W; ++s) {
             const uint32_t par = (uint32_t)(s & 1);
             const int nb = (s + 1) % NBUF;
-#ifdef HB_TIMELINE
+#ifdef HB_TIMELINE_STEPS
             const int drole = warp == 0 ? 1 : (warp == GW - 1 ? 2 : 3);
 #endif
             tc::mbar_wait(gi_full + stage, gi_par);
@@ -1118,7 +1124,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + nb); }
             HB_DBG(drole, s, 6);
-#ifdef HB_TIMELINE
+#ifdef HB_TIMELINE_STEPS
             if (dbg_steps && lane == 0 && s < 128) dbg[8192 + warp * 128 + s] = clock64();     // every gate warp's arrival
 #endif
         }
@@ -2438,6 +2444,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 if (n_chunks > 0)
                     fprintf(stderr, "  last chunk: dec end %.1f\n", (hbuf[4096 + (64 + n_chunks - 1) * 2 + 1] - t0) * 1e-3);
             }
+#ifdef HB_TIMELINE_STEPS
             auto at = [&](int role, int st, int k) { return hbuf[((size_t)role * 128 + st) * 8 + k]; };
             double acc[16] = {0};
             int n = 0;
@@ -2462,6 +2469,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.0f", names[k], acc[1 + (role - 1) * 7 + k] / n);
                 fprintf(stderr, "\n");
             }
+#endif
         }
     }
     cudaError_t ce = cudaGetLastError();
