@@ -672,6 +672,7 @@ template <int NLIVE> __host__ __device__ constexpr int gi_stages() { return NLIV
 // progress publication (chunk-loop kernel); N = 32 has room for 2 only
 template <int N> __host__ __device__ constexpr int h_buffers() { return N <= 16 ? 4 : 2; }
 constexpr int PUBLISH_LAG = 4;
+constexpr int REC_STEP_BARRIER = 3;               // named barrier: gate warps -> MMA issuer, once per step (0 = __syncthreads, 1 / 2 = projection / heads roles)
 
 // One GRU layer as the recurrence role sees it.
 struct RecLayer {
@@ -707,6 +708,7 @@ struct RecArgs {
     unsigned long long epoch;
     long long* dbg;
     int dbg_layer;                 // -DHB_TIMELINE: which layer's steps are recorded
+    long long* phase_times;        // HB_PHASE_TIMES=1 (any build): CTA 0 / forward records [phase][start, first step released, last step done, end] in ns
 };
 
 // W_hh of one direction -> TMEM, spread over `n_warps` gate warps (a multiple of 4).  A warp covers TMEM lanes
@@ -909,6 +911,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 #define HB_STAMP(k) do { } while (0)
 #endif
     if (warp == 0) HB_STAMP(0);                              // phase start (barriers fresh, cross-CTA conditions met)
+    const bool stamp = ra.phase_times != nullptr && cta_x == 0 && dir == 0 && tid == 0 && phase < 64;
+    if (stamp) ra.phase_times[phase * 4 + 0] = (long long)globaltimer_ns();
 
     if (warp == GW + 1) {
         // ===================== gi loader: bulk copies, GI_STAGES steps ahead =====================
@@ -987,7 +991,9 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         const uint64_t himg_desc = tc::smem_desc_sw128(tc::smem_u32(h_img), (STACK && NLIVE == 8) ? HB_BYTES : YBLK);
         for (int s = 0; s < W; ++s) {
             if (s > 0) {
-                tc::mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
+                // h_{s} is complete when every gate warp has arrived: a hardware named barrier (the gate warps arrive
+                // without blocking, this warp syncs) releases this warp ~50 cycles sooner than an mbarrier wake-up
+                tc::named_barrier_sync(REC_STEP_BARRIER, (GW + 1) * 32);
                 tc::tc_fence_after();
             }
             const uint64_t hhi_desc = himg_desc + (uint64_t)(((s % NBUF) * 2 + 0) * HB_BYTES / 16);
@@ -1045,6 +1051,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
         __syncthreads();                                     // pairs with the other roles' barrier
+        if (stamp) ra.phase_times[phase * 4 + 1] = (long long)globaltimer_ns();
 
         // everything below that does not change from step to step stays in registers
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)win0;
@@ -1122,13 +1129,15 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) { tc::mbar_arrive(h_ready); tc::mbar_arrive(y_ready + nb); }
+            if (s + 1 < W) tc::named_barrier_arrive(REC_STEP_BARRIER, (GW + 1) * 32);   // (the last step has no MMA warp waiting)
+            if (lane == 0) tc::mbar_arrive(y_ready + nb);
             HB_DBG(drole, s, 6);
 #ifdef HB_TIMELINE_STEPS
             if (dbg_steps && lane == 0 && s < 128) dbg[8192 + warp * 128 + s] = clock64();     // every gate warp's arrival
 #endif
         }
         if (warp == 0) HB_STAMP(2);                          // last step done
+        if (stamp) ra.phase_times[phase * 4 + 2] = (long long)globaltimer_ns();
         // W_hh of the NEXT phase's layer -> TMEM right away, while the y store drains and publishes the last columns: all
         // MMAs of this phase have completed (every gate warp has waited for its last accumulator) and nothing else reads
         // the weight columns.  (Uploading at the start of the next phase instead kept every role waiting ~1.5 us longer.)
@@ -1141,6 +1150,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     }
     tc::tc_fence_before();
     __syncthreads();                                         // phase end: every role is done with the barriers
+    if (stamp) ra.phase_times[phase * 4 + 3] = (long long)globaltimer_ns();
     if (warp == 0) HB_STAMP(5);
 #undef HB_STAMP
 #ifdef HB_TIMELINE
@@ -1274,7 +1284,7 @@ tc_recurrence2_kernel(const RecArgs ra)
         for (int s = 0; s < W; ++s) {
             for (int tile = 0; tile < 2; ++tile) {
                 if (s > 0) {
-                    tc::mbar_wait(h_ready(tile), (uint32_t)((s - 1) & 1));
+                    tc::named_barrier_sync(REC_STEP_BARRIER + tile, (GW + 1) * 32);   // this tile's gate warps have published h_s
                     tc::tc_fence_after();
                 }
                 const uint64_t base = tc::smem_desc_sw128(tc::smem_u32(h_img_of(tile)), (STACK && NLIVE == 8) ? HB_BYTES : YBLK);
@@ -1388,7 +1398,8 @@ tc_recurrence2_kernel(const RecArgs ra)
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) { tc::mbar_arrive(h_ready(tile)); tc::mbar_arrive(y_ready(tile) + nb); }
+            if (s + 1 < W) tc::named_barrier_arrive(REC_STEP_BARRIER + tile, (GW + 1) * 32);
+            if (lane == 0) tc::mbar_arrive(y_ready(tile) + nb);
         }
         if (ra.h_out != nullptr) {
 #pragma unroll
@@ -1743,6 +1754,8 @@ struct TensorEngine {
     size_t proj_jobs_capacity = 0;            // fixed at creation: a batch whose table does not fit takes per-chunk launches
     int loop_max_ctas8 = 0, loop_max_ctas16 = 0;   // CTAs of the chunk-loop kernel (8- / 16-window tiles) that can be resident at once
     bool coop_with_pdl = true;                // cleared if the driver refuses cooperative + programmatic serialization together
+    long long* phase_times = nullptr;         // HB_PHASE_TIMES=1: [64 phases][4] device stamps of the chunk-loop kernel, printed after the third call
+    int phase_calls = 0;
     int jobs_w = -1, jobs_workers = -1, jobs_pixels = -1; int64_t jobs_n_wg = -1;
     int* proj_px_wgs = nullptr;               // [workers] window groups whose pixel jobs a worker owns
     std::vector<int> proj_jobs_host, proj_job_offsets_host, proj_px_wgs_host;
@@ -1957,6 +1970,7 @@ inline void tensor_engine_destroy(TensorEngine* e) {
     cudaFree(e->proj_px_wgs);
     cudaFree(e->tile_order16);
     cudaFree(e->flags);
+    cudaFree(e->phase_times);
     if (e->side) cudaStreamDestroy(e->side);
     for (auto& ev : e->rec_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (int i = 0; i < 2; ++i) {
@@ -2035,6 +2049,10 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->tile_order16), 4096 * sizeof(int));
         e->flags_capacity = (size_t)1 << 16;
         if (ce == cudaSuccess) ce = cudaMalloc(reinterpret_cast<void**>(&e->flags), e->flags_capacity * sizeof(unsigned long long));
+        if (ce == cudaSuccess && getenv("HB_PHASE_TIMES") != nullptr) {
+            ce = cudaMalloc(reinterpret_cast<void**>(&e->phase_times), 256 * sizeof(long long));
+            if (ce == cudaSuccess) ce = cudaMemset(e->phase_times, 0, 256 * sizeof(long long));
+        }
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
         for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
             ce = cudaEventCreateWithFlags(&e->ev_dec[i], cudaEventDisableTiming);
@@ -2276,6 +2294,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         ra.layer[1].heads_done = heads_done; ra.layer[1].heads_per_chunk = 4 * tiles16;
         ra.n_layers = 2; ra.n_chunks = n_chunks; ra.h_in = nullptr; ra.h_out = nullptr; ra.B = B; ra.W = W;
         ra.tiles_t = tiles8; ra.n_wg = (int)n_wg; ra.epoch = 0; ra.dbg = dbg_buf; ra.dbg_layer = dbg_enc ? 0 : 1;
+        ra.phase_times = e->phase_times;
         ProjArgs pp = pd;
         pp.progress = enc_prog; pp.epoch = 0; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
         pp.pair = 0;          // every CTA of the role picks its own job order (see the loader): no shared tiles
@@ -2395,6 +2414,26 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         argmax_kernel<<<(unsigned)((positions + 255) / 256), 256, 0, s>>>(p_base, p_rle, positions, base_labels, rle_labels);
         launches += 1;
     } else if (n_chunks == 0) {                                // T < W: no chunk at all, labels 0 (memset above covered it)
+    }
+    if (e->phase_times != nullptr && chunkloop && ++e->phase_calls == 3) {
+        // HB_PHASE_TIMES=1 (measurement runs): where the recurrence CTA 0 / forward spent the launch, from device timestamps
+        cudaStreamSynchronize(s);
+        std::vector<long long> pt(256);
+        cudaMemcpy(pt.data(), e->phase_times, pt.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const int n_ph = std::min(2 * n_chunks, 64);
+        double start[2] = {0, 0}, steps[2] = {0, 0}, drain[2] = {0, 0}, gap = 0;
+        for (int ph = 0; ph < n_ph; ++ph) {
+            const long long* q = &pt[ph * 4];
+            start[ph & 1] += (q[1] - q[0]) * 1e-3; steps[ph & 1] += (q[2] - q[1]) * 1e-3; drain[ph & 1] += (q[3] - q[2]) * 1e-3;
+            if (ph + 1 < n_ph) gap += (pt[(ph + 1) * 4] - q[3]) * 1e-3;
+        }
+        const double nc = n_ph / 2.0;
+        fprintf(stderr, "[phase times, CTA 0 forward, us per chunk over %d chunks; %d recurrence CTAs x 2, %d projection workers, %d heads workers]\n"
+                        "  encoder: start %.2f | %d steps %.2f (%.3f us/step) | drain %.2f\n  decoder: start %.2f | %d steps %.2f (%.3f us/step) | drain %.2f\n"
+                        "  between phases %.2f | chunk %.2f | first phase start -> last phase end %.1f us\n",
+                n_ph / 2, plan.rec_ctas, plan.proj_workers, plan.heads_workers,
+                start[0] / nc, W, steps[0] / nc, steps[0] / nc / W, drain[0] / nc, start[1] / nc, W, steps[1] / nc, steps[1] / nc / W, drain[1] / nc,
+                gap / nc, (pt[(n_ph - 1) * 4 + 3] - pt[0]) * 1e-3 / nc, (pt[(n_ph - 1) * 4 + 3] - pt[0]) * 1e-3);
     }
     if (dbg_on && dbg_buf) {
         static int printed = 0;
