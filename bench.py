@@ -62,6 +62,14 @@ def kernel_traffic_bytes(engine, batch, features):
     return table.get(f"{engine}_B{batch}_F{features}")
 
 
+def kernel_traffic_source():
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get("source")
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -389,6 +397,7 @@ def run_native(args, rank, world, local_rank):
                     "flop_per_launch": dom_flop, "kernel_ms_per_launch": dom_ms_launch, "launches_timed": dom_launches,
                     "us_per_dependent_step": 1e3 * dom_ms_launch / (chunks * 2 * WINDOW),
                     "traffic": kernel_traffic_bytes(engine, args.batch, args.features),
+                    "traffic_source": kernel_traffic_source(),
                     "note": "latency-bound at this batch: 3,800 dependent GRU steps per launch (DESIGN.md section 5)"}
         # executed (not algorithmic) MMA work: the fp16 split runs the recurrence as 4 partial products when the
         # [h_hi | h_lo] operand is stacked (3 otherwise), the decoder projection and the heads as 3
