@@ -1,0 +1,107 @@
+"""Input feed: MarginPolish image files -> ready uint8 batches, a block of images per request.
+
+The reference's SequenceDataset (helen/modules/python/models/dataloader_predict.py:54-88) opens the HDF5 file for every
+image and returns one image per item; the DataLoader then collates `batch_size` items.  At the rate the GPU path
+consumes windows (~90 k/s, 8 GB/s of pixels at 90 features) the per-item work has to go: here an item IS a batch -
+`batch_size` consecutive images of one file, read in one pass from the file held open (memory-mapped by
+helen_b200.minih5, or through h5py), padded and stacked into [n, 1000, F] / [n, 1000, 3] arrays once.  Used with
+``DataLoader(batch_size=None, num_workers=N, pin_memory=True)`` the worker processes hand the stacked tensors over
+through shared memory and the main process only pins them.
+
+Order and content are those of SequenceDataset: files in list order, images in `images.keys()` order, short images
+right-padded with zero columns and (-1, -1, -1) positions; a batch never spans two files (the last batch of a file may be
+short), which changes nothing in the prediction files since every image is predicted on its own.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .. import hdf5
+from ..FileManager import FileManager
+from ..options import ImageSizeOptions
+from ..TextColor import TextColor
+
+
+def _scalar(dataset_value):
+    return np.asarray(dataset_value).reshape(-1)[0]
+
+
+class BulkImageBatches(Dataset):
+    """Item i -> (contig list, contig_start i64[n], contig_end i64[n], chunk_id i64[n], images u8[n, 1000, F],
+    position i64[n, 1000, 3], path list): the tuple predict() takes from the reference's DataLoader."""
+
+    def __init__(self, image_directory, file_list=None, batch_size=512):
+        hdf_files = file_list if file_list is not None else FileManager.get_file_paths_from_directory(image_directory)
+        self.blocks = []                               # (path, first image, count)
+        self._names = {}                               # path -> image names in file order
+        self.batch_size = max(int(batch_size), 1)
+        self.total_images = 0
+        for path in hdf_files:
+            with hdf5.open_file(path, 'r') as handle:
+                if 'images' not in handle:
+                    sys.stderr.write(TextColor.YELLOW + "WARN: NO IMAGES FOUND IN FILE: " + path + "\n" + TextColor.END)
+                    continue
+                names = list(handle['images'].keys())
+            self._names[path] = names
+            self.total_images += len(names)
+            for first in range(0, len(names), self.batch_size):
+                self.blocks.append((path, first, min(self.batch_size, len(names) - first)))
+        self._open_path, self._open_file, self._open_pid = None, None, None
+
+    def __len__(self):
+        return len(self.blocks)
+
+    def _file(self, path):
+        if self._open_pid != os.getpid():              # a handle inherited through fork is not ours to use or close
+            self._open_path, self._open_file, self._open_pid = None, None, os.getpid()
+        if self._open_path != path:
+            self.close()
+            self._open_file, self._open_path = hdf5.open_file(path, 'r'), path
+        return self._open_file
+
+    def close(self):
+        if self._open_file is not None and self._open_pid == os.getpid():
+            self._open_file.close()
+        self._open_path, self._open_file = None, None
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_open_path"], state["_open_file"] = None, None
+        return state
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __getitem__(self, index):
+        path, first, count = self.blocks[index]
+        names = self._names[path][first:first + count]
+        groups = self._file(path)['images']
+        seq = ImageSizeOptions.SEQ_LENGTH
+        images = position = None
+        contigs, starts, ends, chunk_ids = [], np.empty(count, np.int64), np.empty(count, np.int64), np.empty(count, np.int64)
+        for k, name in enumerate(names):
+            group = groups[name]
+            contig = _scalar(group['contig'][()])
+            if isinstance(contig, bytes):
+                contig = contig.decode()
+            contigs.append(str(contig).replace("'", ''))
+            starts[k] = int(_scalar(group['contig_start'][()]))
+            ends[k] = int(_scalar(group['contig_end'][()]))
+            chunk_ids[k] = int(_scalar(group['feature_chunk_idx'][()]))
+            image = np.asarray(group['image'][()])
+            pos = np.asarray(group['position'][()])
+            if images is None:                         # zero columns / (-1, -1, -1) positions are the padding of short images
+                images = np.zeros((count, seq, image.shape[1]), np.uint8)
+                position = np.full((count, seq, 3), -1, np.int64)
+            if image.shape[0] > seq or image.shape[1] != images.shape[2] or pos.shape[0] != image.shape[0]:
+                raise ValueError("IMAGE SIZE ERROR: " + str(path) + " " + str(image.shape))
+            images[k, :image.shape[0]] = image
+            position[k, :pos.shape[0]] = pos
+        return (contigs, torch.from_numpy(starts), torch.from_numpy(ends), torch.from_numpy(chunk_ids),
+                torch.from_numpy(images), torch.from_numpy(position), [path] * count)

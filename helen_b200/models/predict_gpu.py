@@ -6,6 +6,7 @@ One OS process per GPU (mp.spawn), each with its own file list and its own
 group only served a DistributedDataParallel wrapper that does nothing under no_grad.  The whole
 per-batch loop body of the reference (predict_gpu.py:97-159) is one call into the CUDA library.
 """
+import os
 import sys
 import time
 
@@ -17,6 +18,7 @@ from ..DataStore import DataStore
 from ..options import ImageSizeOptions
 from ..predictor import WindowPredictor
 from ..TextColor import TextColor
+from .bulk_reader import BulkImageBatches
 from .dataloader_predict import SequenceDataset
 from .ModelHander import ModelHandler
 
@@ -42,9 +44,15 @@ def predict(test_file, output_filename, model_path, batch_size, num_workers, ran
         print(output_filename + "_" + str(rank) + ".hdf")
         sys.stderr.write(TextColor.PURPLE + 'Loading data\n' + TextColor.END)
 
-    test_data = SequenceDataset(image_directory=None, file_list=test_file)
     # pinned batches: the host->device copy is then a plain DMA (no staging memcpy) and can run asynchronously
-    test_loader = DataLoader(test_data, batch_size=batch_size, shuffle=False, num_workers=num_workers, pin_memory=True)
+    if os.environ.get("HELEN_B200_ITEM_READER", "0") not in ("", "0"):
+        # the reference's feed: one image per item, collated by the DataLoader (dataloader_predict.py:54-88)
+        test_data = SequenceDataset(image_directory=None, file_list=test_file)
+        test_loader = DataLoader(test_data, batch_size=batch_size, shuffle=False, num_workers=num_workers, pin_memory=True)
+    else:
+        # bulk feed: an item is a whole batch read from one file in one pass (models/bulk_reader.py)
+        test_data = BulkImageBatches(image_directory=None, file_list=test_file, batch_size=batch_size)
+        test_loader = DataLoader(test_data, batch_size=None, shuffle=False, num_workers=num_workers, pin_memory=True)
     total_batches = len(test_loader)
     windows_done, t_begin = 0, time.time()
     device = _cuda_device(device_id)
