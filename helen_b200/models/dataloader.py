@@ -26,9 +26,9 @@ class SequenceDataset(Dataset):
         hdf5_filepath, image_name = self.all_images[index]
         with hdf5.open_file(hdf5_filepath, 'r') as hdf5_file:                # dataloader.py:58-61
             group = hdf5_file['images'][image_name]
-            image = np.asarray(group['image'][()])
-            label_base = np.asarray(group['label_base'][()]).reshape(-1)
-            label_run_length = np.asarray(group['label_run_length'][()]).reshape(-1)
+            image = np.array(group['image'][()])                             # (copies: the file is closed on return)
+            label_base = np.array(group['label_base'][()]).reshape(-1)
+            label_run_length = np.array(group['label_run_length'][()]).reshape(-1)
         return image, label_base, label_run_length
 
     def __len__(self):

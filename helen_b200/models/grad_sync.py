@@ -74,3 +74,16 @@ class DataParallelContext(object):
 
     def barrier(self):
         dist.barrier(group=self.group)
+
+    def assert_replicas_identical(self, model):
+        """Every rank applied the same mean gradients to the same start values, so the replicas must stay bit-identical;
+        a rank that drifted (a lost all-reduce, a different data order feeding the optimizer state) is caught here, once
+        per epoch, instead of silently training a different model."""
+        device = next(model.parameters()).device
+        mine = torch.stack([p.detach().double().sum() for p in model.parameters()] +
+                           [p.detach().double().abs().sum() for p in model.parameters()])
+        gathered = [torch.empty_like(mine) for _ in range(self.world_size)]
+        dist.all_gather(gathered, mine.to(device), group=self.group)
+        for rank, other in enumerate(gathered):
+            if not torch.equal(other, gathered[0]):
+                raise RuntimeError("data-parallel replicas diverged: rank %d differs from rank 0" % rank)

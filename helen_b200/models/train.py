@@ -106,6 +106,7 @@ def train(train_file, test_file, batch_size, epoch_limit, gpu_mode, num_workers,
                              + ", TOTAL: " + str(round(total_loss, 4)) + "\n")
 
         if dist_ctx is not None:
+            dist_ctx.assert_replicas_identical(transducer_model)
             dist_ctx.barrier()                                # train_distributed.py:243
         if is_main:
             stats_dictionary = test(test_file, batch_size, gpu_mode, transducer_model, num_workers, gru_layers, hidden_size,
