@@ -478,7 +478,7 @@ def run_polish(args, rank, world, local_rank):
     pred = WindowPredictor(random_parameters(args.features, seed=0), device=local_rank, engine=args.engine)
     start, end = shard_bounds(args.polish, world, rank)
     n_local = end - start
-    # the stitched result: [2 heads, N windows, T] uint8 in shared host memory, created by rank 0
+    # the stitched result: [N windows, 2 heads, T] uint8 in shared host memory, created by rank 0
     shm_path = f"/dev/shm/helen_b200_polish_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
     total_bytes = 2 * args.polish * T_COLUMNS
     if rank == 0:
@@ -486,9 +486,22 @@ def run_polish(args, rank, world, local_rank):
             f.truncate(total_bytes)
     if world > 1:
         dist.barrier()
-    host = torch.from_file(shm_path, shared=True, size=total_bytes, dtype=torch.uint8).view(2, args.polish, T_COLUMNS)
+    # layout [window, head, T]: a rank's window range is one contiguous piece of the array, the only piece it page-locks
+    host = torch.from_file(shm_path, shared=True, size=total_bytes, dtype=torch.uint8).view(args.polish, 2, T_COLUMNS)
     cudart = torch.cuda.cudart()
-    registered = int(cudart.cudaHostRegister(host.data_ptr(), total_bytes, 0)) == 0     # page-locked: async DMA straight into it
+    mine = host[start:end]
+    registered = False
+    if n_local > 0:
+        try:
+            registered = int(cudart.cudaHostRegister(mine.data_ptr(), mine.numel(), 0)) == 0     # page-locked: async DMA straight into it
+        except Exception:
+            registered = False
+        if not registered:                                 # (locked-memory limit): clear the error, the copies below then stage through the driver
+            try:
+                import ctypes
+                ctypes.CDLL("libcudart.so.12").cudaGetLastError()
+            except OSError:
+                pass
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     warm = torch.randint(0, 256, (min(args.batch, max(n_local, 1)), T_COLUMNS, args.features), dtype=torch.uint8, device=dev, generator=gen)
     for _ in range(3):
@@ -516,8 +529,8 @@ def run_polish(args, rank, world, local_rank):
         ready.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ready)
-            host[0, start + off:start + off + n].copy_(b, non_blocking=True)
-            host[1, start + off:start + off + n].copy_(r, non_blocking=True)
+            host[start + off:start + off + n, 0].copy_(b, non_blocking=True)
+            host[start + off:start + off + n, 1].copy_(r, non_blocking=True)
             done[it & 1].record(copy_stream)
     main.synchronize()
     t_compute = time.perf_counter() - t0
@@ -532,13 +545,13 @@ def run_polish(args, rank, world, local_rank):
     # checker leg (untimed): this rank's first windows against the oracle, read back from the stitched array
     flips = torch.zeros(3, dtype=torch.int64, device=dev)
     if not args.no_parity and n_local > 0:
-        chk = parity_sample(args.features, kept_images.cpu(), host[0, start:start + keep].numpy(), host[1, start:start + keep].numpy(),
+        chk = parity_sample(args.features, kept_images.cpu(), host[start:start + keep, 0].numpy(), host[start:start + keep, 1].numpy(),
                             list(range(keep)))
         flips = torch.tensor([chk["windows"], chk["flips_above_margin"], chk["flips_sub_margin"]], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(flips)
     if rank == 0:
-        checksum = int(host[0, ::997].to(torch.int64).sum() + host[1, ::997].to(torch.int64).sum())
+        checksum = int(host[::997].to(torch.int64).sum())
         print(json.dumps({
             "metric": "window-sharded polish, end-to-end windows/sec (generate on device, predict, labels streamed into one host array)",
             "value": args.polish / t_total, "unit": "windows/s", "n_gpus": world, "windows": args.polish, "batch_per_launch": args.batch,
@@ -552,8 +565,8 @@ def run_polish(args, rank, world, local_rank):
                                    f"(BASELINE configs[2])"},
         }), flush=True)
     if registered:
-        cudart.cudaHostUnregister(host.data_ptr())
-    del host
+        cudart.cudaHostUnregister(mine.data_ptr())
+    del mine, host
     if world > 1:
         dist.barrier()
     if rank == 0:
