@@ -874,29 +874,16 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     const bool dbg_steps = dbg_on && li == ra.dbg_layer;
 #endif
     if (phase > 0) {
-        // phase boundary: fresh barriers, then the cross-CTA conditions of this phase
-        if (tid == 0) {
-            for (int i = 0; i < 3; ++i) { tc::mbar_inval(acc_ready + i); tc::mbar_init(acc_ready + i, 1); }
-            tc::mbar_inval(h_ready); tc::mbar_init(h_ready, GW);
-            for (int i = 0; i < NBUF; ++i) {
-                tc::mbar_inval(h_free + i); tc::mbar_init(h_free + i, 1);
-                tc::mbar_inval(y_ready + i); tc::mbar_init(y_ready + i, GW);
-            }
-            for (int i = 0; i < GI_STAGES; ++i) {
-                tc::mbar_inval(gi_full + i); tc::mbar_init(gi_full + i, 1);
-                tc::mbar_inval(gi_empty + i); tc::mbar_init(gi_empty + i, GW);
-            }
+        // phase boundary: fresh barriers, one thread each (the barriers lie back to back: acc_ready[3], h_ready, h_free[NBUF],
+        // y_ready[NBUF], gi_full[GI_STAGES], gi_empty[GI_STAGES]).  The cross-CTA conditions of this phase (heads done with the
+        // y image it overwrites, projection done with the previous one) were awaited by the gi loader warp at the end of
+        // the previous phase, while the last steps ran.
+        constexpr int N_BARRIERS = 4 + 2 * NBUF + 2 * GI_STAGES;
+        if (tid < N_BARRIERS) {
+            const bool counted_by_gate_warps = tid == 3 || (tid >= 4 + NBUF && tid < 4 + 2 * NBUF) || tid >= 4 + 2 * NBUF + GI_STAGES;
+            tc::mbar_inval(acc_ready + tid);
+            tc::mbar_init(acc_ready + tid, counted_by_gate_warps ? GW : 1);
             tc::mbar_fence_init();
-        }
-        if (warp == 0) {
-            if (L.heads_done != nullptr && chunk >= 2)       // the heads role has read the image this phase overwrites
-                for (int g = lane; g < NG; g += 32)
-                    if (cta_x * NG + g < ra.n_wg)
-                        tc::spin_until_ge(L.heads_done + (size_t)cta_x * NG + g, (unsigned long long)L.heads_per_chunk * (chunk - 1));
-            if (L.consumed_flags != nullptr && chunk >= 1)   // every projection CTA has read this layer's previous image
-                for (int f = lane; f < NG * ra.tiles_t * 2; f += 32)
-                    if (cta_x * NG + f / (ra.tiles_t * 2) < ra.n_wg)
-                        tc::spin_until_ge(L.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, (unsigned long long)L.consumed_per_chunk * chunk);
         }
         __syncthreads();
     }
@@ -944,6 +931,21 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             if (lane < 3 * NG) tc::bulk_g2s(dst0 + stage * GI_STAGE_BYTES, src0 + (int64_t)t * GI_BLK_FLOATS, GI_BLK_BYTES, gi_full + stage);
         }
         if (!synced) __syncthreads();
+        if (phase + 1 < n_phases) {
+            // this warp is GI_STAGES steps ahead of the gate warps: it uses the time to await the cross-CTA conditions of the
+            // NEXT phase (one acquire load per lane, ~1 us of global round trip that used to sit between the phases)
+            const int next_chunk = (phase + 1) / n_layers;
+            const RecLayer& LN = ra.layer[(phase + 1) - next_chunk * n_layers];
+            if (LN.heads_done != nullptr && next_chunk >= 2)  // the heads role has read the y image the next phase overwrites
+                for (int g = lane; g < NG; g += 32)
+                    if (cta_x * NG + g < ra.n_wg)
+                        tc::spin_until_ge(LN.heads_done + (size_t)cta_x * NG + g, (unsigned long long)LN.heads_per_chunk * (next_chunk - 1));
+            if (LN.consumed_flags != nullptr && next_chunk >= 1)   // every projection CTA has read that layer's previous image
+                for (int f = lane; f < NG * ra.tiles_t * 2; f += 32)
+                    if (cta_x * NG + f / (ra.tiles_t * 2) < ra.n_wg)
+                        tc::spin_until_ge(LN.consumed_flags + (size_t)cta_x * NG * ra.tiles_t * 2 + f, (unsigned long long)LN.consumed_per_chunk * next_chunk);
+            __syncwarp();
+        }
     } else if (warp == GW + 2) {
         // ===================== y store: the h image of step s is the layer output at column t_s ====
         if (phase == 0) tc::pdl_grid_dependency_wait();      // yimg may still be read by an upstream kernel
@@ -998,7 +1000,6 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             }
             const uint64_t hhi_desc = himg_desc + (uint64_t)(((s % NBUF) * 2 + 0) * HB_BYTES / 16);
             const uint64_t hlo_desc = himg_desc + (uint64_t)(((s % NBUF) * 2 + 1) * HB_BYTES / 16);
-            HB_DBG(0, s, 0);
             if (tc::elect_one()) {
 #pragma unroll
                 for (int gb = 0; gb < 3; ++gb) {             // gate blocks r, z, n
@@ -1024,7 +1025,6 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 }
             }
             __syncwarp();
-            HB_DBG(0, s, 1);
         }
     } else {
         // ===================== gate warps =====================
@@ -1472,16 +1472,17 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
     uint8_t* w_s = smem + 2 * PART_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(w_s + 2 * HEADS_WIMG);
     uint64_t* a_empty = a_full + 1;
-    uint64_t* acc_full = a_empty + 1;
-    uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* acc_full = a_empty + 1;                          // [2]: two accumulators of 16 columns, so the softmax / P update of
+    uint64_t* acc_empty = acc_full + 2;                        // [2]  one tile overlaps the load and the MMAs of the next
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     tc::pdl_launch_dependents();
     for (int i = tid; i < 2 * HEADS_WIMG / 16; i += HEADS_THREADS)
         reinterpret_cast<int4*>(w_s)[i] = reinterpret_cast<const int4*>(a.w_img)[i];
     if (tid == 0) {
-        tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1); tc::mbar_init(acc_full, 1); tc::mbar_init(acc_empty, 4);
+        tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
         tc::mbar_fence_init();
     }
     __syncwarp();
@@ -1532,8 +1533,9 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
     } else if (warp == 4) {
         const uint32_t idesc = tc::idesc_f16_f32(128, NCLS);
         for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
+            const int acc = (int)(it & 1);
             HB_TIMED(0, tc::mbar_wait(a_full, (uint32_t)(it & 1)));
-            if (it > 0) HB_TIMED(1, tc::mbar_wait(acc_empty, (uint32_t)((it - 1) & 1)));
+            if (it >= 2) HB_TIMED(1, tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1)));
             tc::tc_fence_after();
             if (tc::elect_one()) {
                 const uint64_t a_hi = tc::smem_desc_sw128(tc::smem_u32(a_img), YBLK), a_lo = tc::smem_desc_sw128(tc::smem_u32(a_img + PART_BYTES), YBLK);
@@ -1541,14 +1543,15 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                 // k-step ks: direction ks / 8 (forward units are k < 128), then (ks % 8) * 16 units into its slice
                 auto koff = [](int ks) { return (uint64_t)(((ks >> 3) * SLICE_BYTES) / 16) + tc::sw128_kstep(ks & 7); };
                 uint32_t accum = 0;
+                const uint32_t d = tmem + acc * NCLS;
 #pragma unroll
-                for (int ks = 0; ks < 16; ++ks) { tc::mma_f16_ss(tmem, a_hi + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, accum); accum = 1; }
+                for (int ks = 0; ks < 16; ++ks) { tc::mma_f16_ss(d, a_hi + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, accum); accum = 1; }
 #pragma unroll
-                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(tmem, a_lo + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, 1);
+                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(d, a_lo + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, 1);
 #pragma unroll
-                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(tmem, a_hi + koff(ks), w_lo + (uint64_t)(ks * 16), idesc, 1);
+                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(d, a_hi + koff(ks), w_lo + (uint64_t)(ks * 16), idesc, 1);
                 tc::mma_commit(a_empty);
-                tc::mma_commit(acc_full);
+                tc::mma_commit(acc_full + acc);
             }
             __syncwarp();
         }
@@ -1563,14 +1566,15 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             const int t = t0 + (row >> 3);
             const int64_t b = wg * WG + (row & 7);
             const int col = a.col0 + chunk * a.col_step + t;
-            HB_TIMED(0, tc::mbar_wait(acc_full, (uint32_t)(it & 1)));
+            const int acc = (int)(it & 1);
+            HB_TIMED(0, tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1)));
             tc::tc_fence_after();
             float v[NCLS];
-            tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+            tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + acc * NCLS, v);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(acc_empty);
+            if (lane == 0) tc::mbar_arrive(acc_empty + acc);
 #ifdef HB_TIMELINE
             const long long t_math = acct ? clock64() : 0;
 #endif
@@ -2484,30 +2488,26 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                     fprintf(stderr, "  last chunk: dec end %.1f\n", (hbuf[4096 + (64 + n_chunks - 1) * 2 + 1] - t0) * 1e-3);
             }
 #ifdef HB_TIMELINE_STEPS
+            // per-step stamps of gate warps 0 and GW-1 (roles 1, 2): cycles after the SAME warp's arrival of the previous step
+            // (the MMA issuer carries no stamps: they changed its code and slowed the issue loop)
             auto at = [&](int role, int st, int k) { return hbuf[((size_t)role * 128 + st) * 8 + k]; };
-            double acc[16] = {0};
-            int n = 0;
-            for (int st = 20; st < 90; ++st, ++n) {
-                const long long base = at(0, st, 0);              // MMA warp released for step st
-                acc[0] += at(0, st, 1) - base;                    // issue done
-                for (int role = 1; role <= 2; ++role)
-                    for (int k = 0; k < 7; ++k) acc[1 + (role - 1) * 7 + k] += at(role, st, k) - base;
-                acc[15] += at(0, st + 1, 0) - base;               // full step
-            }
-            fprintf(stderr, "[timeline, cycles after MMA warp release] issue_done=%.0f step=%.0f\n", acc[0] / n, acc[15] / n);
-            fprintf(stderr, "  arrival of every gate warp:");
-            for (int w = 0; w < 16; ++w) {
-                double a_w = 0;
-                for (int st = 20; st < 90; ++st) a_w += hbuf[8192 + w * 128 + st] - at(0, st, 0);
-                if (hbuf[8192 + w * 128 + 20] != 0) fprintf(stderr, " %d:%.0f", w, a_w / 70);
-            }
-            fprintf(stderr, "\n");
             for (int role = 1; role <= 2; ++role) {
-                fprintf(stderr, "  gate warp %s:", role == 1 ? "0 " : "15");
-                const char* names[7] = {"gi_full", "acc_r", "acc_z", "acc_n", "ldtm_n", "math_done", "arrived"};
-                for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.0f", names[k], acc[1 + (role - 1) * 7 + k] / n);
+                double acc[7] = {0};
+                int n = 0;
+                for (int st = 20; st < 90; ++st, ++n)
+                    for (int k = 0; k < 7; ++k) acc[k] += at(role, st, k) - at(role, st - 1, 6);
+                const char* names[7] = {"gi+h_free", "acc_r", "acc_z", "acc_n", "ldtm_n", "math_done", "arrived(=step)"};
+                fprintf(stderr, "[step timeline, gate warp %s, cycles after its previous arrival]", role == 1 ? "0" : "last");
+                for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.0f", names[k], acc[k] / n);
                 fprintf(stderr, "\n");
             }
+            fprintf(stderr, "  arrival of every gate warp relative to warp 0:");
+            for (int w = 0; w < 16; ++w) {
+                double a_w = 0;
+                for (int st = 20; st < 90; ++st) a_w += hbuf[8192 + w * 128 + st] - hbuf[8192 + st];
+                if (hbuf[8192 + w * 128 + 20] != 0) fprintf(stderr, " %d:%+.0f", w, a_w / 70);
+            }
+            fprintf(stderr, "\n");
 #endif
         }
     }
