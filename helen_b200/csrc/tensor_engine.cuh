@@ -874,15 +874,21 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     const bool dbg_steps = dbg_on && li == ra.dbg_layer;
 #endif
     if (phase > 0) {
-        // phase boundary: fresh barriers, one thread each (the barriers lie back to back: acc_ready[3], h_ready, h_free[NBUF],
-        // y_ready[NBUF], gi_full[GI_STAGES], gi_empty[GI_STAGES]).  The cross-CTA conditions of this phase (heads done with the
-        // y image it overwrites, projection done with the previous one) were awaited by the gi loader warp at the end of
-        // the previous phase, while the last steps ran.
-        constexpr int N_BARRIERS = 4 + 2 * NBUF + 2 * GI_STAGES;
-        if (tid < N_BARRIERS) {
-            const bool counted_by_gate_warps = tid == 3 || (tid >= 4 + NBUF && tid < 4 + 2 * NBUF) || tid >= 4 + 2 * NBUF + GI_STAGES;
-            tc::mbar_inval(acc_ready + tid);
-            tc::mbar_init(acc_ready + tid, counted_by_gate_warps ? GW : 1);
+        // phase boundary: fresh barriers.  The cross-CTA conditions of this phase (heads done with the y image it overwrites,
+        // projection done with the previous one) were awaited by the gi loader warp at the end of the previous phase, while
+        // the last steps ran.  (One thread re-initialises all barriers: with one thread per barrier the kernel failed with
+        // a launch error - not root-caused - and the serial version costs ~0.2 us.)
+        if (tid == 0) {
+            for (int i = 0; i < 3; ++i) { tc::mbar_inval(acc_ready + i); tc::mbar_init(acc_ready + i, 1); }
+            tc::mbar_inval(h_ready); tc::mbar_init(h_ready, GW);
+            for (int i = 0; i < NBUF; ++i) {
+                tc::mbar_inval(h_free + i); tc::mbar_init(h_free + i, 1);
+                tc::mbar_inval(y_ready + i); tc::mbar_init(y_ready + i, GW);
+            }
+            for (int i = 0; i < GI_STAGES; ++i) {
+                tc::mbar_inval(gi_full + i); tc::mbar_init(gi_full + i, 1);
+                tc::mbar_inval(gi_empty + i); tc::mbar_init(gi_empty + i, GW);
+            }
             tc::mbar_fence_init();
         }
         __syncthreads();
@@ -2100,9 +2106,11 @@ inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, in
     if (2 * rec > sms) return false;
     if (sms > (tile == 8 ? max_resident8 : max_resident16)) return false;   // the grid (one CTA per SM) must be co-resident as a whole
     const int left = sms - (int)(2 * rec);
-    // heads: one CTA in seven of what the recurrence leaves, at least 2 (a heads tile is a serial load -> MMA -> epilogue
-    // chain of ~4 us; with 6 workers at B=256 the decoder waited for the heads: 68 k windows/s against 74.6 k with 12)
-    int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 24) * 2);
+    // heads: one CTA in seven of what the recurrence leaves, at least 2 (a heads tile is a load -> MMA -> epilogue chain of
+    // ~3 us with only the epilogue overlapped; measured at B=256 in one run: 4 or 6 heads CTAs 89.9-90.0 k windows/s,
+    // 8 or 12 (both give 12 projection workers + 12 heads CTAs) 91.6-91.7 k - with fewer the heads fall a chunk behind and
+    // the kernel ends with a longer tail)
+    int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 14) * 2);
     int proj = (left - heads) / 6;
     if (proj < (tune.windows_per_cta ? 6 : 10)) return false;
     heads = left - 6 * proj;                                   // whatever the 6-CTA granularity leaves goes to the heads
