@@ -314,8 +314,12 @@ ce_kernel(const float* __restrict__ logit_base, const float* __restrict__ logit_
         for (int c = 0; c < NBASE; ++c) { lb[c] = expf(lb[c] - mb); sb += lb[c]; }
 #pragma unroll
         for (int c = 0; c < NRLE; ++c) { lr[c] = expf(lr[c] - mr); sr += lr[c]; }
-        const int yb = (int)label_base[i], yr = (int)label_rle[i];
-        const float wr = rle_weight[yr];
+        // A label outside its class range poisons the loss with NaN instead of reading past rle_weight
+        // (torch's CrossEntropyLoss raises a device assert there; ChunkTrainer.step turns the NaN into a ValueError).
+        const int64_t yb64 = label_base[i], yr64 = label_rle[i];
+        const bool in_range = yb64 >= 0 && yb64 < NBASE && yr64 >= 0 && yr64 < NRLE;
+        const int yb = in_range ? (int)yb64 : 0, yr = in_range ? (int)yr64 : 0;
+        const float wr = in_range ? rle_weight[yr] : __int_as_float(0x7fc00000);
         if (PASS == 1) {
             float pb = 0.f, pr = 0.f;
 #pragma unroll

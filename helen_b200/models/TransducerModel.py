@@ -4,8 +4,8 @@
 Parameters live in ordinary nn.Parameter tensors under the reference's state_dict keys
 (``gru_encoder.weight_ih_l0`` ...), so reference ``.pkl`` checkpoints load unchanged.
 ``forward`` packs them into a native handle on first use for the device the inputs are on
-and re-packs if the parameters change.  Inference only (the training path is not part of
-this hot path); there is no CPU execution path.
+and re-packs if the parameters change.  ``forward`` is the inference call (no autograd graph); the
+training step over the same parameters is ``train_step.ChunkTrainer``.  There is no CPU execution path.
 """
 import math
 

@@ -92,6 +92,10 @@ class ChunkTrainer(object):
             None if base is None else base.data_ptr(), None if rle is None else rle.data_ptr(),
             self._workspace.data_ptr(), self._workspace.numel(), stream))
         loss, loss_base, loss_rle = self._loss.tolist()              # .item() in the reference loop (train.py:205-207)
+        if loss != loss:
+            # the loss kernel answers NaN for a label outside its class range (nn.CrossEntropyLoss asserts on the device)
+            if int(lb.min()) < 0 or int(lb.max()) >= 5 or int(lr.min()) < 0 or int(lr.max()) >= 11:
+                raise ValueError("labels out of range: base labels must be in [0, 5), run-length labels in [0, 11)")
         if return_logits:
             return loss, loss_base, loss_rle, h_out, base, rle
         return loss, loss_base, loss_rle, h_out

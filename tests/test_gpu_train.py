@@ -85,6 +85,24 @@ def test_train_step_matches_port_autograd(batch, width, features, with_hidden):
     trainer.close()
 
 
+def test_label_out_of_range_is_a_value_error():
+    """nn.CrossEntropyLoss raises a device assert for such a label (train.py:121-126); here the step answers ValueError
+    and nothing is read outside the class-weight table."""
+    from helen_b200.models.train_step import ChunkTrainer
+    model = make_model(random_state_dict(10, seed=3), 10)
+    trainer = ChunkTrainer(model)
+    x = torch.randint(0, 256, (2, 20, 10)).float().cuda()
+    lb = torch.zeros(2, 20, dtype=torch.int64).cuda()
+    for bad_base, bad_rle in ((5, 0), (0, 11), (-1, 0), (0, 1 << 40)):
+        b, r = lb.clone(), lb.clone()
+        b[1, 7], r[0, 3] = bad_base, bad_rle
+        with pytest.raises(ValueError, match="labels out of range"):
+            trainer.step(x, None, b, r)
+    loss, *_ = trainer.step(x, None, lb, lb)
+    assert np.isfinite(loss)
+    trainer.close()
+
+
 def test_training_loop_mirror(tmp_path, monkeypatch):
     """helen_b200.models.train.train (train.py:19-259 mirror) on a tiny in-memory data set: the training loss falls from
     epoch to epoch, every epoch leaves a reference-format checkpoint that load_simple_model reads back, and retraining
