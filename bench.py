@@ -391,7 +391,7 @@ def run_native(args, rank, world, local_rank):
         dom_flop = args.batch * chunks * 2 * mac_chunk
         dom_ms_launch = dom_ms / dom_launches
         dom_tf = dom_flop / (dom_ms_launch * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "tc_chunkloop_kernel", "achieved": dom_tf, "peak": peaks["burst"],
+        roofline = {"bound": "tensor", "kernel": "tc_chunkloop_kernel" if plan["windows_per_cta"] == 8 else "tc_chunkloop2_kernel", "achieved": dom_tf, "peak": peaks["burst"],
                     "unit": "TFLOP/s", "frac": dom_tf / peaks["burst"], "frac_of_sustained": dom_tf / peaks["sustained"],
                     "peak_source": ("measured" if peaks["source"] == "measured" else "fallback") + " bf16 burst",
                     "flop_per_launch": dom_flop, "kernel_ms_per_launch": dom_ms_launch, "launches_timed": dom_launches,

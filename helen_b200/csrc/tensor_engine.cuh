@@ -721,31 +721,39 @@ struct RecArgs {
 // launches with 8 windows per gate thread (inlined: 0 in 400 launches of every tile / gate-warp combination); with ONE
 // staging buffer in a rolled loop over the gate blocks the 32-window per-chunk kernel was wrong in every launch.  Neither
 // was root-caused; tests/test_gpu_stress.py repeats every kernel variant a few hundred times to catch this class of fault.
+// WORDS = 32 or 16 staging registers per buffer (16: for the 19-warp blocks, whose 96-register budget the 64 staging
+// registers of the wide version pushed into local memory - together with loop-invariant values of the step loop).
+template <int WORDS = 32>
 __device__ __forceinline__ void upload_whh(const uint32_t* __restrict__ whh_tmem, const int dir, const uint32_t tmem, const int warp,
                                            const int lane, const int n_warps)
 {
+    static_assert(WORDS == 32 || WORDS == 16, "staging registers per buffer");
+    constexpr int SUBS = 32 / WORDS;
     const int q = warp & 3, row = q * 32 + lane;
     for (int piece = warp >> 2; piece < 4; piece += n_warps >> 2) {
         const int term = piece & 1, half = piece >> 1;
-        auto fetch = [&](int gb, uint32_t* r) {
-            const uint4* p = reinterpret_cast<const uint4*>(whh_tmem + whh_word_index(dir, term, gb, row, half * 32));
+#pragma unroll 1
+        for (int sub = 0; sub < SUBS; ++sub) {
+            auto fetch = [&](int gb, uint32_t* r) {
+                const uint4* p = reinterpret_cast<const uint4*>(whh_tmem + whh_word_index(dir, term, gb, row, half * 32)) + sub * (WORDS / 4) * 32;
 #pragma unroll
-            for (int v = 0; v < 8; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
-        };
-        auto store = [&](int gb, const uint32_t* r) {
-            const uint32_t dst = tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32;
-            tc::tmem_st16(dst, r);
-            tc::tmem_st16(dst + 16, r + 16);
-        };
-        uint32_t ra0[32], ra1[32];
-        fetch(0, ra0);
-        fetch(1, ra1);
-        store(0, ra0);
-        tc::tmem_st_wait();
-        fetch(2, ra0);
-        store(1, ra1);
-        store(2, ra0);
-        tc::tmem_st_wait();
+                for (int v = 0; v < WORDS / 4; ++v) { const uint4 x = __ldg(p + v * 32); r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w; }
+            };
+            auto store = [&](int gb, const uint32_t* r) {
+                const uint32_t dst = tmem + ((uint32_t)(q * 32) << 16) + REC_W_COL0 + (term * 3 + gb) * 64 + half * 32 + sub * WORDS;
+                tc::tmem_st16(dst, r);
+                if constexpr (WORDS == 32) tc::tmem_st16(dst + 16, r + 16);
+            };
+            uint32_t ra0[WORDS], ra1[WORDS];
+            fetch(0, ra0);
+            fetch(1, ra1);
+            store(0, ra0);
+            tc::tmem_st_wait();
+            fetch(2, ra0);
+            store(1, ra1);
+            store(2, ra0);
+            tc::tmem_st_wait();
+        }
     }
 }
 
@@ -1176,20 +1184,28 @@ tc_recurrence_kernel(const RecArgs ra)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Recurrence for large batches: TWO window tiles per CTA that share W_hh in TMEM and take turns on the tensor pipe
-// (throughput mode; one layer, one chunk per launch).  With one tile per CTA the tensor pipe idles during the gate
-// math of a step (~45 % of it) and a second CTA cannot share the SM because each needs 384 of the 512 TMEM columns
-// for W_hh.  Here tile A's MMAs of step s+1 are issued while tile B's gate warps still work on step s: the pipe stays
-// busy and a step pair costs its 2 x 48 (stacked, 8-window tiles) or 2 x 72 (3-term, 16-window tiles) MMAs.
+// Recurrence with TWO window tiles per CTA that share W_hh in TMEM and take turns on the tensor pipe (throughput mode).
+// With one tile per CTA the tensor pipe idles during the gate math of a step (~45 % of it) and a second CTA cannot share
+// the SM because each needs 384 of the 512 TMEM columns for W_hh.  Here tile A's MMAs of step s+1 are issued while tile
+// B's gate warps still work on step s: the pipe stays busy and a step pair costs its 2 x 48 (stacked, 8-window tiles) or
+// 2 x 72 (3-term, 16-window tiles) MMAs.
 // Warps 0-7: gate warps of tile 0, 8-15: of tile 1 (warp w of a tile: TMEM lane quarter w % 4, window half w / 4),
 // 16: MMA issuer, 17: gi' loader, 18: y store.  NLIVE windows per tile; MODE 1 = stacked [h_hi | h_lo] (NLIVE = 8),
 // MODE 0 = 3-term (NLIVE = 16).
+// Like recurrence_role it runs one layer of one chunk (per-chunk launches, n_layers == 1) or, as a role of the chunk-loop
+// kernel, the alternating encoder / decoder phases of the whole chunk loop (n_layers == 2) with the state in registers
+// and the cross-CTA counters of RecLayer; a CTA then covers 2 NLIVE / 8 consecutive window groups.
 // ---------------------------------------------------------------------------------------------
-template <int NLIVE> constexpr size_t recurrence2_smem() { return (size_t)2 * (2 * 2 * 2 * YBLK + 3 * NLIVE * GI_ROW_BYTES) + 512 + 1024; }
+template <int NLIVE> __host__ __device__ constexpr int rec2_stages() { return NLIVE <= 8 ? 6 : 3; }    // gi' stages per tile
+template <int NLIVE> __host__ __device__ constexpr int rec2_hbufs() { return NLIVE <= 8 ? 4 : 2; }     // h image buffers per tile
+template <int NLIVE> constexpr size_t recurrence2_smem() {
+    return (size_t)2 * (2 * rec2_hbufs<NLIVE>() * 2 * YBLK + rec2_stages<NLIVE>() * NLIVE * GI_ROW_BYTES) + 512 +
+           (size_t)REC_GATE_WARPS * 32 * (NLIVE / 2) * 4 + 1024;     // tiles, barriers, state parked between phases, alignment
+}
+constexpr int REC2_PHASE_BARRIER = REC_STEP_BARRIER + 2;     // named barrier: all gate warps of both tiles, once per phase
 
 template <int NLIVE, int MODE>
-__global__ void __launch_bounds__(REC_TC_THREADS, 1)
-tc_recurrence2_kernel(const RecArgs ra)
+__device__ __forceinline__ void recurrence2_role(const RecArgs& ra, uint8_t* smem, const int cta_x, const int dir)
 {
     static_assert((NLIVE == 8 && MODE == 1) || (NLIVE == 16 && MODE == 0), "8-window stacked tiles or 16-window 3-term tiles");
     constexpr bool STACK = MODE == 1;
@@ -1197,42 +1213,47 @@ tc_recurrence2_kernel(const RecArgs ra)
     constexpr int GW = REC_GATE_WARPS / 2;                   // gate warps per tile
     constexpr int NW = NLIVE / 2;                            // windows per gate thread
     constexpr int NG = NLIVE / WG;                           // window groups per tile
+    constexpr int NGC = 2 * NG;                              // window groups per CTA
     constexpr uint32_t HB_BYTES = 2 * YBLK;                  // one h operand image (hi or lo): two 8-row groups
-    constexpr int NBUF = 2, ST = 3;
+    constexpr int NBUF = rec2_hbufs<NLIVE>(), ST = rec2_stages<NLIVE>();
     constexpr uint32_t GI_STAGE_BYTES = NLIVE * GI_ROW_BYTES;
     constexpr uint32_t TILE_BYTES = 2 * NBUF * HB_BYTES + ST * GI_STAGE_BYTES;
-    constexpr int NBAR = 3 + 1 + NBUF + NBUF + ST + ST;      // barriers per tile
-    extern __shared__ __align__(1024) uint8_t smem_rec2[];
-    uint8_t* smem = tc::align_smem_1024(smem_rec2);
+    constexpr int NBAR = 3 + NBUF + NBUF + ST + ST;          // barriers per tile
+    static_assert(2 * NBAR * 8 + 8 <= 512, "barrier area");
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TILE_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NBAR);
+    // the state h is parked here between two phases: kept in registers across the W_hh upload (64 staging registers) the
+    // compiler moved it, and the h image offsets, to local memory for the whole step loop
+    float* h_park = reinterpret_cast<float*>(smem + 2 * TILE_BYTES + 512) + threadIdx.x;
     auto h_img_of = [&](int tile) { return smem + tile * TILE_BYTES; };
     auto gi_of = [&](int tile) { return smem + tile * TILE_BYTES + 2 * NBUF * HB_BYTES; };
-    auto acc_ready = [&](int tile) { return bars + tile * NBAR; };              // [3]
-    auto h_ready = [&](int tile) { return bars + tile * NBAR + 3; };
-    auto h_free = [&](int tile) { return bars + tile * NBAR + 4; };             // [NBUF]
-    auto y_ready = [&](int tile) { return bars + tile * NBAR + 4 + NBUF; };     // [NBUF]
-    auto gi_full = [&](int tile) { return bars + tile * NBAR + 4 + 2 * NBUF; }; // [ST]
-    auto gi_empty = [&](int tile) { return bars + tile * NBAR + 4 + 2 * NBUF + ST; };
+    auto acc_ready = [&](int tile) { return bars + tile * NBAR; };                  // [3]
+    auto h_free = [&](int tile) { return bars + tile * NBAR + 3; };                 // [NBUF]
+    auto y_ready = [&](int tile) { return bars + tile * NBAR + 3 + NBUF; };         // [NBUF]
+    auto gi_full = [&](int tile) { return bars + tile * NBAR + 3 + 2 * NBUF; };     // [ST]
+    auto gi_empty = [&](int tile) { return bars + tile * NBAR + 3 + 2 * NBUF + ST; };
 
-    const RecLayer& L = ra.layer[0];
     const int64_t B = ra.B;
     const int W = ra.W;
-    const int cta_x = (int)blockIdx.x, dir = (int)blockIdx.y;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_layers = ra.n_layers;
+    const int n_phases = (ra.n_chunks > 0 ? ra.n_chunks : 1) * n_layers;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int64_t b0 = (int64_t)cta_x * 2 * NLIVE;           // tile t covers windows [b0 + t NLIVE, b0 + (t + 1) NLIVE)
     const int t_first = dir ? W - 1 : 0, dt = dir ? -1 : 1;
 
     tc::pdl_launch_dependents();
-    if (tid == 0) {
+    // (stacked operand: rows 8-15 of the B operand are group 0 of the lo image; the second 8-row group of an image is never read)
+    auto init_barriers = [&](bool again) {
         for (int tile = 0; tile < 2; ++tile) {
-            for (int i = 0; i < 3; ++i) tc::mbar_init(acc_ready(tile) + i, 1);
-            tc::mbar_init(h_ready(tile), GW);
-            for (int i = 0; i < NBUF; ++i) { tc::mbar_init(h_free(tile) + i, 1); tc::mbar_init(y_ready(tile) + i, GW); }
-            for (int i = 0; i < ST; ++i) { tc::mbar_init(gi_full(tile) + i, 1); tc::mbar_init(gi_empty(tile) + i, GW); }
+            auto one = [&](uint64_t* b, int count) { if (again) tc::mbar_inval(b); tc::mbar_init(b, count); };
+            for (int i = 0; i < 3; ++i) one(acc_ready(tile) + i, 1);
+            for (int i = 0; i < NBUF; ++i) { one(h_free(tile) + i, 1); one(y_ready(tile) + i, GW); }
+            for (int i = 0; i < ST; ++i) { one(gi_full(tile) + i, 1); one(gi_empty(tile) + i, GW); }
         }
         tc::mbar_fence_init();
-    }
+    };
+    if (tid == 0) init_barriers(false);
     __syncwarp();
     if (warp == REC_GATE_WARPS) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
@@ -1240,60 +1261,120 @@ tc_recurrence2_kernel(const RecArgs ra)
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    // gate-thread state that lives across phases
+    const int tile_w = (warp / GW) & 1, wi = warp % GW;
+    const int q = wi & 3, j = q * 32 + lane, win0 = (wi >> 2) * NW;
+    const int64_t bt = b0 + tile_w * NLIVE + win0;           // first window of this gate thread
+
+    for (int phase = 0; phase < n_phases; ++phase) {
+    const int chunk = phase / n_layers, li = phase - chunk * n_layers;
+    const RecLayer& L = ra.layer[li];
+    const int gi_col0 = L.gi_col0 + chunk * L.gi_col_step;
+    uint8_t* __restrict__ yimg = L.yimg[chunk & 1];
+    const unsigned long long prog_base = ra.epoch + (unsigned long long)chunk * W;
+    if (phase > 0) {
+        if (tid == 0) init_barriers(true);                   // (one thread: see recurrence_role)
+        __syncthreads();
+    }
+    const bool stamp = ra.phase_times != nullptr && cta_x == 0 && dir == 0 && tid == 0 && phase < 64;
+    if (stamp) ra.phase_times[phase * 4 + 0] = (long long)globaltimer_ns();
+#ifdef HB_TIMELINE_STEPS
+    // per-step stamps of the MMA issuer ([step][tile][released, issued]) and of the first gate warp of each tile
+    const bool dbg_steps = ra.dbg != nullptr && cta_x == 0 && dir == 0 && li == ra.dbg_layer && (n_layers == 1 || chunk == 2);
+#define HB_DBG2(idx) do { if (dbg_steps && lane == 0 && s < 128) ra.dbg[idx] = clock64(); } while (0)
+#else
+#define HB_DBG2(idx) do { } while (0)
+#endif
+
     if (warp == REC_GATE_WARPS + 1) {
         // ===================== gi' loader: both tiles, ST steps ahead =====================
-        tc::pdl_grid_dependency_wait();
-        tc::fence_proxy_async_all();                         // gi' was written with generic-proxy stores, the bulk loads are async-proxy reads
+        if (phase == 0) { tc::pdl_grid_dependency_wait(); tc::fence_proxy_async_all(); }   // gi' was written with generic-proxy stores, the bulk loads are async-proxy reads
         bool synced = false;
         // lanes [8 tile + 3 g, + 3): the three gate blocks (4 KB each) of group g of a tile
         const int tile_l = lane >> 3, g_l = min((lane & 7) / 3, NG - 1), gate_l = (lane & 7) % 3;
         const bool loads = tile_l < 2 && (lane & 7) < 3 * NG;
-        const float* src0 = L.gi + gi_block(b0 / WG + min(tile_l, 1) * NG + g_l, L.gi_cols, L.gi_col0, dir * 3 + gate_l);
+        const float* src0 = L.gi + gi_block(b0 / WG + min(tile_l, 1) * NG + g_l, L.gi_cols, gi_col0, dir * 3 + gate_l);
+        uint8_t* dst0 = gi_of(min(tile_l, 1)) + g_l * GI_GRP_BYTES + gate_l * GI_BLK_BYTES;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % ST;
             if (s == ST) { __syncthreads(); synced = true; }
+            const int col = L.flag_abs ? gi_col0 + t : t;
+            if (L.tile_flags != nullptr && (s == 0 || (col & 7) == (dir ? 7 : 0)) && (col >> 3) >= L.flag_skip_tiles) {
+                // chunk-loop kernel: the projection CTAs announce finished gi' tiles (see recurrence_role)
+                if (lane < NGC && cta_x * NGC + lane < ra.n_wg)
+                    tc::spin_until_ge(L.tile_flags + (((size_t)cta_x * NGC + lane) * L.flag_tiles + (col >> 3)) * 2 + dir,
+                                      L.flag_need_base + L.flag_need_per_chunk * (unsigned long long)(chunk + 1));
+                __syncwarp();
+                tc::fence_proxy_async_all();
+            }
             for (int tile = 0; tile < 2; ++tile) {
                 if (s >= ST) tc::mbar_wait(gi_empty(tile) + stage, (uint32_t)((s / ST - 1) & 1));
                 if (lane == 0) tc::mbar_arrive_expect_tx(gi_full(tile) + stage, NG * GI_GRP_BYTES);
             }
             __syncwarp();
-            if (loads)
-                tc::bulk_g2s(gi_of(tile_l) + stage * GI_STAGE_BYTES + g_l * GI_GRP_BYTES + gate_l * GI_BLK_BYTES, src0 + (int64_t)t * GI_BLK_FLOATS,
-                             GI_BLK_BYTES, gi_full(tile_l) + stage);
+            if (loads) tc::bulk_g2s(dst0 + stage * GI_STAGE_BYTES, src0 + (int64_t)t * GI_BLK_FLOATS, GI_BLK_BYTES, gi_full(tile_l) + stage);
         }
         if (!synced) __syncthreads();
+        if (phase + 1 < n_phases) {
+            // cross-CTA conditions of the NEXT phase, awaited while this phase's last steps run (see recurrence_role)
+            const int next_chunk = (phase + 1) / n_layers;
+            const RecLayer& LN = ra.layer[(phase + 1) - next_chunk * n_layers];
+            if (LN.heads_done != nullptr && next_chunk >= 2)
+                for (int g = lane; g < NGC; g += 32)
+                    if (cta_x * NGC + g < ra.n_wg)
+                        tc::spin_until_ge(LN.heads_done + (size_t)cta_x * NGC + g, (unsigned long long)LN.heads_per_chunk * (next_chunk - 1));
+            if (LN.consumed_flags != nullptr && next_chunk >= 1)
+                for (int f = lane; f < NGC * ra.tiles_t * 2; f += 32)
+                    if (cta_x * NGC + f / (ra.tiles_t * 2) < ra.n_wg)
+                        tc::spin_until_ge(LN.consumed_flags + (size_t)cta_x * NGC * ra.tiles_t * 2 + f, (unsigned long long)LN.consumed_per_chunk * next_chunk);
+            __syncwarp();
+        }
     } else if (warp == REC_GATE_WARPS + 2) {
-        // ===================== y store =====================
-        tc::pdl_grid_dependency_wait();
+        // ===================== y store: lanes [2 NG tile, + 2 NG) store the (group, part) images of a tile =====================
+        if (phase == 0) tc::pdl_grid_dependency_wait();
         __syncthreads();
-        uint8_t* yimg = L.yimg[0];
+        unsigned long long* flag = L.progress ? L.progress + (size_t)cta_x * 2 + dir : nullptr;
+        const int tile_y = lane / (2 * NG), g_y = (lane % (2 * NG)) >> 1, part_y = lane & 1;
+        const bool stores = lane < 4 * NG;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int buf = (s + 1) % NBUF;
             for (int tile = 0; tile < 2; ++tile) {
                 tc::mbar_wait(y_ready(tile) + buf, (uint32_t)((s / NBUF) & 1));
-                if (lane < 2 * NG) {
-                    const int g = lane >> 1, part = lane & 1;
-                    tc::bulk_s2g(yimg + yimg_block(b0 / WG + tile * NG + g, dir, part, t, W), h_img_of(tile) + (buf * 2 + part) * HB_BYTES + g * YBLK, YBLK);
+                if (stores && tile_y == tile) {
+                    tc::bulk_s2g(yimg + yimg_block(b0 / WG + tile * NG + g_y, dir, part_y, t, W), h_img_of(tile) + (buf * 2 + part_y) * HB_BYTES + g_y * YBLK, YBLK);
                     tc::bulk_commit();
-                    tc::bulk_wait_read0();
                 }
+            }
+            // the buffers of the PREVIOUS step are handed back now: their stores have had a whole step pair to read shared
+            // memory (waiting for each store right after issuing it - twice per step pair - made this warp pace the kernel)
+            if (stores) tc::bulk_wait_read_pending<1>();
+            __syncwarp();
+            if (s > 0 && lane < 2) tc::mbar_arrive(h_free(lane) + s % NBUF);
+            if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG) & 3) == 0) {
+                if (stores) tc::bulk_wait_pending<PUBLISH_LAG>();   // (one bulk group per lane and step)
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(h_free(tile) + buf);
+                if (lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)(s + 1 - PUBLISH_LAG));
             }
         }
-        if (lane < 2 * NG) tc::bulk_wait0();
+        if (stores) tc::bulk_wait0();
+        __syncwarp();
+        if (lane < 2) tc::mbar_arrive(h_free(lane) + W % NBUF);
+        if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)W);
     } else if (warp == REC_GATE_WARPS) {
         // ===================== MMA issuer: tile 0, tile 1, tile 0, ... =====================
         __syncthreads();                                     // weights in TMEM, h_0 of both tiles in smem
         tc::tc_fence_after();
         const uint32_t idesc = tc::idesc_f16_f32(128, NACC);
+        const uint64_t base0 = tc::smem_desc_sw128(tc::smem_u32(h_img_of(0)), (STACK && NLIVE == 8) ? HB_BYTES : YBLK);
         for (int s = 0; s < W; ++s) {
+#pragma unroll
             for (int tile = 0; tile < 2; ++tile) {
                 if (s > 0) {
                     tc::named_barrier_sync(REC_STEP_BARRIER + tile, (GW + 1) * 32);   // this tile's gate warps have published h_s
                     tc::tc_fence_after();
                 }
-                const uint64_t base = tc::smem_desc_sw128(tc::smem_u32(h_img_of(tile)), (STACK && NLIVE == 8) ? HB_BYTES : YBLK);
+                HB_DBG2((s * 2 + tile) * 2);
+                const uint64_t base = base0 + (uint64_t)(tile * (TILE_BYTES / 16));
                 const uint64_t hhi_desc = base + (uint64_t)(((s % NBUF) * 2 + 0) * HB_BYTES / 16);
                 const uint64_t hlo_desc = base + (uint64_t)(((s % NBUF) * 2 + 1) * HB_BYTES / 16);
                 const uint32_t acc0 = tmem + tile * 3 * NACC;
@@ -1319,24 +1400,28 @@ tc_recurrence2_kernel(const RecArgs ra)
                     }
                 }
                 __syncwarp();
+                HB_DBG2((s * 2 + tile) * 2 + 1);
             }
         }
     } else {
         // ===================== gate warps =====================
-        const int tile = warp / GW, wi = warp % GW;
-        const int q = wi & 3, j = q * 32 + lane, win0 = (wi >> 2) * NW;
-        upload_whh(L.whh_tmem, dir, tmem, warp, lane, REC_GATE_WARPS);   // W_hh -> TMEM, split over all gate warps
-        uint8_t* h_img = h_img_of(tile);
-        const uint8_t* gi_s = gi_of(tile);
+        if (phase == 0) upload_whh<16>(L.whh_tmem, dir, tmem, warp, lane, REC_GATE_WARPS);   // W_hh -> TMEM, split over all gate warps
+        uint8_t* h_img = h_img_of(tile_w);
         const float* gc = L.gate_consts + (size_t)dir * 4 * H + j;
         const float inv_r = gc[0], inv_z = gc[H], inv_n = gc[2 * H], bhn = gc[3 * H];
-        const int64_t bt = b0 + tile * NLIVE + win0;          // first window of this thread
-        float h_own[NW];
         uint32_t h_off[NW];
-        tc::pdl_grid_dependency_wait();
+        float h_own[NW];                                     // h * 2^10
+        if (phase == 0) {
+            tc::pdl_grid_dependency_wait();
+#pragma unroll
+            for (int i = 0; i < NW; ++i)
+                h_own[i] = (ra.h_in != nullptr && bt + i < B) ? __ldcg(ra.h_in + ((bt + i) * 2 + dir) * H + j) * ACT_SCALE : 0.f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) h_own[i] = h_park[i * (REC_GATE_WARPS * 32)];
+        }
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-            h_own[i] = (ra.h_in != nullptr && bt + i < B) ? __ldcg(ra.h_in + ((bt + i) * 2 + dir) * H + j) * ACT_SCALE : 0.f;
             h_off[i] = (uint32_t)((win0 + i) / WG) * YBLK + tc::sw128_offset((win0 + i) % WG, j);
             __half hi, lo;
             tc::split_f16(h_own[i], hi, lo);
@@ -1346,8 +1431,16 @@ tc_recurrence2_kernel(const RecArgs ra)
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
         __syncthreads();
+        if (stamp) ra.phase_times[phase * 4 + 1] = (long long)globaltimer_ns();
 
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * 3 * NACC + win0);
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile_w * 3 * NACC + win0);
+        // stage: [group][gate][unit][window in group]; this thread's NW windows lie in one group
+        const float* gs0 = reinterpret_cast<const float*>(gi_of(tile_w)) + (win0 / WG) * (3 * GI_BLK_FLOATS);
+        uint64_t* const my_acc = acc_ready(tile_w);
+        uint64_t* const my_gi_full = gi_full(tile_w);
+        uint64_t* const my_gi_empty = gi_empty(tile_w);
+        uint64_t* const my_h_free = h_free(tile_w);
+        uint64_t* const my_y_ready = y_ready(tile_w);
         auto load_acc = [](uint32_t addr, float* a) {
             tc::tmem_ld_n<NW>(addr, a);
             if constexpr (STACK) {
@@ -1360,38 +1453,51 @@ tc_recurrence2_kernel(const RecArgs ra)
                 tc::tmem_ld_wait();
             }
         };
+        int stage = 0;
+        uint32_t gi_par = 0;
         for (int s = 0; s < W; ++s) {
-            const int stage = s % ST;
             const uint32_t par = (uint32_t)(s & 1);
             const int nb = (s + 1) % NBUF;
-            // stage: [group][gate][unit][window in group]; this thread's NW windows lie in one group
-            const float* gs = reinterpret_cast<const float*>(gi_s + stage * GI_STAGE_BYTES) + (win0 / WG) * (3 * GI_BLK_FLOATS);
             float a[NW], gir[NW], giz[NW], gin[NW];
             GateR gr[NW];
             GateZ gz[NW];
-            tc::mbar_wait(gi_full(tile) + stage, (uint32_t)((s / ST) & 1));
-            if (s >= NBUF) tc::mbar_wait(h_free(tile) + nb, (uint32_t)(((s - NBUF) / NBUF) & 1));
-            gi_load<NW>(gs, j, win0 % WG, gir);
-            gi_load<NW>(gs + GI_BLK_FLOATS, j, win0 % WG, giz);
-            gi_load<NW>(gs + 2 * GI_BLK_FLOATS, j, win0 % WG, gin);
+            tc::mbar_wait(my_gi_full + stage, gi_par);
+            if (s >= NBUF) tc::mbar_wait(my_h_free + nb, (uint32_t)(((s - NBUF) / NBUF) & 1));
+#ifdef HB_TIMELINE_STEPS
+#define HB_DBGG(k) do { if (wi == 0) HB_DBG2(1024 + (tile_w * 128 + s) * 8 + (k)); } while (0)
+#else
+#define HB_DBGG(k) do { } while (0)
+#endif
+            HB_DBGG(0);
+            {
+                const float* gs = gs0 + stage * (GI_STAGE_BYTES / 4);
+                gi_load<NW>(gs, j, win0 % WG, gir);
+                gi_load<NW>(gs + GI_BLK_FLOATS, j, win0 % WG, giz);
+                gi_load<NW>(gs + 2 * GI_BLK_FLOATS, j, win0 % WG, gin);
+            }
             gi_loads_done<NW>(gir, giz, gin);
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(gi_empty(tile) + stage);
-            tc::mbar_wait(acc_ready(tile) + 0, par);
+            if (lane == 0) tc::mbar_arrive(my_gi_empty + stage);
+            if (++stage == ST) { stage = 0; gi_par ^= 1u; }
+            tc::mbar_wait(my_acc + 0, par);
+            HB_DBGG(1);
             tc::tc_fence_after();
             load_acc(taddr, a);
 #pragma unroll
             for (int i = 0; i < NW; ++i) gr[i] = gate_r(a[i], inv_r, gir[i], inv_n, bhn, gin[i]);
-            tc::mbar_wait(acc_ready(tile) + 1, par);
+            tc::mbar_wait(my_acc + 1, par);
+            HB_DBGG(2);
             tc::tc_fence_after();
             load_acc(taddr + NACC, a);
 #pragma unroll
             for (int i = 0; i < NW; ++i) gz[i] = gate_z(a[i], inv_z, giz[i]);
             uint8_t* h_hi = h_img + (nb * 2) * HB_BYTES;
             uint8_t* h_lo = h_hi + HB_BYTES;
-            tc::mbar_wait(acc_ready(tile) + 2, par);
+            tc::mbar_wait(my_acc + 2, par);
+            HB_DBGG(3);
             tc::tc_fence_after();
             load_acc(taddr + 2 * NACC, a);
+            HB_DBGG(4);
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
                 const float hn = gate_n(a[i], gr[i], gz[i], h_own[i]);
@@ -1401,21 +1507,46 @@ tc_recurrence2_kernel(const RecArgs ra)
                 *reinterpret_cast<__half*>(h_hi + h_off[i]) = hi;
                 *reinterpret_cast<__half*>(h_lo + h_off[i]) = lo;
             }
+            HB_DBGG(5);
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
             __syncwarp();
-            if (s + 1 < W) tc::named_barrier_arrive(REC_STEP_BARRIER + tile, (GW + 1) * 32);
-            if (lane == 0) tc::mbar_arrive(y_ready(tile) + nb);
+            if (s + 1 < W) tc::named_barrier_arrive(REC_STEP_BARRIER + tile_w, (GW + 1) * 32);
+            if (lane == 0) tc::mbar_arrive(my_y_ready + nb);
+            HB_DBGG(6);
         }
-        if (ra.h_out != nullptr) {
+#undef HB_DBGG
+        if (stamp) ra.phase_times[phase * 4 + 2] = (long long)globaltimer_ns();
+        if (phase + 1 < n_phases) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) h_park[i * (REC_GATE_WARPS * 32)] = h_own[i];
+        }
+        if (n_layers > 1 && phase + 1 < n_phases) {
+            // W_hh of the next phase's layer -> TMEM while the y store drains; the OTHER tile's last MMAs may still be reading
+            // the weight columns until its gate warps, too, have seen their last accumulator
+            tc::named_barrier_sync(REC2_PHASE_BARRIER, REC_GATE_WARPS * 32);
+            upload_whh<16>(ra.layer[(li + 1) % n_layers].whh_tmem, dir, tmem, warp, lane, REC_GATE_WARPS);
+        }
+        if (phase == n_phases - 1 && ra.h_out != nullptr) {
 #pragma unroll
             for (int i = 0; i < NW; ++i)
                 if (bt + i < B) ra.h_out[((bt + i) * 2 + dir) * H + j] = h_own[i] * ACT_SCALE_INV;
         }
     }
     tc::tc_fence_before();
-    __syncthreads();
+    __syncthreads();                                         // phase end: every role is done with the barriers
+    if (stamp) ra.phase_times[phase * 4 + 3] = (long long)globaltimer_ns();
+#undef HB_DBG2
+    }   // phase loop
     if (warp == REC_GATE_WARPS) tc::tmem_dealloc(tmem, 512);
+}
+
+template <int NLIVE, int MODE>
+__global__ void __launch_bounds__(REC_TC_THREADS, 1)
+tc_recurrence2_kernel(const RecArgs ra)
+{
+    extern __shared__ __align__(1024) uint8_t smem_rec2[];
+    recurrence2_role<NLIVE, MODE>(ra, tc::align_smem_1024(smem_rec2), (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1708,6 +1839,31 @@ tc_chunkloop_kernel(const RecArgs rec, const ProjArgs proj, const HeadsArgs head
     }
 }
 
+// The same kernel with two 8-window tiles per recurrence CTA (recurrence2_role): for batches of up to ~600 windows the
+// recurrence CTAs cover 16 windows each and keep the tensor pipe busy with one tile's MMAs during the other tile's gate math.
+__global__ void __launch_bounds__(REC_TC_THREADS, 1)
+tc_chunkloop2_kernel(const RecArgs rec, const ProjArgs proj, const HeadsArgs heads,
+                     const int rec_ctas, const int proj_workers, const int heads_workers)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw2[];
+    uint8_t* smem_all = tc::align_smem_1024(smem_raw2);
+    const int bid = (int)blockIdx.x;
+    static_assert(REC_TC_THREADS >= PROJ_THREADS && REC_TC_THREADS >= HEADS_THREADS, "the block must hold every role");
+    if (bid < 2 * rec_ctas) {
+        recurrence2_role<8, 1>(rec, smem_all, bid >> 1, bid & 1);
+    } else if (bid < 2 * rec_ctas + 6 * proj_workers) {
+        if (threadIdx.x >= PROJ_THREADS) {
+            if (proj.pair) { tc::cluster_sync_all(); tc::cluster_sync_all(); }
+            return;
+        }
+        const int pb = bid - 2 * rec_ctas;
+        projection_role<true>(proj, smem_all, pb % 6, pb / 6, proj_workers);
+    } else {
+        if (threadIdx.x >= HEADS_THREADS) return;
+        heads_role(heads, smem_all, bid - 2 * rec_ctas - 6 * proj_workers, heads_workers);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -1732,6 +1888,7 @@ struct TensorTuning {
     int heads_workers = 0;      // HB_HEADS_WORKERS: CTAs of the heads role in the chunk-loop kernel (even)
     bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
     bool pingpong = true;       // HB_NO_PINGPONG: one window tile per recurrence CTA in the per-chunk kernels of large batches
+    bool loop_pingpong = true;  // HB_NO_LOOP_PINGPONG: 16-window chunk-loop kernel with one 16-window tile per recurrence CTA instead of two 8-window tiles
     bool cooperative = true;    // HB_NO_COOPERATIVE: chunk-loop kernel launched without the cooperative attribute
     int gate_warps = 8;         // HB_GATE_WARPS = 8 | 16: gate warps of the chunk-loop kernel's recurrence role (4 or 2 windows per thread at 8-window
                                 // tiles).  Measured at B=256: 85.8 k windows/s with 8, 81.7 k with 16 (fewer warps share the per-step waits, TMEM loads,
@@ -1745,6 +1902,7 @@ struct TensorTuning {
         t.chunkloop = getenv("HB_NO_CHUNKLOOP") == nullptr;
         t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
         t.pingpong = getenv("HB_NO_PINGPONG") == nullptr;
+        t.loop_pingpong = getenv("HB_NO_LOOP_PINGPONG") == nullptr;
         t.cooperative = getenv("HB_NO_COOPERATIVE") == nullptr;
         if (const char* v = getenv("HB_GATE_WARPS")) { if (atoi(v) == 8 || atoi(v) == 16) t.gate_warps = atoi(v); }
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
@@ -2041,6 +2199,8 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         set((const void*)tc_chunkloop_kernel<16, 16, 1, 16>, loop16);
         set((const void*)tc_chunkloop_kernel<16, 16, 1, 8>, loop16);
         set((const void*)tc_chunkloop_kernel<16, 16, 0, 16>, loop16);
+        const size_t loop2 = std::max({recurrence2_smem<8>(), detail::projection_smem(YROW, 2), detail::heads_smem()});
+        set((const void*)tc_chunkloop2_kernel, loop2);
         // the chunk-loop kernel's CTAs wait for each other: how many of them fit on the chip at once (one per SM here, but
         // MPS limits, other resident kernels' reservations or a smaller part change that; the plan respects the answer)
         auto resident = [&](const void* fn, size_t bytes, int* out) {
@@ -2050,6 +2210,9 @@ inline TensorEngine* tensor_engine_create(const hb_weights* w, int features, int
         };
         resident((const void*)tc_chunkloop_kernel<16, 8, 1, 16>, loop8, &e->loop_max_ctas8);
         resident((const void*)tc_chunkloop_kernel<16, 16, 1, 16>, loop16, &e->loop_max_ctas16);
+        int max2 = 0;
+        resident((const void*)tc_chunkloop2_kernel, loop2, &max2);
+        e->loop_max_ctas16 = std::min(e->loop_max_ctas16, max2);
         // job table of the chunk-loop projection role, sized once for the largest batch the kernel takes (one 8-window
         // group per two SMs) and chunks of up to 1024 columns; anything larger runs as per-chunk launches
         e->proj_jobs_capacity = (size_t)(sm_count / 2 + 1) * (2 * 128 + PX_R);
@@ -2091,17 +2254,21 @@ inline int pick_windows_per_cta(const TensorTuning& tune, int64_t B, int sm_coun
     return 2 * B <= (int64_t)16 * sm_count ? 16 : 32;
 }
 
-// Role split of the chunk-loop kernel: recurrence CTAs for 8-window tiles, the rest shared between projection workers
-// (6 CTAs each) and heads workers.  Returns false when the batch is too large for it: the projection role has to keep
-// pace with the encoder, and measured against the per-chunk launches the kernel only wins while at least 10 projection
-// workers fit (B <= ~320; at B=384 it ran at 64 k windows/s against 90 k, and one 16-window tile per CTA never won:
-// 86 k against 90 k at B=384, 97 k against 107 k at B=512).  HB_WINDOWS_PER_CTA forces a tile (tests).
+// Role split of the chunk-loop kernel: recurrence CTAs (8 windows each, or 16 as two 8-window tiles that take turns on the
+// tensor pipe), the rest shared between projection workers (6 CTAs each) and heads workers.  Returns false when the
+// batch is too large for it: the projection role has to keep pace with the encoder.  Measured (windows/s, one box):
+//   B=320  8-window tiles, 10 workers 99.7 k
+//   B=384  two tiles 102.5 k | per-chunk launches 98.3 k        B=448  two tiles ~105 k | per-chunk 109 k (before the y-store fix)
+//   B=512  two tiles 127.7-128.8 k | one 16-window tile 118 k | per-chunk launches 115.4 k
+//   B=576  two tiles, 11 workers 111 k | per-chunk launches 119 k
+// so: 8-window tiles while 10 workers fit (B <= 320), two tiles per CTA while 12 workers fit (B <= 512), per-chunk launches
+// above.  HB_WINDOWS_PER_CTA forces a tile (tests).
+// (Measured and dropped: starting the odd window tiles one phase after the even ones, so that the other roles see two waves
+// of work per chunk - the encoder phases got 3 us shorter, the decoder phases 3 us longer, the launch took the same time.)
 struct ChunkloopPlan { int tile, rec_ctas, proj_workers, heads_workers; };
-inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, int max_resident8, int max_resident16, ChunkloopPlan* plan) {
+inline bool plan_chunkloop_tile(const TensorTuning& tune, int tile, int min_workers, int64_t B, int sm_count, int max_resident8, int max_resident16,
+                                ChunkloopPlan* plan) {
     const int sms = sm_count / 2 * 2;
-    const int tile = tune.windows_per_cta ? tune.windows_per_cta : 8;
-    if (tile != 8 && tile != 16) return false;                 // (32 live windows leave no room for two gi' rows per window)
-    if (tile == 8 && !tune.live8 && !tune.windows_per_cta) return false;
     const int64_t rec = (B + tile - 1) / tile;
     if (2 * rec > sms) return false;
     if (sms > (tile == 8 ? max_resident8 : max_resident16)) return false;   // the grid (one CTA per SM) must be co-resident as a whole
@@ -2112,12 +2279,20 @@ inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, in
     // the kernel ends with a longer tail)
     int heads = tune.heads_workers ? tune.heads_workers : std::max(2, (left / 14) * 2);
     int proj = (left - heads) / 6;
-    if (proj < (tune.windows_per_cta ? 6 : 10)) return false;
+    if (proj < min_workers) return false;
     heads = left - 6 * proj;                                   // whatever the 6-CTA granularity leaves goes to the heads
     heads = heads / 2 * 2;
     if (heads < 2) { --proj; heads += 6; }
     plan->tile = tile; plan->rec_ctas = (int)rec; plan->proj_workers = proj; plan->heads_workers = heads;
     return true;
+}
+inline bool plan_chunkloop(const TensorTuning& tune, int64_t B, int sm_count, int max_resident8, int max_resident16, ChunkloopPlan* plan) {
+    if (tune.windows_per_cta) {
+        if (tune.windows_per_cta != 8 && tune.windows_per_cta != 16) return false;     // (32 live windows leave no room for two gi' rows per window)
+        return plan_chunkloop_tile(tune, tune.windows_per_cta, 6, B, sm_count, max_resident8, max_resident16, plan);
+    }
+    if (tune.live8 && plan_chunkloop_tile(tune, 8, 10, B, sm_count, max_resident8, max_resident16, plan)) return true;
+    return tune.stack && tune.loop_pingpong && plan_chunkloop_tile(tune, 16, 12, B, sm_count, max_resident8, max_resident16, plan);
 }
 
 // Returns the number of kernel launches issued, or a negative hb_status (message in err).
@@ -2235,6 +2410,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         if (slot != (size_t)-1) cudaEventRecord(e->rec_events[slot].second, s);
     };
     // ---- chunk-loop kernel: every role of the whole chunk loop resident at once ----
+    bool two_tiles = false;
     if (chunkloop) {
         if (e->tile_order_w != W) {
             // heads: a column tile is complete once the forward pass is past its last column and the reverse pass past its first
@@ -2323,9 +2499,10 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         hp.progress = dec_prog; hp.rec_n = plan.tile; hp.tile_order = e->tile_order16; hp.heads_done = heads_done;
         hp.dbg = dbg_buf;
         const dim3 grid(2 * plan.rec_ctas + 6 * plan.proj_workers + plan.heads_workers), cluster(1, 1, 1);
-        const size_t smem = std::max({plan.tile == 8 ? detail::recurrence_smem<16, 8>() : detail::recurrence_smem<16>(),
+        two_tiles = plan.tile == 16 && e->tune.stack && e->tune.loop_pingpong;
+        const size_t smem = std::max({plan.tile == 8 ? detail::recurrence_smem<16, 8>() : (two_tiles ? recurrence2_smem<8>() : detail::recurrence_smem<16>()),
                                       detail::projection_smem(YROW, 2), detail::heads_smem()});
-        const int gw = e->tune.stack ? e->tune.gate_warps : 16;
+        const int gw = (e->tune.stack && !two_tiles) ? e->tune.gate_warps : 16;
         // Cooperative launch: the CTAs of this kernel spin on each other's counters, so the grid must be resident as a
         // whole - with the attribute the launch waits until it can be (another handle's kernel, or any other work on the
         // device, cannot leave it half scheduled) instead of relying on an idle chip.
@@ -2348,6 +2525,8 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             if (!e->tune.stack) go(tc_chunkloop_kernel<16, 8, 0, 16>);
             else if (gw == 8) go(tc_chunkloop_kernel<16, 8, 1, 8>);
             else go(tc_chunkloop_kernel<16, 8, 1, 16>);
+        } else if (two_tiles) {
+            go(tc_chunkloop2_kernel);
         } else {
             if (!e->tune.stack) go(tc_chunkloop_kernel<16, 16, 0, 16>);
             else if (gw == 8) go(tc_chunkloop_kernel<16, 16, 1, 8>);
@@ -2496,6 +2675,26 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                     fprintf(stderr, "  last chunk: dec end %.1f\n", (hbuf[4096 + (64 + n_chunks - 1) * 2 + 1] - t0) * 1e-3);
             }
 #ifdef HB_TIMELINE_STEPS
+            if (two_tiles) {
+                // two tiles per recurrence CTA: the MMA issuer's step pair and each tile's first gate warp, cycles after the
+                // issuer's release for that tile's step
+                double iss[4] = {0}, g[2][7] = {{0}};
+                int n = 0;
+                for (int st = 20; st < 90; ++st, ++n) {
+                    const long long* q0 = &hbuf[(st * 2) * 2];
+                    iss[0] += q0[1] - q0[0]; iss[1] += q0[2] - q0[1]; iss[2] += q0[3] - q0[2]; iss[3] += q0[4] - q0[3];
+                    for (int tl = 0; tl < 2; ++tl)
+                        for (int k = 0; k < 7; ++k) g[tl][k] += hbuf[1024 + (tl * 128 + st) * 8 + k] - hbuf[(st * 2 + tl) * 2];
+                }
+                fprintf(stderr, "[two-tile step pair, MMA issuer, cycles] tile 0 issue %.0f | wait for tile 1 %.0f | tile 1 issue %.0f | wait for tile 0 %.0f | pair %.0f\n",
+                        iss[0] / n, iss[1] / n, iss[2] / n, iss[3] / n, (iss[0] + iss[1] + iss[2] + iss[3]) / n);
+                const char* names[7] = {"gi+h_free", "acc_r", "acc_z", "acc_n", "ldtm_n", "math_done", "arrived"};
+                for (int tl = 0; tl < 2; ++tl) {
+                    fprintf(stderr, "  tile %d gate warp 0, cycles after the issuer's release of the step:", tl);
+                    for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.0f", names[k], g[tl][k] / n);
+                    fprintf(stderr, "\n");
+                }
+            } else {
             // per-step stamps of gate warps 0 and GW-1 (roles 1, 2): cycles after the SAME warp's arrival of the previous step
             // (the MMA issuer carries no stamps: they changed its code and slowed the issue loop)
             auto at = [&](int role, int st, int k) { return hbuf[((size_t)role * 128 + st) * 8 + k]; };
@@ -2516,6 +2715,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 if (hbuf[8192 + w * 128 + 20] != 0) fprintf(stderr, " %d:%+.0f", w, a_w / 70);
             }
             fprintf(stderr, "\n");
+            }
 #endif
         }
     }

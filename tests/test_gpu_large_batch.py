@@ -1,7 +1,8 @@
 """GPU parity at the sizes that pick each launch structure of the tensor engine by themselves.
 
-`helen polish` defaults to --batch_size 512 (reference helen/helen.py:32-39), which the library runs as per-chunk
-launches (two-tile recurrence kernels); B <= ~320 runs the chunk-loop kernel.  Nothing here forces a variant: the
+`helen polish` defaults to --batch_size 512 (reference helen/helen.py:32-39).  B <= 320 runs the chunk-loop kernel with
+8-window recurrence tiles, 320 < B <= 512 the chunk-loop kernel with two 8-window tiles per recurrence CTA
+(tc_chunkloop2_kernel), larger batches per-chunk launches (two-tile recurrence kernels).  Nothing here forces a variant: the
 library chooses, the test records what it chose (hb_last_launch_plan) and compares with the CPU oracle
 (oracle.predict_port == the reference's own nn.GRU calls, predict.py:90-154) on
 
@@ -87,8 +88,9 @@ def test_config2_every_window_matches_oracle(features):
 @pytest.mark.parametrize("batch,features", [(384, 10), (500, 10), (512, 10), (1024, 10), (2048, 10),
                                             (384, 90), (512, 90), (1000, 90), (2048, 90)])
 def test_auto_selected_large_batch_matches_oracle(batch, features):
-    """Batches above the chunk-loop kernel's reach take per-chunk launches with the two-tile recurrence kernels, multi-wave
-    projection grids and gi images of up to 6.3 GB: checked here at their own sizes, against the oracle."""
+    """Batches above the 8-window chunk-loop kernel's reach: the two-tile chunk-loop kernel up to 512 windows, above that
+    per-chunk launches with the two-tile recurrence kernels, multi-wave projection grids and gi images of up to 6.3 GB:
+    checked here at their own sizes, against the oracle."""
     from helen_b200.predictor import WindowPredictor
     sd = random_state_dict(features, seed=batch % 7)
     gen = torch.Generator().manual_seed(batch + features)
@@ -100,6 +102,8 @@ def test_auto_selected_large_batch_matches_oracle(batch, features):
     base_p, rle_p, pb, pr = pred.predict(dev, return_probs=True)
     base2, rle2 = pred.predict(dev)                                  # run to run
     torch.cuda.synchronize()
+    assert plan["chunkloop"] == (1 if batch <= 512 else 0), plan
+    assert batch > 512 or plan["windows_per_cta"] == 16, plan
     assert torch.equal(base, base_p) and torch.equal(rle, rle_p)
     assert torch.equal(base, base2) and torch.equal(rle, rle2)
     idx = sample_windows(batch, max(plan["windows_per_cta"], 8))
