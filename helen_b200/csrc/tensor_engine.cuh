@@ -672,6 +672,16 @@ template <int NLIVE> __host__ __device__ constexpr int gi_stages() { return NLIV
 // progress publication (chunk-loop kernel); N = 32 has room for 2 only
 template <int N> __host__ __device__ constexpr int h_buffers() { return N <= 16 ? 4 : 2; }
 constexpr int PUBLISH_LAG = 4;
+// The y-store warp publishes its progress counter when the columns stored (and landed) reach a multiple of 8 counted from
+// the edge its direction starts at - the consumers' tile boundaries: projection tiles are 8 columns, heads tiles 16, and the
+// reverse direction's count of W - 8 t columns is congruent to W modulo 8.  The release store costs the warp 3-7 thousand
+// cycles (its MEMBAR.GPU also waits for the newest bulk stores, still in flight): once per 8 steps, not per 4.
+// (A relaxed store after cp.async.bulk.wait_group is NOT enough: tests/test_gpu_stress.py caught batches that differed
+// from run to run with it.)
+#ifndef HB_PUBLISH_EVERY
+#define HB_PUBLISH_EVERY 8
+#endif
+constexpr int PUBLISH_EVERY = HB_PUBLISH_EVERY;
 constexpr int REC_STEP_BARRIER = 3;               // named barrier: gate warps -> MMA issuer, once per step (0 = __syncthreads, 1 / 2 = projection / heads roles)
 
 // One GRU layer as the recurrence role sees it.
@@ -965,6 +975,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         if (phase == 0) tc::pdl_grid_dependency_wait();      // yimg may still be read by an upstream kernel
         __syncthreads();
         unsigned long long* flag = L.progress ? L.progress + (size_t)cta_x * 2 + dir : nullptr;
+        const int pub_off = dir ? (W & (PUBLISH_EVERY - 1)) : 0;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int buf = (s + 1) % NBUF;                  // the image written during step s
             tc::mbar_wait(y_ready + buf, (uint32_t)((s / NBUF) & 1));
@@ -976,8 +987,8 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(h_free + buf);
-            if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG) & 3) == 0) {
-                // every 4th step: all stores but the newest PUBLISH_LAG have landed in global memory, publish
+            if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG - pub_off) & (PUBLISH_EVERY - 1)) == 0) {
+                // at the consumers' tile boundaries: all stores but the newest PUBLISH_LAG have landed in global memory, publish
                 // that many completed columns to the consumer CTAs.  (Waiting for the newest store, or
                 // fencing every step, would put a global round trip on the step's critical path via h_free.)
                 if (lane < 2 * NG) tc::bulk_wait_pending<PUBLISH_LAG>();   // writes performed; the release orders them before the counter
@@ -1334,28 +1345,49 @@ __device__ __forceinline__ void recurrence2_role(const RecArgs& ra, uint8_t* sme
         if (phase == 0) tc::pdl_grid_dependency_wait();
         __syncthreads();
         unsigned long long* flag = L.progress ? L.progress + (size_t)cta_x * 2 + dir : nullptr;
+        const int pub_off = dir ? (W & (PUBLISH_EVERY - 1)) : 0;
         const int tile_y = lane / (2 * NG), g_y = (lane % (2 * NG)) >> 1, part_y = lane & 1;
         const bool stores = lane < 4 * NG;
+#ifdef HB_TIMELINE_STEPS
+        long long ty[4] = {0, 0, 0, 0};
+#define HB_YT(k, ...) do { const long long t_ = clock64(); __VA_ARGS__; if (dbg_steps && s >= 20 && s < 90) ty[k] += clock64() - t_; } while (0)
+#else
+#define HB_YT(k, ...) do { __VA_ARGS__; } while (0)
+#endif
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int buf = (s + 1) % NBUF;
             for (int tile = 0; tile < 2; ++tile) {
-                tc::mbar_wait(y_ready(tile) + buf, (uint32_t)((s / NBUF) & 1));
+                HB_YT(0, tc::mbar_wait(y_ready(tile) + buf, (uint32_t)((s / NBUF) & 1)));
+                HB_YT(1,
                 if (stores && tile_y == tile) {
                     tc::bulk_s2g(yimg + yimg_block(b0 / WG + tile * NG + g_y, dir, part_y, t, W), h_img_of(tile) + (buf * 2 + part_y) * HB_BYTES + g_y * YBLK, YBLK);
                     tc::bulk_commit();
                 }
+                __syncwarp());
             }
             // the buffers of the PREVIOUS step are handed back now: their stores have had a whole step pair to read shared
             // memory (waiting for each store right after issuing it - twice per step pair - made this warp pace the kernel)
-            if (stores) tc::bulk_wait_read_pending<1>();
-            __syncwarp();
+            HB_YT(2, if (stores) tc::bulk_wait_read_pending<1>(); __syncwarp());
             if (s > 0 && lane < 2) tc::mbar_arrive(h_free(lane) + s % NBUF);
-            if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG) & 3) == 0) {
-                if (stores) tc::bulk_wait_pending<PUBLISH_LAG>();   // (one bulk group per lane and step)
-                __syncwarp();
-                if (lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)(s + 1 - PUBLISH_LAG));
+            if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG - pub_off) & (PUBLISH_EVERY - 1)) == 0) {
+                HB_YT(3, if (stores) tc::bulk_wait_pending<PUBLISH_LAG>(); __syncwarp());   // (one bulk group per lane and step)
+#ifndef HB_PUBLISH_LANE
+#define HB_PUBLISH_LANE 0
+#endif
+#ifdef HB_TIMELINE_STEPS
+                { const long long t_ = clock64();
+                  if (lane == HB_PUBLISH_LANE) tc::st_release_gpu(flag, prog_base + (unsigned long long)(s + 1 - PUBLISH_LAG));
+                  __syncwarp();
+                  if (dbg_steps && s >= 20 && s < 90 && lane == 0) ra.dbg[3004] += clock64() - t_; }
+#else
+                if (lane == HB_PUBLISH_LANE) tc::st_release_gpu(flag, prog_base + (unsigned long long)(s + 1 - PUBLISH_LAG));
+#endif
             }
         }
+#ifdef HB_TIMELINE_STEPS
+        if (dbg_steps && lane == 0) for (int k = 0; k < 4; ++k) ra.dbg[3000 + k] = ty[k];
+#endif
+#undef HB_YT
         if (stores) tc::bulk_wait0();
         __syncwarp();
         if (lane < 2) tc::mbar_arrive(h_free(lane) + W % NBUF);
@@ -1461,13 +1493,14 @@ __device__ __forceinline__ void recurrence2_role(const RecArgs& ra, uint8_t* sme
             float a[NW], gir[NW], giz[NW], gin[NW];
             GateR gr[NW];
             GateZ gz[NW];
-            tc::mbar_wait(my_gi_full + stage, gi_par);
-            if (s >= NBUF) tc::mbar_wait(my_h_free + nb, (uint32_t)(((s - NBUF) / NBUF) & 1));
 #ifdef HB_TIMELINE_STEPS
 #define HB_DBGG(k) do { if (wi == 0) HB_DBG2(1024 + (tile_w * 128 + s) * 8 + (k)); } while (0)
 #else
 #define HB_DBGG(k) do { } while (0)
 #endif
+            tc::mbar_wait(my_gi_full + stage, gi_par);
+            HB_DBGG(7);
+            if (s >= NBUF) tc::mbar_wait(my_h_free + nb, (uint32_t)(((s - NBUF) / NBUF) & 1));
             HB_DBGG(0);
             {
                 const float* gs = gs0 + stage * (GI_STAGE_BYTES / 4);
@@ -1556,6 +1589,7 @@ tc_recurrence2_kernel(const RecArgs ra)
 // of ONE position in registers and the two softmaxes need no cross-thread traffic.
 // ---------------------------------------------------------------------------------------------
 constexpr int HEADS_THREADS = 192;
+constexpr int HEADS_EPILOGUE_BARRIER = 6;        // named barrier of the four epilogue warps (0 = __syncthreads, 1 / 2 roles, 3-5 recurrence)
 constexpr int HEADS_WIMG = NCLS * 2 * H * 2;     // one [16 x 256] fp16 image (dense core matrices): 8192 B
 
 struct HeadsArgs {
@@ -1607,9 +1641,9 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
     constexpr uint32_t PART_BYTES = 2 * SLICE_BYTES;
     uint8_t* a_img = smem;                                      // [hi, lo][direction][16 row groups][YBLK]
     uint8_t* w_s = smem + 2 * PART_BYTES;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(w_s + 2 * HEADS_WIMG);
-    uint64_t* a_empty = a_full + 1;
-    uint64_t* acc_full = a_empty + 1;                          // [2]: two accumulators of 16 columns, so the softmax / P update of
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(w_s + 2 * HEADS_WIMG);   // [2]: hi part, lo part of the activation tile - the
+    uint64_t* a_empty = a_full + 2;                            // [2]  loader refills the hi part while the lo part's MMAs still run
+    uint64_t* acc_full = a_empty + 2;                          // [2]: two accumulators of 16 columns, so the softmax / P update of
     uint64_t* acc_empty = acc_full + 2;                        // [2]  one tile overlaps the load and the MMAs of the next
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1618,7 +1652,7 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
     for (int i = tid; i < 2 * HEADS_WIMG / 16; i += HEADS_THREADS)
         reinterpret_cast<int4*>(w_s)[i] = reinterpret_cast<const int4*>(a.w_img)[i];
     if (tid == 0) {
-        tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
         tc::mbar_fence_init();
     }
@@ -1647,7 +1681,6 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
 
     if (warp == 5) {
         for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
-            if (it > 0) HB_TIMED(0, tc::mbar_wait(a_empty, (uint32_t)((it - 1) & 1)));
             const int valid = min(16, W - t0);
             if (a.progress != nullptr) {                     // both decoder directions must have stored these columns
                 if (lane < 2)
@@ -1657,13 +1690,17 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                 __syncwarp();
             }
             const uint8_t* img = ((chunk & 1) && a.yimg_odd) ? a.yimg_odd : a.yimg;
-            if (lane == 0) tc::mbar_arrive_expect_tx(a_full, (uint32_t)(valid * 2 * YROW));
-            __syncwarp();
-            if (lane < 16) {                                 // four copies of four columns per (part, direction); columns are contiguous
-                const int q4 = lane & 3, part = lane >> 3, d = (lane >> 2) & 1;
-                const int cols = min(4, valid - 4 * q4);
-                if (cols > 0)
-                    tc::bulk_g2s(a_img + part * PART_BYTES + d * SLICE_BYTES + q4 * 4 * YBLK, img + yimg_block(wg, d, part, t0 + 4 * q4, W), (uint32_t)(cols * YBLK), a_full);
+            // four copies of four columns per (part, direction); columns are contiguous.  The hi part (64 KB) first: its MMAs
+            // start while the lo part is still on its way
+            const int q4 = lane & 3, d = (lane >> 2) & 1;
+            const int cols = min(4, valid - 4 * q4);
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                if (it > 0) HB_TIMED(0, tc::mbar_wait(a_empty + part, (uint32_t)((it - 1) & 1)));
+                if (lane == 0) tc::mbar_arrive_expect_tx(a_full + part, (uint32_t)(valid * YROW));
+                __syncwarp();
+                if ((lane >> 3) == part && cols > 0)
+                    tc::bulk_g2s(a_img + part * PART_BYTES + d * SLICE_BYTES + q4 * 4 * YBLK, img + yimg_block(wg, d, part, t0 + 4 * q4, W), (uint32_t)(cols * YBLK), a_full + part);
             }
         }
         HB_ROLE_REPORT(0);
@@ -1671,23 +1708,29 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
         const uint32_t idesc = tc::idesc_f16_f32(128, NCLS);
         for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
             const int acc = (int)(it & 1);
-            HB_TIMED(0, tc::mbar_wait(a_full, (uint32_t)(it & 1)));
+            const uint64_t a_hi = tc::smem_desc_sw128(tc::smem_u32(a_img), YBLK), a_lo = tc::smem_desc_sw128(tc::smem_u32(a_img + PART_BYTES), YBLK);
+            const uint64_t w_hi = tc::smem_desc(tc::smem_u32(w_s), 128, 4096), w_lo = tc::smem_desc(tc::smem_u32(w_s + HEADS_WIMG), 128, 4096);
+            // k-step ks: direction ks / 8 (forward units are k < 128), then (ks % 8) * 16 units into its slice
+            auto koff = [](int ks) { return (uint64_t)(((ks >> 3) * SLICE_BYTES) / 16) + tc::sw128_kstep(ks & 7); };
+            const uint32_t d = tmem + acc * NCLS;
+            HB_TIMED(0, tc::mbar_wait(a_full + 0, (uint32_t)(it & 1)));
             if (it >= 2) HB_TIMED(1, tc::mbar_wait(acc_empty + acc, (uint32_t)((it / 2 - 1) & 1)));
             tc::tc_fence_after();
-            if (tc::elect_one()) {
-                const uint64_t a_hi = tc::smem_desc_sw128(tc::smem_u32(a_img), YBLK), a_lo = tc::smem_desc_sw128(tc::smem_u32(a_img + PART_BYTES), YBLK);
-                const uint64_t w_hi = tc::smem_desc(tc::smem_u32(w_s), 128, 4096), w_lo = tc::smem_desc(tc::smem_u32(w_s + HEADS_WIMG), 128, 4096);
-                // k-step ks: direction ks / 8 (forward units are k < 128), then (ks % 8) * 16 units into its slice
-                auto koff = [](int ks) { return (uint64_t)(((ks >> 3) * SLICE_BYTES) / 16) + tc::sw128_kstep(ks & 7); };
+            if (tc::elect_one()) {                           // the two terms that read the hi part, then the part is free again
                 uint32_t accum = 0;
-                const uint32_t d = tmem + acc * NCLS;
 #pragma unroll
                 for (int ks = 0; ks < 16; ++ks) { tc::mma_f16_ss(d, a_hi + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, accum); accum = 1; }
 #pragma unroll
-                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(d, a_lo + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, 1);
-#pragma unroll
                 for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(d, a_hi + koff(ks), w_lo + (uint64_t)(ks * 16), idesc, 1);
-                tc::mma_commit(a_empty);
+                tc::mma_commit(a_empty + 0);
+            }
+            __syncwarp();
+            HB_TIMED(0, tc::mbar_wait(a_full + 1, (uint32_t)(it & 1)));
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) tc::mma_f16_ss(d, a_lo + koff(ks), w_hi + (uint64_t)(ks * 16), idesc, 1);
+                tc::mma_commit(a_empty + 1);
                 tc::mma_commit(acc_full + acc);
             }
             __syncwarp();
@@ -1704,6 +1747,20 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
             const int64_t b = wg * WG + (row & 7);
             const int col = a.col0 + chunk * a.col_step + t;
             const int acc = (int)(it & 1);
+            // p16 mode: the sums the earlier chunks left for this position are fetched BEFORE the wait for the accumulator (a
+            // global round trip that used to follow it).  They were written by this CTA - window groups are pinned to workers -
+            // possibly in the job just before this one and by another warp: the four epilogue warps meet first.
+            const bool live = t < W && b < B;
+            const int first_chunk = col < W ? 0 : (col - W) / a.col_step + 1;
+            const int last_chunk = min(a.total_chunks - 1, col / a.col_step);
+            float4* pp = reinterpret_cast<float4*>(a.p16 + (b * T + col) * NCLS);
+            float4 old4[4];
+            const bool fetch_old = a.p16 != nullptr && live && a.chunk0 + chunk != first_chunk;
+            if (a.p16 != nullptr) {
+                tc::named_barrier_sync(HEADS_EPILOGUE_BARRIER, 128);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) old4[c4] = fetch_old ? __ldcg(pp + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             HB_TIMED(0, tc::mbar_wait(acc_full + acc, (uint32_t)((it / 2) & 1)));
             tc::tc_fence_after();
             float v[NCLS];
@@ -1715,7 +1772,7 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
 #ifdef HB_TIMELINE
             const long long t_math = acct ? clock64() : 0;
 #endif
-            if (t < W && b < B) {
+            if (live) {
                 float mb = -INFINITY, mr = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < NCLS; ++c) {
@@ -1735,15 +1792,10 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                     for (int c = 0; c < NBASE; ++c) v[c] /= sb;
 #pragma unroll
                     for (int c = NBASE; c < NCLS; ++c) v[c] /= sr;
-                    float4* pp = reinterpret_cast<float4*>(a.p16 + (b * T + col) * NCLS);
-                    const int first_chunk = col < W ? 0 : (col - W) / a.col_step + 1;
-                    const int last_chunk = min(a.total_chunks - 1, col / a.col_step);
-                    if (a.chunk0 + chunk != first_chunk) {
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            const float4 o = __ldcg(pp + c4);
-                            v[4 * c4] += o.x; v[4 * c4 + 1] += o.y; v[4 * c4 + 2] += o.z; v[4 * c4 + 3] += o.w;
-                        }
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 o = old4[c4];
+                        v[4 * c4] += o.x; v[4 * c4 + 1] += o.y; v[4 * c4 + 2] += o.z; v[4 * c4 + 3] += o.w;
                     }
                     if (a.chunk0 + chunk == last_chunk) {
                         // the sums of this column are final: first-index argmax (strict >, classes in order), labels only
@@ -2678,19 +2730,23 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             if (two_tiles) {
                 // two tiles per recurrence CTA: the MMA issuer's step pair and each tile's first gate warp, cycles after the
                 // issuer's release for that tile's step
-                double iss[4] = {0}, g[2][7] = {{0}};
+                double iss[4] = {0}, g[2][8] = {{0}};
                 int n = 0;
                 for (int st = 20; st < 90; ++st, ++n) {
                     const long long* q0 = &hbuf[(st * 2) * 2];
                     iss[0] += q0[1] - q0[0]; iss[1] += q0[2] - q0[1]; iss[2] += q0[3] - q0[2]; iss[3] += q0[4] - q0[3];
                     for (int tl = 0; tl < 2; ++tl)
-                        for (int k = 0; k < 7; ++k) g[tl][k] += hbuf[1024 + (tl * 128 + st) * 8 + k] - hbuf[(st * 2 + tl) * 2];
+                        for (int k = 0; k < 8; ++k) g[tl][k] += hbuf[1024 + (tl * 128 + st) * 8 + k] - hbuf[(st * 2 + tl) * 2];
                 }
                 fprintf(stderr, "[two-tile step pair, MMA issuer, cycles] tile 0 issue %.0f | wait for tile 1 %.0f | tile 1 issue %.0f | wait for tile 0 %.0f | pair %.0f\n",
                         iss[0] / n, iss[1] / n, iss[2] / n, iss[3] / n, (iss[0] + iss[1] + iss[2] + iss[3]) / n);
+                fprintf(stderr, "  y-store warp, cycles per step pair: y_ready waits %.0f | store issue %.0f | wait for the previous stores' reads %.0f | publication (every 4th) %.0f\n",
+                        hbuf[3000] / 70.0, hbuf[3001] / 70.0, hbuf[3002] / 70.0, hbuf[3003] / 70.0);
+                fprintf(stderr, "  y-store warp: release store of the progress counter %.0f cycles per step pair\n", hbuf[3004] / 70.0);
                 const char* names[7] = {"gi+h_free", "acc_r", "acc_z", "acc_n", "ldtm_n", "math_done", "arrived"};
                 for (int tl = 0; tl < 2; ++tl) {
                     fprintf(stderr, "  tile %d gate warp 0, cycles after the issuer's release of the step:", tl);
+                    fprintf(stderr, " gi_full=%.0f", g[tl][7] / n);
                     for (int k = 0; k < 7; ++k) fprintf(stderr, " %s=%.0f", names[k], g[tl][k] / n);
                     fprintf(stderr, "\n");
                 }
