@@ -816,12 +816,17 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
     constexpr int NW = NLIVE * 4 / GW;                       // windows per gate thread
     static_assert(NW == 2 || NW == 4 || NW == 8, "a gate thread's windows lie in one window group");
     constexpr int NG = NLIVE / WG;                           // live window groups per CTA
-    constexpr uint32_t HB_BYTES = (N / WG) * YBLK;           // one h operand image (hi or lo), all N columns
+    // one h operand image (hi or lo): all N columns - or, stacked with 8 live windows, just the one 8-row group that exists
+    // (rows 8-15 of the B operand are then the lo image, which directly follows the hi image)
+    constexpr bool COMPACT = STACK && NLIVE == 8;
+    constexpr uint32_t HB_BYTES = COMPACT ? YBLK : (N / WG) * YBLK;
     constexpr uint32_t GI_STAGE_BYTES = NLIVE * GI_ROW_BYTES;
     constexpr int GI_STAGES = gi_stages<NLIVE>();
     // h operand images, NBUF buffers: step s reads buffer s % NBUF (h_s) and writes buffer (s+1) % NBUF (h_{s+1}),
     // so the y store of an image has NBUF steps to drain before the buffer is written again
-    constexpr int NBUF = h_buffers<N>();
+    // (compact images: twice the buffers in the same shared memory.  The y-store warp is away for 3-7 thousand cycles at
+    // every publication of its progress counter - see PUBLISH_EVERY - and hands no buffer back meanwhile)
+    constexpr int NBUF = COMPACT ? 2 * h_buffers<N>() : h_buffers<N>();
     uint8_t* h_img = smem;                                   // [NBUF buffers][hi, lo][HB_BYTES]
     uint8_t* gi_s = smem + 2 * NBUF * HB_BYTES;
     // (Measured and dropped: one commit barrier per group of four gate warps - the extra commits delayed every
@@ -1208,9 +1213,9 @@ tc_recurrence_kernel(const RecArgs ra)
 // and the cross-CTA counters of RecLayer; a CTA then covers 2 NLIVE / 8 consecutive window groups.
 // ---------------------------------------------------------------------------------------------
 template <int NLIVE> __host__ __device__ constexpr int rec2_stages() { return NLIVE <= 8 ? 6 : 3; }    // gi' stages per tile
-template <int NLIVE> __host__ __device__ constexpr int rec2_hbufs() { return NLIVE <= 8 ? 4 : 2; }     // h image buffers per tile
+template <int NLIVE> __host__ __device__ constexpr int rec2_hbufs() { return NLIVE <= 8 ? 8 : 2; }     // h image buffers per tile
 template <int NLIVE> constexpr size_t recurrence2_smem() {
-    return (size_t)2 * (2 * rec2_hbufs<NLIVE>() * 2 * YBLK + rec2_stages<NLIVE>() * NLIVE * GI_ROW_BYTES) + 512 +
+    return (size_t)2 * (2 * rec2_hbufs<NLIVE>() * (NLIVE <= 8 ? 1 : 2) * YBLK + rec2_stages<NLIVE>() * NLIVE * GI_ROW_BYTES) + 512 +
            (size_t)REC_GATE_WARPS * 32 * (NLIVE / 2) * 4 + 1024;     // tiles, barriers, state parked between phases, alignment
 }
 constexpr int REC2_PHASE_BARRIER = REC_STEP_BARRIER + 2;     // named barrier: all gate warps of both tiles, once per phase
@@ -1225,7 +1230,7 @@ __device__ __forceinline__ void recurrence2_role(const RecArgs& ra, uint8_t* sme
     constexpr int NW = NLIVE / 2;                            // windows per gate thread
     constexpr int NG = NLIVE / WG;                           // window groups per tile
     constexpr int NGC = 2 * NG;                              // window groups per CTA
-    constexpr uint32_t HB_BYTES = 2 * YBLK;                  // one h operand image (hi or lo): two 8-row groups
+    constexpr uint32_t HB_BYTES = STACK ? YBLK : 2 * YBLK;   // one h operand image (hi or lo): one (stacked) or two 8-row groups
     constexpr int NBUF = rec2_hbufs<NLIVE>(), ST = rec2_stages<NLIVE>();
     constexpr uint32_t GI_STAGE_BYTES = NLIVE * GI_ROW_BYTES;
     constexpr uint32_t TILE_BYTES = 2 * NBUF * HB_BYTES + ST * GI_STAGE_BYTES;
