@@ -677,7 +677,9 @@ constexpr int PUBLISH_LAG = 4;
 // reverse direction's count of W - 8 t columns is congruent to W modulo 8.  The release store costs the warp 3-7 thousand
 // cycles (its MEMBAR.GPU also waits for the newest bulk stores, still in flight): once per 8 steps, not per 4.
 // (A relaxed store after cp.async.bulk.wait_group is NOT enough: tests/test_gpu_stress.py caught batches that differed
-// from run to run with it.)
+// from run to run with it.)  Nothing is published in the last 8 steps of a phase: the final publication follows anyway,
+// and a warp that has just spent a release store there hands the phase's last images to the copy engine late - the other
+// layer's first tiles wait for exactly those.
 #ifndef HB_PUBLISH_EVERY
 #define HB_PUBLISH_EVERY 8
 #endif
@@ -992,7 +994,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(h_free + buf);
-            if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG - pub_off) & (PUBLISH_EVERY - 1)) == 0) {
+            if (flag != nullptr && s >= PUBLISH_LAG && s + PUBLISH_EVERY < W && ((s + 1 - PUBLISH_LAG - pub_off) & (PUBLISH_EVERY - 1)) == 0) {
                 // at the consumers' tile boundaries: all stores but the newest PUBLISH_LAG have landed in global memory, publish
                 // that many completed columns to the consumer CTAs.  (Waiting for the newest store, or
                 // fencing every step, would put a global round trip on the step's critical path via h_free.)
@@ -1374,7 +1376,7 @@ __device__ __forceinline__ void recurrence2_role(const RecArgs& ra, uint8_t* sme
             // memory (waiting for each store right after issuing it - twice per step pair - made this warp pace the kernel)
             HB_YT(2, if (stores) tc::bulk_wait_read_pending<1>(); __syncwarp());
             if (s > 0 && lane < 2) tc::mbar_arrive(h_free(lane) + s % NBUF);
-            if (flag != nullptr && s >= PUBLISH_LAG && ((s + 1 - PUBLISH_LAG - pub_off) & (PUBLISH_EVERY - 1)) == 0) {
+            if (flag != nullptr && s >= PUBLISH_LAG && s + PUBLISH_EVERY < W && ((s + 1 - PUBLISH_LAG - pub_off) & (PUBLISH_EVERY - 1)) == 0) {
                 HB_YT(3, if (stores) tc::bulk_wait_pending<PUBLISH_LAG>(); __syncwarp());   // (one bulk group per lane and step)
 #ifndef HB_PUBLISH_LANE
 #define HB_PUBLISH_LANE 0
