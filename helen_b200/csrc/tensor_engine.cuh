@@ -90,6 +90,14 @@ __device__ __forceinline__ void gi_load(const float* blk, int u, int w0, float* 
     }
 }
 
+// -DHB_TIMELINE: the chain from the encoder's last column to the decoder's first step of window group 0 in chunk 2
+// (slots 7400..: encoder fwd / rev final publication, scheduler pick, loader issue, MMA commit, counter raised, decoder
+// loader saw the counter, first gi row in shared memory)
+#ifdef HB_TIMELINE
+#define HB_CHAIN(dbgp, cond, k) do { if ((dbgp) != nullptr && (cond)) (dbgp)[7400 + (k)] = (long long)globaltimer_ns(); } while (0)
+#else
+#define HB_CHAIN(dbgp, cond, k) do { } while (0)
+#endif
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -416,9 +424,14 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                         if (acct) t_wait[1] += clock64() - t_;
 #endif
                         e = job_tab[n_px + found];
-                        {   // bit 30: this group's encoder has finished, its decoder may be waiting for the tile: counters go out at once
+                        HB_CHAIN(a.dbg, worker == 0 && blk == 0 && chunk == 2 && lane == 0 && proj_decode(a, e).wg == 0 && proj_decode(a, e).t0 == 0, 2);
+                        {   // bit 30: one direction of this group's encoder has finished, so the tile is one the decoder starts with (the
+                            // forward decoder's first tile is gated by the REVERSE encoder's last columns) or the decoder is
+                            // already running: its counters go out at once, not with the next batch.  (Requiring both directions
+                            // left the decoder's very first tile in a batch whenever the other encoder direction published its
+                            // last columns a microsecond later: 4 us between "counter raised" and "decoder saw it".)
                             const ProjJob q = proj_decode(a, e);
-                            if (enc_count[q.wg * 2] >= base + (unsigned long long)W && enc_count[q.wg * 2 + 1] >= base + (unsigned long long)W) e |= 1 << 30;
+                            if (enc_count[q.wg * 2] >= base + (unsigned long long)W || enc_count[q.wg * 2 + 1] >= base + (unsigned long long)W) e |= 1 << 30;
                         }
                         __syncwarp();
                         if (lane == 0) job_done[found] = 1;
@@ -484,6 +497,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 }
             }
             __syncwarp();
+            HB_CHAIN(a.dbg, loop && worker == 0 && blk == 0 && chunk == 2 && lane == 0 && !j.pixel && j.wg == 0 && j.t0 == 0, 3);
             if (loop && lane == 0) *loader_count = it + 1;
 #ifdef HB_TIMELINE
             if (acct) t_wait[3] += clock64() - t_issue;
@@ -542,6 +556,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                 tc::mma_commit(acc_full + acc);
             }
             __syncwarp();
+            HB_CHAIN(a.dbg, loop && worker == 0 && blk == 0 && chunk == 2 && lane == 0 && !j.pixel && j.wg == 0 && j.t0 == 0, 4);
         }
         }
         HB_ROLE_REPORT(1);
@@ -619,6 +634,7 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                     if (lane == 0)
                         for (int k = 0; k < n_pending; ++k) tc::red_relaxed_gpu_add(pending[k], 1ull);
                     n_pending = 0;
+                    HB_CHAIN(a.dbg, worker == 0 && blk == 0 && chunk == 2 && (warp & 3) == 0 && lane == 0 && !j.pixel && j.wg == 0 && j.t0 == 0, 5);
                 }
             }
 #ifdef HB_TIMELINE
@@ -961,6 +977,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 // the counter; the bulk loads below belong to the async proxy: order them after what the acquire made visible
                 __syncwarp();
                 tc::fence_proxy_async_all();
+                HB_CHAIN(ra.dbg, n_layers > 1 && cta_x == 0 && dir == 0 && chunk == 2 && li == 1 && s == 0 && lane == 0, 6);
             }
             if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
             if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, NG * GI_GRP_BYTES);
@@ -1016,6 +1033,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         if (lane < 2 * NG) tc::bulk_wait0();
         __syncwarp();
         if (flag != nullptr && lane == 0) tc::st_release_gpu(flag, prog_base + (unsigned long long)W);
+        HB_CHAIN(ra.dbg, n_layers > 1 && cta_x == 0 && chunk == 2 && li == 0 && lane == 0, dir);
         HB_STAMP(4);                                         // all columns published
     } else if (warp == GW) {
         // ===================== MMA issuer =====================
@@ -1119,6 +1137,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             const int drole = warp == 0 ? 1 : (warp == GW - 1 ? 2 : 3);
 #endif
             tc::mbar_wait(gi_full + stage, gi_par);
+            HB_CHAIN(ra.dbg, n_layers > 1 && cta_x == 0 && dir == 0 && chunk == 2 && li == 1 && s == 0 && tid == 0, 7);
             // the buffer h_{s+1} goes to: its y store of NBUF steps ago has drained long since - waited for HERE, where
             // the warp would idle anyway, not between the z and n phases
             if (s >= NBUF) tc::mbar_wait(h_free + nb, (uint32_t)(((s - NBUF) / NBUF) & 1));
@@ -1178,6 +1197,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
 #endif
         }
         if (warp == 0) HB_STAMP(2);                          // last step done
+        HB_CHAIN(ra.dbg, n_layers > 1 && cta_x == 0 && chunk == 2 && li == 0 && tid == 0, 8 + dir);
         if (stamp) ra.phase_times[phase * 4 + 2] = (long long)globaltimer_ns();
         // W_hh of the NEXT phase's layer -> TMEM right away, while the y store drains and publishes the last columns: all
         // MMAs of this phase have completed (every gate warp has waited for its last accumulator) and nothing else reads
@@ -2741,6 +2761,13 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
                 }
                 if (n_chunks > 0)
                     fprintf(stderr, "  last chunk: dec end %.1f\n", (hbuf[4096 + (64 + n_chunks - 1) * 2 + 1] - t0) * 1e-3);
+                if (!two_tiles && n_chunks > 2) {
+                    const long long c0 = hbuf[7408];
+                    auto us = [&](int k) { return (hbuf[7400 + k] - c0) * 1e-3; };
+                    fprintf(stderr, "  chunk 2, window group 0, us after the forward encoder's last step: reverse encoder's last step %.2f | final publication fwd %.2f rev %.2f | "
+                            "scheduler picks decoder tile 0 %.2f | copies issued %.2f | MMAs committed %.2f | counter raised %.2f | decoder loader saw it %.2f | first gi row in shared memory %.2f\n",
+                            us(9), us(0), us(1), us(2), us(3), us(4), us(5), us(6), us(7));
+                }
             }
 #ifdef HB_TIMELINE_STEPS
             if (two_tiles) {
