@@ -158,7 +158,8 @@ int hb_enable_kernel_timing(hb_handle *handle, int enable);
 int hb_kernel_time_ms(hb_handle *handle, double *total_ms, int64_t *launches, int reset);
 
 /* How the last hb_predict_windows call of the tensor engine was laid out on the chip (reporting only).
- * chunkloop = 1: the whole chunk loop of the batch ran as ONE launch of tc_chunkloop_kernel with
+ * chunkloop = 1: the whole chunk loop of the batch ran as ONE launch of tc_chunkloop_kernel (windows_per_cta = 8,
+ * batches of up to 320 windows) or tc_chunkloop2_kernel (windows_per_cta = 16 as two 8-window tiles, up to 512) with
  * 2 * recurrence_ctas recurrence CTAs, 6 * projection_workers projection CTAs and heads_workers heads
  * CTAs, all resident at once; chunkloop = 0: four launches per chunk (the batch does not fit on the chip). */
 typedef struct hb_launch_plan {
