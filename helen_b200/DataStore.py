@@ -74,13 +74,25 @@ class DataStore(object):
             self.file_handler[chunk + '/bases'] = np.asarray(predicted_bases).astype(np.uint8)
             self.file_handler[chunk + '/rles'] = np.asarray(predicted_rles).astype(np.uint8)
 
+    def _as_uint32(self, position):
+        """position.astype(uint32) (DataStore.py:126 stores positions as uint32) into a buffer kept between calls: a fresh
+        6 MB array per batch costs more in page faults than the conversion itself."""
+        if position.dtype == np.uint32:
+            return position
+        buf = getattr(self, "_position_buffer", None)
+        if buf is None or buf.shape[1:] != position.shape[1:] or buf.shape[0] < position.shape[0]:
+            buf = self._position_buffer = np.empty(position.shape, np.uint32)
+        out = buf[:position.shape[0]]
+        np.copyto(out, position, casting="unsafe")
+        return out
+
     def write_predictions(self, contig, contig_start, contig_end, chunk_id, position, predicted_bases, predicted_rles,
                           filename=None):
         """One batch of records (the per-batch loop of predict_gpu.py:176-179 in one call): same file content as
         calling write_prediction per record, with the dtype conversions done once per batch."""
-        position = np.asarray(position).astype(np.uint32)
-        predicted_bases = np.asarray(predicted_bases).astype(np.uint8)
-        predicted_rles = np.asarray(predicted_rles).astype(np.uint8)
+        position = self._as_uint32(np.asarray(position))
+        predicted_bases = np.asarray(predicted_bases).astype(np.uint8, copy=False)
+        predicted_rles = np.asarray(predicted_rles).astype(np.uint8, copy=False)
         contig_start = np.asarray(contig_start).reshape(-1).tolist()
         contig_end = np.asarray(contig_end).reshape(-1).tolist()
         chunk_id = np.asarray(chunk_id).reshape(-1).tolist()

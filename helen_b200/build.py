@@ -79,6 +79,33 @@ def build_stitch(force=False):
     return STITCH_LIB
 
 
+
+
+FEED_SRC = os.path.join(PKG, "csrc_host", "feed_host.cpp")
+FEED_LIB = os.path.join(LIB_DIR, "libhelen_feed.so")
+
+
+def build_feed(force=False):
+    """Compile helen_b200/csrc_host/feed_host.cpp -> helen_b200/lib/libhelen_feed.so (include/helen_feed.h)."""
+    deps = [FEED_SRC, os.path.join(ROOT, "include", "helen_feed.h")]
+    if not force and os.path.exists(FEED_LIB) and all(os.path.getmtime(p) <= os.path.getmtime(FEED_LIB) for p in deps):
+        return FEED_LIB
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not found; cannot build libhelen_feed.so")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    tmp = FEED_LIB + ".tmp"
+    cmd = [gxx, "-O3", "-g", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", "-pthread", "-o", tmp, FEED_SRC]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if proc.stderr.strip():
+        sys.stderr.write(proc.stderr)
+    os.replace(tmp, FEED_LIB)
+    return FEED_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_stitch(force="--force" in sys.argv))
+    print(build_feed(force="--force" in sys.argv))

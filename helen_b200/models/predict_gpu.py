@@ -7,6 +7,8 @@ group only served a DistributedDataParallel wrapper that does nothing under no_g
 per-batch loop body of the reference (predict_gpu.py:97-159) is one call into the CUDA library.
 """
 import os
+import queue
+import threading
 import sys
 import time
 
@@ -19,6 +21,7 @@ from ..options import ImageSizeOptions
 from ..predictor import WindowPredictor
 from ..TextColor import TextColor
 from .bulk_reader import BulkImageBatches
+from .prefetch import ThreadPrefetcher
 from .dataloader_predict import SequenceDataset
 from .ModelHander import ModelHandler
 
@@ -50,9 +53,16 @@ def predict(test_file, output_filename, model_path, batch_size, num_workers, ran
         test_data = SequenceDataset(image_directory=None, file_list=test_file)
         test_loader = DataLoader(test_data, batch_size=batch_size, shuffle=False, num_workers=num_workers, pin_memory=True)
     else:
-        # bulk feed: an item is a whole batch read from one file in one pass (models/bulk_reader.py)
-        test_data = BulkImageBatches(image_directory=None, file_list=test_file, batch_size=batch_size)
-        test_loader = DataLoader(test_data, batch_size=None, shuffle=False, num_workers=num_workers, pin_memory=True)
+        # bulk feed: an item is a whole batch read from one file in one pass (models/bulk_reader.py).  Files the native feed
+        # library reads are fetched by its threads straight into a ring of page-locked buffers, one batch ahead of the GPU
+        # (models/prefetch.py); other files go through DataLoader worker processes as in the reference.
+        # Ring of 8: two batches queued, one being filled, the one on the GPU, up to four with the writer thread.
+        test_data = BulkImageBatches(image_directory=None, file_list=test_file, batch_size=batch_size, ring=8)
+        if test_data.native_for_all() and os.environ.get("HELEN_B200_FEED_PROCESSES", "0") in ("", "0"):
+            test_loader = ThreadPrefetcher(test_data, depth=2, held=5)
+        else:
+            test_data.ring = 0
+            test_loader = DataLoader(test_data, batch_size=None, shuffle=False, num_workers=num_workers, pin_memory=True)
     total_batches = len(test_loader)
     windows_done, t_begin = 0, time.time()
     device = _cuda_device(device_id)
@@ -66,16 +76,35 @@ def predict(test_file, output_filename, model_path, batch_size, num_workers, ran
         prediction_data_file.write_predictions(contig, contig_start, contig_end, chunk_id, position,
                                                base_labels, rle_labels, filename)
 
-    in_flight = None
+    # The prediction file is written by its own thread, at most three batches behind the GPU: the loop below only reads a
+    # batch off the feed and launches it (the writer's numpy conversions and file writes release the interpreter lock).
+    pending = queue.Queue(maxsize=3)
+    writer_error = []
+
+    def writer():
+        torch.cuda.set_device(device_id)                # (the current device is a per-thread setting)
+        while True:
+            item = pending.get()
+            if item is None:
+                return
+            if writer_error:
+                continue                                # keep draining so that the producer never blocks
+            try:
+                write_out(item)
+            except BaseException as error:
+                writer_error.append(error)
+
+    writer_thread = threading.Thread(target=writer, name="helen-prediction-writer", daemon=True)
+    writer_thread.start()
     for batch_iterator, (contig, contig_start, contig_end, chunk_id, images, position, filename) in enumerate(test_loader, 1):
         start_time = time.time()
         # the whole loop body of the reference (predict_gpu.py:97-159) is this one asynchronous call
         base_dev, rle_dev = predictor.predict(images.to(device, non_blocking=True))
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(device))
-        if in_flight is not None:
-            write_out(in_flight)
-        in_flight = ((contig, contig_start, contig_end, chunk_id, position, filename), base_dev, rle_dev, done)
+        pending.put(((contig, contig_start, contig_end, chunk_id, position, filename), base_dev, rle_dev, done))
+        if writer_error:
+            break
         windows_done += images.size(0)
         if rank == 0:
             eta = (time.time() - start_time) * (total_batches - batch_iterator)
@@ -83,8 +112,10 @@ def predict(test_file, output_filename, model_path, batch_size, num_workers, ran
             sys.stderr.write(TextColor.GREEN + "INFO: BATCHES DONE: " + str(batch_iterator) + "/" + str(total_batches)
                              + ". ESTIMATED TIME LEFT: " + stamp + " ("
                              + str(int(windows_done / max(time.time() - t_begin, 1e-9))) + " WINDOWS/S)\n" + TextColor.END)
-    if in_flight is not None:
-        write_out(in_flight)
+    pending.put(None)
+    writer_thread.join()
+    if writer_error:
+        raise writer_error[0]
     prediction_data_file.close()
     predictor.close()
 

@@ -7,7 +7,7 @@ _STORE = {}
 
 class _Dataset:
     def __init__(self, value):
-        self.value = np.asarray(value)
+        self.value = np.array(value)                   # a copy, as h5py / minih5 take at assignment: the caller may reuse its buffer
 
     def __getitem__(self, key):
         return self.value if key == () else self.value[key]

@@ -1,0 +1,154 @@
+"""Native input feed (include/helen_feed.h) against the general reader on the same files.
+
+The native library restates, for whole batches and in C++, what SequenceDataset does per image
+(reference helen/modules/python/models/dataloader_predict.py:54-88); helen_b200.minih5 is the checker here: both must
+list the images in the same order and return identical arrays, paddings and contig names."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helen_b200 import _feed_native, hdf5
+from helen_b200.models.bulk_reader import BulkImageBatches
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def write_images(path, n_images, features=90, position_dtype=np.int64, scalar_dtype=np.int64, contig=b"chr20", seed=7, long_image=None):
+    rng = np.random.default_rng(seed)
+    with hdf5.open_file(path, "w") as f:
+        for i in range(n_images):
+            length = 1000 if i % 3 else 700 + (i % 5)
+            if long_image == i:
+                length = 1001
+            image = rng.integers(0, 256, (length, features), dtype=np.uint8)
+            position = np.stack([np.arange(length) + i * 1000, rng.integers(0, 4, length), np.zeros(length, np.int64)], 1).astype(position_dtype)
+            base = "images/img_%05d/" % ((i * 7919) % 100000)        # names out of creation order: the file order is by name
+            f[base + "contig"] = np.array([contig], dtype="S")
+            f[base + "contig_start"] = np.array([i * 1000], dtype=scalar_dtype)
+            f[base + "contig_end"] = np.array([i * 1000 + length], dtype=scalar_dtype)
+            f[base + "feature_chunk_idx"] = np.array([i], dtype=scalar_dtype)
+            f[base + "image"] = image
+            f[base + "position"] = position
+
+
+def test_library_exports_what_the_header_declares():
+    header = open(os.path.join(ROOT, "include", "helen_feed.h")).read()
+    declared = set(re.findall(r"\b(hf_[a-z_]+)\s*\(", header))
+    assert declared == set(_feed_native.SIGNATURES), declared ^ set(_feed_native.SIGNATURES)
+    lib = _feed_native.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.hf_abi_version() == _feed_native.HF_ABI_VERSION
+
+
+@pytest.mark.parametrize("n_images,position_dtype,scalar_dtype,features", [(11, np.int64, np.int64, 90), (300, np.int32, np.int32, 10),
+                                                                            (29, np.uint32, np.int16, 33)])
+def test_native_batches_equal_the_general_reader(tmp_path, monkeypatch, n_images, position_dtype, scalar_dtype, features):
+    monkeypatch.setenv("HELEN_B200_HDF5", "minih5")
+    paths = [str(tmp_path / "a.h5"), str(tmp_path / "b.h5")]
+    write_images(paths[0], n_images, features, position_dtype, scalar_dtype)
+    write_images(paths[1], 5, features, position_dtype, scalar_dtype, contig=b"chr'X'_alt", seed=9)
+    native = BulkImageBatches(None, file_list=paths, batch_size=64, native=True, threads=3)
+    general = BulkImageBatches(None, file_list=paths, batch_size=64, native=False)
+    assert native._native_paths == set(paths) and not general._native_paths
+    assert native.blocks == general.blocks and native._names == general._names        # same images in the same order
+    assert len(native._names[paths[0]]) == n_images
+    for index in range(len(native)):
+        a, b = native[index], general[index]
+        assert a[0] == b[0] and a[6] == b[6]
+        for x, y in zip(a[1:6], b[1:6]):
+            assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y)
+    assert native[len(native) - 1][0][0] == "chrX_alt"                                 # apostrophes removed (dataloader_predict.py:70)
+    native.close()
+    general.close()
+
+
+def test_native_feed_through_worker_processes(tmp_path):
+    from torch.utils.data import DataLoader
+    path = str(tmp_path / "w.h5")
+    write_images(path, 40, 10)
+    want = list(DataLoader(BulkImageBatches(None, file_list=[path], batch_size=16, native=False), batch_size=None))
+    got = list(DataLoader(BulkImageBatches(None, file_list=[path], batch_size=16, native=True), batch_size=None, num_workers=2))
+    assert len(got) == len(want) == 3
+    for a, b in zip(got, want):
+        assert list(a[0]) == list(b[0]) and all(torch.equal(x, y) for x, y in zip(a[1:6], b[1:6]))
+
+
+def test_errors_and_fallback(tmp_path):
+    junk = str(tmp_path / "junk.h5")
+    with open(junk, "wb") as f:
+        f.write(b"not an hdf5 file at all" * 10)
+    with pytest.raises(IOError):
+        _feed_native.ImageFile(junk)
+    long_path = str(tmp_path / "long.h5")
+    write_images(long_path, 4, 10, long_image=2)
+    with pytest.raises(ValueError, match="IMAGE SIZE ERROR"):
+        BulkImageBatches(None, file_list=[long_path], batch_size=8, native=True)[0]
+    with pytest.raises(ValueError, match="IMAGE SIZE ERROR"):
+        BulkImageBatches(None, file_list=[long_path], batch_size=8, native=False)[0]
+    # a file without /images: zero images, skipped with a warning by both readers
+    empty = str(tmp_path / "empty.h5")
+    with hdf5.open_file(empty, "w") as f:
+        f["other/x"] = np.arange(3)
+    assert len(_feed_native.ImageFile(empty)) == 0
+    assert len(BulkImageBatches(None, file_list=[empty], native=True)) == 0
+    # truncated file: the library refuses to read past the mapping instead of faulting
+    whole = open(long_path, "rb").read()
+    cut = str(tmp_path / "cut.h5")
+    with open(cut, "wb") as f:
+        f.write(whole[:len(whole) // 3])
+    try:
+        handle = _feed_native.ImageFile(cut)
+        with pytest.raises((IOError, _feed_native.Unsupported)):
+            handle.read_block(0, len(handle), 1000, 2)
+    except IOError:
+        pass
+
+
+def test_chunked_file_takes_the_general_reader(tmp_path):
+    """A dataset layout outside the subset (chunked + deflate) is refused with `Unsupported`, not misread."""
+    from test_minih5 import _assemble_chunked_file
+    path = str(tmp_path / "c.h5")
+    _assemble_chunked_file(path, np.arange(1000 * 90, dtype=np.uint16).reshape(1000, 90), (256, 32), True, False)
+    handle = _feed_native.ImageFile(path)                     # opens: the root group is fine, there is just no /images
+    assert len(handle) == 0
+
+
+def test_ring_buffers_and_thread_prefetch(tmp_path):
+    """The driver's feed (models/predict_gpu.py): native reads into a ring of reused buffers, one background thread ahead."""
+    from helen_b200.models.prefetch import ThreadPrefetcher
+    paths = [str(tmp_path / "a.h5"), str(tmp_path / "b.h5")]
+    write_images(paths[0], 50, 10)
+    write_images(paths[1], 21, 10, seed=3)
+    general = BulkImageBatches(None, file_list=paths, batch_size=8, native=False)
+    ringed = BulkImageBatches(None, file_list=paths, batch_size=8, native=True, threads=2, ring=5)
+    with pytest.raises(ValueError, match="too small"):
+        ThreadPrefetcher(BulkImageBatches(None, file_list=paths, batch_size=8, native=True, ring=4), depth=2)
+    assert ringed.native_for_all() and not general.native_for_all()
+    seen = 0
+    held = []
+    for index, batch in enumerate(ThreadPrefetcher(ringed, depth=2)):
+        want = general[index]
+        assert batch[0] == want[0] and all(torch.equal(x, y) for x, y in zip(batch[1:6], want[1:6]))
+        held.append((batch, want))
+        if len(held) > 1:                                   # the previous batch is still intact (the driver's in-flight batch)
+            old, old_want = held.pop(0)
+            assert all(torch.equal(x, y) for x, y in zip(old[1:6], old_want[1:6]))
+        seen += batch[4].shape[0]
+    assert seen == 71 and len(ringed._ring_sets) == 5
+    # a consumer that stops early leaves no thread behind a full queue
+    it = iter(ThreadPrefetcher(ringed, depth=1))
+    next(it)
+    it.close()
+
+
+def test_prefetcher_passes_errors_on(tmp_path):
+    from helen_b200.models.prefetch import ThreadPrefetcher
+    path = str(tmp_path / "long.h5")
+    write_images(path, 12, 10, long_image=9)
+    data = BulkImageBatches(None, file_list=[path], batch_size=4, native=True, ring=5)
+    with pytest.raises(ValueError, match="IMAGE SIZE ERROR"):
+        list(ThreadPrefetcher(data, depth=2))

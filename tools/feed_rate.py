@@ -3,7 +3,7 @@
     python tools/feed_rate.py [--images 4096] [--features 90] [--workers 0,4,8] [--out profiles/r02_feed_rate.json]
 Writes MarginPolish-layout image files with the package's HDF5 layer, then times
   * the reference-style feed: SequenceDataset (one image per item) + DataLoader collation,
-  * the bulk feed: BulkImageBatches (one batch per item),
+  * the bulk feed: BulkImageBatches (one batch per item) through the general reader and through the native feed library,
   * DataStore.write_predictions in the reference schema and in the packed schema,
 and prints one JSON object (windows/s per arm, the backend used, host cores)."""
 import argparse
@@ -59,7 +59,10 @@ def main():
     for workers in [int(w) for w in args.workers.split(",")]:
         row = {"workers": workers}
         for name, make in (("item_reader", lambda: DataLoader(SequenceDataset(None, file_list=paths), batch_size=args.batch, shuffle=False, num_workers=workers)),
-                           ("bulk_reader", lambda: DataLoader(BulkImageBatches(None, file_list=paths, batch_size=args.batch), batch_size=None, shuffle=False, num_workers=workers))):
+                           ("bulk_reader", lambda: DataLoader(BulkImageBatches(None, file_list=paths, batch_size=args.batch, native=False), batch_size=None, shuffle=False, num_workers=workers)),
+                           ("native_reader_1_thread", lambda: DataLoader(BulkImageBatches(None, file_list=paths, batch_size=args.batch, native=True, threads=1), batch_size=None, shuffle=False, num_workers=workers)),
+                           ("native_reader_4_threads", lambda: DataLoader(BulkImageBatches(None, file_list=paths, batch_size=args.batch, native=True, threads=4), batch_size=None, shuffle=False, num_workers=workers)),
+                           ("native_reader_8_threads", lambda: DataLoader(BulkImageBatches(None, file_list=paths, batch_size=args.batch, native=True, threads=8), batch_size=None, shuffle=False, num_workers=workers))):
             loader = make()
             t0 = time.perf_counter()
             seen, checksum = 0, 0
