@@ -110,6 +110,31 @@ class DataStore(object):
             self.file_handler[group + '/bases'] = predicted_bases
             self.file_handler[group + '/rles'] = predicted_rles
             return
+        if hasattr(self.file_handler, "set_rows"):
+            # the package's own HDF5 layer: the same datasets as the loop below, with one file write per array and the
+            # bookkeeping of write_prediction (first record of a region / chunk wins) done on the batch
+            regions, region_rows, chunks, chunk_rows = [], [], [], []
+            for i in range(len(contig)):
+                prefix = "{}-{}-{}".format(contig[i], contig_start[i], contig_end[i])
+                base = '{}/{}/{}'.format(self._prediction_path_, contig[i], prefix)
+                if prefix not in self._written_regions:
+                    self._written_regions.add(prefix)
+                    regions.append(base)
+                    region_rows.append(i)
+                name = str(contig[i]) + prefix + str(chunk_id[i])
+                if name not in self._written_chunks:
+                    self._written_chunks.add(name)
+                    chunks.append(base + '/' + str(chunk_id[i]))
+                    chunk_rows.append(i)
+            if regions:
+                self.file_handler.set_rows(regions, 'contig_start', np.asarray([contig_start[i] for i in region_rows]))
+                self.file_handler.set_rows(regions, 'contig_end', np.asarray([contig_end[i] for i in region_rows]))
+            if chunks:
+                every = len(chunk_rows) == len(contig)
+                self.file_handler.set_rows(chunks, 'position', position if every else position[chunk_rows])
+                self.file_handler.set_rows(chunks, 'bases', predicted_bases if every else predicted_bases[chunk_rows])
+                self.file_handler.set_rows(chunks, 'rles', predicted_rles if every else predicted_rles[chunk_rows])
+            return
         for i in range(len(contig)):
             self.write_prediction(contig[i], contig_start[i], contig_end[i], chunk_id[i], position[i],
                                   predicted_bases[i], predicted_rles[i])

@@ -82,12 +82,14 @@ def build_stitch(force=False):
 
 
 FEED_SRC = os.path.join(PKG, "csrc_host", "feed_host.cpp")
+H5WRITE_SRC = os.path.join(PKG, "csrc_host", "h5write_host.cpp")
 FEED_LIB = os.path.join(LIB_DIR, "libhelen_feed.so")
 
 
 def build_feed(force=False):
-    """Compile helen_b200/csrc_host/feed_host.cpp -> helen_b200/lib/libhelen_feed.so (include/helen_feed.h)."""
-    deps = [FEED_SRC, os.path.join(ROOT, "include", "helen_feed.h")]
+    """Compile helen_b200/csrc_host/{feed_host,h5write_host}.cpp -> helen_b200/lib/libhelen_feed.so
+    (include/helen_feed.h: image batches out of the input files; include/helen_h5write.h: the prediction-file writer)."""
+    deps = [FEED_SRC, H5WRITE_SRC, os.path.join(ROOT, "include", "helen_feed.h"), os.path.join(ROOT, "include", "helen_h5write.h")]
     if not force and os.path.exists(FEED_LIB) and all(os.path.getmtime(p) <= os.path.getmtime(FEED_LIB) for p in deps):
         return FEED_LIB
     gxx = shutil.which("g++")
@@ -95,7 +97,7 @@ def build_feed(force=False):
         raise RuntimeError("g++ not found; cannot build libhelen_feed.so")
     os.makedirs(LIB_DIR, exist_ok=True)
     tmp = FEED_LIB + ".tmp"
-    cmd = [gxx, "-O3", "-g", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", "-pthread", "-o", tmp, FEED_SRC]
+    cmd = [gxx, "-O3", "-g", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", "-pthread", "-o", tmp, FEED_SRC, H5WRITE_SRC]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)

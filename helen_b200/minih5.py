@@ -31,7 +31,17 @@ import zlib
 
 import numpy as np
 
+import os
+
 SIGNATURE = b"\x89HDF\r\n\x1a\n"
+
+
+def _native_writer_wanted():
+    """HELEN_B200_NATIVE_WRITER=0 keeps the pure-Python writer; so does a build without libhelen_feed.so."""
+    if os.environ.get("HELEN_B200_NATIVE_WRITER", "1") == "0":
+        return False
+    from . import _h5write_native
+    return os.path.exists(_h5write_native.LIB_PATH)
 UNDEF = 0xFFFFFFFFFFFFFFFF
 LEAF_K, INTERNAL_K = 4, 16                    # libhdf5's defaults: 2K entries per symbol node, 2K children per B-tree node
 
@@ -543,6 +553,76 @@ def _datatype_message(dtype):
     raise TypeError("minih5 cannot store dtype %s" % dtype)
 
 
+def _storable(value):
+    """The array as both writers store it: utf-8 bytes for text, uint8 for booleans, little-endian."""
+    array = np.asarray(value)
+    if array.dtype.kind == "U":
+        array = np.char.encode(array, "utf-8")
+    if array.dtype.kind == "b":
+        array = array.astype(np.uint8)
+    if array.dtype.kind == "O":
+        raise TypeError("minih5 cannot store object arrays")
+    if array.dtype.byteorder == ">":
+        array = array.astype(array.dtype.newbyteorder("<"))
+    if array.dtype.kind not in "iufS" or (array.dtype.kind == "f" and array.dtype.itemsize not in (4, 8)):
+        raise TypeError("minih5 cannot store dtype %s" % array.dtype)     # (at assignment, not when close() writes the header)
+    return array
+
+
+class _NativeWriter(object):
+    """The same writer in C++ (include/helen_h5write.h, helen_b200/csrc_host/h5write_host.cpp): byte-identical files, but
+    the per-dataset bookkeeping and the group structure written at close() - two thirds of the time of a prediction file
+    in the reference's schema - cost no Python."""
+
+    def __init__(self, path):
+        import ctypes
+        from . import _h5write_native as native
+        self._ct, self._native, self._lib = ctypes, native, native.load()
+        self.path = path
+        self._err = ctypes.create_string_buffer(512)
+        self._handle = ctypes.c_void_p()
+        status = self._lib.hw_create(os.fsencode(path), ctypes.byref(self._handle), self._err, len(self._err))
+        if status != native.HW_OK:
+            self._handle = None
+            native.raise_for(status, self._err.value.decode(errors="replace"))
+
+    def _check(self, status):
+        if status != self._native.HW_OK:
+            self._native.raise_for(status, self._err.value.decode(errors="replace"))
+
+    def _described(self, array, shape):
+        if array.dtype.kind not in "iufS":
+            raise TypeError("minih5 cannot store dtype %s" % array.dtype)
+        dims = (self._ct.c_uint64 * max(len(shape), 1))(*shape)
+        return array.dtype.kind.encode(), array.dtype.itemsize, len(shape), dims
+
+    def set(self, path, value):
+        if not [p for p in str(path).split("/") if p]:
+            raise ValueError("empty dataset name")
+        array = _storable(value)
+        kind, itemsize, rank, dims = self._described(array, array.shape)
+        data = np.ascontiguousarray(array)             # (a 0-d array becomes 1-d here: the shape above is the dataset's)
+        self._check(self._lib.hw_dataset(self._handle, str(path).encode(), kind, itemsize, rank, dims, data.ctypes.data,
+                                         self._err, len(self._err)))
+
+    def set_rows(self, parents, name, value):
+        array = np.ascontiguousarray(_storable(value))
+        if array.ndim < 1 or array.shape[0] != len(parents):
+            raise ValueError("set_rows: one row per parent")
+        kind, itemsize, rank, dims = self._described(array, array.shape[1:])
+        packed = b"\0".join(str(p).encode() for p in parents) + b"\0"
+        self._check(self._lib.hw_rows(self._handle, packed, len(parents), str(name).encode(), kind, itemsize, rank, dims,
+                                      array.ctypes.data, self._err, len(self._err)))
+
+    def contains(self, key):
+        return bool(self._lib.hw_contains(self._handle, str(key).encode()))
+
+    def close(self):
+        handle, self._handle = self._handle, None      # (forgotten first: see _feed_native.ImageFile.close)
+        if handle is not None:
+            self._check(self._lib.hw_close(handle, self._err, len(self._err)))
+
+
 class _WNode(object):
     def __init__(self):
         self.children = {}                            # groups
@@ -583,15 +663,7 @@ class _Writer(object):
             node = nxt
         if parts[-1] in node.children:
             raise ValueError("Unable to create dataset (name already exists): " + str(path))
-        array = np.asarray(value)
-        if array.dtype.kind == "U":
-            array = np.char.encode(array, "utf-8")
-        if array.dtype.kind == "b":
-            array = array.astype(np.uint8)
-        if array.dtype.kind == "O":
-            raise TypeError("minih5 cannot store object arrays")
-        if array.dtype.byteorder == ">":
-            array = array.astype(array.dtype.newbyteorder("<"))
+        array = _storable(value)
         leaf = _WNode()
         leaf.is_dataset, leaf.shape, leaf.dtype = True, array.shape, array.dtype
         # the array's own buffer goes to the file: no tobytes() copy (a fresh multi-megabyte bytes object per dataset is
@@ -600,6 +672,42 @@ class _Writer(object):
         leaf.nbytes = flat.nbytes
         leaf.data_address = self._append(flat.view(np.uint8).data if flat.nbytes else b"") if flat.nbytes else UNDEF
         node.children[parts[-1]] = leaf
+
+    def set_rows(self, parents, name, value):
+        """len(parents) datasets ``parents[i] + '/' + name`` = row i of `value`; the array goes to the file in one piece."""
+        array = np.ascontiguousarray(_storable(value))
+        if array.ndim < 1 or array.shape[0] != len(parents):
+            raise ValueError("set_rows: one row per parent")
+        nodes = []
+        for parent in parents:
+            node = self.root
+            for part in [p for p in str(parent).split("/") if p]:
+                nxt = node.children.get(part)
+                if nxt is None:
+                    nxt = node.children[part] = _WNode()
+                if nxt.is_dataset:
+                    raise ValueError("%s/%s: %s is a dataset" % (parent, name, part))
+                node = nxt
+            if name in node.children:
+                raise ValueError("Unable to create dataset (name already exists): %s/%s" % (parent, name))
+            nodes.append(node)
+        row_bytes = array.nbytes // max(len(parents), 1)
+        base = self._append(array.reshape(-1).view(np.uint8).data) if array.nbytes else UNDEF
+        for i, node in enumerate(nodes):
+            if name in node.children:
+                raise ValueError("Unable to create dataset (name already exists): %s (twice in one call)" % name)
+            leaf = _WNode()
+            leaf.is_dataset, leaf.shape, leaf.dtype, leaf.nbytes = True, array.shape[1:], array.dtype, row_bytes
+            leaf.data_address = base + i * row_bytes if row_bytes else UNDEF
+            node.children[name] = leaf
+
+    def contains(self, key):
+        node = self.root
+        for part in [p for p in str(key).split("/") if p]:
+            if node.is_dataset or part not in node.children:
+                return False
+            node = node.children[part]
+        return True
 
     # ---- structure, written by close() ----------------------------------------------------
     def _write_dataset(self, node):
@@ -703,7 +811,7 @@ class File(object):
             self._reader = _Reader(path)
             self._root = Group(self._reader, self._reader.root_header, "/", self._reader.root_symtab)
         elif mode in ("w", "x", "w-"):
-            self._writer = _Writer(path)
+            self._writer = _NativeWriter(path) if _native_writer_wanted() else _Writer(path)
         else:
             raise ValueError("minih5 supports modes 'r' and 'w' (got %r); appending to an existing file needs h5py" % (mode,))
 
@@ -730,18 +838,22 @@ class File(object):
 
     def keys(self):
         if self._root is None:
+            if isinstance(self._writer, _NativeWriter):
+                raise IOError("minih5: a file opened for writing cannot be listed before it is closed")
             return list(self._writer.root.children.keys())
         return self._root.keys()
 
     def __contains__(self, key):
         if self._root is not None:
             return key in self._root
-        node = self._writer.root
-        for part in [p for p in str(key).split("/") if p]:
-            if node.is_dataset or part not in node.children:
-                return False
-            node = node.children[part]
-        return True
+        return self._writer.contains(key)
+
+    def set_rows(self, parents, name, value):
+        """len(parents) datasets ``parents[i] + '/' + name``, dataset i = value[i]: what a loop of assignments writes, with
+        one file write and no per-dataset Python (DataStore.write_predictions)."""
+        if self._writer is None:
+            raise IOError("minih5: file is not open for writing")
+        self._writer.set_rows(parents, name, value)
 
     def __getitem__(self, key):
         if self._root is None:

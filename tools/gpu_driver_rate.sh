@@ -1,6 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for cfg in "65536 90"; do
+timeout 600 python -m pytest tests/test_gpu_driver.py -m gpu -q -x 2>&1 | tail -2
+for cfg in "98304 10" "65536 90"; do
 set -- $cfg
 timeout 900 python tools/driver_rate.py --images $1 --features $2 --out gpurun_out/driver_rate_F$2.json 2> gpurun_out/driver_rate_F$2.err | python -c "
 import json,sys
