@@ -960,13 +960,21 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
         // prefetch then overlaps the W_hh upload of the gate warps)
         if (phase == 0) { tc::pdl_grid_dependency_wait(); tc::fence_proxy_async_all(); }   // gi' comes from an upstream kernel (generic-proxy stores)
         bool synced = false;
+        if (phase > 0) {
+            // later phases: join the phase-start barrier FIRST.  The MMA issuer waits there for every warp, and step 0's MMAs
+            // need h_0 and the weights, not gi: with the first loads ahead of the barrier (as in phase 0, where they overlap
+            // the W_hh upload) every phase started a global round trip late - the counter this warp polls below, then the
+            // copies - ~2.7 us from phase start to the first MMA in the timeline build.
+            __syncthreads();
+            synced = true;
+        }
         // lane 3 g + gate fetches that gate block (4 KB) of group g's column
         const int lg = min(lane / 3, NG - 1), lgate = lane % 3;
         const float* src0 = gi + gi_block(b0 / WG + lg, gi_cols, gi_col0, dir * 3 + lgate);
         uint8_t* dst0 = gi_s + lg * GI_GRP_BYTES + lgate * GI_BLK_BYTES;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % GI_STAGES;
-            if (s == GI_STAGES) { __syncthreads(); synced = true; }
+            if (s == GI_STAGES && !synced) { __syncthreads(); synced = true; }
             const int col = L.flag_abs ? gi_col0 + t : t;
             if (L.tile_flags != nullptr && (s == 0 || (col & 7) == (dir ? 7 : 0)) && (col >> 3) >= L.flag_skip_tiles) {
                 // chunk-loop kernel: the projection CTAs announce finished gi' tiles
@@ -1337,6 +1345,10 @@ __device__ __forceinline__ void recurrence2_role(const RecArgs& ra, uint8_t* sme
         // ===================== gi' loader: both tiles, ST steps ahead =====================
         if (phase == 0) { tc::pdl_grid_dependency_wait(); tc::fence_proxy_async_all(); }   // gi' was written with generic-proxy stores, the bulk loads are async-proxy reads
         bool synced = false;
+        if (phase > 0) {                                     // (see recurrence_role: the phase-start barrier first)
+            __syncthreads();
+            synced = true;
+        }
         // lanes [8 tile + 3 g, + 3): the three gate blocks (4 KB each) of group g of a tile
         const int tile_l = lane >> 3, g_l = min((lane & 7) / 3, NG - 1), gate_l = (lane & 7) % 3;
         const bool loads = tile_l < 2 && (lane & 7) < 3 * NG;
@@ -1344,7 +1356,7 @@ __device__ __forceinline__ void recurrence2_role(const RecArgs& ra, uint8_t* sme
         uint8_t* dst0 = gi_of(min(tile_l, 1)) + g_l * GI_GRP_BYTES + gate_l * GI_BLK_BYTES;
         for (int s = 0, t = t_first; s < W; ++s, t += dt) {
             const int stage = s % ST;
-            if (s == ST) { __syncthreads(); synced = true; }
+            if (s == ST && !synced) { __syncthreads(); synced = true; }
             const int col = L.flag_abs ? gi_col0 + t : t;
             if (L.tile_flags != nullptr && (s == 0 || (col & 7) == (dir ? 7 : 0)) && (col >> 3) >= L.flag_skip_tiles) {
                 // chunk-loop kernel: the projection CTAs announce finished gi' tiles (see recurrence_role)
