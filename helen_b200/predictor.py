@@ -70,9 +70,9 @@ class WindowPredictor(object):
 
     # -- lifecycle ------------------------------------------------------------------------
     def close(self):
-        if getattr(self, "_handle", None) and self._handle.value:
-            self._lib.hb_destroy(self._handle)
-            self._handle = ctypes.c_void_p()
+        handle, self._handle = getattr(self, "_handle", None), None     # forgotten before it is freed (close() also runs at shutdown)
+        if handle is not None and handle.value:
+            self._lib.hb_destroy(handle)
 
     def __del__(self):
         try:
