@@ -71,6 +71,10 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
+// The 128-byte line at `p` will not be read again: L2 may drop it without writing it back to DRAM.
+__device__ __forceinline__ void discard_l2_line(const void* p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void st_global_v4_hint(float4* p, float4 v, uint64_t policy) {
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
                  ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");

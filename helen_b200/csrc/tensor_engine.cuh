@@ -968,6 +968,7 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
             __syncthreads();
             synced = true;
         }
+        const bool discard_gi = n_layers > 1 && li == 1;
         // lane 3 g + gate fetches that gate block (4 KB) of group g's column
         const int lg = min(lane / 3, NG - 1), lgate = lane % 3;
         const float* src0 = gi + gi_block(b0 / WG + lg, gi_cols, gi_col0, dir * 3 + lgate);
@@ -988,6 +989,16 @@ __device__ __forceinline__ void recurrence_role(const RecArgs& ra, uint8_t* smem
                 HB_CHAIN(ra.dbg, n_layers > 1 && cta_x == 0 && dir == 0 && chunk == 2 && li == 1 && s == 0 && lane == 0, 6);
             }
             if (s >= GI_STAGES) tc::mbar_wait(gi_empty + stage, (uint32_t)((s / GI_STAGES - 1) & 1));
+            // chunk-loop kernel, decoder: the gi rows of GI_STAGES steps ago have been consumed and nobody reads them again
+            // (the next chunk's projection overwrites them): L2 may drop the dirty lines instead of writing them to DRAM
+            // (ncu at B=256: DRAM writes of the launch 3.10 -> 1.93 GB; the last GI_STAGES rows of a phase are left alone).
+            // 32 lines of 128 bytes per 4 KB block: one per lane and block - with all of a block's lines on one lane the
+            // loader fell behind and the launch was 9 % slower.
+            if (discard_gi && s >= GI_STAGES) {
+#pragma unroll
+                for (int gb = 0; gb < 3 * NG; ++gb)
+                    tc::discard_l2_line(reinterpret_cast<const char*>(gi + gi_block(b0 / WG + gb / 3, gi_cols, gi_col0 + (t - GI_STAGES * dt), dir * 3 + gb % 3)) + lane * 128);
+            }
             if (lane == 0) tc::mbar_arrive_expect_tx(gi_full + stage, NG * GI_GRP_BYTES);
             __syncwarp();
             // (L2 evict-first: a gi block is dead once this copy has read it - the decoder's - or is read once more a chunk
@@ -1369,6 +1380,11 @@ __device__ __forceinline__ void recurrence2_role(const RecArgs& ra, uint8_t* sme
             for (int tile = 0; tile < 2; ++tile) {
                 if (s >= ST) tc::mbar_wait(gi_empty(tile) + stage, (uint32_t)((s / ST - 1) & 1));
                 if (lane == 0) tc::mbar_arrive_expect_tx(gi_full(tile) + stage, NG * GI_GRP_BYTES);
+            }
+            if (n_layers > 1 && li == 1 && s >= ST) {        // consumed decoder gi rows: see recurrence_role
+#pragma unroll
+                for (int gb = 0; gb < 3 * NGC; ++gb)
+                    tc::discard_l2_line(reinterpret_cast<const char*>(L.gi + gi_block(b0 / WG + gb / 3, L.gi_cols, gi_col0 + (t - ST * dt), dir * 3 + gb % 3)) + lane * 128);
             }
             __syncwarp();
             if (loads) tc::bulk_g2s_hint(dst0 + stage * GI_STAGE_BYTES, src0 + (int64_t)t * GI_BLK_FLOATS, GI_BLK_BYTES, gi_full(tile_l) + stage, tc::L2_EVICT_FIRST);
