@@ -1744,6 +1744,9 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
 #endif
 
     if (warp == 5) {
+        const uint8_t* prev_img = nullptr;
+        int64_t prev_wg = 0;
+        int prev_t0 = 0, prev_valid = 0;
         for (int64_t it = 0; heads_job(a, worker, n_workers, tiles_t, it, chunk, wg, t0); ++it) {
             const int valid = min(16, W - t0);
             if (a.progress != nullptr) {                     // both decoder directions must have stored these columns
@@ -1765,7 +1768,16 @@ __device__ __forceinline__ void heads_role(const HeadsArgs& a, uint8_t* smem, co
                 __syncwarp();
                 if ((lane >> 3) == part && cols > 0)
                     tc::bulk_g2s(a_img + part * PART_BYTES + d * SLICE_BYTES + q4 * 4 * YBLK, img + yimg_block(wg, d, part, t0 + 4 * q4, W), (uint32_t)(cols * YBLK), a_full + part);
+                // chunk-loop kernel: the PREVIOUS tile's part has been multiplied (a_empty above), so its copy out of global
+                // memory completed long ago, and this CTA was its only reader until the decoder overwrites the buffer two
+                // chunks later: L2 may drop the lines instead of writing them to DRAM (16 lines of 128 bytes per column block)
+                if (a.progress != nullptr && it > 0) {
+                    for (int dd = 0; dd < 2; ++dd)
+                        for (int l = lane; l < prev_valid * (YBLK / 128); l += 32)
+                            tc::discard_l2_line(prev_img + yimg_block(prev_wg, dd, part, prev_t0, W) + (int64_t)l * 128);
+                }
             }
+            prev_img = img; prev_wg = wg; prev_t0 = t0; prev_valid = valid;
         }
         HB_ROLE_REPORT(0);
     } else if (warp == 4) {
