@@ -209,6 +209,7 @@ struct ProjArgs {
     const unsigned long long* progress; unsigned long long epoch; int rec_n;   // encoder progress counters, [cta][dir]
     int n_chunks;                  // a chunk's columns count from chunk * W in the progress counters
     unsigned long long* tile_flags;   // [group][tile][decoder direction], PROJ_FLAGS_PER_TILE per chunk
+    unsigned long long* tile_reads;   // [group][tile]: gate-block CTAs that are done with the encoder output tile (6 per chunk), or nullptr
     long long* dbg;                   // -DHB_TIMELINE: worker 0 records when it finished each chunk
     ProjPixelArgs px;                 // px.ximg == nullptr: no pixel jobs
     int col_tiles;                    // tile mode: project only the first col_tiles column tiles (0 = all)
@@ -635,6 +636,22 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                         for (int k = 0; k < n_pending; ++k) tc::red_relaxed_gpu_add(pending[k], 1ull);
                     n_pending = 0;
                     HB_CHAIN(a.dbg, worker == 0 && blk == 0 && chunk == 2 && (warp & 3) == 0 && lane == 0 && !j.pixel && j.wg == 0 && j.t0 == 0, 5);
+                }
+            }
+            if (a.tile_reads != nullptr && !j.pixel && (warp & 3) == 0) {
+                // the sixth gate-block CTA to finish a tile knows that nobody reads the encoder's output columns of it again
+                // before the next chunk's encoder overwrites them: L2 may drop those lines (8 columns x 2 directions x hi, lo
+                // x 2 KB) instead of writing them to DRAM.  (This CTA's own copy of the tile left global memory before the MMAs
+                // ran; the other CTAs count only after their epilogue, too.)
+                unsigned long long before = 0;
+                if (lane == 0) before = atomicAdd(a.tile_reads + (j.wg * tiles_t + (j.t0 >> 3)), 1ull);
+                before = __shfl_sync(0xffffffffu, before, 0);
+                if ((before + 1) % 6 == 0) {
+                    for (int dd = 0; dd < 2; ++dd)
+                        for (int part = 0; part < 2; ++part) {
+                            const uint8_t* tile = in_base + j.wg * in_wg_stride + dd * in_dir_stride + part * in_part_stride + (int64_t)j.t0 * blk_bytes;
+                            for (int l = lane; l < j.valid * (blk_bytes / 128); l += 32) tc::discard_l2_line(tile + (int64_t)l * 128);
+                        }
                 }
             }
 #ifdef HB_TIMELINE
@@ -2470,7 +2487,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
     size_t n_groups = 0, flags_needed = 0;
     if (chunkloop) {
         n_groups = (size_t)plan.rec_ctas * (plan.tile / WG);       // window groups the recurrence CTAs cover (>= n_wg)
-        flags_needed = (size_t)4 * plan.rec_ctas + n_groups + n_groups * tiles8 * 2;
+        flags_needed = (size_t)4 * plan.rec_ctas + n_groups + n_groups * tiles8 * 2 + n_groups * tiles8;
         if (pixels_in_loop && flags_needed + n_groups * px_tiles * 2 > e->flags_capacity) pixels_in_loop = false;
         if (pixels_in_loop) flags_needed += n_groups * px_tiles * 2;
         const int64_t worker_tiles = (n_wg * tiles8 + plan.proj_workers - 1) / plan.proj_workers;    // tiles one projection worker owns
@@ -2595,6 +2612,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         unsigned long long* dec_prog = f;                 f += 2 * plan.rec_ctas;
         unsigned long long* heads_done = f;               f += n_groups;               // one per window group
         unsigned long long* tile_flags = f;               f += n_groups * tiles8 * 2;  // [group][tile][dec direction]
+        unsigned long long* tile_reads = f;               f += n_groups * tiles8;      // [group][tile]
         unsigned long long* px_flags = f;                                              // [group][image column tile][enc direction]
         RecArgs ra{};
         ra.layer[0] = layer_args(e->enc, ws.gi_enc, enc_cols, 0, J, ws.yimg1, ws.yimg1);
@@ -2613,6 +2631,7 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
         ra.phase_times = e->phase_times;
         ProjArgs pp = pd;
         pp.progress = enc_prog; pp.epoch = 0; pp.rec_n = plan.tile; pp.n_chunks = n_chunks; pp.tile_flags = tile_flags;
+        pp.tile_reads = tile_reads;
         pp.pair = 0;          // every CTA of the role picks its own job order (see the loader): no shared tiles
         pp.dbg = dbg_buf;
         pp.jobs = e->proj_jobs; pp.job_offsets = e->proj_job_offsets; 
