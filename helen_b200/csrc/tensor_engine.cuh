@@ -177,6 +177,7 @@ constexpr int PROJ_W_COL0 = 128;
 constexpr int PX_R = 8;                          // at most ceil(J / 8) + 1 new column tiles per chunk
 constexpr int PX_W_COL0 = 384;                   // TMEM columns of the encoder's W_ih block (after the decoder's 256)
 struct ProjPixelArgs {
+    int last;                      // 1: a chunk's pixel jobs are scheduled after its decoder tiles, 0: before
     const uint8_t* ximg; int64_t wg_stride; int blk_bytes, Kp;   // pixel operand image (no-swizzle, lbo 128)
     const uint32_t* w_tmem; const float* scale_row; const float* bias_row;
     float* gi; int cols, tiles;                  // gi image of all `cols` image columns (`tiles` column tiles)
@@ -393,7 +394,12 @@ __device__ __forceinline__ void projection_role(const ProjArgs& a, uint8_t* smem
                     }
                     __syncwarp();
                     int e = 0;
-                    if (px_next < n_px) {
+                    // pixel jobs (the NEXT chunk's encoder projection) wait for nothing.  Small batches take them after the
+                    // chunk's decoder tiles: written half a chunk before their first use instead of a chunk and a half, the gi
+                    // rows are still in L2 when the encoder reads them (ncu at B=256: DRAM reads of the launch 1.52 -> 0.89 GB,
+                    // same speed).  With fewer than 12 workers, or 16 windows per recurrence CTA, the role has no such slack
+                    // (B=320: -5 %, B=512: -3 %): there they go first, into the idle start of the chunk.
+                    if (a.px.last ? lo > hi : px_next < n_px) {
                         e = job_tab[px_next++];
                     } else {
 #ifdef HB_TIMELINE
@@ -2034,6 +2040,7 @@ struct TensorTuning {
     bool pixel_jobs = true;     // HB_NO_PIXEL_JOBS: project every image column before the chunk-loop kernel starts
     bool pingpong = true;       // HB_NO_PINGPONG: one window tile per recurrence CTA in the per-chunk kernels of large batches
     bool loop_pingpong = true;  // HB_NO_LOOP_PINGPONG: 16-window chunk-loop kernel with one 16-window tile per recurrence CTA instead of two 8-window tiles
+    bool pixels_last = true;    // HB_PIXELS_FIRST: pixel jobs before the chunk's decoder tiles also at 8 windows per recurrence CTA
     bool cooperative = true;    // HB_NO_COOPERATIVE: chunk-loop kernel launched without the cooperative attribute
     int gate_warps = 8;         // HB_GATE_WARPS = 8 | 16: gate warps of the chunk-loop kernel's recurrence role (4 or 2 windows per thread at 8-window
                                 // tiles).  Measured at B=256: 85.8 k windows/s with 8, 81.7 k with 16 (fewer warps share the per-step waits, TMEM loads,
@@ -2048,6 +2055,7 @@ struct TensorTuning {
         t.pixel_jobs = getenv("HB_NO_PIXEL_JOBS") == nullptr;
         t.pingpong = getenv("HB_NO_PINGPONG") == nullptr;
         t.loop_pingpong = getenv("HB_NO_LOOP_PINGPONG") == nullptr;
+        t.pixels_last = getenv("HB_PIXELS_FIRST") == nullptr;
         t.cooperative = getenv("HB_NO_COOPERATIVE") == nullptr;
         if (const char* v = getenv("HB_GATE_WARPS")) { if (atoi(v) == 8 || atoi(v) == 16) t.gate_warps = atoi(v); }
         if (const char* v = getenv("HB_WINDOWS_PER_CTA")) {
@@ -2640,6 +2648,9 @@ inline int tensor_engine_predict(TensorEngine* e, const uint8_t* images, int64_t
             pp.px.w_tmem = e->enc.wih_tmem; pp.px.scale_row = e->enc.scale_row; pp.px.bias_row = e->enc.bias_row;
             pp.px.gi = ws.gi_enc; pp.px.cols = enc_cols; pp.px.tiles = px_tiles; pp.px.col_step = J;
             pp.px.flags = px_flags; pp.px.wgs_of_worker = e->proj_px_wgs;
+            // (pixel jobs last only while the projection role has slack: measured at B=320, 10 workers: 101.1 k windows/s with
+            // them last, 106.9 k first)
+            pp.px.last = (plan.tile == 8 && plan.proj_workers >= 12 && e->tune.pixels_last) ? 1 : 0;
         }
         HeadsArgs hp = heads_base;
         hp.yimg = ws.yimg2[0]; hp.yimg_odd = ws.yimg2[1]; hp.col0 = 0; hp.n_chunks = n_chunks;

@@ -14,12 +14,13 @@ pytestmark = pytest.mark.gpu
 
 REPS = 120
 ENV_KEYS = ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8",
-            "HB_NO_PIXEL_JOBS", "HB_NO_PINGPONG", "HB_GATE_WARPS", "HB_NO_COOPERATIVE", "HB_NO_LOOP_PINGPONG")
+            "HB_NO_PIXEL_JOBS", "HB_NO_PINGPONG", "HB_GATE_WARPS", "HB_NO_COOPERATIVE", "HB_NO_LOOP_PINGPONG", "HB_PIXELS_FIRST")
 VARIANTS = {
     "product": {},
     "chunkloop_16_gate_warps": {"HB_GATE_WARPS": "16"},
     "chunkloop_tile16": {"HB_WINDOWS_PER_CTA": "16"},
     "chunkloop_tile16_one_tile": {"HB_WINDOWS_PER_CTA": "16", "HB_NO_LOOP_PINGPONG": "1"},
+    "chunkloop_pixel_jobs_first": {"HB_PIXELS_FIRST": "1"},
     "chunkloop_tile16_16_gate_warps": {"HB_WINDOWS_PER_CTA": "16", "HB_GATE_WARPS": "16"},
     "per_chunk_tile8": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "8"},
     "per_chunk_tile16_pingpong": {"HB_NO_CHUNKLOOP": "1", "HB_WINDOWS_PER_CTA": "16"},

@@ -45,6 +45,7 @@ VARIANTS = {
     "chunkloop_no_pixel_jobs": {"HB_NO_PIXEL_JOBS": "1"},
     "chunkloop_tile16_pixel_jobs": {"HB_WINDOWS_PER_CTA": "16"},
     "chunkloop_tile16_one_tile": {"HB_WINDOWS_PER_CTA": "16", "HB_NO_LOOP_PINGPONG": "1"},
+    "chunkloop_pixel_jobs_first": {"HB_PIXELS_FIRST": "1"},
     "chunkloop_tile16_one_tile_8_gate_warps": {"HB_WINDOWS_PER_CTA": "16", "HB_NO_LOOP_PINGPONG": "1", "HB_GATE_WARPS": "8"},
     "chunkloop_few_heads_workers": {"HB_HEADS_WORKERS": "2"},
     "chunkloop_16_gate_warps": {"HB_GATE_WARPS": "16"},
@@ -60,7 +61,7 @@ def test_kernel_variants_match_fp32_engine(variant, monkeypatch):
     environment when the handle is created) against the fp32 engine, same tolerance as above."""
     from helen_b200.predictor import WindowPredictor
     for k in ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8", "HB_NO_PIXEL_JOBS", "HB_NO_PINGPONG",
-              "HB_GATE_WARPS", "HB_NO_COOPERATIVE", "HB_NO_LOOP_PINGPONG"):
+              "HB_GATE_WARPS", "HB_NO_COOPERATIVE", "HB_NO_LOOP_PINGPONG", "HB_PIXELS_FIRST"):
         monkeypatch.delenv(k, raising=False)
     batch, seq, features = 45, 250, 10
     sd = random_state_dict(features, seed=5)

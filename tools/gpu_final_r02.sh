@@ -57,3 +57,8 @@ HB_LIB=$ST HB_DEBUG_TIMELINE=1 timeout 200 python bench.py $Q > /dev/null 2> gpu
 HB_LIB=$ST HB_DEBUG_TIMELINE=e timeout 200 python bench.py $Q > /dev/null 2> gpurun_out/timeline_steps_enc.err
 HB_LIB=$ST HB_DEBUG_TIMELINE=1 timeout 200 python bench.py $Q --batch 512 > /dev/null 2> gpurun_out/timeline_steps_dec_B512.err
 ls -la gpurun_out | grep -i "ncu-rep\|launches"
+for v in "A=1" "HB_PIXELS_FIRST=1"; do
+  env $v timeout 300 python bench.py --steps 20 --warmup 5 --batch 320 --no-cpu-baseline --no-parity --sustained-seconds 0 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print('B=320 $v: windows/s %.0f ms/step %.3f' % (d['value'], d['ms_per_step']))"
+done | tee gpurun_out/pixels_order_B320.txt
