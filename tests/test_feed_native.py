@@ -152,3 +152,33 @@ def test_prefetcher_passes_errors_on(tmp_path):
     data = BulkImageBatches(None, file_list=[path], batch_size=4, native=True, ring=5)
     with pytest.raises(ValueError, match="IMAGE SIZE ERROR"):
         list(ThreadPrefetcher(data, depth=2))
+
+
+def test_corrupted_files_do_not_crash_the_reader(tmp_path):
+    """The library parses files it did not write: every offset and length it reads from the file is checked against the
+    mapping, so damaged metadata must end in an error status, never in a fault.  300 files with random bytes of the
+    structure region overwritten (and some truncated) are read in a child process; it has to exit normally."""
+    import subprocess
+    import sys
+    good = str(tmp_path / "good.h5")
+    write_images(good, 12, 10)
+    data = bytearray(open(good, "rb").read())
+    rng = np.random.default_rng(2024)
+    meta_start = max(96, len(data) - 30000)                     # raw data comes first in files of this writer; the structure is the tail
+    paths = []
+    for k in range(300):
+        mutated = bytearray(data)
+        region = (0, 96) if k % 10 == 0 else (meta_start, len(data))
+        for _ in range(int(rng.integers(1, 6))):
+            at = int(rng.integers(region[0], region[1]))
+            mutated[at] = int(rng.integers(0, 256))
+        if k % 7 == 0:
+            mutated = mutated[:int(rng.integers(meta_start, len(data)))]
+        path = str(tmp_path / ("m%03d.h5" % k))
+        with open(path, "wb") as f:
+            f.write(mutated)
+        paths.append(path)
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    child = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "feed_fuzz_child.py")] + paths, capture_output=True, text=True, env=env, timeout=300)
+    assert child.returncode == 0, "reader crashed (exit %d)\n%s" % (child.returncode, child.stderr[-2000:])
+    assert "'ok'" in child.stdout
