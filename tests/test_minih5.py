@@ -200,3 +200,33 @@ def test_bulk_batches_equal_the_item_reader(tmp_path):
             assert torch.equal(images[i], ref[4][0]) and torch.equal(position[i], ref[5][0]) and filename[i] == ref[6][0]
             k += 1
     assert k == 16
+
+
+def test_open_predictions_reuses_the_reader_and_notices_rewrites(tmp_path, monkeypatch):
+    """The stitch opens a prediction file once per region (Stitch.py:214-245): with the package's own reader that is one
+    shared handle per process - and a file rewritten under the same name is read anew."""
+    from helen_b200 import DataStore as ds
+    monkeypatch.setenv("HELEN_B200_HDF5", "minih5")
+    ds.forget_packed_views()
+    path = str(tmp_path / "p.hdf")
+
+    def write(value):
+        store = ds.DataStore(path, mode="w", packed=False)
+        position = np.zeros((2, 1000, 3), np.int64)
+        store.write_predictions(["chr1", "chr1"], [0, 0], [1999, 1999], [0, 1], position, np.full((2, 1000), value), np.zeros((2, 1000)))
+        store.close()
+
+    write(1)
+    with ds.open_predictions(path) as a:
+        first = a
+        assert int(a["predictions/chr1/chr1-0-1999/1/bases"][()][5]) == 1
+    with ds.open_predictions(path) as b:
+        assert b is first                                   # not reopened, not closed by the first block
+        assert sorted(b["predictions"]["chr1"]["chr1-0-1999"].keys()) == ["0", "1", "contig_end", "contig_start"]
+    import os, time
+    time.sleep(0.01)
+    write(3)
+    os.utime(path, ns=(time.time_ns(), time.time_ns()))
+    with ds.open_predictions(path) as c:
+        assert c is not first and int(c["predictions/chr1/chr1-0-1999/0/bases"][()][5]) == 3
+    ds.forget_packed_views()
