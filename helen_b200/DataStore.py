@@ -251,9 +251,42 @@ def open_predictions(path):
     return view
 
 
+_region_readers = {}
+
+
+def region_reader(path):
+    """The native reader of a prediction file (include/helen_feed.h: hf_read_prediction_region), opened once per process
+    and file, or None: h5py is in use, the library is not built, HELEN_B200_NATIVE_READER=0, or the file is outside the
+    library's subset.  The stitch reads a region's rows through it in one call without the interpreter lock; a region it
+    cannot serve (a packed file, ...) raises _feed_native.Unsupported and the caller reads it through open_predictions."""
+    if os.environ.get("HELEN_B200_NATIVE_READER", "1") == "0" or hdf5.backend() != "minih5":
+        return None
+    try:
+        stamp = os.stat(path)
+        stamp = (stamp.st_mtime_ns, stamp.st_size)
+    except OSError:
+        return None
+    cached = _region_readers.get(path)
+    if cached is not None and cached[0] == stamp:
+        return cached[1]
+    reader = None
+    try:
+        from . import _feed_native
+        if os.path.exists(_feed_native.LIB_PATH):
+            reader = _feed_native.ImageFile(path)
+    except Exception:
+        reader = None
+    _region_readers[path] = (stamp, reader)
+    return reader
+
+
 def forget_packed_views():
     """Drops the per-process caches of open_predictions (tests rewrite files under the same name)."""
     _packed_views.clear()
     for _, shared in _shared_readers.values():
         shared._handle.close()
     _shared_readers.clear()
+    for _, reader in _region_readers.values():
+        if reader is not None:
+            reader.close()
+    _region_readers.clear()

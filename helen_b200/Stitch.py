@@ -11,7 +11,8 @@ import sys
 import numpy as np
 
 from . import _stitch_native as native
-from .DataStore import open_predictions
+from . import _feed_native
+from .DataStore import open_predictions, region_reader
 from .FileManager import FileManager
 from .options import StitchOptions
 from .TextColor import TextColor
@@ -155,6 +156,16 @@ class Stitch:
         name_sequence_tuples = list()
         for contig_name, file_name, chunk_name, contig_start, contig_end in small_chunk_keys:
             positions, bases, rles = [], [], []
+            native_reader = region_reader(file_name)
+            if native_reader is not None:
+                # the region's rows in one library call (no interpreter lock: the worker threads read in parallel)
+                try:
+                    rows = native_reader.read_prediction_region(contig, chunk_name)
+                    sequence = decode_region(*rows) if len(rows[1]) else ''
+                    name_sequence_tuples.append((contig, contig_start, contig_end, sequence))
+                    continue
+                except (_feed_native.Unsupported, IOError):
+                    pass                                              # a packed file, or one outside the library's subset
             with open_predictions(file_name) as hdf5_file:            # one open per region instead of one per image
                 if 'predictions' in hdf5_file:
                     region = hdf5_file['predictions'][contig][chunk_name]

@@ -12,7 +12,7 @@ import numpy as np
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhelen_feed.so")
 
-HF_ABI_VERSION = 1
+HF_ABI_VERSION = 2
 HF_OK, HF_UNSUPPORTED, HF_E_SIZE, HF_E_FORMAT, HF_E_ARGUMENT = 0, 1, 2, 3, 4
 CONTIG_STRIDE = 256
 
@@ -26,6 +26,7 @@ SIGNATURES = {
     "hf_image_features": (c_int, [c_void_p, c_int64, POINTER(c_int), c_char_p, c_int]),
     "hf_read_block": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_int, c_char_p, c_int]),
+    "hf_read_prediction_region": (c_int, [c_void_p, c_char_p, c_char_p, c_int64, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_char_p, c_int]),
 }
 
 _lib = None
@@ -135,3 +136,17 @@ class ImageFile(object):
             _raise(status, err.value.decode(errors="replace"), self.path)
         names = [bytes(row).split(b"\0", 1)[0].decode() for row in contigs]
         return names, starts, ends, chunk_ids, images, position
+
+    def read_prediction_region(self, contig, region, capacity_rows=8000):
+        """-> (position i64[rows, 3], bases u8[rows], rles u8[rows]) of predictions/<contig>/<region>, chunks in string order."""
+        err, total = ctypes.create_string_buffer(512), c_int64(0)
+        while True:
+            position = np.empty((capacity_rows, 3), np.int64)
+            bases, rles = np.empty(capacity_rows, np.uint8), np.empty(capacity_rows, np.uint8)
+            status = self._lib.hf_read_prediction_region(self._open_handle(), str(contig).encode(), str(region).encode(), capacity_rows,
+                                                         position.ctypes.data, bases.ctypes.data, rles.ctypes.data, ctypes.byref(total), err, len(err))
+            if status != HF_OK:
+                _raise(status, err.value.decode(errors="replace"), self.path)
+            if total.value <= capacity_rows:
+                return position[:total.value], bases[:total.value], rles[:total.value]
+            capacity_rows = total.value

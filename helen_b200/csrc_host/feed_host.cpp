@@ -11,6 +11,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -394,6 +395,107 @@ struct hf_file {
         fail(HF_E_FORMAT, path + ": global heap object " + std::to_string(index) + " not found");
     }
 
+    // ---- one member of a group by name, without listing the group ---------------------------------------------------
+    // Symbol-table groups keep their names sorted in a version-1 B-tree whose keys are local-heap offsets: key[i + 1] is the
+    // largest name below child i.  A contig's group of a prediction file has one member per region - millions for a genome.
+    bool find_member(uint64_t address, bool has_symtab, uint64_t btree, uint64_t heap, const std::string& name, uint64_t* out) const {
+        std::vector<Message> msgs;
+        messages(address, msgs);
+        bool compact = false;
+        for (const Message& m : msgs) {
+            if (m.type == 0x11 && m.size >= 16) {
+                has_symtab = true;
+                btree = uint(m.body, 8);
+                heap = uint(m.body + 8, 8);
+            } else if (m.type == 0x06 || m.type == 0x02) {
+                compact = true;
+            }
+        }
+        if (compact || !has_symtab) {                  // link messages: the group is small (or dense: links() says so)
+            std::vector<std::pair<std::string, uint64_t>> all;
+            links(address, has_symtab, btree, heap, all);
+            for (const auto& kv : all)
+                if (kv.first == name) { *out = kv.second; return true; }
+            return false;
+        }
+        const uint8_t* hh = at(heap, 32);
+        if (std::memcmp(hh, "HEAP", 4) != 0) fail(HF_E_FORMAT, path + ": local heap signature missing at " + std::to_string(heap));
+        const uint64_t heap_size = uint(hh + 8, 8);
+        const uint8_t* heap_data = at(uint(hh + 24, 8), heap_size);
+        auto compare = [&](uint64_t offset) {           // name <=> the heap string at `offset`
+            if (offset >= heap_size) fail(HF_E_FORMAT, path + ": link name outside the local heap");
+            const void* end = std::memchr(heap_data + offset, 0, heap_size - offset);
+            if (end == nullptr) fail(HF_E_FORMAT, path + ": unterminated link name");
+            const size_t len = static_cast<const uint8_t*>(end) - (heap_data + offset);
+            const int c = std::memcmp(name.data(), heap_data + offset, std::min(len, name.size()));
+            return c != 0 ? c : (name.size() < len ? -1 : (name.size() > len ? 1 : 0));
+        };
+        uint64_t node = btree;
+        for (int depth = 0; depth < 32; ++depth) {
+            const uint8_t* head = at(node, 24);
+            if (std::memcmp(head, "TREE", 4) != 0 || head[4] != 0) fail(HF_E_FORMAT, path + ": group B-tree node expected at " + std::to_string(node));
+            const int level = head[5];
+            const uint64_t used = uint(head + 6, 2);
+            const uint8_t* body = at(node + 24, (2 * used + 1) * 8);
+            uint64_t lo = 0, hi = used;                  // first child whose upper key is >= name
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) / 2;
+                if (compare(uint(body + (2 * mid + 2) * 8, 8)) <= 0) hi = mid; else lo = mid + 1;
+            }
+            if (lo == used) return false;
+            const uint64_t child = uint(body + (2 * lo + 1) * 8, 8);
+            if (level > 0) {
+                node = child;
+                continue;
+            }
+            const uint8_t* snod = at(child, 8);
+            if (std::memcmp(snod, "SNOD", 4) != 0) fail(HF_E_FORMAT, path + ": symbol table node expected at " + std::to_string(child));
+            const uint64_t count = uint(snod + 6, 2);
+            const uint8_t* entries = at(child + 8, count * 40);
+            for (uint64_t k = 0; k < count; ++k)
+                if (compare(uint(entries + k * 40, 8)) == 0) { *out = uint(entries + k * 40 + 8, 8); return true; }
+            return false;
+        }
+        fail(HF_E_FORMAT, path + ": group B-tree too deep");
+    }
+
+    // ---- one region of a prediction file: the rows of its chunks, chunk names in string order (Stitch.py:214-245) ----
+    int64_t read_region(const std::string& contig, const std::string& region, int64_t capacity, int64_t* position, uint8_t* bases, uint8_t* rles) const {
+        uint64_t address = 0;
+        if (!find_member(root_header, root_has_symtab, root_btree, root_heap, "predictions", &address)) fail(HF_UNSUPPORTED, path + ": no predictions group");
+        if (!find_member(address, false, 0, 0, contig, &address)) fail(HF_UNSUPPORTED, path + ": no contig " + contig);
+        if (!find_member(address, false, 0, 0, region, &address)) fail(HF_UNSUPPORTED, path + ": no region " + region);
+        std::vector<std::pair<std::string, uint64_t>> chunks, members;
+        links(address, false, 0, 0, chunks);
+        std::sort(chunks.begin(), chunks.end());
+        std::vector<Message> scratch;
+        int64_t total = 0;
+        for (const auto& chunk : chunks) {
+            if (chunk.first == "contig_start" || chunk.first == "contig_end") continue;
+            links(chunk.second, false, 0, 0, members);
+            DatasetInfo pos, b, r;
+            for (const auto& kv : members) {
+                if (kv.first == "position") pos = dataset_info(kv.second, scratch);
+                else if (kv.first == "bases") b = dataset_info(kv.second, scratch);
+                else if (kv.first == "rles") r = dataset_info(kv.second, scratch);
+            }
+            if (!pos.is_dataset || !b.is_dataset || !r.is_dataset || pos.type_class != 0 || b.type_class != 0 || r.type_class != 0)
+                fail(HF_UNSUPPORTED, path + ": chunk " + chunk.first + " of " + region + " is not in the prediction schema");
+            const int64_t rows = (int64_t)b.count();
+            if ((int64_t)r.count() != rows || (int64_t)pos.count() != rows * 3) fail(HF_UNSUPPORTED, path + ": ragged chunk " + chunk.first + " of " + region);
+            if (total + rows <= capacity) {
+                if (pos.type_size == 8) copy_out(pos, position + total * 3, (uint64_t)rows * 24);
+                else for (int64_t k = 0; k < rows * 3; ++k) position[total * 3 + k] = read_int(pos, (uint64_t)k);
+                if (b.type_size == 1) copy_out(b, bases + total, (uint64_t)rows);
+                else for (int64_t k = 0; k < rows; ++k) bases[total + k] = (uint8_t)read_int(b, (uint64_t)k);
+                if (r.type_size == 1) copy_out(r, rles + total, (uint64_t)rows);
+                else for (int64_t k = 0; k < rows; ++k) rles[total + k] = (uint8_t)read_int(r, (uint64_t)k);
+            }
+            total += rows;
+        }
+        return total;
+    }
+
     // ---- one image of a block --------------------------------------------------------------------------------------
     struct Scratch {
         std::vector<Message> msgs;
@@ -597,6 +699,16 @@ int hf_read_block(const hf_file* f, int64_t first, int64_t count, int seq_len, i
     for (std::thread& t : pool) t.join();
     if (status.load() != HF_OK) put_error(err, errlen, message);
     return status.load();
+}
+
+int hf_read_prediction_region(const hf_file* f, const char* contig, const char* region, int64_t capacity_rows, int64_t* position,
+                              uint8_t* bases, uint8_t* rles, int64_t* total_rows, char* err, int errlen) {
+    if (f == nullptr || contig == nullptr || region == nullptr || total_rows == nullptr || capacity_rows < 0 ||
+        (capacity_rows > 0 && (position == nullptr || bases == nullptr || rles == nullptr))) {
+        put_error(err, errlen, "hf_read_prediction_region: bad argument");
+        return HF_E_ARGUMENT;
+    }
+    return guarded(err, errlen, [&]() { *total_rows = f->read_region(contig, region, capacity_rows, position, bases, rles); });
 }
 
 }  // extern "C"

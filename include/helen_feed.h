@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HF_ABI_VERSION 1
+#define HF_ABI_VERSION 2
 
 enum hf_status {
     HF_OK = 0,
@@ -57,6 +57,15 @@ int hf_image_features(const hf_file *file, int64_t i, int *features, char *err, 
 int hf_read_block(const hf_file *file, int64_t first, int64_t count, int seq_len, int features,
                   uint8_t *images, int64_t *position, int64_t *contig_start, int64_t *contig_end, int64_t *chunk_id,
                   char *contigs, int contig_stride, int threads, char *err, int errlen);
+
+/* Prediction files, for the stitch (helen/modules/python/Stitch.py:214-245: per region, the position / bases / rles rows
+ * of all its chunks): the rows of predictions/<contig>/<region>/<chunk>/{position, bases, rles} of every chunk, chunks in
+ * string order of their names, back to back: position i64[rows, 3] (the file's uint32 widened), bases u8[rows], rles u8[rows].
+ * The region is found by searching the groups' B-trees, not by listing them (a contig has one member per region).
+ * *total_rows is always the region's row count; the arrays are filled only if capacity_rows >= *total_rows.
+ * HF_UNSUPPORTED: no such region in this file's `predictions` group (e.g. a packed file), or data outside the subset. */
+int hf_read_prediction_region(const hf_file *file, const char *contig, const char *region, int64_t capacity_rows,
+                              int64_t *position, uint8_t *bases, uint8_t *rles, int64_t *total_rows, char *err, int errlen);
 
 #ifdef __cplusplus
 }

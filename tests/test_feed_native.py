@@ -182,3 +182,75 @@ def test_corrupted_files_do_not_crash_the_reader(tmp_path):
     child = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "feed_fuzz_child.py")] + paths, capture_output=True, text=True, env=env, timeout=300)
     assert child.returncode == 0, "reader crashed (exit %d)\n%s" % (child.returncode, child.stderr[-2000:])
     assert "'ok'" in child.stdout
+
+
+def test_prediction_regions_through_the_library_equal_the_python_reader(tmp_path, monkeypatch):
+    """hf_read_prediction_region (the stitch's per-region read, Stitch.py:214-245) against the package's Python reader on a
+    real file: many regions (several B-tree levels to search), chunk names that sort as strings ("10" before "2"), the
+    uint32 wrap of padded positions, a repeated record; then the whole stitch with and without the library."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import stitch_inputs
+    import helen_b200.StitchInterface as iface
+    from helen_b200 import DataStore as ds
+    from helen_b200.Stitch import decode_region
+    monkeypatch.setenv("HELEN_B200_HDF5", "minih5")
+    ds.forget_packed_views()
+    records = []
+    for k in range(3):
+        records += stitch_inputs.prediction_records(seed=100 + k, regions=12, images_per_region=3 if k % 2 else 11, contig="chr%d" % k)
+    records.append(records[5])                                      # a repeated (region, chunk): the first one wins
+    path = str(tmp_path / "pred_0.hdf")
+    store = ds.DataStore(path, mode="w", packed=False)
+    for lo in range(0, len(records), 64):
+        batch = records[lo:lo + 64]
+        store.write_predictions([r[0] for r in batch], [r[1] for r in batch], [r[2] for r in batch], [r[3] for r in batch],
+                                np.stack([r[4] for r in batch]), np.stack([r[5] for r in batch]), np.stack([r[6] for r in batch]))
+    store.close()
+    native = _feed_native.ImageFile(path)
+    checked = 0
+    with hdf5.open_file(path, "r") as f:
+        for contig in f["predictions"].keys():
+            regions = f["predictions"][contig].keys()
+            for region_name in regions:
+                region = f["predictions"][contig][region_name]
+                chunks = sorted(set(region.keys()) - {"contig_start", "contig_end"})
+                want_p = np.concatenate([np.asarray(region[c]["position"][()], dtype=np.int64).reshape(-1, 3) for c in chunks])
+                want_b = np.concatenate([np.asarray(region[c]["bases"][()]).reshape(-1) for c in chunks])
+                want_r = np.concatenate([np.asarray(region[c]["rles"][()]).reshape(-1) for c in chunks])
+                got_p, got_b, got_r = native.read_prediction_region(contig, region_name, capacity_rows=1500)   # forces the retry with a larger buffer
+                assert np.array_equal(got_p, want_p) and np.array_equal(got_b, want_b) and np.array_equal(got_r, want_r)
+                assert decode_region(got_p, got_b, got_r) == decode_region(want_p, want_b, want_r)
+                checked += 1
+                if len(chunks) > 10:
+                    assert chunks.index("10") < chunks.index("2")
+    assert checked >= 36
+    for missing in (("chrNone", "x"), ("chr0", "chr0-1-2")):
+        with pytest.raises(_feed_native.Unsupported):
+            native.read_prediction_region(*missing)
+    native.close()
+    # a contig with thousands of regions: the region is found by searching a B-tree of several levels
+    big = str(tmp_path / "big_0.hdf")
+    store = ds.DataStore(big, mode="w", packed=False)
+    n = 3000
+    starts = (np.arange(n) * 7919) % 1000003 * 10
+    tiny_position = (np.arange(n * 15).reshape(n, 5, 3) % 4000000000).astype(np.int64)
+    tiny_position[:, 4] = -1
+    tiny_bases, tiny_rles = (np.arange(n * 5).reshape(n, 5) % 5), (np.arange(n * 5).reshape(n, 5) % 11)
+    store.write_predictions(["chrBig"] * n, starts, starts + 9, np.zeros(n, np.int64), tiny_position, tiny_bases, tiny_rles)
+    store.close()
+    native = _feed_native.ImageFile(big)
+    for i in list(range(0, n, 37)) + [n - 1]:
+        p_, b_, r_ = native.read_prediction_region("chrBig", "chrBig-%d-%d" % (starts[i], starts[i] + 9))
+        assert np.array_equal(p_, tiny_position[i].astype(np.uint32).astype(np.int64)) and np.array_equal(b_, tiny_bases[i]) and np.array_equal(r_, tiny_rles[i])
+    with pytest.raises(_feed_native.Unsupported):
+        native.read_prediction_region("chrBig", "chrBig-5-14")
+    native.close()
+    fasta = {}
+    for use in ("1", "0"):
+        monkeypatch.setenv("HELEN_B200_NATIVE_READER", use)
+        ds.forget_packed_views()
+        monkeypatch.setattr(iface, "get_file_paths_from_directory", lambda directory: [path])
+        fasta[use] = open(iface.perform_stitch(str(tmp_path), str(tmp_path / ("out" + use)), "p", 3)).read()
+    assert fasta["1"] == fasta["0"] and fasta["1"].count(">") == 3
+    ds.forget_packed_views()
