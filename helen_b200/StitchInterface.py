@@ -5,7 +5,8 @@ import sys
 from os import listdir
 from os.path import isfile, join
 
-from .DataStore import open_predictions
+from . import _feed_native
+from .DataStore import open_predictions, region_reader
 from .FileManager import FileManager
 from .Stitch import Stitch
 from .TextColor import TextColor
@@ -23,6 +24,20 @@ def perform_stitch(input_directory, output_path, output_prefix, threads):
     # one pass over the files: contig -> [(file, region key, start, end)] (the reference reopens every file per contig)
     regions_of = dict()
     for prediction_file in sorted(all_prediction_files):
+        native_reader = region_reader(prediction_file)
+        if native_reader is not None:
+            # the same listing in one library call per contig (a genome has millions of regions)
+            try:
+                listed = []
+                for contig in native_reader.list_predictions():
+                    names, starts, ends = native_reader.list_predictions(contig)
+                    order = sorted(range(len(names)), key=names.__getitem__)
+                    listed.append((contig, [(prediction_file, names[i], int(starts[i]), int(ends[i])) for i in order]))
+                for contig, entries in listed:
+                    regions_of.setdefault(contig, []).extend(entries)
+                continue
+            except (_feed_native.Unsupported, IOError):
+                pass                                                  # a packed file, or one outside the library's subset
         with open_predictions(prediction_file) as hdf5_file:
             if 'predictions' not in hdf5_file:
                 raise ValueError(TextColor.RED + "ERROR: INVALID HDF5 FILE, FILE DOES NOT CONTAIN predictions KEY.\n"

@@ -26,6 +26,7 @@ SIGNATURES = {
     "hf_image_features": (c_int, [c_void_p, c_int64, POINTER(c_int), c_char_p, c_int]),
     "hf_read_block": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_int, c_char_p, c_int]),
+    "hf_list_predictions": (c_int, [c_void_p, c_char_p, c_char_p, c_int64, c_void_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int64), c_char_p, c_int]),
     "hf_read_prediction_region": (c_int, [c_void_p, c_char_p, c_char_p, c_int64, c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_char_p, c_int]),
 }
 
@@ -150,3 +151,19 @@ class ImageFile(object):
             if total.value <= capacity_rows:
                 return position[:total.value], bases[:total.value], rles[:total.value]
             capacity_rows = total.value
+
+    def list_predictions(self, contig=None):
+        """contig None -> [contig names]; else ([region names], contig_start i64[n], contig_end i64[n]) in file order."""
+        count, need, err = c_int64(0), c_int64(0), ctypes.create_string_buffer(512)
+        key = None if contig is None else str(contig).encode()
+        status = self._lib.hf_list_predictions(self._open_handle(), key, None, 0, None, None, 0, ctypes.byref(count), ctypes.byref(need), err, len(err))
+        if status != HF_OK:
+            _raise(status, err.value.decode(errors="replace"), self.path)
+        names = ctypes.create_string_buffer(max(need.value, 1))
+        starts, ends = np.empty(count.value, np.int64), np.empty(count.value, np.int64)
+        status = self._lib.hf_list_predictions(self._open_handle(), key, names, need.value, starts.ctypes.data, ends.ctypes.data, count.value,
+                                               ctypes.byref(count), ctypes.byref(need), err, len(err))
+        if status != HF_OK:
+            _raise(status, err.value.decode(errors="replace"), self.path)
+        listed = [n.decode("utf-8") for n in names.raw[:need.value].split(b"\0")[:-1]]
+        return listed if contig is None else (listed, starts, ends)

@@ -701,6 +701,39 @@ int hf_read_block(const hf_file* f, int64_t first, int64_t count, int seq_len, i
     return status.load();
 }
 
+int hf_list_predictions(const hf_file* f, const char* contig, char* names, int64_t names_len, int64_t* starts, int64_t* ends, int64_t max_entries,
+                        int64_t* count, int64_t* names_needed, char* err, int errlen) {
+    if (f == nullptr || count == nullptr || names_needed == nullptr) {
+        put_error(err, errlen, "hf_list_predictions: null argument");
+        return HF_E_ARGUMENT;
+    }
+    return guarded(err, errlen, [&]() {
+        uint64_t address = 0;
+        if (!f->find_member(f->root_header, f->root_has_symtab, f->root_btree, f->root_heap, "predictions", &address))
+            fail(HF_UNSUPPORTED, f->path + ": no predictions group");
+        if (contig != nullptr && !f->find_member(address, false, 0, 0, contig, &address)) fail(HF_UNSUPPORTED, f->path + ": no contig " + contig);
+        std::vector<std::pair<std::string, uint64_t>> entries;
+        f->links(address, false, 0, 0, entries);
+        int64_t need = 0;
+        for (const auto& kv : entries) need += (int64_t)kv.first.size() + 1;
+        *count = (int64_t)entries.size();
+        *names_needed = need;
+        const bool fits = names != nullptr && names_len >= need && max_entries >= *count && (contig == nullptr || (starts != nullptr && ends != nullptr));
+        if (!fits) return;
+        char* p = names;
+        hf_file::Scratch scratch;
+        for (size_t i = 0; i < entries.size(); ++i) {
+            std::memcpy(p, entries[i].first.c_str(), entries[i].first.size() + 1);
+            p += entries[i].first.size() + 1;
+            if (contig != nullptr) {
+                f->links(entries[i].second, false, 0, 0, scratch.members);
+                starts[i] = f->scalar(scratch, "contig_start", entries[i].first);
+                ends[i] = f->scalar(scratch, "contig_end", entries[i].first);
+            }
+        }
+    });
+}
+
 int hf_read_prediction_region(const hf_file* f, const char* contig, const char* region, int64_t capacity_rows, int64_t* position,
                               uint8_t* bases, uint8_t* rles, int64_t* total_rows, char* err, int errlen) {
     if (f == nullptr || contig == nullptr || region == nullptr || total_rows == nullptr || capacity_rows < 0 ||

@@ -64,6 +64,11 @@ int hf_read_block(const hf_file *file, int64_t first, int64_t count, int seq_len
  * The region is found by searching the groups' B-trees, not by listing them (a contig has one member per region).
  * *total_rows is always the region's row count; the arrays are filled only if capacity_rows >= *total_rows.
  * HF_UNSUPPORTED: no such region in this file's `predictions` group (e.g. a packed file), or data outside the subset. */
+/* The first pass of the stitch (StitchInterface.py:52-66): contig == NULL lists the contigs of `predictions`; otherwise the
+ * regions of that contig in file order with their contig_start / contig_end datasets.  Names '\0'-terminated back to back;
+ * *count and *names_needed are always set, the arrays filled when they are large enough. */
+int hf_list_predictions(const hf_file *file, const char *contig, char *names, int64_t names_len, int64_t *starts, int64_t *ends,
+                        int64_t max_entries, int64_t *count, int64_t *names_needed, char *err, int errlen);
 int hf_read_prediction_region(const hf_file *file, const char *contig, const char *region, int64_t capacity_rows,
                               int64_t *position, uint8_t *bases, uint8_t *rles, int64_t *total_rows, char *err, int errlen);
 

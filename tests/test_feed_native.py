@@ -225,6 +225,15 @@ def test_prediction_regions_through_the_library_equal_the_python_reader(tmp_path
                 if len(chunks) > 10:
                     assert chunks.index("10") < chunks.index("2")
     assert checked >= 36
+    with hdf5.open_file(path, "r") as f:                              # the stitch's first pass (StitchInterface.py:52-66)
+        assert native.list_predictions() == list(f["predictions"].keys())
+        for contig in f["predictions"].keys():
+            names, starts, ends = native.list_predictions(contig)
+            assert names == list(f["predictions"][contig].keys())
+            assert starts.tolist() == [int(f["predictions"][contig][r]["contig_start"][()]) for r in names]
+            assert ends.tolist() == [int(f["predictions"][contig][r]["contig_end"][()]) for r in names]
+    with pytest.raises(_feed_native.Unsupported):
+        native.list_predictions("chrNone")
     for missing in (("chrNone", "x"), ("chr0", "chr0-1-2")):
         with pytest.raises(_feed_native.Unsupported):
             native.read_prediction_region(*missing)
