@@ -12,6 +12,16 @@ for path in sys.argv[1:]:
         handle.names()
         if n:
             handle.read_block(0, min(n, 8), 1000, 2)
+        try:                                           # prediction files: the stitch's listing and region reads
+            for contig in handle.list_predictions()[:3]:
+                names, _, _ = handle.list_predictions(contig)
+                for region in names[:4] + ["no-such-region"]:
+                    try:
+                        handle.read_prediction_region(contig, region)
+                    except _feed_native.Unsupported:
+                        pass
+        except _feed_native.Unsupported:
+            pass
         handle.close()
         outcomes["ok"] += 1
     except (IOError, ValueError, _feed_native.Unsupported):

@@ -178,6 +178,27 @@ def test_corrupted_files_do_not_crash_the_reader(tmp_path):
         with open(path, "wb") as f:
             f.write(mutated)
         paths.append(path)
+    # ... and a prediction file (the stitch's listing and per-region reads search and parse the same structures)
+    from helen_b200.DataStore import DataStore
+    pred = str(tmp_path / "pred.hdf")
+    store = DataStore(pred, mode="w", packed=False)
+    ids = np.arange(300)
+    store.write_predictions(["chr%d" % (i % 2) for i in ids], ids * 100, ids * 100 + 99, ids % 3, np.zeros((300, 20, 3), np.int64),
+                            np.ones((300, 20), np.uint8), np.ones((300, 20), np.uint8))
+    store.close()
+    data = bytearray(open(pred, "rb").read())
+    meta_start = 96 + 300 * 20 * (12 + 2)
+    for k in range(300):
+        mutated = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            mutated[int(rng.integers(meta_start, len(data)))] = int(rng.integers(0, 256))
+        if k % 9 == 0:
+            mutated = mutated[:int(rng.integers(meta_start, len(data)))]
+        path = str(tmp_path / ("p%03d.hdf" % k))
+        with open(path, "wb") as f:
+            f.write(mutated)
+        paths.append(path)
+    paths.append(pred)
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     child = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "feed_fuzz_child.py")] + paths, capture_output=True, text=True, env=env, timeout=300)
     assert child.returncode == 0, "reader crashed (exit %d)\n%s" % (child.returncode, child.stderr[-2000:])
