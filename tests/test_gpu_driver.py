@@ -44,3 +44,59 @@ def test_predict_driver_writes_reference_schema(tmp_path, monkeypatch):
             assert not diff.any() or (top2_margin(ref[prob][i])[diff] < 1e-5).all()
         assert chunk["position"][()].shape == (1000, 3)
     fake_h5.reset()
+
+
+def test_polish_genome_on_real_files(tmp_path, monkeypatch):
+    """`helen polish` end to end on files on disk (PolishInterface.py:49-91): MarginPolish-layout images -> call_consensus on
+    cuda:0 (native feed, prediction file through the native writer) -> stitch (native listing and region reads) -> FASTA.
+    The predictions are checked against the oracle, the FASTA against the stitch of the same prediction file through the
+    package's Python reader."""
+    import os
+    import helen_b200.StitchInterface as iface
+    from helen_b200 import DataStore as ds
+    from helen_b200.PolishInterface import polish_genome
+    monkeypatch.setenv("HELEN_B200_HDF5", "minih5")
+    monkeypatch.delenv("HELEN_B200_PACKED_PREDICTIONS", raising=False)
+    ds.forget_packed_views()
+    features = 90
+    sd = random_state_dict(features, seed=9)
+    model_path = str(tmp_path / "model.pkl")
+    torch.save({"model_state_dict": {"module." + k: v for k, v in sd.items()}, "model_optimizer": {},
+                "hidden_size": 128, "gru_layers": 1, "epochs": 1}, model_path)
+    image_dir = tmp_path / "images"
+    image_dir.mkdir()
+    rng = np.random.default_rng(3)
+    images, n = [], 24
+    with hdf5.open_file(str(image_dir / "imgs_0.h5"), "w") as f:
+        for i in range(n):
+            region, chunk = i // 3, i % 3                               # three overlapping images per 2000-base region
+            image = rng.integers(0, 256, (1000, features), dtype=np.uint8)
+            start = region * 1800 + chunk * 400
+            position = np.stack([np.arange(1000) + start, np.zeros(1000, np.int64), np.zeros(1000, np.int64)], 1)
+            base = "images/img_%03d/" % i
+            f[base + "contig"] = np.array([b"chrT"], dtype="S")
+            f[base + "contig_start"] = np.array([region * 1800])
+            f[base + "contig_end"] = np.array([region * 1800 + 1999])
+            f[base + "feature_chunk_idx"] = np.array([chunk])
+            f[base + "image"] = image
+            f[base + "position"] = position
+            images.append(image)
+    out_dir = str(tmp_path / "out")
+    prediction_dir = polish_genome(str(image_dir), model_path, 8, 0, 2, out_dir, "HELEN_prediction", True, None, 1)
+    files = [os.path.join(prediction_dir, p) for p in os.listdir(prediction_dir) if p.endswith("hdf")]
+    assert len(files) == 1
+    ref = predict_windows(OracleWeights.from_state_dict(sd), np.stack(images))
+    with hdf5.open_file(files[0], "r") as f:
+        for i in range(n):
+            region, chunk = i // 3, i % 3
+            got = f["predictions/chrT/chrT-%d-%d/%d/bases" % (region * 1800, region * 1800 + 1999, chunk)][()]
+            diff = got != ref["base_label"][i]
+            assert not diff.any() or (top2_margin(ref["base_prob"][i])[diff] < 1e-5).all()
+    fasta = open(os.path.join(out_dir, "HELEN_prediction.fa")).read()
+    assert fasta.startswith(">chrT\n") and len(fasta) > 1000
+    monkeypatch.setenv("HELEN_B200_NATIVE_READER", "0")
+    ds.forget_packed_views()
+    monkeypatch.setattr(iface, "get_file_paths_from_directory", lambda directory: files)
+    again = open(iface.perform_stitch(prediction_dir, str(tmp_path / "again"), "p", 2)).read()
+    assert again == fasta
+    ds.forget_packed_views()
