@@ -4,6 +4,8 @@ The roles of these kernels hand work to each other through mbarriers, counters i
 copies / tensor-memory stores; a missing wait shows up as a wrong result once in tens of launches, not in one.  (Two such
 faults were found this way in round 2, see upload_whh in helen_b200/csrc/tensor_engine.cuh.)  Every variant is launched
 REPS times on the same input and every launch must reproduce the fp32 engine within the stage tolerance."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -12,7 +14,7 @@ from oracle import random_state_dict
 
 pytestmark = pytest.mark.gpu
 
-REPS = 120
+REPS = int(os.environ.get("HB_STRESS_REPS", "120"))
 ENV_KEYS = ("HB_WINDOWS_PER_CTA", "HB_NO_STACK", "HB_NO_PAIR", "HB_NO_PDL", "HB_NO_CHUNKLOOP", "HB_HEADS_WORKERS", "HB_NO_LIVE8",
             "HB_NO_PIXEL_JOBS", "HB_NO_PINGPONG", "HB_GATE_WARPS", "HB_NO_COOPERATIVE", "HB_NO_LOOP_PINGPONG", "HB_PIXELS_FIRST")
 VARIANTS = {
